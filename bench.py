@@ -1,0 +1,392 @@
+#!/usr/bin/env python3
+"""Benchmark of the NSA hot path on B200 (BASELINE.json metric: "NSA prefill tok/s @S=64k, decode us/tok @S=4k;
+%roofline; 1/2/4/8 GPU").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the hot path (scoring -> selection -> three-branch attention -> gated combine,
+nsa_attention.py:1066-1398) over one batch of synthetic sequences: S=65536, m7c head dims (H=12, G=2, h=6,
+Dk=Dv=64, l=32, d=16, l_sel=64, n_sel=16, w=512), bf16, inputs resident in HBM.  The headline `value` is
+tokens/s of that step, whole job (all ranks; the path shards by batch with no collective => weak scaling).
+`e2e` is the same step through the public API with HOST (pinned) buffers, copies inside the timed region.
+`decode` carries the second half of the metric: us/token of one decode step at S=4096 (batch sharded).
+`roofline` is for the dominant kernel of the step; `cpu_baseline` is the oracle port timed on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+M7C = dict(H=12, G=2, h=6, Dk=64, Dv=64, l=32, d=16, l_sel=64, n_sel=16, w=512)
+METRIC = "NSA prefill tok/s @S=64k"
+
+
+# ------------------------------------------------------------------------------------------------------
+# algorithmic work, per sequence per layer
+# ------------------------------------------------------------------------------------------------------
+def num_cmp_at(t, l, d, S_cmp):
+    return 0 if t + 1 < l else min((t + 1 - l) // d + 1, S_cmp)
+
+
+def prefill_flops(S, c=M7C):
+    H, Dk, Dv, l, d = c["H"], c["Dk"], c["Dv"], c["l"], c["d"]
+    S_cmp = 0 if S < l else (S - l) // d + 1
+    sum_cmp = sum(num_cmp_at(t, l, d, S_cmp) for t in range(S))
+    sum_sel = sum(min(t + 1, c["n_sel"] * c["l_sel"]) for t in range(S))
+    sum_win = sum(min(t + 1, c["w"]) for t in range(S))
+    score = 2.0 * S * S_cmp * H * Dk                  # full-row scoring QK^T (reference-prefill parity)
+    cmp_pv = 2.0 * H * Dv * sum_cmp                   # cmp P.V (its QK^T is shared with scoring)
+    sel = 2.0 * H * (Dk + Dv) * sum_sel
+    win = 2.0 * H * (Dk + Dv) * sum_win
+    return dict(score=score, cmp_pv=cmp_pv, sel=sel, win=win, total=score + cmp_pv + sel + win,
+                sel_gather_bytes=2.0 * c["G"] * (Dk + Dv) * sum_sel)
+
+
+def decode_bytes_per_token(S, c=M7C):
+    """reads = num_cmp + n_sel*l_sel + min(w,S) (nsa_attention.py:634-638) x G x (Dk+Dv) x 2 B."""
+    ncmp = 0 if S < c["l"] else (S - c["l"]) // c["d"] + 1
+    reads = ncmp + c["n_sel"] * c["l_sel"] + min(c["w"], S)
+    return reads * c["G"] * (c["Dk"] + c["Dv"]) * 2, reads
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            j = json.load(f)
+        return dict(hbm=j["hbm_gbs"], tf_burst=j["bf16_tflops"], tf_sustained=j.get("bf16_tflops_sustained", j["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region (B200_PROFILING.md)
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.lines = []
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port on a bounded sample of the same workload
+# ------------------------------------------------------------------------------------------------------
+def cpu_prefill_sample(S, rows, seed=0, budget_s=25.0):
+    """Time the oracle's hot path for `rows` consecutive query rows in the middle of an S-token sequence (B=1) against
+    the full caches.  Returns (tok_per_s, cores, sample description)."""
+    from oracle import nsa_oracle as O
+    c = M7C
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(seed)
+    S_cmp = O.num_cmp_blocks(S, c["l"], c["d"])
+    bf = lambda *s: torch.randn(*s, generator=g).bfloat16().float()
+    t0 = S // 2
+    Q = bf(1, rows, c["G"], c["h"], c["Dk"])
+    K_sel, V_sel, K_win, V_win = bf(1, c["G"], S, c["Dk"]), bf(1, c["G"], S, c["Dv"]), bf(1, c["G"], S, c["Dk"]), bf(1, c["G"], S, c["Dv"])
+    K_cmp, V_cmp = bf(1, c["G"], S_cmp, c["Dk"]), bf(1, c["G"], S_cmp, c["Dv"])
+    hid = c["Dk"] // 2
+    gate = (torch.randn(hid, c["Dk"], generator=g) * 0.1, torch.zeros(hid), torch.randn(3, hid, generator=g) * 0.1, torch.zeros(3))
+    kw = dict(l=c["l"], d=c["d"], l_sel=c["l_sel"], n_sel=c["n_sel"], w=c["w"], t0=t0, S_total=S)
+    with torch.no_grad():
+        O.prefill_core(Q[:, :4], K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, gate, **kw)  # warm-up
+        n, el = 0, 0.0
+        while True:
+            t = time.perf_counter()
+            O.prefill_core(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, gate, **kw)
+            el += time.perf_counter() - t
+            n += 1
+            if el > budget_s or n >= 3:
+                break
+    return rows * n / el, cores, f"{rows} query rows at t0={t0} of one S={S} sequence (B=1), full K/V caches, {n} repeats, fp32 oracle"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference cannot travel to the GPU box)
+    on the host cores, same metric and config.  Rank 0 only."""
+    if rank != 0:
+        return
+    per_step = []
+    rows = args.cpu_rows
+    for i in range(args.warmup + args.steps):
+        v, cores, sample = cpu_prefill_sample(args.S, rows, seed=i, budget_s=0.0)
+        if i >= args.warmup:
+            per_step.append(v)
+    val = sum(per_step) / len(per_step)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "tok/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * rows / val, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "cpu_baseline": {"value": val, "unit": "tok/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    return {"workload": f"NSA hot path prefill S={args.S}, m7c head dims (H=12,G=2,h=6,Dk=Dv=64,l=32,d=16,l_sel=64,n_sel=16,w=512), "
+                        f"B={args.B} sequence(s) per GPU, one layer", "S": args.S, "batch_per_gpu": args.B, "global_batch": args.B * world,
+            "selection": "batched-prefill rule, full-row p_cmp normaliser (reference prefill parity)",
+            "l2": "inputs+outputs exceed the 126 MB L2 (no flush needed)", "parallelism": f"batch-sharded x{world}, no collective"}
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def make_inputs(B, S, dev, seed):
+    c = M7C
+    g = torch.Generator(device=dev).manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    S_cmp = 0 if S < c["l"] else (S - c["l"]) // c["d"] + 1
+    t = dict(Q=r(B, S, c["G"], c["h"], c["Dk"]), K_sel=r(B, c["G"], S, c["Dk"]), V_sel=r(B, c["G"], S, c["Dv"]),
+             K_win=r(B, c["G"], S, c["Dk"]), V_win=r(B, c["G"], S, c["Dv"]), K_cmp=r(B, c["G"], S_cmp, c["Dk"]),
+             V_cmp=r(B, c["G"], S_cmp, c["Dv"]))
+    hid = c["Dk"] // 2
+    gate = (torch.randn(hid, c["Dk"], generator=g, device=dev) * 0.1, torch.zeros(hid, device=dev),
+            torch.randn(3, hid, generator=g, device=dev) * 0.1, torch.zeros(3, device=dev))
+    return t, gate
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--S", type=int, default=65536)
+    ap.add_argument("--B", type=int, default=1, help="sequences per GPU in the prefill step")
+    ap.add_argument("--decode-S", type=int, default=4096)
+    ap.add_argument("--decode-B", type=int, default=512, help="sequences per GPU in the decode step")
+    ap.add_argument("--cpu-rows", type=int, default=64)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-decode", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch.distributed as dist
+    from nsa_vibe_b200 import _lib, ops
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    c = M7C
+    cfg = ops.NSAConfig(l=c["l"], d=c["d"], l_sel=c["l_sel"], n_sel=c["n_sel"], w=c["w"])
+    S, B = args.S, args.B
+    inp, gate = make_inputs(B, S, dev, seed=1234 + rank)
+
+    def step(t):
+        ranges = ops.score_select(t["Q"], t["K_cmp"], cfg, mode=0)
+        O, _, _ = ops.prefill_core(t["Q"], t["K_sel"], t["V_sel"], t["K_win"], t["V_win"], t["K_cmp"], t["V_cmp"], gate, cfg,
+                                   sel_mode=0, ranges=ranges)
+        return O
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step(inp)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+        n0 = lib.nsa_kernel_launches()
+        e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_start.record()
+        for i in range(args.steps):
+            ev[i][0].record()
+            ranges = ops.score_select(inp["Q"], inp["K_cmp"], cfg, mode=0)
+            ev[i][1].record()
+            ops.prefill_core(inp["Q"], inp["K_sel"], inp["V_sel"], inp["K_win"], inp["V_win"], inp["K_cmp"], inp["V_cmp"], gate,
+                             cfg, sel_mode=0, ranges=ranges)
+            ev[i][2].record()
+        e_end.record()
+        barrier()
+        launches = lib.nsa_kernel_launches() - n0
+        clocks = sampler.stop() if rank == 0 else None
+        ms_total = e_start.elapsed_time(e_end)
+        ms_score = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+        ms_attn = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+        tt = torch.tensor([ms_total], device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+        ms_step = ms_total / args.steps
+        value = world * B * S / (ms_step * 1e-3)
+
+        # ---- e2e: host buffers in, host result out, copies inside the timed region ------------------------
+        host = {k: v.cpu().pin_memory() for k, v in inp.items()}
+        o_host = torch.empty((B, S, c["G"], c["h"], c["Dv"]), dtype=torch.bfloat16).pin_memory()
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        d2h = o_host.numel() * o_host.element_size()
+
+        def e2e_step():
+            d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            o_host.copy_(step(d), non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_e2e = max(2, min(args.steps, 5))
+        s2.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e2.record()
+        barrier()
+        t2 = torch.tensor([s2.elapsed_time(e2)], device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e_val = world * B * S / (float(t2.item()) / n_e2e * 1e-3)
+        del host, o_host
+
+        # ---- decode @S=4096 -------------------------------------------------------------------------------
+        decode = None
+        if not args.no_decode:
+            decode = bench_decode(args, ops, cfg, dev, rank, world, barrier)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel -------------------------------------------------------------------
+    pk = measured_peaks()
+    fl = prefill_flops(S)
+    if ms_attn >= ms_score:
+        kname = "nsa_prefill_fwd (cmp + sel + win attention, gate, combine)"
+        k_flops, k_ms = B * (fl["cmp_pv"] + fl["sel"] + fl["win"]), ms_attn
+    else:
+        kname = "nsa_score_select (p_cmp softmax, Eq.9/10, top-n, ranges)"
+        k_flops, k_ms = B * fl["score"], ms_score
+    achieved = k_flops / (k_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
+                "traffic": None, "kernel": kname, "kernel_ms": k_ms, "peak_source": pk["src"] + " (bf16 sustained)",
+                "step_tflops": B * fl["total"] / (ms_step * 1e-3) / 1e12, "ms_score_select": ms_score, "ms_prefill_fwd": ms_attn,
+                "algorithmic_gflop_per_seq": {k: v / 1e9 for k, v in fl.items() if k != "sel_gather_bytes"},
+                "sel_gather_GBps": B * fl["sel_gather_bytes"] / (ms_attn * 1e-3) / 1e9}
+    cpu = None
+    if not args.no_cpu:
+        v, cores, sample = cpu_prefill_sample(S, args.cpu_rows)
+        cpu = {"value": v, "unit": "tok/s", "cores": cores, "kind": "port", "sample": sample}
+    line = {"metric": METRIC, "value": value, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "tok/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "decode": decode}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_decode(args, ops, cfg, dev, rank, world, barrier):
+    """us/token of one decode step at context S (caches resident, pre-allocated): score the emitted compressed keys,
+    select, attend over cmp + selected + window, gate, combine -- for decode_B sequences per GPU."""
+    import torch.distributed as dist
+    c = M7C
+    S, Bd = args.decode_S, args.decode_B
+    cap = S + 64
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    r = lambda *s: torch.randn(*s, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    K_sel, V_sel, K_win, V_win = r(Bd, c["G"], cap, c["Dk"]), r(Bd, c["G"], cap, c["Dv"]), r(Bd, c["G"], cap, c["Dk"]), r(Bd, c["G"], cap, c["Dv"])
+    S_cmp = (S - c["l"]) // c["d"] + 1
+    K_cmp, V_cmp = r(Bd, c["G"], S_cmp + 8, c["Dk"]), r(Bd, c["G"], S_cmp + 8, c["Dv"])
+    q = r(Bd, 1, c["G"], c["h"], c["Dk"])
+    hid = c["Dk"] // 2
+    gate = (torch.randn(hid, c["Dk"], generator=g, device=dev) * 0.1, torch.zeros(hid, device=dev),
+            torch.randn(3, hid, generator=g, device=dev) * 0.1, torch.zeros(3, device=dev))
+    gate_cache = ops._gate_struct(gate, dev)
+    out = torch.empty((Bd, 1, c["G"], c["h"], c["Dv"]), dtype=torch.bfloat16, device=dev)
+    rg = torch.empty((Bd, c["G"], c["n_sel"], 2), dtype=torch.int32, device=dev)
+
+    def dstep():
+        ops.decode_core(q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, gate, cfg, t=S - 1, S_sel_kv=S, S_win_kv=S, win_off=0,
+                        S_cmp=S_cmp, ranges_out=rg, out=out, gate_cache=gate_cache)
+
+    for _ in range(3):
+        dstep()
+    barrier()
+    n = 20
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(n):
+        dstep()
+    e.record()
+    barrier()
+    tt = torch.tensor([s.elapsed_time(e) / n], device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    byts, reads = decode_bytes_per_token(S)
+    pk = measured_peaks()
+    ach = Bd * byts / (ms * 1e-3) / 1e9
+    return {"metric": "NSA decode us/tok @S=4k", "value": ms * 1e3 / (Bd * world), "unit": "us/token (step latency / global batch)",
+            "S": S, "batch_per_gpu": Bd, "ms_per_step": ms, "tokens_per_s": world * Bd / (ms * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                         "algorithmic_bytes_per_token": byts, "reads_per_token": reads, "peak_source": pk["src"]}}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,146 @@
+/*
+ * nsa_b200.h -- C ABI of the B200-native NSA hot path (libnsa_b200.so).
+ *
+ * Drop-in boundary for seconds-0/nsa-vibe's attention math.  Every entry point
+ *  - takes raw DEVICE pointers, plain ints/floats and a cudaStream_t passed as void*,
+ *  - allocates nothing, never synchronises the host, is safe to call from several host
+ *    threads on different streams,
+ *  - returns 0 on success or a negative NSA_ERR_* code (never throws); nsa_last_error()
+ *    gives the text of the last failure on the calling thread.
+ * The caller owns all memory, including the workspaces sized by nsa_workspace_bytes().
+ *
+ * Tensor layouts (contiguous, row-major; "cap" = allocated token rows per (b,g) slab, so
+ * pre-allocated caches can be passed without copies):
+ *   Q      [B, S, G, h, Dk]      query rows, RoPE already applied      (nsa_attention.py:998-1009)
+ *   K_*    [B, G, cap, Dk]       per-branch key caches  (NSA_KV, nsa/cache/kv_cache.py:8-26)
+ *   V_*    [B, G, cap, Dv]
+ *   O      [B, S, G, h, Dv]      what the reference hands to self.out   (nsa_attention.py:1401)
+ *   ranges [B, S, G, K, 2] int32 [start,end) token ranges, [0,0] padded (selection_scorer.py:434-605)
+ *   p_grp  [B, S, G, S_sel] fp32 Eq.10 group scores                     (nsa_attention.py:1091)
+ *   gates  [B, S, G, 3] fp32     order (cmp, sel, win)                  (nsa_attention.py:1393-1396)
+ *   lse    [3, B, S, G, h] fp32  natural-log softmax normalisers per branch (cmp, sel, win)
+ * Row s of Q sits at absolute token position t = t0 + s.
+ */
+#ifndef NSA_B200_H_
+#define NSA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSA_OK 0
+#define NSA_ERR_INVALID_ARG (-1)   /* shape/dtype/alignment not supported: the wrapper raises */
+#define NSA_ERR_CUDA (-2)          /* a CUDA runtime call or launch failed */
+#define NSA_ERR_UNSUPPORTED (-3)   /* valid request with no kernel for it (no CPU fallback exists) */
+
+enum { NSA_F32 = 0, NSA_BF16 = 1, NSA_F16 = 2 };                 /* element type of Q/K/V/O */
+enum { NSA_NORM_FULL_ROW = 0, NSA_NORM_CAUSAL = 1 };              /* p_cmp normaliser */
+enum { NSA_GATE_MLP = 0, NSA_GATE_UNIFORM = 1, NSA_GATE_CMP = 2, NSA_GATE_SEL = 3, NSA_GATE_WIN = 4 };
+enum { NSA_IMPL_AUTO = 0, NSA_IMPL_SIMT = 1, NSA_IMPL_TC = 2 };   /* kernel family (both sm_100a CUDA) */
+
+/* Geometry shared by the attention entry points. */
+typedef struct nsa_dims {
+  int32_t B, S, G, h, Dk, Dv;
+  int32_t l, d, l_sel, n_sel, w;      /* NSA block parameters (d | l and d | l_sel) */
+  int32_t t0;                         /* absolute position of query row 0 */
+  int32_t S_sel_kv, cap_sel;          /* tokens present / rows allocated in K_sel,V_sel */
+  int32_t S_win_kv, cap_win, win_off; /* rows present / allocated in K_win,V_win; absolute position of row 0 */
+  int32_t S_cmp, cap_cmp;             /* compressed tokens present / rows allocated */
+  int32_t n_ranges;                   /* K: columns of the ranges tensor */
+  int32_t dtype;                      /* NSA_F32 | NSA_BF16 | NSA_F16 */
+  int32_t gate_mode;                  /* NSA_GATE_* (NSA_FORCE_BRANCH / NSA_FORCE_UNIFORM_GATE) */
+  int32_t gate_hidden;                /* rows of fc1 */
+  int32_t norm_mode;                  /* NSA_NORM_* for the scorer */
+  int32_t impl;                       /* NSA_IMPL_*; AUTO picks tcgen05 kernels when the shape allows */
+  float   gate_tau;                   /* gate temperature */
+  float   scale;                      /* softmax scale, 1/sqrt(Dk) */
+} nsa_dims_t;
+
+/* GateMLP parameters (nsa_attention.py:32-41), fp32, row-major like nn.Linear.weight. */
+typedef struct nsa_gate_params {
+  const float* fc1_w;  /* [hidden, Dk] */
+  const float* fc1_b;  /* [hidden] */
+  const float* fc2_w;  /* [3, hidden] */
+  const float* fc2_b;  /* [3] */
+} nsa_gate_params_t;
+
+const char* nsa_version(void);
+const char* nsa_last_error(void);
+/* Number of kernels this process has launched through this library (bench.py reports it as gpu_launches). */
+int64_t nsa_kernel_launches(void);
+
+/* ---- (2) selection: p_grp -> ranges, bit-exact vs the reference ------------------------- */
+/* Replaces select_topn_ranges_batched + convert_indices_to_ranges_batched_v2
+ * (nsa/core/selection_scorer.py:255-362, :434-605).  S_total is the S argument of the reference
+ * (decides the forced-column count); rows are t = t0 .. t0+S-1.  K must be
+ * nsa_prefill_range_cols(S_total, l_sel, n_sel). */
+int nsa_prefill_range_cols(int S_total, int l_sel, int n_sel);
+int nsa_select_ranges_prefill(const float* p_grp, int B, int S, int G, int S_sel, int l_sel, int n_sel,
+                              int S_total, int t0, int K, int32_t* ranges, void* stream);
+/* Replaces select_topn_ranges (selection_scorer.py:124-249): p_grp [B,G,S_sel], one position t,
+ * ranges [B,G,n_sel,2].  Rows the reference leaves as end<=start garbage are written as [0,0]. */
+int nsa_select_ranges_decode(const float* p_grp, int B, int G, int S_sel, int l_sel, int n_sel, int t,
+                             int32_t* ranges, void* stream);
+
+/* ---- (1) scoring: Q, K_cmp -> p_grp  (compute_pcmp_all + map_pcmp_to_pslc_batched + sum over h;
+ * selection_scorer.py:42-61, :89-116, nsa_attention.py:1091).  p_grp [B,S,G,S_sel] fp32. */
+int nsa_score(const nsa_dims_t* dm, const void* Q, const void* K_cmp, int S_sel, float* p_grp, void* stream);
+/* Fused scoring + selection: nothing but the ranges leaves the SM.  mode 0 = prefill rule, 1 = decode rule.
+ * workspace: nsa_workspace_bytes(dm, NSA_WS_SCORE_SELECT). */
+int nsa_score_select(const nsa_dims_t* dm, const void* Q, const void* K_cmp, int S_sel, int S_total, int mode,
+                     int32_t* ranges, void* workspace, void* stream);
+
+/* ---- (3)(4) branch attention.  branch: 0 = cmp, 1 = sel, 2 = win.
+ * Replace grouped_selection_attention* / selection_attention_{triton,cuda} (attention_kernels.py:181-772,
+ * kernels/triton_sel_kernel, kernels/cuda_sel_kernel/sel_cuda.cpp:28-73), sliding_window_attention
+ * (attention_kernels.py:146-178) and batched_causal_attention_compressed (:106-143) with softmax over
+ * every allowed key.  O_b [B,S,G,h,Dv] in dm->dtype, lse_b [B,S,G,h] fp32 (either may be NULL). */
+int nsa_branch_attn_fwd(const nsa_dims_t* dm, int branch, const void* Q, const void* K, const void* V,
+                        const int32_t* ranges, void* O_b, float* lse_b, void* stream);
+/* Analytical backward of one branch (replaces _selection_attention_backward,
+ * kernels/triton_sel_kernel/__init__.py:163-231, without its first-key-only line).
+ * dO_b [B,S,G,h,Dv] in dm->dtype, O_b as saved, dQ/dK/dV fp32 accumulators (+=, caller zeroes). */
+int nsa_branch_attn_bwd(const nsa_dims_t* dm, int branch, const void* Q, const void* K, const void* V,
+                        const int32_t* ranges, const void* O_b, const float* lse_b, const void* dO_b,
+                        float* dQ, float* dK, float* dV, void* stream);
+
+/* ---- (4) gate: GateMLP forward / backward (nsa_attention.py:32-82) on q_gp = mean_h(Q). */
+int nsa_gate_fwd(const nsa_dims_t* dm, const void* Q, const nsa_gate_params_t* gp, float* gates, void* stream);
+/* dgates [B,S,G,3] -> dQ (+= dq_gp / h per head, fp32) and fp32 parameter gradients (+=). */
+int nsa_gate_bwd(const nsa_dims_t* dm, const void* Q, const nsa_gate_params_t* gp, const float* dgates,
+                 float* dQ, float* d_fc1_w, float* d_fc1_b, float* d_fc2_w, float* d_fc2_b, void* stream);
+
+/* ---- fused hot path ------------------------------------------------------------------------
+ * nsa_prefill_fwd: the three branches + gate + combine in one pass; branch outputs stay on chip
+ * unless O_branches (3 x [B,S,G,h,Dv], dm->dtype) is non-NULL (needed only to run backward).
+ * Replaces nsa_attention.py:1137-1398. */
+int nsa_prefill_fwd(const nsa_dims_t* dm, const void* Q,
+                    const void* K_sel, const void* V_sel, const void* K_win, const void* V_win,
+                    const void* K_cmp, const void* V_cmp, const int32_t* ranges,
+                    const nsa_gate_params_t* gp, void* O, float* lse, float* gates, void* O_branches,
+                    void* stream);
+/* Backward of nsa_prefill_fwd.  dQ [B,S,G,h,Dk], dK_x/dV_x like their caches but fp32 (+=, caller
+ * zeroes), dgates [B,S,G,3] fp32 (written). */
+int nsa_prefill_bwd(const nsa_dims_t* dm, const void* Q,
+                    const void* K_sel, const void* V_sel, const void* K_win, const void* V_win,
+                    const void* K_cmp, const void* V_cmp, const int32_t* ranges,
+                    const void* O_branches, const float* lse, const float* gates, const void* dO,
+                    float* dQ, float* dK_sel, float* dV_sel, float* dK_win, float* dV_win,
+                    float* dK_cmp, float* dV_cmp, float* dgates, void* stream);
+/* nsa_decode_fwd: one decode step after the caches were appended (S must be 1; t = t0).  Scores the
+ * emitted compressed keys, selects with the decode rule, attends over the three branches, gates and
+ * combines (nsa_attention.py:648-971).  ranges_out [B,G,n_sel,2] may be NULL. */
+int nsa_decode_fwd(const nsa_dims_t* dm, const void* Q,
+                   const void* K_sel, const void* V_sel, const void* K_win, const void* V_win,
+                   const void* K_cmp, const void* V_cmp, const nsa_gate_params_t* gp,
+                   void* O, int32_t* ranges_out, void* workspace, void* stream);
+
+enum { NSA_WS_SCORE_SELECT = 0, NSA_WS_DECODE = 1, NSA_WS_PREFILL = 2 };
+int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSA_B200_H_ */

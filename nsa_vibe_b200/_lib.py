@@ -1,0 +1,88 @@
+"""ctypes binding of libnsa_b200.so -- the C ABI declared in include/nsa_b200.h.
+
+There is deliberately no fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("NSA_B200_LIB", os.path.join(_HERE, "lib", "libnsa_b200.so"))
+
+NSA_F32, NSA_BF16, NSA_F16 = 0, 1, 2
+NORM_FULL_ROW, NORM_CAUSAL = 0, 1
+GATE_MLP, GATE_UNIFORM, GATE_CMP, GATE_SEL, GATE_WIN = 0, 1, 2, 3, 4
+IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+WS_SCORE_SELECT, WS_DECODE, WS_PREFILL = 0, 1, 2
+
+
+class Dims(C.Structure):
+    """struct nsa_dims (include/nsa_b200.h)."""
+
+    _fields_ = [(n, C.c_int32) for n in (
+        "B", "S", "G", "h", "Dk", "Dv", "l", "d", "l_sel", "n_sel", "w", "t0",
+        "S_sel_kv", "cap_sel", "S_win_kv", "cap_win", "win_off", "S_cmp", "cap_cmp",
+        "n_ranges", "dtype", "gate_mode", "gate_hidden", "norm_mode", "impl")] + [
+        ("gate_tau", C.c_float), ("scale", C.c_float)]
+
+
+class GateParams(C.Structure):
+    """struct nsa_gate_params (include/nsa_b200.h)."""
+
+    _fields_ = [("fc1_w", C.c_void_p), ("fc1_b", C.c_void_p), ("fc2_w", C.c_void_p), ("fc2_b", C.c_void_p)]
+
+
+_P, _I, _I64 = C.c_void_p, C.c_int, C.c_int64
+_DP, _GP = C.POINTER(Dims), C.POINTER(GateParams)
+
+# name -> (restype, argtypes); must list every symbol include/nsa_b200.h declares
+SIGNATURES = {
+    "nsa_version": (C.c_char_p, []),
+    "nsa_last_error": (C.c_char_p, []),
+    "nsa_kernel_launches": (_I64, []),
+    "nsa_prefill_range_cols": (_I, [_I, _I, _I]),
+    "nsa_select_ranges_prefill": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "nsa_select_ranges_decode": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "nsa_score": (_I, [_DP, _P, _P, _I, _P, _P]),
+    "nsa_score_select": (_I, [_DP, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "nsa_branch_attn_fwd": (_I, [_DP, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "nsa_branch_attn_bwd": (_I, [_DP, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "nsa_gate_fwd": (_I, [_DP, _P, _GP, _P, _P]),
+    "nsa_gate_bwd": (_I, [_DP, _P, _GP, _P, _P, _P, _P, _P, _P, _P]),
+    "nsa_prefill_fwd": (_I, [_DP] + [_P] * 8 + [_GP] + [_P] * 5),
+    "nsa_prefill_bwd": (_I, [_DP] + [_P] * 21),
+    "nsa_decode_fwd": (_I, [_DP] + [_P] * 7 + [_GP] + [_P] * 4),
+    "nsa_workspace_bytes": (_I64, [_DP, _I]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load the shared library (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"libnsa_b200.so not found at {LIB_PATH}: build it with `python -m nsa_vibe_b200.build` "
+                "(there is no CPU or PyTorch fallback for the NSA hot path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError here means header and library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().nsa_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,159 @@
+"""NSA_KV -- the reference's per-branch cache container (nsa/cache/kv_cache.py:8-65) with the same fields,
+shapes and update methods, but appends go into pre-allocated slabs instead of `torch.cat` per token
+(the reference copies O(S) bytes per decode step, kv_cache.py:28-49).  The public tensors are views:
+
+    K_sel, V_sel          [B,G,S,D]        every token (K with RoPE)
+    K_win, V_win          [B,G,min(w,S),D] last w tokens (a view of the full window slab)
+    K_cmp_raw_seq, V_...  [B,G,S,D]        raw (un-rotated) projections feeding phi
+    K_cmp, V_cmp          [B,G,S_cmp,D]    emitted compressed tokens
+
+Callers may still construct it with zero-length tensors exactly as the reference's benches/tests do
+(bench/bench_decode.py:14-33, nsa/model/llama_block_nsa.py:74-101).
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import torch
+
+from ..core.block_index import BlockMeta
+
+
+@dataclass
+class NSA_KV:
+    K_sel: torch.Tensor
+    V_sel: torch.Tensor
+    K_win: torch.Tensor
+    V_win: torch.Tensor
+    K_cmp_raw_seq: torch.Tensor
+    V_cmp_raw_seq: torch.Tensor
+    K_cmp: torch.Tensor
+    V_cmp: torch.Tensor
+    win_ptr: torch.Tensor
+    cmp_emit_next: torch.Tensor
+    meta: BlockMeta
+    reads_pred: torch.Tensor
+    reads_act_total: torch.Tensor
+    reads_act_sel: torch.Tensor
+    reads_act_cmp: torch.Tensor
+    reads_act_win: torch.Tensor
+    # slab bookkeeping (not part of the reference's dataclass)
+    _slabs: Dict[str, torch.Tensor] = field(default_factory=dict, repr=False, compare=False)
+    _views: Dict[str, torch.Tensor] = field(default_factory=dict, repr=False, compare=False)
+    _lens: Dict[str, int] = field(default_factory=dict, repr=False, compare=False)
+
+    # ---- slab management -----------------------------------------------------------------------
+    def _in_sync(self, name: str) -> bool:
+        return name in self._slabs and self._views.get(name) is getattr(self, name)
+
+    def _ensure(self, name: str, extra: int) -> None:
+        """Make `name` slab-backed with room for `extra` more rows, preserving its current content.  A field the
+        caller assigned directly (zero-length placeholders, reference-style exact-size tensors) is adopted by copy."""
+        cur: torch.Tensor = getattr(self, name)
+        sync = self._in_sync(name)
+        n = self._lens[name] if sync else cur.shape[2]
+        if sync and self._slabs[name].shape[2] >= n + extra:
+            return
+        keep = self._slabs[name][:, :, :n] if sync else cur
+        B, G, _, D = cur.shape
+        cap = max(n + extra, 2 * n, 64)
+        new = torch.zeros((B, G, cap, D), dtype=cur.dtype, device=cur.device)
+        if n:
+            new[:, :, :n] = keep
+        self._slabs[name] = new
+        self._lens[name] = n
+        self._set_view(name)
+
+    def _set_view(self, name: str) -> None:
+        n = self._lens[name]
+        window = self._lens.get("__w_" + name)
+        lo = max(0, n - window) if window is not None else 0
+        v = self._slabs[name][:, :, lo:n]
+        self._views[name] = v
+        setattr(self, name, v)
+
+    def _append(self, name: str, x: torch.Tensor, window: Optional[int] = None) -> None:
+        cur: torch.Tensor = getattr(self, name)
+        if cur.dtype != x.dtype or cur.device != x.device:  # zero-length placeholder of another dtype/device
+            if cur.shape[2] != 0:
+                raise RuntimeError(f"NSA_KV.{name}: dtype/device of the cache does not match the new tokens")
+            setattr(self, name, x.new_zeros((x.shape[0], x.shape[1], 0, x.shape[3])))
+            self._slabs.pop(name, None)
+        if window is not None:
+            self._lens["__w_" + name] = int(window)
+        s = x.shape[2]
+        self._ensure(name, s)
+        n = self._lens[name]
+        self._slabs[name][:, :, n:n + s] = x
+        self._lens[name] = n + s
+        self._set_view(name)
+
+    def reserve(self, capacity: int) -> "NSA_KV":
+        """Pre-allocate every cache for `capacity` tokens (decode then never reallocates)."""
+        for name in ("K_sel", "V_sel", "K_win", "V_win", "K_cmp_raw_seq", "V_cmp_raw_seq", "K_cmp", "V_cmp"):
+            have = self._lens[name] if self._in_sync(name) else getattr(self, name).shape[2]
+            self._ensure(name, max(capacity - have, 0))
+        return self
+
+    def slab(self, name: str) -> torch.Tensor:
+        """Backing [B,G,cap,D] slab of a cache field (adopting it if needed)."""
+        self._ensure(name, 0)
+        return self._slabs[name]
+
+    def length(self, name: str) -> int:
+        """Rows held in the slab of `name` (for the window slab: its whole history, not just the last w)."""
+        self._ensure(name, 0)
+        return self._lens[name]
+
+    # ---- the reference's update API ----------------------------------------------------------------
+    def update_selection_raw(self, K: torch.Tensor, V: torch.Tensor) -> None:
+        self._append("K_sel", K)
+        self._append("V_sel", V)
+
+    def update_window(self, K: torch.Tensor, V: torch.Tensor, w: int) -> None:
+        self._append("K_win", K, window=w)  # view keeps the last w tokens (kv_cache.py:32-38)
+        self._append("V_win", V, window=w)
+
+    def update_compressed(self, K_raw_cmp: torch.Tensor, V_raw_cmp: torch.Tensor, l: int, d: int) -> None:
+        # prefill: replace with the freshly pooled sequence (kv_cache.py:40-45)
+        self.K_cmp = K_raw_cmp
+        self.V_cmp = V_raw_cmp
+        self._slabs.pop("K_cmp", None)
+        self._slabs.pop("V_cmp", None)
+
+    def append_compressed(self, K_new: torch.Tensor, V_new: torch.Tensor) -> None:
+        """Decode emission: append one compressed token (nsa_attention.py:598-604 does it with torch.cat)."""
+        self._append("K_cmp", K_new)
+        self._append("V_cmp", V_new)
+
+    def append_cmp_raw(self, K_raw_tok: torch.Tensor, V_raw_tok: torch.Tensor) -> None:
+        self._append("K_cmp_raw_seq", K_raw_tok)
+        self._append("V_cmp_raw_seq", V_raw_tok)
+
+    # ---- read counters (kv_cache.py:51-65) --------------------------------------------------------
+    @staticmethod
+    def _cat(t: torch.Tensor, val: int) -> torch.Tensor:
+        v = torch.full((1,), int(val), dtype=torch.int64, device=t.device)
+        return torch.cat([t, v], dim=0) if t.numel() else v
+
+    def append_reads_pred(self, value: int) -> None:
+        self.reads_pred = self._cat(self.reads_pred, value)
+
+    def append_reads_actual(self, total: int, sel: int, cmp: int, win: int) -> None:
+        self.reads_act_total = self._cat(self.reads_act_total, total)
+        self.reads_act_sel = self._cat(self.reads_act_sel, sel)
+        self.reads_act_cmp = self._cat(self.reads_act_cmp, cmp)
+        self.reads_act_win = self._cat(self.reads_act_win, win)
+
+
+def create_empty_kv(B: int, G: int, d_k: int, d_v: int, meta: BlockMeta, device=None, dtype=torch.float32) -> NSA_KV:
+    """Zero-length caches, as bench/bench_decode.py:14-33 builds them."""
+    device = device if device is not None else torch.device("cuda")
+    z = lambda D: torch.zeros((B, G, 0, D), device=device, dtype=dtype)
+    zi = lambda: torch.zeros((0,), dtype=torch.int64, device=device)
+    return NSA_KV(K_sel=z(d_k), V_sel=z(d_v), K_win=z(d_k), V_win=z(d_v), K_cmp_raw_seq=z(d_k), V_cmp_raw_seq=z(d_v),
+                  K_cmp=z(d_k), V_cmp=z(d_v), win_ptr=torch.zeros((B, G), dtype=torch.int32, device=device),
+                  cmp_emit_next=torch.zeros((B, G), dtype=torch.int32, device=device), meta=meta, reads_pred=zi(),
+                  reads_act_total=zi(), reads_act_sel=zi(), reads_act_cmp=zi(), reads_act_win=zi())

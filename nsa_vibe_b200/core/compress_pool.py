@@ -1,0 +1,25 @@
+"""phi = avg-pool(kernel l, stride d) over RoPE(K) and raw V (nsa/core/compress_pool.py:9-38).
+Producer of K_cmp/V_cmp; kept in torch (SURVEY 8f-1 lists fusing it as 'next')."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from .rope import apply_rope
+
+
+def avg_pool_phi_rope_kv(K_raw: torch.Tensor, V_raw: torch.Tensor, l: int, d: int,
+                         pos: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    B, G, S, Dk = K_raw.shape
+    Dv = V_raw.shape[-1]
+    if pos is None:
+        pos = torch.arange(S, device=K_raw.device)
+    K_rope = apply_rope(K_raw, pos)
+    if S < l:
+        return (K_raw.new_zeros((B, G, 0, Dk)), V_raw.new_zeros((B, G, 0, Dv)))
+    Kp = F.avg_pool1d(K_rope.reshape(B * G, S, Dk).transpose(1, 2), kernel_size=l, stride=d)
+    Vp = F.avg_pool1d(V_raw.reshape(B * G, S, Dv).transpose(1, 2), kernel_size=l, stride=d)
+    S_cmp = Kp.shape[-1]
+    return (Kp.transpose(1, 2).reshape(B, G, S_cmp, Dk).contiguous(), Vp.transpose(1, 2).reshape(B, G, S_cmp, Dv).contiguous())

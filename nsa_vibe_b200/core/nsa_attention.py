@@ -1,0 +1,293 @@
+"""NSAAttention -- drop-in for the reference module (nsa/core/nsa_attention.py:168-1855).
+
+Same constructor, parameter names (state-dict compatible: W_Q, W_K_sel, W_V_sel, W_K_win, W_V_win, W_K_cmp,
+W_V_cmp, out, gate.fc1, gate.fc2), `forward(x, kv, *, prefill) -> (out, kv)`, observability getters and
+NSA_* environment flags (snapshotted at construction like the reference, :300-394).  Everything between
+"Q/K/V projected + RoPE'd" and "O handed to self.out" runs in hand-written sm_100a kernels through
+libnsa_b200.so (ops.prefill_core / ops.decode_core); projections, RoPE and the phi pooling that produce the
+hot path's inputs stay in torch (SURVEY 8f lists fusing them as next).
+
+Semantics: all three branches are true softmax over their allowed keys (the reference's default
+per-token SDPA routes attend to one key only, F1).  Selection follows the reference's rule for the mode in use
+(F2): NSA_PREFILL_BATCHED=1 -> select_topn_ranges_batched; sequential prefill / decode -> select_topn_ranges.
+Flags that only choose among the reference's removed back ends (NSA_USE_FA2*, NSA_USE_TRITON_SEL, NSA_SEL_CUDA,
+NSA_USE_SEL_PACK/MASK/VARLEN, NSA_FORCE_SEL_MASK, NSA_USE_CMP_MASK, NSA_USE_WIN_MASK, NSA_FORCE_PARITY) are accepted
+and ignored: every route is the one CUDA path.  CPU tensors raise -- there is no fallback.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..cache.kv_cache import NSA_KV
+from .block_index import build_block_meta
+from .compress_pool import avg_pool_phi_rope_kv
+from .rope import apply_rope
+
+
+def _env_true(name: str, default: str = "0") -> bool:
+    return os.getenv(name, default).lower() in ("1", "true", "yes")
+
+
+class GateMLP(nn.Module):
+    """Gate network (nsa_attention.py:32-82).  The fused kernels evaluate it on-chip from these parameters;
+    this torch forward exists for callers that invoke the gate directly."""
+
+    def __init__(self, d_k: int, hidden: Optional[int] = None):
+        super().__init__()
+        hidden = hidden or max(1, d_k // 2)
+        self.fc1 = nn.Linear(d_k, hidden)
+        self.fc2 = nn.Linear(hidden, 3)
+        nn.init.xavier_uniform_(self.fc2.weight, gain=0.1)
+        nn.init.zeros_(self.fc2.bias)
+        self._force_uniform_gate = _env_true("NSA_FORCE_UNIFORM_GATE")
+        self._force_branch = os.getenv("NSA_FORCE_BRANCH")
+
+    def mode(self) -> int:
+        if self._force_uniform_gate:
+            return ops.GATE_UNIFORM
+        fb = (self._force_branch or "").strip().lower()
+        return {"cmp": ops.GATE_CMP, "sel": ops.GATE_SEL, "win": ops.GATE_WIN}.get(fb, ops.GATE_MLP)
+
+    def params(self):
+        return (self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)
+
+    def forward(self, q_group_pooled: torch.Tensor, tau: float = 1.0) -> torch.Tensor:
+        m = self.mode()
+        shape = (*q_group_pooled.shape[:-1], 3)
+        if m == ops.GATE_UNIFORM:
+            return torch.full(shape, 1.0 / 3.0, device=q_group_pooled.device, dtype=q_group_pooled.dtype)
+        if m != ops.GATE_MLP:
+            one = torch.zeros(shape, device=q_group_pooled.device, dtype=q_group_pooled.dtype)
+            one[..., m - ops.GATE_CMP] = 1.0
+            return one
+        g = self.fc2(F.silu(self.fc1(q_group_pooled))) / max(tau, 1e-6)
+        p = F.softmax(g, dim=-1)
+        top2 = torch.topk(g.detach(), k=2, dim=-1).values
+        peaked = (top2[..., 0] - top2[..., 1]) > 50.0
+        hard = F.one_hot(torch.argmax(g, dim=-1), 3).to(p.dtype)
+        return torch.where(peaked.unsqueeze(-1), hard, p)
+
+
+def _compute_gate_stats(gates: torch.Tensor) -> dict:
+    """Gate health statistics (nsa_attention.py:127-165), one device->host transfer."""
+    with torch.no_grad():
+        g = gates.reshape(-1, 3).float()
+        ent = -(g * (g + 1e-8).log()).sum(dim=-1)
+        mx = g.max(dim=-1)[0]
+        collapsed = ((ent < 0.1) & (mx > 0.95)).float().mean()
+        packed = torch.cat([torch.stack([ent.mean(), ent.min(), mx.mean(), mx.max(), collapsed]), g.mean(dim=0)]).tolist()
+    return {"entropy_mean": packed[0], "entropy_min": packed[1], "max_gate_mean": packed[2], "max_gate_max": packed[3],
+            "branch_shares": packed[5:8], "collapse_fraction": packed[4], "total_gates": int(g.shape[0])}
+
+
+class NSAAttention(nn.Module):
+    def __init__(self, dim: int, n_heads: int, n_kv_groups: int, d_k: int, d_v: int, l: int = 32, d: int = 16,
+                 l_sel: int = 64, n_sel: int = 16, w: int = 512, phi: str = "avg", gate_hidden: Optional[int] = None,
+                 gate_temp: float = 1.0, rope_impl: str = "llama", use_flash: bool = True,
+                 use_triton_sel: bool = False) -> None:
+        super().__init__()
+        assert n_heads % n_kv_groups == 0, "heads must be divisible by kv groups"
+        if l % d != 0 or l_sel % d != 0:
+            raise ValueError("M0 requires d|l and d|l_sel; set valid block sizes/stride.")
+        self.dim, self.n_heads, self.n_kv_groups = dim, n_heads, n_kv_groups
+        self.h_per_group = n_heads // n_kv_groups
+        self.d_k, self.d_v = d_k, d_v
+        self.l, self.d, self.l_sel, self.n_sel, self.w = l, d, l_sel, n_sel, w
+        self.gate_temp = gate_temp
+        self.phi_type = (phi or "avg").lower()
+        if self.phi_type != "avg":
+            # the reference's phi="mlp" is broken (phi_v_conv is always None, nsa_attention.py:289-291)
+            raise NotImplementedError("only phi='avg' is supported on the B200 path")
+        self._last_gates: Optional[torch.Tensor] = None
+        self._last_ranges: Optional[torch.Tensor] = None
+        self._fallback_counters = {k: 0 for k in (
+            "selection_triton_fails", "selection_cuda_fails", "selection_pack_fails", "selection_mask_fails",
+            "compressed_fa2_fails", "sliding_fa2_fails", "total_fallbacks")}
+        self.W_Q = nn.Linear(dim, n_heads * d_k, bias=False)
+        self.W_K_sel = nn.Linear(dim, n_kv_groups * d_k, bias=False)
+        self.W_V_sel = nn.Linear(dim, n_kv_groups * d_v, bias=False)
+        self.W_K_win = nn.Linear(dim, n_kv_groups * d_k, bias=False)
+        self.W_V_win = nn.Linear(dim, n_kv_groups * d_v, bias=False)
+        self.W_K_cmp = nn.Linear(dim, n_kv_groups * d_k, bias=False)
+        self.W_V_cmp = nn.Linear(dim, n_kv_groups * d_v, bias=False)
+        self.out = nn.Linear(n_heads * d_v, dim, bias=False)
+        self.gate = GateMLP(d_k, gate_hidden)
+        self.use_flash_default = use_flash      # accepted for API compatibility; no flash-attn route exists
+        self.use_triton_sel = use_triton_sel    # accepted for API compatibility; no Triton route exists
+        self._cache_env_vars()
+
+    # ---- flags (nsa_attention.py:300-394) ---------------------------------------------------------
+    def _cache_env_vars(self) -> None:
+        self._env_cache = {
+            "prefill_batched": _env_true("NSA_PREFILL_BATCHED"),
+            "strict_asserts": _env_true("NSA_STRICT_ASSERTS"),
+            "stopgrad_gates": _env_true("NSA_STOPGRAD_GATES"),
+            "nvtx": _env_true("NSA_NVTX"),
+            "disable_aux_stats": _env_true("NSA_DISABLE_AUX_STATS"),
+            "pcmp_norm": os.getenv("NSA_PCMP_NORM", "full_row").strip().lower(),  # B200 addition
+        }
+        try:
+            rs = float(os.getenv("NSA_ROPE_SCALE", "1.0"))
+            self.rope_scale = rs if (rs > 0.0 and rs == rs) else 1.0
+        except ValueError:
+            self.rope_scale = 1.0
+        try:
+            self.prefill_tile = max(0, int(os.getenv("NSA_PREFILL_TILE", "0")))
+        except ValueError:
+            self.prefill_tile = 0
+
+    def _cfg(self, *, causal_norm: bool = False) -> ops.NSAConfig:
+        norm = ops.NORM_CAUSAL if (causal_norm or self._env_cache["pcmp_norm"] == "causal") else ops.NORM_FULL_ROW
+        return ops.NSAConfig(l=self.l, d=self.d, l_sel=self.l_sel, n_sel=self.n_sel, w=self.w,
+                             gate_tau=float(self.gate_temp), gate_mode=self.gate.mode(), norm_mode=norm)
+
+    def _shape_q(self, Q: torch.Tensor, B: int, S: int) -> torch.Tensor:
+        return Q.view(B, S, self.n_kv_groups, self.h_per_group, self.d_k)
+
+    def _shape_kv(self, X: torch.Tensor, B: int, S: int) -> torch.Tensor:
+        return X.view(B, S, self.n_kv_groups, -1).permute(0, 2, 1, 3).contiguous()  # [B,G,S,D*]
+
+    # ---- observability (nsa_attention.py:407-507); stats are reduced on demand, not per step ---------
+    def get_gate_stats(self) -> Optional[dict]:
+        return None if self._last_gates is None else _compute_gate_stats(self._last_gates)
+
+    def get_fallback_counters(self) -> dict:
+        return self._fallback_counters.copy()  # always zero: there is nothing to fall back to
+
+    def reset_fallback_counters(self) -> dict:
+        prev = self._fallback_counters.copy()
+        for k in self._fallback_counters:
+            self._fallback_counters[k] = 0
+        return prev
+
+    def get_selection_stats(self) -> Optional[dict]:
+        r = self._last_ranges
+        if r is None:
+            return None
+        base = {"l_sel": int(self.l_sel), "n_sel": int(self.n_sel)}
+        if r.numel() == 0:
+            return {"k_mean": 0.0, "k_max": 0, "rows": 0, "pct_at_max": 0.0, **base}
+        L = (r[..., 1] - r[..., 0]).clamp_min(0).sum(dim=-1).to(torch.int64).reshape(-1)
+        k_max = L.max()
+        packed = torch.stack([L.float().mean(), k_max.float(), (L == k_max).float().mean()]).tolist()
+        k_max_i = int(packed[1])
+        return {"k_mean": packed[0], "k_max": k_max_i, "rows": int(L.numel()), "pct_at_max": packed[2] if k_max_i > 0 else 0.0,
+                **base}
+
+    # ---- forward ---------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, kv: NSA_KV, *, prefill: bool) -> tuple[torch.Tensor, NSA_KV]:
+        assert x.dim() == 3, "x must be [B,S,dim]"
+        B, S, _ = x.shape
+        if not x.is_cuda:
+            raise RuntimeError("NSAAttention (B200) needs CUDA tensors: the hot path has no CPU fallback")
+        if prefill:
+            assert S > 0, f"Prefill mode requires S > 0, got S={S}"
+            return self._forward_prefill(x, kv)
+        assert S == 1, (f"Decode mode requires S=1 (single token), got S={S}. "
+                        f"This ensures proper causal ordering in decode steps.")
+        return self._forward_decode(x, kv)
+
+    def _project(self, x: torch.Tensor, t0: int):
+        B, S, _ = x.shape
+        pos = torch.arange(t0, t0 + S, device=x.device)
+        # the reference rotates Q as ONE vector of width n_heads*d_k (nsa_attention.py:1002-1009, :551-556)
+        Q = apply_rope(self.W_Q(x), pos, scale=self.rope_scale)
+        Q = self._shape_q(Q, B, S)
+        K_sel = apply_rope(self._shape_kv(self.W_K_sel(x), B, S), pos, scale=self.rope_scale)
+        V_sel = self._shape_kv(self.W_V_sel(x), B, S)
+        K_win = apply_rope(self._shape_kv(self.W_K_win(x), B, S), pos, scale=self.rope_scale)
+        V_win = self._shape_kv(self.W_V_win(x), B, S)
+        K_raw = self._shape_kv(self.W_K_cmp(x), B, S)
+        V_raw = self._shape_kv(self.W_V_cmp(x), B, S)
+        return Q, K_sel, V_sel, K_win, V_win, K_raw, V_raw
+
+    def _nvtx(self, name: Optional[str]):
+        if self._env_cache["nvtx"]:
+            if name is None:
+                torch.cuda.nvtx.range_pop()
+            else:
+                torch.cuda.nvtx.range_push(name)
+
+    def _forward_prefill(self, x: torch.Tensor, kv: NSA_KV) -> tuple[torch.Tensor, NSA_KV]:
+        """All three reference prefill routes (batched :978-1448, sequential :1521-1723, via-decode :1507-1519)
+        collapse onto one fused pass; they differ only in the selection rule and the p_cmp normaliser."""
+        B, S, _ = x.shape
+        t0 = int(kv.K_sel.shape[2])
+        self._nvtx("projections+rope")
+        Q, K_sel, V_sel, K_win, V_win, K_raw, V_raw = self._project(x, t0)
+        self._nvtx(None)
+        kv.update_selection_raw(K_sel.detach(), V_sel.detach())
+        kv.meta = build_block_meta(seq_len=t0 + S, l=self.l, d=self.d, l_sel=self.l_sel, n_sel=self.n_sel, w=self.w)
+        kv.update_window(K_win.detach(), V_win.detach(), self.w)
+        # NOTE: unlike the reference (whose prefill never fills K_cmp_raw_seq, so a following decode restarts the
+        # emission count at zero) the raw stream is recorded, keeping "emit every d after warm-up l" absolute.
+        kv.append_cmp_raw(K_raw.detach(), V_raw.detach())
+        if t0 == 0:
+            K_cmp, V_cmp = avg_pool_phi_rope_kv(K_raw, V_raw, self.l, self.d, pos=torch.arange(S, device=x.device))
+        else:
+            K_cmp, V_cmp = avg_pool_phi_rope_kv(kv.K_cmp_raw_seq, kv.V_cmp_raw_seq, self.l, self.d,
+                                                pos=torch.arange(t0 + S, device=x.device))
+        kv.update_compressed(K_cmp.detach(), V_cmp.detach(), self.l, self.d)
+
+        via_decode = self.prefill_tile > 0
+        sel_mode = 0 if (self._env_cache["prefill_batched"] and not via_decode) else 1
+        cfg = self._cfg(causal_norm=via_decode)
+        gate = self.gate.params() if cfg.gate_mode == ops.GATE_MLP else None
+        self._nvtx("branch_attn+gate")
+        if t0 == 0:
+            O, ranges, gates = ops.prefill_core(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, gate, cfg, sel_mode=sel_mode,
+                                                t0=0, stopgrad_gates=self._env_cache["stopgrad_gates"])
+        else:  # chunked prefill continues on the cache slabs (inference only)
+            n = t0 + S
+            O, ranges, gates = ops.prefill_core(
+                Q, kv.slab("K_sel"), kv.slab("V_sel"), kv.slab("K_win"), kv.slab("V_win"), K_cmp, V_cmp, gate, cfg,
+                sel_mode=sel_mode, t0=t0, S_sel_kv=n, S_win_kv=kv.length("K_win"), win_off=n - kv.length("K_win"))
+        self._nvtx(None)
+        if self._env_cache["strict_asserts"] and ranges.numel() > 0:
+            tpos = torch.arange(t0, t0 + S, device=x.device).view(1, S, 1, 1)
+            assert bool((ranges[..., 1] <= tpos + 1).all()), "Selection ranges cannot access future tokens."
+        self._last_gates, self._last_ranges = gates, ranges
+        out = self.out(O.reshape(B, S, self.n_heads * self.d_v))
+        return out, kv
+
+    def _forward_decode(self, x: torch.Tensor, kv: NSA_KV) -> tuple[torch.Tensor, NSA_KV]:
+        """One decode step (nsa_attention.py:545-976)."""
+        B = x.shape[0]
+        t = int(kv.K_sel.shape[2])  # position of the new token
+        with torch.no_grad():
+            Q, K_sel, V_sel, K_win, V_win, K_raw, V_raw = self._project(x, t)
+            kv.update_selection_raw(K_sel, V_sel)
+            kv.update_window(K_win, V_win, self.w)
+            kv.append_cmp_raw(K_raw, V_raw)
+            S_raw = int(kv.K_cmp_raw_seq.shape[2])
+            if S_raw >= self.l and (S_raw - self.l) % self.d == 0:  # emission schedule (:587-604)
+                pos_last = torch.arange(S_raw - self.l, S_raw, device=x.device)
+                K_new, V_new = avg_pool_phi_rope_kv(kv.K_cmp_raw_seq[:, :, S_raw - self.l:S_raw],
+                                                    kv.V_cmp_raw_seq[:, :, S_raw - self.l:S_raw], self.l, self.d, pos=pos_last)
+                kv.append_compressed(K_new, V_new)
+            need = max(t + 1, self.l_sel)
+            if getattr(kv, "meta", None) is None or kv.meta.sel_starts.numel() * self.l_sel < t + 1 or kv.meta.sel_starts.numel() == 0:
+                kv.meta = build_block_meta(seq_len=need, l=self.l, d=self.d, l_sel=self.l_sel, n_sel=self.n_sel, w=self.w)
+            if not self._env_cache["disable_aux_stats"]:
+                num_cmp = 0 if S_raw < self.l else (S_raw - self.l) // self.d + 1
+                reads = num_cmp + self.n_sel * self.l_sel + min(self.w, S_raw)  # :634-638
+                kv.append_reads_pred(reads)
+                kv.append_reads_actual(reads, self.n_sel * self.l_sel, num_cmp, min(self.w, S_raw))
+            cfg = self._cfg()
+            gate = self.gate.params() if cfg.gate_mode == ops.GATE_MLP else None
+            ranges = torch.empty((B, self.n_kv_groups, self.n_sel, 2), dtype=torch.int32, device=x.device)
+            n_win = kv.length("K_win")
+            O = ops.decode_core(Q, kv.slab("K_sel"), kv.slab("V_sel"), kv.slab("K_win"), kv.slab("V_win"),
+                                kv.slab("K_cmp"), kv.slab("V_cmp"), gate, cfg, t=t, S_sel_kv=t + 1, S_win_kv=n_win,
+                                win_off=(t + 1) - n_win, S_cmp=int(kv.K_cmp.shape[2]), ranges_out=ranges)
+            if self._env_cache["strict_asserts"]:
+                assert int(ranges[..., 1].max()) <= t + 1, "Selection must not access future tokens."
+            self._last_ranges = ranges
+            out = self.out(O.reshape(B, 1, self.n_heads * self.d_v))
+        return out, kv

@@ -1,0 +1,256 @@
+// C ABI of libnsa_b200.so (see include/nsa_b200.h).  Validates arguments, picks the kernel family
+// (tcgen05 kernels when the shape allows, SIMT otherwise -- both hand-written sm_100a CUDA; there is no
+// CPU path) and launches on the caller's stream.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "select.cuh"
+#include "launchers.h"
+
+namespace nsa {
+
+static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return NSA_ERR_CUDA;
+  }
+  __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED);
+  return NSA_OK;
+}
+
+static int validate_dims(const nsa_dims_t* dm, const char* who) {
+  NSA_REQUIRE(dm != nullptr, "%s: dims is NULL", who);
+  NSA_REQUIRE(dm->B >= 0 && dm->S >= 0 && dm->G >= 1 && dm->h >= 1, "%s: bad B/S/G/h = %d/%d/%d/%d", who, dm->B, dm->S,
+              dm->G, dm->h);
+  NSA_REQUIRE(dm->Dk >= 1 && dm->Dv >= 1, "%s: bad Dk/Dv", who);
+  NSA_REQUIRE(dm->l >= 1 && dm->d >= 1 && dm->l_sel >= 1, "%s: block parameters must be positive", who);
+  NSA_REQUIRE(dm->l % dm->d == 0 && dm->l_sel % dm->d == 0, "%s: require d|l and d|l_sel (l=%d d=%d l_sel=%d)", who,
+              dm->l, dm->d, dm->l_sel);  // nsa_attention.py:210-211
+  NSA_REQUIRE(dm->dtype == NSA_F32 || dm->dtype == NSA_BF16 || dm->dtype == NSA_F16, "%s: dtype %d", who, dm->dtype);
+  NSA_REQUIRE(dm->S_cmp <= dm->cap_cmp && dm->S_sel_kv <= dm->cap_sel && dm->S_win_kv <= dm->cap_win,
+              "%s: cache rows exceed capacity", who);
+  return NSA_OK;
+}
+
+static bool tc_eligible(const nsa_dims_t& dm) {
+  return dm.impl != NSA_IMPL_SIMT && tc_supported(dm);
+}
+
+}  // namespace nsa
+
+using namespace nsa;
+
+extern "C" {
+
+const char* nsa_version(void) { return "nsa_b200 0.1 (sm_100a)"; }
+const char* nsa_last_error(void) { return g_err; }
+int64_t nsa_kernel_launches(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+int nsa_prefill_range_cols(int S_total, int l_sel, int n_sel) { return prefill_range_cols(S_total, l_sel, n_sel); }
+
+int nsa_select_ranges_prefill(const float* p_grp, int B, int S, int G, int S_sel, int l_sel, int n_sel, int S_total,
+                              int t0, int K, int32_t* ranges, void* stream) {
+  NSA_REQUIRE(p_grp && ranges, "select_prefill: NULL pointer");
+  NSA_REQUIRE(l_sel >= 1 && n_sel >= 0 && S_total >= 1, "select_prefill: bad l_sel/n_sel/S_total");
+  NSA_REQUIRE(K == prefill_range_cols(S_total, l_sel, n_sel), "select_prefill: K=%d but the reference emits %d columns",
+              K, prefill_range_cols(S_total, l_sel, n_sel));
+  return launch_select(p_grp, B * S * G, S, G, S_sel, l_sel, n_sel, 0, prefill_forced_cols(S_total, l_sel), K, t0, ranges,
+                       (cudaStream_t)stream);
+}
+
+int nsa_select_ranges_decode(const float* p_grp, int B, int G, int S_sel, int l_sel, int n_sel, int t, int32_t* ranges,
+                             void* stream) {
+  NSA_REQUIRE(p_grp && ranges, "select_decode: NULL pointer");
+  NSA_REQUIRE(l_sel >= 1 && n_sel >= 0 && t >= 0, "select_decode: bad l_sel/n_sel/t");
+  return launch_select(p_grp, B * G, 1, G, S_sel, l_sel, n_sel, 1, 3, n_sel, t, ranges, (cudaStream_t)stream);
+}
+
+int nsa_score(const nsa_dims_t* dm, const void* Q, const void* K_cmp, int S_sel, float* p_grp, void* stream) {
+  if (int rc = validate_dims(dm, "score")) return rc;
+  NSA_REQUIRE(Q && p_grp && (K_cmp || dm->S_cmp == 0), "score: NULL pointer");
+  if (tc_eligible(*dm) && tc_score_supported(*dm))
+    return launch_score_tc(*dm, Q, K_cmp, S_sel, 0, 0, 0, p_grp, nullptr, nullptr, (cudaStream_t)stream);
+  return launch_score_generic(*dm, Q, K_cmp, S_sel, dm->t0 + dm->S, 0, 0, p_grp, nullptr, (cudaStream_t)stream);
+}
+
+int nsa_score_select(const nsa_dims_t* dm, const void* Q, const void* K_cmp, int S_sel, int S_total, int mode,
+                     int32_t* ranges, void* workspace, void* stream) {
+  if (int rc = validate_dims(dm, "score_select")) return rc;
+  NSA_REQUIRE(Q && ranges && (K_cmp || dm->S_cmp == 0), "score_select: NULL pointer");
+  NSA_REQUIRE(mode == 0 || mode == 1, "score_select: mode %d", mode);
+  const int K = mode == 0 ? prefill_range_cols(S_total, dm->l_sel, dm->n_sel) : dm->n_sel;
+  NSA_REQUIRE(dm->n_ranges == K, "score_select: dims.n_ranges=%d but this rule emits %d columns", dm->n_ranges, K);
+  if (tc_eligible(*dm) && tc_score_supported(*dm))
+    return launch_score_tc(*dm, Q, K_cmp, S_sel, S_total, mode, K, nullptr, ranges, workspace, (cudaStream_t)stream);
+  return launch_score_generic(*dm, Q, K_cmp, S_sel, S_total, mode, K, nullptr, ranges, (cudaStream_t)stream);
+}
+
+static void fill_fwd(FwdArgs& a, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
+                     const void* V_win, const void* K_cmp, const void* V_cmp) {
+  memset(&a, 0, sizeof(a));
+  a.Q = Q;
+  a.K[0] = K_cmp; a.V[0] = V_cmp;
+  a.K[1] = K_sel; a.V[1] = V_sel;
+  a.K[2] = K_win; a.V[2] = V_win;
+}
+
+int nsa_branch_attn_fwd(const nsa_dims_t* dm, int branch, const void* Q, const void* K, const void* V,
+                        const int32_t* ranges, void* O_b, float* lse_b, void* stream) {
+  if (int rc = validate_dims(dm, "branch_attn_fwd")) return rc;
+  NSA_REQUIRE(branch >= 0 && branch <= 2, "branch_attn_fwd: branch %d", branch);
+  NSA_REQUIRE(Q && O_b, "branch_attn_fwd: NULL pointer");
+  NSA_REQUIRE(branch != 1 || ranges, "branch_attn_fwd: the selected branch needs ranges");
+  if (tc_eligible(*dm)) return launch_branch_tc(*dm, branch, Q, K, V, ranges, O_b, lse_b, (cudaStream_t)stream);
+  FwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.Q = Q;
+  a.K[branch] = K;
+  a.V[branch] = V;
+  a.ranges = ranges;
+  a.branch_mask = 1 << branch;
+  // write this branch's result into slot `branch` of the [3][...] views by offsetting the base pointers back
+  const size_t rows_h = (size_t)dm->B * dm->S * dm->G * dm->h;
+  a.O_br = (char*)O_b - (size_t)branch * rows_h * dm->Dv * elt_size(dm->dtype);
+  a.lse = lse_b ? lse_b - (size_t)branch * rows_h : nullptr;
+  nsa_dims_t d2 = *dm;
+  d2.gate_mode = NSA_GATE_UNIFORM;  // gates are irrelevant here (O is not produced)
+  return launch_fwd_generic(d2, a, (cudaStream_t)stream);
+}
+
+int nsa_branch_attn_bwd(const nsa_dims_t* dm, int branch, const void* Q, const void* K, const void* V,
+                        const int32_t* ranges, const void* O_b, const float* lse_b, const void* dO_b, float* dQ,
+                        float* dK, float* dV, void* stream) {
+  if (int rc = validate_dims(dm, "branch_attn_bwd")) return rc;
+  NSA_REQUIRE(branch >= 0 && branch <= 2, "branch_attn_bwd: branch %d", branch);
+  NSA_REQUIRE(Q && O_b && lse_b && dO_b && dQ && dK && dV, "branch_attn_bwd: NULL pointer");
+  BwdArgs a;
+  memset(&a, 0, sizeof(a));
+  const size_t rows_h = (size_t)dm->B * dm->S * dm->G * dm->h;
+  a.Q = Q;
+  a.K[branch] = K;
+  a.V[branch] = V;
+  a.ranges = ranges;
+  a.O_br = (const char*)O_b - (size_t)branch * rows_h * dm->Dv * elt_size(dm->dtype);
+  a.lse = lse_b - (size_t)branch * rows_h;
+  a.dO = dO_b;
+  a.dQ = dQ;
+  a.dK[branch] = dK;
+  a.dV[branch] = dV;
+  a.branch_mask = 1 << branch;
+  return launch_bwd_generic(*dm, a, (cudaStream_t)stream);
+}
+
+int nsa_gate_fwd(const nsa_dims_t* dm, const void* Q, const nsa_gate_params_t* gp, float* gates, void* stream) {
+  if (int rc = validate_dims(dm, "gate_fwd")) return rc;
+  NSA_REQUIRE(Q && gates && gp, "gate_fwd: NULL pointer");
+  NSA_REQUIRE(dm->gate_mode != NSA_GATE_MLP || (gp->fc1_w && gp->fc2_w), "gate_fwd: MLP weights missing");
+  return launch_gate_fwd(*dm, Q, *gp, gates, (cudaStream_t)stream);
+}
+
+int nsa_gate_bwd(const nsa_dims_t* dm, const void* Q, const nsa_gate_params_t* gp, const float* dgates, float* dQ,
+                 float* d_fc1_w, float* d_fc1_b, float* d_fc2_w, float* d_fc2_b, void* stream) {
+  if (int rc = validate_dims(dm, "gate_bwd")) return rc;
+  NSA_REQUIRE(Q && gp && dgates && d_fc1_w && d_fc1_b && d_fc2_w && d_fc2_b, "gate_bwd: NULL pointer");
+  return launch_gate_bwd(*dm, Q, *gp, dgates, dQ, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b, (cudaStream_t)stream);
+}
+
+int nsa_prefill_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
+                    const void* V_win, const void* K_cmp, const void* V_cmp, const int32_t* ranges,
+                    const nsa_gate_params_t* gp, void* O, float* lse, float* gates, void* O_branches, void* stream) {
+  if (int rc = validate_dims(dm, "prefill_fwd")) return rc;
+  NSA_REQUIRE(Q && O && ranges && gp, "prefill_fwd: NULL pointer");
+  NSA_REQUIRE(dm->gate_mode != NSA_GATE_MLP || (gp->fc1_w && gp->fc2_w), "prefill_fwd: MLP weights missing");
+  if (tc_eligible(*dm))
+    return launch_prefill_tc(*dm, Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, ranges, *gp, O, lse, gates, O_branches,
+                             (cudaStream_t)stream);
+  FwdArgs a;
+  fill_fwd(a, Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp);
+  a.ranges = ranges;
+  a.gp = *gp;
+  a.O = O;
+  a.lse = lse;
+  a.gates_out = gates;
+  a.O_br = O_branches;
+  a.branch_mask = 7;
+  return launch_fwd_generic(*dm, a, (cudaStream_t)stream);
+}
+
+int nsa_prefill_bwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
+                    const void* V_win, const void* K_cmp, const void* V_cmp, const int32_t* ranges,
+                    const void* O_branches, const float* lse, const float* gates, const void* dO, float* dQ,
+                    float* dK_sel, float* dV_sel, float* dK_win, float* dV_win, float* dK_cmp, float* dV_cmp,
+                    float* dgates, void* stream) {
+  if (int rc = validate_dims(dm, "prefill_bwd")) return rc;
+  NSA_REQUIRE(Q && ranges && O_branches && lse && gates && dO && dQ, "prefill_bwd: NULL pointer");
+  NSA_REQUIRE(dK_sel && dV_sel && dK_win && dV_win && dK_cmp && dV_cmp, "prefill_bwd: NULL gradient buffer");
+  BwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.Q = Q;
+  a.K[0] = K_cmp; a.V[0] = V_cmp; a.dK[0] = dK_cmp; a.dV[0] = dV_cmp;
+  a.K[1] = K_sel; a.V[1] = V_sel; a.dK[1] = dK_sel; a.dV[1] = dV_sel;
+  a.K[2] = K_win; a.V[2] = V_win; a.dK[2] = dK_win; a.dV[2] = dV_win;
+  a.ranges = ranges;
+  a.O_br = O_branches;
+  a.lse = lse;
+  a.gates = gates;
+  a.dO = dO;
+  a.dQ = dQ;
+  a.dgates = dgates;
+  a.branch_mask = 7;
+  return launch_bwd_generic(*dm, a, (cudaStream_t)stream);
+}
+
+int nsa_decode_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
+                   const void* V_win, const void* K_cmp, const void* V_cmp, const nsa_gate_params_t* gp, void* O,
+                   int32_t* ranges_out, void* workspace, void* stream) {
+  if (int rc = validate_dims(dm, "decode_fwd")) return rc;
+  NSA_REQUIRE(dm->S == 1, "decode_fwd: decode requires S == 1, got S=%d", dm->S);  // nsa_attention.py:532-535
+  NSA_REQUIRE(Q && O && gp, "decode_fwd: NULL pointer");
+  NSA_REQUIRE(ranges_out || workspace, "decode_fwd: need ranges_out or a workspace");
+  NSA_REQUIRE(dm->n_ranges == dm->n_sel, "decode_fwd: dims.n_ranges must equal n_sel");
+  if (tc_eligible(*dm) && tc_decode_supported(*dm))
+    return launch_decode_tc(*dm, Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, *gp, O, ranges_out, workspace,
+                            (cudaStream_t)stream);
+  int32_t* ranges = ranges_out ? ranges_out : (int32_t*)workspace;
+  const int t = dm->t0;
+  const int cover = t + 1 > dm->l_sel ? t + 1 : dm->l_sel;  // meta covers max(t+1, l_sel) tokens (nsa_attention.py:609-632)
+  const int S_sel = ceil_div(cover, dm->l_sel);
+  nsa_dims_t d2 = *dm;
+  d2.norm_mode = NSA_NORM_FULL_ROW;  // decode sees only emitted blocks: softmax over all of them (:650-651)
+  if (int rc = launch_score_generic(d2, Q, K_cmp, S_sel, t + 1, 1, dm->n_sel, nullptr, ranges, (cudaStream_t)stream)) return rc;
+  FwdArgs a;
+  fill_fwd(a, Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp);
+  a.ranges = ranges;
+  a.gp = *gp;
+  a.O = O;
+  a.branch_mask = 7;
+  return launch_fwd_generic(*dm, a, (cudaStream_t)stream);
+}
+
+int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which) {
+  if (!dm) return 0;
+  switch (which) {
+    case NSA_WS_DECODE:
+      return (int64_t)dm->B * dm->G * dm->n_sel * 2 * sizeof(int32_t) + tc_decode_workspace(*dm);
+    case NSA_WS_SCORE_SELECT:
+      return tc_score_workspace(*dm);
+    case NSA_WS_PREFILL:
+      return 0;
+    default:
+      return 0;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,593 @@
+// Shape- and dtype-generic SIMT kernels for the NSA hot path (fp32 / bf16 / fp16, any Dk,Dv <= 128,
+// h <= 16).  They are the parity workhorse (fp32 against the oracle at 5e-5) and serve every shape the
+// tcgen05 kernels do not specialise.  Mapping: one warp per (b, s, g) query-row group; lanes split the head
+// dimension, so every K/V row is one coalesced warp load shared by all h heads of the group (GQA reuse).
+#include "common.cuh"
+#include "select.cuh"
+#include "launchers.h"
+
+namespace nsa {
+
+// ------------------------------------------------------------------------------------------------
+// Gate MLP (nsa/core/nsa_attention.py:32-82) evaluated by one warp.  qgp: smem float[Dk] (mean over heads),
+// xs: smem float[hidden] scratch.  Returns the three gate probabilities in every lane.
+// ------------------------------------------------------------------------------------------------
+struct Gate3 { float c, s, w; };
+
+__device__ inline Gate3 gate_forward_warp(const float* qgp, float* xs, float* pre, const nsa_gate_params_t& gp, int Dk,
+                                          int hidden, float tau, int mode, bool* peaked_out) {
+  const int lane = threadIdx.x & 31;
+  if (peaked_out) *peaked_out = false;
+  if (mode == NSA_GATE_UNIFORM) return {1.0f / 3.0f, 1.0f / 3.0f, 1.0f / 3.0f};
+  if (mode == NSA_GATE_CMP) return {1.f, 0.f, 0.f};
+  if (mode == NSA_GATE_SEL) return {0.f, 1.f, 0.f};
+  if (mode == NSA_GATE_WIN) return {0.f, 0.f, 1.f};
+  for (int u = lane; u < hidden; u += 32) {
+    float a = gp.fc1_b ? gp.fc1_b[u] : 0.f;
+    const float* wrow = gp.fc1_w + (size_t)u * Dk;
+    for (int k = 0; k < Dk; ++k) a = fmaf(wrow[k], qgp[k], a);
+    if (pre) pre[u] = a;
+    xs[u] = a / (1.0f + expf(-a));  // silu
+  }
+  __syncwarp();
+  float g[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float a = 0.f;
+    for (int u = lane; u < hidden; u += 32) a = fmaf(gp.fc2_w[c * hidden + u], xs[u], a);
+    a = warp_sum(a);
+    g[c] = (a + (gp.fc2_b ? gp.fc2_b[c] : 0.f)) / fmaxf(tau, 1e-6f);
+  }
+  float mx = fmaxf(g[0], fmaxf(g[1], g[2]));
+  int am = g[0] >= g[1] ? (g[0] >= g[2] ? 0 : 2) : (g[1] >= g[2] ? 1 : 2);  // first maximum
+  float second = am == 0 ? fmaxf(g[1], g[2]) : (am == 1 ? fmaxf(g[0], g[2]) : fmaxf(g[0], g[1]));
+  if (mx - second > 50.0f) {  // hard one-hot (nsa_attention.py:74-81)
+    if (peaked_out) *peaked_out = true;
+    return {am == 0 ? 1.f : 0.f, am == 1 ? 1.f : 0.f, am == 2 ? 1.f : 0.f};
+  }
+  float e0 = expf(g[0] - mx), e1 = expf(g[1] - mx), e2 = expf(g[2] - mx);
+  float inv = 1.0f / (e0 + e1 + e2);
+  return {e0 * inv, e1 * inv, e2 * inv};
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scoring: p_cmp softmax -> Eq.9 -> Eq.10, optional fused selection.
+// ------------------------------------------------------------------------------------------------
+constexpr int kScoreWarps = 4;
+
+__global__ void __launch_bounds__(kScoreWarps * 32)
+score_generic_kernel(nsa_dims_t dm, const void* __restrict__ Q, const void* __restrict__ Kc, int S_sel, int S_total,
+                     int sel_mode, int nf, int Kr, float* __restrict__ p_grp, int32_t* __restrict__ ranges) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_warp = dm.S_cmp + S_sel + dm.h * dm.Dk;
+  float* lg = smem + (size_t)warp * per_warp;  // [S_cmp] logits -> probabilities
+  float* pg = lg + dm.S_cmp;                   // [S_sel]
+  float* qs = pg + S_sel;                      // [h][Dk]
+  const int n_rows = dm.B * dm.S * dm.G;
+  const int dt = dm.dtype;
+  for (int row = blockIdx.x * kScoreWarps + warp; row < n_rows; row += gridDim.x * kScoreWarps) {
+    const int g = row % dm.G, s = (row / dm.G) % dm.S, b = row / (dm.G * dm.S);
+    const int t = dm.t0 + s;
+    const int nkeys = dm.norm_mode == NSA_NORM_CAUSAL ? num_cmp_at(t, dm.l, dm.d, dm.S_cmp) : dm.S_cmp;
+    for (int j = lane; j < S_sel; j += 32) pg[j] = 0.f;
+    const size_t qbase = (size_t)row * dm.h * dm.Dk;
+    for (int i = lane; i < dm.h * dm.Dk; i += 32) qs[i] = ld_elt(Q, qbase + i, dt);
+    __syncwarp();
+    const size_t kbase = (size_t)(b * dm.G + g) * dm.cap_cmp * dm.Dk;
+    for (int hh = 0; hh < dm.h; ++hh) {
+      const float* qh = qs + hh * dm.Dk;
+      float m = -INFINITY;
+      for (int i = lane; i < nkeys; i += 32) {
+        float a = 0.f;
+        const size_t kr = kbase + (size_t)i * dm.Dk;
+        for (int k = 0; k < dm.Dk; ++k) a = fmaf(qh[k], ld_elt(Kc, kr + k, dt), a);
+        a *= dm.scale;
+        lg[i] = a;
+        m = fmaxf(m, a);
+      }
+      m = warp_max(m);
+      float sum = 0.f;
+      for (int i = lane; i < nkeys; i += 32) {
+        float e = expf(lg[i] - m);
+        lg[i] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      const float inv = nkeys > 0 ? 1.0f / sum : 0.f;
+      __syncwarp();
+      // Eq.9 (block_index.py:43-71): compressed block i = [i*d, i*d+l) gives overlap/l to selection block j;
+      // accumulated in ascending i like the reference's CPU scatter_add (selection_scorer.py:111-115).
+      for (int j = lane; j < S_sel; j += 32) {
+        const int b0 = j * dm.l_sel, b1 = b0 + dm.l_sel;
+        int i_lo = b0 - dm.l + 1 <= 0 ? 0 : (b0 - dm.l + 1 + dm.d - 1) / dm.d;
+        int i_hi = (b1 - 1) / dm.d;
+        if (i_hi > nkeys - 1) i_hi = nkeys - 1;
+        float acc = 0.f;
+        for (int i = i_lo; i <= i_hi; ++i) {
+          const int a0 = i * dm.d, a1 = a0 + dm.l;
+          const int ov = min(a1, b1) - max(a0, b0);
+          if (ov > 0) acc += (lg[i] * inv) * ((float)ov / (float)dm.l);
+        }
+        pg[j] += acc;  // Eq.10: sum over the heads of the group (nsa_attention.py:1091)
+      }
+      __syncwarp();
+    }
+    if (p_grp) {
+      float* dst = p_grp + (size_t)row * S_sel;
+      for (int j = lane; j < S_sel; j += 32) dst[j] = pg[j];
+    }
+    if (ranges) {
+      __syncwarp();
+      select_row_warp(pg, S_sel, dm.l_sel, dm.n_sel, sel_mode, nf, Kr, t, ranges + (size_t)row * Kr * 2);
+    }
+    __syncwarp();
+  }
+}
+
+int launch_score_generic(const nsa_dims_t& dm, const void* Q, const void* Kc, int S_sel, int S_total, int sel_mode, int Kr,
+                         float* p_grp, int32_t* ranges, cudaStream_t stream) {
+  const int n_rows = dm.B * dm.S * dm.G;
+  if (n_rows == 0) return NSA_OK;
+  NSA_REQUIRE(S_sel >= 1 && S_sel <= kSelMaxWords * 1024, "score: S_sel=%d unsupported", S_sel);
+  size_t smem = (size_t)kScoreWarps * (dm.S_cmp + S_sel + dm.h * dm.Dk) * sizeof(float);
+  NSA_REQUIRE(smem <= 200 * 1024, "score(simt): S_cmp=%d needs %zu B of shared memory", dm.S_cmp, smem);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(score_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("score: smem attr: %s", cudaGetErrorString(e)); return NSA_ERR_CUDA; }
+  }
+  int blocks = ceil_div(n_rows, kScoreWarps);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  const int nf = prefill_forced_cols(S_total, dm.l_sel);
+  score_generic_kernel<<<blocks, kScoreWarps * 32, smem, stream>>>(dm, Q, Kc, S_sel, S_total, sel_mode, nf, Kr, p_grp,
+                                                                  ranges);
+  return check_launch("score_generic_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attention over key ranges, forward.  branch_mask bit b enables branch b (0 cmp, 1 sel, 2 win).
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kAttnWarps = 4;
+
+// number of [start,end) pieces and the piece itself for one branch of one row (absolute key rows in the cache)
+__device__ __forceinline__ int branch_pieces(const nsa_dims_t& dm, int branch) { return branch == 1 ? dm.n_ranges : 1; }
+__device__ __forceinline__ void branch_piece(const nsa_dims_t& dm, int branch, int t, const int32_t* rrow, int i, int& a0,
+                                             int& a1) {
+  if (branch == 0) {  // compressed tokens [0, num_cmp(t))            (attention_kernels.py:117-126)
+    a0 = 0;
+    a1 = num_cmp_at(t, dm.l, dm.d, dm.S_cmp);
+  } else if (branch == 1) {  // selected ranges, clamped to the cache  (attention_kernels.py:724-725)
+    a0 = rrow[2 * i];
+    a1 = rrow[2 * i + 1];
+    if (a0 < 0) a0 = 0;
+    if (a1 > dm.S_sel_kv) a1 = dm.S_sel_kv;
+  } else {  // sliding window [t-w+1, t] in cache rows                 (attention_kernels.py:159-161)
+    int lo = t - dm.w + 1;
+    if (lo < dm.win_off) lo = dm.win_off;
+    if (lo < 0) lo = 0;
+    a0 = lo - dm.win_off;
+    a1 = t + 1 - dm.win_off;
+    if (a1 > dm.S_win_kv) a1 = dm.S_win_kv;
+    if (dm.w <= 0) a1 = a0;
+  }
+}
+__device__ __forceinline__ int branch_cap(const nsa_dims_t& dm, int branch) {
+  return branch == 0 ? dm.cap_cmp : (branch == 1 ? dm.cap_sel : dm.cap_win);
+}
+
+template <int HMAX, int EPT>
+__global__ void __launch_bounds__(kAttnWarps * 32)
+fwd_generic_kernel(nsa_dims_t dm, FwdArgs a) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* qgp = smem + (size_t)warp * (dm.Dk + 2 * dm.gate_hidden);
+  float* xs = qgp + dm.Dk;
+  const int n_rows = dm.B * dm.S * dm.G;
+  const int dt = dm.dtype, h = dm.h, Dk = dm.Dk, Dv = dm.Dv;
+  const size_t rows_h = (size_t)n_rows * h;
+  for (int row = blockIdx.x * kAttnWarps + warp; row < n_rows; row += gridDim.x * kAttnWarps) {
+    const int g = row % dm.G, s = (row / dm.G) % dm.S, b = row / (dm.G * dm.S);
+    const int t = dm.t0 + s;
+    float q[HMAX][EPT];
+    const size_t qbase = (size_t)row * h * Dk;
+#pragma unroll
+    for (int hh = 0; hh < HMAX; ++hh)
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int k = lane + 32 * e;
+        q[hh][e] = (hh < h && k < Dk) ? ld_elt(a.Q, qbase + (size_t)hh * Dk + k, dt) : 0.f;
+      }
+    // ---- gates ---------------------------------------------------------------------------------
+    Gate3 gt;
+    if (a.gates_in) {
+      gt = {a.gates_in[(size_t)row * 3], a.gates_in[(size_t)row * 3 + 1], a.gates_in[(size_t)row * 3 + 2]};
+    } else {
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int k = lane + 32 * e;
+        float m = 0.f;
+#pragma unroll
+        for (int hh = 0; hh < HMAX; ++hh) m += q[hh][e];
+        if (k < Dk) qgp[k] = m / (float)h;  // q_gp = mean over heads (nsa_attention.py:1357)
+      }
+      __syncwarp();
+      gt = gate_forward_warp(qgp, xs, nullptr, a.gp, Dk, dm.gate_hidden, dm.gate_tau, dm.gate_mode, nullptr);
+      __syncwarp();
+    }
+    if (a.gates_out && lane == 0) {
+      a.gates_out[(size_t)row * 3] = gt.c;
+      a.gates_out[(size_t)row * 3 + 1] = gt.s;
+      a.gates_out[(size_t)row * 3 + 2] = gt.w;
+    }
+    float out[HMAX][EPT];
+#pragma unroll
+    for (int hh = 0; hh < HMAX; ++hh)
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) out[hh][e] = 0.f;
+
+    const int32_t* rrow = a.ranges ? a.ranges + (size_t)row * dm.n_ranges * 2 : nullptr;
+#pragma unroll 1
+    for (int br = 0; br < 3; ++br) {
+      if (!(a.branch_mask & (1 << br))) continue;
+      const float gb = br == 0 ? gt.c : (br == 1 ? gt.s : gt.w);
+      float m[HMAX], ls[HMAX], acc[HMAX][EPT];
+#pragma unroll
+      for (int hh = 0; hh < HMAX; ++hh) {
+        m[hh] = -INFINITY;
+        ls[hh] = 0.f;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) acc[hh][e] = 0.f;
+      }
+      const size_t slab = (size_t)(b * dm.G + g) * branch_cap(dm, br);
+      const int np = (br == 1 && !rrow) ? 0 : branch_pieces(dm, br);
+      for (int pi = 0; pi < np; ++pi) {
+        int a0, a1;
+        branch_piece(dm, br, t, rrow, pi, a0, a1);
+        for (int key = a0; key < a1; ++key) {
+          float kk[EPT], vv[EPT];
+          const size_t kr = (slab + key) * Dk, vr = (slab + key) * Dv;
+#pragma unroll
+          for (int e = 0; e < EPT; ++e) {
+            const int k = lane + 32 * e;
+            kk[e] = k < Dk ? ld_elt(a.K[br], kr + k, dt) : 0.f;
+            vv[e] = k < Dv ? ld_elt(a.V[br], vr + k, dt) : 0.f;
+          }
+#pragma unroll
+          for (int hh = 0; hh < HMAX; ++hh) {
+            if (hh < h) {
+              float part = 0.f;
+#pragma unroll
+              for (int e = 0; e < EPT; ++e) part = fmaf(q[hh][e], kk[e], part);
+              const float sc = warp_sum(part) * dm.scale;
+              const float mn = fmaxf(m[hh], sc);
+              const float al = expf(m[hh] - mn);  // exp(-inf) = 0 on the first key
+              const float p = expf(sc - mn);
+              ls[hh] = ls[hh] * al + p;
+#pragma unroll
+              for (int e = 0; e < EPT; ++e) acc[hh][e] = fmaf(p, vv[e], acc[hh][e] * al);
+              m[hh] = mn;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int hh = 0; hh < HMAX; ++hh) {
+        if (hh < h) {
+          const float inv = ls[hh] > 0.f ? 1.0f / ls[hh] : 0.f;  // empty row -> zeros (attention_kernels.py:769-771)
+          if (a.lse && lane == 0)
+            a.lse[(size_t)br * rows_h + (size_t)row * h + hh] = ls[hh] > 0.f ? m[hh] + logf(ls[hh]) : -INFINITY;
+#pragma unroll
+          for (int e = 0; e < EPT; ++e) {
+            const float o = acc[hh][e] * inv;
+            const int k = lane + 32 * e;
+            if (a.O_br && k < Dv) st_elt(a.O_br, ((size_t)br * rows_h + (size_t)row * h + hh) * Dv + k, dt, o);
+            out[hh][e] = fmaf(gb, o, out[hh][e]);
+          }
+        }
+      }
+    }
+    if (a.O) {
+#pragma unroll
+      for (int hh = 0; hh < HMAX; ++hh)
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          const int k = lane + 32 * e;
+          if (hh < h && k < Dv) st_elt(a.O, ((size_t)row * h + hh) * Dv + k, dt, out[hh][e]);
+        }
+    }
+    __syncwarp();
+  }
+}
+
+template <int HMAX, int EPT>
+static int launch_fwd_t(const nsa_dims_t& dm, const FwdArgs& a, cudaStream_t stream) {
+  const int n_rows = dm.B * dm.S * dm.G;
+  int blocks = ceil_div(n_rows, kAttnWarps);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  size_t smem = (size_t)kAttnWarps * (dm.Dk + 2 * dm.gate_hidden) * sizeof(float);
+  fwd_generic_kernel<HMAX, EPT><<<blocks, kAttnWarps * 32, smem, stream>>>(dm, a);
+  return check_launch("fwd_generic_kernel");
+}
+
+#define NSA_DISPATCH_HE(FN, ...)                                                      \
+  do {                                                                                \
+    const int dmax = dm.Dk > dm.Dv ? dm.Dk : dm.Dv;                                   \
+    const int ept = dmax <= 32 ? 1 : (dmax <= 64 ? 2 : 4);                            \
+    const int hm = dm.h <= 4 ? 4 : (dm.h <= 8 ? 8 : 16);                              \
+    if (hm == 4 && ept == 1) return FN<4, 1>(__VA_ARGS__);                            \
+    if (hm == 4 && ept == 2) return FN<4, 2>(__VA_ARGS__);                            \
+    if (hm == 4 && ept == 4) return FN<4, 4>(__VA_ARGS__);                            \
+    if (hm == 8 && ept == 1) return FN<8, 1>(__VA_ARGS__);                            \
+    if (hm == 8 && ept == 2) return FN<8, 2>(__VA_ARGS__);                            \
+    if (hm == 8 && ept == 4) return FN<8, 4>(__VA_ARGS__);                            \
+    if (hm == 16 && ept == 1) return FN<16, 1>(__VA_ARGS__);                          \
+    if (hm == 16 && ept == 2) return FN<16, 2>(__VA_ARGS__);                          \
+    return FN<16, 4>(__VA_ARGS__);                                                    \
+  } while (0)
+
+int launch_fwd_generic(const nsa_dims_t& dm, const FwdArgs& a, cudaStream_t stream) {
+  if (dm.B * dm.S * dm.G == 0) return NSA_OK;
+  NSA_REQUIRE(dm.h >= 1 && dm.h <= 16, "attention(simt): h=%d outside [1,16]", dm.h);
+  NSA_REQUIRE(dm.Dk >= 1 && dm.Dk <= 128 && dm.Dv >= 1 && dm.Dv <= 128, "attention(simt): Dk=%d Dv=%d outside [1,128]",
+              dm.Dk, dm.Dv);
+  NSA_REQUIRE(dm.gate_hidden >= 0 && dm.gate_hidden <= 1024, "gate_hidden=%d", dm.gate_hidden);
+  NSA_DISPATCH_HE(launch_fwd_t, dm, a, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attention over key ranges, analytical backward (flash-style recompute from the saved LSE).
+//   dV = P^T dO, dP = dO V^T, dS = P o (dP - rowsum(dO o O)), dQ = dS K scale, dK = dS^T Q scale
+// (the reference's _selection_attention_backward, kernels/triton_sel_kernel/__init__.py:163-231, without
+// its first-key-only line).  dK/dV are scatter-added with fp32 atomics because many rows share a key.
+// ------------------------------------------------------------------------------------------------
+
+template <int HMAX, int EPT>
+__global__ void __launch_bounds__(kAttnWarps * 32)
+bwd_generic_kernel(nsa_dims_t dm, BwdArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_rows = dm.B * dm.S * dm.G;
+  const int dt = dm.dtype, h = dm.h, Dk = dm.Dk, Dv = dm.Dv;
+  const size_t rows_h = (size_t)n_rows * h;
+  for (int row = blockIdx.x * kAttnWarps + warp; row < n_rows; row += gridDim.x * kAttnWarps) {
+    const int g = row % dm.G, s = (row / dm.G) % dm.S, b = row / (dm.G * dm.S);
+    const int t = dm.t0 + s;
+    float q[HMAX][EPT], dO[HMAX][EPT], dq[HMAX][EPT];
+#pragma unroll
+    for (int hh = 0; hh < HMAX; ++hh)
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int k = lane + 32 * e;
+        q[hh][e] = (hh < h && k < Dk) ? ld_elt(a.Q, ((size_t)row * h + hh) * Dk + k, dt) : 0.f;
+        dO[hh][e] = (hh < h && k < Dv) ? ld_elt(a.dO, ((size_t)row * h + hh) * Dv + k, dt) : 0.f;
+        dq[hh][e] = 0.f;
+      }
+    const int32_t* rrow = a.ranges ? a.ranges + (size_t)row * dm.n_ranges * 2 : nullptr;
+#pragma unroll 1
+    for (int br = 0; br < 3; ++br) {
+      if (!(a.branch_mask & (1 << br))) continue;
+      const float gb = a.gates ? a.gates[(size_t)row * 3 + br] : 1.0f;
+      float delta[HMAX], lse[HMAX];
+      float dg = 0.f;
+#pragma unroll
+      for (int hh = 0; hh < HMAX; ++hh) {
+        float part = 0.f;
+        if (hh < h) {
+#pragma unroll
+          for (int e = 0; e < EPT; ++e) {
+            const int k = lane + 32 * e;
+            if (k < Dv) part = fmaf(dO[hh][e], ld_elt(a.O_br, ((size_t)br * rows_h + (size_t)row * h + hh) * Dv + k, dt), part);
+          }
+        }
+        part = warp_sum(part);
+        dg += part;              // d gate_b = sum_{h,d} dO * O_b
+        delta[hh] = gb * part;   // rowsum(dO_b o O_b) with dO_b = g_b dO
+        lse[hh] = hh < h ? a.lse[(size_t)br * rows_h + (size_t)row * h + hh] : -INFINITY;
+      }
+      if (a.dgates && lane == 0) a.dgates[(size_t)row * 3 + br] = dg;
+      if (gb == 0.f) continue;  // forced-branch gates: nothing flows into this branch
+      const size_t slab = (size_t)(b * dm.G + g) * branch_cap(dm, br);
+      const int np = (br == 1 && !rrow) ? 0 : branch_pieces(dm, br);
+      for (int pi = 0; pi < np; ++pi) {
+        int a0, a1;
+        branch_piece(dm, br, t, rrow, pi, a0, a1);
+        for (int key = a0; key < a1; ++key) {
+          float kk[EPT], vv[EPT], dk[EPT], dv[EPT];
+          const size_t kr = (slab + key) * Dk, vr = (slab + key) * Dv;
+#pragma unroll
+          for (int e = 0; e < EPT; ++e) {
+            const int k = lane + 32 * e;
+            kk[e] = k < Dk ? ld_elt(a.K[br], kr + k, dt) : 0.f;
+            vv[e] = k < Dv ? ld_elt(a.V[br], vr + k, dt) : 0.f;
+            dk[e] = 0.f;
+            dv[e] = 0.f;
+          }
+#pragma unroll
+          for (int hh = 0; hh < HMAX; ++hh) {
+            if (hh < h) {
+              float ps = 0.f, pd = 0.f;
+#pragma unroll
+              for (int e = 0; e < EPT; ++e) {
+                ps = fmaf(q[hh][e], kk[e], ps);
+                pd = fmaf(dO[hh][e], vv[e], pd);
+              }
+              const float sc = warp_sum(ps) * dm.scale;
+              const float dp = gb * warp_sum(pd);
+              const float p = isinf(lse[hh]) ? 0.f : expf(sc - lse[hh]);
+              const float ds = p * (dp - delta[hh]) * dm.scale;
+              const float pg = p * gb;
+#pragma unroll
+              for (int e = 0; e < EPT; ++e) {
+                dq[hh][e] = fmaf(ds, kk[e], dq[hh][e]);
+                dk[e] = fmaf(ds, q[hh][e], dk[e]);
+                dv[e] = fmaf(pg, dO[hh][e], dv[e]);
+              }
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < EPT; ++e) {
+            const int k = lane + 32 * e;
+            if (k < Dk) atomicAdd(a.dK[br] + kr + k, dk[e]);
+            if (k < Dv) atomicAdd(a.dV[br] + vr + k, dv[e]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int hh = 0; hh < HMAX; ++hh)
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int k = lane + 32 * e;
+        if (hh < h && k < Dk) a.dQ[((size_t)row * h + hh) * Dk + k] += dq[hh][e];  // row owned by this warp
+      }
+  }
+}
+
+template <int HMAX, int EPT>
+static int launch_bwd_t(const nsa_dims_t& dm, const BwdArgs& a, cudaStream_t stream) {
+  const int n_rows = dm.B * dm.S * dm.G;
+  int blocks = ceil_div(n_rows, kAttnWarps);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  bwd_generic_kernel<HMAX, EPT><<<blocks, kAttnWarps * 32, 0, stream>>>(dm, a);
+  return check_launch("bwd_generic_kernel");
+}
+
+int launch_bwd_generic(const nsa_dims_t& dm, const BwdArgs& a, cudaStream_t stream) {
+  if (dm.B * dm.S * dm.G == 0) return NSA_OK;
+  NSA_REQUIRE(dm.h >= 1 && dm.h <= 16, "attention bwd(simt): h=%d outside [1,16]", dm.h);
+  NSA_REQUIRE(dm.Dk <= 128 && dm.Dv <= 128, "attention bwd(simt): Dk=%d Dv=%d", dm.Dk, dm.Dv);
+  NSA_DISPATCH_HE(launch_bwd_t, dm, a, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gate forward (standalone) and backward.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kAttnWarps * 32)
+gate_fwd_kernel(nsa_dims_t dm, const void* __restrict__ Q, nsa_gate_params_t gp, float* __restrict__ gates) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* qgp = smem + (size_t)warp * (dm.Dk + 2 * dm.gate_hidden);
+  float* xs = qgp + dm.Dk;
+  const int n_rows = dm.B * dm.S * dm.G;
+  for (int row = blockIdx.x * kAttnWarps + warp; row < n_rows; row += gridDim.x * kAttnWarps) {
+    for (int k = lane; k < dm.Dk; k += 32) {
+      float m = 0.f;
+      for (int hh = 0; hh < dm.h; ++hh) m += ld_elt(Q, ((size_t)row * dm.h + hh) * dm.Dk + k, dm.dtype);
+      qgp[k] = m / (float)dm.h;
+    }
+    __syncwarp();
+    Gate3 gt = gate_forward_warp(qgp, xs, nullptr, gp, dm.Dk, dm.gate_hidden, dm.gate_tau, dm.gate_mode, nullptr);
+    if (lane == 0) {
+      gates[(size_t)row * 3] = gt.c;
+      gates[(size_t)row * 3 + 1] = gt.s;
+      gates[(size_t)row * 3 + 2] = gt.w;
+    }
+    __syncwarp();
+  }
+}
+
+int launch_gate_fwd(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t& gp, float* gates, cudaStream_t stream) {
+  const int n_rows = dm.B * dm.S * dm.G;
+  if (n_rows == 0) return NSA_OK;
+  int blocks = ceil_div(n_rows, kAttnWarps);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  size_t smem = (size_t)kAttnWarps * (dm.Dk + 2 * dm.gate_hidden) * sizeof(float);
+  gate_fwd_kernel<<<blocks, kAttnWarps * 32, smem, stream>>>(dm, Q, gp, gates);
+  return check_launch("gate_fwd_kernel");
+}
+
+// Backward: recompute the MLP per row, accumulate parameter gradients in shared memory per CTA, flush with
+// one atomicAdd per parameter per CTA.
+__global__ void __launch_bounds__(kAttnWarps * 32)
+gate_bwd_kernel(nsa_dims_t dm, const void* __restrict__ Q, nsa_gate_params_t gp, const float* __restrict__ dgates,
+                float* __restrict__ dQ, float* d_fc1_w, float* d_fc1_b, float* d_fc2_w, float* d_fc2_b) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Dk = dm.Dk, H = dm.gate_hidden;
+  float* a_w1 = smem;             // [H*Dk]
+  float* a_b1 = a_w1 + H * Dk;    // [H]
+  float* a_w2 = a_b1 + H;         // [3*H]
+  float* a_b2 = a_w2 + 3 * H;     // [3] (+1 pad)
+  float* wbase = a_b2 + 4 + (size_t)warp * (Dk + 3 * H);
+  float* qgp = wbase;             // [Dk]
+  float* xs = qgp + Dk;           // [H]
+  float* pre = xs + H;            // [H]
+  float* dpre = pre + H;          // [H]
+  const int nacc = H * Dk + H + 3 * H + 4;
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) smem[i] = 0.f;
+  __syncthreads();
+  const int n_rows = dm.B * dm.S * dm.G;
+  const float inv_tau = 1.0f / fmaxf(dm.gate_tau, 1e-6f);
+  for (int row = blockIdx.x * kAttnWarps + warp; row < n_rows; row += gridDim.x * kAttnWarps) {
+    for (int k = lane; k < Dk; k += 32) {
+      float m = 0.f;
+      for (int hh = 0; hh < dm.h; ++hh) m += ld_elt(Q, ((size_t)row * dm.h + hh) * Dk + k, dm.dtype);
+      qgp[k] = m / (float)dm.h;
+    }
+    __syncwarp();
+    bool peaked = false;
+    Gate3 gt = gate_forward_warp(qgp, xs, pre, gp, Dk, H, dm.gate_tau, NSA_GATE_MLP, &peaked);
+    __syncwarp();
+    if (!peaked) {  // the hard one-hot is a constant: no gradient (torch.where(peaked, one_hot, p))
+      const float p[3] = {gt.c, gt.s, gt.w};
+      const float dp[3] = {dgates[(size_t)row * 3], dgates[(size_t)row * 3 + 1], dgates[(size_t)row * 3 + 2]};
+      const float dot = p[0] * dp[0] + p[1] * dp[1] + p[2] * dp[2];
+      float dg[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dg[c] = p[c] * (dp[c] - dot) * inv_tau;
+      if (lane < 3) atomicAdd(a_b2 + lane, dg[lane]);
+      for (int u = lane; u < H; u += 32) {
+        float dx = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          atomicAdd(a_w2 + c * H + u, dg[c] * xs[u]);
+          dx = fmaf(gp.fc2_w[c * H + u], dg[c], dx);
+        }
+        const float z = pre[u];
+        const float sg = 1.0f / (1.0f + expf(-z));
+        const float d = dx * sg * (1.0f + z * (1.0f - sg));  // d silu
+        dpre[u] = d;
+        atomicAdd(a_b1 + u, d);
+      }
+      __syncwarp();
+      for (int u = 0; u < H; ++u) {
+        const float d = dpre[u];
+        for (int k = lane; k < Dk; k += 32) atomicAdd(a_w1 + u * Dk + k, d * qgp[k]);
+      }
+      if (dQ) {
+        for (int k = lane; k < Dk; k += 32) {
+          float dqg = 0.f;
+          for (int u = 0; u < H; ++u) dqg = fmaf(gp.fc1_w[(size_t)u * Dk + k], dpre[u], dqg);
+          dqg /= (float)dm.h;
+          for (int hh = 0; hh < dm.h; ++hh) dQ[((size_t)row * dm.h + hh) * Dk + k] += dqg;  // row owned by this warp
+        }
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H * Dk; i += blockDim.x) atomicAdd(d_fc1_w + i, a_w1[i]);
+  for (int i = threadIdx.x; i < H; i += blockDim.x) atomicAdd(d_fc1_b + i, a_b1[i]);
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) atomicAdd(d_fc2_w + i, a_w2[i]);
+  for (int i = threadIdx.x; i < 3; i += blockDim.x) atomicAdd(d_fc2_b + i, a_b2[i]);
+}
+
+int launch_gate_bwd(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t& gp, const float* dgates, float* dQ,
+                    float* d_fc1_w, float* d_fc1_b, float* d_fc2_w, float* d_fc2_b, cudaStream_t stream) {
+  const int n_rows = dm.B * dm.S * dm.G;
+  if (n_rows == 0 || dm.gate_mode != NSA_GATE_MLP) return NSA_OK;
+  const int H = dm.gate_hidden, Dk = dm.Dk;
+  size_t smem = ((size_t)H * Dk + H + 3 * H + 4 + (size_t)kAttnWarps * (Dk + 3 * H)) * sizeof(float);
+  NSA_REQUIRE(smem <= 200 * 1024, "gate bwd: hidden=%d Dk=%d needs %zu B of shared memory", H, Dk, smem);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(gate_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("gate bwd: smem attr: %s", cudaGetErrorString(e)); return NSA_ERR_CUDA; }
+  }
+  int blocks = ceil_div(n_rows, kAttnWarps * 8);
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  if (blocks < 1) blocks = 1;
+  gate_bwd_kernel<<<blocks, kAttnWarps * 32, smem, stream>>>(dm, Q, gp, dgates, dQ, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b);
+  return check_launch("gate_bwd_kernel");
+}
+
+}  // namespace nsa

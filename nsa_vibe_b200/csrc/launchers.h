@@ -1,0 +1,59 @@
+// Internal launcher declarations shared by api.cu and the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+namespace nsa {
+
+struct FwdArgs {
+  const void *Q, *K[3], *V[3];  // index = branch: 0 cmp, 1 sel, 2 win
+  const int32_t* ranges;
+  nsa_gate_params_t gp;
+  const float* gates_in;  // optional precomputed gates [rows,3]
+  void* O;                // combined output (may be NULL)
+  float* lse;             // [3][rows][h] (may be NULL)
+  float* gates_out;       // [rows,3] (may be NULL)
+  void* O_br;             // [3][rows][h][Dv] (may be NULL)
+  int branch_mask;
+};
+
+struct BwdArgs {
+  const void *Q, *K[3], *V[3];
+  const int32_t* ranges;
+  const void* O_br;     // [3][rows][h][Dv] saved branch outputs
+  const float* lse;     // [3][rows][h]
+  const float* gates;   // [rows][3]; NULL -> every enabled branch has weight 1 (single-branch API)
+  const void* dO;       // [rows][h][Dv]
+  float *dQ, *dK[3], *dV[3];
+  float* dgates;        // [rows][3] (may be NULL)
+  int branch_mask;
+};
+
+// select.cu
+int launch_select(const float* p_grp, int n_rows, int S_rows, int G, int S_sel, int l_sel, int n_sel, int mode, int nf,
+                  int K, int t0, int32_t* ranges, cudaStream_t stream);
+// generic.cu (SIMT)
+int launch_score_generic(const nsa_dims_t& dm, const void* Q, const void* Kc, int S_sel, int S_total, int sel_mode, int Kr,
+                         float* p_grp, int32_t* ranges, cudaStream_t stream);
+int launch_fwd_generic(const nsa_dims_t& dm, const FwdArgs& a, cudaStream_t stream);
+int launch_bwd_generic(const nsa_dims_t& dm, const BwdArgs& a, cudaStream_t stream);
+int launch_gate_fwd(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t& gp, float* gates, cudaStream_t stream);
+int launch_gate_bwd(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t& gp, const float* dgates, float* dQ,
+                    float* d_fc1_w, float* d_fc1_b, float* d_fc2_w, float* d_fc2_b, cudaStream_t stream);
+// tc_*.cu (tcgen05 / TMA kernels)
+bool tc_supported(const nsa_dims_t& dm);
+bool tc_score_supported(const nsa_dims_t& dm);
+bool tc_decode_supported(const nsa_dims_t& dm);
+int64_t tc_score_workspace(const nsa_dims_t& dm);
+int64_t tc_decode_workspace(const nsa_dims_t& dm);
+int launch_score_tc(const nsa_dims_t& dm, const void* Q, const void* Kc, int S_sel, int S_total, int sel_mode, int Kr,
+                    float* p_grp, int32_t* ranges, void* workspace, cudaStream_t stream);
+int launch_branch_tc(const nsa_dims_t& dm, int branch, const void* Q, const void* K, const void* V, const int32_t* ranges,
+                     void* O_b, float* lse_b, cudaStream_t stream);
+int launch_prefill_tc(const nsa_dims_t& dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
+                      const void* V_win, const void* K_cmp, const void* V_cmp, const int32_t* ranges,
+                      const nsa_gate_params_t& gp, void* O, float* lse, float* gates, void* O_branches, cudaStream_t stream);
+int launch_decode_tc(const nsa_dims_t& dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
+                     const void* V_win, const void* K_cmp, const void* V_cmp, const nsa_gate_params_t& gp, void* O,
+                     int32_t* ranges_out, void* workspace, cudaStream_t stream);
+
+}  // namespace nsa

@@ -1,0 +1,166 @@
+// Warp-level top-n block selection and range merging (NSA Eq.11-12 as the reference implements it).
+//
+// One warp owns one (b, t, g) row of p_grp.  Restates, for one row:
+//   prefill: select_topn_ranges_batched + convert_indices_to_ranges_batched_v2
+//            (nsa/core/selection_scorer.py:255-362, :434-605)
+//   decode : select_topn_ranges (selection_scorer.py:124-249)
+// The selected block ids are kept as a bitmap spread over the warp, so "sort, drop duplicates, merge
+// adjacent blocks" is simply "find runs of set bits".
+#pragma once
+#include "common.cuh"
+
+namespace nsa {
+
+constexpr int kSelMaxWords = 4;  // bitmap words per lane -> S_sel <= 4096 blocks (262144 tokens at l_sel=64)
+
+__host__ __device__ inline int prefill_forced_cols(int S_total, int l_sel) {
+  // the reference drops duplicate forced COLUMNS (unique_consecutive(dim=-1), selection_scorer.py:299-300)
+  return S_total <= l_sel ? 1 : (S_total <= 2 * l_sel ? 2 : 3);
+}
+
+__host__ __device__ inline int prefill_range_cols(int S_total, int l_sel, int n_sel) {
+  int S_sel = S_total <= 0 ? 0 : (S_total + l_sel - 1) / l_sel;
+  if (n_sel >= S_sel) return S_sel;
+  int nf = prefill_forced_cols(S_total, l_sel);
+  int k_rest = n_sel - nf > 0 ? n_sel - nf : 0;
+  if (k_rest > 0) return nf + (k_rest < S_sel ? k_rest : S_sel);
+  return nf < n_sel ? nf : n_sel;
+}
+
+__device__ __forceinline__ void bitmap_set(uint32_t (&bm)[kSelMaxWords], int lane, int j) {
+  int word = j >> 5;
+  if ((word & 31) == lane) bm[word >> 5] |= 1u << (j & 31);
+}
+
+// `sc`: this warp's copy of the row (S_sel floats in shared memory, clobbered).
+// mode 0 = prefill rule, 1 = decode rule.  Writes out[K][2] (int32 token ranges, [0,0] padded).
+__device__ inline void select_row_warp(float* sc, int S_sel, int l_sel, int n_sel, int mode, int nf, int K, int t,
+                                       int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const float NEG = -INFINITY;
+  uint32_t bm[kSelMaxWords];
+#pragma unroll
+  for (int i = 0; i < kSelMaxWords; ++i) bm[i] = 0u;
+
+  int nvalid = (t + 1) / l_sel;
+  if (nvalid > S_sel) nvalid = S_sel;
+  const int cb = t / l_sel;
+  const int cb1 = cb > 0 ? cb - 1 : 0;
+
+  if (mode == 0 && n_sel >= S_sel) {
+    // selection_scorer.py:348-354: n_top >= S_sel -> exactly all complete blocks [0, nvalid).
+    // bitmap word w (ids 32w..32w+31) is owned by lane w % 32, slot w / 32.
+    for (int w = lane; w * 32 < nvalid; w += 32) {
+      int rem = nvalid - w * 32;
+      bm[w >> 5] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+    }
+  } else {
+    // forced ids (sorted ascending): prefill keeps nf distinct columns, decode always three
+    int forced[3];
+    int nfc;
+    if (mode == 0) {
+      nfc = nf;
+      if (nf == 1) { forced[0] = 0; forced[1] = 0; forced[2] = 0; }
+      else if (nf == 2) { forced[0] = 0; forced[1] = cb; forced[2] = cb; }
+      else { forced[0] = 0; forced[1] = cb1; forced[2] = cb; }
+    } else {
+      nfc = 3;
+      forced[0] = 0; forced[1] = cb1; forced[2] = cb;
+    }
+    const int k_rest = n_sel - nfc > 0 ? n_sel - nfc : 0;
+    // forced members of the selection
+    int take = nfc;
+    if (mode == 0 && k_rest == 0) take = nfc < n_sel ? nfc : n_sel;  // forced[..., :n_top]
+    for (int i = 0; i < take; ++i) {
+      int j = forced[i];
+      bool ok = mode == 0 ? (j < nvalid) : (j < S_sel);  // prefill drops incomplete blocks (:343-347)
+      if (ok) bitmap_set(bm, lane, j);
+    }
+    if (k_rest > 0) {
+      const int k_act = k_rest < S_sel ? k_rest : S_sel;
+      // composite = fp32(p) - fp32(fp32(j) * 1e-8f): two separately rounded fp32 ops (:182-184, :312-318)
+      float best = NEG;
+      int best_j = 0x7fffffff;
+      for (int j = lane; j < S_sel; j += 32) {
+        float c = NEG;
+        if (j < nvalid && j != forced[0] && j != forced[1] && j != forced[2])
+          c = __fsub_rn(sc[j], __fmul_rn((float)j, 1e-8f));
+        sc[j] = c;
+        if (c > best) { best = c; best_j = j; }  // ascending j: first maximum = lowest index
+      }
+      for (int it = 0; it < k_act; ++it) {
+        float v = best;
+        int vj = best_j;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          float ov = __shfl_xor_sync(0xffffffffu, v, o);
+          int oj = __shfl_xor_sync(0xffffffffu, vj, o);
+          if (ov > v || (ov == v && oj < vj)) { v = ov; vj = oj; }
+        }
+        if (!(v > NEG)) break;  // only -inf left: invalid picks are dropped in both modes
+        bitmap_set(bm, lane, vj);
+        if ((vj & 31) == lane) {  // owner rescans its strided elements
+          sc[vj] = NEG;
+          best = NEG;
+          best_j = 0x7fffffff;
+          for (int j = lane; j < S_sel; j += 32) {
+            float c = sc[j];
+            if (c > best) { best = c; best_j = j; }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- runs of set bits -> [start,end) ranges -------------------------------------------------
+  int nstart_before = 0, nend_before = 0;
+  const int nwords = (S_sel + 31) >> 5;
+  uint32_t prev_hi = 0;  // bit 31 of lane 31's word in the previous slot
+#pragma unroll
+  for (int s = 0; s < kSelMaxWords; ++s) {
+    if (s * 32 >= nwords) break;
+    const uint32_t b = bm[s];
+    uint32_t left = __shfl_up_sync(0xffffffffu, b, 1);
+    uint32_t carry_in = (lane == 0 ? prev_hi : left) >> 31;
+    uint32_t right = __shfl_down_sync(0xffffffffu, b, 1);
+    uint32_t next_first = (s + 1 < kSelMaxWords) ? bm[s + 1] : 0u;
+    next_first = __shfl_sync(0xffffffffu, next_first, 0);
+    uint32_t carry_out = (lane == 31 ? next_first : right) & 1u;
+    uint32_t starts = b & ~((b << 1) | carry_in);
+    uint32_t ends = b & ~((b >> 1) | (carry_out << 31));
+    int ns = __popc(starts), ne = __popc(ends);
+    // exclusive prefix over lanes
+    int ps = ns, pe = ne;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int a = __shfl_up_sync(0xffffffffu, ps, o);
+      int c = __shfl_up_sync(0xffffffffu, pe, o);
+      if (lane >= o) { ps += a; pe += c; }
+    }
+    int is = nstart_before + ps - ns, ie = nend_before + pe - ne;
+    const int base_id = (s * 32 + lane) * 32;
+    while (starts) {
+      int bit = __ffs(starts) - 1;
+      starts &= starts - 1;
+      if (is < K) out[2 * is] = (base_id + bit) * l_sel;
+      ++is;
+    }
+    while (ends) {
+      int bit = __ffs(ends) - 1;
+      ends &= ends - 1;
+      int e = (base_id + bit + 1) * l_sel;
+      if (e > t + 1) e = t + 1;  // clamp to the causal limit (:242-246, :567-573)
+      if (ie < K) out[2 * ie + 1] = e;
+      ++ie;
+    }
+    nstart_before += __shfl_sync(0xffffffffu, ps, 31);
+    nend_before += __shfl_sync(0xffffffffu, pe, 31);
+    prev_hi = __shfl_sync(0xffffffffu, b, 31);
+  }
+  for (int i = nstart_before + lane; i < K; i += 32) {
+    out[2 * i] = 0;
+    out[2 * i + 1] = 0;
+  }
+}
+
+}  // namespace nsa

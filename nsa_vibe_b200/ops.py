@@ -1,0 +1,366 @@
+"""Tensor-level wrappers over the C ABI (include/nsa_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream; every op below launches hand-written
+sm_100a kernels through libnsa_b200.so on torch's current stream.  CPU tensors are rejected -- there is no
+fallback (BASELINE.json north_star).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from dataclasses import dataclass, field
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (GATE_CMP, GATE_MLP, GATE_SEL, GATE_UNIFORM, GATE_WIN, IMPL_AUTO, IMPL_SIMT, IMPL_TC,  # noqa: F401
+                   NORM_CAUSAL, NORM_FULL_ROW)
+
+_DTYPES = {torch.float32: _lib.NSA_F32, torch.bfloat16: _lib.NSA_BF16, torch.float16: _lib.NSA_F16}
+
+# how many kernels this process launched through the C ABI (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+@dataclass
+class NSAConfig:
+    """Static NSA geometry + switches for one module (nsa_attention.py:188-206 ctor arguments)."""
+    l: int = 32
+    d: int = 16
+    l_sel: int = 64
+    n_sel: int = 16
+    w: int = 512
+    gate_tau: float = 1.0
+    gate_mode: int = GATE_MLP
+    norm_mode: int = NORM_FULL_ROW
+    impl: int = IMPL_AUTO
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("nsa_vibe_b200 ops need CUDA tensors: the NSA hot path has no CPU fallback")
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _gate_struct(gate, dev):
+    """gate = (fc1_w, fc1_b, fc2_w, fc2_b) tensors (any float dtype) or None -> (GateParams, keepalive, hidden)."""
+    gp = _lib.GateParams()
+    if gate is None:
+        return gp, (), 0
+    keep = tuple(None if t is None else _c(t.detach().to(device=dev, dtype=torch.float32)) for t in gate)
+    gp.fc1_w, gp.fc1_b, gp.fc2_w, gp.fc2_b = (None if t is None else t.data_ptr() for t in keep)
+    return gp, keep, int(keep[0].shape[0])
+
+
+def make_dims(Q: torch.Tensor, cfg: NSAConfig, *, t0: int = 0, K_sel=None, K_win=None, K_cmp=None, V=None,
+              S_sel_kv=None, S_win_kv=None, S_cmp=None, win_off: int = 0, n_ranges: int = 0, gate_hidden: int = 0,
+              Dv: Optional[int] = None) -> _lib.Dims:
+    B, S, G, h, Dk = Q.shape
+    dm = _lib.Dims()
+    dm.B, dm.S, dm.G, dm.h, dm.Dk = B, S, G, h, Dk
+    dm.Dv = int(Dv if Dv is not None else (V.shape[-1] if V is not None else Dk))
+    dm.l, dm.d, dm.l_sel, dm.n_sel, dm.w = cfg.l, cfg.d, cfg.l_sel, cfg.n_sel, cfg.w
+    dm.t0 = int(t0)
+    dm.cap_sel = int(K_sel.shape[2]) if K_sel is not None else 0
+    dm.S_sel_kv = dm.cap_sel if S_sel_kv is None else int(S_sel_kv)
+    dm.cap_win = int(K_win.shape[2]) if K_win is not None else 0
+    dm.S_win_kv = dm.cap_win if S_win_kv is None else int(S_win_kv)
+    dm.win_off = int(win_off)
+    dm.cap_cmp = int(K_cmp.shape[2]) if K_cmp is not None else 0
+    dm.S_cmp = dm.cap_cmp if S_cmp is None else int(S_cmp)
+    dm.n_ranges = int(n_ranges)
+    dm.dtype = _DTYPES[Q.dtype]
+    dm.gate_mode, dm.gate_hidden, dm.norm_mode = int(cfg.gate_mode), int(gate_hidden), int(cfg.norm_mode)
+    dm.impl = int(os.environ.get("NSA_B200_IMPL", cfg.impl))
+    dm.gate_tau = float(cfg.gate_tau)
+    dm.scale = 1.0 / math.sqrt(Dk)
+    return dm
+
+
+def _call(name: str, *args):
+    global launch_count
+    lib = _lib.load()
+    rc = getattr(lib, name)(*args)
+    _lib.check(rc, name)
+    launch_count += 1
+
+
+def prefill_range_cols(S_total: int, l_sel: int, n_sel: int) -> int:
+    return int(_lib.load().nsa_prefill_range_cols(S_total, l_sel, n_sel))
+
+
+def num_sel_blocks(seq_len: int, l_sel: int) -> int:
+    return 0 if seq_len <= 0 else (seq_len + l_sel - 1) // l_sel
+
+
+# ----------------------------------------------------------------------------------------------------
+# (2) selection
+# ----------------------------------------------------------------------------------------------------
+def select_ranges_prefill(p_grp: torch.Tensor, l_sel: int, n_sel: int, S_total: Optional[int] = None, t0: int = 0) -> torch.Tensor:
+    """p_grp [B,S,G,S_sel] fp32 -> ranges [B,S,G,K,2] int32; bit-exact vs select_topn_ranges_batched
+    (nsa/core/selection_scorer.py:255-362)."""
+    _require_cuda(p_grp)
+    B, S, G, S_sel = p_grp.shape
+    S_total = S if S_total is None else S_total
+    p = _c(p_grp.detach().float())
+    K = prefill_range_cols(S_total, l_sel, n_sel)
+    out = torch.empty((B, S, G, K, 2), dtype=torch.int32, device=p.device)
+    if out.numel():
+        _call("nsa_select_ranges_prefill", _ptr(p), B, S, G, S_sel, l_sel, n_sel, S_total, t0, K, _ptr(out), _stream())
+    return out
+
+
+def select_ranges_decode(p_grp: torch.Tensor, l_sel: int, n_sel: int, t: int) -> torch.Tensor:
+    """p_grp [B,G,S_sel] fp32 -> ranges [B,G,n_sel,2] int32 (select_topn_ranges, selection_scorer.py:124-249)."""
+    _require_cuda(p_grp)
+    B, G, S_sel = p_grp.shape
+    p = _c(p_grp.detach().float())
+    out = torch.empty((B, G, n_sel, 2), dtype=torch.int32, device=p.device)
+    if out.numel():
+        _call("nsa_select_ranges_decode", _ptr(p), B, G, S_sel, l_sel, n_sel, int(t), _ptr(out), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# (1) scoring
+# ----------------------------------------------------------------------------------------------------
+def score_pgrp(Q: torch.Tensor, K_cmp: torch.Tensor, cfg: NSAConfig, *, t0: int = 0, S_sel: Optional[int] = None) -> torch.Tensor:
+    """Q [B,S,G,h,Dk], K_cmp [B,G,S_cmp,Dk] -> p_grp [B,S,G,S_sel] fp32 (Eq.8-10)."""
+    _require_cuda(Q, K_cmp)
+    Q, K_cmp = _c(Q.detach()), _c(K_cmp.detach())
+    B, S, G, h, Dk = Q.shape
+    if S_sel is None:
+        S_sel = num_sel_blocks(t0 + S, cfg.l_sel)
+    dm = make_dims(Q, cfg, t0=t0, K_cmp=K_cmp)
+    out = torch.empty((B, S, G, S_sel), dtype=torch.float32, device=Q.device)
+    if out.numel():
+        _call("nsa_score", C.byref(dm), _ptr(Q), _ptr(K_cmp), S_sel, _ptr(out), _stream())
+    return out
+
+
+def score_select(Q: torch.Tensor, K_cmp: torch.Tensor, cfg: NSAConfig, *, mode: int = 0, t0: int = 0,
+                 S_total: Optional[int] = None, S_sel: Optional[int] = None, S_cmp: Optional[int] = None) -> torch.Tensor:
+    """Fused scoring + selection -> ranges [B,S,G,K,2] int32.  mode 0: batched-prefill rule, 1: decode rule."""
+    _require_cuda(Q, K_cmp)
+    Q, K_cmp = _c(Q.detach()), _c(K_cmp.detach())
+    B, S, G, h, Dk = Q.shape
+    S_total = t0 + S if S_total is None else S_total
+    if S_sel is None:
+        S_sel = num_sel_blocks(max(S_total, cfg.l_sel), cfg.l_sel)
+    K = prefill_range_cols(S_total, cfg.l_sel, cfg.n_sel) if mode == 0 else cfg.n_sel
+    dm = make_dims(Q, cfg, t0=t0, K_cmp=K_cmp, n_ranges=K, S_cmp=S_cmp)
+    out = torch.zeros((B, S, G, K, 2), dtype=torch.int32, device=Q.device)
+    ws_bytes = int(_lib.load().nsa_workspace_bytes(C.byref(dm), _lib.WS_SCORE_SELECT))
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=Q.device)
+    if out.numel():
+        _call("nsa_score_select", C.byref(dm), _ptr(Q), _ptr(K_cmp), S_sel, S_total, mode, _ptr(out), _ptr(ws), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# (3)(4) single-branch attention with autograd
+# ----------------------------------------------------------------------------------------------------
+BR_CMP, BR_SEL, BR_WIN = 0, 1, 2
+
+
+def _branch_dims(branch, Q, K, V, cfg, ranges, t0, win_off):
+    kw = dict(t0=t0, V=V, n_ranges=0 if ranges is None else ranges.shape[3])
+    if branch == BR_CMP:
+        return make_dims(Q, cfg, K_cmp=K, **kw)
+    if branch == BR_SEL:
+        return make_dims(Q, cfg, K_sel=K, **kw)
+    return make_dims(Q, cfg, K_win=K, win_off=win_off, **kw)
+
+
+class _BranchAttn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Q, K, V, ranges, branch, cfg, t0, win_off):
+        Qc, Kc, Vc = _c(Q), _c(K), _c(V)
+        rg = None if ranges is None else _c(ranges.to(torch.int32))
+        dm = _branch_dims(branch, Qc, Kc, Vc, cfg, rg, t0, win_off)
+        B, S, G, h, _ = Qc.shape
+        O = torch.empty((B, S, G, h, Vc.shape[-1]), dtype=Qc.dtype, device=Qc.device)
+        lse = torch.empty((B, S, G, h), dtype=torch.float32, device=Qc.device)
+        if O.numel():
+            _call("nsa_branch_attn_fwd", C.byref(dm), branch, _ptr(Qc), _ptr(Kc), _ptr(Vc), _ptr(rg), _ptr(O), _ptr(lse), _stream())
+        ctx.save_for_backward(Qc, Kc, Vc, rg if rg is not None else torch.empty(0, device=Qc.device), O, lse)
+        ctx.meta = (branch, cfg, t0, win_off, rg is not None)
+        ctx.mark_non_differentiable(lse)
+        return O, lse
+
+    @staticmethod
+    def backward(ctx, dO, _dlse):
+        Q, K, V, rg, O, lse = ctx.saved_tensors
+        branch, cfg, t0, win_off, has_r = ctx.meta
+        rg = rg if has_r else None
+        dm = _branch_dims(branch, Q, K, V, cfg, rg, t0, win_off)
+        dm.impl = IMPL_SIMT
+        dQ = torch.zeros(Q.shape, dtype=torch.float32, device=Q.device)
+        dK = torch.zeros(K.shape, dtype=torch.float32, device=Q.device)
+        dV = torch.zeros(V.shape, dtype=torch.float32, device=Q.device)
+        dOc = _c(dO.to(Q.dtype))
+        if O.numel():
+            _call("nsa_branch_attn_bwd", C.byref(dm), branch, _ptr(Q), _ptr(K), _ptr(V), _ptr(rg), _ptr(O), _ptr(lse),
+                  _ptr(dOc), _ptr(dQ), _ptr(dK), _ptr(dV), _stream())
+        return dQ.to(Q.dtype), dK.to(K.dtype), dV.to(V.dtype), None, None, None, None, None
+
+
+def branch_attention(branch: int, Q, K, V, cfg: NSAConfig, ranges=None, *, t0: int = 0, win_off: int = 0,
+                     return_lse: bool = False):
+    """True-softmax attention of one NSA branch (0 cmp, 1 sel, 2 win) with analytical backward."""
+    _require_cuda(Q, K, V, ranges)
+    O, lse = _BranchAttn.apply(Q, K, V, ranges, branch, cfg, t0, win_off)
+    return (O, lse) if return_lse else O
+
+
+# ----------------------------------------------------------------------------------------------------
+# (4) gate
+# ----------------------------------------------------------------------------------------------------
+def gate_forward(Q: torch.Tensor, gate, cfg: NSAConfig) -> torch.Tensor:
+    """GateMLP on q_gp = mean_h(Q): Q [B,S,G,h,Dk] -> gates [B,S,G,3] fp32 (nsa_attention.py:32-82)."""
+    _require_cuda(Q)
+    Qc = _c(Q.detach())
+    gp, keep, hid = _gate_struct(gate, Qc.device)
+    dm = make_dims(Qc, cfg, gate_hidden=hid)
+    B, S, G = Qc.shape[:3]
+    out = torch.empty((B, S, G, 3), dtype=torch.float32, device=Qc.device)
+    if out.numel():
+        _call("nsa_gate_fwd", C.byref(dm), _ptr(Qc), C.byref(gp), _ptr(out), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# fused hot path: prefill
+# ----------------------------------------------------------------------------------------------------
+class _PrefillCore(torch.autograd.Function):
+    """The drop-in for nsa_attention.py:1066-1398 (scores -> ranges -> three branches -> gated combine)."""
+
+    @staticmethod
+    def forward(ctx, Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, fc1_w, fc1_b, fc2_w, fc2_b, cfg, sel_mode, t0,
+                stopgrad_gates, ranges_in, geom):
+        Q, K_sel, V_sel, K_win, V_win = _c(Q), _c(K_sel), _c(V_sel), _c(K_win), _c(V_win)
+        K_cmp, V_cmp = _c(K_cmp), _c(V_cmp)
+        B, S, G, h, Dk = Q.shape
+        Dv = V_sel.shape[-1]
+        dev = Q.device
+        geom = dict(geom or {})
+        if ranges_in is None:
+            ranges = score_select(Q, K_cmp, cfg, mode=sel_mode, t0=t0, S_cmp=geom.get("S_cmp"))
+        else:
+            ranges = _c(ranges_in.to(torch.int32))
+        gate = (fc1_w, fc1_b, fc2_w, fc2_b) if fc1_w is not None else None
+        gp, keep, hid = _gate_struct(gate, dev)
+        dm = make_dims(Q, cfg, t0=t0, K_sel=K_sel, K_win=K_win, K_cmp=K_cmp, V=V_sel, n_ranges=ranges.shape[3],
+                       gate_hidden=hid, **geom)
+        need_grad = any(ctx.needs_input_grad[:11])
+        O = torch.empty((B, S, G, h, Dv), dtype=Q.dtype, device=dev)
+        gates = torch.empty((B, S, G, 3), dtype=torch.float32, device=dev)
+        lse = torch.empty((3, B, S, G, h), dtype=torch.float32, device=dev) if need_grad else None
+        O_br = torch.empty((3, B, S, G, h, Dv), dtype=Q.dtype, device=dev) if need_grad else None
+        if O.numel():
+            _call("nsa_prefill_fwd", C.byref(dm), _ptr(Q), _ptr(K_sel), _ptr(V_sel), _ptr(K_win), _ptr(V_win), _ptr(K_cmp),
+                  _ptr(V_cmp), _ptr(ranges), C.byref(gp), _ptr(O), _ptr(lse), _ptr(gates), _ptr(O_br), _stream())
+        if need_grad:
+            ctx.save_for_backward(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, ranges, lse, gates, O_br, *[k for k in keep if k is not None])
+            ctx.geom = geom
+            ctx.meta = (cfg, t0, hid, stopgrad_gates, gate is not None, [k is not None for k in keep],
+                        [None if t is None else t.dtype for t in (fc1_w, fc1_b, fc2_w, fc2_b)])
+        ctx.mark_non_differentiable(ranges, gates)
+        return O, ranges, gates
+
+    @staticmethod
+    def backward(ctx, dO, _dr, _dg):
+        Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, ranges, lse, gates, O_br, *gk = ctx.saved_tensors
+        cfg, t0, hid, stopgrad, has_gate, gmask, gdt = ctx.meta
+        dev = Q.device
+        dm = make_dims(Q, cfg, t0=t0, K_sel=K_sel, K_win=K_win, K_cmp=K_cmp, V=V_sel, n_ranges=ranges.shape[3], gate_hidden=hid,
+                       **ctx.geom)
+        f32 = dict(dtype=torch.float32, device=dev)
+        dQ = torch.zeros(Q.shape, **f32)
+        grads = [torch.zeros(t.shape, **f32) for t in (K_sel, V_sel, K_win, V_win, K_cmp, V_cmp)]
+        dgates = torch.zeros(gates.shape, **f32)
+        dOc = _c(dO.to(Q.dtype))
+        if Q.numel():
+            _call("nsa_prefill_bwd", C.byref(dm), _ptr(Q), _ptr(K_sel), _ptr(V_sel), _ptr(K_win), _ptr(V_win), _ptr(K_cmp),
+                  _ptr(V_cmp), _ptr(ranges), _ptr(O_br), _ptr(lse), _ptr(gates), _ptr(dOc), _ptr(dQ),
+                  *[_ptr(g) for g in grads], _ptr(dgates), _stream())
+        dparams = [None, None, None, None]
+        if has_gate and cfg.gate_mode == GATE_MLP and not stopgrad:
+            it = iter(gk)
+            full = [next(it) if m else None for m in gmask]
+            gp = _lib.GateParams()
+            gp.fc1_w, gp.fc1_b, gp.fc2_w, gp.fc2_b = (None if t is None else t.data_ptr() for t in full)
+            H, Dk = full[0].shape
+            d1w, d1b = torch.zeros((H, Dk), **f32), torch.zeros((H,), **f32)
+            d2w, d2b = torch.zeros((3, H), **f32), torch.zeros((3,), **f32)
+            if Q.numel():
+                _call("nsa_gate_bwd", C.byref(dm), _ptr(Q), C.byref(gp), _ptr(dgates), _ptr(dQ), _ptr(d1w), _ptr(d1b),
+                      _ptr(d2w), _ptr(d2b), _stream())
+            dparams = [d1w, d1b if gmask[1] else None, d2w, d2b if gmask[3] else None]
+            dparams = [None if g is None else g.to(dt) for g, dt in zip(dparams, gdt)]
+        outs = [dQ.to(Q.dtype)] + [g.to(t.dtype) for g, t in zip(grads, (K_sel, V_sel, K_win, V_win, K_cmp, V_cmp))]
+        return (*outs, *dparams, None, None, None, None, None, None)
+
+
+def prefill_core(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, gate, cfg: NSAConfig, *, sel_mode: int = 0, t0: int = 0,
+                 stopgrad_gates: bool = False, ranges: Optional[torch.Tensor] = None, S_sel_kv: Optional[int] = None,
+                 S_win_kv: Optional[int] = None, S_cmp: Optional[int] = None, win_off: int = 0):
+    """NSA hot path for S query rows.  gate = (fc1_w, fc1_b, fc2_w, fc2_b) or None for forced/uniform gates.
+    Returns (O [B,S,G,h,Dv], ranges [B,S,G,K,2] int32, gates [B,S,G,3] fp32)."""
+    _require_cuda(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp)
+    g = gate if gate is not None else (None, None, None, None)
+    if gate is not None:
+        # the kernels read fp32 gate weights; keep autograd attached to the caller's parameters
+        g = tuple(None if t is None else t for t in gate)
+    geom = {k: v for k, v in dict(S_sel_kv=S_sel_kv, S_win_kv=S_win_kv, S_cmp=S_cmp).items() if v is not None}
+    if win_off:
+        geom["win_off"] = win_off
+    return _PrefillCore.apply(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, g[0], g[1], g[2], g[3], cfg, sel_mode, t0,
+                              stopgrad_gates, ranges, geom)
+
+
+# ----------------------------------------------------------------------------------------------------
+# fused hot path: decode
+# ----------------------------------------------------------------------------------------------------
+def decode_core(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, gate, cfg: NSAConfig, *, t: int, S_sel_kv: int,
+                S_win_kv: int, win_off: int, S_cmp: int, ranges_out: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None, gate_cache=None) -> torch.Tensor:
+    """One decode step.  Q [B,1,G,h,Dk]; caches may be over-allocated ([B,G,cap,D], rows present given by S_*).
+    Returns O [B,1,G,h,Dv]."""
+    _require_cuda(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp)
+    Q = _c(Q)
+    B, S, G, h, Dk = Q.shape
+    if S != 1:
+        raise AssertionError(f"Decode mode requires S=1 (single token), got S={S}.")  # nsa_attention.py:532-535
+    Dv = V_sel.shape[-1]
+    if gate_cache is not None:
+        gp, keep, hid = gate_cache
+    else:
+        gp, keep, hid = _gate_struct(gate, Q.device)
+    dm = make_dims(Q, cfg, t0=t, K_sel=K_sel, K_win=K_win, K_cmp=K_cmp, Dv=Dv, S_sel_kv=S_sel_kv, S_win_kv=S_win_kv,
+                   S_cmp=S_cmp, win_off=win_off, n_ranges=cfg.n_sel, gate_hidden=hid)
+    O = out if out is not None else torch.empty((B, 1, G, h, Dv), dtype=Q.dtype, device=Q.device)
+    if ranges_out is None:
+        ranges_out = torch.empty((B, G, cfg.n_sel, 2), dtype=torch.int32, device=Q.device)
+    ws_bytes = int(_lib.load().nsa_workspace_bytes(C.byref(dm), _lib.WS_DECODE))
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=Q.device)
+    for name, t_ in (("K_sel", K_sel), ("V_sel", V_sel), ("K_win", K_win), ("V_win", V_win), ("K_cmp", K_cmp), ("V_cmp", V_cmp)):
+        if not t_.is_contiguous():
+            raise RuntimeError(f"decode_core: {name} must be contiguous [B,G,cap,D]")
+    _call("nsa_decode_fwd", C.byref(dm), _ptr(Q), _ptr(K_sel), _ptr(V_sel), _ptr(K_win), _ptr(V_win), _ptr(K_cmp),
+          _ptr(V_cmp), C.byref(gp), _ptr(O), _ptr(ranges_out), _ptr(ws), _stream())
+    return O

@@ -140,7 +140,7 @@ def num_cmp_at(t: int, l: int, d: int, S_cmp: int) -> int:
 # Scores: p_cmp, Eq.9, Eq.10                        (nsa/core/selection_scorer.py:42-121)
 # ----------------------------------------------------------------------------------------
 def pcmp_all(Q: torch.Tensor, K_cmp: torch.Tensor, scale: float, norm: str = "full_row",
-             l: int = 0, d: int = 0) -> torch.Tensor:
+             l: int = 0, d: int = 0, t0: int = 0) -> torch.Tensor:
     """Q [B,S,G,h,Dk], K_cmp [B,G,S_cmp,Dk] -> p [B,S,G,h,S_cmp].
     norm="full_row": softmax over every compressed key for every row, the reference's prefill
     behaviour (selection_scorer.py:58-61; non-causal normaliser).
@@ -148,7 +148,7 @@ def pcmp_all(Q: torch.Tensor, K_cmp: torch.Tensor, scale: float, norm: str = "fu
     logits = torch.einsum("bsghd,bgcd->bsghc", Q.float(), K_cmp.float()) * scale
     if norm == "causal":
         S, S_cmp = Q.shape[1], K_cmp.shape[2]
-        nc = torch.tensor([num_cmp_at(t, l, d, S_cmp) for t in range(S)])
+        nc = torch.tensor([num_cmp_at(t0 + t, l, d, S_cmp) for t in range(S)])
         dis = torch.arange(S_cmp)[None, :] >= nc[:, None]
         logits = logits.masked_fill(dis[None, :, None, None, :], NEG_INF)
         p = torch.softmax(logits, dim=-1)
@@ -250,7 +250,7 @@ def prefill_range_cols(S: int, l_sel: int, n_sel: int) -> int:
     return nf + min(k_rest, S_sel) if k_rest > 0 else min(nf, n_sel)
 
 
-def select_ranges_prefill(p_grp: torch.Tensor, l_sel: int, n_sel: int, S: int) -> torch.Tensor:
+def select_ranges_prefill(p_grp: torch.Tensor, l_sel: int, n_sel: int, S: int, t0: int = 0) -> torch.Tensor:
     """select_topn_ranges_batched + convert_indices_to_ranges_batched_v2
     (selection_scorer.py:255-362, :434-605): p_grp [B,S,G,S_sel] -> [B,S,G,K,2] int32.
     Every entry (forced included) must be a *complete* block at row t; if n_sel >= S_sel the
@@ -262,7 +262,8 @@ def select_ranges_prefill(p_grp: torch.Tensor, l_sel: int, n_sel: int, S: int) -
     k_rest = max(0, n_sel - nf)
     out = np.zeros((B, S_q, G, K, 2), dtype=np.int32)
     for b in range(B):
-        for t in range(S_q):
+        for tq in range(S_q):
+            t = t0 + tq  # absolute position of this row
             nvalid = min((t + 1) // l_sel, S_sel)
             cb = t // l_sel
             forced3 = sorted([0, cb, max(cb - 1, 0)])
@@ -273,7 +274,7 @@ def select_ranges_prefill(p_grp: torch.Tensor, l_sel: int, n_sel: int, S: int) -
                 if n_sel >= S_sel:
                     ids = list(range(nvalid))
                 else:
-                    masked = p[b, t, g].copy()
+                    masked = p[b, tq, g].copy()
                     masked[nvalid:] = NEG_INF
                     for j in forced:
                         masked[j] = NEG_INF
@@ -292,8 +293,8 @@ def select_ranges_prefill(p_grp: torch.Tensor, l_sel: int, n_sel: int, S: int) -
                     else:
                         runs.append([j, j])
                 for i, (j0, j1) in enumerate(runs):
-                    out[b, t, g, i, 0] = j0 * l_sel
-                    out[b, t, g, i, 1] = min((j1 + 1) * l_sel, t + 1)
+                    out[b, tq, g, i, 0] = j0 * l_sel
+                    out[b, tq, g, i, 1] = min((j1 + 1) * l_sel, t + 1)
     return torch.from_numpy(out)
 
 
@@ -419,30 +420,31 @@ def combine(gates: torch.Tensor, O_cmp, O_sel, O_win) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------
 # End-to-end hot path
 # ----------------------------------------------------------------------------------------
-def prefill_scores(Q, K_cmp, l, d, l_sel, n_sel, w, norm="full_row"):
-    """nsa_attention.py:1073-1091: p_cmp -> p_slc -> p_grp for every row."""
+def prefill_scores(Q, K_cmp, l, d, l_sel, n_sel, w, norm="full_row", t0=0, S_total=None):
+    """nsa_attention.py:1073-1091: p_cmp -> p_slc -> p_grp for every row (rows t0 .. t0+S-1 of S_total)."""
     S = Q.shape[1]
-    meta = build_meta(S, l, d, l_sel, n_sel, w)
+    meta = build_meta(S_total if S_total is not None else t0 + S, l, d, l_sel, n_sel, w)
     scale = 1.0 / math.sqrt(Q.shape[-1])
     if K_cmp.shape[2] == 0:
         return torch.zeros(Q.shape[0], S, Q.shape[2], meta.S_sel)
-    p = pcmp_all(Q, K_cmp, scale, norm, l, d)
+    p = pcmp_all(Q, K_cmp, scale, norm, l, d, t0)
     return pgrp_from_pslc(pslc_from_pcmp(p, meta))
 
 
 def prefill_core(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, gate_params, *, l, d, l_sel, n_sel, w,
-                 tau=1.0, gate_mode=GATE_MLP, norm="full_row", ranges=None):
+                 tau=1.0, gate_mode=GATE_MLP, norm="full_row", ranges=None, t0=0, S_total=None):
     """Hot path of _forward_prefill_batched (nsa_attention.py:1066-1398) between "Q/K/V
     projected + RoPE'd" and "O handed to self.out", intended semantics.  Returns dict."""
     S = Q.shape[1]
+    S_total = t0 + S if S_total is None else S_total
     if ranges is None:
-        p_grp = prefill_scores(Q, K_cmp, l, d, l_sel, n_sel, w, norm)
-        ranges = select_ranges_prefill(p_grp, l_sel, n_sel, S)
+        p_grp = prefill_scores(Q, K_cmp, l, d, l_sel, n_sel, w, norm, t0, S_total)
+        ranges = select_ranges_prefill(p_grp, l_sel, n_sel, S_total, t0)
     else:
         p_grp = None
-    O_cmp, lse_cmp = cmp_attention(Q, K_cmp, V_cmp, l, d)
+    O_cmp, lse_cmp = cmp_attention(Q, K_cmp, V_cmp, l, d, t0)
     O_sel, lse_sel = sel_attention(Q, K_sel, V_sel, ranges)
-    O_win, lse_win = win_attention(Q, K_win, V_win, w)
+    O_win, lse_win = win_attention(Q, K_win, V_win, w, t0)
     q_gp = Q.float().mean(dim=3) if Q.dtype != torch.float64 else Q.mean(dim=3)
     gates = gate_mlp(q_gp, *gate_params, tau=tau, mode=gate_mode)
     O = combine(gates.to(O_cmp.dtype), O_cmp, O_sel, O_win)
