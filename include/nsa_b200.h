@@ -115,12 +115,14 @@ int nsa_gate_bwd(const nsa_dims_t* dm, const void* Q, const nsa_gate_params_t* g
 /* ---- fused hot path ------------------------------------------------------------------------
  * nsa_prefill_fwd: the three branches + gate + combine in one pass; branch outputs stay on chip
  * unless O_branches (3 x [B,S,G,h,Dv], dm->dtype) is non-NULL (needed only to run backward).
+ * workspace: nsa_workspace_bytes(dm, NSA_WS_PREFILL) bytes when O_branches is NULL (0 when the single fused kernel
+ * serves the shape; otherwise staging for branch kernels that run separately).
  * Replaces nsa_attention.py:1137-1398. */
 int nsa_prefill_fwd(const nsa_dims_t* dm, const void* Q,
                     const void* K_sel, const void* V_sel, const void* K_win, const void* V_win,
                     const void* K_cmp, const void* V_cmp, const int32_t* ranges,
                     const nsa_gate_params_t* gp, void* O, float* lse, float* gates, void* O_branches,
-                    void* stream);
+                    void* workspace, void* stream);
 /* Backward of nsa_prefill_fwd.  dQ [B,S,G,h,Dk], dK_x/dV_x like their caches but fp32 (+=, caller
  * zeroes), dgates [B,S,G,3] fp32 (written). */
 int nsa_prefill_bwd(const nsa_dims_t* dm, const void* Q,

@@ -51,7 +51,7 @@ SIGNATURES = {
     "nsa_branch_attn_bwd": (_I, [_DP, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nsa_gate_fwd": (_I, [_DP, _P, _GP, _P, _P]),
     "nsa_gate_bwd": (_I, [_DP, _P, _GP, _P, _P, _P, _P, _P, _P, _P]),
-    "nsa_prefill_fwd": (_I, [_DP] + [_P] * 8 + [_GP] + [_P] * 5),
+    "nsa_prefill_fwd": (_I, [_DP] + [_P] * 8 + [_GP] + [_P] * 6),
     "nsa_prefill_bwd": (_I, [_DP] + [_P] * 21),
     "nsa_decode_fwd": (_I, [_DP] + [_P] * 7 + [_GP] + [_P] * 4),
     "nsa_workspace_bytes": (_I64, [_DP, _I]),

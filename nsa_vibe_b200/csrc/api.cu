@@ -44,9 +44,7 @@ static int validate_dims(const nsa_dims_t* dm, const char* who) {
   return NSA_OK;
 }
 
-static bool tc_eligible(const nsa_dims_t& dm) {
-  return dm.impl != NSA_IMPL_SIMT && tc_supported(dm);
-}
+static bool tc_eligible(const nsa_dims_t& dm) { return dm.impl != NSA_IMPL_SIMT; }
 
 }  // namespace nsa
 
@@ -112,7 +110,8 @@ int nsa_branch_attn_fwd(const nsa_dims_t* dm, int branch, const void* Q, const v
   NSA_REQUIRE(branch >= 0 && branch <= 2, "branch_attn_fwd: branch %d", branch);
   NSA_REQUIRE(Q && O_b, "branch_attn_fwd: NULL pointer");
   NSA_REQUIRE(branch != 1 || ranges, "branch_attn_fwd: the selected branch needs ranges");
-  if (tc_eligible(*dm)) return launch_branch_tc(*dm, branch, Q, K, V, ranges, O_b, lse_b, (cudaStream_t)stream);
+  if (tc_branch_supported(*dm, branch)) return launch_branch_tc(*dm, branch, Q, K, V, ranges, O_b, lse_b, (cudaStream_t)stream);
+  NSA_REQUIRE(dm->impl != NSA_IMPL_TC, "branch_attn_fwd: no tcgen05 kernel for this shape/branch (impl=TC was forced)");
   FwdArgs a;
   memset(&a, 0, sizeof(a));
   a.Q = Q;
@@ -168,23 +167,49 @@ int nsa_gate_bwd(const nsa_dims_t* dm, const void* Q, const nsa_gate_params_t* g
 
 int nsa_prefill_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
                     const void* V_win, const void* K_cmp, const void* V_cmp, const int32_t* ranges,
-                    const nsa_gate_params_t* gp, void* O, float* lse, float* gates, void* O_branches, void* stream) {
+                    const nsa_gate_params_t* gp, void* O, float* lse, float* gates, void* O_branches, void* workspace,
+                    void* stream) {
   if (int rc = validate_dims(dm, "prefill_fwd")) return rc;
   NSA_REQUIRE(Q && O && ranges && gp, "prefill_fwd: NULL pointer");
   NSA_REQUIRE(dm->gate_mode != NSA_GATE_MLP || (gp->fc1_w && gp->fc2_w), "prefill_fwd: MLP weights missing");
-  if (tc_eligible(*dm))
-    return launch_prefill_tc(*dm, Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, ranges, *gp, O, lse, gates, O_branches,
-                             (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
   FwdArgs a;
   fill_fwd(a, Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp);
   a.ranges = ranges;
   a.gp = *gp;
-  a.O = O;
   a.lse = lse;
-  a.gates_out = gates;
-  a.O_br = O_branches;
-  a.branch_mask = 7;
-  return launch_fwd_generic(*dm, a, (cudaStream_t)stream);
+  int tc_mask = 0;
+  for (int br = 0; br < 3; ++br)
+    if (tc_branch_supported(*dm, br)) tc_mask |= 1 << br;
+  if (tc_mask == 0) {  // everything in the one fused SIMT kernel: branch outputs never leave the SM
+    NSA_REQUIRE(dm->impl != NSA_IMPL_TC, "prefill_fwd: no tcgen05 kernel for this shape (impl=TC was forced)");
+    a.O = O;
+    a.gates_out = gates;
+    a.O_br = O_branches;
+    a.branch_mask = 7;
+    return launch_fwd_generic(*dm, a, st);
+  }
+  // tensor-core branches run as their own kernels; branch outputs go through O_branches (or the workspace)
+  void* obr = O_branches ? O_branches : workspace;
+  NSA_REQUIRE(obr, "prefill_fwd: this shape needs O_branches or a workspace of nsa_workspace_bytes(NSA_WS_PREFILL)");
+  const size_t rows_h = (size_t)dm->B * dm->S * dm->G * dm->h;
+  const size_t per_branch = rows_h * dm->Dv * elt_size(dm->dtype);
+  const void* Ks[3] = {K_cmp, K_sel, K_win};
+  const void* Vs[3] = {V_cmp, V_sel, V_win};
+  for (int br = 0; br < 3; ++br) {
+    if (!(tc_mask & (1 << br))) continue;
+    if (int rc = launch_branch_tc(*dm, br, Q, Ks[br], Vs[br], ranges, (char*)obr + br * per_branch,
+                                  lse ? lse + br * rows_h : nullptr, st))
+      return rc;
+  }
+  if (tc_mask != 7) {
+    a.O_br = obr;
+    a.branch_mask = 7 & ~tc_mask;
+    nsa_dims_t d2 = *dm;
+    d2.gate_mode = NSA_GATE_UNIFORM;  // gates are applied by the combine kernel
+    if (int rc = launch_fwd_generic(d2, a, st)) return rc;
+  }
+  return launch_combine(*dm, Q, *gp, obr, O, gates, st);
 }
 
 int nsa_prefill_bwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
@@ -246,8 +271,12 @@ int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which) {
       return (int64_t)dm->B * dm->G * dm->n_sel * 2 * sizeof(int32_t) + tc_decode_workspace(*dm);
     case NSA_WS_SCORE_SELECT:
       return tc_score_workspace(*dm);
-    case NSA_WS_PREFILL:
+    case NSA_WS_PREFILL: {
+      for (int br = 0; br < 3; ++br)
+        if (tc_branch_supported(*dm, br))
+          return (int64_t)3 * dm->B * dm->S * dm->G * dm->h * dm->Dv * (int64_t)elt_size(dm->dtype);
       return 0;
+    }
     default:
       return 0;
   }

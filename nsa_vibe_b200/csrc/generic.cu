@@ -496,6 +496,52 @@ int launch_gate_fwd(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t
   return check_launch("gate_fwd_kernel");
 }
 
+// Gate + three-branch combine over branch outputs already in HBM (used when the branches ran as separate kernels).
+__global__ void __launch_bounds__(kAttnWarps * 32)
+combine_kernel(nsa_dims_t dm, const void* __restrict__ Q, nsa_gate_params_t gp, const void* __restrict__ O_br,
+               void* __restrict__ O, float* __restrict__ gates) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* qgp = smem + (size_t)warp * (dm.Dk + 2 * dm.gate_hidden);
+  float* xs = qgp + dm.Dk;
+  const int n_rows = dm.B * dm.S * dm.G;
+  const size_t per_branch = (size_t)n_rows * dm.h * dm.Dv;
+  for (int row = blockIdx.x * kAttnWarps + warp; row < n_rows; row += gridDim.x * kAttnWarps) {
+    if (dm.gate_mode == NSA_GATE_MLP) {
+      for (int k = lane; k < dm.Dk; k += 32) {
+        float m = 0.f;
+        for (int hh = 0; hh < dm.h; ++hh) m += ld_elt(Q, ((size_t)row * dm.h + hh) * dm.Dk + k, dm.dtype);
+        qgp[k] = m / (float)dm.h;
+      }
+      __syncwarp();
+    }
+    Gate3 gt = gate_forward_warp(qgp, xs, nullptr, gp, dm.Dk, dm.gate_hidden, dm.gate_tau, dm.gate_mode, nullptr);
+    if (gates && lane == 0) {
+      gates[(size_t)row * 3] = gt.c;
+      gates[(size_t)row * 3 + 1] = gt.s;
+      gates[(size_t)row * 3 + 2] = gt.w;
+    }
+    const size_t base = (size_t)row * dm.h * dm.Dv;
+    for (int i = lane; i < dm.h * dm.Dv; i += 32) {
+      const float v = gt.c * ld_elt(O_br, base + i, dm.dtype) + gt.s * ld_elt(O_br, per_branch + base + i, dm.dtype) +
+                      gt.w * ld_elt(O_br, 2 * per_branch + base + i, dm.dtype);
+      st_elt(O, base + i, dm.dtype, v);
+    }
+    __syncwarp();
+  }
+}
+
+int launch_combine(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t& gp, const void* O_br, void* O, float* gates,
+                   cudaStream_t stream) {
+  const int n_rows = dm.B * dm.S * dm.G;
+  if (n_rows == 0) return NSA_OK;
+  int blocks = ceil_div(n_rows, kAttnWarps);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  size_t smem = (size_t)kAttnWarps * (dm.Dk + 2 * dm.gate_hidden) * sizeof(float);
+  combine_kernel<<<blocks, kAttnWarps * 32, smem, stream>>>(dm, Q, gp, O_br, O, gates);
+  return check_launch("combine_kernel");
+}
+
 // Backward: recompute the MLP per row, accumulate parameter gradients in shared memory per CTA, flush with
 // one atomicAdd per parameter per CTA.
 __global__ void __launch_bounds__(kAttnWarps * 32)

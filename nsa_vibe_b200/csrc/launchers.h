@@ -39,8 +39,10 @@ int launch_bwd_generic(const nsa_dims_t& dm, const BwdArgs& a, cudaStream_t stre
 int launch_gate_fwd(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t& gp, float* gates, cudaStream_t stream);
 int launch_gate_bwd(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t& gp, const float* dgates, float* dQ,
                     float* d_fc1_w, float* d_fc1_b, float* d_fc2_w, float* d_fc2_b, cudaStream_t stream);
+int launch_combine(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t& gp, const void* O_br, void* O, float* gates,
+                   cudaStream_t stream);
 // tc_*.cu (tcgen05 / TMA kernels)
-bool tc_supported(const nsa_dims_t& dm);
+bool tc_branch_supported(const nsa_dims_t& dm, int branch);
 bool tc_score_supported(const nsa_dims_t& dm);
 bool tc_decode_supported(const nsa_dims_t& dm);
 int64_t tc_score_workspace(const nsa_dims_t& dm);
@@ -49,9 +51,6 @@ int launch_score_tc(const nsa_dims_t& dm, const void* Q, const void* Kc, int S_s
                     float* p_grp, int32_t* ranges, void* workspace, cudaStream_t stream);
 int launch_branch_tc(const nsa_dims_t& dm, int branch, const void* Q, const void* K, const void* V, const int32_t* ranges,
                      void* O_b, float* lse_b, cudaStream_t stream);
-int launch_prefill_tc(const nsa_dims_t& dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
-                      const void* V_win, const void* K_cmp, const void* V_cmp, const int32_t* ranges,
-                      const nsa_gate_params_t& gp, void* O, float* lse, float* gates, void* O_branches, cudaStream_t stream);
 int launch_decode_tc(const nsa_dims_t& dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
                      const void* V_win, const void* K_cmp, const void* V_cmp, const nsa_gate_params_t& gp, void* O,
                      int32_t* ranges_out, void* workspace, cudaStream_t stream);

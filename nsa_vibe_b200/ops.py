@@ -271,9 +271,13 @@ class _PrefillCore(torch.autograd.Function):
         gates = torch.empty((B, S, G, 3), dtype=torch.float32, device=dev)
         lse = torch.empty((3, B, S, G, h), dtype=torch.float32, device=dev) if need_grad else None
         O_br = torch.empty((3, B, S, G, h, Dv), dtype=Q.dtype, device=dev) if need_grad else None
+        ws = None
+        if O_br is None:
+            ws_bytes = int(_lib.load().nsa_workspace_bytes(C.byref(dm), _lib.WS_PREFILL))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
         if O.numel():
             _call("nsa_prefill_fwd", C.byref(dm), _ptr(Q), _ptr(K_sel), _ptr(V_sel), _ptr(K_win), _ptr(V_win), _ptr(K_cmp),
-                  _ptr(V_cmp), _ptr(ranges), C.byref(gp), _ptr(O), _ptr(lse), _ptr(gates), _ptr(O_br), _stream())
+                  _ptr(V_cmp), _ptr(ranges), C.byref(gp), _ptr(O), _ptr(lse), _ptr(gates), _ptr(O_br), _ptr(ws), _stream())
         if need_grad:
             ctx.save_for_backward(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, ranges, lse, gates, O_br, *[k for k in keep if k is not None])
             ctx.geom = geom

@@ -1,0 +1,59 @@
+"""tcgen05 / TMA kernels against the SIMT kernels and the fp32 oracle (bf16 tolerance: max-abs 2e-2, MAE 1e-3)."""
+import pytest
+import torch
+
+from oracle import nsa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from nsa_vibe_b200 import ops
+    return ops
+
+
+def _case(B, S, G, h, l, d, ls, n, w, seed, dtype):
+    gen = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=gen).to(dtype).float()
+    S_cmp = O.num_cmp_blocks(S, l, d)
+    return [r(B, S, G, h, 64), r(B, G, S, 64), r(B, G, S, 64), r(B, G, S, 64), r(B, G, S, 64), r(B, G, S_cmp, 64), r(B, G, S_cmp, 64)]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("sel_mode,S,h", [(0, 700, 6), (1, 700, 6), (0, 1500, 4), (1, 333, 8), (0, 64, 1)])
+def test_sel_branch_tc_vs_simt_vs_oracle(dtype, sel_mode, S, h):
+    ops = _ops()
+    B, G, l, d, ls, n, w = 2, 2, 32, 16, 64, 16, 512
+    ts = _case(B, S, G, h, l, d, ls, n, w, seed=S + h, dtype=dtype)
+    cfg_tc = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w, impl=ops.IMPL_TC)
+    cfg_simt = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w, impl=ops.IMPL_SIMT)
+    Q, K, V = (t.cuda().to(dtype) for t in ts[:3])
+    ranges = ops.score_select(Q, ts[5].cuda().to(dtype), cfg_simt, mode=sel_mode)
+    o_tc, lse_tc = ops.branch_attention(ops.BR_SEL, Q, K, V, cfg_tc, ranges, return_lse=True)
+    o_si, lse_si = ops.branch_attention(ops.BR_SEL, Q, K, V, cfg_simt, ranges, return_lse=True)
+    want, lse_w = O.sel_attention(ts[0], ts[1], ts[2], ranges.cpu())
+    err = (o_tc.float().cpu() - want).abs()
+    assert err.max() <= 2e-2 and err.mean() <= 1e-3, (err.max(), err.mean())
+    assert (o_tc.float() - o_si.float()).abs().max() <= 2e-2
+    fin = torch.isfinite(lse_w)
+    assert torch.equal(torch.isfinite(lse_tc.cpu()), fin)
+    assert (lse_tc.cpu()[fin] - lse_w[fin]).abs().max() <= 2e-2
+    empty = ~fin.any(dim=-1)
+    if empty.any():
+        assert torch.all(o_tc.float().cpu()[empty] == 0)
+
+
+def test_prefill_core_tc_composition_bf16():
+    """nsa_prefill_fwd with the selected branch on tensor cores (auto dispatch) == oracle."""
+    ops = _ops()
+    B, S, G, h, l, d, ls, n, w = 1, 900, 2, 6, 32, 16, 64, 16, 512
+    ts = _case(B, S, G, h, l, d, ls, n, w, seed=4, dtype=torch.bfloat16)
+    gen = torch.Generator().manual_seed(1)
+    gate = (torch.randn(32, 64, generator=gen) * 0.3, torch.randn(32, generator=gen) * 0.1, torch.randn(3, 32, generator=gen) * 0.5,
+            torch.zeros(3))
+    cfg = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w)
+    Oc, ranges, gates = ops.prefill_core(*[t.cuda().bfloat16() for t in ts], tuple(x.cuda() for x in gate), cfg, sel_mode=0)
+    want = O.prefill_core(*ts, gate, l=l, d=d, l_sel=ls, n_sel=n, w=w, ranges=ranges.cpu())
+    err = (Oc.float().cpu() - want["O"]).abs()
+    assert err.max() <= 2e-2 and err.mean() <= 1e-3, (err.max(), err.mean())
+    assert torch.allclose(gates.cpu(), want["gates"], atol=1e-3)
