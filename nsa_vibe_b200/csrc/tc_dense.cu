@@ -1,0 +1,375 @@
+// Dense ranged attention on tcgen05 tensor cores: the compressed and sliding-window branches of NSA prefill.
+//   cmp: row t attends compressed tokens [0, num_cmp(t))            (attention_kernels.py:106-143, packing.py:15-23)
+//   win: row t attends cache rows of tokens [max(0, t-w+1), t]      (attention_kernels.py:146-178)
+// both with softmax over every allowed key.  Flash-attention structure, B200 style:
+//   * one CTA = MT M-tiles of 128 rows, a row being one (token, head) of one (b, g): TOK = 128/h tokens per M-tile, so
+//     every K/V tile is shared by all h heads of TOK*MT tokens (GQA reuse) and loaded once by TMA;
+//   * S = Q.K^T (M=128, N=128, K=64) into TMEM; softmax warps (thread = TMEM lane = row) take the tile max, write
+//     P = exp2(s*c - m*c) as bf16 into 128B-swizzled shared memory; O_t = P.V (M=128, N=64, K=128) into TMEM with V as the
+//     MN-major B operand; O_t is folded into fp32 register accumulators with the online-softmax rescale;
+//   * the two M-tiles ping-pong: while one runs its softmax (MUFU-bound), the tensor core works for the other.
+// Warp roles: warps [0, 4*MT) softmax, warp 4*MT TMA producer, warp 4*MT+1 MMA issuer.
+#include "tc_common.cuh"
+#include "launchers.h"
+
+namespace nsa {
+using namespace tc;
+
+constexpr int kDnMT = 2;
+constexpr int kDnKS = 3;             // K ring stages
+constexpr int kDnVS = 3;             // V ring stages
+constexpr int kDnTile = 128 * 128;   // bytes: 128 rows x 64 x 2 B
+
+struct DnSmem {
+  static constexpr int q = 0;                               // MT x 16 KB
+  static constexpr int k = q + kDnMT * kDnTile;
+  static constexpr int v = k + kDnKS * kDnTile;
+  static constexpr int p = v + kDnVS * kDnTile;             // MT x 32 KB: [2 key halves][128 rows][128 B]
+  static constexpr int misc = p + kDnMT * 2 * kDnTile;
+  static constexpr int total = misc + 512 + 1024;
+};
+
+struct DnMisc {
+  uint64_t q_full;
+  uint64_t k_full[kDnKS], k_empty[kDnKS], v_full[kDnVS], v_empty[kDnVS];
+  uint64_t s_full[kDnMT], s_empty[kDnMT], p_full[kDnMT], p_empty[kDnMT];
+  uint64_t o_full[kDnMT][2], o_empty[kDnMT][2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float dn_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void dn_ld_wait32(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+// key range of one row in cache-row coordinates
+__device__ __forceinline__ void dn_row_range(const nsa_dims_t& dm, int branch, int t, int& lo, int& hi) {
+  if (branch == 0) {
+    lo = 0;
+    hi = num_cmp_at(t, dm.l, dm.d, dm.S_cmp);
+  } else {
+    int a = t - dm.w + 1;
+    if (a < dm.win_off) a = dm.win_off;
+    if (a < 0) a = 0;
+    lo = a - dm.win_off;
+    hi = t + 1 - dm.win_off;
+    if (hi > dm.S_win_kv) hi = dm.S_win_kv;
+    if (dm.w <= 0 || hi < lo) hi = lo;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32 * (4 * kDnMT + 2), 1)
+dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, nsa_dims_t dm, int branch, T* __restrict__ O,
+                     float* __restrict__ lse, int TOK) {
+  constexpr int MT = kDnMT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  DnMisc* ms = reinterpret_cast<DnMisc*>(smem + DnSmem::misc);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kSoftWarps = 4 * MT;
+
+  const int tiles_per_seq = ceil_div(dm.S, MT * TOK);
+  const int tile = blockIdx.x % tiles_per_seq;
+  const int bg = blockIdx.x / tiles_per_seq;
+  const int g = bg % dm.G, b = bg / dm.G;
+  const int s_base = tile * MT * TOK;
+  int s_last = s_base + MT * TOK - 1;
+  if (s_last > dm.S - 1) s_last = dm.S - 1;
+  // union of the rows' key ranges -> key tiles [kt_lo, kt_lo + n)
+  int lo_first, hi_first, lo_last, hi_last;
+  dn_row_range(dm, branch, dm.t0 + s_base, lo_first, hi_first);
+  dn_row_range(dm, branch, dm.t0 + s_last, lo_last, hi_last);
+  const int kt_lo = lo_first >> 7;
+  const int n = hi_last > lo_first ? ceil_div(hi_last, 128) - kt_lo : 0;
+
+  // ---- setup ---------------------------------------------------------------------------------------------
+  {
+    uint4 z = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < MT * kDnTile / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem + DnSmem::q)[i] = z;
+  }
+  if (tid == 0) {
+    mbar_init(&ms->q_full, 1);
+    for (int i = 0; i < kDnKS; ++i) { mbar_init(&ms->k_full[i], 1); mbar_init(&ms->k_empty[i], 1); }
+    for (int i = 0; i < kDnVS; ++i) { mbar_init(&ms->v_full[i], 1); mbar_init(&ms->v_empty[i], 1); }
+    for (int m = 0; m < MT; ++m) {
+      mbar_init(&ms->s_full[m], 1);
+      mbar_init(&ms->s_empty[m], 4);
+      mbar_init(&ms->p_full[m], 4);
+      mbar_init(&ms->p_empty[m], 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(&ms->o_full[m][i], 1); mbar_init(&ms->o_empty[m][i], 4); }
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 0) tmem_alloc(&ms->tmem_base, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ms->tmem_base;
+  // TMEM columns: S[mt] at mt*128 ; O_t[mt][st] at 256 + (mt*2+st)*64
+
+  if (warp == kSoftWarps) {
+    // ===== TMA producer ====================================================================================
+    if (lane == 0 && n > 0) {
+      mbar_expect_tx(&ms->q_full, MT * TOK * dm.h * 128);
+      for (int m = 0; m < MT; ++m)
+        tma_load_4d(smem + DnSmem::q + m * kDnTile, &tmQ, &ms->q_full, 0, 0, g, b * dm.S + s_base + m * TOK);
+      for (int i = 0; i < n; ++i) {
+        const int ks = i % kDnKS, vs = i % kDnVS;
+        mbar_wait(&ms->k_empty[ks], ((i / kDnKS) & 1) ^ 1);
+        mbar_expect_tx(&ms->k_full[ks], kDnTile);
+        tma_load_3d(smem + DnSmem::k + ks * kDnTile, &tmK, &ms->k_full[ks], 0, (kt_lo + i) * 128, bg);
+        mbar_wait(&ms->v_empty[vs], ((i / kDnVS) & 1) ^ 1);
+        mbar_expect_tx(&ms->v_full[vs], kDnTile);
+        tma_load_3d(smem + DnSmem::v + vs * kDnTile, &tmV, &ms->v_full[vs], 0, (kt_lo + i) * 128, bg);
+      }
+    }
+  } else if (warp == kSoftWarps + 1) {
+    // ===== MMA issuer ======================================================================================
+    if (lane == 0 && n > 0) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, TcType<T>::fmt, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, TcType<T>::fmt, 0, 1);
+      auto issue_qk = [&](int m, int i) {
+        const uint32_t qb = smem_u32(smem + DnSmem::q + m * kDnTile);
+        const uint32_t kb = smem_u32(smem + DnSmem::k + (i % kDnKS) * kDnTile);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem + m * 128, make_smem_desc(qb + k * 32, 16, 1024, kSwizzle128B),
+                   make_smem_desc(kb + k * 32, 16, 1024, kSwizzle128B), idesc_qk, k > 0);
+        umma_commit(&ms->s_full[m]);
+      };
+      mbar_wait(&ms->q_full, 0);
+      mbar_wait(&ms->k_full[0], 0);
+      tc_fence_after();
+      for (int m = 0; m < MT; ++m) issue_qk(m, 0);
+      umma_commit(&ms->k_empty[0]);
+      for (int i = 0; i < n; ++i) {
+        const int vs = i % kDnVS;
+        mbar_wait(&ms->v_full[vs], (i / kDnVS) & 1);
+        if (i + 1 < n) mbar_wait(&ms->k_full[(i + 1) % kDnKS], ((i + 1) / kDnKS) & 1);
+        const uint32_t vb = smem_u32(smem + DnSmem::v + vs * kDnTile);
+        for (int m = 0; m < MT; ++m) {
+          mbar_wait(&ms->p_full[m], i & 1);
+          mbar_wait(&ms->o_empty[m][i & 1], ((i >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t pb = smem_u32(smem + DnSmem::p + m * 2 * kDnTile);
+          const uint32_t od = tmem + 256 + (m * 2 + (i & 1)) * 64;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_f16(od, make_smem_desc(pb + (k >> 2) * kDnTile + (k & 3) * 32, 16, 1024, kSwizzle128B),
+                     make_smem_desc(vb + k * 2048, 8192, 1024, kSwizzle128B), idesc_pv, k > 0);
+          umma_commit(&ms->o_full[m][i & 1]);
+          umma_commit(&ms->p_empty[m]);
+          if (i + 1 < n) {
+            mbar_wait(&ms->s_empty[m], i & 1);
+            tc_fence_after();
+            issue_qk(m, i + 1);
+          }
+        }
+        umma_commit(&ms->v_empty[vs]);
+        if (i + 1 < n) umma_commit(&ms->k_empty[(i + 1) % kDnKS]);
+      }
+    }
+  } else {
+    // ===== softmax warps ===================================================================================
+    const int mt = warp >> 2;
+    const int r = tid & 127;
+    const int tok_l = r / dm.h, head = r - tok_l * dm.h;
+    const int s = s_base + mt * TOK + tok_l;
+    const bool row_ok = tok_l < TOK && s < dm.S;
+    int lo = 0, hi = 0;
+    if (row_ok) dn_row_range(dm, branch, dm.t0 + s, lo, hi);
+    const float c = dm.scale * kLog2e;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tm_S = tmem + lane_off + mt * 128;
+    const uint32_t tm_O = tmem + lane_off + 256 + mt * 128;
+    uint8_t* prow = smem + DnSmem::p + mt * 2 * kDnTile + r * 128;
+    const int sw = r & 7;
+
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+
+    auto fold_o = [&](int i, float alpha) {  // acc = acc * alpha + O_t(i)
+      const int st = i & 1;
+      mbar_wait(&ms->o_full[mt][st], (i >> 1) & 1);
+      tc_fence_after();
+      uint32_t oa[32], ob[32];
+      tmem_ld32(tm_O + st * 64, oa);
+      tmem_ld32(tm_O + st * 64 + 32, ob);
+      dn_ld_wait32(oa);
+      dn_ld_wait32(ob);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ms->o_empty[mt][st]);
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        acc[e] = fmaf(acc[e], alpha, __uint_as_float(oa[e]));
+        acc[32 + e] = fmaf(acc[32 + e], alpha, __uint_as_float(ob[e]));
+      }
+    };
+
+    for (int i = 0; i < n; ++i) {
+      const int col_base = (kt_lo + i) * 128;
+      mbar_wait(&ms->s_full[mt], i & 1);
+      tc_fence_after();
+      const bool full_tile = col_base >= lo && col_base + 128 <= hi;
+      // ---- pass A: tile max ----
+      float cm = -INFINITY;
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld32(tm_S, va);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t(&cur)[32] = (ch & 1) ? vb : va;
+          uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
+          dn_ld_wait32(cur);
+          if (ch < 3) tmem_ld32(tm_S + (ch + 1) * 32, nxt);
+          if (full_tile) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) cm = fmaxf(cm, __uint_as_float(cur[e]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int col = col_base + ch * 32 + e;
+              if (col >= lo && col < hi) cm = fmaxf(cm, __uint_as_float(cur[e]));
+            }
+          }
+        }
+      }
+      const float m_new = fmaxf(m_run, cm);
+      const bool any = m_new > -INFINITY;
+      const float alpha = any ? dn_ex2((m_run - m_new) * c) : 1.f;
+      const float mc = any ? m_new * c : 0.f;
+      mbar_wait(&ms->p_empty[mt], (i & 1) ^ 1);  // P.V of the previous tile has read the P buffer
+      // ---- pass B: probabilities -> bf16 P tile (K-major, 128B swizzle) ----
+      float rowsum = 0.f;
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld32(tm_S, va);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t(&cur)[32] = (ch & 1) ? vb : va;
+          uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
+          dn_ld_wait32(cur);
+          if (ch < 3) tmem_ld32(tm_S + (ch + 1) * 32, nxt);
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float p0, p1;
+            if (full_tile) {
+              p0 = dn_ex2(fmaf(__uint_as_float(cur[e]), c, -mc));
+              p1 = dn_ex2(fmaf(__uint_as_float(cur[e + 1]), c, -mc));
+            } else {
+              const int col = col_base + ch * 32 + e;
+              p0 = (any && col >= lo && col < hi) ? dn_ex2(fmaf(__uint_as_float(cur[e]), c, -mc)) : 0.f;
+              p1 = (any && col + 1 >= lo && col + 1 < hi) ? dn_ex2(fmaf(__uint_as_float(cur[e + 1]), c, -mc)) : 0.f;
+            }
+            rowsum += p0 + p1;
+            pk[e >> 1] = pack2(T(), p0, p1);
+          }
+          // 32 keys = 4 chunks of 16 B; key chunk index kc = ch*4 + q in [0,16): half = kc >> 3, chunk-in-row = kc & 7
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int kc = ch * 4 + q;
+            *reinterpret_cast<uint4*>(prow + (kc >> 3) * kDnTile + (((kc & 7) ^ sw) << 4)) =
+                make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&ms->s_empty[mt]);
+        mbar_arrive(&ms->p_full[mt]);
+      }
+      l_run = fmaf(l_run, alpha, rowsum);
+      m_run = m_new;
+      if (i > 0) fold_o(i - 1, alpha_prev);
+      alpha_prev = alpha;
+    }
+    if (n > 0) fold_o(n - 1, alpha_prev);
+
+    // ---- epilogue -------------------------------------------------------------------------------------------
+    if (row_ok) {
+      const size_t orow = (((size_t)b * dm.S + s) * dm.G + g) * dm.h + head;
+      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;  // empty row -> zeros
+      uint4* dst = reinterpret_cast<uint4*>(O + orow * 64);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        uint4 v;
+        v.x = pack2(T(), acc[q * 8 + 0] * inv, acc[q * 8 + 1] * inv);
+        v.y = pack2(T(), acc[q * 8 + 2] * inv, acc[q * 8 + 3] * inv);
+        v.z = pack2(T(), acc[q * 8 + 4] * inv, acc[q * 8 + 5] * inv);
+        v.w = pack2(T(), acc[q * 8 + 6] * inv, acc[q * 8 + 7] * inv);
+        dst[q] = v;
+      }
+      if (lse) lse[orow] = l_run > 0.f ? m_run * dm.scale + logf(l_run) : -INFINITY;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------
+int make_tmap_q_heads(CUtensorMap* out, const void* base, int dtype, int D, int h, int G, long long n_tokens, int box_tokens);
+
+bool tc_dense_supported(const nsa_dims_t& dm, int branch) {
+  if (dm.impl == NSA_IMPL_SIMT) return false;
+  if (!((dm.dtype == NSA_BF16 || dm.dtype == NSA_F16) && dm.Dk == 64 && dm.Dv == 64 && dm.h >= 1 && dm.h <= 64 && dm.S >= 1))
+    return false;
+  if (branch == 0) return dm.S_cmp >= 1;
+  if (branch == 2) return dm.S_win_kv >= 1 && dm.w >= 1;
+  return false;
+}
+
+template <typename T>
+static int launch_dense_t(const nsa_dims_t& dm, int branch, const void* Q, const void* K, const void* V, void* O, float* lse,
+                          cudaStream_t stream) {
+  const int TOK = 128 / dm.h;
+  CUtensorMap tmQ, tmK, tmV;
+  const int rows = branch == 0 ? dm.S_cmp : dm.S_win_kv;
+  const long long cap = branch == 0 ? dm.cap_cmp : dm.cap_win;
+  if (int rc = make_tmap_q_heads(&tmQ, Q, dm.dtype, 64, dm.h, dm.G, (long long)dm.B * dm.S, TOK)) return rc;
+  if (int rc = make_tmap_rows(&tmK, K, dm.dtype, 64, rows, 64, cap * 64, dm.B * dm.G, 128)) return rc;
+  if (int rc = make_tmap_rows(&tmV, V, dm.dtype, 64, rows, 64, cap * 64, dm.B * dm.G, 128)) return rc;
+  auto kern = dense_attn_tc_kernel<T>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DnSmem::total);
+    if (e != cudaSuccess) { set_error("dense tc: smem attr: %s", cudaGetErrorString(e)); return NSA_ERR_CUDA; }
+    attr_set = true;
+  }
+  const int grid = dm.B * dm.G * ceil_div(dm.S, kDnMT * TOK);
+  kern<<<grid, 32 * (4 * kDnMT + 2), DnSmem::total, stream>>>(tmQ, tmK, tmV, dm, branch, (T*)O, lse, TOK);
+  return check_launch("dense_attn_tc_kernel");
+}
+
+int launch_dense_tc(const nsa_dims_t& dm, int branch, const void* Q, const void* K, const void* V, void* O, float* lse,
+                    cudaStream_t stream) {
+  static_assert(sizeof(DnMisc) <= 512, "DnMisc must fit its slot");
+  if (dm.B * dm.S * dm.G == 0) return NSA_OK;
+  if (dm.dtype == NSA_BF16) return launch_dense_t<__nv_bfloat16>(dm, branch, Q, K, V, O, lse, stream);
+  return launch_dense_t<__half>(dm, branch, Q, K, V, O, lse, stream);
+}
+
+}  // namespace nsa

@@ -60,6 +60,24 @@ int make_tmap_q(CUtensorMap* out, const void* base, int dtype, int D, int h, int
   return NSA_OK;
 }
 
+// 4-D map over Q [tokens][G][h][D] whose box holds ALL heads of box_tokens tokens of one group: (D, h, 1, box_tokens)
+// -> smem rows ordered (token, head), 128 B each.
+int make_tmap_q_heads(CUtensorMap* out, const void* base, int dtype, int D, int h, int G, long long n_tokens, int box_tokens) {
+  auto enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return NSA_ERR_CUDA; }
+  NSA_REQUIRE(((uintptr_t)base & 15) == 0, "TMA needs 16-byte aligned tensors");
+  NSA_REQUIRE(D * 2 == 128, "TMA tiles here are 128-byte rows (D=64, 2-byte elements), got D=%d", D);
+  NSA_REQUIRE(h >= 1 && h <= 256 && box_tokens >= 1 && box_tokens <= 256, "Q box h=%d tokens=%d", h, box_tokens);
+  cuuint64_t gdim[4] = {(cuuint64_t)D, (cuuint64_t)h, (cuuint64_t)G, (cuuint64_t)n_tokens};
+  cuuint64_t gstr[3] = {(cuuint64_t)D * 2, (cuuint64_t)h * D * 2, (cuuint64_t)G * h * D * 2};
+  cuuint32_t box[4] = {(cuuint32_t)D, (cuuint32_t)h, 1, (cuuint32_t)box_tokens};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, tm_dtype(dtype), 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(Q heads) failed with CUresult %d", (int)r); return NSA_ERR_CUDA; }
+  return NSA_OK;
+}
+
 // ---- capability checks ---------------------------------------------------------------------------------------
 bool tc_sel_supported(const nsa_dims_t& dm);
 int launch_sel_tc(const nsa_dims_t& dm, const void* Q, const void* K, const void* V, const int32_t* ranges, void* O, float* lse,
@@ -70,15 +88,9 @@ bool tc_branch_supported(const nsa_dims_t& dm, int branch) {
   if (branch == 1) return tc_sel_supported(dm);
   return false;
 }
-bool tc_score_supported(const nsa_dims_t& dm) { (void)dm; return false; }
 bool tc_decode_supported(const nsa_dims_t& dm) { (void)dm; return false; }
-int64_t tc_score_workspace(const nsa_dims_t& dm) { (void)dm; return 0; }
 int64_t tc_decode_workspace(const nsa_dims_t& dm) { (void)dm; return 0; }
 
-int launch_score_tc(const nsa_dims_t&, const void*, const void*, int, int, int, int, float*, int32_t*, void*, cudaStream_t) {
-  set_error("tcgen05 scorer not built");
-  return NSA_ERR_UNSUPPORTED;
-}
 int launch_branch_tc(const nsa_dims_t& dm, int branch, const void* Q, const void* K, const void* V, const int32_t* ranges,
                      void* O_b, float* lse_b, cudaStream_t stream) {
   if (branch == 1) return launch_sel_tc(dm, Q, K, V, ranges, O_b, lse_b, stream);

@@ -1,0 +1,322 @@
+// Compressed-key scoring on tcgen05 tensor cores (NSA Eq.8-10):
+//   p_cmp = softmax_i(Q . K_cmp^T / sqrt(Dk))   (compute_pcmp_all, nsa/core/selection_scorer.py:42-61)
+//   p_slc = Eq.9 overlap stencil                (map_pcmp_to_pslc_batched, selection_scorer.py:89-116)
+//   p_grp = sum over the h heads of the group   (nsa_attention.py:1091)
+//
+// One CTA owns MT M-tiles of 128 rows; a row is one (token, head) of one (b, g), so TOK = 128 / h tokens fill an
+// M-tile and all heads of a token sit on adjacent TMEM lanes.  Key tiles of 128 compressed keys stream through a TMA
+// ring and are shared by the MT M-tiles.  The softmax is exact two-pass: pass 1 reduces the row max and normaliser
+// online, pass 2 recomputes S = Q.K^T (tensor work is cheap here: K = Dk = 64; the kernel is bound by exp throughput),
+// forms p = exp2(s*c - (m*c + log2 l)) and folds it through the Eq.9 stencil in ascending compressed index -- the
+// order of the reference's CPU scatter_add.  Nothing but p_grp [B,S,G,S_sel] leaves the SM.
+//
+// Warp roles: warps [0, 4*MT) softmax (thread = TMEM lane = row), warp 4*MT TMA producer, warp 4*MT+1 MMA issuer.
+#include "tc_common.cuh"
+#include "launchers.h"
+#include "select.cuh"
+
+namespace nsa {
+using namespace tc;
+
+constexpr int kScStages = 4;       // K ring depth (16 KB tiles)
+constexpr int kScTile = 128 * 128; // bytes of one 128-row x 64-element tile
+constexpr int kScRedLd = 33;       // padded row of the head-reduction buffer
+
+template <int MT>
+struct ScSmem {
+  static constexpr int q = 0;
+  static constexpr int ring = q + MT * kScTile;
+  static constexpr int red = ring + kScStages * kScTile;           // [MT][2][128][33] fp32
+  static constexpr int misc = red + MT * 2 * 128 * kScRedLd * 4;
+  static constexpr int total = misc + 256 + 1024;                   // + alignment slack
+};
+
+template <int MT>
+struct ScMisc {
+  uint64_t k_full[kScStages], k_empty[kScStages];
+  uint64_t s_full[MT][2], s_empty[MT][2];
+  uint64_t q_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// tcgen05.wait::ld that also names the destination registers, so no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// R = l_sel / d compressed blocks start inside one selection block; l = 2 d, so the last of them straddles into the
+// next selection block with weight 1/2 each (block_index.py:43-71).
+template <typename T, int MT, int R>
+__global__ void __launch_bounds__(32 * (4 * MT + 2), 1)
+score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, nsa_dims_t dm, int S_sel,
+                float* __restrict__ p_grp, int TOK) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  using SM = ScSmem<MT>;
+  ScMisc<MT>* ms = reinterpret_cast<ScMisc<MT>*>(smem + SM::misc);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kSoftWarps = 4 * MT;
+  constexpr int BPT = 128 / R;  // selection blocks completed per key tile
+
+  const int tiles_per_seq = ceil_div(dm.S, MT * TOK);
+  const int tile = blockIdx.x % tiles_per_seq;
+  const int bg = blockIdx.x / tiles_per_seq;
+  const int g = bg % dm.G, b = bg / dm.G;
+  const int s_base = tile * MT * TOK;
+  const bool causal = dm.norm_mode == NSA_NORM_CAUSAL;
+  int s_last = s_base + MT * TOK - 1;
+  if (s_last > dm.S - 1) s_last = dm.S - 1;
+  const int nk_cta = causal ? num_cmp_at(dm.t0 + s_last, dm.l, dm.d, dm.S_cmp) : dm.S_cmp;
+  const int NT = ceil_div(nk_cta, 128);        // key tiles with work
+  const int NTO = ceil_div(S_sel, BPT);        // output tiles (tiles >= NT only flush the carry / write zeros)
+
+  // ---- setup ---------------------------------------------------------------------------------------------
+  {  // rows of the Q tiles that TMA does not write (>= TOK*h) must hold finite data
+    uint4 z = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < MT * kScTile / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem + SM::q)[i] = z;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < kScStages; ++i) { mbar_init(&ms->k_full[i], 1); mbar_init(&ms->k_empty[i], 1); }
+    for (int m = 0; m < MT; ++m)
+      for (int i = 0; i < 2; ++i) { mbar_init(&ms->s_full[m][i], 1); mbar_init(&ms->s_empty[m][i], 4); }
+    mbar_init(&ms->q_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+  }
+  if (warp == 0) tmem_alloc(&ms->tmem_base, MT * 256);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ms->tmem_base;
+
+  if (warp == kSoftWarps) {
+    // ===== TMA producer ====================================================================================
+    if (lane == 0) {
+      mbar_expect_tx(&ms->q_full, MT * TOK * dm.h * 128);
+      for (int m = 0; m < MT; ++m)
+        tma_load_4d(smem + SM::q + m * kScTile, &tmQ, &ms->q_full, 0, 0, g, b * dm.S + s_base + m * TOK);
+      for (int it = 0; it < 2 * NT; ++it) {
+        const int ks = it % kScStages;
+        mbar_wait(&ms->k_empty[ks], ((it / kScStages) & 1) ^ 1);
+        mbar_expect_tx(&ms->k_full[ks], kScTile);
+        tma_load_3d(smem + SM::ring + ks * kScTile, &tmK, &ms->k_full[ks], 0, (it % NT) * 128, bg);
+      }
+    }
+  } else if (warp == kSoftWarps + 1) {
+    // ===== MMA issuer ======================================================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, 128, TcType<T>::fmt, 0, 0);
+      mbar_wait(&ms->q_full, 0);
+      for (int it = 0; it < 2 * NT; ++it) {
+        const int ks = it % kScStages, st = it & 1;
+        mbar_wait(&ms->k_full[ks], (it / kScStages) & 1);
+        const uint32_t kb = smem_u32(smem + SM::ring + ks * kScTile);
+        for (int m = 0; m < MT; ++m) {
+          mbar_wait(&ms->s_empty[m][st], ((it >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t qb = smem_u32(smem + SM::q + m * kScTile);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = make_smem_desc(qb + k * 32, 16, 1024, kSwizzle128B);
+            const uint64_t bd = make_smem_desc(kb + k * 32, 16, 1024, kSwizzle128B);
+            umma_f16(tmem + (m * 2 + st) * 128, ad, bd, idesc, k > 0);
+          }
+          umma_commit(&ms->s_full[m][st]);
+        }
+        umma_commit(&ms->k_empty[ks]);
+      }
+    }
+  } else {
+    // ===== softmax / Eq.9 / Eq.10 warps ====================================================================
+    const int mt = warp >> 2;
+    const int r = tid & 127;                              // row of the M-tile == TMEM lane
+    const int tok_l = r / dm.h;
+    const int s = s_base + mt * TOK + tok_l;
+    const bool row_ok = tok_l < TOK && s < dm.S;
+    const int t = dm.t0 + s;
+    const int nk = !row_ok ? 0 : (causal ? num_cmp_at(t, dm.l, dm.d, dm.S_cmp) : dm.S_cmp);
+    const float c = dm.scale * kLog2e;
+    const uint32_t tm_row = tmem + ((uint32_t)((warp & 3) * 32) << 16) + mt * 256;
+    float* red = reinterpret_cast<float*>(smem + SM::red) + (size_t)mt * 2 * 128 * kScRedLd;
+
+    // ---- pass 1: row max and normaliser --------------------------------------------------------------------
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int kt = 0; kt < NT; ++kt) {
+      const int it = kt, st = it & 1;
+      mbar_wait(&ms->s_full[mt][st], (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t va[32], vb[32];
+      tmem_ld32(tm_row + st * 128, va);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t(&cur)[32] = (ch & 1) ? vb : va;
+        uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
+        tmem_ld_wait32(cur);
+        if (ch < 3) tmem_ld32(tm_row + st * 128 + (ch + 1) * 32, nxt);
+        const int col0 = kt * 128 + ch * 32;
+        if (col0 < nk) {
+          float cm = -INFINITY;
+          if (col0 + 32 <= nk) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(cur[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (col0 + i >= nk) cur[i] = 0xff800000u;  // -inf
+              cm = fmaxf(cm, __uint_as_float(cur[i]));
+            }
+          }
+          const float m_new = fmaxf(m_run, cm);
+          const float mc = m_new * c;
+          float sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sum += ex2f(fmaf(__uint_as_float(cur[i]), c, -mc));
+          l_run = fmaf(l_run, ex2f((m_run - m_new) * c), sum);
+          m_run = m_new;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ms->s_empty[mt][st]);
+    }
+    // p = exp2(s*c - offs); rows without keys produce zeros
+    const bool has = l_run > 0.f;
+    const float offs = has ? fmaf(m_run, c, log2f(l_run)) : 0.f;
+
+    // ---- pass 2: probabilities -> Eq.9 -> Eq.10 ------------------------------------------------------------
+    float carry = 0.f;  // half of the last straddling compressed block, owed to the next selection block
+    for (int kt = 0; kt < NTO; ++kt) {
+      float* rb = red + (size_t)(kt & 1) * 128 * kScRedLd + (size_t)r * kScRedLd;
+      if (kt < NT) {
+        const int it = NT + kt, st = it & 1;
+        mbar_wait(&ms->s_full[mt][st], (it >> 1) & 1);
+        tc_fence_after();
+        uint32_t va[32], vb[32];
+        tmem_ld32(tm_row + st * 128, va);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t(&cur)[32] = (ch & 1) ? vb : va;
+          uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
+          tmem_ld_wait32(cur);
+          if (ch < 3) tmem_ld32(tm_row + st * 128 + (ch + 1) * 32, nxt);
+          const int col0 = kt * 128 + ch * 32;
+          float p[32];
+          if (has && col0 + 32 <= nk) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) p[i] = ex2f(fmaf(__uint_as_float(cur[i]), c, -offs));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              p[i] = (has && col0 + i < nk) ? ex2f(fmaf(__uint_as_float(cur[i]), c, -offs)) : 0.f;
+          }
+#pragma unroll
+          for (int jj = 0; jj < 32 / R; ++jj) {
+            float a = carry;
+#pragma unroll
+            for (int q = 0; q < R - 1; ++q) a += p[jj * R + q];
+            const float half = 0.5f * p[jj * R + R - 1];
+            a += half;
+            carry = half;
+            rb[ch * (32 / R) + jj] = a;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ms->s_empty[mt][st]);
+      } else {
+#pragma unroll 4
+        for (int jj = 0; jj < BPT; ++jj) rb[jj] = jj == 0 ? carry : 0.f;
+        carry = 0.f;
+      }
+      named_bar_sync(1 + mt, 128);
+      // Eq.10: sum the h head rows of each token; 32 lanes write 32 consecutive blocks of one token
+      const float* rd = red + (size_t)(kt & 1) * 128 * kScRedLd;
+      for (int idx = r; idx < TOK * BPT; idx += 128) {
+        const int tk = idx / BPT, cc = idx % BPT;
+        const int ss = s_base + mt * TOK + tk;
+        const int j = kt * BPT + cc;
+        if (ss < dm.S && j < S_sel) {
+          float a = 0.f;
+          for (int hh = 0; hh < dm.h; ++hh) a += rd[(size_t)(tk * dm.h + hh) * kScRedLd + cc];
+          p_grp[(((size_t)b * dm.S + ss) * dm.G + g) * S_sel + j] = a;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, MT * 256);
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------
+int make_tmap_q_heads(CUtensorMap* out, const void* base, int dtype, int D, int h, int G, long long n_tokens, int box_tokens);
+
+bool tc_score_supported(const nsa_dims_t& dm) {
+  if (dm.impl == NSA_IMPL_SIMT) return false;
+  return (dm.dtype == NSA_BF16 || dm.dtype == NSA_F16) && dm.Dk == 64 && dm.l == 2 * dm.d && dm.l_sel == 4 * dm.d &&
+         dm.h >= 1 && dm.h <= 64 && dm.S_cmp >= 1 && dm.S >= 1;
+}
+
+int64_t tc_score_workspace(const nsa_dims_t& dm) {
+  // p_grp staging for the fused score+select entry point: [B,S,G,S_sel] fp32 with S_sel <= ceil((t0+S)/l_sel) + 1
+  const int64_t S_sel = ceil_div(dm.t0 + dm.S > dm.l_sel ? dm.t0 + dm.S : dm.l_sel, dm.l_sel) + 1;
+  return (int64_t)dm.B * dm.S * dm.G * S_sel * 4;
+}
+
+template <typename T>
+static int launch_score_t(const nsa_dims_t& dm, const void* Q, const void* Kc, int S_sel, float* p_grp, cudaStream_t stream) {
+  constexpr int MT = 2;
+  const int TOK = 128 / dm.h;
+  CUtensorMap tmQ, tmK;
+  if (int rc = make_tmap_q_heads(&tmQ, Q, dm.dtype, 64, dm.h, dm.G, (long long)dm.B * dm.S, TOK)) return rc;
+  if (int rc = make_tmap_rows(&tmK, Kc, dm.dtype, 64, dm.S_cmp, 64, (long long)dm.cap_cmp * 64, dm.B * dm.G, 128)) return rc;
+  auto kern = score_tc_kernel<T, MT, 4>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ScSmem<MT>::total);
+    if (e != cudaSuccess) { set_error("score tc: smem attr: %s", cudaGetErrorString(e)); return NSA_ERR_CUDA; }
+    attr_set = true;
+  }
+  const int grid = dm.B * dm.G * ceil_div(dm.S, MT * TOK);
+  kern<<<grid, 32 * (4 * MT + 2), ScSmem<MT>::total, stream>>>(tmQ, tmK, dm, S_sel, p_grp, TOK);
+  return check_launch("score_tc_kernel");
+}
+
+int launch_score_tc(const nsa_dims_t& dm, const void* Q, const void* Kc, int S_sel, int S_total, int sel_mode, int Kr,
+                    float* p_grp, int32_t* ranges, void* workspace, cudaStream_t stream) {
+  static_assert(sizeof(ScMisc<2>) <= 256, "ScMisc must fit its slot");
+  if (dm.B * dm.S * dm.G == 0) return NSA_OK;
+  float* pg = p_grp;
+  if (!pg) {
+    NSA_REQUIRE(workspace, "score_select(tc): needs a workspace of nsa_workspace_bytes(NSA_WS_SCORE_SELECT) bytes");
+    NSA_REQUIRE((int64_t)dm.B * dm.S * dm.G * S_sel * 4 <= tc_score_workspace(dm), "score_select(tc): S_sel=%d exceeds the workspace", S_sel);
+    pg = reinterpret_cast<float*>(workspace);
+  }
+  int rc = dm.dtype == NSA_BF16 ? launch_score_t<__nv_bfloat16>(dm, Q, Kc, S_sel, pg, stream)
+                                : launch_score_t<__half>(dm, Q, Kc, S_sel, pg, stream);
+  if (rc) return rc;
+  if (!ranges) return NSA_OK;
+  const int nf = sel_mode == 0 ? prefill_forced_cols(S_total, dm.l_sel) : 3;
+  return launch_select(pg, dm.B * dm.S * dm.G, dm.S, dm.G, S_sel, dm.l_sel, dm.n_sel, sel_mode, nf, Kr, dm.t0, ranges, stream);
+}
+
+}  // namespace nsa

@@ -57,3 +57,48 @@ def test_prefill_core_tc_composition_bf16():
     err = (Oc.float().cpu() - want["O"]).abs()
     assert err.max() <= 2e-2 and err.mean() <= 1e-3, (err.max(), err.mean())
     assert torch.allclose(gates.cpu(), want["gates"], atol=1e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("norm", ["full_row", "causal"])
+@pytest.mark.parametrize("S,h,t0", [(700, 6, 0), (2064, 6, 0), (333, 8, 0), (96, 1, 0), (1200, 4, 0), (48, 16, 0)])
+def test_score_tc_vs_oracle(dtype, norm, S, h, t0):
+    """tcgen05 scorer (Q.K_cmp^T -> softmax -> Eq.9 -> Eq.10) against the fp32 oracle on the same 16-bit inputs.
+    Tolerance: p_grp entries are probabilities summed over h heads; max-abs 2e-5 * h (fp32 softmax of exact products)."""
+    ops = _ops()
+    B, G, l, d, ls, n, w = 2, 2, 32, 16, 64, 16, 512
+    gen = torch.Generator().manual_seed(S * 7 + h)
+    Q = torch.randn(B, S, G, h, 64, generator=gen).to(dtype).float()
+    Kc = torch.randn(B, G, O.num_cmp_blocks(S, l, d), 64, generator=gen).to(dtype).float()
+    nm = ops.NORM_CAUSAL if norm == "causal" else ops.NORM_FULL_ROW
+    cfg_tc = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w, impl=ops.IMPL_TC, norm_mode=nm)
+    cfg_si = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w, impl=ops.IMPL_SIMT, norm_mode=nm)
+    want = O.prefill_scores(Q, Kc, l, d, ls, n, w, norm)
+    got = ops.score_pgrp(Q.cuda().to(dtype), Kc.cuda().to(dtype), cfg_tc).cpu()
+    simt = ops.score_pgrp(Q.cuda().to(dtype), Kc.cuda().to(dtype), cfg_si).cpu()
+    assert got.shape == want.shape
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max() <= 2e-5 * h, (got - want).abs().max()
+    assert (got - simt).abs().max() <= 2e-5 * h
+    # rows sum to (number of heads with any key) like the reference's p_grp
+    assert torch.allclose(got.sum(-1), want.sum(-1), atol=1e-4 * h)
+    # fused scoring + selection == standalone selection on the same scores; near-ties only vs the oracle's scores
+    r = ops.score_select(Q.cuda().to(dtype), Kc.cuda().to(dtype), cfg_tc, mode=0).cpu()
+    assert torch.equal(r, ops.select_ranges_prefill(got.cuda(), ls, n, S).cpu())
+    ok, bad = O.ranges_equivalent(r, O.select_ranges_prefill(want, ls, n, S))
+    assert bad <= max(2, B * S * G // 200), f"{bad} of {B * S * G} rows differ"
+
+
+def test_score_tc_chunked_t0():
+    """Rows t0..t0+S-1 of a longer sequence (chunked prefill): same scores as the corresponding rows of the full run."""
+    ops = _ops()
+    B, G, h, l, d, ls, n, w = 1, 2, 6, 32, 16, 64, 16, 512
+    S_full, t0, S = 1024, 640, 200
+    gen = torch.Generator().manual_seed(11)
+    Q = torch.randn(B, S_full, G, h, 64, generator=gen).bfloat16()
+    Kc = torch.randn(B, G, O.num_cmp_blocks(S_full, l, d), 64, generator=gen).bfloat16()
+    for nm in (ops.NORM_FULL_ROW, ops.NORM_CAUSAL):
+        cfg = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w, impl=ops.IMPL_TC, norm_mode=nm)
+        full = ops.score_pgrp(Q.cuda(), Kc.cuda(), cfg)
+        part = ops.score_pgrp(Q[:, t0:t0 + S].contiguous().cuda(), Kc.cuda(), cfg, t0=t0, S_sel=full.shape[-1])
+        assert torch.equal(part, full[:, t0:t0 + S])
