@@ -80,13 +80,16 @@ int make_tmap_q_heads(CUtensorMap* out, const void* base, int dtype, int D, int 
 
 // ---- capability checks ---------------------------------------------------------------------------------------
 bool tc_sel_supported(const nsa_dims_t& dm);
+bool tc_dense_supported(const nsa_dims_t& dm, int branch);
+int launch_dense_tc(const nsa_dims_t& dm, int branch, const void* Q, const void* K, const void* V, void* O, float* lse,
+                    cudaStream_t stream);
 int launch_sel_tc(const nsa_dims_t& dm, const void* Q, const void* K, const void* V, const int32_t* ranges, void* O, float* lse,
                   cudaStream_t stream);
 
 bool tc_branch_supported(const nsa_dims_t& dm, int branch) {
   if (dm.impl == NSA_IMPL_SIMT) return false;
   if (branch == 1) return tc_sel_supported(dm);
-  return false;
+  return tc_dense_supported(dm, branch);
 }
 bool tc_decode_supported(const nsa_dims_t& dm) { (void)dm; return false; }
 int64_t tc_decode_workspace(const nsa_dims_t& dm) { (void)dm; return 0; }
@@ -94,8 +97,7 @@ int64_t tc_decode_workspace(const nsa_dims_t& dm) { (void)dm; return 0; }
 int launch_branch_tc(const nsa_dims_t& dm, int branch, const void* Q, const void* K, const void* V, const int32_t* ranges,
                      void* O_b, float* lse_b, cudaStream_t stream) {
   if (branch == 1) return launch_sel_tc(dm, Q, K, V, ranges, O_b, lse_b, stream);
-  set_error("tcgen05 kernel for branch %d not built", branch);
-  return NSA_ERR_UNSUPPORTED;
+  return launch_dense_tc(dm, branch, Q, K, V, O_b, lse_b, stream);
 }
 int launch_decode_tc(const nsa_dims_t&, const void*, const void*, const void*, const void*, const void*, const void*,
                      const void*, const nsa_gate_params_t&, void*, int32_t*, void*, cudaStream_t) {

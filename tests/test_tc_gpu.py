@@ -102,3 +102,66 @@ def test_score_tc_chunked_t0():
         full = ops.score_pgrp(Q.cuda(), Kc.cuda(), cfg)
         part = ops.score_pgrp(Q[:, t0:t0 + S].contiguous().cuda(), Kc.cuda(), cfg, t0=t0, S_sel=full.shape[-1])
         assert torch.equal(part, full[:, t0:t0 + S])
+
+
+def _check_branch(o, lse, want, lse_w):
+    err = (o.float().cpu() - want).abs()
+    assert torch.isfinite(o.float()).all()
+    assert err.max() <= 2e-2 and err.mean() <= 1e-3, (err.max(), err.mean())
+    fin = torch.isfinite(lse_w)
+    assert torch.equal(torch.isfinite(lse.cpu()), fin)
+    if fin.any():
+        assert (lse.cpu()[fin] - lse_w[fin]).abs().max() <= 2e-2
+    empty = ~fin
+    if empty.any():
+        assert torch.all(o.float().cpu()[empty] == 0)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("S,h,w", [(700, 6, 512), (1500, 4, 512), (333, 8, 64), (40, 1, 512), (2100, 6, 300), (130, 16, 1)])
+def test_dense_branches_tc_vs_oracle(dtype, S, h, w):
+    """tcgen05 dense ranged attention (cmp and win branches) against the fp32 oracle on the same 16-bit inputs.
+    Tolerance: max-abs 2e-2, MAE 1e-3 (bf16 P and O rounding)."""
+    ops = _ops()
+    B, G, l, d, ls, n = 2, 2, 32, 16, 64, 16
+    ts = _case(B, S, G, h, l, d, ls, n, w, seed=S + h + w, dtype=dtype)
+    cfg = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w, impl=ops.IMPL_TC)
+    Q = ts[0].cuda().to(dtype)
+    o, lse = ops.branch_attention(ops.BR_WIN, Q, ts[3].cuda().to(dtype), ts[4].cuda().to(dtype), cfg, return_lse=True)
+    _check_branch(o, lse, *O.win_attention(ts[0], ts[3], ts[4], w))
+    o, lse = ops.branch_attention(ops.BR_CMP, Q, ts[5].cuda().to(dtype), ts[6].cuda().to(dtype), cfg, return_lse=True)
+    _check_branch(o, lse, *O.cmp_attention(ts[0], ts[5], ts[6], l, d))
+
+
+def test_dense_branches_tc_chunked_rows():
+    """Query rows t0..t0+S-1 against full caches (chunked prefill): equals the same rows of the full run."""
+    ops = _ops()
+    B, G, h, l, d, ls, n, w = 1, 2, 6, 32, 16, 64, 16, 512
+    S_full, t0, S = 1400, 777, 300
+    ts = _case(B, S_full, G, h, l, d, ls, n, w, seed=5, dtype=torch.bfloat16)
+    cfg = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w, impl=ops.IMPL_TC)
+    dev = [t.cuda().bfloat16() for t in ts]
+    Qp = dev[0][:, t0:t0 + S].contiguous()
+    for br, K, V in ((ops.BR_WIN, dev[3], dev[4]), (ops.BR_CMP, dev[5], dev[6])):
+        full, lse_f = ops.branch_attention(br, dev[0], K, V, cfg, return_lse=True)
+        part, lse_p = ops.branch_attention(br, Qp, K, V, cfg, t0=t0, return_lse=True)
+        assert (part.float() - full[:, t0:t0 + S].float()).abs().max() <= 1e-2
+        assert (lse_p - lse_f[:, t0:t0 + S]).abs().max() <= 1e-3
+
+
+def test_prefill_core_all_tc_bf16_m7c():
+    """nsa_prefill_fwd with scoring and all three branches on tensor cores == oracle (given the same ranges)."""
+    ops = _ops()
+    B, S, G, h, l, d, ls, n, w = 2, 2048, 2, 6, 32, 16, 64, 16, 512
+    ts = _case(B, S, G, h, l, d, ls, n, w, seed=9, dtype=torch.bfloat16)
+    gen = torch.Generator().manual_seed(2)
+    gate = (torch.randn(32, 64, generator=gen) * 0.3, torch.randn(32, generator=gen) * 0.1, torch.randn(3, 32, generator=gen) * 0.5,
+            torch.zeros(3))
+    cfg = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w, impl=ops.IMPL_TC)
+    Oc, ranges, gates = ops.prefill_core(*[t.cuda().bfloat16() for t in ts], tuple(x.cuda() for x in gate), cfg, sel_mode=0)
+    want = O.prefill_core(*ts, gate, l=l, d=d, l_sel=ls, n_sel=n, w=w, ranges=ranges.cpu())
+    err = (Oc.float().cpu() - want["O"]).abs()
+    assert err.max() <= 2e-2 and err.mean() <= 1e-3, (err.max(), err.mean())
+    pg = O.prefill_scores(ts[0], ts[5], l, d, ls, n, w)
+    _, bad = O.ranges_equivalent(ranges.cpu(), O.select_ranges_prefill(pg, ls, n, S))
+    assert bad <= B * S * G // 200, bad
