@@ -268,7 +268,7 @@ int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which) {
   if (!dm) return 0;
   switch (which) {
     case NSA_WS_DECODE:
-      return (int64_t)dm->B * dm->G * dm->n_sel * 2 * sizeof(int32_t) + tc_decode_workspace(*dm);
+      return (((int64_t)dm->B * dm->G * dm->n_sel * 2 * sizeof(int32_t) + 15) & ~(int64_t)15) + tc_decode_workspace(*dm);
     case NSA_WS_SCORE_SELECT:
       return tc_score_workspace(*dm);
     case NSA_WS_PREFILL: {

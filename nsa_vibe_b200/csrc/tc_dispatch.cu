@@ -2,6 +2,7 @@
 // Shapes outside the specialisation of these kernels run on the SIMT kernels in generic.cu (same device,
 // same semantics) -- never on a CPU path.
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "launchers.h"
 #include "tc_common.cuh"
@@ -81,6 +82,11 @@ int make_tmap_q_heads(CUtensorMap* out, const void* base, int dtype, int D, int 
 // ---- capability checks ---------------------------------------------------------------------------------------
 bool tc_sel_supported(const nsa_dims_t& dm);
 bool tc_dense_supported(const nsa_dims_t& dm, int branch);
+bool tc_gather_supported(const nsa_dims_t& dm, int branch_mask);
+int launch_gather_tc(const nsa_dims_t& dm, int branch_mask, const void* Q, const void* const* K, const void* const* V,
+                     const int32_t* ranges, void* const* O_br, float* const* lse, const float* gates, void* O,
+                     const nsa_gate_params_t* gp_fuse, int S_sel, int32_t* ranges_out, cudaStream_t stream);
+bool tc_gather_fuse_supported(const nsa_dims_t& dm, int S_sel);
 int launch_dense_tc(const nsa_dims_t& dm, int branch, const void* Q, const void* K, const void* V, void* O, float* lse,
                     cudaStream_t stream);
 int launch_sel_tc(const nsa_dims_t& dm, const void* Q, const void* K, const void* V, const int32_t* ranges, void* O, float* lse,
@@ -88,21 +94,48 @@ int launch_sel_tc(const nsa_dims_t& dm, const void* Q, const void* K, const void
 
 bool tc_branch_supported(const nsa_dims_t& dm, int branch) {
   if (dm.impl == NSA_IMPL_SIMT) return false;
-  if (branch == 1) return tc_sel_supported(dm);
+  if (branch == 1) return tc_gather_supported(dm, 2);
   return tc_dense_supported(dm, branch);
 }
-bool tc_decode_supported(const nsa_dims_t& dm) { (void)dm; return false; }
-int64_t tc_decode_workspace(const nsa_dims_t& dm) { (void)dm; return 0; }
+// ---- decode step on the tensor-core gather kernel ---------------------------------------------------------------
+// workspace layout: [ranges: B*G*n_sel*2 int32 (used when ranges_out is NULL)] [gates: B*G*3 fp32]
+bool tc_decode_supported(const nsa_dims_t& dm) { return dm.S == 1 && tc_gather_supported(dm, 7); }
+int64_t tc_decode_workspace(const nsa_dims_t& dm) { return (int64_t)dm.B * dm.G * 3 * sizeof(float) + 16; }
+
+int launch_decode_tc(const nsa_dims_t& dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
+                     const void* V_win, const void* K_cmp, const void* V_cmp, const nsa_gate_params_t& gp, void* O,
+                     int32_t* ranges_out, void* workspace, cudaStream_t stream) {
+  NSA_REQUIRE(workspace, "decode_fwd(tc): needs a workspace of nsa_workspace_bytes(NSA_WS_DECODE) bytes");
+  const size_t rbytes = ((size_t)dm.B * dm.G * dm.n_sel * 2 * sizeof(int32_t) + 15) & ~(size_t)15;
+  int32_t* ranges = ranges_out ? ranges_out : reinterpret_cast<int32_t*>(workspace);
+  float* gates = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + rbytes);
+  const int t = dm.t0;
+  const int cover = t + 1 > dm.l_sel ? t + 1 : dm.l_sel;  // meta covers max(t+1, l_sel) tokens (nsa_attention.py:609-632)
+  const int S_sel = ceil_div(cover, dm.l_sel);
+  const void* Ks[3] = {K_cmp, K_sel, K_win};
+  const void* Vs[3] = {V_cmp, V_sel, V_win};
+  static const bool no_fuse = getenv("NSA_B200_DECODE_UNFUSED") != nullptr;  // A/B switch (benchmarks only)
+  if (!no_fuse && tc_gather_fuse_supported(dm, S_sel))  // one launch: scoring, selection, gate, three branches, combine
+    return launch_gather_tc(dm, 7, Q, Ks, Vs, nullptr, nullptr, nullptr, nullptr, O, &gp, S_sel, ranges_out, stream);
+  nsa_dims_t d2 = dm;
+  d2.norm_mode = NSA_NORM_FULL_ROW;  // decode sees only emitted blocks: softmax over all of them (:650-651)
+  if (int rc = launch_score_generic(d2, Q, K_cmp, S_sel, t + 1, 1, dm.n_sel, nullptr, ranges, stream)) return rc;
+  if (int rc = launch_gate_fwd(dm, Q, gp, gates, stream)) return rc;
+  return launch_gather_tc(dm, 7, Q, Ks, Vs, ranges, nullptr, nullptr, gates, O, nullptr, 0, nullptr, stream);
+}
 
 int launch_branch_tc(const nsa_dims_t& dm, int branch, const void* Q, const void* K, const void* V, const int32_t* ranges,
                      void* O_b, float* lse_b, cudaStream_t stream) {
-  if (branch == 1) return launch_sel_tc(dm, Q, K, V, ranges, O_b, lse_b, stream);
+  if (branch == 1) {
+    static const bool old_kernel = getenv("NSA_B200_OLD_SEL") != nullptr && tc_sel_supported(dm);  // A/B switch (benchmarks only)
+    if (old_kernel) return launch_sel_tc(dm, Q, K, V, ranges, O_b, lse_b, stream);
+    const void* Ks[3] = {nullptr, K, nullptr};
+    const void* Vs[3] = {nullptr, V, nullptr};
+    void* Os[3] = {nullptr, O_b, nullptr};
+    float* Ls[3] = {nullptr, lse_b, nullptr};
+    return launch_gather_tc(dm, 2, Q, Ks, Vs, ranges, Os, Ls, nullptr, nullptr, nullptr, 0, nullptr, stream);
+  }
   return launch_dense_tc(dm, branch, Q, K, V, O_b, lse_b, stream);
-}
-int launch_decode_tc(const nsa_dims_t&, const void*, const void*, const void*, const void*, const void*, const void*,
-                     const void*, const nsa_gate_params_t&, void*, int32_t*, void*, cudaStream_t) {
-  set_error("tcgen05 decode kernel not built");
-  return NSA_ERR_UNSUPPORTED;
 }
 
 }  // namespace nsa

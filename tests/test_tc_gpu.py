@@ -165,3 +165,45 @@ def test_prefill_core_all_tc_bf16_m7c():
     pg = O.prefill_scores(ts[0], ts[5], l, d, ls, n, w)
     _, bad = O.ranges_equivalent(ranges.cpu(), O.select_ranges_prefill(pg, ls, n, S))
     assert bad <= B * S * G // 200, bad
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("t,h,w,win_off", [(4095, 6, 512, 0), (1000, 6, 512, 0), (700, 4, 64, 200), (63, 8, 512, 0), (40, 2, 512, 0),
+                                            (2500, 6, 300, 0), (129, 1, 20, 100)])
+def test_decode_step_tc_vs_oracle(dtype, t, h, w, win_off):
+    """Fused decode step on the tcgen05 gather kernel (scoring + decode-rule selection + gate + cmp/sel/win attention +
+    combine in one launch) against the fp32 oracle on the same 16-bit inputs.  Ranges must be equivalent except at fp32
+    near-ties of p_grp; rows with the same ranges must agree within max-abs 2e-2 / MAE 1e-3."""
+    ops = _ops()
+    B, G, l, d, ls, n = 5, 2, 32, 16, 64, 16
+    n_tok = t + 1
+    cap = n_tok + 37
+    gen = torch.Generator().manual_seed(t + h)
+    r = lambda *s: torch.randn(*s, generator=gen).to(dtype).float()
+    S_cmp = O.num_cmp_blocks(n_tok, l, d)
+    q = r(B, G, h, 64)
+    K_sel, V_sel = r(B, G, cap, 64), r(B, G, cap, 64)
+    n_win = n_tok - win_off                       # the window cache holds tokens win_off .. t
+    K_win, V_win = r(B, G, n_win + 5, 64), r(B, G, n_win + 5, 64)
+    K_cmp, V_cmp = r(B, G, S_cmp + 3, 64), r(B, G, S_cmp + 3, 64)
+    gate = (torch.randn(32, 64, generator=gen) * 0.3, torch.randn(32, generator=gen) * 0.1, torch.randn(3, 32, generator=gen) * 0.5,
+            torch.randn(3, generator=gen) * 0.1)
+    lo = max(0, n_tok - w) - win_off
+    assert lo >= 0
+    want = O.decode_core(q, K_sel[:, :, :n_tok], V_sel[:, :, :n_tok], K_win[:, :, lo:n_win], V_win[:, :, lo:n_win],
+                         K_cmp[:, :, :S_cmp], V_cmp[:, :, :S_cmp], gate, l=l, d=d, l_sel=ls, n_sel=n, w=w)
+    cfg = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w, impl=ops.IMPL_TC)
+    rg = torch.full((B, G, n, 2), -7, dtype=torch.int32, device="cuda")
+    cu = lambda x: x.cuda().to(dtype)
+    got = ops.decode_core(cu(q[:, None]), cu(K_sel), cu(V_sel), cu(K_win), cu(V_win), cu(K_cmp), cu(V_cmp),
+                          tuple(x.cuda() for x in gate), cfg, t=t, S_sel_kv=n_tok, S_win_kv=n_win, win_off=win_off, S_cmp=S_cmp,
+                          ranges_out=rg)
+    assert torch.isfinite(got.float()).all()
+    rg = rg.cpu()
+    same = torch.tensor([[O.nonempty_ranges(rg[b, g].tolist()) == O.nonempty_ranges(want["ranges"][b, g].tolist())
+                          for g in range(G)] for b in range(B)])
+    assert (~same).sum() <= 1, f"{(~same).sum()} of {B * G} rows picked different blocks"
+    err = (got[:, 0].float().cpu() - want["O"]).abs()[same]
+    assert err.max() <= 2e-2 and err.mean() <= 1e-3, (err.max(), err.mean())
+    # causality and clamping of what was selected
+    assert (rg[..., 1] <= n_tok).all() and (rg[..., 0] >= 0).all()

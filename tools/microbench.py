@@ -53,6 +53,28 @@ def main():
                     c2 = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w, impl=impl)
                     ms = timeit(lambda: ops.branch_attention(br, Q, K, V, c2, ranges if br == 1 else None), n=3, warm=1)
                     print(f"branch {name} ({nm:4s})     : {ms:9.3f} ms")
+        if "decode" in what:
+            Sd, Bd = 4096, 512
+            cap = Sd + 64
+            Ks2, Vs2, Kw2, Vw2 = r(Bd, G, cap, D), r(Bd, G, cap, D), r(Bd, G, cap, D), r(Bd, G, cap, D)
+            Sc = (Sd - l) // d + 1
+            Kc2, Vc2 = r(Bd, G, Sc + 8, D), r(Bd, G, Sc + 8, D)
+            q = r(Bd, 1, G, h, D)
+            gc = ops._gate_struct(gate, torch.device(dev))
+            out = torch.empty((Bd, 1, G, h, D), dtype=torch.bfloat16, device=dev)
+            rg = torch.empty((Bd, G, n, 2), dtype=torch.int32, device=dev)
+            for impl, nm in ((ops.IMPL_AUTO, "auto"), (ops.IMPL_SIMT, "simt")):
+                c2 = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w, impl=impl)
+                f = lambda: ops.decode_core(q, Ks2, Vs2, Kw2, Vw2, Kc2, Vc2, gate, c2, t=Sd - 1, S_sel_kv=Sd, S_win_kv=Sd, win_off=0,
+                                            S_cmp=Sc, ranges_out=rg, out=out, gate_cache=gc)
+                ms = timeit(f, n=20, warm=3)
+                print(f"decode step B={Bd} S={Sd} ({nm:4s}): {1e3 * ms:9.1f} us  -> {Bd * 916992 / (ms * 1e-3) / 1e9:7.1f} GB/s algorithmic")
+            c2 = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w)
+            dm_q = q
+            ms = timeit(lambda: ops.score_select(q, Kc2, c2, mode=1, t0=Sd - 1, S_total=Sd, S_cmp=Sc), n=20, warm=3)
+            print(f"decode score_select only: {1e3 * ms:9.1f} us")
+            ms = timeit(lambda: ops.gate_forward(q, gate, c2), n=20, warm=3)
+            print(f"decode gate only        : {1e3 * ms:9.1f} us")
         if "fwd" in what:
             ms = timeit(lambda: ops.prefill_core(Q, Ks, Vs, Kw, Vw, Kc, Vc, gate, cfg, sel_mode=0, ranges=ranges), n=3, warm=1)
             print(f"prefill_fwd (given ranges): {ms:9.3f} ms")
