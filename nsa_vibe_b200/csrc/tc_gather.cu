@@ -29,14 +29,15 @@ constexpr int kGMaxBlk = 16;      // <= 1024 keys per item
 constexpr int kGMaxPairs = kGMaxBlk / 2;
 constexpr int kGPair = 128 * 128; // bytes of one pair stage
 constexpr int kGTmemCols = 256;   // S^T: 8 pairs x 16 columns; O^T: 2 x 16 columns
+constexpr int kGSlots = 4;        // block-list / Q^T slots: how far the producer may run ahead of the epilogue
 
 struct GSmem {
   static constexpr int ring = 0;
   static constexpr int P = ring + kGStages * kGPair;               // [2 slots][8 pairs][128 keys][8 heads] 16-bit
-  static constexpr int Qt = P + 2 * kGMaxPairs * 128 * kGN * 2;    // [2 slots][2 head groups][8 k-chunks][8 heads][8] 16-bit
-  static constexpr int misc = Qt + 2 * 2048;
-  static constexpr int fuse = misc + 1024;                          // fused decode scoring scratch (GFuse)
-  static constexpr int total = fuse + 7168 + 1024;
+  static constexpr int Qt = P + 2 * kGMaxPairs * 128 * kGN * 2;    // [4 slots][2 head groups][8 k-chunks][8 heads][8] 16-bit
+  static constexpr int misc = Qt + kGSlots * 2048;
+  static constexpr int fuse = misc + 1280;                          // fused decode scoring scratch (GFuse)
+  static constexpr int total = fuse + 6688 + 1024;                  // 2 CTAs per SM: 2 x (total + 1 KB) <= 228 KB
 };
 
 constexpr int kGMaxSel = 320;  // selection blocks the fused decode scorer can rank (1024 compressed keys -> <= 257)
@@ -45,18 +46,20 @@ constexpr int kGMaxSel = 320;  // selection blocks the fused decode scorer can r
 struct GFuse {
   float pkey[kGMaxPairs * 128];
   float pg[kGMaxSel];
-  int32_t ranges[64];
-  float gate3[4];
+  int32_t ranges[2][64];
+  float gate3[2][4];
   float qgp[64];
   float xs[128];
 };
+static_assert(sizeof(GFuse) <= 6688, "GFuse must fit its slot");
+
 
 struct GMisc {
   uint64_t full[kGStages], empty[kGStages];
-  uint64_t list_full[2], row_free[2], p_ready[2], o_done[2], s_done, s_free;
+  uint64_t list_full[kGSlots], row_free[kGSlots], p_ready[2], o_done[2], o_free[2], s_done, s_free, sel_ready[2];
   uint32_t tmem_base;
-  int nblk[2];
-  int blk_row[2][kGMaxBlk], blk_valid[2][kGMaxBlk];
+  int nblk[kGSlots];
+  int blk_row[kGSlots][kGMaxBlk], blk_valid[kGSlots][kGMaxBlk];
   float red_max[2][4][kGN], red_sum[2][4][kGN];
 };
 
@@ -76,10 +79,20 @@ struct GatherArgs {
   int32_t* ranges_out;  // [rows][n_sel][2] (may be NULL)
 };
 
+__device__ __forceinline__ float g_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void g_tmem_ld8f(uint32_t taddr, float (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void g_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 template <typename T>
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(192, 2)
 gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
                       const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1,
                       const __grid_constant__ CUtensorMap tmK2, const __grid_constant__ CUtensorMap tmV2, nsa_dims_t dm,
@@ -101,19 +114,33 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
   const long long tokens = (long long)dm.B * dm.G * dm.S;
   const long long tok_begin = (long long)blockIdx.x * tokens / gridDim.x;
   const long long tok_end = (long long)(blockIdx.x + 1) * tokens / gridDim.x;
-  const long long first = tok_begin * nbr;
   const int n_it = (int)(tok_end - tok_begin) * nbr;
 
-  // item -> (row, branch, t); items ordered (b, g, s, branch) so a CTA walks consecutive tokens of one (b, g)
-  auto decode_item = [&](int it, size_t& row, int& bg, int& br, int& t) {
-    const long long gi = first + it;
-    br = brs[(int)(gi % nbr)];
-    const long long tok = gi / nbr;
+  // item -> (row, branch, t, token parity).  Plain order is (b, g, s, branch), so a CTA walks consecutive tokens of one
+  // (b, g).  A fused decode step interleaves tokens -- c0 w0 c1 s0 w1 c2 s1 w2 ... -- so the ranges a token selects
+  // (during its cmp item) are three items old when its sel item needs them.
+  const int n_tok = n_it / (nbr > 0 ? nbr : 1);
+  auto decode_item = [&](int it, size_t& row, int& bg, int& br, int& t, int& tp) {
+    int tk, b3;
+    if (a.fuse) {
+      if (it < 2) { tk = 0; b3 = it; }
+      else if (it == n_it - 1) { tk = n_tok - 1; b3 = 2; }
+      else {
+        const int k = (it + 1) / 3, r = (it + 1) % 3;
+        if (r == 0) { tk = k; b3 = 0; } else if (r == 1) { tk = k - 1; b3 = 2; } else { tk = k; b3 = 1; }
+      }
+    } else {
+      tk = it / nbr;
+      b3 = it % nbr;
+    }
+    br = brs[b3];
+    const long long tok = tok_begin + tk;
     const int s = (int)(tok % dm.S);
     bg = (int)(tok / dm.S);
     const int g = bg % dm.G, b = bg / dm.G;
     row = ((size_t)b * dm.S + s) * dm.G + g;
     t = dm.t0 + s;
+    tp = tk & 1;
   };
 
   // ---- one-time setup ---------------------------------------------------------------------------------
@@ -123,11 +150,15 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
   }
   if (tid == 0) {
     for (int i = 0; i < kGStages; ++i) { mbar_init(&ms->full[i], 1); mbar_init(&ms->empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kGSlots; ++i) {
       mbar_init(&ms->list_full[i], 1);
       mbar_init(&ms->row_free[i], 4);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ms->o_free[i], 4);
       mbar_init(&ms->p_ready[i], 4);
       mbar_init(&ms->o_done[i], 1);
+      mbar_init(&ms->sel_ready[i], 1);
     }
     mbar_init(&ms->s_done, 1);
     mbar_init(&ms->s_free, 4);
@@ -151,7 +182,8 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
     }
     uint32_t n_loads = 0;
     int prev_bg = 0, prev_br = 0;
-    auto issue_pairs = [&](int rs, int bg, int br, bool is_v) {  // lane 0 only
+    int tok_sel_count[2] = {0, 0};
+    auto issue_pairs = [&](int rs, int bg, int br, bool is_v) {  // lane 0 only; rs = list slot
       const CUtensorMap* tm = br == 0 ? (is_v ? &tmV0 : &tmK0) : (br == 1 ? (is_v ? &tmV1 : &tmK1) : (is_v ? &tmV2 : &tmK2));
       const int nblk = ms->nblk[rs];
       const int np = (nblk + 1) >> 1;
@@ -169,8 +201,8 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
     // hides behind the TMA issue loop
     struct Pre { int a0, a1; uint4 q[4]; };
     auto prefetch = [&](int it, Pre& pr) {
-      size_t row; int bg, br, t;
-      decode_item(it, row, bg, br, t);
+      size_t row; int bg, br, t, tp;
+      decode_item(it, row, bg, br, t, tp);
       pr.a0 = 0; pr.a1 = 0;
       if (br == 1) {
         if (lane < dm.n_ranges && !a.fuse) {
@@ -201,16 +233,19 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
     Pre cur, nxt;
     if (n_it > 0) prefetch(0, cur);
     for (int it = 0; it < n_it; ++it) {
-      const int rs = it & 1;
-      size_t row; int bg, br, t;
-      decode_item(it, row, bg, br, t);
+      const int rs = it & (kGSlots - 1);  // list / Q^T slot
+      size_t row; int bg, br, t, tp;
+      decode_item(it, row, bg, br, t, tp);
       if (it + 1 < n_it) prefetch(it + 1, nxt);
-      mbar_wait(&ms->row_free[rs], ((it >> 1) & 1) ^ 1);
+      mbar_wait(&ms->row_free[rs], ((it / kGSlots) & 1) ^ 1);
       // ---- block list: each lane owns one [a0, a1) piece, a warp prefix sum places its 64-key blocks ----
       int a0 = cur.a0, a1 = cur.a1;
-      if (a.fuse && br == 1 && lane < dm.n_ranges) {  // ranges this CTA selected while the cmp item was in its softmax
-        a0 = fz->ranges[2 * lane] < 0 ? 0 : fz->ranges[2 * lane];
-        a1 = fz->ranges[2 * lane + 1] > dm.S_sel_kv ? dm.S_sel_kv : fz->ranges[2 * lane + 1];
+      if (a.fuse && br == 1) {  // ranges this CTA selected while the token's cmp item was in its softmax
+        mbar_wait(&ms->sel_ready[tp], ((tok_sel_count[tp]++) & 1));
+        if (lane < dm.n_ranges) {
+          a0 = fz->ranges[tp][2 * lane] < 0 ? 0 : fz->ranges[tp][2 * lane];
+          a1 = fz->ranges[tp][2 * lane + 1] > dm.S_sel_kv ? dm.S_sel_kv : fz->ranges[tp][2 * lane + 1];
+        }
       }
       const int nb = a1 > a0 ? (a1 - a0 + 63) >> 6 : 0;
       int incl = nb;
@@ -243,13 +278,13 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
       if (lane == 0) {
         mbar_arrive(&ms->list_full[rs]);
         issue_pairs(rs, bg, br, false);                       // K pairs of item it
-        if (it > 0) issue_pairs(rs ^ 1, prev_bg, prev_br, true);  // V pairs of item it-1
+        if (it > 0) issue_pairs((it - 1) & (kGSlots - 1), prev_bg, prev_br, true);  // V pairs of item it-1
       }
       prev_bg = bg; prev_br = br;
       cur = nxt;
       __syncwarp();
     }
-    if (lane == 0 && n_it > 0) issue_pairs((n_it - 1) & 1, prev_bg, prev_br, true);
+    if (lane == 0 && n_it > 0) issue_pairs((n_it - 1) & (kGSlots - 1), prev_bg, prev_br, true);
   } else if (warp == 5) {
     // ===== MMA issuer ======================================================================================
     if (lane == 0) {
@@ -257,10 +292,11 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
       constexpr uint32_t idesc_pv = make_idesc_f16(64, kGN, TcType<T>::fmt, 1, 1);
       uint32_t n_cons = 0;
       auto pv = [&](int i) {
-        const int rs = i & 1;
-        const int nblk = ms->nblk[rs];
+        const int rs = i & 1, ls = i & (kGSlots - 1);
+        const int nblk = ms->nblk[ls];
         const int np = (nblk + 1) >> 1;
         mbar_wait(&ms->p_ready[rs], (i >> 1) & 1);
+        mbar_wait(&ms->o_free[rs], ((i >> 1) & 1) ^ 1);  // the epilogue of item i-2 has read this O^T slot
         tc_fence_after();
         bool first_mma = true;
         for (int j = 0; j < np; ++j) {
@@ -269,8 +305,8 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
           tc_fence_after();
           const uint32_t v_base = smem_u32(ring + st * kGPair);
           const uint32_t p_base = smem_u32(smem + GSmem::P + (rs * kGMaxPairs + j) * 128 * 16);
-          int keys = ms->blk_valid[rs][2 * j];
-          if (2 * j + 1 < nblk) keys = 64 + ms->blk_valid[rs][2 * j + 1];
+          int keys = ms->blk_valid[ls][2 * j];
+          if (2 * j + 1 < nblk) keys = 64 + ms->blk_valid[ls][2 * j + 1];
           const int ksteps = (keys + 15) >> 4;  // skip k-steps made only of masked keys
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t ad = make_smem_desc(v_base + k * 2048, 8192, 1024, kSwizzle128B);  // V^T: MN-major A
@@ -284,13 +320,13 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
         umma_commit(&ms->o_done[rs]);
       };
       for (int it = 0; it < n_it; ++it) {
-        const int rs = it & 1;
-        mbar_wait(&ms->list_full[rs], (it >> 1) & 1);
-        const int nblk = ms->nblk[rs];
+        const int ls = it & (kGSlots - 1);
+        mbar_wait(&ms->list_full[ls], (it / kGSlots) & 1);
+        const int nblk = ms->nblk[ls];
         const int np = (nblk + 1) >> 1;
         mbar_wait(&ms->s_free, (it & 1) ^ 1);  // the softmax warps hold S^T of item it-1 in registers
         tc_fence_after();
-        const uint32_t q_base = smem_u32(smem + GSmem::Qt + rs * 2048);
+        const uint32_t q_base = smem_u32(smem + GSmem::Qt + ls * 2048);
         for (int j = 0; j < np; ++j) {
           const uint32_t st = n_cons % kGStages;
           mbar_wait(&ms->full[st], (n_cons / kGStages) & 1);
@@ -312,44 +348,61 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
     }
   } else {
     // ===== softmax + epilogue warps: thread = key lane of every pair ========================================
+    // Per item: A = pull S^T out of TMEM (frees it for the next item's Q.K^T), B = softmax + P^T (+ fused decode
+    // scoring), C = epilogue once P.V is done.  A of item it+1 runs BEFORE C of item it, so the MMA thread never waits
+    // for an epilogue and the TMA ring keeps moving across item boundaries.
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const float sl2 = dm.scale * kLog2e;
     const bool combine = (a.gates != nullptr || a.fuse) && a.O != nullptr;
-    float comb[kGN];
+    float comb0[kGN], comb1[kGN];  // gated sums of the (at most two) tokens in flight
 #pragma unroll
-    for (int e = 0; e < kGN; ++e) comb[e] = 0.f;
+    for (int e = 0; e < kGN; ++e) { comb0[e] = 0.f; comb1[e] = 0.f; }
+    float sc[kGMaxPairs][kGN];
 
-    for (int it = 0; it < n_it; ++it) {
-      const int rs = it & 1;
-      size_t row; int bg, br, t;
-      decode_item(it, row, bg, br, t);
-      mbar_wait(&ms->list_full[rs], (it >> 1) & 1);
-      const int nblk = ms->nblk[rs];
+    auto stage_a = [&](int it) {  // S^T -> registers (masked), arrive s_free
+      const int ls = it & (kGSlots - 1);
+      mbar_wait(&ms->list_full[ls], (it / kGSlots) & 1);
+      const int nblk = ms->nblk[ls];
       const int np = (nblk + 1) >> 1;
       mbar_wait(&ms->s_done, it & 1);
       tc_fence_after();
-      float sc[kGMaxPairs][kGN];
+#pragma unroll
+      for (int j = 0; j < kGMaxPairs; ++j)
+        if (j < np) g_tmem_ld8f(tmem_S + lane_base + j * kGNQ, sc[j]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < kGMaxPairs; ++j)  // no use of the loaded registers may be scheduled above the wait
+        asm volatile("" : "+f"(sc[j][0]), "+f"(sc[j][1]), "+f"(sc[j][2]), "+f"(sc[j][3]), "+f"(sc[j][4]), "+f"(sc[j][5]),
+                          "+f"(sc[j][6]), "+f"(sc[j][7]));
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ms->s_free);
+#pragma unroll
+      for (int j = 0; j < kGMaxPairs; ++j) {
+        const int blk = 2 * j + (tid >> 6);
+        const bool ok = j < np && blk < nblk && (tid & 63) < ms->blk_valid[ls][blk];
+#pragma unroll
+        for (int e = 0; e < kGN; ++e) sc[j][e] = ok ? sc[j][e] : -INFINITY;
+      }
+    };
+
+    if (n_it > 0) stage_a(0);
+    for (int it = 0; it < n_it; ++it) {
+      const int rs = it & 1, ls = it & (kGSlots - 1);
+      size_t row; int bg, br, t, tp;
+      decode_item(it, row, bg, br, t, tp);
+      const int nblk = ms->nblk[ls];
+      const int np = (nblk + 1) >> 1;
+      // ---- B: exact softmax over the item's keys ------------------------------------------------------------
       float mx[kGN];
 #pragma unroll
       for (int e = 0; e < kGN; ++e) mx[e] = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < kGMaxPairs; ++j) {
+      for (int j = 0; j < kGMaxPairs; ++j)
         if (j < np) {
-          uint32_t r[8];
-          tmem_ld8(tmem_S + lane_base + j * kGNQ, r);
-          tmem_ld_wait();
-          const int blk = 2 * j + (tid >> 6);
-          const bool ok = blk < nblk && (tid & 63) < ms->blk_valid[rs][blk];
 #pragma unroll
-          for (int e = 0; e < kGN; ++e) {
-            sc[j][e] = ok ? __uint_as_float(r[e]) : -INFINITY;
-            mx[e] = fmaxf(mx[e], sc[j][e]);
-          }
+          for (int e = 0; e < kGN; ++e) mx[e] = fmaxf(mx[e], sc[j][e]);
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ms->s_free);
 #pragma unroll
       for (int e = 0; e < kGN; ++e) mx[e] = warp_max(mx[e]);
       if (lane == 0) {
@@ -361,6 +414,7 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
 #pragma unroll
       for (int e = 0; e < kGN; ++e) {
         mx[e] = fmaxf(fmaxf(ms->red_max[rs][0][e], ms->red_max[rs][1][e]), fmaxf(ms->red_max[rs][2][e], ms->red_max[rs][3][e]));
+        mx[e] = mx[e] > -INFINITY ? mx[e] * sl2 : 0.f;  // log2-domain offset; all-masked head slots stay finite
         sum[e] = 0.f;
       }
       uint8_t* Pbuf = smem + GSmem::P + rs * kGMaxPairs * 128 * 16;
@@ -370,8 +424,8 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
           uint32_t pk[4];
 #pragma unroll
           for (int e = 0; e < kGN; e += 2) {
-            const float p0 = exp2f((sc[j][e] - mx[e]) * sl2);  // masked keys: exp2(-inf) = 0
-            const float p1 = exp2f((sc[j][e + 1] - mx[e + 1]) * sl2);
+            const float p0 = g_ex2(fmaf(sc[j][e], sl2, -mx[e]));  // masked keys: ex2(-inf) = 0
+            const float p1 = g_ex2(fmaf(sc[j][e + 1], sl2, -mx[e + 1]));
             sum[e] += p0;
             sum[e + 1] += p1;
             sc[j][e] = p0;
@@ -412,7 +466,7 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
           }
         }
         g_named_bar(1, 128);
-        const int nkeys = nblk > 0 ? (nblk - 1) * 64 + ms->blk_valid[rs][nblk - 1] : 0;
+        const int nkeys = nblk > 0 ? (nblk - 1) * 64 + ms->blk_valid[ls][nblk - 1] : 0;
         for (int blk = tid; blk < a.S_sel; blk += 128) {  // Eq.9 with l = 2d, l_sel = 4d, ascending compressed index
           const int i0 = 4 * blk;
           float acc = (i0 - 1 >= 0 && i0 - 1 < nkeys) ? 0.5f * fz->pkey[i0 - 1] : 0.f;
@@ -431,49 +485,58 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
           }
           __syncwarp();
           Gate3 gt = gate_forward_warp(fz->qgp, fz->xs, nullptr, a.gp, 64, dm.gate_hidden, dm.gate_tau, dm.gate_mode, nullptr);
-          if (lane == 0) { fz->gate3[0] = gt.c; fz->gate3[1] = gt.s; fz->gate3[2] = gt.w; }
+          if (lane == 0) { fz->gate3[tp][0] = gt.c; fz->gate3[tp][1] = gt.s; fz->gate3[tp][2] = gt.w; }
         }
         g_named_bar(1, 128);
         if (warp == 0) {
-          select_row_warp(fz->pg, a.S_sel, dm.l_sel, dm.n_sel, 1, 3, dm.n_sel, t, fz->ranges);
+          select_row_warp(fz->pg, a.S_sel, dm.l_sel, dm.n_sel, 1, 3, dm.n_sel, t, fz->ranges[tp]);
           __syncwarp();
           if (a.ranges_out && lane < dm.n_sel)
-            *reinterpret_cast<int2*>(a.ranges_out + (row * dm.n_sel + lane) * 2) = make_int2(fz->ranges[2 * lane], fz->ranges[2 * lane + 1]);
+            *reinterpret_cast<int2*>(a.ranges_out + (row * dm.n_sel + lane) * 2) =
+                make_int2(fz->ranges[tp][2 * lane], fz->ranges[tp][2 * lane + 1]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ms->sel_ready[tp]);
         }
       }
 
-      // ---- epilogue: O^T (64 dv x 8 heads, M=64 layout: dv row r on lane 32*(r/16) + r%16) -------------------
+      // ---- A of the next item ----------------------------------------------------------------------------------
+      if (it + 1 < n_it) stage_a(it + 1);
+
+      // ---- C: epilogue: O^T (64 dv x 8 heads, M=64 layout: dv row r on lane 32*(r/16) + r%16) ---------------------
       mbar_wait(&ms->o_done[rs], (it >> 1) & 1);
       tc_fence_after();
       uint32_t r[8];
       if (nblk > 0) {
         tmem_ld8(tmem_O + rs * 16 + lane_base, r);
         tmem_ld_wait();
+        asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]));
       } else {
 #pragma unroll
         for (int e = 0; e < kGN; ++e) r[e] = 0u;  // empty item -> zeros, lse = -inf (attention_kernels.py:769-771)
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ms->o_free[rs]);
       float gate = 1.f;
-      if (a.fuse) gate = fz->gate3[br];
+      if (a.fuse) gate = fz->gate3[tp][br];
       else if (combine) gate = a.gates[row * 3 + br];
       if (lane < 16) {
         const int dv = warp * 16 + lane;
         T* ob = a.O_br[br] ? reinterpret_cast<T*>(a.O_br[br]) : nullptr;
+        const bool last = combine && br == brs[nbr - 1];  // last branch item of this token: write the gated output
+        T* of = reinterpret_cast<T*>(a.O);
 #pragma unroll
         for (int e = 0; e < kGN; ++e) {
           if (e < h) {
             const float l = ms->red_sum[rs][0][e] + ms->red_sum[rs][1][e] + ms->red_sum[rs][2][e] + ms->red_sum[rs][3][e];
             const float o = l > 0.f ? __uint_as_float(r[e]) / l : 0.f;
             if (ob) ob[(row * h + e) * 64 + dv] = T(o);
-            if (combine) comb[e] = fmaf(gate, o, comb[e]);
-          }
-        }
-        if (combine && br == brs[nbr - 1]) {  // last branch item of this token: write the gated output
-          T* of = reinterpret_cast<T*>(a.O);
-#pragma unroll
-          for (int e = 0; e < kGN; ++e) {
-            if (e < h) of[(row * h + e) * 64 + dv] = T(comb[e]);
-            comb[e] = 0.f;
+            if (combine) {
+              const float c = fmaf(gate, o, tp ? comb1[e] : comb0[e]);
+              if (last) of[(row * h + e) * 64 + dv] = T(c);
+              if (tp) comb1[e] = last ? 0.f : c;
+              else comb0[e] = last ? 0.f : c;
+            }
           }
         }
       }
@@ -484,7 +547,7 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ms->row_free[rs]);
+      if (lane == 0) mbar_arrive(&ms->row_free[ls]);
     }
   }
 
@@ -552,7 +615,7 @@ bool tc_gather_fuse_supported(const nsa_dims_t& dm, int S_sel) {
 int launch_gather_tc(const nsa_dims_t& dm, int branch_mask, const void* Q, const void* const* K, const void* const* V,
                      const int32_t* ranges, void* const* O_br, float* const* lse, const float* gates, void* O,
                      const nsa_gate_params_t* gp_fuse, int S_sel, int32_t* ranges_out, cudaStream_t stream) {
-  static_assert(sizeof(GMisc) <= 1024, "GMisc must fit its slot");
+  static_assert(sizeof(GMisc) <= 1280, "GMisc must fit its slot");
   if (dm.B * dm.S * dm.G == 0 || branch_mask == 0) return NSA_OK;
   GatherArgs a;
   memset(&a, 0, sizeof(a));
