@@ -207,7 +207,7 @@ def main():
     ap.add_argument("--S", type=int, default=65536)
     ap.add_argument("--B", type=int, default=1, help="sequences per GPU in the prefill step")
     ap.add_argument("--decode-S", type=int, default=4096)
-    ap.add_argument("--decode-B", type=int, default=512, help="sequences per GPU in the decode step")
+    ap.add_argument("--decode-B", type=int, default=592, help="sequences per GPU in the decode step (592 x G=2 = 4 (b,g) rows per resident CTA: 2 CTAs x 148 SMs)")
     ap.add_argument("--cpu-rows", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-decode", action="store_true")

@@ -88,6 +88,23 @@ __device__ inline void select_row_warp(float* sc, int S_sel, int l_sel, int n_se
         sc[j] = c;
         if (c > best) { best = c; best_j = j; }  // ascending j: first maximum = lowest index
       }
+      if (S_sel <= 128) {
+        // Few candidates (decode, short prefill): rank every candidate against all others instead of k rounds of warp
+        // arg-max.  rank_j = #{i : c_i > c_j or (c_i == c_j and i < j)}; j is picked iff rank_j < k and c_j > -inf --
+        // the same set the rounds below produce, with no serial dependence between picks.
+        __syncwarp();
+        for (int s = 0; s * 32 < S_sel; ++s) {
+          const int j = s * 32 + lane;
+          const float c = j < S_sel ? sc[j] : NEG;
+          int rank = 0;
+          for (int i = 0; i < S_sel; ++i) {
+            const float ci = sc[i];
+            rank += (ci > c || (ci == c && i < j)) ? 1 : 0;
+          }
+          const uint32_t word = __ballot_sync(0xffffffffu, c > NEG && rank < k_act);
+          if ((s & 31) == lane) bm[s >> 5] |= word;
+        }
+      } else
       for (int it = 0; it < k_act; ++it) {
         float v = best;
         int vj = best_j;

@@ -13,6 +13,7 @@
 // softmax + epilogue.  With gates given, the three branch items of a token are combined in registers and only the gated
 // O is written (decode: branch outputs never reach HBM).
 #include "tc_common.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 #include "launchers.h"
@@ -37,9 +38,10 @@ struct GSmem {
   static constexpr int Qt = P + 2 * kGMaxPairs * 128 * kGN * 2;    // [4 slots][2 head groups][8 k-chunks][8 heads][8] 16-bit
   static constexpr int misc = Qt + kGSlots * 2048;
   static constexpr int fuse = misc + 1280;                          // fused decode scoring scratch (GFuse)
-  static constexpr int total = fuse + 6688 + 1024;                  // 2 CTAs per SM: 2 x (total + 1 KB) <= 228 KB
+  static constexpr int total = fuse + 6784 + 1024;                  // 2 CTAs per SM: 2 x (total + 1 KB) <= 228 KB
 };
 
+constexpr int kGGateSlots = 8;
 constexpr int kGMaxSel = 320;  // selection blocks the fused decode scorer can rank (1024 compressed keys -> <= 257)
 
 // scratch of the fused decode step: p_cmp summed over heads per compressed key, p_grp, the selected ranges, gate MLP
@@ -47,11 +49,11 @@ struct GFuse {
   float pkey[kGMaxPairs * 128];
   float pg[kGMaxSel];
   int32_t ranges[2][64];
-  float gate3[2][4];
+  float gate3[kGGateSlots][4];  // per token of this CTA (slot = token % kGGateSlots)
   float qgp[64];
   float xs[128];
 };
-static_assert(sizeof(GFuse) <= 6688, "GFuse must fit its slot");
+static_assert(sizeof(GFuse) <= 6784, "GFuse must fit its slot");
 
 
 struct GMisc {
@@ -77,7 +79,16 @@ struct GatherArgs {
   int S_sel;
   nsa_gate_params_t gp;
   int32_t* ranges_out;  // [rows][n_sel][2] (may be NULL)
+  long long* dbg;       // debug timeline of CTA 0 (NSA_B200_GATHER_DBG=1), else NULL
 };
+
+#define GDBG(tag, it)                                                                 \
+  do {                                                                                \
+    if (a.dbg && blockIdx.x == 0) {                                                   \
+      const unsigned long long i_ = atomicAdd((unsigned long long*)a.dbg, 1ull);      \
+      if (i_ < 4000) { a.dbg[1 + 2 * i_] = ((long long)(tag) << 32) | (unsigned)(it); a.dbg[2 + 2 * i_] = clock64(); } \
+    }                                                                                 \
+  } while (0)
 
 __device__ __forceinline__ float g_ex2(float x) {
   float y;
@@ -111,9 +122,9 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
   if (a.branch_mask & 2) brs[nbr++] = 1;
   GFuse* fz = reinterpret_cast<GFuse*>(smem + GSmem::fuse);
   // balanced partition of the tokens (b, g, s) over the grid; a token's branch items stay in one CTA
-  const long long tokens = (long long)dm.B * dm.G * dm.S;
-  const long long tok_begin = (long long)blockIdx.x * tokens / gridDim.x;
-  const long long tok_end = (long long)(blockIdx.x + 1) * tokens / gridDim.x;
+  const long long tokens = (long long)dm.B * dm.G * dm.S;  // < 2^31 (checked on the host)
+  const int tok_begin = (int)((long long)blockIdx.x * tokens / gridDim.x);
+  const int tok_end = (int)((long long)(blockIdx.x + 1) * tokens / gridDim.x);
   const int n_it = (int)(tok_end - tok_begin) * nbr;
 
   // item -> (row, branch, t, token parity).  Plain order is (b, g, s, branch), so a CTA walks consecutive tokens of one
@@ -134,13 +145,13 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
       b3 = it % nbr;
     }
     br = brs[b3];
-    const long long tok = tok_begin + tk;
-    const int s = (int)(tok % dm.S);
-    bg = (int)(tok / dm.S);
+    const int tok = tok_begin + tk;
+    bg = tok / dm.S;
+    const int s = tok - bg * dm.S;
     const int g = bg % dm.G, b = bg / dm.G;
     row = ((size_t)b * dm.S + s) * dm.G + g;
     t = dm.t0 + s;
-    tp = tk & 1;
+    tp = tk;
   };
 
   // ---- one-time setup ---------------------------------------------------------------------------------
@@ -237,14 +248,16 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
       size_t row; int bg, br, t, tp;
       decode_item(it, row, bg, br, t, tp);
       if (it + 1 < n_it) prefetch(it + 1, nxt);
+      if (lane == 0) GDBG(1, it);
       mbar_wait(&ms->row_free[rs], ((it / kGSlots) & 1) ^ 1);
+      if (lane == 0) GDBG(2, it);
       // ---- block list: each lane owns one [a0, a1) piece, a warp prefix sum places its 64-key blocks ----
       int a0 = cur.a0, a1 = cur.a1;
       if (a.fuse && br == 1) {  // ranges this CTA selected while the token's cmp item was in its softmax
-        mbar_wait(&ms->sel_ready[tp], ((tok_sel_count[tp]++) & 1));
+        mbar_wait(&ms->sel_ready[tp & 1], ((tok_sel_count[tp & 1]++) & 1));
         if (lane < dm.n_ranges) {
-          a0 = fz->ranges[tp][2 * lane] < 0 ? 0 : fz->ranges[tp][2 * lane];
-          a1 = fz->ranges[tp][2 * lane + 1] > dm.S_sel_kv ? dm.S_sel_kv : fz->ranges[tp][2 * lane + 1];
+          a0 = fz->ranges[tp & 1][2 * lane] < 0 ? 0 : fz->ranges[tp & 1][2 * lane];
+          a1 = fz->ranges[tp & 1][2 * lane + 1] > dm.S_sel_kv ? dm.S_sel_kv : fz->ranges[tp & 1][2 * lane + 1];
         }
       }
       const int nb = a1 > a0 ? (a1 - a0 + 63) >> 6 : 0;
@@ -277,8 +290,11 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&ms->list_full[rs]);
+        GDBG(3, it);
         issue_pairs(rs, bg, br, false);                       // K pairs of item it
+        GDBG(4, it);
         if (it > 0) issue_pairs((it - 1) & (kGSlots - 1), prev_bg, prev_br, true);  // V pairs of item it-1
+        GDBG(5, it);
       }
       prev_bg = bg; prev_br = br;
       cur = nxt;
@@ -295,7 +311,9 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
         const int rs = i & 1, ls = i & (kGSlots - 1);
         const int nblk = ms->nblk[ls];
         const int np = (nblk + 1) >> 1;
+        GDBG(20, i);
         mbar_wait(&ms->p_ready[rs], (i >> 1) & 1);
+        GDBG(21, i);
         mbar_wait(&ms->o_free[rs], ((i >> 1) & 1) ^ 1);  // the epilogue of item i-2 has read this O^T slot
         tc_fence_after();
         bool first_mma = true;
@@ -318,13 +336,17 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
           ++n_cons;
         }
         umma_commit(&ms->o_done[rs]);
+        GDBG(22, i);
       };
       for (int it = 0; it < n_it; ++it) {
         const int ls = it & (kGSlots - 1);
+        GDBG(10, it);
         mbar_wait(&ms->list_full[ls], (it / kGSlots) & 1);
         const int nblk = ms->nblk[ls];
         const int np = (nblk + 1) >> 1;
-        mbar_wait(&ms->s_free, (it & 1) ^ 1);  // the softmax warps hold S^T of item it-1 in registers
+        GDBG(11, it);
+        mbar_wait(&ms->s_free, (it & 1) ^ 1);
+        GDBG(12, it);  // the softmax warps hold S^T of item it-1 in registers
         tc_fence_after();
         const uint32_t q_base = smem_u32(smem + GSmem::Qt + ls * 2048);
         for (int j = 0; j < np; ++j) {
@@ -342,6 +364,7 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
           ++n_cons;
         }
         umma_commit(&ms->s_done);
+        GDBG(13, it);
         if (it > 0) pv(it - 1);
       }
       if (n_it > 0) pv(n_it - 1);
@@ -359,12 +382,40 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
     for (int e = 0; e < kGN; ++e) { comb0[e] = 0.f; comb1[e] = 0.f; }
     float sc[kGMaxPairs][kGN];
 
+    // gate MLP on q_gp = mean over heads (nsa_attention.py:32-82, :908-912) by one warp -> fz->gate3[token slot]
+    auto gate_of_token = [&](size_t row, int tk, float* qgp, float* xs) {
+      const T* qrow = reinterpret_cast<const T*>(a.Q) + row * h * 64;
+      for (int k = lane; k < 64; k += 32) {
+        float m = 0.f;
+        for (int hh = 0; hh < h; ++hh) m += (float)qrow[hh * 64 + k];
+        qgp[k] = m / (float)h;
+      }
+      __syncwarp();
+      Gate3 gt = gate_forward_warp(qgp, xs, nullptr, a.gp, 64, dm.gate_hidden, dm.gate_tau, dm.gate_mode, nullptr);
+      if (lane == 0) { fz->gate3[tk % kGGateSlots][0] = gt.c; fz->gate3[tk % kGGateSlots][1] = gt.s; fz->gate3[tk % kGGateSlots][2] = gt.w; }
+      __syncwarp();
+    };
+    if (a.fuse) {
+      // prologue: the gates of this CTA's first tokens, one warp per token, while the first K blocks are in flight.
+      // Scratch lives in the (still unused) P buffer.
+      float* scratch = reinterpret_cast<float*>(smem + GSmem::P) + warp * 256;
+      for (int tk = warp; tk < n_tok && tk < kGGateSlots; tk += 4) {
+        const int tok = tok_begin + tk;
+        const int bg_ = tok / dm.S, s_ = tok - bg_ * dm.S;
+        const size_t row_ = ((size_t)(bg_ / dm.G) * dm.S + s_) * dm.G + (bg_ % dm.G);
+        gate_of_token(row_, tk, scratch, scratch + 64);
+      }
+      g_named_bar(1, 128);
+    }
+
     auto stage_a = [&](int it) {  // S^T -> registers (masked), arrive s_free
       const int ls = it & (kGSlots - 1);
       mbar_wait(&ms->list_full[ls], (it / kGSlots) & 1);
       const int nblk = ms->nblk[ls];
       const int np = (nblk + 1) >> 1;
+      if (tid == 0) GDBG(30, it);
       mbar_wait(&ms->s_done, it & 1);
+      if (tid == 0) GDBG(31, it);
       tc_fence_after();
 #pragma unroll
       for (int j = 0; j < kGMaxPairs; ++j)
@@ -446,6 +497,7 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&ms->p_ready[rs]);
       g_named_bar(1, 128);
+      if (tid == 0) GDBG(32, it);
 
       if (a.fuse && br == 0) {
         // ---- fused decode scoring: p_cmp (this item's softmax) -> Eq.9 -> Eq.10 -> top-n ranges; gate MLP ----
@@ -465,6 +517,12 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
             fz->pkey[j * 128 + tid] = ph;
           }
         }
+      }
+
+      // ---- A of the next item ----------------------------------------------------------------------------------
+      if (it + 1 < n_it) stage_a(it + 1);
+
+      if (a.fuse && br == 0) {
         g_named_bar(1, 128);
         const int nkeys = nblk > 0 ? (nblk - 1) * 64 + ms->blk_valid[ls][nblk - 1] : 0;
         for (int blk = tid; blk < a.S_sel; blk += 128) {  // Eq.9 with l = 2d, l_sel = 4d, ascending compressed index
@@ -476,34 +534,24 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
           if (i0 + 3 < nkeys) acc += 0.5f * fz->pkey[i0 + 3];
           fz->pg[blk] = acc;
         }
-        if (warp == 1) {  // gate MLP on q_gp = mean over heads (nsa_attention.py:32-82, :908-912)
-          const T* qrow = reinterpret_cast<const T*>(a.Q) + row * h * 64;
-          for (int k = lane; k < 64; k += 32) {
-            float m = 0.f;
-            for (int hh = 0; hh < h; ++hh) m += (float)qrow[hh * 64 + k];
-            fz->qgp[k] = m / (float)h;
-          }
-          __syncwarp();
-          Gate3 gt = gate_forward_warp(fz->qgp, fz->xs, nullptr, a.gp, 64, dm.gate_hidden, dm.gate_tau, dm.gate_mode, nullptr);
-          if (lane == 0) { fz->gate3[tp][0] = gt.c; fz->gate3[tp][1] = gt.s; fz->gate3[tp][2] = gt.w; }
-        }
+        if (warp == 1 && tp >= kGGateSlots) gate_of_token(row, tp, fz->qgp, fz->xs);  // tokens the prologue did not cover
         g_named_bar(1, 128);
         if (warp == 0) {
-          select_row_warp(fz->pg, a.S_sel, dm.l_sel, dm.n_sel, 1, 3, dm.n_sel, t, fz->ranges[tp]);
+          select_row_warp(fz->pg, a.S_sel, dm.l_sel, dm.n_sel, 1, 3, dm.n_sel, t, fz->ranges[tp & 1]);
           __syncwarp();
           if (a.ranges_out && lane < dm.n_sel)
             *reinterpret_cast<int2*>(a.ranges_out + (row * dm.n_sel + lane) * 2) =
-                make_int2(fz->ranges[tp][2 * lane], fz->ranges[tp][2 * lane + 1]);
+                make_int2(fz->ranges[tp & 1][2 * lane], fz->ranges[tp & 1][2 * lane + 1]);
           __syncwarp();
-          if (lane == 0) mbar_arrive(&ms->sel_ready[tp]);
+          if (lane == 0) mbar_arrive(&ms->sel_ready[tp & 1]);
         }
       }
 
-      // ---- A of the next item ----------------------------------------------------------------------------------
-      if (it + 1 < n_it) stage_a(it + 1);
 
       // ---- C: epilogue: O^T (64 dv x 8 heads, M=64 layout: dv row r on lane 32*(r/16) + r%16) ---------------------
+      if (tid == 0) GDBG(33, it);
       mbar_wait(&ms->o_done[rs], (it >> 1) & 1);
+      if (tid == 0) GDBG(34, it);
       tc_fence_after();
       uint32_t r[8];
       if (nblk > 0) {
@@ -518,7 +566,7 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&ms->o_free[rs]);
       float gate = 1.f;
-      if (a.fuse) gate = fz->gate3[tp][br];
+      if (a.fuse) gate = fz->gate3[tp % kGGateSlots][br];
       else if (combine) gate = a.gates[row * 3 + br];
       if (lane < 16) {
         const int dv = warp * 16 + lane;
@@ -529,12 +577,12 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
         for (int e = 0; e < kGN; ++e) {
           if (e < h) {
             const float l = ms->red_sum[rs][0][e] + ms->red_sum[rs][1][e] + ms->red_sum[rs][2][e] + ms->red_sum[rs][3][e];
-            const float o = l > 0.f ? __uint_as_float(r[e]) / l : 0.f;
+            const float o = l > 0.f ? __fdividef(__uint_as_float(r[e]), l) : 0.f;
             if (ob) ob[(row * h + e) * 64 + dv] = T(o);
             if (combine) {
-              const float c = fmaf(gate, o, tp ? comb1[e] : comb0[e]);
+              const float c = fmaf(gate, o, (tp & 1) ? comb1[e] : comb0[e]);
               if (last) of[(row * h + e) * 64 + dv] = T(c);
-              if (tp) comb1[e] = last ? 0.f : c;
+              if (tp & 1) comb1[e] = last ? 0.f : c;
               else comb0[e] = last ? 0.f : c;
             }
           }
@@ -548,6 +596,7 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ms->row_free[ls]);
+      if (tid == 0) GDBG(35, it);
     }
   }
 
@@ -601,7 +650,25 @@ static int launch_gather_t(const nsa_dims_t& dm, const GatherPtrs& kv, GatherArg
     if (e != cudaSuccess) { set_error("gather tc: smem attr: %s", cudaGetErrorString(e)); return NSA_ERR_CUDA; }
     attr_set = true;
   }
+  static const bool dbg_on = getenv("NSA_B200_GATHER_DBG") != nullptr;
+  static long long* dbg_buf = nullptr;
+  if (dbg_on) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 8008 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 8008 * sizeof(long long), stream);
+    a.dbg = dbg_buf;
+  }
   kern<<<grid, 192, GSmem::total, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], dm, a);
+  if (dbg_on) {  // debug only: dump the timeline of CTA 0 (tag, item, clock)
+    static int dumps = 0;
+    cudaStreamSynchronize(stream);
+    if (dumps++ == 3) {
+      static long long host[8008];
+      cudaMemcpy(host, dbg_buf, sizeof(host), cudaMemcpyDeviceToHost);
+      long long n = host[0] < 4000 ? host[0] : 4000;
+      for (long long i = 0; i < n; ++i)
+        fprintf(stderr, "GDBG %lld %lld %lld\n", host[1 + 2 * i] >> 32, host[1 + 2 * i] & 0xffffffff, host[2 + 2 * i]);
+    }
+  }
   return check_launch("gather_attn_tc_kernel");
 }
 
@@ -617,6 +684,7 @@ int launch_gather_tc(const nsa_dims_t& dm, int branch_mask, const void* Q, const
                      const nsa_gate_params_t* gp_fuse, int S_sel, int32_t* ranges_out, cudaStream_t stream) {
   static_assert(sizeof(GMisc) <= 1280, "GMisc must fit its slot");
   if (dm.B * dm.S * dm.G == 0 || branch_mask == 0) return NSA_OK;
+  NSA_REQUIRE((long long)dm.B * dm.S * dm.G < (1LL << 31), "gather(tc): B*S*G must be below 2^31");
   GatherArgs a;
   memset(&a, 0, sizeof(a));
   GatherPtrs kv;

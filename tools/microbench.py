@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--S", type=int, default=65536)
     ap.add_argument("--B", type=int, default=1)
     ap.add_argument("--what", default="sel,cmp,win,score,fwd")
+    ap.add_argument("--decode-B", type=int, default=512)
     a = ap.parse_args()
     G, h, D, l, d, ls, n, w = 2, 6, 64, 32, 16, 64, 16, 512
     S, B = a.S, a.B
@@ -54,7 +55,7 @@ def main():
                     ms = timeit(lambda: ops.branch_attention(br, Q, K, V, c2, ranges if br == 1 else None), n=3, warm=1)
                     print(f"branch {name} ({nm:4s})     : {ms:9.3f} ms")
         if "decode" in what:
-            Sd, Bd = 4096, 512
+            Sd, Bd = 4096, a.decode_B
             cap = Sd + 64
             Ks2, Vs2, Kw2, Vw2 = r(Bd, G, cap, D), r(Bd, G, cap, D), r(Bd, G, cap, D), r(Bd, G, cap, D)
             Sc = (Sd - l) // d + 1
