@@ -60,6 +60,20 @@ def decode_bytes_per_token(S, c=M7C):
     return reads * c["G"] * (c["Dk"] + c["Dv"]) * 2, reads
 
 
+def num_sel_blocks(S, l_sel):
+    return (S + l_sel - 1) // l_sel
+
+
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+    (profiles/traffic.json: kernel name -> bytes), or {}."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -303,6 +317,27 @@ def main():
         e2e_val = world * B * S / (float(t2.item()) / n_e2e * 1e-3)
         del host, o_host
 
+        # ---- per-kernel device times (outside the timed region; same inputs) -------------------------------
+        def t_of(fn, n=3):
+            fn()
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for _ in range(n):
+                fn()
+            b_.record()
+            torch.cuda.synchronize()
+            return a_.elapsed_time(b_) / n
+        pg = ops.score_pgrp(inp["Q"], inp["K_cmp"], cfg)
+        rg_ = ops.select_ranges_prefill(pg, c["l_sel"], c["n_sel"], S)
+        kms = {"score": t_of(lambda: ops.score_pgrp(inp["Q"], inp["K_cmp"], cfg)),
+               "select": t_of(lambda: ops.select_ranges_prefill(pg, c["l_sel"], c["n_sel"], S)),
+               "cmp": t_of(lambda: ops.branch_attention(ops.BR_CMP, inp["Q"], inp["K_cmp"], inp["V_cmp"], cfg)),
+               "sel": t_of(lambda: ops.branch_attention(ops.BR_SEL, inp["Q"], inp["K_sel"], inp["V_sel"], cfg, rg_)),
+               "win": t_of(lambda: ops.branch_attention(ops.BR_WIN, inp["Q"], inp["K_win"], inp["V_win"], cfg))}
+        kms["gate_combine_and_rest"] = max(0.0, ms_step - sum(kms.values()))
+        del pg, rg_
+
         # ---- decode @S=4096 -------------------------------------------------------------------------------
         decode = None
         if not args.no_decode:
@@ -315,18 +350,31 @@ def main():
     # ---- roofline of the dominant kernel -------------------------------------------------------------------
     pk = measured_peaks()
     fl = prefill_flops(S)
-    if ms_attn >= ms_score:
-        kname = "nsa_prefill_fwd (cmp + sel + win attention, gate, combine)"
-        k_flops, k_ms = B * (fl["cmp_pv"] + fl["sel"] + fl["win"]), ms_attn
+    traffic = load_traffic()
+    # (name, ms, bound, algorithmic work per launch [FLOP or bytes], how the work is counted)
+    cand = [
+        ("score_tc_kernel", kms["score"], "tensor", B * fl["score"], "2*S*S_cmp*H*Dk (full-row scoring QK^T)"),
+        ("select_kernel", kms["select"], "hbm", B * S * c["G"] * (4.0 * num_sel_blocks(S, c["l_sel"]) + 8.0 * c["n_sel"]),
+         "4*S_sel B read + 8*n_sel B written per (b,t,g) row"),
+        ("dense_attn_tc_kernel[cmp]", kms["cmp"], "tensor", B * fl["cmp_pv"], "2*H*Dv*sum_t num_cmp(t) (P.V; its QK^T is counted under scoring)"),
+        ("gather_attn_tc_kernel[sel]", kms["sel"], "hbm", B * fl["sel_gather_bytes"], "2 B*G*(Dk+Dv)*sum_t min(t+1, n_sel*l_sel) gathered K/V bytes"),
+        ("dense_attn_tc_kernel[win]", kms["win"], "tensor", B * fl["win"], "2*H*(Dk+Dv)*sum_t min(t+1, w)"),
+    ]
+    kname, k_ms, bound, work, how = max(cand, key=lambda x: x[1])
+    if bound == "tensor":
+        achieved, peak, unit, src = work / (k_ms * 1e-3) / 1e12, pk["tf_sustained"], "TFLOP/s", pk["src"] + " (bf16 sustained)"
     else:
-        kname = "nsa_score_select (p_cmp softmax, Eq.9/10, top-n, ranges)"
-        k_flops, k_ms = B * fl["score"], ms_score
-    achieved = k_flops / (k_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
-                "traffic": None, "kernel": kname, "kernel_ms": k_ms, "peak_source": pk["src"] + " (bf16 sustained)",
-                "step_tflops": B * fl["total"] / (ms_step * 1e-3) / 1e12, "ms_score_select": ms_score, "ms_prefill_fwd": ms_attn,
+        achieved, peak, unit, src = work / (k_ms * 1e-3) / 1e9, pk["hbm"], "GB/s", pk["src"] + " (HBM copy)"
+    roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+                "traffic": traffic.get(kname), "kernel": kname, "kernel_ms": k_ms, "algorithmic_work": how, "peak_source": src,
+                "step_tflops": B * fl["total"] / (ms_step * 1e-3) / 1e12,
+                "step_frac_of_tensor_peak": B * fl["total"] / (ms_step * 1e-3) / 1e12 / pk["tf_sustained"],
+                "kernel_ms_breakdown": kms, "ms_score_select": ms_score, "ms_prefill_fwd": ms_attn,
                 "algorithmic_gflop_per_seq": {k: v / 1e9 for k, v in fl.items() if k != "sel_gather_bytes"},
-                "sel_gather_GBps": B * fl["sel_gather_bytes"] / (ms_attn * 1e-3) / 1e9}
+                "per_kernel": [{"kernel": n_, "ms": m_, "bound": b_, "achieved": (w_ / (m_ * 1e-3) / (1e12 if b_ == "tensor" else 1e9)),
+                                "unit": "TFLOP/s" if b_ == "tensor" else "GB/s",
+                                "frac": (w_ / (m_ * 1e-3) / (1e12 if b_ == "tensor" else 1e9)) / (pk["tf_sustained"] if b_ == "tensor" else pk["hbm"])}
+                               for n_, m_, b_, w_, _ in cand]}
     cpu = None
     if not args.no_cpu:
         v, cores, sample = cpu_prefill_sample(S, args.cpu_rows)
@@ -379,13 +427,29 @@ def bench_decode(args, ops, cfg, dev, rank, world, barrier):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms = float(tt.item())
+    # single-sequence latency (launch-bound: 0.9 MB per step cannot fill the machine)
+    q1, o1, r1 = q[:1], out[:1], rg[:1]
+    def d1():
+        ops.decode_core(q1, K_sel[:1], V_sel[:1], K_win[:1], V_win[:1], K_cmp[:1], V_cmp[:1], gate, cfg, t=S - 1, S_sel_kv=S,
+                        S_win_kv=S, win_off=0, S_cmp=S_cmp, ranges_out=r1, out=o1, gate_cache=gate_cache)
+    for _ in range(3):
+        d1()
+    torch.cuda.synchronize()
+    s1, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s1.record()
+    for _ in range(n):
+        d1()
+    e1.record()
+    torch.cuda.synchronize()
+    b1_us = s1.elapsed_time(e1) / n * 1e3
     byts, reads = decode_bytes_per_token(S)
     pk = measured_peaks()
     ach = Bd * byts / (ms * 1e-3) / 1e9
     return {"metric": "NSA decode us/tok @S=4k", "value": ms * 1e3 / (Bd * world), "unit": "us/token (step latency / global batch)",
-            "S": S, "batch_per_gpu": Bd, "ms_per_step": ms, "tokens_per_s": world * Bd / (ms * 1e-3),
+            "S": S, "batch_per_gpu": Bd, "ms_per_step": ms, "tokens_per_s": world * Bd / (ms * 1e-3), "b1_step_latency_us": b1_us,
+            "kernel": "gather_attn_tc_kernel (fused decode step: scoring, selection, gate, cmp+sel+win attention, combine; 1 launch)",
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                         "algorithmic_bytes_per_token": byts, "reads_per_token": reads, "peak_source": pk["src"]}}
+                         "traffic": load_traffic().get("gather_attn_tc_kernel[decode]"), "algorithmic_bytes_per_token": byts, "reads_per_token": reads, "peak_source": pk["src"]}}
 
 
 if __name__ == "__main__":
