@@ -9,6 +9,8 @@
 //     MN-major B operand; O_t is folded into fp32 register accumulators with the online-softmax rescale;
 //   * the two M-tiles ping-pong: while one runs its softmax (MUFU-bound), the tensor core works for the other.
 // Warp roles: warps [0, 4*MT) softmax, warp 4*MT TMA producer, warp 4*MT+1 MMA issuer.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 #include "launchers.h"
 
@@ -68,11 +70,19 @@ __device__ __forceinline__ void dn_row_range(const nsa_dims_t& dm, int branch, i
   }
 }
 
+#define DDBG(tag, it)                                                                 \
+  do {                                                                                \
+    if (dbg && blockIdx.x == gridDim.x / 2 + 200) {                                         \
+      const unsigned long long i_ = atomicAdd((unsigned long long*)dbg, 1ull);        \
+      if (i_ < 4000) { dbg[1 + 2 * i_] = ((long long)(tag) << 32) | (unsigned)(it); dbg[2 + 2 * i_] = clock64(); } \
+    }                                                                                 \
+  } while (0)
+
 template <typename T>
 __global__ void __launch_bounds__(32 * (4 * kDnMT + 2), 1)
 dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, nsa_dims_t dm, int branch, T* __restrict__ O,
-                     float* __restrict__ lse, int TOK) {
+                     float* __restrict__ lse, int TOK, long long* dbg) {
   constexpr int MT = kDnMT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -164,8 +174,10 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (i + 1 < n) mbar_wait(&ms->k_full[(i + 1) % kDnKS], ((i + 1) / kDnKS) & 1);
         const uint32_t vb = smem_u32(smem + DnSmem::v + vs * kDnTile);
         for (int m = 0; m < MT; ++m) {
+          DDBG(10 + m, i);
           mbar_wait(&ms->p_full[m], i & 1);
           mbar_wait(&ms->o_empty[m][i & 1], ((i >> 1) & 1) ^ 1);
+          DDBG(12 + m, i);
           tc_fence_after();
           const uint32_t pb = smem_u32(smem + DnSmem::p + m * 2 * kDnTile);
           const uint32_t od = tmem + 256 + (m * 2 + (i & 1)) * 64;
@@ -227,7 +239,9 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
     for (int i = 0; i < n; ++i) {
       const int col_base = (kt_lo + i) * 128;
+      if (tid == 0) DDBG(1, i);
       mbar_wait(&ms->s_full[mt], i & 1);
+      if (tid == 0) DDBG(2, i);
       tc_fence_after();
       const bool full_tile = col_base >= lo && col_base + 128 <= hi;
       // ---- pass A: tile max ----
@@ -257,7 +271,9 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const bool any = m_new > -INFINITY;
       const float alpha = any ? dn_ex2((m_run - m_new) * c) : 1.f;
       const float mc = any ? m_new * c : 0.f;
+      if (tid == 0) DDBG(3, i);
       mbar_wait(&ms->p_empty[mt], (i & 1) ^ 1);  // P.V of the previous tile has read the P buffer
+      if (tid == 0) DDBG(4, i);
       // ---- pass B: probabilities -> bf16 P tile (K-major, 128B swizzle) ----
       float rowsum = 0.f;
       {
@@ -269,21 +285,31 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
           dn_ld_wait32(cur);
           if (ch < 3) tmem_ld32(tm_S + (ch + 1) * 32, nxt);
-          uint32_t pk[16];
+          // issue the 32 exponentials first, consume them afterwards (a MUFU result used by the next instruction stalls
+          // the in-order issue for the MUFU latency; only 2 warps share a scheduler here)
+          float pe[32];
+          if (full_tile) {
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float p0, p1;
-            if (full_tile) {
-              p0 = dn_ex2(fmaf(__uint_as_float(cur[e]), c, -mc));
-              p1 = dn_ex2(fmaf(__uint_as_float(cur[e + 1]), c, -mc));
-            } else {
+            for (int e = 0; e < 32; ++e) pe[e] = dn_ex2(fmaf(__uint_as_float(cur[e]), c, -mc));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
               const int col = col_base + ch * 32 + e;
-              p0 = (any && col >= lo && col < hi) ? dn_ex2(fmaf(__uint_as_float(cur[e]), c, -mc)) : 0.f;
-              p1 = (any && col + 1 >= lo && col + 1 < hi) ? dn_ex2(fmaf(__uint_as_float(cur[e + 1]), c, -mc)) : 0.f;
+              pe[e] = (any && col >= lo && col < hi) ? dn_ex2(fmaf(__uint_as_float(cur[e]), c, -mc)) : 0.f;
             }
-            rowsum += p0 + p1;
-            pk[e >> 1] = pack2(T(), p0, p1);
           }
+          uint32_t pk[16];
+          float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {
+            r0 += pe[e] + pe[e + 1];
+            r1 += pe[e + 2] + pe[e + 3];
+            r2 += pe[e + 4] + pe[e + 5];
+            r3 += pe[e + 6] + pe[e + 7];
+          }
+          rowsum += (r0 + r1) + (r2 + r3);
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) pk[e >> 1] = pack2(T(), pe[e], pe[e + 1]);
           // 32 keys = 4 chunks of 16 B; key chunk index kc = ch*4 + q in [0,16): half = kc >> 3, chunk-in-row = kc & 7
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -293,6 +319,7 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
         }
       }
+      if (tid == 0) DDBG(5, i);
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
@@ -300,9 +327,11 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_arrive(&ms->s_empty[mt]);
         mbar_arrive(&ms->p_full[mt]);
       }
+      if (tid == 0) DDBG(6, i);
       l_run = fmaf(l_run, alpha, rowsum);
       m_run = m_new;
       if (i > 0) fold_o(i - 1, alpha_prev);
+      if (tid == 0) DDBG(7, i);
       alpha_prev = alpha;
     }
     if (n > 0) fold_o(n - 1, alpha_prev);
@@ -360,7 +389,24 @@ static int launch_dense_t(const nsa_dims_t& dm, int branch, const void* Q, const
     attr_set = true;
   }
   const int grid = dm.B * dm.G * ceil_div(dm.S, kDnMT * TOK);
-  kern<<<grid, 32 * (4 * kDnMT + 2), DnSmem::total, stream>>>(tmQ, tmK, tmV, dm, branch, (T*)O, lse, TOK);
+  static const bool dbg_on = getenv("NSA_B200_DENSE_DBG") != nullptr;
+  static long long* dbg_buf = nullptr;
+  if (dbg_on) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 8008 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 8008 * sizeof(long long), stream);
+  }
+  kern<<<grid, 32 * (4 * kDnMT + 2), DnSmem::total, stream>>>(tmQ, tmK, tmV, dm, branch, (T*)O, lse, TOK, dbg_on ? dbg_buf : nullptr);
+  if (dbg_on) {  // debug only: timeline of the middle CTA (tag, tile, clock)
+    static int dumps = 0;
+    cudaStreamSynchronize(stream);
+    if (dumps++ == 2) {
+      static long long host[8008];
+      cudaMemcpy(host, dbg_buf, sizeof(host), cudaMemcpyDeviceToHost);
+      long long n = host[0] < 4000 ? host[0] : 4000;
+      for (long long i = 0; i < n; ++i)
+        fprintf(stderr, "DDBG %lld %lld %lld\n", host[1 + 2 * i] >> 32, host[1 + 2 * i] & 0xffffffff, host[2 + 2 * i]);
+    }
+  }
   return check_launch("dense_attn_tc_kernel");
 }
 

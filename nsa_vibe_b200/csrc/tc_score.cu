@@ -11,6 +11,8 @@
 // order of the reference's CPU scatter_add.  Nothing but p_grp [B,S,G,S_sel] leaves the SM.
 //
 // Warp roles: warps [0, 4*MT) softmax (thread = TMEM lane = row), warp 4*MT TMA producer, warp 4*MT+1 MMA issuer.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 #include "launchers.h"
 #include "select.cuh"
@@ -22,12 +24,16 @@ constexpr int kScStages = 4;       // K ring depth (16 KB tiles)
 constexpr int kScTile = 128 * 128; // bytes of one 128-row x 64-element tile
 constexpr int kScRedLd = 33;       // padded row of the head-reduction buffer
 
+// MT M-tiles per CTA share every K tile.  TMEM (512 columns) holds STG = 4 / MT accumulator stages of 128 columns per
+// M-tile: MT = 2 double-buffers S; MT = 4 single-buffers it and relies on 4 softmax warps per scheduler to hide the MMA.
 template <int MT>
 struct ScSmem {
+  static constexpr int STG = MT <= 2 ? 2 : 1;                       // S accumulator stages per M-tile
+  static constexpr int RB = MT <= 2 ? 2 : 1;                        // head-reduction buffers per M-tile
   static constexpr int q = 0;
   static constexpr int ring = q + MT * kScTile;
-  static constexpr int red = ring + kScStages * kScTile;           // [MT][2][128][33] fp32
-  static constexpr int misc = red + MT * 2 * 128 * kScRedLd * 4;
+  static constexpr int red = ring + kScStages * kScTile;           // [MT][RB][128][33] fp32
+  static constexpr int misc = red + MT * RB * 128 * kScRedLd * 4;
   static constexpr int total = misc + 256 + 1024;                   // + alignment slack
 };
 
@@ -65,7 +71,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 template <typename T, int MT, int R>
 __global__ void __launch_bounds__(32 * (4 * MT + 2), 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, nsa_dims_t dm, int S_sel,
-                float* __restrict__ p_grp, int TOK) {
+                float* __restrict__ p_grp, int TOK, int dbg_stop) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   using SM = ScSmem<MT>;
@@ -73,6 +79,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int kSoftWarps = 4 * MT;
   constexpr int BPT = 128 / R;  // selection blocks completed per key tile
+  constexpr int STG = SM::STG, RB = SM::RB;
 
   const int tiles_per_seq = ceil_div(dm.S, MT * TOK);
   const int tile = blockIdx.x % tiles_per_seq;
@@ -83,8 +90,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   int s_last = s_base + MT * TOK - 1;
   if (s_last > dm.S - 1) s_last = dm.S - 1;
   const int nk_cta = causal ? num_cmp_at(dm.t0 + s_last, dm.l, dm.d, dm.S_cmp) : dm.S_cmp;
-  const int NT = ceil_div(nk_cta, 128);        // key tiles with work
-  const int NTO = ceil_div(S_sel, BPT);        // output tiles (tiles >= NT only flush the carry / write zeros)
+  const int NT = (dbg_stop == 1 || dbg_stop >= 3) ? 0 : ceil_div(nk_cta, 128);        // key tiles with work
+  const int NTO = (dbg_stop == 2 || dbg_stop == 3) ? 0 : ceil_div(S_sel, BPT);        // output tiles (tiles >= NT only flush the carry / write zeros)
 
   // ---- setup ---------------------------------------------------------------------------------------------
   {  // rows of the Q tiles that TMA does not write (>= TOK*h) must hold finite data
@@ -100,7 +107,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
   }
-  if (warp == 0) tmem_alloc(&ms->tmem_base, MT * 256);
+  if (warp == 0) tmem_alloc(&ms->tmem_base, MT * STG * 128);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -109,11 +116,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp == kSoftWarps) {
     // ===== TMA producer ====================================================================================
-    if (lane == 0) {
+    if (lane == 0 && dbg_stop < 3) {
       mbar_expect_tx(&ms->q_full, MT * TOK * dm.h * 128);
       for (int m = 0; m < MT; ++m)
         tma_load_4d(smem + SM::q + m * kScTile, &tmQ, &ms->q_full, 0, 0, g, b * dm.S + s_base + m * TOK);
-      for (int it = 0; it < 2 * NT; ++it) {
+      for (int it = 0; it < (dbg_stop == 2 ? NT : 2 * NT); ++it) {
         const int ks = it % kScStages;
         mbar_wait(&ms->k_empty[ks], ((it / kScStages) & 1) ^ 1);
         mbar_expect_tx(&ms->k_full[ks], kScTile);
@@ -124,20 +131,20 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ===== MMA issuer ======================================================================================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(128, 128, TcType<T>::fmt, 0, 0);
-      mbar_wait(&ms->q_full, 0);
-      for (int it = 0; it < 2 * NT; ++it) {
-        const int ks = it % kScStages, st = it & 1;
+      if (dbg_stop < 3) mbar_wait(&ms->q_full, 0);
+      for (int it = 0; it < (dbg_stop == 2 ? NT : 2 * NT); ++it) {
+        const int ks = it % kScStages, st = it % STG;
         mbar_wait(&ms->k_full[ks], (it / kScStages) & 1);
         const uint32_t kb = smem_u32(smem + SM::ring + ks * kScTile);
         for (int m = 0; m < MT; ++m) {
-          mbar_wait(&ms->s_empty[m][st], ((it >> 1) & 1) ^ 1);
+          mbar_wait(&ms->s_empty[m][st], ((it / STG) & 1) ^ 1);
           tc_fence_after();
           const uint32_t qb = smem_u32(smem + SM::q + m * kScTile);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t ad = make_smem_desc(qb + k * 32, 16, 1024, kSwizzle128B);
             const uint64_t bd = make_smem_desc(kb + k * 32, 16, 1024, kSwizzle128B);
-            umma_f16(tmem + (m * 2 + st) * 128, ad, bd, idesc, k > 0);
+            umma_f16(tmem + (m * STG + st) * 128, ad, bd, idesc, k > 0);
           }
           umma_commit(&ms->s_full[m][st]);
         }
@@ -154,14 +161,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int t = dm.t0 + s;
     const int nk = !row_ok ? 0 : (causal ? num_cmp_at(t, dm.l, dm.d, dm.S_cmp) : dm.S_cmp);
     const float c = dm.scale * kLog2e;
-    const uint32_t tm_row = tmem + ((uint32_t)((warp & 3) * 32) << 16) + mt * 256;
-    float* red = reinterpret_cast<float*>(smem + SM::red) + (size_t)mt * 2 * 128 * kScRedLd;
+    const uint32_t tm_row = tmem + ((uint32_t)((warp & 3) * 32) << 16) + mt * STG * 128;
+    float* red = reinterpret_cast<float*>(smem + SM::red) + (size_t)mt * RB * 128 * kScRedLd;
 
     // ---- pass 1: row max and normaliser --------------------------------------------------------------------
     float m_run = -INFINITY, l_run = 0.f;
     for (int kt = 0; kt < NT; ++kt) {
-      const int it = kt, st = it & 1;
-      mbar_wait(&ms->s_full[mt][st], (it >> 1) & 1);
+      const int it = kt, st = it % STG;
+      mbar_wait(&ms->s_full[mt][st], (it / STG) & 1);
       tc_fence_after();
       uint32_t va[32], vb[32];
       tmem_ld32(tm_row + st * 128, va);
@@ -186,10 +193,17 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           const float m_new = fmaxf(m_run, cm);
           const float mc = m_new * c;
-          float sum = 0.f;
+          // all 32 exponentials are issued before the first is consumed: with 2 warps per scheduler a MUFU result used by
+          // the next instruction stalls the in-order issue for the MUFU latency
+          float e[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sum += ex2f(fmaf(__uint_as_float(cur[i]), c, -mc));
-          l_run = fmaf(l_run, ex2f((m_run - m_new) * c), sum);
+          for (int i = 0; i < 32; ++i) e[i] = ex2f(fmaf(__uint_as_float(cur[i]), c, -mc));
+          const float corr = ex2f((m_run - m_new) * c);
+          float s0 = e[0], s1 = e[1], s2 = e[2], s3 = e[3];
+#pragma unroll
+          for (int i = 4; i < 32; i += 4) { s0 += e[i]; s1 += e[i + 1]; s2 += e[i + 2]; s3 += e[i + 3]; }
+          const float sum = (s0 + s1) + (s2 + s3);
+          l_run = fmaf(l_run, corr, sum);
           m_run = m_new;
         }
       }
@@ -204,10 +218,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ---- pass 2: probabilities -> Eq.9 -> Eq.10 ------------------------------------------------------------
     float carry = 0.f;  // half of the last straddling compressed block, owed to the next selection block
     for (int kt = 0; kt < NTO; ++kt) {
-      float* rb = red + (size_t)(kt & 1) * 128 * kScRedLd + (size_t)r * kScRedLd;
+      float* rb = red + (size_t)(kt % RB) * 128 * kScRedLd + (size_t)r * kScRedLd;
       if (kt < NT) {
-        const int it = NT + kt, st = it & 1;
-        mbar_wait(&ms->s_full[mt][st], (it >> 1) & 1);
+        const int it = NT + kt, st = it % STG;
+        mbar_wait(&ms->s_full[mt][st], (it / STG) & 1);
         tc_fence_after();
         uint32_t va[32], vb[32];
         tmem_ld32(tm_row + st * 128, va);
@@ -248,7 +262,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       named_bar_sync(1 + mt, 128);
       // Eq.10: sum the h head rows of each token; 32 lanes write 32 consecutive blocks of one token
-      const float* rd = red + (size_t)(kt & 1) * 128 * kScRedLd;
+      const float* rd = red + (size_t)(kt % RB) * 128 * kScRedLd;
       for (int idx = r; idx < TOK * BPT; idx += 128) {
         const int tk = idx / BPT, cc = idx % BPT;
         const int ss = s_base + mt * TOK + tk;
@@ -259,12 +273,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           p_grp[(((size_t)b * dm.S + ss) * dm.G + g) * S_sel + j] = a;
         }
       }
+      if (RB == 1) named_bar_sync(1 + mt, 128);  // single buffer: the next tile's partial sums overwrite it
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, MT * 256);
+  if (warp == 0) tmem_dealloc(tmem, MT * STG * 128);
 }
 
 // ---- host ------------------------------------------------------------------------------------------------------
@@ -282,9 +297,8 @@ int64_t tc_score_workspace(const nsa_dims_t& dm) {
   return (int64_t)dm.B * dm.S * dm.G * S_sel * 4;
 }
 
-template <typename T>
+template <typename T, int MT>
 static int launch_score_t(const nsa_dims_t& dm, const void* Q, const void* Kc, int S_sel, float* p_grp, cudaStream_t stream) {
-  constexpr int MT = 2;
   const int TOK = 128 / dm.h;
   CUtensorMap tmQ, tmK;
   if (int rc = make_tmap_q_heads(&tmQ, Q, dm.dtype, 64, dm.h, dm.G, (long long)dm.B * dm.S, TOK)) return rc;
@@ -297,13 +311,14 @@ static int launch_score_t(const nsa_dims_t& dm, const void* Q, const void* Kc, i
     attr_set = true;
   }
   const int grid = dm.B * dm.G * ceil_div(dm.S, MT * TOK);
-  kern<<<grid, 32 * (4 * MT + 2), ScSmem<MT>::total, stream>>>(tmQ, tmK, dm, S_sel, p_grp, TOK);
+  static const int dbg_stop = getenv("NSA_B200_SCORE_STOP") ? atoi(getenv("NSA_B200_SCORE_STOP")) : 0;
+  kern<<<grid, 32 * (4 * MT + 2), ScSmem<MT>::total, stream>>>(tmQ, tmK, dm, S_sel, p_grp, TOK, dbg_stop);
   return check_launch("score_tc_kernel");
 }
 
 int launch_score_tc(const nsa_dims_t& dm, const void* Q, const void* Kc, int S_sel, int S_total, int sel_mode, int Kr,
                     float* p_grp, int32_t* ranges, void* workspace, cudaStream_t stream) {
-  static_assert(sizeof(ScMisc<2>) <= 256, "ScMisc must fit its slot");
+  static_assert(sizeof(ScMisc<4>) <= 256, "ScMisc must fit its slot");
   if (dm.B * dm.S * dm.G == 0) return NSA_OK;
   float* pg = p_grp;
   if (!pg) {
@@ -311,8 +326,15 @@ int launch_score_tc(const nsa_dims_t& dm, const void* Q, const void* Kc, int S_s
     NSA_REQUIRE((int64_t)dm.B * dm.S * dm.G * S_sel * 4 <= tc_score_workspace(dm), "score_select(tc): S_sel=%d exceeds the workspace", S_sel);
     pg = reinterpret_cast<float*>(workspace);
   }
-  int rc = dm.dtype == NSA_BF16 ? launch_score_t<__nv_bfloat16>(dm, Q, Kc, S_sel, pg, stream)
-                                : launch_score_t<__half>(dm, Q, Kc, S_sel, pg, stream);
+  // 4 M-tiles per CTA (16 softmax warps) when there are enough rows to fill the machine, 2 otherwise;
+  // NSA_B200_SCORE_MT=2|4 forces one (benchmarks / tests)
+  static const int mt_env = getenv("NSA_B200_SCORE_MT") ? atoi(getenv("NSA_B200_SCORE_MT")) : 0;
+  const bool big = mt_env == 4 || (mt_env != 2 && (long long)dm.B * dm.G * dm.S >= 4LL * (128 / dm.h) * 148);
+  int rc;
+  if (dm.dtype == NSA_BF16)
+    rc = big ? launch_score_t<__nv_bfloat16, 4>(dm, Q, Kc, S_sel, pg, stream) : launch_score_t<__nv_bfloat16, 2>(dm, Q, Kc, S_sel, pg, stream);
+  else
+    rc = big ? launch_score_t<__half, 4>(dm, Q, Kc, S_sel, pg, stream) : launch_score_t<__half, 2>(dm, Q, Kc, S_sel, pg, stream);
   if (rc) return rc;
   if (!ranges) return NSA_OK;
   const int nf = sel_mode == 0 ? prefill_forced_cols(S_total, dm.l_sel) : 3;

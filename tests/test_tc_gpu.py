@@ -207,3 +207,22 @@ def test_decode_step_tc_vs_oracle(dtype, t, h, w, win_off):
     assert err.max() <= 2e-2 and err.mean() <= 1e-3, (err.max(), err.mean())
     # causality and clamping of what was selected
     assert (rg[..., 1] <= n_tok).all() and (rg[..., 0] >= 0).all()
+
+
+@pytest.mark.parametrize("norm", ["full_row", "causal"])
+def test_score_tc_four_mtile_path(norm):
+    """Enough rows (B*G*S >= 4*21*148) that the scorer runs 4 M-tiles per CTA with single-buffered accumulators."""
+    ops = _ops()
+    B, S, G, h, l, d, ls, n, w = 2, 4096 + 77, 2, 6, 32, 16, 64, 16, 512
+    gen = torch.Generator().manual_seed(3)
+    Q = torch.randn(B, S, G, h, 64, generator=gen).bfloat16().float()
+    Kc = torch.randn(B, G, O.num_cmp_blocks(S, l, d), 64, generator=gen).bfloat16().float()
+    nm = ops.NORM_CAUSAL if norm == "causal" else ops.NORM_FULL_ROW
+    cfg = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w, impl=ops.IMPL_TC, norm_mode=nm)
+    want = O.prefill_scores(Q, Kc, l, d, ls, n, w, norm)
+    got = ops.score_pgrp(Q.cuda().bfloat16(), Kc.cuda().bfloat16(), cfg).cpu()
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max() <= 2e-5 * h, (got - want).abs().max()
+    r = ops.score_select(Q.cuda().bfloat16(), Kc.cuda().bfloat16(), cfg, mode=0).cpu()
+    _, bad = O.ranges_equivalent(r, O.select_ranges_prefill(want, ls, n, S))
+    assert bad <= B * S * G // 200, bad
