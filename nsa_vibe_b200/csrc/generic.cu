@@ -490,10 +490,126 @@ combine_kernel(nsa_dims_t dm, const void* __restrict__ Q, nsa_gate_params_t gp, 
   }
 }
 
+// Fast gate + combine for 16-bit tensors (the prefill path after the tensor-core branch kernels): HBM-bound.
+// Gate weights live in shared memory (fc1 transposed so lane u reads column u without bank conflicts); one warp per row:
+// q_gp by 16-byte loads, lane u = hidden unit u of fc1, three warp sums for fc2, then O = sum_b g_b O_b by 16-byte chunks.
+// Algorithmic bytes per row: (1 + 3 + 1) * h * D * 2.
+constexpr int kCfWarps = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(kCfWarps * 32)
+combine_fast_kernel(nsa_dims_t dm, const T* __restrict__ Q, nsa_gate_params_t gp, const T* __restrict__ O_br, T* __restrict__ O,
+                    float* __restrict__ gates) {
+  extern __shared__ float smem[];
+  const int Dk = dm.Dk, H = dm.gate_hidden, h = dm.h;
+  float* w1t = smem;                 // [Dk][H]
+  float* b1 = w1t + Dk * H;          // [H]
+  float* w2 = b1 + H;                // [3][H]
+  float* b2 = w2 + 3 * H;            // [4]
+  float* qg = b2 + 4;                // [warps][Dk]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool mlp = dm.gate_mode == NSA_GATE_MLP;
+  if (mlp) {
+    for (int i = threadIdx.x; i < Dk * H; i += blockDim.x) w1t[(i % Dk) * H + i / Dk] = gp.fc1_w[i];
+    for (int i = threadIdx.x; i < H; i += blockDim.x) b1[i] = gp.fc1_b ? gp.fc1_b[i] : 0.f;
+    for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) w2[i] = gp.fc2_w[i];
+    if (threadIdx.x < 3) b2[threadIdx.x] = gp.fc2_b ? gp.fc2_b[threadIdx.x] : 0.f;
+  }
+  __syncthreads();
+  float* qgp = qg + warp * Dk;
+  const int n_rows = dm.B * dm.S * dm.G;
+  const int row_elems = h * dm.Dv;           // multiple of 8 (checked on the host)
+  const int chunks = row_elems / 8;          // 16-byte chunks per row
+  const size_t per_branch = (size_t)n_rows * row_elems;
+  const float inv_tau = 1.0f / fmaxf(dm.gate_tau, 1e-6f);
+  for (int row = blockIdx.x * kCfWarps + warp; row < n_rows; row += gridDim.x * kCfWarps) {
+    float g0 = 1.0f / 3.0f, g1 = 1.0f / 3.0f, g2 = 1.0f / 3.0f;
+    if (dm.gate_mode == NSA_GATE_CMP) { g0 = 1.f; g1 = 0.f; g2 = 0.f; }
+    else if (dm.gate_mode == NSA_GATE_SEL) { g0 = 0.f; g1 = 1.f; g2 = 0.f; }
+    else if (dm.gate_mode == NSA_GATE_WIN) { g0 = 0.f; g1 = 0.f; g2 = 1.f; }
+    else if (mlp) {
+      // q_gp = mean over heads (nsa_attention.py:1357): lane owns k = 2*lane, 2*lane+1 (+64, ...)
+      const T* qrow = Q + (size_t)row * h * Dk;
+      for (int k = 2 * lane; k < Dk; k += 64) {
+        float m0 = 0.f, m1 = 0.f;
+        for (int hh = 0; hh < h; ++hh) {
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(qrow + hh * Dk + k);
+          m0 += (float)reinterpret_cast<const T*>(&v)[0];
+          m1 += (float)reinterpret_cast<const T*>(&v)[1];
+        }
+        qgp[k] = m0 / (float)h;
+        qgp[k + 1] = m1 / (float)h;
+      }
+      __syncwarp();
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f;
+      for (int u = lane; u < H; u += 32) {
+        float a = b1[u];
+        for (int k = 0; k < Dk; ++k) a = fmaf(w1t[k * H + u], qgp[k], a);
+        const float x = a / (1.0f + expf(-a));  // silu
+        l0 = fmaf(w2[u], x, l0);
+        l1 = fmaf(w2[H + u], x, l1);
+        l2 = fmaf(w2[2 * H + u], x, l2);
+      }
+      l0 = (warp_sum(l0) + b2[0]) * inv_tau;
+      l1 = (warp_sum(l1) + b2[1]) * inv_tau;
+      l2 = (warp_sum(l2) + b2[2]) * inv_tau;
+      const float mx = fmaxf(l0, fmaxf(l1, l2));
+      const int am = l0 >= l1 ? (l0 >= l2 ? 0 : 2) : (l1 >= l2 ? 1 : 2);  // first maximum
+      const float second = am == 0 ? fmaxf(l1, l2) : (am == 1 ? fmaxf(l0, l2) : fmaxf(l0, l1));
+      if (mx - second > 50.0f) {  // hard one-hot (nsa_attention.py:74-81)
+        g0 = am == 0 ? 1.f : 0.f; g1 = am == 1 ? 1.f : 0.f; g2 = am == 2 ? 1.f : 0.f;
+      } else {
+        const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), e2 = expf(l2 - mx);
+        const float inv = 1.0f / (e0 + e1 + e2);
+        g0 = e0 * inv; g1 = e1 * inv; g2 = e2 * inv;
+      }
+      __syncwarp();
+    }
+    if (gates && lane == 0) {
+      gates[(size_t)row * 3] = g0;
+      gates[(size_t)row * 3 + 1] = g1;
+      gates[(size_t)row * 3 + 2] = g2;
+    }
+    const size_t base = (size_t)row * row_elems;
+    for (int cidx = lane; cidx < chunks; cidx += 32) {
+      const uint4 a = *reinterpret_cast<const uint4*>(O_br + base + cidx * 8);
+      const uint4 b = *reinterpret_cast<const uint4*>(O_br + per_branch + base + cidx * 8);
+      const uint4 c = *reinterpret_cast<const uint4*>(O_br + 2 * per_branch + base + cidx * 8);
+      const T* pa = reinterpret_cast<const T*>(&a);
+      const T* pb = reinterpret_cast<const T*>(&b);
+      const T* pc = reinterpret_cast<const T*>(&c);
+      uint4 o;
+      T* po = reinterpret_cast<T*>(&o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) po[e] = T(g0 * (float)pa[e] + g1 * (float)pb[e] + g2 * (float)pc[e]);
+      *reinterpret_cast<uint4*>(O + base + cidx * 8) = o;
+    }
+  }
+}
+
+template <typename T>
+static int launch_combine_fast(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t& gp, const void* O_br, void* O,
+                               float* gates, cudaStream_t stream) {
+  const int n_rows = dm.B * dm.S * dm.G;
+  const int H = dm.gate_mode == NSA_GATE_MLP ? dm.gate_hidden : 0;
+  size_t smem = ((size_t)dm.Dk * H + H + 3 * H + 4 + (size_t)kCfWarps * dm.Dk) * sizeof(float);
+  int blocks = ceil_div(n_rows, kCfWarps);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  combine_fast_kernel<T><<<blocks, kCfWarps * 32, smem, stream>>>(dm, (const T*)Q, gp, (const T*)O_br, (T*)O, gates);
+  return check_launch("combine_fast_kernel");
+}
+
 int launch_combine(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t& gp, const void* O_br, void* O, float* gates,
                    cudaStream_t stream) {
   const int n_rows = dm.B * dm.S * dm.G;
   if (n_rows == 0) return NSA_OK;
+  const int H = dm.gate_mode == NSA_GATE_MLP ? dm.gate_hidden : 0;
+  if (dm.dtype != NSA_F32 && (dm.h * dm.Dv) % 8 == 0 && dm.Dk % 2 == 0 &&
+      ((size_t)dm.Dk * H + 4 * H + 4 + (size_t)kCfWarps * dm.Dk) * sizeof(float) <= 48 * 1024 &&
+      ((uintptr_t)O_br & 15) == 0 && ((uintptr_t)O & 15) == 0 && ((uintptr_t)Q & 3) == 0) {
+    if (dm.dtype == NSA_BF16) return launch_combine_fast<__nv_bfloat16>(dm, Q, gp, O_br, O, gates, stream);
+    return launch_combine_fast<__half>(dm, Q, gp, O_br, O, gates, stream);
+  }
   int blocks = ceil_div(n_rows, kAttnWarps);
   if (blocks > 148 * 16) blocks = 148 * 16;
   size_t smem = (size_t)kAttnWarps * (dm.Dk + 2 * dm.gate_hidden) * sizeof(float);
