@@ -35,7 +35,6 @@ struct DnMisc {
   uint64_t q_full;
   uint64_t k_full[kDnKS], k_empty[kDnKS], v_full[kDnVS], v_empty[kDnVS];
   uint64_t s_full[kDnMT], s_empty[kDnMT], p_full[kDnMT], p_empty[kDnMT];
-  uint64_t o_full[kDnMT][2], o_empty[kDnMT][2];
   uint32_t tmem_base;
 };
 
@@ -50,6 +49,14 @@ __device__ __forceinline__ void dn_ld_wait32(uint32_t (&r)[32]) {
                  "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
                  "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
                  "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+__device__ __forceinline__ void dn_ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                :
                : "memory");
 }
@@ -70,13 +77,17 @@ __device__ __forceinline__ void dn_row_range(const nsa_dims_t& dm, int branch, i
   }
 }
 
+#ifdef NSA_DENSE_DBG  // compile-time: timeline of one CTA (tag, tile, clock) for tools/dbg_dense.py
 #define DDBG(tag, it)                                                                 \
   do {                                                                                \
-    if (dbg && blockIdx.x == gridDim.x / 2 + 200) {                                         \
+    if (dbg && blockIdx.x == gridDim.x / 2 + 200) {                                   \
       const unsigned long long i_ = atomicAdd((unsigned long long*)dbg, 1ull);        \
       if (i_ < 4000) { dbg[1 + 2 * i_] = ((long long)(tag) << 32) | (unsigned)(it); dbg[2 + 2 * i_] = clock64(); } \
     }                                                                                 \
   } while (0)
+#else
+#define DDBG(tag, it) do { } while (0)
+#endif
 
 template <typename T>
 __global__ void __launch_bounds__(32 * (4 * kDnMT + 2), 1)
@@ -118,7 +129,6 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(&ms->s_empty[m], 4);
       mbar_init(&ms->p_full[m], 4);
       mbar_init(&ms->p_empty[m], 1);
-      for (int i = 0; i < 2; ++i) { mbar_init(&ms->o_full[m][i], 1); mbar_init(&ms->o_empty[m][i], 4); }
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmQ);
@@ -131,7 +141,7 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = ms->tmem_base;
-  // TMEM columns: S[mt] at mt*128 ; O_t[mt][st] at 256 + (mt*2+st)*64
+  // TMEM columns: S[mt] at mt*128 ; O[mt] (accumulated over all key tiles) at 256 + mt*64
 
   if (warp == kSoftWarps) {
     // ===== TMA producer ====================================================================================
@@ -176,16 +186,14 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int m = 0; m < MT; ++m) {
           DDBG(10 + m, i);
           mbar_wait(&ms->p_full[m], i & 1);
-          mbar_wait(&ms->o_empty[m][i & 1], ((i >> 1) & 1) ^ 1);
           DDBG(12 + m, i);
           tc_fence_after();
           const uint32_t pb = smem_u32(smem + DnSmem::p + m * 2 * kDnTile);
-          const uint32_t od = tmem + 256 + (m * 2 + (i & 1)) * 64;
+          const uint32_t od = tmem + 256 + m * 64;
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma_f16(od, make_smem_desc(pb + (k >> 2) * kDnTile + (k & 3) * 32, 16, 1024, kSwizzle128B),
-                     make_smem_desc(vb + k * 2048, 8192, 1024, kSwizzle128B), idesc_pv, k > 0);
-          umma_commit(&ms->o_full[m][i & 1]);
+                     make_smem_desc(vb + k * 2048, 8192, 1024, kSwizzle128B), idesc_pv, (i > 0 || k > 0) ? 1u : 0u);
           umma_commit(&ms->p_empty[m]);
           if (i + 1 < n) {
             mbar_wait(&ms->s_empty[m], i & 1);
@@ -204,122 +212,127 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int tok_l = r / dm.h, head = r - tok_l * dm.h;
     const int s = s_base + mt * TOK + tok_l;
     const bool row_ok = tok_l < TOK && s < dm.S;
-    int lo = 0, hi = 0;
+    // rows that are not stored (padding rows of the M-tile, tokens beyond S) behave like rows that see every key, so they
+    // never push their warp onto the masked path
+    int lo = 0, hi = 0x3fffffff;
     if (row_ok) dn_row_range(dm, branch, dm.t0 + s, lo, hi);
     const float c = dm.scale * kLog2e;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tm_S = tmem + lane_off + mt * 128;
-    const uint32_t tm_O = tmem + lane_off + 256 + mt * 128;
+    const uint32_t tm_O = tmem + lane_off + 256 + mt * 64;
     uint8_t* prow = smem + DnSmem::p + mt * 2 * kDnTile + r * 128;
     const int sw = r & 7;
 
-    float acc[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+    float m_run = -INFINITY, l_run = 0.f;
 
-    auto fold_o = [&](int i, float alpha) {  // acc = acc * alpha + O_t(i)
-      const int st = i & 1;
-      mbar_wait(&ms->o_full[mt][st], (i >> 1) & 1);
-      tc_fence_after();
-      uint32_t oa[32], ob[32];
-      tmem_ld32(tm_O + st * 64, oa);
-      tmem_ld32(tm_O + st * 64 + 32, ob);
-      dn_ld_wait32(oa);
-      dn_ld_wait32(ob);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ms->o_empty[mt][st]);
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        acc[e] = fmaf(acc[e], alpha, __uint_as_float(oa[e]));
-        acc[32 + e] = fmaf(acc[32 + e], alpha, __uint_as_float(ob[e]));
-      }
-    };
-
+    // Online softmax with a LAZY reference: m_run is fixed by the first tile that holds a valid key (two passes over that
+    // tile: max, then probabilities) and then only moves when a later tile exceeds it by more than kJump (log2 units), in
+    // which case that row redoes the tile against the new reference and rescales.  Every other tile is ONE pass over S:
+    // p = exp2(s*c - m_run*c) (values above 1 are fine in fp32 / bf16), so S is read from TMEM once and nothing waits
+    // for a tile maximum.  Exact: P, l and acc always share one reference per row.
+    constexpr float kJump = 24.f;
     for (int i = 0; i < n; ++i) {
       const int col_base = (kt_lo + i) * 128;
       if (tid == 0) DDBG(1, i);
       mbar_wait(&ms->s_full[mt], i & 1);
       if (tid == 0) DDBG(2, i);
       tc_fence_after();
-      const bool full_tile = col_base >= lo && col_base + 128 <= hi;
-      // ---- pass A: tile max ----
-      float cm = -INFINITY;
-      {
-        uint32_t va[32], vb[32];
-        tmem_ld32(tm_S, va);
+      // one path per warp: the masked path also handles full rows, so a warp takes it as a whole or not at all
+      const bool full_tile = __all_sync(0xffffffffu, col_base >= lo && col_base + 128 <= hi);
+      // tcgen05.ld is warp-collective: every decision that guards one is made warp-uniform with a ballot
+      if (__ballot_sync(0xffffffffu, !(m_run > -INFINITY)) != 0u) {  // a row without a reference: take this tile's maximum
+        float cm = -INFINITY;
+        uint32_t ua[16];
+#pragma unroll 1
+        for (int ch = 0; ch < 8; ++ch) {
+          tmem_ld16(tm_S + ch * 16, ua);
+          dn_ld_wait16(ua);
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t(&cur)[32] = (ch & 1) ? vb : va;
-          uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
-          dn_ld_wait32(cur);
-          if (ch < 3) tmem_ld32(tm_S + (ch + 1) * 32, nxt);
-          if (full_tile) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) cm = fmaxf(cm, __uint_as_float(cur[e]));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int col = col_base + ch * 32 + e;
-              if (col >= lo && col < hi) cm = fmaxf(cm, __uint_as_float(cur[e]));
-            }
+          for (int e = 0; e < 16; ++e) {
+            const int col = col_base + ch * 16 + e;
+            if (col >= lo && col < hi) cm = fmaxf(cm, __uint_as_float(ua[e]));
           }
         }
+        if (!(m_run > -INFINITY)) m_run = cm;
       }
-      const float m_new = fmaxf(m_run, cm);
-      const bool any = m_new > -INFINITY;
-      const float alpha = any ? dn_ex2((m_run - m_new) * c) : 1.f;
-      const float mc = any ? m_new * c : 0.f;
       if (tid == 0) DDBG(3, i);
       mbar_wait(&ms->p_empty[mt], (i & 1) ^ 1);  // P.V of the previous tile has read the P buffer
       if (tid == 0) DDBG(4, i);
-      // ---- pass B: probabilities -> bf16 P tile (K-major, 128B swizzle) ----
-      float rowsum = 0.f;
-      {
-        uint32_t va[32], vb[32];
-        tmem_ld32(tm_S, va);
+      float alpha = 1.f, rowsum = 0.f;
+#pragma unroll 1
+      for (int rep = 0; rep < 2; ++rep) {
+        const bool any = m_run > -INFINITY;
+        const float mc = any ? m_run * c : 0.f;
+        float cm = -INFINITY;
+        rowsum = 0.f;
+        // 8 chunks of 16 columns, TMEM loads double-buffered; probabilities overwrite the loaded registers in place
+        uint32_t ua[16], ub[16];
+        tmem_ld16(tm_S, ua);
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t(&cur)[32] = (ch & 1) ? vb : va;
-          uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
-          dn_ld_wait32(cur);
-          if (ch < 3) tmem_ld32(tm_S + (ch + 1) * 32, nxt);
-          // issue the 32 exponentials first, consume them afterwards (a MUFU result used by the next instruction stalls
-          // the in-order issue for the MUFU latency; only 2 warps share a scheduler here)
-          float pe[32];
+        for (int ch = 0; ch < 8; ++ch) {
+          uint32_t(&cur)[16] = (ch & 1) ? ub : ua;
+          uint32_t(&nxt)[16] = (ch & 1) ? ua : ub;
+          dn_ld_wait16(cur);
+          if (ch < 7) tmem_ld16(tm_S + (ch + 1) * 16, nxt);
           if (full_tile) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) pe[e] = dn_ex2(fmaf(__uint_as_float(cur[e]), c, -mc));
+            for (int e = 0; e < 16; e += 2) cm = fmaxf(cm, fmaxf(__uint_as_float(cur[e]), __uint_as_float(cur[e + 1])));
+            // issue the 16 exponentials first, consume them afterwards (a MUFU result used by the next instruction
+            // stalls the in-order issue for the MUFU latency)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) cur[e] = __float_as_uint(dn_ex2(fmaf(__uint_as_float(cur[e]), c, -mc)));
           } else {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int col = col_base + ch * 32 + e;
-              pe[e] = (any && col >= lo && col < hi) ? dn_ex2(fmaf(__uint_as_float(cur[e]), c, -mc)) : 0.f;
+            for (int e = 0; e < 16; ++e) {
+              const int col = col_base + ch * 16 + e;
+              const bool ok = any && col >= lo && col < hi;
+              if (ok) cm = fmaxf(cm, __uint_as_float(cur[e]));
+              cur[e] = ok ? __float_as_uint(dn_ex2(fmaf(__uint_as_float(cur[e]), c, -mc))) : 0u;
             }
           }
-          uint32_t pk[16];
-          float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+          float r0 = 0.f, r1 = 0.f;
+          uint32_t pk[8];
 #pragma unroll
-          for (int e = 0; e < 32; e += 8) {
-            r0 += pe[e] + pe[e + 1];
-            r1 += pe[e + 2] + pe[e + 3];
-            r2 += pe[e + 4] + pe[e + 5];
-            r3 += pe[e + 6] + pe[e + 7];
+          for (int e = 0; e < 16; e += 4) {
+            r0 += __uint_as_float(cur[e]) + __uint_as_float(cur[e + 1]);
+            r1 += __uint_as_float(cur[e + 2]) + __uint_as_float(cur[e + 3]);
           }
-          rowsum += (r0 + r1) + (r2 + r3);
+          rowsum += r0 + r1;
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) pk[e >> 1] = pack2(T(), pe[e], pe[e + 1]);
-          // 32 keys = 4 chunks of 16 B; key chunk index kc = ch*4 + q in [0,16): half = kc >> 3, chunk-in-row = kc & 7
+          for (int e = 0; e < 16; e += 2) pk[e >> 1] = pack2(T(), __uint_as_float(cur[e]), __uint_as_float(cur[e + 1]));
+          // 16 keys = 2 chunks of 16 B; key chunk index kc = ch*2 + q in [0,16): half = kc >> 3, chunk-in-row = kc & 7
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int kc = ch * 4 + q;
+          for (int q = 0; q < 2; ++q) {
+            const int kc = ch * 2 + q;
             *reinterpret_cast<uint4*>(prow + (kc >> 3) * kDnTile + (((kc & 7) ^ sw) << 4)) =
                 make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
           }
         }
+        const bool jump = any && (cm - m_run) * c > kJump;
+        if (rep == 1 || __ballot_sync(0xffffffffu, jump) == 0u) break;
+        // rare: a row's tile maximum is far above its reference -> new reference for that row; the whole warp redoes the
+        // tile (rows that did not move recompute the same values) and the past is rescaled
+        if (jump) {
+          alpha = dn_ex2((m_run - cm) * c);
+          l_run *= alpha;
+          m_run = cm;
+        }
       }
       if (tid == 0) DDBG(5, i);
+      // rare, warp-uniform: a row moved its reference -> scale the O accumulated so far (in TMEM; P.V of tile i-1 is complete,
+      // P.V of this tile has not been released yet)
+      if (__ballot_sync(0xffffffffu, alpha != 1.f) != 0u && i > 0) {
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t oa[32];
+          tmem_ld32(tm_O + hf * 32, oa);
+          dn_ld_wait32(oa);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) oa[e] = __float_as_uint(__uint_as_float(oa[e]) * alpha);
+          tmem_st32(tm_O + hf * 32, oa);
+        }
+        tmem_st_wait();
+      }
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
@@ -328,15 +341,25 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_arrive(&ms->p_full[mt]);
       }
       if (tid == 0) DDBG(6, i);
-      l_run = fmaf(l_run, alpha, rowsum);
-      m_run = m_new;
-      if (i > 0) fold_o(i - 1, alpha_prev);
-      if (tid == 0) DDBG(7, i);
-      alpha_prev = alpha;
+      l_run += rowsum;
     }
-    if (n > 0) fold_o(n - 1, alpha_prev);
 
-    // ---- epilogue -------------------------------------------------------------------------------------------
+    // ---- epilogue: O (TMEM, all key tiles accumulated) / l -> global ------------------------------------------
+    float acc[64];
+    if (n > 0) {
+      mbar_wait(&ms->p_empty[mt], (n - 1) & 1);  // the last P.V has completed
+      tc_fence_after();
+      uint32_t oa[32], ob[32];
+      tmem_ld32(tm_O, oa);
+      tmem_ld32(tm_O + 32, ob);
+      dn_ld_wait32(oa);
+      dn_ld_wait32(ob);
+#pragma unroll
+      for (int e = 0; e < 32; ++e) { acc[e] = __uint_as_float(oa[e]); acc[32 + e] = __uint_as_float(ob[e]); }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 64; ++e) acc[e] = 0.f;
+    }
     if (row_ok) {
       const size_t orow = (((size_t)b * dm.S + s) * dm.G + g) * dm.h + head;
       const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;  // empty row -> zeros

@@ -159,7 +159,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int s = s_base + mt * TOK + tok_l;
     const bool row_ok = tok_l < TOK && s < dm.S;
     const int t = dm.t0 + s;
-    const int nk = !row_ok ? 0 : (causal ? num_cmp_at(t, dm.l, dm.d, dm.S_cmp) : dm.S_cmp);
+    // rows that are not stored (padding rows of the M-tile, tokens beyond S) take the key count of the CTA's last row, so
+    // they never push their warp onto the masked path
+    const int nk = !row_ok ? nk_cta : (causal ? num_cmp_at(t, dm.l, dm.d, dm.S_cmp) : dm.S_cmp);
     const float c = dm.scale * kLog2e;
     const uint32_t tm_row = tmem + ((uint32_t)((warp & 3) * 32) << 16) + mt * STG * 128;
     float* red = reinterpret_cast<float*>(smem + SM::red) + (size_t)mt * RB * 128 * kScRedLd;
@@ -179,9 +181,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_wait32(cur);
         if (ch < 3) tmem_ld32(tm_row + st * 128 + (ch + 1) * 32, nxt);
         const int col0 = kt * 128 + ch * 32;
+        const bool wfull = __all_sync(0xffffffffu, col0 + 32 <= nk);  // one path per warp (no divergent double execution)
         if (col0 < nk) {
           float cm = -INFINITY;
-          if (col0 + 32 <= nk) {
+          if (wfull) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(cur[i]));
           } else {
@@ -233,7 +236,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (ch < 3) tmem_ld32(tm_row + st * 128 + (ch + 1) * 32, nxt);
           const int col0 = kt * 128 + ch * 32;
           float p[32];
-          if (has && col0 + 32 <= nk) {
+          if (__all_sync(0xffffffffu, has && col0 + 32 <= nk)) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) p[i] = ex2f(fmaf(__uint_as_float(cur[i]), c, -offs));
           } else {

@@ -226,3 +226,26 @@ def test_score_tc_four_mtile_path(norm):
     r = ops.score_select(Q.cuda().bfloat16(), Kc.cuda().bfloat16(), cfg, mode=0).cpu()
     _, bad = O.ranges_equivalent(r, O.select_ranges_prefill(want, ls, n, S))
     assert bad <= B * S * G // 200, bad
+
+
+def test_dense_tc_reference_jump():
+    """Later key tiles hold logits far above the first tile's maximum: the lazy softmax reference must move (rows redo the
+    tile and rescale the accumulated O in TMEM) and still match the oracle."""
+    ops = _ops()
+    B, S, G, h, l, d, ls, n, w = 1, 1100, 2, 6, 32, 16, 64, 16, 512
+    ts = _case(B, S, G, h, l, d, ls, n, w, seed=21, dtype=torch.bfloat16)
+    # window keys: tokens >= 400 are 30x larger; compressed keys: entries >= 20 are 30x larger
+    ts[3][:, :, 400:] *= 30.0
+    ts[5][:, :, 20:] *= 30.0
+    ts = [t.bfloat16().float() for t in ts]
+    cfg = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w, impl=ops.IMPL_TC)
+    Q = ts[0].cuda().bfloat16()
+    o, lse = ops.branch_attention(ops.BR_WIN, Q, ts[3].cuda().bfloat16(), ts[4].cuda().bfloat16(), cfg, return_lse=True)
+    want, lse_w = O.win_attention(ts[0], ts[3], ts[4], w)
+    assert torch.isfinite(o.float()).all()
+    assert (o.float().cpu() - want).abs().max() <= 3e-2, (o.float().cpu() - want).abs().max()
+    assert (lse.cpu() - lse_w).abs().max() <= 0.25  # logits are O(1e3) here; bf16-rounded inputs, fp32 accumulate
+    o, lse = ops.branch_attention(ops.BR_CMP, Q, ts[5].cuda().bfloat16(), ts[6].cuda().bfloat16(), cfg, return_lse=True)
+    want, lse_w = O.cmp_attention(ts[0], ts[5], ts[6], l, d)
+    assert torch.isfinite(o.float()).all()
+    assert (o.float().cpu() - want).abs().max() <= 3e-2, (o.float().cpu() - want).abs().max()
