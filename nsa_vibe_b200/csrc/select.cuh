@@ -104,6 +104,56 @@ __device__ inline void select_row_warp(float* sc, int S_sel, int l_sel, int n_se
           const uint32_t word = __ballot_sync(0xffffffffu, c > NEG && rank < k_act);
           if ((s & 31) == lane) bm[s >> 5] |= word;
         }
+      } else if (S_sel <= 1024) {
+        // <= 32 candidates per lane in 4 groups of 8 (group = 8 consecutive strides): the group maxima live in registers, a
+        // round is two warp reductions (redux max on an order-preserving key, redux min on the index for the lower-index
+        // tie rule) and the owner lane rescans only the 8 entries of the group it took from.
+        __syncwarp();
+        float gv[4];
+        int gj[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          gv[g] = NEG;
+          gj[g] = 0x7fffffff;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const int j = lane + 32 * (8 * g + kk);
+            if (j < S_sel) {
+              const float c = sc[j];
+              if (c > gv[g]) { gv[g] = c; gj[g] = j; }
+            }
+          }
+        }
+        for (int it = 0; it < k_act; ++it) {
+          float bv = gv[0];
+          int bj = gj[0];
+#pragma unroll
+          for (int g = 1; g < 4; ++g)
+            if (gv[g] > bv) { bv = gv[g]; bj = gj[g]; }  // ascending j across groups: strict > keeps the lower index
+          const uint32_t bits = __float_as_uint(bv);
+          const uint32_t key = bits ^ ((bits >> 31) ? 0xffffffffu : 0x80000000u);  // order-preserving
+          const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
+          if (kmax == (0xff800000u ^ 0xffffffffu)) break;  // only -inf left: invalid picks are dropped in both modes
+          const int vj = (int)__reduce_min_sync(0xffffffffu, key == kmax ? (uint32_t)bj : 0x7fffffffu);
+          bitmap_set(bm, lane, vj);
+          if ((vj & 31) == lane) {
+            sc[vj] = NEG;
+            const int g = vj >> 8;  // (vj / 32) / 8
+            float v = NEG;
+            int vi = 0x7fffffff;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const int j = lane + 32 * (8 * g + kk);
+              if (j < S_sel) {
+                const float c = sc[j];
+                if (c > v) { v = c; vi = j; }
+              }
+            }
+#pragma unroll
+            for (int g2 = 0; g2 < 4; ++g2)
+              if (g2 == g) { gv[g2] = v; gj[g2] = vi; }
+          }
+        }
       } else
       for (int it = 0; it < k_act; ++it) {
         float v = best;
