@@ -99,6 +99,12 @@ int nsa_score_select(const nsa_dims_t* dm, const void* Q, const void* K_cmp, int
  * every allowed key.  O_b [B,S,G,h,Dv] in dm->dtype, lse_b [B,S,G,h] fp32 (either may be NULL). */
 int nsa_branch_attn_fwd(const nsa_dims_t* dm, int branch, const void* Q, const void* K, const void* V,
                         const int32_t* ranges, void* O_b, float* lse_b, void* stream);
+/* Selected branch, KV-block-major: every 64-key block is read once per run of the queries that selected it and the
+ * per-(query, block) partials are merged (same result as nsa_branch_attn_fwd(branch = 1); the form that scales to long
+ * prefill, where the query-major gather is bound by L2 bandwidth).  workspace: nsa_workspace_bytes(dm, NSA_WS_SEL_BLOCKMAJOR).
+ * Returns NSA_ERR_UNSUPPORTED when the shape has no block-major kernel (use nsa_branch_attn_fwd). */
+int nsa_sel_attn_fwd_blockmajor(const nsa_dims_t* dm, const void* Q, const void* K_sel, const void* V_sel,
+                                const int32_t* ranges, void* O_b, float* lse_b, void* workspace, void* stream);
 /* Analytical backward of one branch (replaces _selection_attention_backward,
  * kernels/triton_sel_kernel/__init__.py:163-231, without its first-key-only line).
  * dO_b [B,S,G,h,Dv] in dm->dtype, O_b as saved, dQ/dK/dV fp32 accumulators (+=, caller zeroes). */
@@ -115,8 +121,8 @@ int nsa_gate_bwd(const nsa_dims_t* dm, const void* Q, const nsa_gate_params_t* g
 /* ---- fused hot path ------------------------------------------------------------------------
  * nsa_prefill_fwd: the three branches + gate + combine in one pass; branch outputs stay on chip
  * unless O_branches (3 x [B,S,G,h,Dv], dm->dtype) is non-NULL (needed only to run backward).
- * workspace: nsa_workspace_bytes(dm, NSA_WS_PREFILL) bytes when O_branches is NULL (0 when the single fused kernel
- * serves the shape; otherwise staging for branch kernels that run separately).
+ * workspace: nsa_workspace_bytes(dm, NSA_WS_PREFILL) bytes (0 when the single fused kernel serves the shape; otherwise
+ * staging for the branch kernels that run separately plus the index / partials of the block-major selected branch).
  * Replaces nsa_attention.py:1137-1398. */
 int nsa_prefill_fwd(const nsa_dims_t* dm, const void* Q,
                     const void* K_sel, const void* V_sel, const void* K_win, const void* V_win,
@@ -139,7 +145,7 @@ int nsa_decode_fwd(const nsa_dims_t* dm, const void* Q,
                    const void* K_cmp, const void* V_cmp, const nsa_gate_params_t* gp,
                    void* O, int32_t* ranges_out, void* workspace, void* stream);
 
-enum { NSA_WS_SCORE_SELECT = 0, NSA_WS_DECODE = 1, NSA_WS_PREFILL = 2 };
+enum { NSA_WS_SCORE_SELECT = 0, NSA_WS_DECODE = 1, NSA_WS_PREFILL = 2, NSA_WS_SEL_BLOCKMAJOR = 3 };
 int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which);
 
 #ifdef __cplusplus

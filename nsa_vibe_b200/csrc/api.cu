@@ -2,6 +2,7 @@
 // (tcgen05 kernels when the shape allows, SIMT otherwise -- both hand-written sm_100a CUDA; there is no
 // CPU path) and launches on the caller's stream.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -45,6 +46,15 @@ static int validate_dims(const nsa_dims_t* dm, const char* who) {
 }
 
 static bool tc_eligible(const nsa_dims_t& dm) { return dm.impl != NSA_IMPL_SIMT; }
+
+// The block-major selected branch pays for an index build and a merge pass: worth it once the query-major gather is bound by
+// L2 bandwidth, i.e. for long prefill.  NSA_B200_SEL2=0|1 forces the choice (benchmarks / tests).
+static bool use_sel2(const nsa_dims_t& dm) {
+  static const int env = getenv("NSA_B200_SEL2") ? atoi(getenv("NSA_B200_SEL2")) : -1;
+  if (!tc_sel2_supported(dm) || env == 0) return false;
+  if (env == 1) return true;
+  return (long long)dm.B * dm.S * dm.G >= 16384 && dm.S_sel_kv >= 4096;
+}
 
 }  // namespace nsa
 
@@ -128,6 +138,17 @@ int nsa_branch_attn_fwd(const nsa_dims_t* dm, int branch, const void* Q, const v
   return launch_fwd_generic(d2, a, (cudaStream_t)stream);
 }
 
+int nsa_sel_attn_fwd_blockmajor(const nsa_dims_t* dm, const void* Q, const void* K_sel, const void* V_sel,
+                                const int32_t* ranges, void* O_b, float* lse_b, void* workspace, void* stream) {
+  if (int rc = validate_dims(dm, "sel_attn_fwd_blockmajor")) return rc;
+  NSA_REQUIRE(Q && K_sel && V_sel && ranges && O_b && workspace, "sel_attn_fwd_blockmajor: NULL pointer");
+  if (!tc_sel2_supported(*dm)) {
+    set_error("sel_attn_fwd_blockmajor: no block-major kernel for this shape/dtype");
+    return NSA_ERR_UNSUPPORTED;
+  }
+  return launch_sel2_tc(*dm, Q, K_sel, V_sel, ranges, O_b, lse_b, workspace, (cudaStream_t)stream);
+}
+
 int nsa_branch_attn_bwd(const nsa_dims_t* dm, int branch, const void* Q, const void* K, const void* V,
                         const int32_t* ranges, const void* O_b, const float* lse_b, const void* dO_b, float* dQ,
                         float* dK, float* dV, void* stream) {
@@ -190,17 +211,22 @@ int nsa_prefill_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, cons
     return launch_fwd_generic(*dm, a, st);
   }
   // tensor-core branches run as their own kernels; branch outputs go through O_branches (or the workspace)
-  void* obr = O_branches ? O_branches : workspace;
-  NSA_REQUIRE(obr, "prefill_fwd: this shape needs O_branches or a workspace of nsa_workspace_bytes(NSA_WS_PREFILL)");
   const size_t rows_h = (size_t)dm->B * dm->S * dm->G * dm->h;
   const size_t per_branch = rows_h * dm->Dv * elt_size(dm->dtype);
+  const size_t staging = (3 * per_branch + 255) & ~(size_t)255;
+  void* obr = O_branches ? O_branches : workspace;
+  NSA_REQUIRE(obr, "prefill_fwd: this shape needs O_branches or a workspace of nsa_workspace_bytes(NSA_WS_PREFILL)");
   const void* Ks[3] = {K_cmp, K_sel, K_win};
   const void* Vs[3] = {V_cmp, V_sel, V_win};
   for (int br = 0; br < 3; ++br) {
     if (!(tc_mask & (1 << br))) continue;
-    if (int rc = launch_branch_tc(*dm, br, Q, Ks[br], Vs[br], ranges, (char*)obr + br * per_branch,
-                                  lse ? lse + br * rows_h : nullptr, st))
-      return rc;
+    void* ob = (char*)obr + br * per_branch;
+    float* lb = lse ? lse + br * rows_h : nullptr;
+    if (br == 1 && workspace && use_sel2(*dm)) {  // long prefill: KV-block-major selected branch
+      if (int rc = launch_sel2_tc(*dm, Q, K_sel, V_sel, ranges, ob, lb, (char*)workspace + staging, st)) return rc;
+      continue;
+    }
+    if (int rc = launch_branch_tc(*dm, br, Q, Ks[br], Vs[br], ranges, ob, lb, st)) return rc;
   }
   if (tc_mask != 7) {
     a.O_br = obr;
@@ -273,10 +299,14 @@ int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which) {
       return tc_score_workspace(*dm);
     case NSA_WS_PREFILL: {
       for (int br = 0; br < 3; ++br)
-        if (tc_branch_supported(*dm, br))
-          return (int64_t)3 * dm->B * dm->S * dm->G * dm->h * dm->Dv * (int64_t)elt_size(dm->dtype);
+        if (tc_branch_supported(*dm, br)) {
+          const int64_t staging = ((int64_t)3 * dm->B * dm->S * dm->G * dm->h * dm->Dv * (int64_t)elt_size(dm->dtype) + 255) & ~(int64_t)255;
+          return staging + (use_sel2(*dm) ? tc_sel2_workspace(*dm) : 0);
+        }
       return 0;
     }
+    case NSA_WS_SEL_BLOCKMAJOR:
+      return tc_sel2_workspace(*dm);
     default:
       return 0;
   }

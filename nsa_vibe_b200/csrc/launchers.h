@@ -45,6 +45,10 @@ int launch_combine(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t&
 bool tc_branch_supported(const nsa_dims_t& dm, int branch);
 bool tc_score_supported(const nsa_dims_t& dm);
 bool tc_decode_supported(const nsa_dims_t& dm);
+bool tc_sel2_supported(const nsa_dims_t& dm);
+int64_t tc_sel2_workspace(const nsa_dims_t& dm);
+int launch_sel2_tc(const nsa_dims_t& dm, const void* Q, const void* K, const void* V, const int32_t* ranges, void* O, float* lse,
+                   void* workspace, cudaStream_t stream);
 int64_t tc_score_workspace(const nsa_dims_t& dm);
 int64_t tc_decode_workspace(const nsa_dims_t& dm);
 int launch_score_tc(const nsa_dims_t& dm, const void* Q, const void* Kc, int S_sel, int S_total, int sel_mode, int Kr,

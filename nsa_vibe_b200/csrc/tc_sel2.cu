@@ -1,0 +1,622 @@
+// Selected-branch attention, KV-block-major ("inverted index") -- the prefill path for long sequences.
+//
+// The query-major gather kernel (tc_gather.cu) re-reads 16 x 16 KB of K/V for every (b, t, g) row: 34 GB per 64k
+// sequence, bound by L2 bandwidth.  Here the roles are swapped: for every 64-key block the queries that selected it are
+// listed (a CSR built on the device from the ranges), the block's K/V tile is loaded ONCE per run of those queries, and
+// each (query, block) pair yields a partial (O, lse) that a merge kernel folds per query -- exactly the split-softmax
+// identity, so the result equals grouped_selection_attention_masked (attention_kernels.py:705-772) like the gather kernel.
+//   1. sel2_count / sel2_scan / sel2_fill : ranges -> per-block pair lists (padded to whole M-tiles), pair_of[row][slot]
+//   2. sel2_attn_kernel (tcgen05)         : per block, M-tiles of TOK queries x h heads against the block's 64 keys:
+//        S = Q_g.K_j^T (M=128, N=64), exact softmax of the tile, O_p = P.V_j (M=128, N=64, K=64); Q rows arrive by one TMA
+//        box per query (hardware swizzle), two M-tile slots ping-pong on the tensor core
+//   3. sel2_merge                         : O[row] = sum_k w_k O_k, w_k = exp(lse_k - LSE), LSE = logsumexp_k lse_k
+// Traffic per 64k sequence: Q rows 1.6 GB (L2-resident source) + partials 1.7 GB written + read, instead of 34 GB.
+#include <stdlib.h>
+#include <string.h>
+
+#include "tc_common.cuh"
+#include "launchers.h"
+
+namespace nsa {
+using namespace tc;
+
+constexpr int kS2MaxSlots = 16;   // 64-key blocks per row (n_sel * l_sel <= 1024 keys)
+constexpr int kS2Run = 24;        // M-tiles one CTA walks (same block: its K/V tile is loaded once)
+constexpr int kS2Tile = 128 * 128;  // bytes of one 128-row Q tile / P tile half
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 1. index build.  One thread per (b, s, g) row; CTA-level shared-memory aggregation keeps the hot counters (block 0 and
+//    the local blocks are picked by every row) off the global atomics.
+// ---------------------------------------------------------------------------------------------------------------------
+struct S2Geom {
+  int B, S, G, n_ranges, S_kv, NB, t0, tokp;  // NB = 64-key blocks per slab, tokp = queries per M-tile
+};
+
+__device__ __forceinline__ int s2_row_blocks(const S2Geom& gm, const int32_t* __restrict__ rr, int* blk, int* valid) {
+  int n = 0;
+  for (int i = 0; i < gm.n_ranges; ++i) {
+    int a0 = rr[2 * i], a1 = rr[2 * i + 1];
+    if (a0 < 0) a0 = 0;
+    if (a1 > gm.S_kv) a1 = gm.S_kv;
+    for (int p = a0; p < a1 && n < kS2MaxSlots; p += 64) {
+      blk[n] = p >> 6;
+      valid[n] = a1 - p < 64 ? a1 - p : 64;
+      ++n;
+    }
+  }
+  return n;
+}
+
+constexpr int kS2IdxThreads = 256;
+
+// counts[bg * NB + j] += number of rows that selected block j
+__global__ void __launch_bounds__(kS2IdxThreads)
+sel2_count_kernel(S2Geom gm, const int32_t* __restrict__ ranges, int* __restrict__ counts) {
+  extern __shared__ int hist[];  // [G * NB] (rows of one CTA are consecutive (b, s, g): one b, every g)
+  const int n_rows = gm.B * gm.S * gm.G;
+  const int row0 = blockIdx.x * kS2IdxThreads;
+  const int b0 = row0 / (gm.S * gm.G);
+  for (int i = threadIdx.x; i < 2 * gm.G * gm.NB; i += blockDim.x) hist[i] = 0;  // two batches may meet in one CTA
+  __syncthreads();
+  const int row = row0 + threadIdx.x;
+  if (row < n_rows) {
+    const int g = row % gm.G, b = row / (gm.S * gm.G);
+    int blk[kS2MaxSlots], valid[kS2MaxSlots];
+    const int n = s2_row_blocks(gm, ranges + (size_t)row * gm.n_ranges * 2, blk, valid);
+    for (int k = 0; k < n; ++k) atomicAdd(&hist[((b - b0) * gm.G + g) * gm.NB + blk[k]], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * gm.G * gm.NB; i += blockDim.x) {
+    const int v = hist[i];
+    if (v) {
+      const int bb = b0 + i / (gm.G * gm.NB);
+      if (bb < gm.B) atomicAdd(&counts[(size_t)bb * gm.G * gm.NB + i % (gm.G * gm.NB)], v);
+    }
+  }
+}
+
+// Offsets of the block lists (each padded to a whole number of M-tiles) and the run table of the attention kernel:
+// run = (list, first M-tile, number of M-tiles <= kS2Run), every run inside one list so its CTA loads one K/V tile.
+// One CTA, sequential over chunks of 1024 lists (2 x 1024 lists at 64k: microseconds).
+struct S2Run { int list, tile0, ntiles, pad; };
+
+__device__ __forceinline__ int s2_block_scan(int v, int* buf) {  // inclusive scan over 1024 threads
+  buf[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int a = threadIdx.x >= o ? buf[threadIdx.x - o] : 0;
+    __syncthreads();
+    buf[threadIdx.x] += a;
+    __syncthreads();
+  }
+  const int r = buf[threadIdx.x];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(1024)
+sel2_scan_kernel(S2Geom gm, const int* __restrict__ counts, int* __restrict__ offs, int* __restrict__ cursors,
+                 S2Run* __restrict__ runs, int* __restrict__ n_runs) {
+  __shared__ int buf[1024];
+  __shared__ int tile_base, run_base;
+  if (threadIdx.x == 0) { tile_base = 0; run_base = 0; }
+  __syncthreads();
+  const int nlists = gm.B * gm.G * gm.NB;
+  for (int l0 = 0; l0 < nlists; l0 += 1024) {
+    const int l = l0 + threadIdx.x;
+    const int c = l < nlists ? counts[l] : 0;
+    const int tiles = (c + gm.tokp - 1) / gm.tokp;
+    const int nr = (tiles + kS2Run - 1) / kS2Run;
+    const int t_incl = s2_block_scan(tiles, buf);
+    const int r_incl = s2_block_scan(nr, buf);
+    const int tb = tile_base, rb = run_base;
+    if (l < nlists) {
+      const int t0 = tb + t_incl - tiles;
+      offs[l] = t0;
+      cursors[l] = 0;
+      for (int r = 0; r < nr; ++r) {
+        S2Run run;
+        run.list = l;
+        run.tile0 = t0 + r * kS2Run;
+        run.ntiles = tiles - r * kS2Run < kS2Run ? tiles - r * kS2Run : kS2Run;
+        run.pad = 0;
+        runs[rb + r_incl - nr + r] = run;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) { tile_base = tb + t_incl; run_base = rb + r_incl; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    offs[nlists] = tile_base;  // sentinel = total M-tiles
+    *n_runs = run_base;
+  }
+}
+
+// pair p (= tile * tokp + position) gets: tok[p] = b*S + s (query), hi[p] = valid keys of the block for that row;
+// pair_of[row][slot] = p.  Order inside a block list is arbitrary: partials are merged per (row, slot), so the result does
+// not depend on it.
+__global__ void __launch_bounds__(kS2IdxThreads)
+sel2_fill_kernel(S2Geom gm, const int32_t* __restrict__ ranges, const int* __restrict__ offs, int* __restrict__ cursors,
+                 int* __restrict__ tok, int* __restrict__ hi, int* __restrict__ pair_of) {
+  extern __shared__ int sm[];  // hist[2*G*NB] then base[2*G*NB]
+  const int nb2 = 2 * gm.G * gm.NB;
+  int* hist = sm;
+  int* basep = sm + nb2;
+  const int n_rows = gm.B * gm.S * gm.G;
+  const int row0 = blockIdx.x * kS2IdxThreads;
+  const int b0 = row0 / (gm.S * gm.G);
+  for (int i = threadIdx.x; i < nb2; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const int row = row0 + threadIdx.x;
+  int blk[kS2MaxSlots], valid[kS2MaxSlots], rank[kS2MaxSlots];
+  int n = 0, g = 0, b = 0;
+  if (row < n_rows) {
+    g = row % gm.G;
+    b = row / (gm.S * gm.G);
+    n = s2_row_blocks(gm, ranges + (size_t)row * gm.n_ranges * 2, blk, valid);
+    for (int k = 0; k < n; ++k) rank[k] = atomicAdd(&hist[((b - b0) * gm.G + g) * gm.NB + blk[k]], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb2; i += blockDim.x) {
+    const int v = hist[i];
+    const int bb = b0 + i / (gm.G * gm.NB);
+    basep[i] = (v && bb < gm.B) ? atomicAdd(&cursors[(size_t)bb * gm.G * gm.NB + i % (gm.G * gm.NB)], v) : 0;
+  }
+  __syncthreads();
+  if (row < n_rows) {
+    const int s = (row / gm.G) % gm.S;
+    for (int k = 0; k < kS2MaxSlots; ++k) {
+      int p = -1;
+      if (k < n) {
+        const int li = ((b - b0) * gm.G + g) * gm.NB + blk[k];
+        p = offs[(size_t)(b * gm.G + g) * gm.NB + blk[k]] * gm.tokp + basep[li] + rank[k];
+        tok[p] = b * gm.S + s;
+        hi[p] = valid[k];
+      }
+      pair_of[(size_t)row * kS2MaxSlots + k] = p;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 2. block-major attention on tcgen05
+// ---------------------------------------------------------------------------------------------------------------------
+struct S2Smem {
+  static constexpr int kv = 0;                              // K tile 8 KB, V tile 8 KB (64 keys)
+  static constexpr int q = kv + 2 * 8192;                   // [2 slots][2 stages] x 16 KB
+  static constexpr int p = q + 4 * kS2Tile;                 // [2 slots] x 16 KB  (128 rows x 64 keys, 16-bit, 128B-swizzled)
+  static constexpr int misc = p + 2 * kS2Tile;
+  static constexpr int total = misc + 512 + 1024;
+};
+
+struct S2Misc {
+  uint64_t kv_full;
+  uint64_t q_full[2][2], q_empty[2][2];
+  uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2], o_full[2], o_empty[2];
+  uint32_t tmem_base;
+  int tile0, ntiles, bg, blk;
+};
+
+__device__ __forceinline__ float s2_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void s2_ld_wait32(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+// grid: an upper bound on the number of runs; CTAs beyond *n_runs exit.  Each CTA loads the K/V tile of its block once and
+// walks its M-tiles, alternating between two slots (softmax warpgroups) that ping-pong on the tensor core.
+// O_p [pairs][h][64] (dtype T, normalised by the tile's own l), lse_p [pairs][h] fp32 (natural log).
+template <typename T>
+__global__ void __launch_bounds__(320, 2)
+sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, nsa_dims_t dm, S2Geom gm, const S2Run* __restrict__ runs,
+                 const int* __restrict__ n_runs, const int* __restrict__ tok, const int* __restrict__ hi,
+                 T* __restrict__ O_p, float* __restrict__ lse_p) {
+  if ((int)blockIdx.x >= *n_runs) return;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  S2Misc* ms = reinterpret_cast<S2Misc*>(smem + S2Smem::misc);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = dm.h, TOK = gm.tokp;
+  const S2Run run = runs[blockIdx.x];
+  const int bg = run.list / gm.NB, blk = run.list % gm.NB;
+  const int g = bg % gm.G;
+  const int n = run.ntiles;                 // M-tiles of this CTA; tile i goes to slot i & 1
+  const int n0 = (n + 1) >> 1, n1 = n >> 1;  // tiles per slot
+
+  // ---- setup ---------------------------------------------------------------------------------------------
+  {  // rows the TMA never writes (padding rows >= TOK*h, padded queries) must hold finite data
+    uint4 z = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 4 * kS2Tile / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem + S2Smem::q)[i] = z;
+  }
+  if (tid == 0) {
+    mbar_init(&ms->kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      for (int i = 0; i < 2; ++i) { mbar_init(&ms->q_full[s][i], 1); mbar_init(&ms->q_empty[s][i], 1); }
+      mbar_init(&ms->s_full[s], 1);
+      mbar_init(&ms->s_empty[s], 4);
+      mbar_init(&ms->p_full[s], 4);
+      mbar_init(&ms->p_empty[s], 1);
+      mbar_init(&ms->o_full[s], 1);
+      mbar_init(&ms->o_empty[s], 4);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 0) tmem_alloc(&ms->tmem_base, 256);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ms->tmem_base;
+  // TMEM columns: S[slot] at slot*64 ; O[slot] at 128 + slot*64
+
+  if (warp == 8) {
+    // ===== TMA producer: K/V tile once, then one box per query of every M-tile =================================
+    if (lane == 0) {
+      mbar_expect_tx(&ms->kv_full, 2 * 8192);
+      tma_load_3d(smem + S2Smem::kv, &tmK, &ms->kv_full, 0, blk * 64, bg);
+      tma_load_3d(smem + S2Smem::kv + 8192, &tmV, &ms->kv_full, 0, blk * 64, bg);
+    }
+    for (int i = 0; i < n; ++i) {
+      const int s = i & 1, k = i >> 1, st = k & 1;
+      const int p0 = (run.tile0 + i) * TOK;
+      const int tk = lane < TOK ? tok[p0 + lane] : -1;                // query (b*S + s) of pair p0 + lane, -1 = padding
+      const unsigned have = __ballot_sync(0xffffffffu, tk >= 0);
+      if (lane == 0) {
+        mbar_wait(&ms->q_empty[s][st], ((k >> 1) & 1) ^ 1);
+        mbar_expect_tx(&ms->q_full[s][st], __popc(have) * h * 128);
+      }
+      __syncwarp();
+      if (tk >= 0)  // one box (64 x h x 1 x 1) = the h head rows of one query, swizzled by the TMA unit
+        tma_load_4d(smem + S2Smem::q + (s * 2 + st) * kS2Tile + lane * h * 128, &tmQ, &ms->q_full[s][st], 0, 0, g, tk);
+      __syncwarp();
+    }
+  } else if (warp == 9) {
+    // ===== MMA issuer ======================================================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(128, 64, TcType<T>::fmt, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, TcType<T>::fmt, 0, 1);
+      const uint32_t kb = smem_u32(smem + S2Smem::kv), vb = kb + 8192;
+      auto issue_qk = [&](int s, int k) {  // k-th tile of slot s
+        const int st = k & 1;
+        mbar_wait(&ms->q_full[s][st], (k >> 1) & 1);
+        mbar_wait(&ms->s_empty[s], (k & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t qb = smem_u32(smem + S2Smem::q + (s * 2 + st) * kS2Tile);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_f16(tmem + s * 64, make_smem_desc(qb + kk * 32, 16, 1024, kSwizzle128B),
+                   make_smem_desc(kb + kk * 32, 16, 1024, kSwizzle128B), idesc_qk, kk > 0);
+        umma_commit(&ms->s_full[s]);
+        umma_commit(&ms->q_empty[s][st]);
+      };
+      auto issue_pv = [&](int s, int k) {
+        mbar_wait(&ms->p_full[s], k & 1);
+        mbar_wait(&ms->o_empty[s], (k & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t pb = smem_u32(smem + S2Smem::p + s * kS2Tile);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_f16(tmem + 128 + s * 64, make_smem_desc(pb + kk * 32, 16, 1024, kSwizzle128B),
+                   make_smem_desc(vb + kk * 2048, 8192, 1024, kSwizzle128B), idesc_pv, kk > 0);
+        umma_commit(&ms->o_full[s]);
+        umma_commit(&ms->p_empty[s]);
+      };
+      mbar_wait(&ms->kv_full, 0);
+      if (n0 > 0) issue_qk(0, 0);
+      if (n1 > 0) issue_qk(1, 0);
+      for (int k = 0; k < n0; ++k) {
+        issue_pv(0, k);
+        if (k + 1 < n0) issue_qk(0, k + 1);
+        if (k < n1) {
+          issue_pv(1, k);
+          if (k + 1 < n1) issue_qk(1, k + 1);
+        }
+      }
+    }
+  } else {
+    // ===== softmax warps: slot = warp / 4, thread = TMEM lane = row (query, head) ============================
+    const int s = warp >> 2;
+    const int r = tid & 127;
+    const int tok_l = r / h, head = r - tok_l * h;
+    const int ns = s == 0 ? n0 : n1;
+    const float c = dm.scale * kLog2e;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tm_S = tmem + lane_off + s * 64;
+    const uint32_t tm_O = tmem + lane_off + 128 + s * 64;
+    uint8_t* prow = smem + S2Smem::p + s * kS2Tile + r * 128;
+    const int sw = r & 7;
+    for (int k = 0; k < ns; ++k) {
+      const int i = 2 * k + s;
+      const int p = (run.tile0 + i) * TOK + tok_l;
+      const bool row_ok = tok_l < TOK && tok[p] >= 0;
+      // rows that are not stored see the whole tile, so they never push their warp onto the masked path
+      const int nk = row_ok ? hi[p] : 64;
+      mbar_wait(&ms->s_full[s], k & 1);
+      tc_fence_after();
+      uint32_t va[32], vb2[32];
+      tmem_ld32(tm_S, va);
+      tmem_ld32(tm_S + 32, vb2);
+      s2_ld_wait32(va);
+      s2_ld_wait32(vb2);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ms->s_empty[s]);
+      // exact softmax of the tile (64 keys): max, exponentials, sum
+      const bool full = __all_sync(0xffffffffu, nk >= 64);
+      float m = -INFINITY;
+      if (full) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) m = fmaxf(m, fmaxf(__uint_as_float(va[e]), __uint_as_float(vb2[e])));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          if (e < nk) m = fmaxf(m, __uint_as_float(va[e]));
+          if (32 + e < nk) m = fmaxf(m, __uint_as_float(vb2[e]));
+        }
+      }
+      const bool any = m > -INFINITY;
+      const float mc = any ? m * c : 0.f;
+      if (full) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          va[e] = __float_as_uint(s2_ex2(fmaf(__uint_as_float(va[e]), c, -mc)));
+          vb2[e] = __float_as_uint(s2_ex2(fmaf(__uint_as_float(vb2[e]), c, -mc)));
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          va[e] = (any && e < nk) ? __float_as_uint(s2_ex2(fmaf(__uint_as_float(va[e]), c, -mc))) : 0u;
+          vb2[e] = (any && 32 + e < nk) ? __float_as_uint(s2_ex2(fmaf(__uint_as_float(vb2[e]), c, -mc))) : 0u;
+        }
+      }
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        l0 += __uint_as_float(va[e]);
+        l1 += __uint_as_float(va[e + 1]);
+        l2 += __uint_as_float(vb2[e]);
+        l3 += __uint_as_float(vb2[e + 1]);
+      }
+      const float l = (l0 + l1) + (l2 + l3);
+      mbar_wait(&ms->p_empty[s], (k & 1) ^ 1);  // P.V of the slot's previous tile has read the P buffer
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {  // keys 0..31: chunks 0..3 ; keys 32..63: chunks 4..7 (16 B = 8 keys each)
+        uint4 u, w;
+        u.x = pack2(T(), __uint_as_float(va[q * 8 + 0]), __uint_as_float(va[q * 8 + 1]));
+        u.y = pack2(T(), __uint_as_float(va[q * 8 + 2]), __uint_as_float(va[q * 8 + 3]));
+        u.z = pack2(T(), __uint_as_float(va[q * 8 + 4]), __uint_as_float(va[q * 8 + 5]));
+        u.w = pack2(T(), __uint_as_float(va[q * 8 + 6]), __uint_as_float(va[q * 8 + 7]));
+        w.x = pack2(T(), __uint_as_float(vb2[q * 8 + 0]), __uint_as_float(vb2[q * 8 + 1]));
+        w.y = pack2(T(), __uint_as_float(vb2[q * 8 + 2]), __uint_as_float(vb2[q * 8 + 3]));
+        w.z = pack2(T(), __uint_as_float(vb2[q * 8 + 4]), __uint_as_float(vb2[q * 8 + 5]));
+        w.w = pack2(T(), __uint_as_float(vb2[q * 8 + 6]), __uint_as_float(vb2[q * 8 + 7]));
+        *reinterpret_cast<uint4*>(prow + ((q ^ sw) << 4)) = u;
+        *reinterpret_cast<uint4*>(prow + (((4 + q) ^ sw) << 4)) = w;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ms->p_full[s]);
+      // ---- partial output of this (query, block) pair ----
+      mbar_wait(&ms->o_full[s], k & 1);
+      tc_fence_after();
+      tmem_ld32(tm_O, va);
+      tmem_ld32(tm_O + 32, vb2);
+      s2_ld_wait32(va);
+      s2_ld_wait32(vb2);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ms->o_empty[s]);
+      if (row_ok) {
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+        uint4* dst = reinterpret_cast<uint4*>(O_p + ((size_t)p * h + head) * 64);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u, w;
+          u.x = pack2(T(), __uint_as_float(va[q * 8 + 0]) * inv, __uint_as_float(va[q * 8 + 1]) * inv);
+          u.y = pack2(T(), __uint_as_float(va[q * 8 + 2]) * inv, __uint_as_float(va[q * 8 + 3]) * inv);
+          u.z = pack2(T(), __uint_as_float(va[q * 8 + 4]) * inv, __uint_as_float(va[q * 8 + 5]) * inv);
+          u.w = pack2(T(), __uint_as_float(va[q * 8 + 6]) * inv, __uint_as_float(va[q * 8 + 7]) * inv);
+          w.x = pack2(T(), __uint_as_float(vb2[q * 8 + 0]) * inv, __uint_as_float(vb2[q * 8 + 1]) * inv);
+          w.y = pack2(T(), __uint_as_float(vb2[q * 8 + 2]) * inv, __uint_as_float(vb2[q * 8 + 3]) * inv);
+          w.z = pack2(T(), __uint_as_float(vb2[q * 8 + 4]) * inv, __uint_as_float(vb2[q * 8 + 5]) * inv);
+          w.w = pack2(T(), __uint_as_float(vb2[q * 8 + 6]) * inv, __uint_as_float(vb2[q * 8 + 7]) * inv);
+          dst[q] = u;
+          dst[4 + q] = w;
+        }
+        lse_p[(size_t)p * h + head] = l > 0.f ? m * dm.scale + logf(l) : -INFINITY;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 3. merge: one warp per (b, s, g) row.  O[row][head] = sum_k exp(lse_k - LSE) O_k, LSE = logsumexp_k lse_k; empty row ->
+//    zeros and lse = -inf (attention_kernels.py:769-771).  Slots are folded in slot order, so the result is deterministic.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+sel2_merge_kernel(int n_rows, int h, const int* __restrict__ pair_of, const T* __restrict__ O_p, const float* __restrict__ lse_p,
+                  T* __restrict__ O, float* __restrict__ lse) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks = h * 8;  // 16-byte chunks per row (h heads x 64 x 2 B)
+  for (int row = blockIdx.x * 8 + warp; row < n_rows; row += gridDim.x * 8) {
+    const int p_l = lane < kS2MaxSlots ? pair_of[(size_t)row * kS2MaxSlots + lane] : -1;
+    for (int cidx = lane; cidx < ((chunks + 31) & ~31); cidx += 32) {
+      const bool act = cidx < chunks;
+      const int head = act ? cidx >> 3 : 0;
+      float mx = -INFINITY;
+      float ls[kS2MaxSlots];
+#pragma unroll
+      for (int k = 0; k < kS2MaxSlots; ++k) {
+        const int p = __shfl_sync(0xffffffffu, p_l, k);
+        ls[k] = (p >= 0 && act) ? lse_p[(size_t)p * h + head] : -INFINITY;
+        mx = fmaxf(mx, ls[k]);
+      }
+      float acc[8], den = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+      for (int k = 0; k < kS2MaxSlots; ++k) {
+        const int p = __shfl_sync(0xffffffffu, p_l, k);
+        if (p >= 0 && act && ls[k] > -INFINITY) {
+          const float w = __expf(ls[k] - mx);
+          den += w;
+          const uint4 v = *reinterpret_cast<const uint4*>(O_p + (size_t)p * h * 64 + cidx * 8);
+          const T* pv = reinterpret_cast<const T*>(&v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, (float)pv[e], acc[e]);
+        }
+      }
+      if (act) {
+        const float inv = den > 0.f ? 1.0f / den : 0.f;
+        uint4 o;
+        T* po = reinterpret_cast<T*>(&o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) po[e] = T(acc[e] * inv);
+        *reinterpret_cast<uint4*>(O + (size_t)row * h * 64 + cidx * 8) = o;
+        if (lse && (cidx & 7) == 0) lse[(size_t)row * h + head] = den > 0.f ? mx + logf(den) : -INFINITY;
+      }
+    }
+  }
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------
+int make_tmap_q_heads(CUtensorMap* out, const void* base, int dtype, int D, int h, int G, long long n_tokens, int box_tokens);
+
+static S2Geom s2_geom(const nsa_dims_t& dm) {
+  S2Geom gm;
+  gm.B = dm.B; gm.S = dm.S; gm.G = dm.G; gm.n_ranges = dm.n_ranges; gm.S_kv = dm.S_sel_kv;
+  gm.NB = (dm.S_sel_kv + 63) / 64;
+  gm.t0 = dm.t0;
+  gm.tokp = 128 / dm.h > 32 ? 32 : 128 / dm.h;  // one producer lane per query
+  return gm;
+}
+
+// workspace carve-up (bytes, all 256-aligned)
+struct S2Ws {
+  size_t counts, offs, cursors, runs, n_runs, tok, hi, pair_of, lse_p, O_p, total;
+  int max_pairs, max_runs;
+};
+
+static S2Ws s2_ws(const nsa_dims_t& dm) {
+  const S2Geom gm = s2_geom(dm);
+  S2Ws w;
+  const long long rows = (long long)dm.B * dm.S * dm.G;
+  const long long nlists = (long long)dm.B * dm.G * gm.NB;
+  const long long max_tiles = (rows * kS2MaxSlots + gm.tokp - 1) / gm.tokp + nlists;  // every list padded by < one tile
+  w.max_pairs = (int)(max_tiles * gm.tokp);
+  w.max_runs = (int)(max_tiles / kS2Run + nlists + 1);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 255) & ~(size_t)255; return at; };
+  w.counts = take(nlists * 4);
+  w.offs = take((nlists + 1) * 4);
+  w.cursors = take(nlists * 4);
+  w.runs = take((size_t)w.max_runs * sizeof(S2Run));
+  w.n_runs = take(4);
+  w.tok = take((size_t)w.max_pairs * 4);
+  w.hi = take((size_t)w.max_pairs * 4);
+  w.pair_of = take((size_t)rows * kS2MaxSlots * 4);
+  w.lse_p = take((size_t)w.max_pairs * dm.h * 4);
+  w.O_p = take((size_t)w.max_pairs * dm.h * 64 * 2);
+  w.total = o;
+  return w;
+}
+
+bool tc_sel2_supported(const nsa_dims_t& dm) {
+  if (dm.impl == NSA_IMPL_SIMT) return false;
+  if (!((dm.dtype == NSA_BF16 || dm.dtype == NSA_F16) && dm.Dk == 64 && dm.Dv == 64 && dm.h >= 1 && dm.h <= 64)) return false;
+  if (dm.l_sel % 64 != 0 || (long long)dm.n_sel * dm.l_sel > 64 * kS2MaxSlots || dm.n_ranges < 1 || dm.S_sel_kv < 1) return false;
+  const long long rows = (long long)dm.B * dm.S * dm.G;
+  const long long nb = (dm.S_sel_kv + 63) / 64;
+  if (dm.S * dm.G < kS2IdxThreads) return false;            // an index CTA (256 rows) may touch at most two batches
+  if (2 * dm.G * nb * 2 * 4 > 200 * 1024) return false;     // shared-memory histograms of the index kernels
+  if (rows * kS2MaxSlots + (long long)dm.B * dm.G * nb * 64 >= (1LL << 31)) return false;
+  return true;
+}
+
+int64_t tc_sel2_workspace(const nsa_dims_t& dm) { return tc_sel2_supported(dm) ? (int64_t)s2_ws(dm).total : 0; }
+
+template <typename T>
+static int launch_sel2_t(const nsa_dims_t& dm, const void* Q, const void* K, const void* V, const int32_t* ranges, void* O,
+                         float* lse, void* workspace, cudaStream_t stream) {
+  const S2Geom gm = s2_geom(dm);
+  const S2Ws w = s2_ws(dm);
+  char* ws = reinterpret_cast<char*>(workspace);
+  int* counts = reinterpret_cast<int*>(ws + w.counts);
+  int* offs = reinterpret_cast<int*>(ws + w.offs);
+  int* cursors = reinterpret_cast<int*>(ws + w.cursors);
+  S2Run* runs = reinterpret_cast<S2Run*>(ws + w.runs);
+  int* n_runs = reinterpret_cast<int*>(ws + w.n_runs);
+  int* tok = reinterpret_cast<int*>(ws + w.tok);
+  int* hi = reinterpret_cast<int*>(ws + w.hi);
+  int* pair_of = reinterpret_cast<int*>(ws + w.pair_of);
+  float* lse_p = reinterpret_cast<float*>(ws + w.lse_p);
+  T* O_p = reinterpret_cast<T*>(ws + w.O_p);
+  const int n_rows = dm.B * dm.S * dm.G;
+  const int nlists = dm.B * dm.G * gm.NB;
+
+  cudaMemsetAsync(counts, 0, (size_t)nlists * 4, stream);
+  cudaMemsetAsync(tok, 0xff, (size_t)w.max_pairs * 4, stream);  // -1 = padding pair
+  const int idx_blocks = ceil_div(n_rows, kS2IdxThreads);
+  const size_t hist_bytes = (size_t)2 * gm.G * gm.NB * 4;
+  static bool idx_attr = false;
+  if (!idx_attr) {
+    cudaFuncSetAttribute(sel2_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(sel2_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    idx_attr = true;
+  }
+  sel2_count_kernel<<<idx_blocks, kS2IdxThreads, hist_bytes, stream>>>(gm, ranges, counts);
+  if (int rc = check_launch("sel2_count_kernel")) return rc;
+  sel2_scan_kernel<<<1, 1024, 0, stream>>>(gm, counts, offs, cursors, runs, n_runs);
+  if (int rc = check_launch("sel2_scan_kernel")) return rc;
+  sel2_fill_kernel<<<idx_blocks, kS2IdxThreads, 2 * hist_bytes, stream>>>(gm, ranges, offs, cursors, tok, hi, pair_of);
+  if (int rc = check_launch("sel2_fill_kernel")) return rc;
+
+  CUtensorMap tmQ, tmK, tmV;
+  const int slabs = dm.B * dm.G;
+  if (int rc = make_tmap_q_heads(&tmQ, Q, dm.dtype, 64, dm.h, dm.G, (long long)dm.B * dm.S, 1)) return rc;
+  if (int rc = make_tmap_rows(&tmK, K, dm.dtype, 64, dm.S_sel_kv, 64, (long long)dm.cap_sel * 64, slabs, 64)) return rc;
+  if (int rc = make_tmap_rows(&tmV, V, dm.dtype, 64, dm.S_sel_kv, 64, (long long)dm.cap_sel * 64, slabs, 64)) return rc;
+  auto kern = sel2_attn_kernel<T>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S2Smem::total);
+    if (e != cudaSuccess) { set_error("sel2: smem attr: %s", cudaGetErrorString(e)); return NSA_ERR_CUDA; }
+    attr_set = true;
+  }
+  kern<<<w.max_runs, 320, S2Smem::total, stream>>>(tmQ, tmK, tmV, dm, gm, runs, n_runs, tok, hi, O_p, lse_p);
+  if (int rc = check_launch("sel2_attn_kernel")) return rc;
+  int mblocks = ceil_div(n_rows, 8);
+  if (mblocks > 148 * 16) mblocks = 148 * 16;
+  sel2_merge_kernel<T><<<mblocks, 256, 0, stream>>>(n_rows, dm.h, pair_of, O_p, lse_p, (T*)O, lse);
+  return check_launch("sel2_merge_kernel");
+}
+
+int launch_sel2_tc(const nsa_dims_t& dm, const void* Q, const void* K, const void* V, const int32_t* ranges, void* O, float* lse,
+                   void* workspace, cudaStream_t stream) {
+  static_assert(sizeof(S2Misc) <= 512, "S2Misc must fit its slot");
+  if (dm.B * dm.S * dm.G == 0) return NSA_OK;
+  NSA_REQUIRE(workspace, "sel2: needs a workspace of nsa_workspace_bytes(NSA_WS_SEL) bytes");
+  if (dm.dtype == NSA_BF16) return launch_sel2_t<__nv_bfloat16>(dm, Q, K, V, ranges, O, lse, workspace, stream);
+  return launch_sel2_t<__half>(dm, Q, K, V, ranges, O, lse, workspace, stream);
+}
+
+}  // namespace nsa

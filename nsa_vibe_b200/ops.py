@@ -227,6 +227,23 @@ def branch_attention(branch: int, Q, K, V, cfg: NSAConfig, ranges=None, *, t0: i
     return (O, lse) if return_lse else O
 
 
+def sel_attention_blockmajor(Q, K, V, cfg: NSAConfig, ranges, *, t0: int = 0, return_lse: bool = False):
+    """Selected-branch attention, KV-block-major (forward only; nsa_sel_attn_fwd_blockmajor).  Same result as
+    branch_attention(BR_SEL, ...)."""
+    _require_cuda(Q, K, V, ranges)
+    Qc, Kc, Vc = _c(Q.detach()), _c(K.detach()), _c(V.detach())
+    rg = _c(ranges.to(torch.int32))
+    dm = _branch_dims(BR_SEL, Qc, Kc, Vc, cfg, rg, t0, 0)
+    B, S, G, h, _ = Qc.shape
+    O = torch.empty((B, S, G, h, Vc.shape[-1]), dtype=Qc.dtype, device=Qc.device)
+    lse = torch.empty((B, S, G, h), dtype=torch.float32, device=Qc.device)
+    ws_bytes = int(_lib.load().nsa_workspace_bytes(C.byref(dm), _lib.WS_SEL_BLOCKMAJOR))
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=Qc.device)
+    if O.numel():
+        _call("nsa_sel_attn_fwd_blockmajor", C.byref(dm), _ptr(Qc), _ptr(Kc), _ptr(Vc), _ptr(rg), _ptr(O), _ptr(lse), _ptr(ws), _stream())
+    return (O, lse) if return_lse else O
+
+
 # ----------------------------------------------------------------------------------------------------
 # (4) gate
 # ----------------------------------------------------------------------------------------------------
@@ -271,10 +288,8 @@ class _PrefillCore(torch.autograd.Function):
         gates = torch.empty((B, S, G, 3), dtype=torch.float32, device=dev)
         lse = torch.empty((3, B, S, G, h), dtype=torch.float32, device=dev) if need_grad else None
         O_br = torch.empty((3, B, S, G, h, Dv), dtype=Q.dtype, device=dev) if need_grad else None
-        ws = None
-        if O_br is None:
-            ws_bytes = int(_lib.load().nsa_workspace_bytes(C.byref(dm), _lib.WS_PREFILL))
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+        ws_bytes = int(_lib.load().nsa_workspace_bytes(C.byref(dm), _lib.WS_PREFILL))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
         if O.numel():
             _call("nsa_prefill_fwd", C.byref(dm), _ptr(Q), _ptr(K_sel), _ptr(V_sel), _ptr(K_win), _ptr(V_win), _ptr(K_cmp),
                   _ptr(V_cmp), _ptr(ranges), C.byref(gp), _ptr(O), _ptr(lse), _ptr(gates), _ptr(O_br), _ptr(ws), _stream())

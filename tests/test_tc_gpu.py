@@ -249,3 +249,31 @@ def test_dense_tc_reference_jump():
     want, lse_w = O.cmp_attention(ts[0], ts[5], ts[6], l, d)
     assert torch.isfinite(o.float()).all()
     assert (o.float().cpu() - want).abs().max() <= 3e-2, (o.float().cpu() - want).abs().max()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("sel_mode,S,h,B", [(0, 700, 6, 2), (1, 700, 6, 1), (0, 1500, 4, 2), (1, 333, 8, 1), (0, 2100, 6, 1),
+                                             (0, 200, 16, 3), (1, 130, 1, 2)])
+def test_sel_blockmajor_vs_gather_vs_oracle(dtype, sel_mode, S, h, B):
+    """KV-block-major selected branch (index build -> tcgen05 per-block attention -> merge of partials) against the fp32
+    oracle and the query-major gather kernel.  Tolerance: max-abs 2e-2 / MAE 1e-3 (partials are stored in 16 bits)."""
+    ops = _ops()
+    G, l, d, ls, n, w = 2, 32, 16, 64, 16, 512
+    ts = _case(B, S, G, h, l, d, ls, n, w, seed=3 * S + h, dtype=dtype)
+    cfg = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w, impl=ops.IMPL_TC)
+    Q, K, V = (t.cuda().to(dtype) for t in ts[:3])
+    ranges = ops.score_select(Q, ts[5].cuda().to(dtype), cfg, mode=sel_mode)
+    o_bm, lse_bm = ops.sel_attention_blockmajor(Q, K, V, cfg, ranges, return_lse=True)
+    cfg_auto = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w)  # gather kernel where it exists (h <= 8), else SIMT
+    o_g, lse_g = ops.branch_attention(ops.BR_SEL, Q, K, V, cfg_auto, ranges, return_lse=True)
+    want, lse_w = O.sel_attention(ts[0], ts[1], ts[2], ranges.cpu())
+    assert torch.isfinite(o_bm.float()).all()
+    err = (o_bm.float().cpu() - want).abs()
+    assert err.max() <= 2e-2 and err.mean() <= 1e-3, (err.max(), err.mean())
+    assert (o_bm.float() - o_g.float()).abs().max() <= 2e-2
+    fin = torch.isfinite(lse_w)
+    assert torch.equal(torch.isfinite(lse_bm.cpu()), fin)
+    assert (lse_bm.cpu()[fin] - lse_w[fin]).abs().max() <= 2e-2
+    empty = ~fin.any(dim=-1)
+    if empty.any():
+        assert torch.all(o_bm.float().cpu()[empty] == 0)

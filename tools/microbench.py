@@ -54,6 +54,9 @@ def main():
                     c2 = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w, impl=impl)
                     ms = timeit(lambda: ops.branch_attention(br, Q, K, V, c2, ranges if br == 1 else None), n=3, warm=1)
                     print(f"branch {name} ({nm:4s})     : {ms:9.3f} ms")
+        if "sel2" in what:
+            ms = timeit(lambda: ops.sel_attention_blockmajor(Q, Ks, Vs, cfg, ranges), n=3, warm=1)
+            print(f"branch sel block-major: {ms:9.3f} ms")
         if "decode" in what:
             Sd, Bd = 4096, a.decode_B
             cap = Sd + 64
