@@ -277,3 +277,23 @@ def test_sel_blockmajor_vs_gather_vs_oracle(dtype, sel_mode, S, h, B):
     empty = ~fin.any(dim=-1)
     if empty.any():
         assert torch.all(o_bm.float().cpu()[empty] == 0)
+
+
+def test_prefill_core_long_uses_blockmajor_sel():
+    """B*S*G >= 16384 and S >= 4096: nsa_prefill_fwd routes the selected branch through the block-major kernels."""
+    ops = _ops()
+    B, S, G, h, l, d, ls, n, w = 2, 4096, 2, 6, 32, 16, 64, 16, 512
+    ts = _case(B, S, G, h, l, d, ls, n, w, seed=13, dtype=torch.bfloat16)
+    gen = torch.Generator().manual_seed(5)
+    gate = (torch.randn(32, 64, generator=gen) * 0.3, torch.randn(32, generator=gen) * 0.1, torch.randn(3, 32, generator=gen) * 0.5,
+            torch.zeros(3))
+    cfg = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w)
+    dev = [t.cuda().bfloat16() for t in ts]
+    Oc, ranges, gates = ops.prefill_core(*dev, tuple(x.cuda() for x in gate), cfg, sel_mode=0)
+    # the selected branch alone, both kernels, same ranges
+    o_bm = ops.sel_attention_blockmajor(dev[0], dev[1], dev[2], cfg, ranges)
+    o_g = ops.branch_attention(ops.BR_SEL, dev[0], dev[1], dev[2], cfg, ranges)
+    assert (o_bm.float() - o_g.float()).abs().max() <= 2e-2
+    want = O.prefill_core(*ts, gate, l=l, d=d, l_sel=ls, n_sel=n, w=w, ranges=ranges.cpu())
+    err = (Oc.float().cpu() - want["O"]).abs()
+    assert err.max() <= 2e-2 and err.mean() <= 1e-3, (err.max(), err.mean())
