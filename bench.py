@@ -98,7 +98,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -215,7 +215,7 @@ def make_inputs(B, S, dev, seed):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--S", type=int, default=65536)
@@ -328,10 +328,16 @@ def main():
             return a_.elapsed_time(b_) / n
         pg = ops.score_pgrp(inp["Q"], inp["K_cmp"], cfg)
         rg_ = ops.select_ranges_prefill(pg, c["l_sel"], c["n_sel"], S)
+        # which selected-branch kernel does nsa_prefill_fwd use for this shape?  (its workspace then includes the index + partials)
+        import ctypes as _C
+        dm_ = ops.make_dims(inp["Q"], cfg, K_sel=inp["K_sel"], K_win=inp["K_win"], K_cmp=inp["K_cmp"], V=inp["V_sel"], n_ranges=rg_.shape[3], gate_hidden=c["Dk"] // 2)
+        staging_ = (3 * inp["Q"].numel() * 2 + 255) // 256 * 256
+        sel_blockmajor = int(lib.nsa_workspace_bytes(_C.byref(dm_), _lib.WS_PREFILL)) > staging_
         kms = {"score": t_of(lambda: ops.score_pgrp(inp["Q"], inp["K_cmp"], cfg)),
                "select": t_of(lambda: ops.select_ranges_prefill(pg, c["l_sel"], c["n_sel"], S)),
                "cmp": t_of(lambda: ops.branch_attention(ops.BR_CMP, inp["Q"], inp["K_cmp"], inp["V_cmp"], cfg)),
-               "sel": t_of(lambda: ops.branch_attention(ops.BR_SEL, inp["Q"], inp["K_sel"], inp["V_sel"], cfg, rg_)),
+               "sel": t_of((lambda: ops.sel_attention_blockmajor(inp["Q"], inp["K_sel"], inp["V_sel"], cfg, rg_)) if sel_blockmajor else
+                           (lambda: ops.branch_attention(ops.BR_SEL, inp["Q"], inp["K_sel"], inp["V_sel"], cfg, rg_))),
                "win": t_of(lambda: ops.branch_attention(ops.BR_WIN, inp["Q"], inp["K_win"], inp["V_win"], cfg))}
         kms["gate_combine_and_rest"] = max(0.0, ms_step - sum(kms.values()))
         del pg, rg_
@@ -355,7 +361,8 @@ def main():
         ("select_kernel", kms["select"], "hbm", B * S * c["G"] * (4.0 * num_sel_blocks(S, c["l_sel"]) + 8.0 * c["n_sel"]),
          "4*S_sel B read + 8*n_sel B written per (b,t,g) row"),
         ("dense_attn_tc_kernel[cmp]", kms["cmp"], "tensor", B * fl["cmp_pv"], "2*H*Dv*sum_t num_cmp(t) (P.V; its QK^T is counted under scoring)"),
-        ("gather_attn_tc_kernel[sel]", kms["sel"], "hbm", B * fl["sel_gather_bytes"], "2 B*G*(Dk+Dv)*sum_t min(t+1, n_sel*l_sel) gathered K/V bytes"),
+        ("sel2_attn_kernel+index+merge[sel, KV-block-major]" if sel_blockmajor else "gather_attn_tc_kernel[sel]", kms["sel"], "hbm",
+         B * fl["sel_gather_bytes"], "2 B*G*(Dk+Dv)*sum_t min(t+1, n_sel*l_sel) K/V bytes a query-major gather moves (the reference's own GB/s definition, triton_sel_kernel/__init__.py:483-509); the block-major kernels read each block once per run of queries, so >1 of HBM peak is expected"),
         ("dense_attn_tc_kernel[win]", kms["win"], "tensor", B * fl["win"], "2*H*(Dk+Dv)*sum_t min(t+1, w)"),
     ]
     kname, k_ms, bound, work, how = max(cand, key=lambda x: x[1])
@@ -365,6 +372,8 @@ def main():
         achieved, peak, unit, src = work / (k_ms * 1e-3) / 1e9, pk["hbm"], "GB/s", pk["src"] + " (HBM copy)"
     roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
                 "traffic": traffic.get(kname), "kernel": kname, "kernel_ms": k_ms, "algorithmic_work": how, "peak_source": src,
+                "exp_bound": {"what": "MUFU ex2 throughput also bounds the scorer: 2 passes x S*S_cmp*H exponentials", "ex2_per_s": 2.0 * B * S * ((S - c["l"]) // c["d"] + 1) * c["H"] / (kms["score"] * 1e-3),
+                              "peak_ex2_per_s": 16 * 148 * 1.965e9, "peak_source": "tools/ubench/mufu.cu on this pool: 15.9 ex2/clk/SM", "frac": 2.0 * B * S * ((S - c["l"]) // c["d"] + 1) * c["H"] / (kms["score"] * 1e-3) / (16 * 148 * 1.965e9)},
                 "step_tflops": B * fl["total"] / (ms_step * 1e-3) / 1e12,
                 "step_frac_of_tensor_peak": B * fl["total"] / (ms_step * 1e-3) / 1e12 / pk["tf_sustained"],
                 "kernel_ms_breakdown": kms, "ms_score_select": ms_score, "ms_prefill_fwd": ms_attn,
