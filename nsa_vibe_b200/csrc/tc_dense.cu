@@ -17,24 +17,29 @@
 namespace nsa {
 using namespace tc;
 
-constexpr int kDnMT = 2;
 constexpr int kDnKS = 3;             // K ring stages
 constexpr int kDnVS = 3;             // V ring stages
 constexpr int kDnTile = 128 * 128;   // bytes: 128 rows x 64 x 2 B
+constexpr int kDnMaxMT = 4;
 
+// Two shapes of the same kernel: (MT, NK) = (4, 64) -- 4 M-tiles x 64-key tiles, 16 softmax warps, TMEM exactly full
+// (4 x 64 S columns + 4 x 64 O columns) -- is the default; (2, 128) is kept for comparison (NSA_B200_DENSE_MT=2).
+template <int MT, int NK>
 struct DnSmem {
+  static constexpr int kvtile = NK * 128;                   // bytes of one K or V tile
+  static constexpr int ptile = 128 * NK * 2;                // bytes of one P tile: [NK/64 key halves][128 rows][128 B]
   static constexpr int q = 0;                               // MT x 16 KB
-  static constexpr int k = q + kDnMT * kDnTile;
-  static constexpr int v = k + kDnKS * kDnTile;
-  static constexpr int p = v + kDnVS * kDnTile;             // MT x 32 KB: [2 key halves][128 rows][128 B]
-  static constexpr int misc = p + kDnMT * 2 * kDnTile;
+  static constexpr int k = q + MT * kDnTile;
+  static constexpr int v = k + kDnKS * kvtile;
+  static constexpr int p = v + kDnVS * kvtile;
+  static constexpr int misc = p + MT * ptile;
   static constexpr int total = misc + 512 + 1024;
 };
 
 struct DnMisc {
   uint64_t q_full;
   uint64_t k_full[kDnKS], k_empty[kDnKS], v_full[kDnVS], v_empty[kDnVS];
-  uint64_t s_full[kDnMT], s_empty[kDnMT], p_full[kDnMT], p_empty[kDnMT];
+  uint64_t s_full[kDnMaxMT], s_empty[kDnMaxMT], p_full[kDnMaxMT], p_empty[kDnMaxMT];
   uint32_t tmem_base;
 };
 
@@ -89,20 +94,20 @@ __device__ __forceinline__ void dn_row_range(const nsa_dims_t& dm, int branch, i
 #define DDBG(tag, it) do { } while (0)
 #endif
 
-template <typename T>
-__global__ void __launch_bounds__(32 * (4 * kDnMT + 2), 1)
+template <typename T, int MT, int NK>
+__global__ void __launch_bounds__(32 * (4 * MT + 2), 1)
 dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, nsa_dims_t dm, int branch, T* __restrict__ O,
                      float* __restrict__ lse, int TOK, long long* dbg) {
-  constexpr int MT = kDnMT;
+  using SM = DnSmem<MT, NK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  DnMisc* ms = reinterpret_cast<DnMisc*>(smem + DnSmem::misc);
+  DnMisc* ms = reinterpret_cast<DnMisc*>(smem + SM::misc);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int kSoftWarps = 4 * MT;
 
   const int tiles_per_seq = ceil_div(dm.S, MT * TOK);
-  const int tile = blockIdx.x % tiles_per_seq;
+  const int tile = tiles_per_seq - 1 - blockIdx.x % tiles_per_seq;  // longest (latest, causal) query tiles first
   const int bg = blockIdx.x / tiles_per_seq;
   const int g = bg % dm.G, b = bg / dm.G;
   const int s_base = tile * MT * TOK;
@@ -112,13 +117,13 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   int lo_first, hi_first, lo_last, hi_last;
   dn_row_range(dm, branch, dm.t0 + s_base, lo_first, hi_first);
   dn_row_range(dm, branch, dm.t0 + s_last, lo_last, hi_last);
-  const int kt_lo = lo_first >> 7;
-  const int n = hi_last > lo_first ? ceil_div(hi_last, 128) - kt_lo : 0;
+  const int kt_lo = lo_first / NK;
+  const int n = hi_last > lo_first ? ceil_div(hi_last, NK) - kt_lo : 0;
 
   // ---- setup ---------------------------------------------------------------------------------------------
   {
     uint4 z = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < MT * kDnTile / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem + DnSmem::q)[i] = z;
+    for (int i = tid; i < MT * kDnTile / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem + SM::q)[i] = z;
   }
   if (tid == 0) {
     mbar_init(&ms->q_full, 1);
@@ -141,35 +146,35 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = ms->tmem_base;
-  // TMEM columns: S[mt] at mt*128 ; O[mt] (accumulated over all key tiles) at 256 + mt*64
+  // TMEM columns: S[mt] at mt*NK ; O[mt] (accumulated over all key tiles) at MT*NK + mt*64
 
   if (warp == kSoftWarps) {
     // ===== TMA producer ====================================================================================
     if (lane == 0 && n > 0) {
       mbar_expect_tx(&ms->q_full, MT * TOK * dm.h * 128);
       for (int m = 0; m < MT; ++m)
-        tma_load_4d(smem + DnSmem::q + m * kDnTile, &tmQ, &ms->q_full, 0, 0, g, b * dm.S + s_base + m * TOK);
+        tma_load_4d(smem + SM::q + m * kDnTile, &tmQ, &ms->q_full, 0, 0, g, b * dm.S + s_base + m * TOK);
       for (int i = 0; i < n; ++i) {
         const int ks = i % kDnKS, vs = i % kDnVS;
         mbar_wait(&ms->k_empty[ks], ((i / kDnKS) & 1) ^ 1);
-        mbar_expect_tx(&ms->k_full[ks], kDnTile);
-        tma_load_3d(smem + DnSmem::k + ks * kDnTile, &tmK, &ms->k_full[ks], 0, (kt_lo + i) * 128, bg);
+        mbar_expect_tx(&ms->k_full[ks], SM::kvtile);
+        tma_load_3d(smem + SM::k + ks * SM::kvtile, &tmK, &ms->k_full[ks], 0, (kt_lo + i) * NK, bg);
         mbar_wait(&ms->v_empty[vs], ((i / kDnVS) & 1) ^ 1);
-        mbar_expect_tx(&ms->v_full[vs], kDnTile);
-        tma_load_3d(smem + DnSmem::v + vs * kDnTile, &tmV, &ms->v_full[vs], 0, (kt_lo + i) * 128, bg);
+        mbar_expect_tx(&ms->v_full[vs], SM::kvtile);
+        tma_load_3d(smem + SM::v + vs * SM::kvtile, &tmV, &ms->v_full[vs], 0, (kt_lo + i) * NK, bg);
       }
     }
   } else if (warp == kSoftWarps + 1) {
     // ===== MMA issuer ======================================================================================
     if (lane == 0 && n > 0) {
-      constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, TcType<T>::fmt, 0, 0);
+      constexpr uint32_t idesc_qk = make_idesc_f16(128, NK, TcType<T>::fmt, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, TcType<T>::fmt, 0, 1);
       auto issue_qk = [&](int m, int i) {
-        const uint32_t qb = smem_u32(smem + DnSmem::q + m * kDnTile);
-        const uint32_t kb = smem_u32(smem + DnSmem::k + (i % kDnKS) * kDnTile);
+        const uint32_t qb = smem_u32(smem + SM::q + m * kDnTile);
+        const uint32_t kb = smem_u32(smem + SM::k + (i % kDnKS) * SM::kvtile);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16(tmem + m * 128, make_smem_desc(qb + k * 32, 16, 1024, kSwizzle128B),
+          umma_f16(tmem + m * NK, make_smem_desc(qb + k * 32, 16, 1024, kSwizzle128B),
                    make_smem_desc(kb + k * 32, 16, 1024, kSwizzle128B), idesc_qk, k > 0);
         umma_commit(&ms->s_full[m]);
       };
@@ -182,16 +187,16 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int vs = i % kDnVS;
         mbar_wait(&ms->v_full[vs], (i / kDnVS) & 1);
         if (i + 1 < n) mbar_wait(&ms->k_full[(i + 1) % kDnKS], ((i + 1) / kDnKS) & 1);
-        const uint32_t vb = smem_u32(smem + DnSmem::v + vs * kDnTile);
+        const uint32_t vb = smem_u32(smem + SM::v + vs * SM::kvtile);
         for (int m = 0; m < MT; ++m) {
           DDBG(10 + m, i);
           mbar_wait(&ms->p_full[m], i & 1);
           DDBG(12 + m, i);
           tc_fence_after();
-          const uint32_t pb = smem_u32(smem + DnSmem::p + m * 2 * kDnTile);
-          const uint32_t od = tmem + 256 + m * 64;
+          const uint32_t pb = smem_u32(smem + SM::p + m * SM::ptile);
+          const uint32_t od = tmem + MT * NK + m * 64;
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
+          for (int k = 0; k < NK / 16; ++k)
             umma_f16(od, make_smem_desc(pb + (k >> 2) * kDnTile + (k & 3) * 32, 16, 1024, kSwizzle128B),
                      make_smem_desc(vb + k * 2048, 8192, 1024, kSwizzle128B), idesc_pv, (i > 0 || k > 0) ? 1u : 0u);
           umma_commit(&ms->p_empty[m]);
@@ -218,9 +223,9 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (row_ok) dn_row_range(dm, branch, dm.t0 + s, lo, hi);
     const float c = dm.scale * kLog2e;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tm_S = tmem + lane_off + mt * 128;
-    const uint32_t tm_O = tmem + lane_off + 256 + mt * 64;
-    uint8_t* prow = smem + DnSmem::p + mt * 2 * kDnTile + r * 128;
+    const uint32_t tm_S = tmem + lane_off + mt * NK;
+    const uint32_t tm_O = tmem + lane_off + MT * NK + mt * 64;
+    uint8_t* prow = smem + SM::p + mt * SM::ptile + r * 128;
     const int sw = r & 7;
 
     float m_run = -INFINITY, l_run = 0.f;
@@ -232,19 +237,19 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // for a tile maximum.  Exact: P, l and acc always share one reference per row.
     constexpr float kJump = 24.f;
     for (int i = 0; i < n; ++i) {
-      const int col_base = (kt_lo + i) * 128;
+      const int col_base = (kt_lo + i) * NK;
       if (tid == 0) DDBG(1, i);
       mbar_wait(&ms->s_full[mt], i & 1);
       if (tid == 0) DDBG(2, i);
       tc_fence_after();
       // one path per warp: the masked path also handles full rows, so a warp takes it as a whole or not at all
-      const bool full_tile = __all_sync(0xffffffffu, col_base >= lo && col_base + 128 <= hi);
+      const bool full_tile = __all_sync(0xffffffffu, col_base >= lo && col_base + NK <= hi);
       // tcgen05.ld is warp-collective: every decision that guards one is made warp-uniform with a ballot
       if (__ballot_sync(0xffffffffu, !(m_run > -INFINITY)) != 0u) {  // a row without a reference: take this tile's maximum
         float cm = -INFINITY;
         uint32_t ua[16];
 #pragma unroll 1
-        for (int ch = 0; ch < 8; ++ch) {
+        for (int ch = 0; ch < NK / 16; ++ch) {
           tmem_ld16(tm_S + ch * 16, ua);
           dn_ld_wait16(ua);
 #pragma unroll
@@ -269,11 +274,11 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         uint32_t ua[16], ub[16];
         tmem_ld16(tm_S, ua);
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
+        for (int ch = 0; ch < NK / 16; ++ch) {
           uint32_t(&cur)[16] = (ch & 1) ? ub : ua;
           uint32_t(&nxt)[16] = (ch & 1) ? ua : ub;
           dn_ld_wait16(cur);
-          if (ch < 7) tmem_ld16(tm_S + (ch + 1) * 16, nxt);
+          if (ch < NK / 16 - 1) tmem_ld16(tm_S + (ch + 1) * 16, nxt);
           if (full_tile) {
 #pragma unroll
             for (int e = 0; e < 16; e += 2) cm = fmaxf(cm, fmaxf(__uint_as_float(cur[e]), __uint_as_float(cur[e + 1])));
@@ -345,36 +350,36 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
 
     // ---- epilogue: O (TMEM, all key tiles accumulated) / l -> global ------------------------------------------
-    float acc[64];
     if (n > 0) {
       mbar_wait(&ms->p_empty[mt], (n - 1) & 1);  // the last P.V has completed
       tc_fence_after();
-      uint32_t oa[32], ob[32];
-      tmem_ld32(tm_O, oa);
-      tmem_ld32(tm_O + 32, ob);
-      dn_ld_wait32(oa);
-      dn_ld_wait32(ob);
-#pragma unroll
-      for (int e = 0; e < 32; ++e) { acc[e] = __uint_as_float(oa[e]); acc[32 + e] = __uint_as_float(ob[e]); }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 64; ++e) acc[e] = 0.f;
     }
-    if (row_ok) {
-      const size_t orow = (((size_t)b * dm.S + s) * dm.G + g) * dm.h + head;
-      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;  // empty row -> zeros
-      uint4* dst = reinterpret_cast<uint4*>(O + orow * 64);
+    const size_t orow = (((size_t)b * dm.S + s) * dm.G + g) * dm.h + head;
+    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;  // empty row -> zeros
+#pragma unroll 1
+    for (int hf = 0; hf < 2; ++hf) {
+      uint32_t oa[32];
+      if (n > 0) {  // CTA-uniform
+        tmem_ld32(tm_O + hf * 32, oa);
+        dn_ld_wait32(oa);
+      } else {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        uint4 v;
-        v.x = pack2(T(), acc[q * 8 + 0] * inv, acc[q * 8 + 1] * inv);
-        v.y = pack2(T(), acc[q * 8 + 2] * inv, acc[q * 8 + 3] * inv);
-        v.z = pack2(T(), acc[q * 8 + 4] * inv, acc[q * 8 + 5] * inv);
-        v.w = pack2(T(), acc[q * 8 + 6] * inv, acc[q * 8 + 7] * inv);
-        dst[q] = v;
+        for (int e = 0; e < 32; ++e) oa[e] = 0u;
       }
-      if (lse) lse[orow] = l_run > 0.f ? m_run * dm.scale + logf(l_run) : -INFINITY;
+      if (row_ok) {
+        uint4* dst = reinterpret_cast<uint4*>(O + orow * 64 + hf * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 v;
+          v.x = pack2(T(), __uint_as_float(oa[q * 8 + 0]) * inv, __uint_as_float(oa[q * 8 + 1]) * inv);
+          v.y = pack2(T(), __uint_as_float(oa[q * 8 + 2]) * inv, __uint_as_float(oa[q * 8 + 3]) * inv);
+          v.z = pack2(T(), __uint_as_float(oa[q * 8 + 4]) * inv, __uint_as_float(oa[q * 8 + 5]) * inv);
+          v.w = pack2(T(), __uint_as_float(oa[q * 8 + 6]) * inv, __uint_as_float(oa[q * 8 + 7]) * inv);
+          dst[q] = v;
+        }
+      }
     }
+    if (row_ok && lse) lse[orow] = l_run > 0.f ? m_run * dm.scale + logf(l_run) : -INFINITY;
   }
 
   tc_fence_before();
@@ -394,32 +399,33 @@ bool tc_dense_supported(const nsa_dims_t& dm, int branch) {
   return false;
 }
 
-template <typename T>
+template <typename T, int MT, int NK>
 static int launch_dense_t(const nsa_dims_t& dm, int branch, const void* Q, const void* K, const void* V, void* O, float* lse,
                           cudaStream_t stream) {
+  using SM = DnSmem<MT, NK>;
   const int TOK = 128 / dm.h;
   CUtensorMap tmQ, tmK, tmV;
   const int rows = branch == 0 ? dm.S_cmp : dm.S_win_kv;
   const long long cap = branch == 0 ? dm.cap_cmp : dm.cap_win;
   if (int rc = make_tmap_q_heads(&tmQ, Q, dm.dtype, 64, dm.h, dm.G, (long long)dm.B * dm.S, TOK)) return rc;
-  if (int rc = make_tmap_rows(&tmK, K, dm.dtype, 64, rows, 64, cap * 64, dm.B * dm.G, 128)) return rc;
-  if (int rc = make_tmap_rows(&tmV, V, dm.dtype, 64, rows, 64, cap * 64, dm.B * dm.G, 128)) return rc;
-  auto kern = dense_attn_tc_kernel<T>;
+  if (int rc = make_tmap_rows(&tmK, K, dm.dtype, 64, rows, 64, cap * 64, dm.B * dm.G, NK)) return rc;
+  if (int rc = make_tmap_rows(&tmV, V, dm.dtype, 64, rows, 64, cap * 64, dm.B * dm.G, NK)) return rc;
+  auto kern = dense_attn_tc_kernel<T, MT, NK>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DnSmem::total);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::total);
     if (e != cudaSuccess) { set_error("dense tc: smem attr: %s", cudaGetErrorString(e)); return NSA_ERR_CUDA; }
     attr_set = true;
   }
-  const int grid = dm.B * dm.G * ceil_div(dm.S, kDnMT * TOK);
+  const int grid = dm.B * dm.G * ceil_div(dm.S, MT * TOK);
   static const bool dbg_on = getenv("NSA_B200_DENSE_DBG") != nullptr;
   static long long* dbg_buf = nullptr;
   if (dbg_on) {
     if (!dbg_buf) cudaMalloc(&dbg_buf, 8008 * sizeof(long long));
     cudaMemsetAsync(dbg_buf, 0, 8008 * sizeof(long long), stream);
   }
-  kern<<<grid, 32 * (4 * kDnMT + 2), DnSmem::total, stream>>>(tmQ, tmK, tmV, dm, branch, (T*)O, lse, TOK, dbg_on ? dbg_buf : nullptr);
-  if (dbg_on) {  // debug only: timeline of the middle CTA (tag, tile, clock)
+  kern<<<grid, 32 * (4 * MT + 2), SM::total, stream>>>(tmQ, tmK, tmV, dm, branch, (T*)O, lse, TOK, dbg_on ? dbg_buf : nullptr);
+  if (dbg_on) {  // debug only: timeline of one CTA (tag, tile, clock)
     static int dumps = 0;
     cudaStreamSynchronize(stream);
     if (dumps++ == 2) {
@@ -433,12 +439,22 @@ static int launch_dense_t(const nsa_dims_t& dm, int branch, const void* Q, const
   return check_launch("dense_attn_tc_kernel");
 }
 
+template <typename T>
+static int launch_dense_mt(const nsa_dims_t& dm, int branch, const void* Q, const void* K, const void* V, void* O, float* lse,
+                           cudaStream_t stream) {
+  static const int mt_env = getenv("NSA_B200_DENSE_MT") ? atoi(getenv("NSA_B200_DENSE_MT")) : 0;
+  // 4 M-tiles per CTA once there are enough rows to fill the machine with 84-token CTAs
+  const bool big = mt_env == 4 || (mt_env != 2 && (long long)dm.B * dm.G * dm.S >= 4LL * (128 / dm.h) * 148);
+  if (big) return launch_dense_t<T, 4, 64>(dm, branch, Q, K, V, O, lse, stream);
+  return launch_dense_t<T, 2, 128>(dm, branch, Q, K, V, O, lse, stream);
+}
+
 int launch_dense_tc(const nsa_dims_t& dm, int branch, const void* Q, const void* K, const void* V, void* O, float* lse,
                     cudaStream_t stream) {
   static_assert(sizeof(DnMisc) <= 512, "DnMisc must fit its slot");
   if (dm.B * dm.S * dm.G == 0) return NSA_OK;
-  if (dm.dtype == NSA_BF16) return launch_dense_t<__nv_bfloat16>(dm, branch, Q, K, V, O, lse, stream);
-  return launch_dense_t<__half>(dm, branch, Q, K, V, O, lse, stream);
+  if (dm.dtype == NSA_BF16) return launch_dense_mt<__nv_bfloat16>(dm, branch, Q, K, V, O, lse, stream);
+  return launch_dense_mt<__half>(dm, branch, Q, K, V, O, lse, stream);
 }
 
 }  // namespace nsa

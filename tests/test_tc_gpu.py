@@ -118,7 +118,8 @@ def _check_branch(o, lse, want, lse_w):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("S,h,w", [(700, 6, 512), (1500, 4, 512), (333, 8, 64), (40, 1, 512), (2100, 6, 300), (130, 16, 1)])
+@pytest.mark.parametrize("S,h,w", [(700, 6, 512), (1500, 4, 512), (333, 8, 64), (40, 1, 512), (2100, 6, 300), (130, 16, 1),
+                                   (3300, 6, 512), (3201, 4, 100)])  # the last two: >= 4*TOK*148 rows -> 4 M-tiles x 64-key tiles
 def test_dense_branches_tc_vs_oracle(dtype, S, h, w):
     """tcgen05 dense ranged attention (cmp and win branches) against the fp32 oracle on the same 16-bit inputs.
     Tolerance: max-abs 2e-2, MAE 1e-3 (bf16 P and O rounding)."""
