@@ -174,7 +174,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     per_step = []
-    rows = args.cpu_rows
+    rows = max(32, args.cpu_rows // 2)  # ~1.5 s per step on 16 cores: a 40-step run ends within a minute
     for i in range(args.warmup + args.steps):
         v, cores, sample = cpu_prefill_sample(args.S, rows, seed=i, budget_s=0.0)
         if i >= args.warmup:
@@ -222,7 +222,7 @@ def main():
     ap.add_argument("--B", type=int, default=1, help="sequences per GPU in the prefill step")
     ap.add_argument("--decode-S", type=int, default=4096)
     ap.add_argument("--decode-B", type=int, default=592, help="sequences per GPU in the decode step (592 x G=2 = 4 (b,g) rows per resident CTA: 2 CTAs x 148 SMs)")
-    ap.add_argument("--cpu-rows", type=int, default=64)
+    ap.add_argument("--cpu-rows", type=int, default=512, help="query rows of the CPU sample (cpu_baseline leg; --impl reference uses half)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-decode", action="store_true")
     args = ap.parse_args()
