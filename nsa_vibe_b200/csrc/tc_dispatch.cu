@@ -80,7 +80,6 @@ int make_tmap_q_heads(CUtensorMap* out, const void* base, int dtype, int D, int 
 }
 
 // ---- capability checks ---------------------------------------------------------------------------------------
-bool tc_sel_supported(const nsa_dims_t& dm);
 bool tc_dense_supported(const nsa_dims_t& dm, int branch);
 bool tc_gather_supported(const nsa_dims_t& dm, int branch_mask);
 int launch_gather_tc(const nsa_dims_t& dm, int branch_mask, const void* Q, const void* const* K, const void* const* V,
@@ -89,8 +88,6 @@ int launch_gather_tc(const nsa_dims_t& dm, int branch_mask, const void* Q, const
 bool tc_gather_fuse_supported(const nsa_dims_t& dm, int S_sel);
 int launch_dense_tc(const nsa_dims_t& dm, int branch, const void* Q, const void* K, const void* V, void* O, float* lse,
                     cudaStream_t stream);
-int launch_sel_tc(const nsa_dims_t& dm, const void* Q, const void* K, const void* V, const int32_t* ranges, void* O, float* lse,
-                  cudaStream_t stream);
 
 bool tc_branch_supported(const nsa_dims_t& dm, int branch) {
   if (dm.impl == NSA_IMPL_SIMT) return false;
@@ -127,8 +124,6 @@ int launch_decode_tc(const nsa_dims_t& dm, const void* Q, const void* K_sel, con
 int launch_branch_tc(const nsa_dims_t& dm, int branch, const void* Q, const void* K, const void* V, const int32_t* ranges,
                      void* O_b, float* lse_b, cudaStream_t stream) {
   if (branch == 1) {
-    static const bool old_kernel = getenv("NSA_B200_OLD_SEL") != nullptr && tc_sel_supported(dm);  // A/B switch (benchmarks only)
-    if (old_kernel) return launch_sel_tc(dm, Q, K, V, ranges, O_b, lse_b, stream);
     const void* Ks[3] = {nullptr, K, nullptr};
     const void* Vs[3] = {nullptr, V, nullptr};
     void* Os[3] = {nullptr, O_b, nullptr};

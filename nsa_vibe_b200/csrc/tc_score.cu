@@ -71,7 +71,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 template <typename T, int MT, int R>
 __global__ void __launch_bounds__(32 * (4 * MT + 2), 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, nsa_dims_t dm, int S_sel,
-                float* __restrict__ p_grp, int TOK, int dbg_stop) {
+                float* __restrict__ p_grp, int TOK) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   using SM = ScSmem<MT>;
@@ -90,8 +90,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   int s_last = s_base + MT * TOK - 1;
   if (s_last > dm.S - 1) s_last = dm.S - 1;
   const int nk_cta = causal ? num_cmp_at(dm.t0 + s_last, dm.l, dm.d, dm.S_cmp) : dm.S_cmp;
-  const int NT = (dbg_stop == 1 || dbg_stop >= 3) ? 0 : ceil_div(nk_cta, 128);        // key tiles with work
-  const int NTO = (dbg_stop == 2 || dbg_stop == 3) ? 0 : ceil_div(S_sel, BPT);        // output tiles (tiles >= NT only flush the carry / write zeros)
+  const int NT = ceil_div(nk_cta, 128);        // key tiles with work
+  const int NTO = ceil_div(S_sel, BPT);        // output tiles (tiles >= NT only flush the carry / write zeros)
 
   // ---- setup ---------------------------------------------------------------------------------------------
   {  // rows of the Q tiles that TMA does not write (>= TOK*h) must hold finite data
@@ -116,11 +116,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp == kSoftWarps) {
     // ===== TMA producer ====================================================================================
-    if (lane == 0 && dbg_stop < 3) {
+    if (lane == 0) {
       mbar_expect_tx(&ms->q_full, MT * TOK * dm.h * 128);
       for (int m = 0; m < MT; ++m)
         tma_load_4d(smem + SM::q + m * kScTile, &tmQ, &ms->q_full, 0, 0, g, b * dm.S + s_base + m * TOK);
-      for (int it = 0; it < (dbg_stop == 2 ? NT : 2 * NT); ++it) {
+      for (int it = 0; it < 2 * NT; ++it) {
         const int ks = it % kScStages;
         mbar_wait(&ms->k_empty[ks], ((it / kScStages) & 1) ^ 1);
         mbar_expect_tx(&ms->k_full[ks], kScTile);
@@ -131,8 +131,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ===== MMA issuer ======================================================================================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(128, 128, TcType<T>::fmt, 0, 0);
-      if (dbg_stop < 3) mbar_wait(&ms->q_full, 0);
-      for (int it = 0; it < (dbg_stop == 2 ? NT : 2 * NT); ++it) {
+      mbar_wait(&ms->q_full, 0);
+      for (int it = 0; it < 2 * NT; ++it) {
         const int ks = it % kScStages, st = it % STG;
         mbar_wait(&ms->k_full[ks], (it / kScStages) & 1);
         const uint32_t kb = smem_u32(smem + SM::ring + ks * kScTile);
@@ -314,8 +314,7 @@ static int launch_score_t(const nsa_dims_t& dm, const void* Q, const void* Kc, i
     attr_set = true;
   }
   const int grid = dm.B * dm.G * ceil_div(dm.S, MT * TOK);
-  static const int dbg_stop = getenv("NSA_B200_SCORE_STOP") ? atoi(getenv("NSA_B200_SCORE_STOP")) : 0;
-  kern<<<grid, 32 * (4 * MT + 2), ScSmem<MT>::total, stream>>>(tmQ, tmK, dm, S_sel, p_grp, TOK, dbg_stop);
+  kern<<<grid, 32 * (4 * MT + 2), ScSmem<MT>::total, stream>>>(tmQ, tmK, dm, S_sel, p_grp, TOK);
   return check_launch("score_tc_kernel");
 }
 

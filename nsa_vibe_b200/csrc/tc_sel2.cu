@@ -451,50 +451,59 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 // 3. merge: one warp per (b, s, g) row.  O[row][head] = sum_k exp(lse_k - LSE) O_k, LSE = logsumexp_k lse_k; empty row ->
 //    zeros and lse = -inf (attention_kernels.py:769-771).  Slots are folded in slot order, so the result is deterministic.
 // ---------------------------------------------------------------------------------------------------------------------
+// One thread per 16-byte chunk of a row (h*8 chunks): its 16 lse values and 16 partial chunks are all requested before any
+// is used, so a row costs two memory round trips (pair_of, then everything else).
+constexpr int kS2MergeRows = 4;  // rows per CTA
+
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kS2MergeRows * 64)
 sel2_merge_kernel(int n_rows, int h, const int* __restrict__ pair_of, const T* __restrict__ O_p, const float* __restrict__ lse_p,
                   T* __restrict__ O, float* __restrict__ lse) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chunks = h * 8;  // 16-byte chunks per row (h heads x 64 x 2 B)
-  for (int row = blockIdx.x * 8 + warp; row < n_rows; row += gridDim.x * 8) {
-    const int p_l = lane < kS2MaxSlots ? pair_of[(size_t)row * kS2MaxSlots + lane] : -1;
-    for (int cidx = lane; cidx < ((chunks + 31) & ~31); cidx += 32) {
-      const bool act = cidx < chunks;
-      const int head = act ? cidx >> 3 : 0;
-      float mx = -INFINITY;
-      float ls[kS2MaxSlots];
+  const int chunks = h * 8;                   // 16-byte chunks per row (h heads x 64 x 2 B), <= 64 threads per row
+  const int rl = threadIdx.x / 64, cidx = threadIdx.x % 64;
+  for (int row = blockIdx.x * kS2MergeRows + rl; row < n_rows; row += gridDim.x * kS2MergeRows) {
+    if (cidx >= chunks) continue;
+    const int head = cidx >> 3;
+    int pk[kS2MaxSlots];
+    {
+      const int4* pp = reinterpret_cast<const int4*>(pair_of + (size_t)row * kS2MaxSlots);
 #pragma unroll
-      for (int k = 0; k < kS2MaxSlots; ++k) {
-        const int p = __shfl_sync(0xffffffffu, p_l, k);
-        ls[k] = (p >= 0 && act) ? lse_p[(size_t)p * h + head] : -INFINITY;
-        mx = fmaxf(mx, ls[k]);
-      }
-      float acc[8], den = 0.f;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-#pragma unroll
-      for (int k = 0; k < kS2MaxSlots; ++k) {
-        const int p = __shfl_sync(0xffffffffu, p_l, k);
-        if (p >= 0 && act && ls[k] > -INFINITY) {
-          const float w = __expf(ls[k] - mx);
-          den += w;
-          const uint4 v = *reinterpret_cast<const uint4*>(O_p + (size_t)p * h * 64 + cidx * 8);
-          const T* pv = reinterpret_cast<const T*>(&v);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, (float)pv[e], acc[e]);
-        }
-      }
-      if (act) {
-        const float inv = den > 0.f ? 1.0f / den : 0.f;
-        uint4 o;
-        T* po = reinterpret_cast<T*>(&o);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) po[e] = T(acc[e] * inv);
-        *reinterpret_cast<uint4*>(O + (size_t)row * h * 64 + cidx * 8) = o;
-        if (lse && (cidx & 7) == 0) lse[(size_t)row * h + head] = den > 0.f ? mx + logf(den) : -INFINITY;
+      for (int q = 0; q < kS2MaxSlots / 4; ++q) {
+        const int4 t = pp[q];
+        pk[4 * q] = t.x; pk[4 * q + 1] = t.y; pk[4 * q + 2] = t.z; pk[4 * q + 3] = t.w;
       }
     }
+    float ls[kS2MaxSlots];
+    uint4 v[kS2MaxSlots];
+#pragma unroll
+    for (int k = 0; k < kS2MaxSlots; ++k) {
+      const int p = pk[k];
+      ls[k] = p >= 0 ? lse_p[(size_t)p * h + head] : -INFINITY;
+      v[k] = p >= 0 ? *reinterpret_cast<const uint4*>(O_p + (size_t)p * h * 64 + cidx * 8) : make_uint4(0, 0, 0, 0);
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kS2MaxSlots; ++k) mx = fmaxf(mx, ls[k]);
+    float acc[8], den = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int k = 0; k < kS2MaxSlots; ++k) {
+      if (ls[k] > -INFINITY) {
+        const float w = __expf(ls[k] - mx);
+        den += w;
+        const T* pv = reinterpret_cast<const T*>(&v[k]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, (float)pv[e], acc[e]);
+      }
+    }
+    const float inv = den > 0.f ? 1.0f / den : 0.f;
+    uint4 o;
+    T* po = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) po[e] = T(acc[e] * inv);
+    *reinterpret_cast<uint4*>(O + (size_t)row * h * 64 + cidx * 8) = o;
+    if (lse && (cidx & 7) == 0) lse[(size_t)row * h + head] = den > 0.f ? mx + logf(den) : -INFINITY;
   }
 }
 
@@ -542,7 +551,7 @@ static S2Ws s2_ws(const nsa_dims_t& dm) {
 
 bool tc_sel2_supported(const nsa_dims_t& dm) {
   if (dm.impl == NSA_IMPL_SIMT) return false;
-  if (!((dm.dtype == NSA_BF16 || dm.dtype == NSA_F16) && dm.Dk == 64 && dm.Dv == 64 && dm.h >= 1 && dm.h <= 64)) return false;
+  if (!((dm.dtype == NSA_BF16 || dm.dtype == NSA_F16) && dm.Dk == 64 && dm.Dv == 64 && dm.h >= 1 && dm.h <= 8)) return false;  // merge: h*8 <= 64 threads per row
   if (dm.l_sel % 64 != 0 || (long long)dm.n_sel * dm.l_sel > 64 * kS2MaxSlots || dm.n_ranges < 1 || dm.S_sel_kv < 1) return false;
   const long long rows = (long long)dm.B * dm.S * dm.G;
   const long long nb = (dm.S_sel_kv + 63) / 64;
@@ -604,9 +613,9 @@ static int launch_sel2_t(const nsa_dims_t& dm, const void* Q, const void* K, con
   }
   kern<<<w.max_runs, 320, S2Smem::total, stream>>>(tmQ, tmK, tmV, dm, gm, runs, n_runs, tok, hi, O_p, lse_p);
   if (int rc = check_launch("sel2_attn_kernel")) return rc;
-  int mblocks = ceil_div(n_rows, 8);
-  if (mblocks > 148 * 16) mblocks = 148 * 16;
-  sel2_merge_kernel<T><<<mblocks, 256, 0, stream>>>(n_rows, dm.h, pair_of, O_p, lse_p, (T*)O, lse);
+  int mblocks = ceil_div(n_rows, kS2MergeRows);
+  if (mblocks > 148 * 64) mblocks = 148 * 64;
+  sel2_merge_kernel<T><<<mblocks, kS2MergeRows * 64, 0, stream>>>(n_rows, dm.h, pair_of, O_p, lse_p, (T*)O, lse);
   return check_launch("sel2_merge_kernel");
 }
 

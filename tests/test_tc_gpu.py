@@ -254,7 +254,7 @@ def test_dense_tc_reference_jump():
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("sel_mode,S,h,B", [(0, 700, 6, 2), (1, 700, 6, 1), (0, 1500, 4, 2), (1, 333, 8, 1), (0, 2100, 6, 1),
-                                             (0, 200, 16, 3), (1, 130, 1, 2)])
+                                             (0, 200, 8, 3), (1, 130, 1, 2)])
 def test_sel_blockmajor_vs_gather_vs_oracle(dtype, sel_mode, S, h, B):
     """KV-block-major selected branch (index build -> tcgen05 per-block attention -> merge of partials) against the fp32
     oracle and the query-major gather kernel.  Tolerance: max-abs 2e-2 / MAE 1e-3 (partials are stored in 16 bits)."""
