@@ -187,7 +187,10 @@ struct S2Smem {
   static constexpr int q = kv + 2 * 8192;                   // [2 slots][2 stages] x 16 KB
   static constexpr int p = q + 4 * kS2Tile;                 // [2 slots] x 16 KB  (128 rows x 64 keys, 16-bit, 128B-swizzled)
   static constexpr int misc = p + 2 * kS2Tile;
-  static constexpr int total = misc + 512 + 1024;
+  // Two CTAs must fit one SM (2 x (total + 1 KB reserved) <= 228 KB), so there is no alignment slack: the kernel requires the
+  // dynamic shared-memory window to start 1024-byte aligned (it does on sm_100: it follows the 1 KB reserved region) and
+  // traps otherwise.
+  static constexpr int total = misc + 256;
 };
 
 struct S2Misc {
@@ -223,8 +226,9 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                  const int* __restrict__ n_runs, const int* __restrict__ tok, const int* __restrict__ hi,
                  T* __restrict__ O_p, float* __restrict__ lse_p) {
   if ((int)blockIdx.x >= *n_runs) return;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if (smem_u32(smem_raw) & 1023u) __trap();  // see S2Smem::total
+  uint8_t* smem = smem_raw;
   S2Misc* ms = reinterpret_cast<S2Misc*>(smem + S2Smem::misc);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = dm.h, TOK = gm.tokp;
@@ -339,12 +343,24 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t tm_O = tmem + lane_off + 128 + s * 64;
     uint8_t* prow = smem + S2Smem::p + s * kS2Tile + r * 128;
     const int sw = r & 7;
+    // the pair's (query, valid keys) of the NEXT tile are fetched while the current one is processed: no global latency
+    // at the head of a tile
+    int tok_n = -1, hi_n = 64;
+    if (ns > 0 && tok_l < TOK) {
+      const int p0 = (run.tile0 + s) * TOK + tok_l;
+      tok_n = tok[p0];
+      hi_n = hi[p0];
+    }
     for (int k = 0; k < ns; ++k) {
       const int i = 2 * k + s;
       const int p = (run.tile0 + i) * TOK + tok_l;
-      const bool row_ok = tok_l < TOK && tok[p] >= 0;
+      const bool row_ok = tok_l < TOK && tok_n >= 0;
       // rows that are not stored see the whole tile, so they never push their warp onto the masked path
-      const int nk = row_ok ? hi[p] : 64;
+      const int nk = row_ok ? hi_n : 64;
+      if (k + 1 < ns && tok_l < TOK) {
+        tok_n = tok[p + 2 * TOK];
+        hi_n = hi[p + 2 * TOK];
+      }
       mbar_wait(&ms->s_full[s], k & 1);
       tc_fence_after();
       uint32_t va[32], vb2[32];
@@ -621,7 +637,7 @@ static int launch_sel2_t(const nsa_dims_t& dm, const void* Q, const void* K, con
 
 int launch_sel2_tc(const nsa_dims_t& dm, const void* Q, const void* K, const void* V, const int32_t* ranges, void* O, float* lse,
                    void* workspace, cudaStream_t stream) {
-  static_assert(sizeof(S2Misc) <= 512, "S2Misc must fit its slot");
+  static_assert(sizeof(S2Misc) <= 256, "S2Misc must fit its slot");
   if (dm.B * dm.S * dm.G == 0) return NSA_OK;
   NSA_REQUIRE(workspace, "sel2: needs a workspace of nsa_workspace_bytes(NSA_WS_SEL) bytes");
   if (dm.dtype == NSA_BF16) return launch_sel2_t<__nv_bfloat16>(dm, Q, K, V, ranges, O, lse, workspace, stream);

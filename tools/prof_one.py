@@ -26,6 +26,8 @@ with torch.no_grad():
             ops.branch_attention(ops.BR_CMP, Q, Kc, Vc, cfg)
         elif what == "win":
             ops.branch_attention(ops.BR_WIN, Q, Kw, Vw, cfg)
+        elif what == "sel2":
+            ops.sel_attention_blockmajor(Q, Ks, Vs, cfg, ranges)
         else:
             ops.branch_attention(ops.BR_SEL, Q, Ks, Vs, cfg, ranges)
 torch.cuda.synchronize()
