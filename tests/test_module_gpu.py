@@ -139,3 +139,40 @@ def test_stats_getters_and_llama_block():
     y = blk(torch.randn(2, 96, 64, device="cuda", requires_grad=True))
     y.sum().backward()  # train smoke (nsa/tests/test_train_smoke.py:6-13)
     assert torch.isfinite(y).all()
+
+
+def test_module_m7c_bf16_tensor_core_path_prefill_and_decode():
+    """m7c head dims (D=64, h=6) in bf16: batched prefill and decode steps run on the tcgen05 kernels (scorer, dense, gather /
+    fused decode step).  Reference = the same module and weights in fp32 (SIMT kernels, already pinned on the goldens).
+    Tolerance: mean-abs 3e-3, max-abs 0.15 on the module output (bf16 projections; a flipped near-tie selection is a
+    localised difference)."""
+    from nsa_vibe_b200 import NSAAttention, build_block_meta, create_empty_kv
+    os.environ["NSA_PREFILL_BATCHED"] = "1"
+    try:
+        torch.manual_seed(7)
+        dim, H, G, dk, dv, l, d, ls, n, w = 768, 12, 2, 64, 64, 32, 16, 64, 16, 512
+        m32 = NSAAttention(dim, H, G, dk, dv, l=l, d=d, l_sel=ls, n_sel=n, w=w).cuda()
+        m16 = NSAAttention(dim, H, G, dk, dv, l=l, d=d, l_sel=ls, n_sel=n, w=w).cuda()
+        m16.load_state_dict(m32.state_dict())
+        m16 = m16.bfloat16()
+    finally:
+        os.environ.pop("NSA_PREFILL_BATCHED", None)
+    B, S0, n_dec = 2, 700, 6
+    x = torch.randn(B, S0 + n_dec, dim, device="cuda")
+    mk = lambda dt: create_empty_kv(B, G, dk, dv, build_block_meta(64, l, d, ls, n, w), device="cuda", dtype=dt)
+    outs = {}
+    with torch.no_grad():
+        for name, mod, dt in (("f32", m32, torch.float32), ("bf16", m16, torch.bfloat16)):
+            kv = mk(dt)
+            o0, kv = mod(x[:, :S0].to(dt), kv, prefill=True)
+            steps = [o0]
+            for i in range(S0, S0 + n_dec):
+                o, kv = mod(x[:, i:i + 1].to(dt), kv, prefill=False)
+                steps.append(o)
+            outs[name] = torch.cat(steps, dim=1).float()
+            assert kv.K_sel.shape[2] == S0 + n_dec and kv.K_win.shape[2] == min(w, S0 + n_dec)
+    assert torch.isfinite(outs["bf16"]).all()
+    err = (outs["bf16"] - outs["f32"]).abs()
+    assert err.mean() <= 3e-3 and err.max() <= 0.15, (err.mean(), err.max())
+    err_dec = err[:, S0:]
+    assert err_dec.mean() <= 3e-3 and err_dec.max() <= 0.15, (err_dec.mean(), err_dec.max())
