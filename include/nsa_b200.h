@@ -107,10 +107,12 @@ int nsa_sel_attn_fwd_blockmajor(const nsa_dims_t* dm, const void* Q, const void*
                                 const int32_t* ranges, void* O_b, float* lse_b, void* workspace, void* stream);
 /* Analytical backward of one branch (replaces _selection_attention_backward,
  * kernels/triton_sel_kernel/__init__.py:163-231, without its first-key-only line).
- * dO_b [B,S,G,h,Dv] in dm->dtype, O_b as saved, dQ/dK/dV fp32 accumulators (+=, caller zeroes). */
+ * dO_b [B,S,G,h,Dv] in dm->dtype, O_b as saved, dQ/dK/dV fp32 accumulators (+=, caller zeroes).
+ * workspace: nsa_workspace_bytes(dm, NSA_WS_BWD) bytes for the tcgen05 kernels (KV-tile-major, dK/dV accumulated in
+ * TMEM, dQ by fp32 reductions); NULL or a shape they do not serve -> the SIMT kernel. */
 int nsa_branch_attn_bwd(const nsa_dims_t* dm, int branch, const void* Q, const void* K, const void* V,
                         const int32_t* ranges, const void* O_b, const float* lse_b, const void* dO_b,
-                        float* dQ, float* dK, float* dV, void* stream);
+                        float* dQ, float* dK, float* dV, void* workspace, void* stream);
 
 /* ---- (4) gate: GateMLP forward / backward (nsa_attention.py:32-82) on q_gp = mean_h(Q). */
 int nsa_gate_fwd(const nsa_dims_t* dm, const void* Q, const nsa_gate_params_t* gp, float* gates, void* stream);
@@ -130,13 +132,13 @@ int nsa_prefill_fwd(const nsa_dims_t* dm, const void* Q,
                     const nsa_gate_params_t* gp, void* O, float* lse, float* gates, void* O_branches,
                     void* workspace, void* stream);
 /* Backward of nsa_prefill_fwd.  dQ [B,S,G,h,Dk], dK_x/dV_x like their caches but fp32 (+=, caller
- * zeroes), dgates [B,S,G,3] fp32 (written). */
+ * zeroes), dgates [B,S,G,3] fp32 (written).  workspace: nsa_workspace_bytes(dm, NSA_WS_BWD) (see nsa_branch_attn_bwd). */
 int nsa_prefill_bwd(const nsa_dims_t* dm, const void* Q,
                     const void* K_sel, const void* V_sel, const void* K_win, const void* V_win,
                     const void* K_cmp, const void* V_cmp, const int32_t* ranges,
                     const void* O_branches, const float* lse, const float* gates, const void* dO,
                     float* dQ, float* dK_sel, float* dV_sel, float* dK_win, float* dV_win,
-                    float* dK_cmp, float* dV_cmp, float* dgates, void* stream);
+                    float* dK_cmp, float* dV_cmp, float* dgates, void* workspace, void* stream);
 /* nsa_decode_fwd: one decode step after the caches were appended (S must be 1; t = t0).  Scores the
  * emitted compressed keys, selects with the decode rule, attends over the three branches, gates and
  * combines (nsa_attention.py:648-971).  ranges_out [B,G,n_sel,2] may be NULL. */
@@ -145,7 +147,7 @@ int nsa_decode_fwd(const nsa_dims_t* dm, const void* Q,
                    const void* K_cmp, const void* V_cmp, const nsa_gate_params_t* gp,
                    void* O, int32_t* ranges_out, void* workspace, void* stream);
 
-enum { NSA_WS_SCORE_SELECT = 0, NSA_WS_DECODE = 1, NSA_WS_PREFILL = 2, NSA_WS_SEL_BLOCKMAJOR = 3 };
+enum { NSA_WS_SCORE_SELECT = 0, NSA_WS_DECODE = 1, NSA_WS_PREFILL = 2, NSA_WS_SEL_BLOCKMAJOR = 3, NSA_WS_BWD = 4 };
 int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which);
 
 #ifdef __cplusplus

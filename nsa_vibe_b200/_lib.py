@@ -15,7 +15,7 @@ NSA_F32, NSA_BF16, NSA_F16 = 0, 1, 2
 NORM_FULL_ROW, NORM_CAUSAL = 0, 1
 GATE_MLP, GATE_UNIFORM, GATE_CMP, GATE_SEL, GATE_WIN = 0, 1, 2, 3, 4
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
-WS_SCORE_SELECT, WS_DECODE, WS_PREFILL, WS_SEL_BLOCKMAJOR = 0, 1, 2, 3
+WS_SCORE_SELECT, WS_DECODE, WS_PREFILL, WS_SEL_BLOCKMAJOR, WS_BWD = 0, 1, 2, 3, 4
 
 
 class Dims(C.Structure):
@@ -49,11 +49,11 @@ SIGNATURES = {
     "nsa_score_select": (_I, [_DP, _P, _P, _I, _I, _I, _P, _P, _P]),
     "nsa_branch_attn_fwd": (_I, [_DP, _I, _P, _P, _P, _P, _P, _P, _P]),
     "nsa_sel_attn_fwd_blockmajor": (_I, [_DP, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "nsa_branch_attn_bwd": (_I, [_DP, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "nsa_branch_attn_bwd": (_I, [_DP, _I] + [_P] * 12),
     "nsa_gate_fwd": (_I, [_DP, _P, _GP, _P, _P]),
     "nsa_gate_bwd": (_I, [_DP, _P, _GP, _P, _P, _P, _P, _P, _P, _P]),
     "nsa_prefill_fwd": (_I, [_DP] + [_P] * 8 + [_GP] + [_P] * 6),
-    "nsa_prefill_bwd": (_I, [_DP] + [_P] * 21),
+    "nsa_prefill_bwd": (_I, [_DP] + [_P] * 22),
     "nsa_decode_fwd": (_I, [_DP] + [_P] * 7 + [_GP] + [_P] * 4),
     "nsa_workspace_bytes": (_I64, [_DP, _I]),
 }

@@ -151,7 +151,7 @@ int nsa_sel_attn_fwd_blockmajor(const nsa_dims_t* dm, const void* Q, const void*
 
 int nsa_branch_attn_bwd(const nsa_dims_t* dm, int branch, const void* Q, const void* K, const void* V,
                         const int32_t* ranges, const void* O_b, const float* lse_b, const void* dO_b, float* dQ,
-                        float* dK, float* dV, void* stream) {
+                        float* dK, float* dV, void* workspace, void* stream) {
   if (int rc = validate_dims(dm, "branch_attn_bwd")) return rc;
   NSA_REQUIRE(branch >= 0 && branch <= 2, "branch_attn_bwd: branch %d", branch);
   NSA_REQUIRE(Q && O_b && lse_b && dO_b && dQ && dK && dV, "branch_attn_bwd: NULL pointer");
@@ -169,7 +169,7 @@ int nsa_branch_attn_bwd(const nsa_dims_t* dm, int branch, const void* Q, const v
   a.dK[branch] = dK;
   a.dV[branch] = dV;
   a.branch_mask = 1 << branch;
-  return launch_bwd_generic(*dm, a, (cudaStream_t)stream);
+  return launch_bwd_tc(*dm, a, workspace, (cudaStream_t)stream);
 }
 
 int nsa_gate_fwd(const nsa_dims_t* dm, const void* Q, const nsa_gate_params_t* gp, float* gates, void* stream) {
@@ -242,7 +242,7 @@ int nsa_prefill_bwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, cons
                     const void* V_win, const void* K_cmp, const void* V_cmp, const int32_t* ranges,
                     const void* O_branches, const float* lse, const float* gates, const void* dO, float* dQ,
                     float* dK_sel, float* dV_sel, float* dK_win, float* dV_win, float* dK_cmp, float* dV_cmp,
-                    float* dgates, void* stream) {
+                    float* dgates, void* workspace, void* stream) {
   if (int rc = validate_dims(dm, "prefill_bwd")) return rc;
   NSA_REQUIRE(Q && ranges && O_branches && lse && gates && dO && dQ, "prefill_bwd: NULL pointer");
   NSA_REQUIRE(dK_sel && dV_sel && dK_win && dV_win && dK_cmp && dV_cmp, "prefill_bwd: NULL gradient buffer");
@@ -260,7 +260,7 @@ int nsa_prefill_bwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, cons
   a.dQ = dQ;
   a.dgates = dgates;
   a.branch_mask = 7;
-  return launch_bwd_generic(*dm, a, (cudaStream_t)stream);
+  return launch_bwd_tc(*dm, a, workspace, (cudaStream_t)stream);
 }
 
 int nsa_decode_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
@@ -307,6 +307,8 @@ int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which) {
     }
     case NSA_WS_SEL_BLOCKMAJOR:
       return tc_sel2_workspace(*dm);
+    case NSA_WS_BWD:
+      return tc_bwd_workspace(*dm);
     default:
       return 0;
   }

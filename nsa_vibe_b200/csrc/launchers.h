@@ -49,6 +49,11 @@ bool tc_sel2_supported(const nsa_dims_t& dm);
 int64_t tc_sel2_workspace(const nsa_dims_t& dm);
 int launch_sel2_tc(const nsa_dims_t& dm, const void* Q, const void* K, const void* V, const int32_t* ranges, void* O, float* lse,
                    void* workspace, cudaStream_t stream);
+// tensor-core backward (tc_bwd.cu); falls back to launch_bwd_generic per branch when a shape has no tcgen05 kernel or
+// workspace is NULL
+bool tc_bwd_supported(const nsa_dims_t& dm, int branch);
+int64_t tc_bwd_workspace(const nsa_dims_t& dm);
+int launch_bwd_tc(const nsa_dims_t& dm, const BwdArgs& a, void* workspace, cudaStream_t stream);
 int64_t tc_score_workspace(const nsa_dims_t& dm);
 int64_t tc_decode_workspace(const nsa_dims_t& dm);
 int launch_score_tc(const nsa_dims_t& dm, const void* Q, const void* Kc, int S_sel, int S_total, int sel_mode, int Kr,

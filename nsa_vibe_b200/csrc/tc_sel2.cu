@@ -16,22 +16,17 @@
 
 #include "tc_common.cuh"
 #include "launchers.h"
+#include "tc_sel2.cuh"
 
 namespace nsa {
 using namespace tc;
 
-constexpr int kS2MaxSlots = 16;   // 64-key blocks per row (n_sel * l_sel <= 1024 keys)
-constexpr int kS2Run = 24;        // M-tiles one CTA walks (same block: its K/V tile is loaded once)
 constexpr int kS2Tile = 128 * 128;  // bytes of one 128-row Q tile / P tile half
 
 // ---------------------------------------------------------------------------------------------------------------------
 // 1. index build.  One thread per (b, s, g) row; CTA-level shared-memory aggregation keeps the hot counters (block 0 and
 //    the local blocks are picked by every row) off the global atomics.
 // ---------------------------------------------------------------------------------------------------------------------
-struct S2Geom {
-  int B, S, G, n_ranges, S_kv, NB, t0, tokp;  // NB = 64-key blocks per slab, tokp = queries per M-tile
-};
-
 __device__ __forceinline__ int s2_row_blocks(const S2Geom& gm, const int32_t* __restrict__ rr, int* blk, int* valid) {
   int n = 0;
   for (int i = 0; i < gm.n_ranges; ++i) {
@@ -78,8 +73,6 @@ sel2_count_kernel(S2Geom gm, const int32_t* __restrict__ ranges, int* __restrict
 // Offsets of the block lists (each padded to a whole number of M-tiles) and the run table of the attention kernel:
 // run = (list, first M-tile, number of M-tiles <= kS2Run), every run inside one list so its CTA loads one K/V tile.
 // One CTA, sequential over chunks of 1024 lists (2 x 1024 lists at 64k: microseconds).
-struct S2Run { int list, tile0, ntiles, pad; };
-
 __device__ __forceinline__ int s2_block_scan(int v, int* buf) {  // inclusive scan over 1024 threads
   buf[threadIdx.x] = v;
   __syncthreads();
@@ -174,7 +167,7 @@ sel2_fill_kernel(S2Geom gm, const int32_t* __restrict__ ranges, const int* __res
         tok[p] = b * gm.S + s;
         hi[p] = valid[k];
       }
-      pair_of[(size_t)row * kS2MaxSlots + k] = p;
+      if (pair_of) pair_of[(size_t)row * kS2MaxSlots + k] = p;
     }
   }
 }
@@ -535,9 +528,9 @@ static S2Geom s2_geom(const nsa_dims_t& dm) {
   return gm;
 }
 
-// workspace carve-up (bytes, all 256-aligned)
+// workspace carve-up (bytes, all 256-aligned); the index comes first so the backward can use it without the partials
 struct S2Ws {
-  size_t counts, offs, cursors, runs, n_runs, tok, hi, pair_of, lse_p, O_p, total;
+  size_t counts, offs, cursors, runs, n_runs, tok, hi, index_total, pair_of, lse_p, O_p, total;
   int max_pairs, max_runs;
 };
 
@@ -558,6 +551,7 @@ static S2Ws s2_ws(const nsa_dims_t& dm) {
   w.n_runs = take(4);
   w.tok = take((size_t)w.max_pairs * 4);
   w.hi = take((size_t)w.max_pairs * 4);
+  w.index_total = o;
   w.pair_of = take((size_t)rows * kS2MaxSlots * 4);
   w.lse_p = take((size_t)w.max_pairs * dm.h * 4);
   w.O_p = take((size_t)w.max_pairs * dm.h * 64 * 2);
@@ -565,9 +559,8 @@ static S2Ws s2_ws(const nsa_dims_t& dm) {
   return w;
 }
 
-bool tc_sel2_supported(const nsa_dims_t& dm) {
-  if (dm.impl == NSA_IMPL_SIMT) return false;
-  if (!((dm.dtype == NSA_BF16 || dm.dtype == NSA_F16) && dm.Dk == 64 && dm.Dv == 64 && dm.h >= 1 && dm.h <= 8)) return false;  // merge: h*8 <= 64 threads per row
+bool sel2_index_supported(const nsa_dims_t& dm) {
+  if (dm.h < 1 || dm.h > 128) return false;
   if (dm.l_sel % 64 != 0 || (long long)dm.n_sel * dm.l_sel > 64 * kS2MaxSlots || dm.n_ranges < 1 || dm.S_sel_kv < 1) return false;
   const long long rows = (long long)dm.B * dm.S * dm.G;
   const long long nb = (dm.S_sel_kv + 63) / 64;
@@ -577,14 +570,18 @@ bool tc_sel2_supported(const nsa_dims_t& dm) {
   return true;
 }
 
-int64_t tc_sel2_workspace(const nsa_dims_t& dm) { return tc_sel2_supported(dm) ? (int64_t)s2_ws(dm).total : 0; }
+bool tc_sel2_supported(const nsa_dims_t& dm) {
+  if (dm.impl == NSA_IMPL_SIMT) return false;
+  if (!((dm.dtype == NSA_BF16 || dm.dtype == NSA_F16) && dm.Dk == 64 && dm.Dv == 64 && dm.h >= 1 && dm.h <= 8)) return false;  // merge: h*8 <= 64 threads per row
+  return sel2_index_supported(dm);
+}
 
-template <typename T>
-static int launch_sel2_t(const nsa_dims_t& dm, const void* Q, const void* K, const void* V, const int32_t* ranges, void* O,
-                         float* lse, void* workspace, cudaStream_t stream) {
+int64_t tc_sel2_workspace(const nsa_dims_t& dm) { return tc_sel2_supported(dm) ? (int64_t)s2_ws(dm).total : 0; }
+int64_t sel2_index_workspace(const nsa_dims_t& dm) { return sel2_index_supported(dm) ? (int64_t)s2_ws(dm).index_total : 0; }
+
+// ranges -> block lists + run table.  pair_of [rows][16] is written only when the caller merges partials (forward).
+static int s2_build(const nsa_dims_t& dm, const int32_t* ranges, char* ws, const S2Ws& w, bool with_pair_of, cudaStream_t stream) {
   const S2Geom gm = s2_geom(dm);
-  const S2Ws w = s2_ws(dm);
-  char* ws = reinterpret_cast<char*>(workspace);
   int* counts = reinterpret_cast<int*>(ws + w.counts);
   int* offs = reinterpret_cast<int*>(ws + w.offs);
   int* cursors = reinterpret_cast<int*>(ws + w.cursors);
@@ -592,12 +589,9 @@ static int launch_sel2_t(const nsa_dims_t& dm, const void* Q, const void* K, con
   int* n_runs = reinterpret_cast<int*>(ws + w.n_runs);
   int* tok = reinterpret_cast<int*>(ws + w.tok);
   int* hi = reinterpret_cast<int*>(ws + w.hi);
-  int* pair_of = reinterpret_cast<int*>(ws + w.pair_of);
-  float* lse_p = reinterpret_cast<float*>(ws + w.lse_p);
-  T* O_p = reinterpret_cast<T*>(ws + w.O_p);
+  int* pair_of = with_pair_of ? reinterpret_cast<int*>(ws + w.pair_of) : nullptr;
   const int n_rows = dm.B * dm.S * dm.G;
   const int nlists = dm.B * dm.G * gm.NB;
-
   cudaMemsetAsync(counts, 0, (size_t)nlists * 4, stream);
   cudaMemsetAsync(tok, 0xff, (size_t)w.max_pairs * 4, stream);  // -1 = padding pair
   const int idx_blocks = ceil_div(n_rows, kS2IdxThreads);
@@ -613,7 +607,38 @@ static int launch_sel2_t(const nsa_dims_t& dm, const void* Q, const void* K, con
   sel2_scan_kernel<<<1, 1024, 0, stream>>>(gm, counts, offs, cursors, runs, n_runs);
   if (int rc = check_launch("sel2_scan_kernel")) return rc;
   sel2_fill_kernel<<<idx_blocks, kS2IdxThreads, 2 * hist_bytes, stream>>>(gm, ranges, offs, cursors, tok, hi, pair_of);
-  if (int rc = check_launch("sel2_fill_kernel")) return rc;
+  return check_launch("sel2_fill_kernel");
+}
+
+int sel2_build_index(const nsa_dims_t& dm, const int32_t* ranges, void* workspace, cudaStream_t stream, S2Index* out) {
+  NSA_REQUIRE(sel2_index_supported(dm), "sel2 index: shape not supported");
+  const S2Ws w = s2_ws(dm);
+  char* ws = reinterpret_cast<char*>(workspace);
+  if (int rc = s2_build(dm, ranges, ws, w, false, stream)) return rc;
+  out->gm = s2_geom(dm);
+  out->runs = reinterpret_cast<const S2Run*>(ws + w.runs);
+  out->n_runs = reinterpret_cast<const int*>(ws + w.n_runs);
+  out->tok = reinterpret_cast<const int*>(ws + w.tok);
+  out->hi = reinterpret_cast<const int*>(ws + w.hi);
+  out->max_runs = w.max_runs;
+  return NSA_OK;
+}
+
+template <typename T>
+static int launch_sel2_t(const nsa_dims_t& dm, const void* Q, const void* K, const void* V, const int32_t* ranges, void* O,
+                         float* lse, void* workspace, cudaStream_t stream) {
+  const S2Geom gm = s2_geom(dm);
+  const S2Ws w = s2_ws(dm);
+  char* ws = reinterpret_cast<char*>(workspace);
+  S2Run* runs = reinterpret_cast<S2Run*>(ws + w.runs);
+  int* n_runs = reinterpret_cast<int*>(ws + w.n_runs);
+  int* tok = reinterpret_cast<int*>(ws + w.tok);
+  int* hi = reinterpret_cast<int*>(ws + w.hi);
+  int* pair_of = reinterpret_cast<int*>(ws + w.pair_of);
+  float* lse_p = reinterpret_cast<float*>(ws + w.lse_p);
+  T* O_p = reinterpret_cast<T*>(ws + w.O_p);
+  const int n_rows = dm.B * dm.S * dm.G;
+  if (int rc = s2_build(dm, ranges, ws, w, true, stream)) return rc;
 
   CUtensorMap tmQ, tmK, tmV;
   const int slabs = dm.B * dm.G;

@@ -99,6 +99,12 @@ def _call(name: str, *args):
     launch_count += 1
 
 
+def _workspace(dm, which: int, dev) -> Optional[torch.Tensor]:
+    """Scratch the kernels of one call need (nsa_workspace_bytes); None when the call needs none."""
+    n = int(_lib.load().nsa_workspace_bytes(C.byref(dm), which))
+    return torch.empty(n, dtype=torch.uint8, device=dev) if n else None
+
+
 def prefill_range_cols(S_total: int, l_sel: int, n_sel: int) -> int:
     return int(_lib.load().nsa_prefill_range_cols(S_total, l_sel, n_sel))
 
@@ -208,14 +214,14 @@ class _BranchAttn(torch.autograd.Function):
         branch, cfg, t0, win_off, has_r = ctx.meta
         rg = rg if has_r else None
         dm = _branch_dims(branch, Q, K, V, cfg, rg, t0, win_off)
-        dm.impl = IMPL_SIMT
+        ws = _workspace(dm, _lib.WS_BWD, Q.device)
         dQ = torch.zeros(Q.shape, dtype=torch.float32, device=Q.device)
         dK = torch.zeros(K.shape, dtype=torch.float32, device=Q.device)
         dV = torch.zeros(V.shape, dtype=torch.float32, device=Q.device)
         dOc = _c(dO.to(Q.dtype))
         if O.numel():
             _call("nsa_branch_attn_bwd", C.byref(dm), branch, _ptr(Q), _ptr(K), _ptr(V), _ptr(rg), _ptr(O), _ptr(lse),
-                  _ptr(dOc), _ptr(dQ), _ptr(dK), _ptr(dV), _stream())
+                  _ptr(dOc), _ptr(dQ), _ptr(dK), _ptr(dV), _ptr(ws), _stream())
         return dQ.to(Q.dtype), dK.to(K.dtype), dV.to(V.dtype), None, None, None, None, None
 
 
@@ -313,10 +319,11 @@ class _PrefillCore(torch.autograd.Function):
         grads = [torch.zeros(t.shape, **f32) for t in (K_sel, V_sel, K_win, V_win, K_cmp, V_cmp)]
         dgates = torch.zeros(gates.shape, **f32)
         dOc = _c(dO.to(Q.dtype))
+        ws = _workspace(dm, _lib.WS_BWD, dev)
         if Q.numel():
             _call("nsa_prefill_bwd", C.byref(dm), _ptr(Q), _ptr(K_sel), _ptr(V_sel), _ptr(K_win), _ptr(V_win), _ptr(K_cmp),
                   _ptr(V_cmp), _ptr(ranges), _ptr(O_br), _ptr(lse), _ptr(gates), _ptr(dOc), _ptr(dQ),
-                  *[_ptr(g) for g in grads], _ptr(dgates), _stream())
+                  *[_ptr(g) for g in grads], _ptr(dgates), _ptr(ws), _stream())
         dparams = [None, None, None, None]
         if has_gate and cfg.gate_mode == GATE_MLP and not stopgrad:
             it = iter(gk)

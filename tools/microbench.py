@@ -82,6 +82,16 @@ def main():
         if "fwd" in what:
             ms = timeit(lambda: ops.prefill_core(Q, Ks, Vs, Kw, Vw, Kc, Vc, gate, cfg, sel_mode=0, ranges=ranges), n=3, warm=1)
             print(f"prefill_fwd (given ranges): {ms:9.3f} ms")
+    if "bwd" in what:  # backward of the fused hot path alone (graph retained), tensor-core vs SIMT kernels
+        impls = [(ops.IMPL_AUTO, "auto")] + ([(ops.IMPL_SIMT, "simt")] if S <= 8192 else [])
+        for impl, nm in impls:
+            c2 = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w, impl=impl)
+            leaves = [t.clone().requires_grad_(True) for t in (Q, Ks, Vs, Kw, Vw, Kc, Vc)]
+            O, _, _ = ops.prefill_core(*leaves, gate, c2, sel_mode=0, ranges=ranges)
+            dO = torch.randn_like(O)
+            ms = timeit(lambda: torch.autograd.grad(O, leaves, dO, retain_graph=True), n=3, warm=1)
+            print(f"prefill_bwd ({nm:4s}) incl. torch zero-fill/casts: {ms:9.3f} ms")
+            del O, leaves
 
 
 if __name__ == "__main__":
