@@ -15,8 +15,12 @@
 // An M-tile is 128 rows = TOK queries x h heads; Q and dO rows of one query arrive as one TMA box each (hardware swizzle).
 // Per (M-tile, key tile) pair:  S, dP (M=128, N=64) -> softmax warps form P~ = g.P and dS~ = g.scale.P o (dP - D) as 16-bit
 // swizzled tiles -> dV += P~^T.dO, dK += dS~^T.Q (M=64, N=64, K=128; A and B both MN-major), dQ_t = dS~.K (M=128, N=64)
-// -> four drain warps add dQ_t into the fp32 dQ with 16-byte vector reductions.  S/dP, P~/dS~, dQ_t and the Q/dO stages
-// are double-buffered: the tensor core works on pair i+1 while the softmax warps are on pair i and the drain warps on i-1.
+// -> four drain warps stage dQ_t as fp32 rows in shared memory and add each row into the fp32 dQ with one bulk
+// reduction (cp.reduce.async.bulk .add.f32: the TMA unit streams the row to the L2 atomic units; per-lane REDG tops out
+// near one fp32 per clock per SM, which made the first version of this kernel atomic-bound at ~3 us per pair).
+// S/dP, P~/dS~ and dQ_t are double-buffered, the Q/dO tiles triple-buffered: the tensor core works on pair i+1 while the
+// softmax warps are on pair i and the drain warps on i-1.  The binding resource is shared-memory bandwidth (136 KB of MMA
+// operand reads + 128 KB of tile writes/reads per pair).
 // g = gate weight of the branch for the row (the gated combine O = sum_b g_b O_b is folded in: dO_b = g_b dO).
 // Warp roles: 0-3 softmax, 4-7 dQ drain, 8 TMA producer, 9 MMA issuer; the epilogue (dK, dV -> global) uses warps 0-7.
 #include <stdlib.h>
@@ -31,20 +35,25 @@ using namespace tc;
 
 constexpr int kBwTile = 128 * 128;  // bytes: 128 rows x 64 x 2 B
 
+constexpr int kBwQS = 3;            // Q/dO stages
+constexpr int kBwDqRow = 256 + 16;  // bytes per staged dQ row: 64 fp32 + 16 B so that 16-byte stores of a warp spread over banks
+
 struct BwSmem {
   static constexpr int k = 0;                       // K tile 8 KB
   static constexpr int v = 8192;                    // V tile 8 KB
-  static constexpr int q = 16384;                   // [2] x 16 KB
-  static constexpr int dO = q + 2 * kBwTile;        // [2] x 16 KB
-  static constexpr int p = dO + 2 * kBwTile;        // [2] x 16 KB   P~  (128 rows x 64 keys)
+  static constexpr int q = 16384;                   // [kBwQS] x 16 KB
+  static constexpr int dO = q + kBwQS * kBwTile;    // [kBwQS] x 16 KB
+  static constexpr int p = dO + kBwQS * kBwTile;    // [2] x 16 KB   P~  (128 rows x 64 keys)
   static constexpr int ds = p + 2 * kBwTile;        // [2] x 16 KB   dS~
-  static constexpr int misc = ds + 2 * kBwTile;
+  static constexpr int dq = ds + 2 * kBwTile;       // 128 rows x kBwDqRow: dQ_t staged for the bulk reductions
+  static constexpr int misc = dq + 128 * kBwDqRow;
   static constexpr int total = misc + 512 + 1024;
 };
 
 struct BwMisc {
   uint64_t kv_full, fin;
-  uint64_t qdo_full[2], qdo_empty[2], s_full[2], s_empty[2], pds_full[2], pds_empty[2], dq_full[2], dq_empty[2];
+  uint64_t qdo_full[kBwQS], qdo_empty[kBwQS];
+  uint64_t s_full[2], s_empty[2], pds_full[2], pds_empty[2], dq_full[2], dq_empty[2];
   uint32_t tmem_base;
 };
 
@@ -81,6 +90,16 @@ __device__ __forceinline__ void bw_red4(float* p, uint32_t a, uint32_t b, uint32
                "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
                : "memory");
 }
+
+// global[dst .. dst+bytes) += shared[src ..) as fp32, done by the TMA unit (bulk async-group completion)
+__device__ __forceinline__ void bw_bulk_red_add_f32(float* dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bw_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bw_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bw_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // key range of one query row in cache-row coordinates (cmp: packing.py:15-23; win: attention_kernels.py:146-178)
 __device__ __forceinline__ void bw_row_range(const nsa_dims_t& dm, int branch, int t, int& lo, int& hi) {
@@ -153,14 +172,16 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   // ---- setup ---------------------------------------------------------------------------------------------------
   {  // rows the TMA never writes (padding rows, padded queries) must hold finite data
     uint4 z = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < 4 * kBwTile / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem + BwSmem::q)[i] = z;
+    for (int i = tid; i < 2 * kBwQS * kBwTile / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem + BwSmem::q)[i] = z;
   }
   if (tid == 0) {
     mbar_init(&ms->kv_full, 1);
     mbar_init(&ms->fin, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kBwQS; ++s) {
       mbar_init(&ms->qdo_full[s], 1);
       mbar_init(&ms->qdo_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&ms->s_full[s], 1);
       mbar_init(&ms->s_empty[s], 4);
       mbar_init(&ms->pds_full[s], 4);
@@ -192,17 +213,17 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     }
     int tk = get_tk(0, lane);
     for (int i = 0; i < n; ++i) {
-      const int s = i & 1, k = i >> 1;
+      const int st = i % kBwQS, k = i / kBwQS;
       const int tk_next = get_tk(i + 1, lane);
       const unsigned have = __ballot_sync(0xffffffffu, tk >= 0);
       if (lane == 0) {
-        mbar_wait(&ms->qdo_empty[s], (k & 1) ^ 1);
-        mbar_expect_tx(&ms->qdo_full[s], __popc(have) * h * 256);
+        mbar_wait(&ms->qdo_empty[st], (k & 1) ^ 1);
+        mbar_expect_tx(&ms->qdo_full[st], __popc(have) * h * 256);
       }
       __syncwarp();
       if (tk >= 0) {
-        tma_load_4d(smem + BwSmem::q + s * kBwTile + lane * h * 128, &tmQ, &ms->qdo_full[s], 0, 0, g, tk);
-        tma_load_4d(smem + BwSmem::dO + s * kBwTile + lane * h * 128, &tmdO, &ms->qdo_full[s], 0, 0, g, tk);
+        tma_load_4d(smem + BwSmem::q + st * kBwTile + lane * h * 128, &tmQ, &ms->qdo_full[st], 0, 0, g, tk);
+        tma_load_4d(smem + BwSmem::dO + st * kBwTile + lane * h * 128, &tmdO, &ms->qdo_full[st], 0, 0, g, tk);
       }
       __syncwarp();
       tk = tk_next;
@@ -215,12 +236,12 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       constexpr uint32_t idesc_kv = make_idesc_f16(64, 64, TcType<T>::fmt, 1, 1);    // dV += P~^T.dO, dK += dS~^T.Q
       const uint32_t kb = smem_u32(smem + BwSmem::k), vb = smem_u32(smem + BwSmem::v);
       auto issue_sdp = [&](int i) {
-        const int s = i & 1, k = i >> 1;
-        mbar_wait(&ms->qdo_full[s], k & 1);
+        const int s = i & 1, k = i >> 1, st = i % kBwQS;
+        mbar_wait(&ms->qdo_full[st], (i / kBwQS) & 1);
         mbar_wait(&ms->s_empty[s], (k & 1) ^ 1);
         tc_fence_after();
-        const uint32_t qb = smem_u32(smem + BwSmem::q + s * kBwTile);
-        const uint32_t ob = smem_u32(smem + BwSmem::dO + s * kBwTile);
+        const uint32_t qb = smem_u32(smem + BwSmem::q + st * kBwTile);
+        const uint32_t ob = smem_u32(smem + BwSmem::dO + st * kBwTile);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           umma_f16(tmem + kColS + s * 64, make_smem_desc(qb + kk * 32, 16, 1024, kSwizzle128B),
@@ -232,12 +253,12 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         umma_commit(&ms->s_full[s]);
       };
       auto issue_grads = [&](int i) {
-        const int s = i & 1, k = i >> 1;
+        const int s = i & 1, k = i >> 1, st = i % kBwQS;
         mbar_wait(&ms->pds_full[s], k & 1);
         mbar_wait(&ms->dq_empty[s], (k & 1) ^ 1);
         tc_fence_after();
-        const uint32_t qb = smem_u32(smem + BwSmem::q + s * kBwTile);
-        const uint32_t ob = smem_u32(smem + BwSmem::dO + s * kBwTile);
+        const uint32_t qb = smem_u32(smem + BwSmem::q + st * kBwTile);
+        const uint32_t ob = smem_u32(smem + BwSmem::dO + st * kBwTile);
         const uint32_t pb = smem_u32(smem + BwSmem::p + s * kBwTile);
         const uint32_t sb = smem_u32(smem + BwSmem::ds + s * kBwTile);
 #pragma unroll
@@ -254,7 +275,7 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                    make_smem_desc(kb + kk * 2048, 8192, 1024, kSwizzle128B), idesc_dq, kk > 0);
         umma_commit(&ms->dq_full[s]);
         umma_commit(&ms->pds_empty[s]);
-        umma_commit(&ms->qdo_empty[s]);
+        umma_commit(&ms->qdo_empty[st]);
       };
       mbar_wait(&ms->kv_full, 0);
       issue_sdp(0);
@@ -383,16 +404,21 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ms->dq_empty[s]);
-      if (tk >= 0) {
-        float* dst = a.dQ + (((size_t)tk * dm.G + g) * h + head) * 64;
+      if (tk >= 0) {  // this thread's staging row is its own: no cross-thread synchronisation
+        bw_bulk_wait_read0();  // the previous tile's reduction has read the row
+        uint4* stage = reinterpret_cast<uint4*>(smem + BwSmem::dq + r * kBwDqRow);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          bw_red4(dst + q * 4, va[q * 4], va[q * 4 + 1], va[q * 4 + 2], va[q * 4 + 3]);
-          bw_red4(dst + 32 + q * 4, vb2[q * 4], vb2[q * 4 + 1], vb2[q * 4 + 2], vb2[q * 4 + 3]);
+          stage[q] = make_uint4(va[q * 4], va[q * 4 + 1], va[q * 4 + 2], va[q * 4 + 3]);
+          stage[8 + q] = make_uint4(vb2[q * 4], vb2[q * 4 + 1], vb2[q * 4 + 2], vb2[q * 4 + 3]);
         }
+        fence_proxy_async();
+        bw_bulk_red_add_f32(a.dQ + (((size_t)tk * dm.G + g) * h + head) * 64, stage, 256);
+        bw_bulk_commit();
       }
       tk = tk_next;
     }
+    bw_bulk_wait0();
   }
 
   // ---- epilogue: dK (warps 0-3) and dV (warps 4-7) of the tile -> global, M=64 layout: key r on lane 32*(r/16) + r%16 ----

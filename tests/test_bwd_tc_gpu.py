@@ -19,7 +19,9 @@ def _ops():
 
 
 def _rel(a, b):
-    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+    # relative to the reference norm; a reference that is exactly zero (w = 1: dS = P o (dP - D) = 0) is compared in
+    # absolute terms instead (rms error <= tol * 1e-4)
+    return float((a - b).norm() / b.norm().clamp_min(1e-4 * b.numel() ** 0.5))
 
 
 def _case(B, S, G, h, l, d, seed, dtype, S_kv=None):
