@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "select.cuh"
 #include "gate.cuh"
+#include <string.h>
 #include "launchers.h"
 
 namespace nsa {
@@ -693,11 +694,175 @@ gate_bwd_kernel(nsa_dims_t dm, const void* __restrict__ Q, nsa_gate_params_t gp,
   for (int i = threadIdx.x; i < 3; i += blockDim.x) atomicAdd(d_fc2_b + i, a_b2[i]);
 }
 
+// Fast gate backward for the training shapes (16-bit Q, Dk = 64, hidden <= 32): lane u owns hidden unit u and keeps its row
+// of d_fc1_w (64 values) and its d_fc1_b / d_fc2_w entries in registers over all rows of the warp, so a row costs ~200
+// instructions per lane instead of 2048 shared-memory atomics; weights sit in shared memory in both orientations.  Partial
+// sums are folded per CTA in shared memory and flushed with one atomicAdd per parameter per CTA.
+constexpr int kGbWarps = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(kGbWarps * 32)
+gate_bwd_fast_kernel(nsa_dims_t dm, const T* __restrict__ Q, nsa_gate_params_t gp, const float* __restrict__ dgates,
+                     float* __restrict__ dQ, float* d_fc1_w, float* d_fc1_b, float* d_fc2_w, float* d_fc2_b) {
+  constexpr int DK = 64;
+  extern __shared__ float smem[];
+  const int H = dm.gate_hidden, h = dm.h;
+  float* w1 = smem;                 // [H][DK]
+  float* w1t = w1 + H * DK;         // [DK][H]
+  float* w2 = w1t + DK * H;         // [3][H]
+  float* acc_s = w2 + 3 * H;        // [H*DK + H + 3*H + 4] CTA accumulators
+  float* per_warp = acc_s + H * DK + 4 * H + 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* qgp = per_warp + warp * (DK + 32);  // [DK]
+  float* dpre_s = qgp + DK;                  // [32]
+  for (int i = threadIdx.x; i < H * DK; i += blockDim.x) {
+    const float v = gp.fc1_w[i];
+    w1[i] = v;
+    w1t[(i % DK) * H + i / DK] = v;
+  }
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) w2[i] = gp.fc2_w[i];
+  for (int i = threadIdx.x; i < H * DK + 4 * H + 4; i += blockDim.x) acc_s[i] = 0.f;
+  __syncthreads();
+  const bool unit = lane < H;
+  const float b1 = unit && gp.fc1_b ? gp.fc1_b[lane] : 0.f;
+  const float b2[3] = {gp.fc2_b ? gp.fc2_b[0] : 0.f, gp.fc2_b ? gp.fc2_b[1] : 0.f, gp.fc2_b ? gp.fc2_b[2] : 0.f};
+  const float w2u[3] = {unit ? w2[lane] : 0.f, unit ? w2[H + lane] : 0.f, unit ? w2[2 * H + lane] : 0.f};
+  float a_w1[DK], a_b1 = 0.f, a_w2[3] = {0.f, 0.f, 0.f}, a_b2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < DK; ++k) a_w1[k] = 0.f;
+  const int n_rows = dm.B * dm.S * dm.G;
+  const float inv_tau = 1.0f / fmaxf(dm.gate_tau, 1e-6f), inv_h = 1.0f / (float)h;
+  // the next row's Q heads and dgates are requested before the current row is processed (a row is a chain of dependent
+  // steps; without the prefetch every row also pays a global-memory round trip)
+  constexpr int HM = 8;
+  uint32_t qn[HM];
+  float dn0 = 0.f, dn1 = 0.f, dn2 = 0.f;
+  auto fetch = [&](int row) {
+    if (row < n_rows) {
+#pragma unroll
+      for (int hh = 0; hh < HM; ++hh)
+        qn[hh] = hh < h ? reinterpret_cast<const uint32_t*>(Q + ((size_t)row * h + hh) * DK)[lane] : 0u;
+      dn0 = dgates[(size_t)row * 3];
+      dn1 = dgates[(size_t)row * 3 + 1];
+      dn2 = dgates[(size_t)row * 3 + 2];
+    }
+  };
+  fetch(blockIdx.x * kGbWarps + warp);
+  for (int row = blockIdx.x * kGbWarps + warp; row < n_rows; row += gridDim.x * kGbWarps) {
+    // q_gp = mean over heads; lane owns k = 2*lane, 2*lane+1 (one 4-byte load per head)
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int hh = 0; hh < HM; ++hh) {
+      const uint32_t u = qn[hh];  // zero bits for hh >= h: +0.0 in both 16-bit formats
+      T lo, hi;
+      memcpy(&lo, &u, 2);
+      memcpy(&hi, reinterpret_cast<const char*>(&u) + 2, 2);
+      q0 += (float)lo;
+      q1 += (float)hi;
+    }
+    const float dp0 = dn0, dp1 = dn1, dp2 = dn2;
+    fetch(row + gridDim.x * kGbWarps);
+    __syncwarp();
+    reinterpret_cast<float2*>(qgp)[lane] = make_float2(q0 * inv_h, q1 * inv_h);
+    __syncwarp();
+    float pre = b1;
+    if (unit) {
+#pragma unroll
+      for (int k = 0; k < DK; k += 4) {
+        const float4 qv = *reinterpret_cast<const float4*>(qgp + k);
+        pre = fmaf(w1t[k * H + lane], qv.x, pre);
+        pre = fmaf(w1t[(k + 1) * H + lane], qv.y, pre);
+        pre = fmaf(w1t[(k + 2) * H + lane], qv.z, pre);
+        pre = fmaf(w1t[(k + 3) * H + lane], qv.w, pre);
+      }
+    }
+    const float sg = 1.0f / (1.0f + expf(-pre));
+    const float xs = unit ? pre * sg : 0.f;
+    float g[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[c] = (warp_sum(w2u[c] * xs) + b2[c]) * inv_tau;
+    const float mx = fmaxf(g[0], fmaxf(g[1], g[2]));
+    const int am = g[0] >= g[1] ? (g[0] >= g[2] ? 0 : 2) : (g[1] >= g[2] ? 1 : 2);
+    const float second = am == 0 ? fmaxf(g[1], g[2]) : (am == 1 ? fmaxf(g[0], g[2]) : fmaxf(g[0], g[1]));
+    if (mx - second > 50.0f) continue;  // hard one-hot: constant, no gradient (nsa_attention.py:74-81); warp-uniform
+    const float e0 = expf(g[0] - mx), e1 = expf(g[1] - mx), e2 = expf(g[2] - mx);
+    const float inv = 1.0f / (e0 + e1 + e2);
+    const float p[3] = {e0 * inv, e1 * inv, e2 * inv};
+    const float dot = p[0] * dp0 + p[1] * dp1 + p[2] * dp2;
+    const float dg[3] = {p[0] * (dp0 - dot) * inv_tau, p[1] * (dp1 - dot) * inv_tau, p[2] * (dp2 - dot) * inv_tau};
+    if (lane < 3) a_b2 += lane == 0 ? dg[0] : (lane == 1 ? dg[1] : dg[2]);
+    float dx = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      a_w2[c] = fmaf(dg[c], xs, a_w2[c]);
+      dx = fmaf(w2u[c], dg[c], dx);
+    }
+    const float d = unit ? dx * sg * (1.0f + pre * (1.0f - sg)) : 0.f;  // d silu
+    a_b1 += d;
+#pragma unroll
+    for (int k = 0; k < DK; k += 4) {
+      const float4 qv = *reinterpret_cast<const float4*>(qgp + k);
+      a_w1[k] = fmaf(d, qv.x, a_w1[k]);
+      a_w1[k + 1] = fmaf(d, qv.y, a_w1[k + 1]);
+      a_w1[k + 2] = fmaf(d, qv.z, a_w1[k + 2]);
+      a_w1[k + 3] = fmaf(d, qv.w, a_w1[k + 3]);
+    }
+    if (dQ) {
+      dpre_s[lane] = d;
+      __syncwarp();
+      float dq0 = 0.f, dq1 = 0.f;
+      for (int u = 0; u < H; ++u) {
+        const float2 wv = reinterpret_cast<const float2*>(w1 + u * DK)[lane];
+        const float du = dpre_s[u];
+        dq0 = fmaf(wv.x, du, dq0);
+        dq1 = fmaf(wv.y, du, dq1);
+      }
+      dq0 *= inv_h;
+      dq1 *= inv_h;
+      for (int hh = 0; hh < h; ++hh) {  // row owned by this warp
+        float2* dst = reinterpret_cast<float2*>(dQ + ((size_t)row * h + hh) * DK) + lane;
+        float2 v = *dst;
+        v.x += dq0;
+        v.y += dq1;
+        *dst = v;
+      }
+    }
+  }
+  if (unit) {
+#pragma unroll
+    for (int k = 0; k < DK; ++k) atomicAdd(acc_s + k * H + lane, a_w1[k]);  // [DK][H]: lanes on distinct banks
+    atomicAdd(acc_s + H * DK + lane, a_b1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) atomicAdd(acc_s + H * DK + H + c * H + lane, a_w2[c]);
+  }
+  if (lane < 3) atomicAdd(acc_s + H * DK + 4 * H + lane, a_b2);
+  __syncthreads();
+  for (int i = threadIdx.x; i < H * DK; i += blockDim.x) atomicAdd(d_fc1_w + i, acc_s[(i % DK) * H + i / DK]);
+  for (int i = threadIdx.x; i < H; i += blockDim.x) atomicAdd(d_fc1_b + i, acc_s[H * DK + i]);
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) atomicAdd(d_fc2_w + i, acc_s[H * DK + H + i]);
+  for (int i = threadIdx.x; i < 3; i += blockDim.x) atomicAdd(d_fc2_b + i, acc_s[H * DK + 4 * H + i]);
+}
+
+template <typename T>
+static int launch_gate_bwd_fast(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t& gp, const float* dgates, float* dQ,
+                                float* d_fc1_w, float* d_fc1_b, float* d_fc2_w, float* d_fc2_b, cudaStream_t stream) {
+  const int H = dm.gate_hidden, n_rows = dm.B * dm.S * dm.G;
+  const size_t smem = ((size_t)3 * H * 64 + 3 * H + 4 * H + 4 + (size_t)kGbWarps * (64 + 32)) * sizeof(float);
+  int blocks = ceil_div(n_rows, kGbWarps * 4);
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  gate_bwd_fast_kernel<T><<<blocks, kGbWarps * 32, smem, stream>>>(dm, (const T*)Q, gp, dgates, dQ, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b);
+  return check_launch("gate_bwd_fast_kernel");
+}
+
 int launch_gate_bwd(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t& gp, const float* dgates, float* dQ,
                     float* d_fc1_w, float* d_fc1_b, float* d_fc2_w, float* d_fc2_b, cudaStream_t stream) {
   const int n_rows = dm.B * dm.S * dm.G;
   if (n_rows == 0 || dm.gate_mode != NSA_GATE_MLP) return NSA_OK;
   const int H = dm.gate_hidden, Dk = dm.Dk;
+  if (Dk == 64 && H >= 1 && H <= 32 && dm.h <= 8 && dm.dtype != NSA_F32) {
+    if (dm.dtype == NSA_BF16) return launch_gate_bwd_fast<__nv_bfloat16>(dm, Q, gp, dgates, dQ, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b, stream);
+    return launch_gate_bwd_fast<__half>(dm, Q, gp, dgates, dQ, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b, stream);
+  }
   size_t smem = ((size_t)H * Dk + H + 3 * H + 4 + (size_t)kAttnWarps * (Dk + 3 * H)) * sizeof(float);
   NSA_REQUIRE(smem <= 200 * 1024, "gate bwd: hidden=%d Dk=%d needs %zu B of shared memory", H, Dk, smem);
   if (smem > 48 * 1024) {

@@ -12,7 +12,8 @@
 //   win : tile j = cache rows [64j, 64j+64)        queries in [first key, last key + w - 1], masked to [t-w+1, t]
 //   sel : tile j = selection block j               queries from the device-built inverted index (tc_sel2.cuh), masked to the
 //                                                  clamped block length
-// An M-tile is 128 rows = TOK queries x h heads; Q and dO rows of one query arrive as one TMA box each (hardware swizzle).
+// An M-tile is 128 rows = TOK queries x h heads; its Q and dO rows arrive by TMA with hardware swizzle: one box per tile
+// for cmp / win (consecutive tokens), one box per query for sel.
 // Per (M-tile, key tile) pair:  S, dP (M=128, N=64) -> softmax warps form P~ = g.P and dS~ = g.scale.P o (dP - D) as 16-bit
 // swizzled tiles -> dV += P~^T.dO, dK += dS~^T.Q (M=64, N=64, K=128; A and B both MN-major), dQ_t = dS~.K (M=128, N=64)
 // -> four drain warps stage dQ_t as fp32 rows in shared memory and add each row into the fp32 dQ with one bulk
@@ -22,7 +23,8 @@
 // softmax warps are on pair i and the drain warps on i-1.  The binding resource is shared-memory bandwidth (136 KB of MMA
 // operand reads + 128 KB of tile writes/reads per pair).
 // g = gate weight of the branch for the row (the gated combine O = sum_b g_b O_b is folded in: dO_b = g_b dO).
-// Warp roles: 0-3 softmax, 4-7 dQ drain, 8 TMA producer, 9 MMA issuer; the epilogue (dK, dV -> global) uses warps 0-7.
+// Warp roles: 0-7 softmax (two per scheduler, each half of the key columns), 8-11 dQ drain, 12 TMA producer, 13 MMA issuer;
+// the epilogue (dK, dV -> global) uses warps 0-7.
 #include <stdlib.h>
 #include <string.h>
 
@@ -37,6 +39,8 @@ constexpr int kBwTile = 128 * 128;  // bytes: 128 rows x 64 x 2 B
 
 constexpr int kBwQS = 3;            // Q/dO stages
 constexpr int kBwDqRow = 256 + 16;  // bytes per staged dQ row: 64 fp32 + 16 B so that 16-byte stores of a warp spread over banks
+
+constexpr int kBwThreads = 14 * 32;  // warps 0-7 softmax, 8-11 dQ drain, 12 TMA producer, 13 MMA issuer
 
 struct BwSmem {
   static constexpr int k = 0;                       // K tile 8 KB
@@ -69,6 +73,7 @@ struct BwKArgs {
   int NB;              // sel: 64-key blocks per slab
   int TOK, R;          // queries per M-tile; M-tiles per CTA (cmp / win)
   int rows_present, cap;
+  long long* dbg;      // -DNSA_BWD_DBG: timeline of one CTA (tag, tile, clock) for tools/dbg_bwd.py
 };
 
 __device__ __forceinline__ float bw_ex2(float x) {
@@ -117,13 +122,23 @@ __device__ __forceinline__ void bw_row_range(const nsa_dims_t& dm, int branch, i
   }
 }
 
+#ifdef NSA_BWD_DBG  // one slot per (tag, tile): plain stores, no atomics, so the probes cost a clock read each
+#define BDBG(tag, it)                                                                                  \
+  do {                                                                                                 \
+    if (a.dbg && blockIdx.x == 0 && blockIdx.y == gridDim.y / 2 && blockIdx.z == 0 && (it) < 100)     \
+      a.dbg[(tag) * 100 + (it)] = clock64();                                                           \
+  } while (0)
+#else
+#define BDBG(tag, it) do { } while (0)
+#endif
+
 struct BwRow {
   int klo, khi;        // valid key columns of the tile for this row ([0,0) = row contributes nothing)
-  float lse2, dl, gt;  // lse in log2 units, D, gate weight
+  float lse, dl, gt;   // natural-log normaliser, D, gate weight
 };
 
 template <typename T, int BR>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(kBwThreads, 1)
 bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
               const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, nsa_dims_t dm, BwKArgs a) {
   // ---- work item: (slab bg, key tile j, M-tiles [tile0, tile0 + n)) -----------------------------------------------
@@ -183,8 +198,8 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&ms->s_full[s], 1);
-      mbar_init(&ms->s_empty[s], 4);
-      mbar_init(&ms->pds_full[s], 4);
+      mbar_init(&ms->s_empty[s], 8);
+      mbar_init(&ms->pds_full[s], 8);
       mbar_init(&ms->pds_empty[s], 1);
       mbar_init(&ms->dq_full[s], 1);
       mbar_init(&ms->dq_empty[s], 4);
@@ -204,105 +219,135 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   // TMEM columns: S[s] = s*64, dP[s] = 128 + s*64, dQ_t[s] = 256 + s*64, dK = 384 (M=64), dV = 448 (M=64)
   constexpr uint32_t kColS = 0, kColDP = 128, kColDQ = 256, kColDK = 384, kColDV = 448;
 
-  if (warp == 8) {
-    // ===== TMA producer: the key tile once, then one Q box and one dO box per query of every M-tile ==============
+  if (warp == 12) {
+    // ===== TMA producer: the key tile once, then the Q and dO rows of every M-tile.  cmp / win: the queries of a tile are
+    // consecutive tokens -> one box (64, h, 1, TOK) per tensor; sel: one box (64, h, 1, 1) per query and tensor (small boxes
+    // cost ~70 cycles each in the TMA unit, which bounds the sel walk; a 16-byte cp.async gather was 4x slower still). ====
     if (lane == 0) {
       mbar_expect_tx(&ms->kv_full, 2 * 8192);
       tma_load_3d(smem + BwSmem::k, &tmK, &ms->kv_full, 0, j * 64, bg);
       tma_load_3d(smem + BwSmem::v, &tmV, &ms->kv_full, 0, j * 64, bg);
     }
-    int tk = get_tk(0, lane);
-    for (int i = 0; i < n; ++i) {
-      const int st = i % kBwQS, k = i / kBwQS;
-      const int tk_next = get_tk(i + 1, lane);
-      const unsigned have = __ballot_sync(0xffffffffu, tk >= 0);
+    if (BR != 1) {
       if (lane == 0) {
-        mbar_wait(&ms->qdo_empty[st], (k & 1) ^ 1);
-        mbar_expect_tx(&ms->qdo_full[st], __popc(have) * h * 256);
+        for (int i = 0; i < n; ++i) {
+          const int st = i % kBwQS, k = i / kBwQS;
+          BDBG(1, i);
+          mbar_wait(&ms->qdo_empty[st], (k & 1) ^ 1);
+          BDBG(2, i);
+          mbar_expect_tx(&ms->qdo_full[st], TOK * h * 256);
+          const int tok0 = b * dm.S + s_lo + (tile0 + i) * TOK;  // rows past the sequence are loaded (or zero-filled) and masked
+          tma_load_4d(smem + BwSmem::q + st * kBwTile, &tmQ, &ms->qdo_full[st], 0, 0, g, tok0);
+          tma_load_4d(smem + BwSmem::dO + st * kBwTile, &tmdO, &ms->qdo_full[st], 0, 0, g, tok0);
+        }
       }
-      __syncwarp();
-      if (tk >= 0) {
-        tma_load_4d(smem + BwSmem::q + st * kBwTile + lane * h * 128, &tmQ, &ms->qdo_full[st], 0, 0, g, tk);
-        tma_load_4d(smem + BwSmem::dO + st * kBwTile + lane * h * 128, &tmdO, &ms->qdo_full[st], 0, 0, g, tk);
-      }
-      __syncwarp();
-      tk = tk_next;
-    }
-  } else if (warp == 9) {
-    // ===== MMA issuer ===========================================================================================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_f16(128, 64, TcType<T>::fmt, 0, 0);    // S = Q.K^T, dP = dO.V^T
-      constexpr uint32_t idesc_dq = make_idesc_f16(128, 64, TcType<T>::fmt, 0, 1);   // dQ_t = dS~.K   (K: MN-major B)
-      constexpr uint32_t idesc_kv = make_idesc_f16(64, 64, TcType<T>::fmt, 1, 1);    // dV += P~^T.dO, dK += dS~^T.Q
-      const uint32_t kb = smem_u32(smem + BwSmem::k), vb = smem_u32(smem + BwSmem::v);
-      auto issue_sdp = [&](int i) {
-        const int s = i & 1, k = i >> 1, st = i % kBwQS;
-        mbar_wait(&ms->qdo_full[st], (i / kBwQS) & 1);
-        mbar_wait(&ms->s_empty[s], (k & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t qb = smem_u32(smem + BwSmem::q + st * kBwTile);
-        const uint32_t ob = smem_u32(smem + BwSmem::dO + st * kBwTile);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_f16(tmem + kColS + s * 64, make_smem_desc(qb + kk * 32, 16, 1024, kSwizzle128B),
-                   make_smem_desc(kb + kk * 32, 16, 1024, kSwizzle128B), idesc_s, kk > 0);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_f16(tmem + kColDP + s * 64, make_smem_desc(ob + kk * 32, 16, 1024, kSwizzle128B),
-                   make_smem_desc(vb + kk * 32, 16, 1024, kSwizzle128B), idesc_s, kk > 0);
-        umma_commit(&ms->s_full[s]);
-      };
-      auto issue_grads = [&](int i) {
-        const int s = i & 1, k = i >> 1, st = i % kBwQS;
-        mbar_wait(&ms->pds_full[s], k & 1);
-        mbar_wait(&ms->dq_empty[s], (k & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t qb = smem_u32(smem + BwSmem::q + st * kBwTile);
-        const uint32_t ob = smem_u32(smem + BwSmem::dO + st * kBwTile);
-        const uint32_t pb = smem_u32(smem + BwSmem::p + s * kBwTile);
-        const uint32_t sb = smem_u32(smem + BwSmem::ds + s * kBwTile);
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)  // contraction over the 128 rows, 16 per step
-          umma_f16(tmem + kColDV, make_smem_desc(pb + kk * 2048, 8192, 1024, kSwizzle128B),
-                   make_smem_desc(ob + kk * 2048, 8192, 1024, kSwizzle128B), idesc_kv, (i > 0 || kk > 0) ? 1u : 0u);
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_f16(tmem + kColDK, make_smem_desc(sb + kk * 2048, 8192, 1024, kSwizzle128B),
-                   make_smem_desc(qb + kk * 2048, 8192, 1024, kSwizzle128B), idesc_kv, (i > 0 || kk > 0) ? 1u : 0u);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)  // contraction over the 64 keys
-          umma_f16(tmem + kColDQ + s * 64, make_smem_desc(sb + kk * 32, 16, 1024, kSwizzle128B),
-                   make_smem_desc(kb + kk * 2048, 8192, 1024, kSwizzle128B), idesc_dq, kk > 0);
-        umma_commit(&ms->dq_full[s]);
-        umma_commit(&ms->pds_empty[s]);
-        umma_commit(&ms->qdo_empty[st]);
-      };
-      mbar_wait(&ms->kv_full, 0);
-      issue_sdp(0);
-      if (n > 1) issue_sdp(1);
+    } else {
+      int tk = get_tk(0, lane);
       for (int i = 0; i < n; ++i) {
-        issue_grads(i);
-        if (i + 2 < n) issue_sdp(i + 2);
+        const int st = i % kBwQS, k = i / kBwQS;
+        const int tk_next = get_tk(i + 1, lane);
+        const unsigned have = __ballot_sync(0xffffffffu, tk >= 0);
+        if (lane == 0) {
+          mbar_wait(&ms->qdo_empty[st], (k & 1) ^ 1);
+          mbar_expect_tx(&ms->qdo_full[st], __popc(have) * h * 256);
+        }
+        __syncwarp();
+        if (tk >= 0) {
+          tma_load_4d(smem + BwSmem::q + st * kBwTile + lane * h * 128, &tmQ, &ms->qdo_full[st], 0, 0, g, tk);
+          tma_load_4d(smem + BwSmem::dO + st * kBwTile + lane * h * 128, &tmdO, &ms->qdo_full[st], 0, 0, g, tk);
+        }
+        __syncwarp();
+        tk = tk_next;
       }
-      umma_commit(&ms->fin);
     }
-  } else if (warp < 4) {
-    // ===== softmax warps: thread = TMEM lane = row (query, head) ==================================================
-    const int r = tid;
+  } else if (warp == 13) {
+    // ===== MMA issuer: the whole warp runs this code (warp-uniform control flow and operands, so the descriptors live in
+    // uniform registers and each tcgen05.mma costs a couple of uniform adds); one elected lane issues.  Building every
+    // descriptor from scratch under `if (lane == 0)` cost ~80 cycles per MMA and bounded the walk at ~3000 cycles per pair.
+    constexpr uint32_t idesc_s = make_idesc_f16(128, 64, TcType<T>::fmt, 0, 0);    // S = Q.K^T, dP = dO.V^T
+    constexpr uint32_t idesc_dq = make_idesc_f16(128, 64, TcType<T>::fmt, 0, 1);   // dQ_t = dS~.K   (K: MN-major B)
+    constexpr uint32_t idesc_kv = make_idesc_f16(64, 64, TcType<T>::fmt, 1, 1);    // dV += P~^T.dO, dK += dS~^T.Q
+    // descriptor words: lo = addr>>4 | (LBO>>4)<<16, hi = SBO>>4 | version | swizzle; K-major tiles use LBO 16 and advance
+    // 32 B per 16-element k-step, MN-major tiles use LBO 8192 and advance 2048 B (16 rows) per k-step
+    constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | ((uint32_t)kSwizzle128B << 29);
+    constexpr uint32_t kLoK = (16u >> 4) << 16, kLoMN = (8192u >> 4) << 16;
+    constexpr uint32_t kStepK = 32u >> 4, kStepMN = 2048u >> 4;
+    const uint32_t smem0 = smem_u32(smem) >> 4;
+    const uint32_t k_k = (smem0 + (BwSmem::k >> 4)) | kLoK, k_mn = (smem0 + (BwSmem::k >> 4)) | kLoMN;
+    const uint32_t v_k = (smem0 + (BwSmem::v >> 4)) | kLoK;
+    auto issue_sdp = [&](int i) {
+      const int s = i & 1, k = i >> 1, st = i % kBwQS;
+      if (lane == 0) BDBG(10, i);
+      mbar_wait(&ms->qdo_full[st], (i / kBwQS) & 1);
+      mbar_wait(&ms->s_empty[s], (k & 1) ^ 1);
+      if (lane == 0) BDBG(12, i);
+      tc_fence_after();
+      const uint32_t q_k = (smem0 + ((BwSmem::q + st * kBwTile) >> 4)) | kLoK;
+      const uint32_t o_k = (smem0 + ((BwSmem::dO + st * kBwTile) >> 4)) | kLoK;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        umma_f16_elect(tmem + kColS + s * 64, q_k + kk * kStepK, kHi, k_k + kk * kStepK, kHi, idesc_s, kk > 0);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        umma_f16_elect(tmem + kColDP + s * 64, o_k + kk * kStepK, kHi, v_k + kk * kStepK, kHi, idesc_s, kk > 0);
+      umma_commit_elect(&ms->s_full[s]);
+    };
+    auto issue_grads = [&](int i) {
+      const int s = i & 1, k = i >> 1, st = i % kBwQS;
+      if (lane == 0) BDBG(13, i);
+      mbar_wait(&ms->pds_full[s], k & 1);
+      if (lane == 0) BDBG(14, i);
+      mbar_wait(&ms->dq_empty[s], (k & 1) ^ 1);
+      if (lane == 0) BDBG(15, i);
+      tc_fence_after();
+      const uint32_t q_mn = (smem0 + ((BwSmem::q + st * kBwTile) >> 4)) | kLoMN;
+      const uint32_t o_mn = (smem0 + ((BwSmem::dO + st * kBwTile) >> 4)) | kLoMN;
+      const uint32_t p_mn = (smem0 + ((BwSmem::p + s * kBwTile) >> 4)) | kLoMN;
+      const uint32_t s_mn = (smem0 + ((BwSmem::ds + s * kBwTile) >> 4)) | kLoMN;
+      const uint32_t s_k = (smem0 + ((BwSmem::ds + s * kBwTile) >> 4)) | kLoK;
+      const uint32_t acc0 = i > 0 ? 1u : 0u;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)  // contraction over the 128 rows, 16 per step
+        umma_f16_elect(tmem + kColDV, p_mn + kk * kStepMN, kHi, o_mn + kk * kStepMN, kHi, idesc_kv, kk > 0 ? 1u : acc0);
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)
+        umma_f16_elect(tmem + kColDK, s_mn + kk * kStepMN, kHi, q_mn + kk * kStepMN, kHi, idesc_kv, kk > 0 ? 1u : acc0);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)  // contraction over the 64 keys
+        umma_f16_elect(tmem + kColDQ + s * 64, s_k + kk * kStepK, kHi, k_mn + kk * kStepMN, kHi, idesc_dq, kk > 0);
+      umma_commit_elect(&ms->dq_full[s]);
+      umma_commit_elect(&ms->pds_empty[s]);
+      umma_commit_elect(&ms->qdo_empty[st]);
+      if (lane == 0) BDBG(16, i);
+    };
+    mbar_wait(&ms->kv_full, 0);
+    issue_sdp(0);
+    if (n > 1) issue_sdp(1);
+    for (int i = 0; i < n; ++i) {
+      issue_grads(i);
+      if (i + 2 < n) issue_sdp(i + 2);
+    }
+    umma_commit_elect(&ms->fin);
+  } else if (warp < 8) {
+    // ===== softmax warps: thread = TMEM lane = row (query, head); warps 0-3 take key columns 0-31, warps 4-7 columns 32-63
+    // (two warps per scheduler: one warp alone issues ~1 instruction per 2-3 cycles, which bounded the first version) =====
+    const int r = tid & 127, hf = warp >> 2;
     const int tok_l = r / h, head = r - tok_l * h;
     const float c = dm.scale * kLog2e;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const int sw = r & 7;
     auto get_hi = [&](int i) -> int {
       if (BR != 1 || i >= n || tok_l >= TOK) return 0;
       return a.hi[(size_t)(tile0 + i) * TOK + tok_l];
     };
+    // Row data as loaded; nothing here is looked at until the tile is processed, so the loads of tile i+1 stay in flight
+    // while tile i is computed (two-level prefetch: the query of tile i+2 is requested at the same time).
     auto meta = [&](int tk, int hi_blk) -> BwRow {
       BwRow m;
-      m.klo = 0; m.khi = 0; m.lse2 = 0.f; m.dl = 0.f; m.gt = 0.f;
+      m.klo = 0; m.khi = 0; m.lse = -INFINITY; m.dl = 0.f; m.gt = 0.f;
       if (tk >= 0) {
         const size_t grow = ((size_t)tk * dm.G + g) * h + head;
-        const float lse = a.lse[grow];
+        m.lse = a.lse[grow];
         m.dl = a.delta[grow];
         m.gt = a.gates ? a.gates[((size_t)tk * dm.G + g) * 3 + BR] : 1.0f;
         if (BR == 1) {
@@ -315,12 +360,9 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           m.klo = lo < 0 ? 0 : (lo > 64 ? 64 : lo);
           m.khi = hi < 0 ? 0 : (hi > 64 ? 64 : hi);
         }
-        if (!(lse > -INFINITY) || m.khi <= m.klo) { m.klo = 0; m.khi = 0; }
-        m.lse2 = lse > -INFINITY ? lse * kLog2e : 0.f;
       }
       return m;
     };
-    // two-level prefetch: the query of tile i+2 and the row data of tile i+1 are requested while tile i is processed
     BwRow cur = meta(get_tk(0, tok_l), get_hi(0));
     int tk_n = get_tk(1, tok_l), hi_n = get_hi(1);
     for (int i = 0; i < n; ++i) {
@@ -328,53 +370,54 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       const BwRow nxt = meta(tk_n, hi_n);
       tk_n = get_tk(i + 2, tok_l);
       hi_n = get_hi(i + 2);
-      const float gs = cur.gt * dm.scale;
-      const bool full = __all_sync(0xffffffffu, cur.klo == 0 && cur.khi == 64);
+      // P~ = g.exp2(S.c - lse2) = exp2(S.c - (lse2 - log2 g));  dS~ = P~.(dP.scale - D.scale)
+      const bool live = cur.lse > -INFINITY && cur.gt > 0.f && cur.khi > cur.klo;
+      const int klo = live ? cur.klo : 0, khi = live ? cur.khi : 0;
+      const float e0 = live ? cur.lse * kLog2e - __log2f(cur.gt) : 0.f;
+      const float dls = cur.dl * dm.scale;
+      const bool full = __all_sync(0xffffffffu, klo == 0 && khi == 64);
       uint8_t* prow = smem + BwSmem::p + s * kBwTile + r * 128;
       uint8_t* srow = smem + BwSmem::ds + s * kBwTile + r * 128;
+      if (tid == 0) BDBG(20, i);
       mbar_wait(&ms->s_full[s], k & 1);
+      if (tid == 0) BDBG(21, i);
       mbar_wait(&ms->pds_empty[s], (k & 1) ^ 1);  // the gradient MMAs of tile i-2 have read these P~/dS~ buffers
+      if (tid == 0) BDBG(22, i);
       tc_fence_after();
-#pragma unroll 1
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t sa[32], da[32];
-        tmem_ld32(tmem + lane_off + kColS + s * 64 + hf * 32, sa);
-        tmem_ld32(tmem + lane_off + kColDP + s * 64 + hf * 32, da);
-        bw_ld_wait32(sa);
-        bw_ld_wait32(da);
-        if (full) {
+      uint32_t sa[32], da[32];
+      tmem_ld32(tmem + lane_off + kColS + s * 64 + hf * 32, sa);
+      tmem_ld32(tmem + lane_off + kColDP + s * 64 + hf * 32, da);
+      bw_ld_wait32(sa);
+      bw_ld_wait32(da);
+      if (full) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) sa[e] = __float_as_uint(bw_ex2(fmaf(__uint_as_float(sa[e]), c, -cur.lse2)));
+        for (int e = 0; e < 32; ++e) sa[e] = __float_as_uint(bw_ex2(fmaf(__uint_as_float(sa[e]), c, -e0)));
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float p = __uint_as_float(sa[e]);
-            da[e] = __float_as_uint(p * (__uint_as_float(da[e]) - cur.dl) * gs);
-            sa[e] = __float_as_uint(p * cur.gt);
-          }
-        } else {
+        for (int e = 0; e < 32; ++e)
+          da[e] = __float_as_uint(__uint_as_float(sa[e]) * fmaf(__uint_as_float(da[e]), dm.scale, -dls));
+      } else {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int col = hf * 32 + e;
-            const bool ok = col >= cur.klo && col < cur.khi;
-            const float p = ok ? bw_ex2(fmaf(__uint_as_float(sa[e]), c, -cur.lse2)) : 0.f;
-            da[e] = ok ? __float_as_uint(p * (__uint_as_float(da[e]) - cur.dl) * gs) : 0u;
-            sa[e] = __float_as_uint(p * cur.gt);
-          }
+        for (int e = 0; e < 32; ++e) {
+          const int col = hf * 32 + e;
+          const bool ok = col >= klo && col < khi;
+          const float p = ok ? bw_ex2(fmaf(__uint_as_float(sa[e]), c, -e0)) : 0.f;
+          da[e] = ok ? __float_as_uint(p * fmaf(__uint_as_float(da[e]), dm.scale, -dls)) : 0u;
+          sa[e] = __float_as_uint(p);
         }
+      }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {  // 8 keys = one 16-byte chunk; chunk index hf*4 + q, swizzled by the row
-          uint4 u, w;
-          u.x = pack2(T(), __uint_as_float(sa[q * 8 + 0]), __uint_as_float(sa[q * 8 + 1]));
-          u.y = pack2(T(), __uint_as_float(sa[q * 8 + 2]), __uint_as_float(sa[q * 8 + 3]));
-          u.z = pack2(T(), __uint_as_float(sa[q * 8 + 4]), __uint_as_float(sa[q * 8 + 5]));
-          u.w = pack2(T(), __uint_as_float(sa[q * 8 + 6]), __uint_as_float(sa[q * 8 + 7]));
-          w.x = pack2(T(), __uint_as_float(da[q * 8 + 0]), __uint_as_float(da[q * 8 + 1]));
-          w.y = pack2(T(), __uint_as_float(da[q * 8 + 2]), __uint_as_float(da[q * 8 + 3]));
-          w.z = pack2(T(), __uint_as_float(da[q * 8 + 4]), __uint_as_float(da[q * 8 + 5]));
-          w.w = pack2(T(), __uint_as_float(da[q * 8 + 6]), __uint_as_float(da[q * 8 + 7]));
-          *reinterpret_cast<uint4*>(prow + (((hf * 4 + q) ^ sw) << 4)) = u;
-          *reinterpret_cast<uint4*>(srow + (((hf * 4 + q) ^ sw) << 4)) = w;
-        }
+      for (int q = 0; q < 4; ++q) {  // 8 keys = one 16-byte chunk; chunk index hf*4 + q, swizzled by the row
+        uint4 u, w;
+        u.x = pack2(T(), __uint_as_float(sa[q * 8 + 0]), __uint_as_float(sa[q * 8 + 1]));
+        u.y = pack2(T(), __uint_as_float(sa[q * 8 + 2]), __uint_as_float(sa[q * 8 + 3]));
+        u.z = pack2(T(), __uint_as_float(sa[q * 8 + 4]), __uint_as_float(sa[q * 8 + 5]));
+        u.w = pack2(T(), __uint_as_float(sa[q * 8 + 6]), __uint_as_float(sa[q * 8 + 7]));
+        w.x = pack2(T(), __uint_as_float(da[q * 8 + 0]), __uint_as_float(da[q * 8 + 1]));
+        w.y = pack2(T(), __uint_as_float(da[q * 8 + 2]), __uint_as_float(da[q * 8 + 3]));
+        w.z = pack2(T(), __uint_as_float(da[q * 8 + 4]), __uint_as_float(da[q * 8 + 5]));
+        w.w = pack2(T(), __uint_as_float(da[q * 8 + 6]), __uint_as_float(da[q * 8 + 7]));
+        *reinterpret_cast<uint4*>(prow + (((hf * 4 + q) ^ sw) << 4)) = u;
+        *reinterpret_cast<uint4*>(srow + (((hf * 4 + q) ^ sw) << 4)) = w;
       }
       tc_fence_before();
       fence_proxy_async();
@@ -383,18 +426,21 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         mbar_arrive(&ms->s_empty[s]);
         mbar_arrive(&ms->pds_full[s]);
       }
+      if (tid == 0) BDBG(23, i);
       cur = nxt;
     }
   } else {
     // ===== dQ drain warps: dQ_t (TMEM) -> fp32 dQ by vector reductions ============================================
-    const int r = tid - 128;
+    const int r = tid - 256;
     const int tok_l = r / h, head = r - tok_l * h;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     int tk = get_tk(0, tok_l);
     for (int i = 0; i < n; ++i) {
       const int s = i & 1, k = i >> 1;
       const int tk_next = get_tk(i + 1, tok_l);
+      if (tid == 256) BDBG(30, i);
       mbar_wait(&ms->dq_full[s], k & 1);
+      if (tid == 256) BDBG(31, i);
       tc_fence_after();
       uint32_t va[32], vb2[32];
       tmem_ld32(tmem + lane_off + kColDQ + s * 64, va);
@@ -404,7 +450,7 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ms->dq_empty[s]);
-      if (tk >= 0) {  // this thread's staging row is its own: no cross-thread synchronisation
+      if (tk >= 0 && a.dQ) {  // this thread's staging row is its own: no cross-thread synchronisation
         bw_bulk_wait_read0();  // the previous tile's reduction has read the row
         uint4* stage = reinterpret_cast<uint4*>(smem + BwSmem::dq + r * kBwDqRow);
 #pragma unroll
@@ -416,6 +462,7 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         bw_bulk_red_add_f32(a.dQ + (((size_t)tk * dm.G + g) * h + head) * 64, stage, 256);
         bw_bulk_commit();
       }
+      if (tid == 256) BDBG(32, i);
       tk = tk_next;
     }
     bw_bulk_wait0();
@@ -479,6 +526,46 @@ bwd_delta_kernel(nsa_dims_t dm, const void* __restrict__ dO, const void* __restr
   }
 }
 
+// 16-bit, Dv = 64: one 4-byte load per lane covers a head row; all loads of a head are issued before any is used.
+template <typename T>
+__global__ void __launch_bounds__(kBwDeltaWarps * 32)
+bwd_delta16_kernel(nsa_dims_t dm, const T* __restrict__ dO, const T* __restrict__ O_br, int branch_mask, float* __restrict__ delta,
+                   float* __restrict__ dgates) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_rows = dm.B * dm.S * dm.G, h = dm.h;
+  const size_t rows_h = (size_t)n_rows * h;
+  auto unpack = [](uint32_t u, float& lo, float& hi) {
+    T a, b;
+    memcpy(&a, &u, 2);
+    memcpy(&b, reinterpret_cast<const char*>(&u) + 2, 2);
+    lo = (float)a;
+    hi = (float)b;
+  };
+  for (int row = blockIdx.x * kBwDeltaWarps + warp; row < n_rows; row += gridDim.x * kBwDeltaWarps) {
+    float dg[3] = {0.f, 0.f, 0.f};
+    for (int hh = 0; hh < h; ++hh) {
+      const size_t e0 = ((size_t)row * h + hh) * 64;
+      const uint32_t ud = reinterpret_cast<const uint32_t*>(dO + e0)[lane];
+      uint32_t uo[3];
+#pragma unroll
+      for (int br = 0; br < 3; ++br)
+        uo[br] = (branch_mask & (1 << br)) ? reinterpret_cast<const uint32_t*>(O_br + br * rows_h * 64 + e0)[lane] : 0u;
+      float d0, d1;
+      unpack(ud, d0, d1);
+#pragma unroll
+      for (int br = 0; br < 3; ++br) {
+        if (!(branch_mask & (1 << br))) continue;
+        float o0, o1;
+        unpack(uo[br], o0, o1);
+        const float part = warp_sum(fmaf(d0, o0, d1 * o1));
+        dg[br] += part;
+        if (lane == 0) delta[br * rows_h + (size_t)row * h + hh] = part;
+      }
+    }
+    if (dgates && lane < 3 && (branch_mask & (1 << lane))) dgates[(size_t)row * 3 + lane] = lane == 0 ? dg[0] : (lane == 1 ? dg[1] : dg[2]);
+  }
+}
+
 // ---- host ------------------------------------------------------------------------------------------------------
 int make_tmap_q_heads(CUtensorMap* out, const void* base, int dtype, int D, int h, int G, long long n_tokens, int box_tokens);
 
@@ -511,8 +598,9 @@ static int launch_bwd_branch(const nsa_dims_t& dm, const BwdArgs& a, const float
   const int cap = BR == 0 ? dm.cap_cmp : (BR == 1 ? dm.cap_sel : dm.cap_win);
   const int slabs = dm.B * dm.G;
   CUtensorMap tmQ, tmdO, tmK, tmV;
-  if (int rc = make_tmap_q_heads(&tmQ, a.Q, dm.dtype, 64, dm.h, dm.G, (long long)dm.B * dm.S, 1)) return rc;
-  if (int rc = make_tmap_q_heads(&tmdO, a.dO, dm.dtype, 64, dm.h, dm.G, (long long)dm.B * dm.S, 1)) return rc;
+  const int box_tok = BR == 1 ? 1 : bw_tokp(dm);  // cmp / win tiles are runs of consecutive tokens: one box per tile
+  if (int rc = make_tmap_q_heads(&tmQ, a.Q, dm.dtype, 64, dm.h, dm.G, (long long)dm.B * dm.S, box_tok)) return rc;
+  if (int rc = make_tmap_q_heads(&tmdO, a.dO, dm.dtype, 64, dm.h, dm.G, (long long)dm.B * dm.S, box_tok)) return rc;
   if (int rc = make_tmap_rows(&tmK, a.K[BR], dm.dtype, 64, rows, 64, (long long)cap * 64, slabs, 64)) return rc;
   if (int rc = make_tmap_rows(&tmV, a.V[BR], dm.dtype, 64, rows, 64, (long long)cap * 64, slabs, 64)) return rc;
   BwKArgs k;
@@ -520,7 +608,8 @@ static int launch_bwd_branch(const nsa_dims_t& dm, const BwdArgs& a, const float
   k.lse = a.lse + BR * rows_h;
   k.delta = delta + BR * rows_h;
   k.gates = a.gates;
-  k.dQ = a.dQ;
+  static const bool no_dq = getenv("NSA_B200_BWD_NODQ") != nullptr;  // A/B switch (benchmarks only): skip the dQ reductions
+  k.dQ = no_dq ? nullptr : a.dQ;
   k.dK = a.dK[BR];
   k.dV = a.dV[BR];
   k.TOK = bw_tokp(dm);
@@ -554,7 +643,26 @@ static int launch_bwd_branch(const nsa_dims_t& dm, const BwdArgs& a, const float
     if (e != cudaSuccess) { set_error("bwd tc: smem attr: %s", cudaGetErrorString(e)); return NSA_ERR_CUDA; }
     attr_set = true;
   }
-  kern<<<grid, 320, BwSmem::total, stream>>>(tmQ, tmdO, tmK, tmV, dm, k);
+#ifdef NSA_BWD_DBG
+  static long long* dbg_buf = nullptr;
+  if (!dbg_buf) cudaMalloc(&dbg_buf, 8008 * sizeof(long long));
+  cudaMemsetAsync(dbg_buf, 0, 8008 * sizeof(long long), stream);
+  k.dbg = BR == 2 ? dbg_buf : nullptr;
+#endif
+  kern<<<grid, kBwThreads, BwSmem::total, stream>>>(tmQ, tmdO, tmK, tmV, dm, k);
+#ifdef NSA_BWD_DBG
+  if (BR == 2) {  // debug only: timeline of one CTA of the win walk (tag, tile, clock)
+    static int dumps = 0;
+    cudaStreamSynchronize(stream);
+    if (dumps++ == 2) {
+      static long long host[8008];
+      cudaMemcpy(host, dbg_buf, sizeof(host), cudaMemcpyDeviceToHost);
+      for (int tag = 0; tag < 40; ++tag)
+        for (int it = 0; it < 100; ++it)
+          if (host[tag * 100 + it]) fprintf(stderr, "BDBG %d %d %lld\n", tag, it, host[tag * 100 + it]);
+    }
+  }
+#endif
   return check_launch("bwd_tc_kernel");
 }
 
@@ -565,7 +673,10 @@ static int launch_bwd_tc_t(const nsa_dims_t& dm, const BwdArgs& a, int tc_mask, 
   const int n_rows = dm.B * dm.S * dm.G;
   int blocks = ceil_div(n_rows, kBwDeltaWarps);
   if (blocks > 148 * 32) blocks = 148 * 32;
-  bwd_delta_kernel<<<blocks, kBwDeltaWarps * 32, 0, stream>>>(dm, a.dO, a.O_br, a.branch_mask, delta, a.dgates);
+  if (dm.Dv == 64)
+    bwd_delta16_kernel<T><<<blocks, kBwDeltaWarps * 32, 0, stream>>>(dm, (const T*)a.dO, (const T*)a.O_br, a.branch_mask, delta, a.dgates);
+  else
+    bwd_delta_kernel<<<blocks, kBwDeltaWarps * 32, 0, stream>>>(dm, a.dO, a.O_br, a.branch_mask, delta, a.dgates);
   if (int rc = check_launch("bwd_delta_kernel")) return rc;
   if (tc_mask & 1)
     if (int rc = launch_bwd_branch<T, 0>(dm, a, delta, nullptr, stream)) return rc;
