@@ -7,6 +7,7 @@ exists because callers and tests construct and inspect it.
 """
 from __future__ import annotations
 
+import functools
 from dataclasses import dataclass
 from typing import Tuple
 
@@ -59,6 +60,13 @@ def build_M_csl_csr(seq_len: int, l: int, d: int, l_sel: int) -> Tuple[torch.Ten
 
 
 def build_block_meta(seq_len: int, l: int, d: int, l_sel: int, n_sel: int, w: int) -> BlockMeta:
+    """Same result as the reference's builder; memoised per geometry (the module asks for it on every forward, and the
+    tensors are read-only CPU metadata, so one instance per (seq_len, l, d, l_sel, n_sel, w) is shared)."""
+    return _build_block_meta_cached(int(seq_len), int(l), int(d), int(l_sel), int(n_sel), int(w))
+
+
+@functools.lru_cache(maxsize=64)
+def _build_block_meta_cached(seq_len: int, l: int, d: int, l_sel: int, n_sel: int, w: int) -> BlockMeta:
     if l % d != 0 or l_sel % d != 0:
         raise ValueError("Require d|l and d|l_sel in M0")
     cmp_starts, sel_starts = build_block_starts(seq_len, l, d, l_sel)

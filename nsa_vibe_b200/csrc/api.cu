@@ -48,12 +48,13 @@ static int validate_dims(const nsa_dims_t* dm, const char* who) {
 static bool tc_eligible(const nsa_dims_t& dm) { return dm.impl != NSA_IMPL_SIMT; }
 
 // The block-major selected branch pays for an index build and a merge pass: worth it once the query-major gather is bound by
-// L2 bandwidth, i.e. for long prefill.  NSA_B200_SEL2=0|1 forces the choice (benchmarks / tests).
+// L2 bandwidth: from a few thousand query rows on.  NSA_B200_SEL2=0|1 forces the choice (benchmarks / tests).
 static bool use_sel2(const nsa_dims_t& dm) {
   static const int env = getenv("NSA_B200_SEL2") ? atoi(getenv("NSA_B200_SEL2")) : -1;
   if (!tc_sel2_supported(dm) || env == 0) return false;
   if (env == 1) return true;
-  return (long long)dm.B * dm.S * dm.G >= 16384 && dm.S_sel_kv >= 4096;
+  // measured on B200 (m7c dims): B=1 S=2048 0.204 vs 0.229 ms for the whole prefill_fwd, B=8 S=2048 0.615 vs 1.139 ms
+  return (long long)dm.B * dm.S * dm.G >= 4096 && dm.S_sel_kv >= 1024;
 }
 
 }  // namespace nsa

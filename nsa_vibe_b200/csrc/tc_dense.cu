@@ -165,49 +165,54 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     }
   } else if (warp == kSoftWarps + 1) {
-    // ===== MMA issuer ======================================================================================
-    if (lane == 0 && n > 0) {
+    // ===== MMA issuer: the whole warp runs this code with warp-uniform operands (descriptors stay in uniform registers, a
+    // k-step is one uniform add) and one elected lane issues; building each descriptor from scratch under `if (lane == 0)`
+    // cost ~80 cycles per tcgen05.mma =======================================================================
+    if (n > 0) {
       constexpr uint32_t idesc_qk = make_idesc_f16(128, NK, TcType<T>::fmt, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, TcType<T>::fmt, 0, 1);
+      // descriptor words: lo = addr>>4 | (LBO>>4)<<16, hi = SBO>>4 | version | swizzle
+      constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | ((uint32_t)kSwizzle128B << 29);
+      constexpr uint32_t kLoK = (16u >> 4) << 16, kLoMN = (8192u >> 4) << 16;
+      const uint32_t smem0 = smem_u32(smem) >> 4;
       auto issue_qk = [&](int m, int i) {
-        const uint32_t qb = smem_u32(smem + SM::q + m * kDnTile);
-        const uint32_t kb = smem_u32(smem + SM::k + (i % kDnKS) * SM::kvtile);
+        const uint32_t q_lo = (smem0 + ((SM::q + m * kDnTile) >> 4)) | kLoK;
+        const uint32_t k_lo = (smem0 + ((SM::k + (i % kDnKS) * SM::kvtile) >> 4)) | kLoK;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(tmem + m * NK, make_smem_desc(qb + k * 32, 16, 1024, kSwizzle128B),
-                   make_smem_desc(kb + k * 32, 16, 1024, kSwizzle128B), idesc_qk, k > 0);
-        umma_commit(&ms->s_full[m]);
+        for (int k = 0; k < 4; ++k) umma_f16_elect(tmem + m * NK, q_lo + k * 2, kHi, k_lo + k * 2, kHi, idesc_qk, k > 0);
+        umma_commit_elect(&ms->s_full[m]);
       };
       mbar_wait(&ms->q_full, 0);
       mbar_wait(&ms->k_full[0], 0);
       tc_fence_after();
       for (int m = 0; m < MT; ++m) issue_qk(m, 0);
-      umma_commit(&ms->k_empty[0]);
+      umma_commit_elect(&ms->k_empty[0]);
       for (int i = 0; i < n; ++i) {
         const int vs = i % kDnVS;
         mbar_wait(&ms->v_full[vs], (i / kDnVS) & 1);
         if (i + 1 < n) mbar_wait(&ms->k_full[(i + 1) % kDnKS], ((i + 1) / kDnKS) & 1);
-        const uint32_t vb = smem_u32(smem + SM::v + vs * SM::kvtile);
+        const uint32_t v_lo = (smem0 + ((SM::v + vs * SM::kvtile) >> 4)) | kLoMN;
         for (int m = 0; m < MT; ++m) {
-          DDBG(10 + m, i);
+          if (lane == 0) DDBG(10 + m, i);
           mbar_wait(&ms->p_full[m], i & 1);
-          DDBG(12 + m, i);
+          if (lane == 0) DDBG(12 + m, i);
           tc_fence_after();
-          const uint32_t pb = smem_u32(smem + SM::p + m * SM::ptile);
+          const uint32_t p_lo = (smem0 + ((SM::p + m * SM::ptile) >> 4)) | kLoK;
           const uint32_t od = tmem + MT * NK + m * 64;
+          const uint32_t acc0 = i > 0 ? 1u : 0u;
 #pragma unroll
-          for (int k = 0; k < NK / 16; ++k)
-            umma_f16(od, make_smem_desc(pb + (k >> 2) * kDnTile + (k & 3) * 32, 16, 1024, kSwizzle128B),
-                     make_smem_desc(vb + k * 2048, 8192, 1024, kSwizzle128B), idesc_pv, (i > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&ms->p_empty[m]);
+          for (int k = 0; k < NK / 16; ++k)  // P: 64-key halves of 16 KB, 32 B per k-step; V: 16 rows = 2048 B per k-step
+            umma_f16_elect(od, p_lo + (k >> 2) * (kDnTile >> 4) + (k & 3) * 2, kHi, v_lo + k * (2048 >> 4), kHi, idesc_pv,
+                           k > 0 ? 1u : acc0);
+          umma_commit_elect(&ms->p_empty[m]);
           if (i + 1 < n) {
             mbar_wait(&ms->s_empty[m], i & 1);
             tc_fence_after();
             issue_qk(m, i + 1);
           }
         }
-        umma_commit(&ms->v_empty[vs]);
-        if (i + 1 < n) umma_commit(&ms->k_empty[(i + 1) % kDnKS]);
+        umma_commit_elect(&ms->v_empty[vs]);
+        if (i + 1 < n) umma_commit_elect(&ms->k_empty[(i + 1) % kDnKS]);
       }
     }
   } else {

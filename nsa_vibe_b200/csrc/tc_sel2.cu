@@ -282,46 +282,44 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       __syncwarp();
     }
   } else if (warp == 9) {
-    // ===== MMA issuer ======================================================================================
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc_f16(128, 64, TcType<T>::fmt, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, TcType<T>::fmt, 0, 1);
-      const uint32_t kb = smem_u32(smem + S2Smem::kv), vb = kb + 8192;
-      auto issue_qk = [&](int s, int k) {  // k-th tile of slot s
-        const int st = k & 1;
-        mbar_wait(&ms->q_full[s][st], (k >> 1) & 1);
-        mbar_wait(&ms->s_empty[s], (k & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t qb = smem_u32(smem + S2Smem::q + (s * 2 + st) * kS2Tile);
+    // ===== MMA issuer: whole warp, warp-uniform operands (descriptors in uniform registers), one elected lane issues ======
+    constexpr uint32_t idesc_qk = make_idesc_f16(128, 64, TcType<T>::fmt, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, TcType<T>::fmt, 0, 1);
+    constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | ((uint32_t)kSwizzle128B << 29);
+    constexpr uint32_t kLoK = (16u >> 4) << 16, kLoMN = (8192u >> 4) << 16;
+    const uint32_t smem0 = smem_u32(smem) >> 4;
+    const uint32_t k_lo = (smem0 + (S2Smem::kv >> 4)) | kLoK, v_lo = (smem0 + ((S2Smem::kv + 8192) >> 4)) | kLoMN;
+    auto issue_qk = [&](int s, int k) {  // k-th tile of slot s
+      const int st = k & 1;
+      mbar_wait(&ms->q_full[s][st], (k >> 1) & 1);
+      mbar_wait(&ms->s_empty[s], (k & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t q_lo = (smem0 + ((S2Smem::q + (s * 2 + st) * kS2Tile) >> 4)) | kLoK;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_f16(tmem + s * 64, make_smem_desc(qb + kk * 32, 16, 1024, kSwizzle128B),
-                   make_smem_desc(kb + kk * 32, 16, 1024, kSwizzle128B), idesc_qk, kk > 0);
-        umma_commit(&ms->s_full[s]);
-        umma_commit(&ms->q_empty[s][st]);
-      };
-      auto issue_pv = [&](int s, int k) {
-        mbar_wait(&ms->p_full[s], k & 1);
-        mbar_wait(&ms->o_empty[s], (k & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t pb = smem_u32(smem + S2Smem::p + s * kS2Tile);
+      for (int kk = 0; kk < 4; ++kk) umma_f16_elect(tmem + s * 64, q_lo + kk * 2, kHi, k_lo + kk * 2, kHi, idesc_qk, kk > 0);
+      umma_commit_elect(&ms->s_full[s]);
+      umma_commit_elect(&ms->q_empty[s][st]);
+    };
+    auto issue_pv = [&](int s, int k) {
+      mbar_wait(&ms->p_full[s], k & 1);
+      mbar_wait(&ms->o_empty[s], (k & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t p_lo = (smem0 + ((S2Smem::p + s * kS2Tile) >> 4)) | kLoK;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_f16(tmem + 128 + s * 64, make_smem_desc(pb + kk * 32, 16, 1024, kSwizzle128B),
-                   make_smem_desc(vb + kk * 2048, 8192, 1024, kSwizzle128B), idesc_pv, kk > 0);
-        umma_commit(&ms->o_full[s]);
-        umma_commit(&ms->p_empty[s]);
-      };
-      mbar_wait(&ms->kv_full, 0);
-      if (n0 > 0) issue_qk(0, 0);
-      if (n1 > 0) issue_qk(1, 0);
-      for (int k = 0; k < n0; ++k) {
-        issue_pv(0, k);
-        if (k + 1 < n0) issue_qk(0, k + 1);
-        if (k < n1) {
-          issue_pv(1, k);
-          if (k + 1 < n1) issue_qk(1, k + 1);
-        }
+      for (int kk = 0; kk < 4; ++kk)
+        umma_f16_elect(tmem + 128 + s * 64, p_lo + kk * 2, kHi, v_lo + kk * (2048 >> 4), kHi, idesc_pv, kk > 0);
+      umma_commit_elect(&ms->o_full[s]);
+      umma_commit_elect(&ms->p_empty[s]);
+    };
+    mbar_wait(&ms->kv_full, 0);
+    if (n0 > 0) issue_qk(0, 0);
+    if (n1 > 0) issue_qk(1, 0);
+    for (int k = 0; k < n0; ++k) {
+      issue_pv(0, k);
+      if (k + 1 < n0) issue_qk(0, k + 1);
+      if (k < n1) {
+        issue_pv(1, k);
+        if (k + 1 < n1) issue_qk(1, k + 1);
       }
     }
   } else {

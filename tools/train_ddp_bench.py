@@ -42,6 +42,8 @@ def main():
     ap.add_argument("--B", type=int, default=2, help="sequences per GPU")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--graph", action="store_true", help="capture forward + backward + optimizer step in one CUDA graph and replay it")
+    ap.add_argument("--profile", action="store_true", help="cProfile of the host side of the timed steps (rank 0)")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -55,7 +57,7 @@ def main():
     if world > 1:
         model = nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
         nd.register_bf16_compress(model)
-    opt = torch.optim.AdamW(model.parameters(), lr=2e-4)
+    opt = torch.optim.AdamW(model.parameters(), lr=2e-4, capturable=a.graph)
     ids = torch.randint(0, 256, (a.B, a.S + 1), device=dev)
     lib = _lib.load()
 
@@ -68,6 +70,32 @@ def main():
         opt.step()
         return loss
 
+    mode = "eager"
+    if a.graph:
+        # whole-step capture: the step is host-bound in eager mode (~170 NSA launches + ~2000 torch ops per step); the C ABI
+        # allocates nothing and never synchronises, so its launches are captured like any other kernel
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(3, a.warmup) if world == 1 else 11):  # DDP needs 11 eager iterations before capture
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=True)
+        holder = {}
+        with torch.cuda.graph(graph):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                logits = model(ids[:, :-1])
+            holder["loss"] = F.cross_entropy(logits.float().reshape(-1, 256), ids[:, 1:].reshape(-1))
+            holder["loss"].backward()
+            opt.step()
+
+        def step():  # noqa: F811
+            graph.replay()
+            return holder["loss"]
+
+        mode = "cuda-graph replay of forward+backward+AdamW"
     for _ in range(a.warmup):
         step()
     if world > 1:
@@ -75,16 +103,25 @@ def main():
     torch.cuda.synchronize()
     n0 = lib.nsa_kernel_launches()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof = None
+    if a.profile and rank == 0:
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     s.record()
     for _ in range(a.steps):
         loss = step()
     e.record()
+    if prof is not None:
+        prof.disable()
+        import pstats
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("tottime").print_stats(45)
     torch.cuda.synchronize()
     ms = nd.max_over_ranks(s.elapsed_time(e) / a.steps, device=dev)
     if rank == 0:
         print(json.dumps({"config": "C5 m7c TinyLM DDP training step", "layers": a.layers, "params": n_params, "S": a.S,
-                          "batch_per_gpu": a.B, "n_gpus": world, "ms_per_step": ms, "tokens_per_s": world * a.B * a.S / (ms * 1e-3),
-                          "loss": float(loss), "nsa_kernel_launches_per_step": (lib.nsa_kernel_launches() - n0) / a.steps,
+                          "batch_per_gpu": a.B, "n_gpus": world, "mode": mode, "ms_per_step": ms, "tokens_per_s": world * a.B * a.S / (ms * 1e-3),
+                          "loss": float(loss.detach()), "nsa_kernel_launches_per_step": (lib.nsa_kernel_launches() - n0) / a.steps,
                           "grad_allreduce": "DDP bf16_compress_hook over NCCL" if world > 1 else "none (single GPU)",
                           "allreduce_bytes_per_step": 2 * n_params if world > 1 else 0}))
     if world > 1:
