@@ -225,6 +225,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=512, help="query rows of the CPU sample (cpu_baseline leg; --impl reference uses half)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the forward+backward block (training shape, config C5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -346,6 +347,9 @@ def main():
         decode = None
         if not args.no_decode:
             decode = bench_decode(args, ops, cfg, dev, rank, world, barrier)
+    train = None
+    if not args.no_train:
+        train = bench_train_core(ops, cfg, dev, rank, world, barrier)
 
     if rank != 0:
         if world > 1:
@@ -392,10 +396,49 @@ def main():
             "e2e": {"value": e2e_val, "unit": "tok/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "how": "PrefillEngine.run: pinned host tensors in/out every step, H2D / kernels / D2H of neighbouring steps on 3 streams",
                     "matches_device_path": e2e_ok},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "decode": decode}
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "decode": decode, "train_core": train}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_train_core(ops, cfg, dev, rank, world, barrier, S=2048, B=8):
+    """Forward + analytical backward of the hot path at the training shape of config C5 (m7c dims, S=2048, bf16), one layer,
+    B sequences per GPU: scoring + selection + three branches + gated combine, then dQ / dK / dV of every branch and the
+    gate MLP gradients (tensor-core backward, tc_bwd.cu)."""
+    import torch.distributed as dist
+    c = M7C
+    inp, gate = make_inputs(B, S, dev, seed=77 + rank)
+    leaves = [inp[k].requires_grad_(True) for k in ("Q", "K_sel", "V_sel", "K_win", "V_win", "K_cmp", "V_cmp")]
+    gate = tuple(t.requires_grad_(True) for t in gate)
+    dO = torch.randn((B, S, c["G"], c["h"], c["Dv"]), device=dev).to(torch.bfloat16)
+
+    def fwd():
+        return ops.prefill_core(*leaves, gate, cfg, sel_mode=0)[0]
+
+    def timed(fn, n=5):
+        for _ in range(2):
+            fn()
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        barrier()
+        tt = torch.tensor([s.elapsed_time(e) / n], device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    with torch.no_grad():
+        ms_f = timed(fwd)
+    O = fwd()
+    ms_b = timed(lambda: torch.autograd.grad(O, leaves + list(gate), dO, retain_graph=True))
+    return {"what": "NSA hot path forward + backward, one layer, training shape (config C5)", "S": S, "batch_per_gpu": B,
+            "fwd_ms": ms_f, "bwd_ms": ms_b, "tokens_per_s_fwd_bwd": world * B * S / ((ms_f + ms_b) * 1e-3),
+            "bwd_kernels": "bwd_delta16 + bwd_tc_kernel[cmp|win|sel] (tcgen05, KV-tile-major, dK/dV in TMEM, dQ by TMA bulk "
+                           "reductions) + sel2 index + gate_bwd_fast; bwd_ms includes torch's fp32 zero-fills and casts"}
 
 
 def bench_decode(args, ops, cfg, dev, rank, world, barrier):

@@ -128,27 +128,27 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp == kSoftWarps + 1) {
-    // ===== MMA issuer ======================================================================================
-    if (lane == 0) {
+    // ===== MMA issuer: whole warp, warp-uniform operands (descriptors in uniform registers), one elected lane issues ======
+    {
       constexpr uint32_t idesc = make_idesc_f16(128, 128, TcType<T>::fmt, 0, 0);
+      constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | ((uint32_t)kSwizzle128B << 29);
+      constexpr uint32_t kLoK = (16u >> 4) << 16;
+      const uint32_t smem0 = smem_u32(smem) >> 4;
       mbar_wait(&ms->q_full, 0);
       for (int it = 0; it < 2 * NT; ++it) {
         const int ks = it % kScStages, st = it % STG;
         mbar_wait(&ms->k_full[ks], (it / kScStages) & 1);
-        const uint32_t kb = smem_u32(smem + SM::ring + ks * kScTile);
+        const uint32_t k_lo = (smem0 + ((SM::ring + ks * kScTile) >> 4)) | kLoK;
         for (int m = 0; m < MT; ++m) {
           mbar_wait(&ms->s_empty[m][st], ((it / STG) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t qb = smem_u32(smem + SM::q + m * kScTile);
+          const uint32_t q_lo = (smem0 + ((SM::q + m * kScTile) >> 4)) | kLoK;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = make_smem_desc(qb + k * 32, 16, 1024, kSwizzle128B);
-            const uint64_t bd = make_smem_desc(kb + k * 32, 16, 1024, kSwizzle128B);
-            umma_f16(tmem + (m * STG + st) * 128, ad, bd, idesc, k > 0);
-          }
-          umma_commit(&ms->s_full[m][st]);
+          for (int k = 0; k < 4; ++k)
+            umma_f16_elect(tmem + (m * STG + st) * 128, q_lo + k * 2, kHi, k_lo + k * 2, kHi, idesc, k > 0);
+          umma_commit_elect(&ms->s_full[m][st]);
         }
-        umma_commit(&ms->k_empty[ks]);
+        umma_commit_elect(&ms->k_empty[ks]);
       }
     }
   } else {
