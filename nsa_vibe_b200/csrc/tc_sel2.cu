@@ -209,6 +209,15 @@ __device__ __forceinline__ void s2_ld_wait32(uint32_t (&r)[32]) {
                : "memory");
 }
 
+#ifdef NSA_SEL2_DBG  // timeline of one CTA: one slot per (tag, tile), plain stores (tools/dbg_bwd.py prints it)
+#define S2DBG(tag, it)                                                                      \
+  do {                                                                                      \
+    if (dbg && blockIdx.x == 2000 && (it) < 100) dbg[(tag) * 100 + (it)] = clock64();       \
+  } while (0)
+#else
+#define S2DBG(tag, it) do { } while (0)
+#endif
+
 // grid: an upper bound on the number of runs; CTAs beyond *n_runs exit.  Each CTA loads the K/V tile of its block once and
 // walks its M-tiles, alternating between two slots (softmax warpgroups) that ping-pong on the tensor core.
 // O_p [pairs][h][64] (dtype T, normalised by the tile's own l), lse_p [pairs][h] fp32 (natural log).
@@ -217,7 +226,7 @@ __global__ void __launch_bounds__(320, 2)
 sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, nsa_dims_t dm, S2Geom gm, const S2Run* __restrict__ runs,
                  const int* __restrict__ n_runs, const int* __restrict__ tok, const int* __restrict__ hi,
-                 T* __restrict__ O_p, float* __restrict__ lse_p) {
+                 T* __restrict__ O_p, float* __restrict__ lse_p, long long* dbg) {
   if ((int)blockIdx.x >= *n_runs) return;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if (smem_u32(smem_raw) & 1023u) __trap();  // see S2Smem::total
@@ -273,7 +282,9 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int tk = lane < TOK ? tok[p0 + lane] : -1;                // query (b*S + s) of pair p0 + lane, -1 = padding
       const unsigned have = __ballot_sync(0xffffffffu, tk >= 0);
       if (lane == 0) {
+        S2DBG(1, i);
         mbar_wait(&ms->q_empty[s][st], ((k >> 1) & 1) ^ 1);
+        S2DBG(2, i);
         mbar_expect_tx(&ms->q_full[s][st], __popc(have) * h * 128);
       }
       __syncwarp();
@@ -291,8 +302,11 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t k_lo = (smem0 + (S2Smem::kv >> 4)) | kLoK, v_lo = (smem0 + ((S2Smem::kv + 8192) >> 4)) | kLoMN;
     auto issue_qk = [&](int s, int k) {  // k-th tile of slot s
       const int st = k & 1;
+      if (lane == 0) S2DBG(10, 2 * k + s);
       mbar_wait(&ms->q_full[s][st], (k >> 1) & 1);
+      if (lane == 0) S2DBG(11, 2 * k + s);
       mbar_wait(&ms->s_empty[s], (k & 1) ^ 1);
+      if (lane == 0) S2DBG(12, 2 * k + s);
       tc_fence_after();
       const uint32_t q_lo = (smem0 + ((S2Smem::q + (s * 2 + st) * kS2Tile) >> 4)) | kLoK;
 #pragma unroll
@@ -301,8 +315,11 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       umma_commit_elect(&ms->q_empty[s][st]);
     };
     auto issue_pv = [&](int s, int k) {
+      if (lane == 0) S2DBG(13, 2 * k + s);
       mbar_wait(&ms->p_full[s], k & 1);
+      if (lane == 0) S2DBG(14, 2 * k + s);
       mbar_wait(&ms->o_empty[s], (k & 1) ^ 1);
+      if (lane == 0) S2DBG(15, 2 * k + s);
       tc_fence_after();
       const uint32_t p_lo = (smem0 + ((S2Smem::p + s * kS2Tile) >> 4)) | kLoK;
 #pragma unroll
@@ -352,7 +369,9 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tok_n = tok[p + 2 * TOK];
         hi_n = hi[p + 2 * TOK];
       }
+      if ((tid & 127) == 0) S2DBG(20, i);
       mbar_wait(&ms->s_full[s], k & 1);
+      if ((tid & 127) == 0) S2DBG(21, i);
       tc_fence_after();
       uint32_t va[32], vb2[32];
       tmem_ld32(tm_S, va);
@@ -399,7 +418,12 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         l3 += __uint_as_float(vb2[e + 1]);
       }
       const float l = (l0 + l1) + (l2 + l3);
-      mbar_wait(&ms->p_empty[s], (k & 1) ^ 1);  // P.V of the slot's previous tile has read the P buffer
+      if ((tid & 127) == 0) S2DBG(22, i);
+      // the warp's 32 rows of the P buffer double as the staging area of its partial-O store: the bulk store of the previous
+      // tile must have read them (issued by this warp's lane 0) and P.V of the previous tile must have read P
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      mbar_wait(&ms->p_empty[s], (k & 1) ^ 1);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {  // keys 0..31: chunks 0..3 ; keys 32..63: chunks 4..7 (16 B = 8 keys each)
         uint4 u, w;
@@ -417,8 +441,10 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ms->p_full[s]);
+      if ((tid & 127) == 0) S2DBG(23, i);
       // ---- partial output of this (query, block) pair ----
       mbar_wait(&ms->o_full[s], k & 1);
+      if ((tid & 127) == 0) S2DBG(24, i);
       tc_fence_after();
       tmem_ld32(tm_O, va);
       tmem_ld32(tm_O + 32, vb2);
@@ -427,26 +453,46 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ms->o_empty[s]);
-      if (row_ok) {
+      // Partial O of the tile: every warp stages its 32 rows (16-bit, normalised by the tile's own l) in its rows of the
+      // slot's P buffer -- P.V has completed, so the buffer is free -- and sends them as one bulk store (the rows of a tile
+      // are contiguous in O_p).  Per-thread 16-byte
+      // stores of 128-byte rows touch 32 sectors per instruction: the store queue then stalled each warp for ~3000 cycles
+      // per tile (timeline, -DNSA_SEL2_DBG).  Rows of padding pairs carry stale bytes: the merge never reads them.
+      {
         const float inv = l > 0.f ? 1.0f / l : 0.f;
-        uint4* dst = reinterpret_cast<uint4*>(O_p + ((size_t)p * h + head) * 64);
+        uint4* dst = reinterpret_cast<uint4*>(smem + S2Smem::p + s * kS2Tile + r * 128);
+        if (row_ok) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u, w;
-          u.x = pack2(T(), __uint_as_float(va[q * 8 + 0]) * inv, __uint_as_float(va[q * 8 + 1]) * inv);
-          u.y = pack2(T(), __uint_as_float(va[q * 8 + 2]) * inv, __uint_as_float(va[q * 8 + 3]) * inv);
-          u.z = pack2(T(), __uint_as_float(va[q * 8 + 4]) * inv, __uint_as_float(va[q * 8 + 5]) * inv);
-          u.w = pack2(T(), __uint_as_float(va[q * 8 + 6]) * inv, __uint_as_float(va[q * 8 + 7]) * inv);
-          w.x = pack2(T(), __uint_as_float(vb2[q * 8 + 0]) * inv, __uint_as_float(vb2[q * 8 + 1]) * inv);
-          w.y = pack2(T(), __uint_as_float(vb2[q * 8 + 2]) * inv, __uint_as_float(vb2[q * 8 + 3]) * inv);
-          w.z = pack2(T(), __uint_as_float(vb2[q * 8 + 4]) * inv, __uint_as_float(vb2[q * 8 + 5]) * inv);
-          w.w = pack2(T(), __uint_as_float(vb2[q * 8 + 6]) * inv, __uint_as_float(vb2[q * 8 + 7]) * inv);
-          dst[q] = u;
-          dst[4 + q] = w;
+          for (int q = 0; q < 4; ++q) {
+            uint4 u, w;
+            u.x = pack2(T(), __uint_as_float(va[q * 8 + 0]) * inv, __uint_as_float(va[q * 8 + 1]) * inv);
+            u.y = pack2(T(), __uint_as_float(va[q * 8 + 2]) * inv, __uint_as_float(va[q * 8 + 3]) * inv);
+            u.z = pack2(T(), __uint_as_float(va[q * 8 + 4]) * inv, __uint_as_float(va[q * 8 + 5]) * inv);
+            u.w = pack2(T(), __uint_as_float(va[q * 8 + 6]) * inv, __uint_as_float(va[q * 8 + 7]) * inv);
+            w.x = pack2(T(), __uint_as_float(vb2[q * 8 + 0]) * inv, __uint_as_float(vb2[q * 8 + 1]) * inv);
+            w.y = pack2(T(), __uint_as_float(vb2[q * 8 + 2]) * inv, __uint_as_float(vb2[q * 8 + 3]) * inv);
+            w.z = pack2(T(), __uint_as_float(vb2[q * 8 + 4]) * inv, __uint_as_float(vb2[q * 8 + 5]) * inv);
+            w.w = pack2(T(), __uint_as_float(vb2[q * 8 + 6]) * inv, __uint_as_float(vb2[q * 8 + 7]) * inv);
+            dst[q] = u;
+            dst[4 + q] = w;
+          }
+          lse_p[(size_t)p * h + head] = l > 0.f ? m * dm.scale + logf(l) : -INFINITY;
         }
-        lse_p[(size_t)p * h + head] = l > 0.f ? m * dm.scale + logf(l) : -INFINITY;
+        fence_proxy_async();
+        __syncwarp();
+        const int row0 = (warp & 3) * 32;
+        const int nrows = TOK * h - row0 < 32 ? TOK * h - row0 : 32;  // rows beyond TOK*h are padding
+        if (lane == 0 && nrows > 0) {
+          T* gdst = O_p + ((size_t)(run.tile0 + i) * TOK * h + row0) * 64;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                       "r"(smem_u32(smem + S2Smem::p + s * kS2Tile + row0 * 128)), "r"(nrows * 128)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
+      if ((tid & 127) == 0) S2DBG(25, i);
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -650,8 +696,28 @@ static int launch_sel2_t(const nsa_dims_t& dm, const void* Q, const void* K, con
     if (e != cudaSuccess) { set_error("sel2: smem attr: %s", cudaGetErrorString(e)); return NSA_ERR_CUDA; }
     attr_set = true;
   }
-  kern<<<w.max_runs, 320, S2Smem::total, stream>>>(tmQ, tmK, tmV, dm, gm, runs, n_runs, tok, hi, O_p, lse_p);
+  long long* dbg_buf = nullptr;
+#ifdef NSA_SEL2_DBG
+  static long long* dbg_static = nullptr;
+  if (!dbg_static) cudaMalloc(&dbg_static, 4000 * sizeof(long long));
+  cudaMemsetAsync(dbg_static, 0, 4000 * sizeof(long long), stream);
+  dbg_buf = dbg_static;
+#endif
+  kern<<<w.max_runs, 320, S2Smem::total, stream>>>(tmQ, tmK, tmV, dm, gm, runs, n_runs, tok, hi, O_p, lse_p, dbg_buf);
   if (int rc = check_launch("sel2_attn_kernel")) return rc;
+#ifdef NSA_SEL2_DBG
+  {
+    static int dumps = 0;
+    cudaStreamSynchronize(stream);
+    if (dumps++ == 2) {
+      static long long host[4000];
+      cudaMemcpy(host, dbg_buf, sizeof(host), cudaMemcpyDeviceToHost);
+      for (int tag = 0; tag < 40; ++tag)
+        for (int it = 0; it < 100; ++it)
+          if (host[tag * 100 + it]) fprintf(stderr, "BDBG %d %d %lld\n", tag, it, host[tag * 100 + it]);
+    }
+  }
+#endif
   int mblocks = ceil_div(n_rows, kS2MergeRows);
   if (mblocks > 148 * 64) mblocks = 148 * 64;
   sel2_merge_kernel<T><<<mblocks, kS2MergeRows * 64, 0, stream>>>(n_rows, dm.h, pair_of, O_p, lse_p, (T*)O, lse);
