@@ -7,7 +7,7 @@ namespace nsa {
 
 constexpr int kSelWarps = 8;
 
-__global__ void __launch_bounds__(kSelWarps * 32)
+__global__ void __launch_bounds__(kSelWarps * 32, 4)
 select_kernel(const float* __restrict__ p_grp, int n_rows, int S_rows, int G, int S_sel, int l_sel, int n_sel,
               int mode, int nf, int K, int t0, int32_t* __restrict__ ranges) {
   extern __shared__ float smem[];
@@ -17,9 +17,13 @@ select_kernel(const float* __restrict__ p_grp, int n_rows, int S_rows, int G, in
     // prefill rows are (b, s, g): t = t0 + s ; decode rows are (b, g): t = t0
     const int t = mode == 0 ? t0 + (row / G) % S_rows : t0;
     const float* src = p_grp + (size_t)row * S_sel;
-    for (int j = lane; j < S_sel; j += 32) sc[j] = __ldg(src + j);
-    __syncwarp();
-    select_row_warp(sc, S_sel, l_sel, n_sel, mode, nf, K, t, ranges + (size_t)row * K * 2);
+    if (S_sel > 128 && S_sel <= 1024) {  // warp-uniform
+      select_row_warp_1024(src, sc, S_sel, l_sel, n_sel, mode, nf, K, t, ranges + (size_t)row * K * 2);
+    } else {
+      for (int j = lane; j < S_sel; j += 32) sc[j] = __ldg(src + j);
+      __syncwarp();
+      select_row_warp(sc, S_sel, l_sel, n_sel, mode, nf, K, t, ranges + (size_t)row * K * 2);
+    }
     __syncwarp();
   }
 }

@@ -32,6 +32,60 @@ __device__ __forceinline__ void bitmap_set(uint32_t (&bm)[kSelMaxWords], int lan
   if ((word & 31) == lane) bm[word >> 5] |= 1u << (j & 31);
 }
 
+// ---- runs of set bits -> [start,end) ranges (sort, dedup and merge of adjacent blocks in one step) ----------------
+__device__ inline void sel_bitmap_to_ranges(const uint32_t (&bm)[kSelMaxWords], int S_sel, int l_sel, int K, int t,
+                                            int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  int nstart_before = 0, nend_before = 0;
+  const int nwords = (S_sel + 31) >> 5;
+  uint32_t prev_hi = 0;  // bit 31 of lane 31's word in the previous slot
+#pragma unroll
+  for (int s = 0; s < kSelMaxWords; ++s) {
+    if (s * 32 >= nwords) break;
+    const uint32_t b = bm[s];
+    uint32_t left = __shfl_up_sync(0xffffffffu, b, 1);
+    uint32_t carry_in = (lane == 0 ? prev_hi : left) >> 31;
+    uint32_t right = __shfl_down_sync(0xffffffffu, b, 1);
+    uint32_t next_first = (s + 1 < kSelMaxWords) ? bm[s + 1] : 0u;
+    next_first = __shfl_sync(0xffffffffu, next_first, 0);
+    uint32_t carry_out = (lane == 31 ? next_first : right) & 1u;
+    uint32_t starts = b & ~((b << 1) | carry_in);
+    uint32_t ends = b & ~((b >> 1) | (carry_out << 31));
+    int ns = __popc(starts), ne = __popc(ends);
+    // exclusive prefix over lanes
+    int ps = ns, pe = ne;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int a = __shfl_up_sync(0xffffffffu, ps, o);
+      int c = __shfl_up_sync(0xffffffffu, pe, o);
+      if (lane >= o) { ps += a; pe += c; }
+    }
+    int is = nstart_before + ps - ns, ie = nend_before + pe - ne;
+    const int base_id = (s * 32 + lane) * 32;
+    while (starts) {
+      int bit = __ffs(starts) - 1;
+      starts &= starts - 1;
+      if (is < K) out[2 * is] = (base_id + bit) * l_sel;
+      ++is;
+    }
+    while (ends) {
+      int bit = __ffs(ends) - 1;
+      ends &= ends - 1;
+      int e = (base_id + bit + 1) * l_sel;
+      if (e > t + 1) e = t + 1;  // clamp to the causal limit (:242-246, :567-573)
+      if (ie < K) out[2 * ie + 1] = e;
+      ++ie;
+    }
+    nstart_before += __shfl_sync(0xffffffffu, ps, 31);
+    nend_before += __shfl_sync(0xffffffffu, pe, 31);
+    prev_hi = __shfl_sync(0xffffffffu, b, 31);
+  }
+  for (int i = nstart_before + lane; i < K; i += 32) {
+    out[2 * i] = 0;
+    out[2 * i + 1] = 0;
+  }
+}
+
 // `sc`: this warp's copy of the row (S_sel floats in shared memory, clobbered).
 // mode 0 = prefill rule, 1 = decode rule.  Writes out[K][2] (int32 token ranges, [0,0] padded).
 __device__ inline void select_row_warp(float* sc, int S_sel, int l_sel, int n_sel, int mode, int nf, int K, int t,
@@ -179,55 +233,124 @@ __device__ inline void select_row_warp(float* sc, int S_sel, int l_sel, int n_se
     }
   }
 
-  // ---- runs of set bits -> [start,end) ranges -------------------------------------------------
-  int nstart_before = 0, nend_before = 0;
-  const int nwords = (S_sel + 31) >> 5;
-  uint32_t prev_hi = 0;  // bit 31 of lane 31's word in the previous slot
+  sel_bitmap_to_ranges(bm, S_sel, l_sel, K, t, out);
+}
+
+// Fast path of the standalone kernel for 128 < S_sel <= 1024 (long prefill): the row goes from global memory straight into
+// registers (lane owns blocks j = lane + 32k, all loads in flight at once), composites are formed there and written to shared
+// memory once (only the owner of a picked block ever re-reads them), and every (lane, group of 8 strides) bucket keeps its best
+// AND second-best entry, so taking a bucket's maximum promotes the runner-up instead of rescanning; a rescan happens only
+// when one bucket is picked twice.  Same comparisons, same tie rule (lower block id first) as select_row_warp: the picked
+// set is identical.  The first version (row staged in shared memory, three passes over it, a rescan per pick) ran 3300
+// instructions per row and was issue-bound (79 % issue-active, 0.49 ms for 131072 rows at 64k).
+__device__ inline void select_row_warp_1024(const float* __restrict__ src, float* sc, int S_sel, int l_sel, int n_sel, int mode,
+                                            int nf, int K, int t, int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const float NEG = -INFINITY;
+  float raw[32];
 #pragma unroll
-  for (int s = 0; s < kSelMaxWords; ++s) {
-    if (s * 32 >= nwords) break;
-    const uint32_t b = bm[s];
-    uint32_t left = __shfl_up_sync(0xffffffffu, b, 1);
-    uint32_t carry_in = (lane == 0 ? prev_hi : left) >> 31;
-    uint32_t right = __shfl_down_sync(0xffffffffu, b, 1);
-    uint32_t next_first = (s + 1 < kSelMaxWords) ? bm[s + 1] : 0u;
-    next_first = __shfl_sync(0xffffffffu, next_first, 0);
-    uint32_t carry_out = (lane == 31 ? next_first : right) & 1u;
-    uint32_t starts = b & ~((b << 1) | carry_in);
-    uint32_t ends = b & ~((b >> 1) | (carry_out << 31));
-    int ns = __popc(starts), ne = __popc(ends);
-    // exclusive prefix over lanes
-    int ps = ns, pe = ne;
+  for (int k = 0; k < 32; ++k) {
+    const int j = lane + 32 * k;
+    raw[k] = j < S_sel ? __ldg(src + j) : 0.f;
+  }
+  uint32_t bm[kSelMaxWords];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int a = __shfl_up_sync(0xffffffffu, ps, o);
-      int c = __shfl_up_sync(0xffffffffu, pe, o);
-      if (lane >= o) { ps += a; pe += c; }
+  for (int i = 0; i < kSelMaxWords; ++i) bm[i] = 0u;
+  int nvalid = (t + 1) / l_sel;
+  if (nvalid > S_sel) nvalid = S_sel;
+  const int cb = t / l_sel;
+  const int cb1 = cb > 0 ? cb - 1 : 0;
+  if (mode == 0 && n_sel >= S_sel) {
+    for (int w = lane; w * 32 < nvalid; w += 32) {
+      int rem = nvalid - w * 32;
+      bm[w >> 5] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
     }
-    int is = nstart_before + ps - ns, ie = nend_before + pe - ne;
-    const int base_id = (s * 32 + lane) * 32;
-    while (starts) {
-      int bit = __ffs(starts) - 1;
-      starts &= starts - 1;
-      if (is < K) out[2 * is] = (base_id + bit) * l_sel;
-      ++is;
+  } else {
+    int forced[3];
+    int nfc;
+    if (mode == 0) {
+      nfc = nf;
+      if (nf == 1) { forced[0] = 0; forced[1] = 0; forced[2] = 0; }
+      else if (nf == 2) { forced[0] = 0; forced[1] = cb; forced[2] = cb; }
+      else { forced[0] = 0; forced[1] = cb1; forced[2] = cb; }
+    } else {
+      nfc = 3;
+      forced[0] = 0; forced[1] = cb1; forced[2] = cb;
     }
-    while (ends) {
-      int bit = __ffs(ends) - 1;
-      ends &= ends - 1;
-      int e = (base_id + bit + 1) * l_sel;
-      if (e > t + 1) e = t + 1;  // clamp to the causal limit (:242-246, :567-573)
-      if (ie < K) out[2 * ie + 1] = e;
-      ++ie;
+    const int k_rest = n_sel - nfc > 0 ? n_sel - nfc : 0;
+    int take = nfc;
+    if (mode == 0 && k_rest == 0) take = nfc < n_sel ? nfc : n_sel;
+    for (int i = 0; i < take; ++i) {
+      int j = forced[i];
+      bool ok = mode == 0 ? (j < nvalid) : (j < S_sel);
+      if (ok) bitmap_set(bm, lane, j);
     }
-    nstart_before += __shfl_sync(0xffffffffu, ps, 31);
-    nend_before += __shfl_sync(0xffffffffu, pe, 31);
-    prev_hi = __shfl_sync(0xffffffffu, b, 31);
+    if (k_rest > 0) {
+      const int k_act = k_rest < S_sel ? k_rest : S_sel;
+      // composites + best / second best of each bucket (ascending j inside a bucket: strict > keeps the lower id first)
+      float v1[4], v2[4];
+      int j1[4], j2[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        v1[g] = NEG; v2[g] = NEG; j1[g] = 0x7fffffff; j2[g] = 0x7fffffff;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const int j = lane + 32 * (8 * g + kk);
+          float c = NEG;
+          if (j < nvalid && j != forced[0] && j != forced[1] && j != forced[2])
+            c = __fsub_rn(raw[8 * g + kk], __fmul_rn((float)j, 1e-8f));  // two separately rounded fp32 ops (:182-184, :312-318)
+          if (j < S_sel) sc[j] = c;
+          if (c > v1[g]) { v2[g] = v1[g]; j2[g] = j1[g]; v1[g] = c; j1[g] = j; }
+          else if (c > v2[g]) { v2[g] = c; j2[g] = j; }
+        }
+      }
+      __syncwarp();
+      // have2[g]: v2/j2 of bucket g are the true runner-up (false after a promotion until the bucket is rescanned)
+      bool have2[4] = {true, true, true, true};
+      for (int it = 0; it < k_act; ++it) {
+        float bv = v1[0];
+        int bj = j1[0];
+#pragma unroll
+        for (int g = 1; g < 4; ++g)
+          if (v1[g] > bv) { bv = v1[g]; bj = j1[g]; }  // ascending j across buckets: strict > keeps the lower id
+        const uint32_t bits = __float_as_uint(bv);
+        const uint32_t key = bits ^ ((bits >> 31) ? 0xffffffffu : 0x80000000u);  // order-preserving
+        const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
+        if (kmax == (0xff800000u ^ 0xffffffffu)) break;  // only -inf left: invalid picks are dropped in both modes
+        const int vj = (int)__reduce_min_sync(0xffffffffu, key == kmax ? (uint32_t)bj : 0x7fffffffu);
+        bitmap_set(bm, lane, vj);
+        if ((vj & 31) == lane) {
+          sc[vj] = NEG;
+          const int g = vj >> 8;  // (vj / 32) / 8
+          bool promote = false;
+#pragma unroll
+          for (int g2 = 0; g2 < 4; ++g2)
+            if (g2 == g) promote = have2[g2];
+          if (promote) {
+#pragma unroll
+            for (int g2 = 0; g2 < 4; ++g2)
+              if (g2 == g) { v1[g2] = v2[g2]; j1[g2] = j2[g2]; have2[g2] = false; }
+          } else {  // second pick from this bucket since its last scan: rescan its 8 entries
+            float a1 = NEG, a2 = NEG;
+            int i1 = 0x7fffffff, i2 = 0x7fffffff;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const int j = lane + 32 * (8 * g + kk);
+              if (j < S_sel) {
+                const float c = sc[j];
+                if (c > a1) { a2 = a1; i2 = i1; a1 = c; i1 = j; }
+                else if (c > a2) { a2 = c; i2 = j; }
+              }
+            }
+#pragma unroll
+            for (int g2 = 0; g2 < 4; ++g2)
+              if (g2 == g) { v1[g2] = a1; j1[g2] = i1; v2[g2] = a2; j2[g2] = i2; have2[g2] = true; }
+          }
+        }
+      }
+    }
   }
-  for (int i = nstart_before + lane; i < K; i += 32) {
-    out[2 * i] = 0;
-    out[2 * i + 1] = 0;
-  }
+  sel_bitmap_to_ranges(bm, S_sel, l_sel, K, t, out);
 }
 
 }  // namespace nsa
