@@ -14,8 +14,8 @@ select_kernel(const float* __restrict__ p_grp, int n_rows, int S_rows, int G, in
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sc = smem + (size_t)warp * S_sel;
   for (int row = blockIdx.x * kSelWarps + warp; row < n_rows; row += gridDim.x * kSelWarps) {
-    // prefill rows are (b, s, g): t = t0 + s ; decode rows are (b, g): t = t0
-    const int t = mode == 0 ? t0 + (row / G) % S_rows : t0;
+    // rows are (b, s, g) with t = t0 + s under either rule; a decode step has S_rows = 1, i.e. t = t0
+    const int t = t0 + (row / G) % S_rows;
     const float* src = p_grp + (size_t)row * S_sel;
     if (S_sel > 128 && S_sel <= 1024) {  // warp-uniform
       select_row_warp_1024(src, sc, S_sel, l_sel, n_sel, mode, nf, K, t, ranges + (size_t)row * K * 2);

@@ -71,7 +71,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 template <typename T, int MT, int R>
 __global__ void __launch_bounds__(32 * (4 * MT + 2), 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, nsa_dims_t dm, int S_sel,
-                float* __restrict__ p_grp, int TOK) {
+                float* __restrict__ p_grp, int TOK, int sel_only) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   using SM = ScSmem<MT>;
@@ -82,7 +82,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr int STG = SM::STG, RB = SM::RB;
 
   const int tiles_per_seq = ceil_div(dm.S, MT * TOK);
-  const int tile = blockIdx.x % tiles_per_seq;
+  const int tile = tiles_per_seq - 1 - blockIdx.x % tiles_per_seq;  // latest (longest, when causal) query tiles first
   const int bg = blockIdx.x / tiles_per_seq;
   const int g = bg % dm.G, b = bg / dm.G;
   const int s_base = tile * MT * TOK;
@@ -91,7 +91,18 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (s_last > dm.S - 1) s_last = dm.S - 1;
   const int nk_cta = causal ? num_cmp_at(dm.t0 + s_last, dm.l, dm.d, dm.S_cmp) : dm.S_cmp;
   const int NT = ceil_div(nk_cta, 128);        // key tiles with work
-  const int NTO = ceil_div(S_sel, BPT);        // output tiles (tiles >= NT only flush the carry / write zeros)
+  // Pass 2 (probabilities) covers every key tile when the caller wants p_grp itself.  When p_grp only feeds the selection
+  // (sel_only), a row t never looks at blocks j >= (t+1)/l_sel (selection_scorer.py:303-309 masks them), i.e. at compressed
+  // keys i >= R*(t+1)/l_sel -- so the CTA stops pass 2 at its last row's limit: half of the pass-2 exponentials on average.
+  // Pass 1 keeps every key: the full-row normaliser is the reference's.  Columns past the limit stay unwritten.
+  int NT2 = NT;
+  if (sel_only) {
+    int need = ((dm.t0 + s_last + 1) / dm.l_sel) * R;
+    if (need > nk_cta) need = nk_cta;
+    NT2 = ceil_div(need, 128);
+  }
+  int NTO = ceil_div(S_sel, BPT);              // output tiles (tiles >= NT2 only flush the carry / write zeros)
+  if (sel_only && NT2 + 1 < NTO) NTO = NT2 + 1;
 
   // ---- setup ---------------------------------------------------------------------------------------------
   {  // rows of the Q tiles that TMA does not write (>= TOK*h) must hold finite data
@@ -120,7 +131,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_expect_tx(&ms->q_full, MT * TOK * dm.h * 128);
       for (int m = 0; m < MT; ++m)
         tma_load_4d(smem + SM::q + m * kScTile, &tmQ, &ms->q_full, 0, 0, g, b * dm.S + s_base + m * TOK);
-      for (int it = 0; it < 2 * NT; ++it) {
+      for (int it = 0; it < NT + NT2; ++it) {
         const int ks = it % kScStages;
         mbar_wait(&ms->k_empty[ks], ((it / kScStages) & 1) ^ 1);
         mbar_expect_tx(&ms->k_full[ks], kScTile);
@@ -135,7 +146,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t kLoK = (16u >> 4) << 16;
       const uint32_t smem0 = smem_u32(smem) >> 4;
       mbar_wait(&ms->q_full, 0);
-      for (int it = 0; it < 2 * NT; ++it) {
+      for (int it = 0; it < NT + NT2; ++it) {
         const int ks = it % kScStages, st = it % STG;
         mbar_wait(&ms->k_full[ks], (it / kScStages) & 1);
         const uint32_t k_lo = (smem0 + ((SM::ring + ks * kScTile) >> 4)) | kLoK;
@@ -222,7 +233,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float carry = 0.f;  // half of the last straddling compressed block, owed to the next selection block
     for (int kt = 0; kt < NTO; ++kt) {
       float* rb = red + (size_t)(kt % RB) * 128 * kScRedLd + (size_t)r * kScRedLd;
-      if (kt < NT) {
+      if (kt < NT2) {
         const int it = NT + kt, st = it % STG;
         mbar_wait(&ms->s_full[mt][st], (it / STG) & 1);
         tc_fence_after();
@@ -301,7 +312,8 @@ int64_t tc_score_workspace(const nsa_dims_t& dm) {
 }
 
 template <typename T, int MT>
-static int launch_score_t(const nsa_dims_t& dm, const void* Q, const void* Kc, int S_sel, float* p_grp, cudaStream_t stream) {
+static int launch_score_t(const nsa_dims_t& dm, const void* Q, const void* Kc, int S_sel, float* p_grp, bool sel_only,
+                          cudaStream_t stream) {
   const int TOK = 128 / dm.h;
   CUtensorMap tmQ, tmK;
   if (int rc = make_tmap_q_heads(&tmQ, Q, dm.dtype, 64, dm.h, dm.G, (long long)dm.B * dm.S, TOK)) return rc;
@@ -314,7 +326,7 @@ static int launch_score_t(const nsa_dims_t& dm, const void* Q, const void* Kc, i
     attr_set = true;
   }
   const int grid = dm.B * dm.G * ceil_div(dm.S, MT * TOK);
-  kern<<<grid, 32 * (4 * MT + 2), ScSmem<MT>::total, stream>>>(tmQ, tmK, dm, S_sel, p_grp, TOK);
+  kern<<<grid, 32 * (4 * MT + 2), ScSmem<MT>::total, stream>>>(tmQ, tmK, dm, S_sel, p_grp, TOK, sel_only ? 1 : 0);
   return check_launch("score_tc_kernel");
 }
 
@@ -332,11 +344,15 @@ int launch_score_tc(const nsa_dims_t& dm, const void* Q, const void* Kc, int S_s
   // NSA_B200_SCORE_MT=2|4 forces one (benchmarks / tests)
   static const int mt_env = getenv("NSA_B200_SCORE_MT") ? atoi(getenv("NSA_B200_SCORE_MT")) : 0;
   const bool big = mt_env == 4 || (mt_env != 2 && (long long)dm.B * dm.G * dm.S >= 4LL * (128 / dm.h) * 148);
+  // the staged p_grp only feeds the selection: pass 2 may stop at each CTA's causal limit (NSA_B200_SCORE_CAUSAL_P2=0 keeps
+  // every column, for A/B runs)
+  static const bool p2_env = !(getenv("NSA_B200_SCORE_CAUSAL_P2") && atoi(getenv("NSA_B200_SCORE_CAUSAL_P2")) == 0);
+  const bool so = !p_grp && ranges && p2_env;
   int rc;
   if (dm.dtype == NSA_BF16)
-    rc = big ? launch_score_t<__nv_bfloat16, 4>(dm, Q, Kc, S_sel, pg, stream) : launch_score_t<__nv_bfloat16, 2>(dm, Q, Kc, S_sel, pg, stream);
+    rc = big ? launch_score_t<__nv_bfloat16, 4>(dm, Q, Kc, S_sel, pg, so, stream) : launch_score_t<__nv_bfloat16, 2>(dm, Q, Kc, S_sel, pg, so, stream);
   else
-    rc = big ? launch_score_t<__half, 4>(dm, Q, Kc, S_sel, pg, stream) : launch_score_t<__half, 2>(dm, Q, Kc, S_sel, pg, stream);
+    rc = big ? launch_score_t<__half, 4>(dm, Q, Kc, S_sel, pg, so, stream) : launch_score_t<__half, 2>(dm, Q, Kc, S_sel, pg, so, stream);
   if (rc) return rc;
   if (!ranges) return NSA_OK;
   const int nf = sel_mode == 0 ? prefill_forced_cols(S_total, dm.l_sel) : 3;

@@ -298,3 +298,24 @@ def test_prefill_core_long_uses_blockmajor_sel():
     want = O.prefill_core(*ts, gate, l=l, d=d, l_sel=ls, n_sel=n, w=w, ranges=ranges.cpu())
     err = (Oc.float().cpu() - want["O"]).abs()
     assert err.max() <= 2e-2 and err.mean() <= 1e-3, (err.max(), err.mean())
+
+
+@pytest.mark.parametrize("S,h,B", [(300, 6, 2), (2100, 6, 1), (5000, 4, 1), (1100, 8, 2), (64, 1, 1)])
+def test_score_select_causal_pass2_is_bit_exact(S, h, B):
+    """nsa_score_select stops the scorer's second pass at each CTA's causal limit (blocks a row may never select are not
+    scored); the ranges must equal those selected from the complete p_grp -- bit-exact, both rules, full rows and chunks."""
+    ops = _ops()
+    G, l, d, ls, n, w = 2, 32, 16, 64, 16, 512
+    ts = _case(B, S, G, h, l, d, ls, n, w, seed=S + 3 * h, dtype=torch.bfloat16)
+    Q, Kc = ts[0].cuda().bfloat16(), ts[5].cuda().bfloat16()
+    cfg = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w, impl=ops.IMPL_TC)
+    pg = ops.score_pgrp(Q, Kc, cfg)
+    fused0 = ops.score_select(Q, Kc, cfg, mode=0)
+    assert torch.equal(fused0, ops.select_ranges_prefill(pg, ls, n, S))
+    fused1 = ops.score_select(Q, Kc, cfg, mode=1)
+    for t in sorted({0, 1, ls - 1, ls, S // 3, S - 2, S - 1} & set(range(S))):
+        assert torch.equal(fused1[:, t], ops.select_ranges_decode(pg[:, t].contiguous(), ls, n, t)), t
+    if S >= 2000:  # chunk of rows (the sequence so far ends with the chunk; still more than n_sel blocks) against the same cache
+        t0, Sc = S // 2 + 5, S // 4
+        part = ops.score_select(Q[:, t0:t0 + Sc].contiguous(), Kc, cfg, mode=0, t0=t0)
+        assert torch.equal(part, fused0[:, t0:t0 + Sc])

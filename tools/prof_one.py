@@ -1,4 +1,4 @@
-"""Run one hot-path kernel a few times (for ncu captures): python tools/prof_one.py {score|cmp|win|sel} [S]"""
+"""Run one hot-path kernel a few times (for ncu captures): python tools/prof_one.py {score|score_select|cmp|win|sel|sel2} [S]"""
 import os
 import sys
 
@@ -22,6 +22,8 @@ with torch.no_grad():
     for _ in range(3):
         if what == "score":
             ops.score_pgrp(Q, Kc, cfg)
+        elif what == "score_select":  # the scorer as the hot path runs it: pass 2 stops at the causal limit
+            ops.score_select(Q, Kc, cfg, mode=0)
         elif what == "cmp":
             ops.branch_attention(ops.BR_CMP, Q, Kc, Vc, cfg)
         elif what == "win":
