@@ -147,6 +147,19 @@ int nsa_decode_fwd(const nsa_dims_t* dm, const void* Q,
                    const void* K_cmp, const void* V_cmp, const nsa_gate_params_t* gp,
                    void* O, int32_t* ranges_out, void* workspace, void* stream);
 
+/* ---- producers of the hot path's inputs ----------------------------------------------------------
+ * RoPE (nsa/core/rope.py:16-51: interleaved pairs, angle = (pos / scale) * base^(-2i/dim) in fp32, sin/cos rounded to the
+ * tensor's dtype) fused with the re-layout between the projection output [B,S,V,D] (layout 0) and the cache layout [B,V,S,D]
+ * (layout 1; nsa_attention.py:403-405).  rot_dim = V*D rotates the V*D values of a token as ONE vector (what the reference
+ * does to Q, nsa_attention.py:1002-1009), rot_dim = D rotates each D-vector, rot_dim = 0 only re-lays out.  Row s sits at
+ * position t0 + s.  inverse = 1 applies the transposed rotation: the backward pass is the same call with the layouts swapped. */
+int nsa_rope_shape(const void* x, void* y, int B, int S, int V, int D, int src_layout, int dst_layout, int rot_dim, int t0,
+                   float base, float scale, int inverse, int dtype, void* stream);
+/* phi (compress_pool.py:9-38): y[bg, c, :] = mean_{r<l} R(x[bg, c*d + r, :]) with R = RoPE (rope = 1, K) or identity (rope = 0,
+ * V); x [BG,S,D] -> y [BG,(S-l)/d+1,D].  backward = 1 maps dy [BG,S_cmp,D] -> dx [BG,S,D] (written, not accumulated). */
+int nsa_phi_avgpool(const void* x, void* y, int BG, int S, int D, int l, int d, int rope, int t0, float base, float scale,
+                    int backward, int dtype, void* stream);
+
 enum { NSA_WS_SCORE_SELECT = 0, NSA_WS_DECODE = 1, NSA_WS_PREFILL = 2, NSA_WS_SEL_BLOCKMAJOR = 3, NSA_WS_BWD = 4 };
 int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which);
 

@@ -55,6 +55,8 @@ SIGNATURES = {
     "nsa_prefill_fwd": (_I, [_DP] + [_P] * 8 + [_GP] + [_P] * 6),
     "nsa_prefill_bwd": (_I, [_DP] + [_P] * 22),
     "nsa_decode_fwd": (_I, [_DP] + [_P] * 7 + [_GP] + [_P] * 4),
+    "nsa_rope_shape": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, C.c_float, C.c_float, _I, _I, _P]),
+    "nsa_phi_avgpool": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, C.c_float, C.c_float, _I, _I, _P]),
     "nsa_workspace_bytes": (_I64, [_DP, _I]),
 }
 

@@ -4,8 +4,8 @@ Same constructor, parameter names (state-dict compatible: W_Q, W_K_sel, W_V_sel,
 W_V_cmp, out, gate.fc1, gate.fc2), `forward(x, kv, *, prefill) -> (out, kv)`, observability getters and
 NSA_* environment flags (snapshotted at construction like the reference, :300-394).  Everything between
 "Q/K/V projected + RoPE'd" and "O handed to self.out" runs in hand-written sm_100a kernels through
-libnsa_b200.so (ops.prefill_core / ops.decode_core); projections, RoPE and the phi pooling that produce the
-hot path's inputs stay in torch (SURVEY 8f lists fusing them as next).
+libnsa_b200.so (ops.prefill_core / ops.decode_core); so do RoPE, the re-layout into the cache format and the phi pooling that
+produce the hot path's inputs (ops.rope_shape / ops.phi_avgpool, one pass each); the projections themselves are nn.Linear.
 
 Semantics: all three branches are true softmax over their allowed keys (the reference's default
 per-token SDPA routes attend to one key only, F1).  Selection follows the reference's rule for the mode in use
@@ -194,17 +194,19 @@ class NSAAttention(nn.Module):
         return self._forward_decode(x, kv)
 
     def _project(self, x: torch.Tensor, t0: int):
-        B, S, _ = x.shape
-        pos = torch.arange(t0, t0 + S, device=x.device)
+        """Projections (cuBLAS through nn.Linear) followed by ONE kernel per tensor that applies RoPE and writes the cache
+        layout (ops.rope_shape) -- the reference's rope + view + permute + contiguous chain (nsa_attention.py:998-1016)."""
+        rs = self.rope_scale
+        G, Dk, Dv = self.n_kv_groups, self.d_k, self.d_v
         # the reference rotates Q as ONE vector of width n_heads*d_k (nsa_attention.py:1002-1009, :551-556)
-        Q = apply_rope(self.W_Q(x), pos, scale=self.rope_scale)
-        Q = self._shape_q(Q, B, S)
-        K_sel = apply_rope(self._shape_kv(self.W_K_sel(x), B, S), pos, scale=self.rope_scale)
-        V_sel = self._shape_kv(self.W_V_sel(x), B, S)
-        K_win = apply_rope(self._shape_kv(self.W_K_win(x), B, S), pos, scale=self.rope_scale)
-        V_win = self._shape_kv(self.W_V_win(x), B, S)
-        K_raw = self._shape_kv(self.W_K_cmp(x), B, S)
-        V_raw = self._shape_kv(self.W_V_cmp(x), B, S)
+        Q = ops.rope_shape(self.W_Q(x), self.n_heads, Dk, rope="token", t0=t0, scale=rs)
+        Q = Q.view(x.shape[0], x.shape[1], G, self.h_per_group, Dk)
+        K_sel = ops.rope_shape(self.W_K_sel(x), G, Dk, rope="vector", to_cache_layout=True, t0=t0, scale=rs)
+        V_sel = ops.rope_shape(self.W_V_sel(x), G, Dv, to_cache_layout=True)
+        K_win = ops.rope_shape(self.W_K_win(x), G, Dk, rope="vector", to_cache_layout=True, t0=t0, scale=rs)
+        V_win = ops.rope_shape(self.W_V_win(x), G, Dv, to_cache_layout=True)
+        K_raw = ops.rope_shape(self.W_K_cmp(x), G, Dk, to_cache_layout=True)
+        V_raw = ops.rope_shape(self.W_V_cmp(x), G, Dv, to_cache_layout=True)
         return Q, K_sel, V_sel, K_win, V_win, K_raw, V_raw
 
     def _nvtx(self, name: Optional[str]):
@@ -229,10 +231,9 @@ class NSAAttention(nn.Module):
         # emission count at zero) the raw stream is recorded, keeping "emit every d after warm-up l" absolute.
         kv.append_cmp_raw(K_raw.detach(), V_raw.detach())
         if t0 == 0:
-            K_cmp, V_cmp = avg_pool_phi_rope_kv(K_raw, V_raw, self.l, self.d, pos=torch.arange(S, device=x.device))
+            K_cmp, V_cmp = ops.phi_avgpool(K_raw, V_raw, self.l, self.d)
         else:
-            K_cmp, V_cmp = avg_pool_phi_rope_kv(kv.K_cmp_raw_seq, kv.V_cmp_raw_seq, self.l, self.d,
-                                                pos=torch.arange(t0 + S, device=x.device))
+            K_cmp, V_cmp = ops.phi_avgpool(kv.K_cmp_raw_seq, kv.V_cmp_raw_seq, self.l, self.d)
         kv.update_compressed(K_cmp.detach(), V_cmp.detach(), self.l, self.d)
 
         via_decode = self.prefill_tile > 0
@@ -267,9 +268,8 @@ class NSAAttention(nn.Module):
             kv.append_cmp_raw(K_raw, V_raw)
             S_raw = int(kv.K_cmp_raw_seq.shape[2])
             if S_raw >= self.l and (S_raw - self.l) % self.d == 0:  # emission schedule (:587-604)
-                pos_last = torch.arange(S_raw - self.l, S_raw, device=x.device)
-                K_new, V_new = avg_pool_phi_rope_kv(kv.K_cmp_raw_seq[:, :, S_raw - self.l:S_raw],
-                                                    kv.V_cmp_raw_seq[:, :, S_raw - self.l:S_raw], self.l, self.d, pos=pos_last)
+                K_new, V_new = ops.phi_avgpool(kv.K_cmp_raw_seq[:, :, S_raw - self.l:S_raw],
+                                               kv.V_cmp_raw_seq[:, :, S_raw - self.l:S_raw], self.l, self.d, t0=S_raw - self.l)
                 kv.append_compressed(K_new, V_new)
             need = max(t + 1, self.l_sel)
             if getattr(kv, "meta", None) is None or kv.meta.sel_starts.numel() * self.l_sel < t + 1 or kv.meta.sel_starts.numel() == 0:

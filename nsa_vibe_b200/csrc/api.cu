@@ -291,6 +291,18 @@ int nsa_decode_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, const
   return launch_fwd_generic(*dm, a, (cudaStream_t)stream);
 }
 
+int nsa_rope_shape(const void* x, void* y, int B, int S, int V, int D, int src_layout, int dst_layout, int rot_dim, int t0,
+                   float base, float scale, int inverse, int dtype, void* stream) {
+  NSA_REQUIRE(dtype == NSA_F32 || dtype == NSA_BF16 || dtype == NSA_F16, "rope_shape: dtype %d", dtype);
+  return launch_rope_shape(x, y, B, S, V, D, src_layout, dst_layout, rot_dim, t0, base, scale, inverse, dtype, (cudaStream_t)stream);
+}
+
+int nsa_phi_avgpool(const void* x, void* y, int BG, int S, int D, int l, int d, int rope, int t0, float base, float scale,
+                    int backward, int dtype, void* stream) {
+  NSA_REQUIRE(dtype == NSA_F32 || dtype == NSA_BF16 || dtype == NSA_F16, "phi_avgpool: dtype %d", dtype);
+  return launch_phi_avgpool(x, y, BG, S, D, l, d, rope, t0, base, scale, backward, dtype, (cudaStream_t)stream);
+}
+
 int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which) {
   if (!dm) return 0;
   switch (which) {

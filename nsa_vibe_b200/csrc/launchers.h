@@ -41,6 +41,11 @@ int launch_gate_bwd(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t
                     float* d_fc1_w, float* d_fc1_b, float* d_fc2_w, float* d_fc2_b, cudaStream_t stream);
 int launch_combine(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t& gp, const void* O_br, void* O, float* gates,
                    cudaStream_t stream);
+// producers.cu (RoPE + re-layout, phi average pool)
+int launch_rope_shape(const void* x, void* y, int B, int S, int V, int D, int src_layout, int dst_layout, int rot_dim, int t0,
+                      float base, float scale, int inverse, int dtype, cudaStream_t stream);
+int launch_phi_avgpool(const void* x, void* y, int BG, int S, int D, int l, int d, int rope, int t0, float base, float scale,
+                       int backward, int dtype, cudaStream_t stream);
 // tc_*.cu (tcgen05 / TMA kernels)
 bool tc_branch_supported(const nsa_dims_t& dm, int branch);
 bool tc_score_supported(const nsa_dims_t& dm);

@@ -1,0 +1,186 @@
+// Producers of the hot path's inputs: RoPE fused with the [B,S,V*D] <-> [B,V,S,D] re-layout the caches use, and
+// the phi average pool over RoPE(K_raw) / V_raw that emits the compressed tokens.  The reference does these with a dozen ATen
+// kernels per tensor (rope.py:16-51: pow, sin, cos, two casts, reshape, four multiplies, two add/sub, stack; then
+// permute().contiguous(), nsa_attention.py:403-405; avg_pool1d between two transposes, compress_pool.py:9-38); here each is one
+// HBM-bound pass.  Numerics follow the reference's order: angle = (pos / scale) * base^(-2i/dim) in fp32, sin/cos rounded to
+// the tensor's dtype, every product and sum rounded to that dtype; the pool accumulates in fp32 and divides by l.
+#include "common.cuh"
+#include "launchers.h"
+
+namespace nsa {
+
+template <typename T> struct PrT;
+template <> struct PrT<float> {
+  static __device__ __forceinline__ float ld(const float* p) { return *p; }
+  static __device__ __forceinline__ float rnd(float v) { return v; }
+  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <> struct PrT<__nv_bfloat16> {
+  static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ float rnd(float v) { return __bfloat162float(__float2bfloat16(v)); }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+};
+template <> struct PrT<__half> {
+  static __device__ __forceinline__ float ld(const __half* p) { return __half2float(*p); }
+  static __device__ __forceinline__ float rnd(float v) { return __half2float(__float2half(v)); }
+  static __device__ __forceinline__ void st(__half* p, float v) { *p = __float2half(v); }
+};
+
+// sin / cos of the rotation of pair `pair` (of a vector of width dim) at position pos, rounded to T like sin.to(x.dtype)
+template <typename T>
+__device__ __forceinline__ void rope_sincos(int pos, int pair, int dim, float base, float scale, float& sn, float& cs) {
+  // ATen divides a tensor by a scalar as a multiplication by its fp32 reciprocal (BinaryDivTrueKernel.cu): mirrored here so
+  // that fp32 results agree with the reference's `base ** (-2 * idx / dim)` and `pos / scale` to the last bit
+  const float inv_freq = powf(base, __fmul_rn(__fmul_rn(-2.0f, (float)pair), __fdiv_rn(1.0f, (float)dim)));
+  const float ang = __fmul_rn(__fmul_rn((float)pos, __fdiv_rn(1.0f, scale)), inv_freq);
+  sn = PrT<T>::rnd(sinf(ang));
+  cs = PrT<T>::rnd(cosf(ang));
+}
+
+// (x0, x1) -> rotated pair; inverse applies the transposed rotation (the backward of the forward one)
+template <typename T>
+__device__ __forceinline__ void rope_rotate(float x0, float x1, float sn, float cs, bool inverse, float& y0, float& y1) {
+  if (inverse) sn = -sn;
+  y0 = PrT<T>::rnd(__fsub_rn(PrT<T>::rnd(__fmul_rn(x0, cs)), PrT<T>::rnd(__fmul_rn(x1, sn))));
+  y1 = PrT<T>::rnd(__fadd_rn(PrT<T>::rnd(__fmul_rn(x0, sn)), PrT<T>::rnd(__fmul_rn(x1, cs))));
+}
+
+// One thread per pair.  Element (b, s, v, e): layout 0 = [B,S,V,D], layout 1 = [B,V,S,D].
+template <typename T>
+__global__ void __launch_bounds__(256)
+rope_shape_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int S, int V, int D, int src_layout, int dst_layout,
+                  int rot_dim, int t0, float base, float scale, int inverse) {
+  const long long n_pairs = (long long)B * S * V * (D / 2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pairs; i += (long long)gridDim.x * blockDim.x) {
+    // iterate in DESTINATION order so the stores coalesce; the loads coalesce too (D stays the fastest axis)
+    const int p = (int)(i % (D / 2));
+    long long r = i / (D / 2);
+    int b, s, v;
+    if (dst_layout == 0) { v = (int)(r % V); r /= V; s = (int)(r % S); b = (int)(r / S); }
+    else { s = (int)(r % S); r /= S; v = (int)(r % V); b = (int)(r / V); }
+    const size_t so = (src_layout == 0 ? (((size_t)b * S + s) * V + v) : (((size_t)b * V + v) * S + s)) * D + 2 * p;
+    const size_t dof = (dst_layout == 0 ? (((size_t)b * S + s) * V + v) : (((size_t)b * V + v) * S + s)) * D + 2 * p;
+    const float x0 = PrT<T>::ld(x + so), x1 = PrT<T>::ld(x + so + 1);
+    float y0 = x0, y1 = x1;
+    if (rot_dim > 0) {
+      const int pair = rot_dim == D ? p : v * (D / 2) + p;  // Q is rotated as ONE vector of width V*D (nsa_attention.py:1002-1009)
+      float sn, cs;
+      rope_sincos<T>(t0 + s, pair, rot_dim, base, scale, sn, cs);
+      rope_rotate<T>(x0, x1, sn, cs, inverse != 0, y0, y1);
+    }
+    PrT<T>::st(y + dof, y0);
+    PrT<T>::st(y + dof + 1, y1);
+  }
+}
+
+// y[bg, c, :] = (1/l) sum_{r<l} rot(x[bg, c*d + r, :])   (rope = 0: plain average).  One thread per output pair.
+template <typename T>
+__global__ void __launch_bounds__(256)
+phi_avgpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int BG, int S, int S_cmp, int D, int l, int d, int rope, int t0,
+                       float base, float scale) {
+  const long long n = (long long)BG * S_cmp * (D / 2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % (D / 2));
+    const long long r = i / (D / 2);
+    const int c = (int)(r % S_cmp), bg = (int)(r / S_cmp);
+    float a0 = 0.f, a1 = 0.f;
+    for (int k = 0; k < l; ++k) {
+      const int s = c * d + k;
+      const T* row = x + ((size_t)bg * S + s) * D + 2 * p;
+      float v0 = PrT<T>::ld(row), v1 = PrT<T>::ld(row + 1);
+      if (rope) {
+        float sn, cs, w0, w1;
+        rope_sincos<T>(t0 + s, p, D, base, scale, sn, cs);
+        rope_rotate<T>(v0, v1, sn, cs, false, w0, w1);
+        v0 = w0;
+        v1 = w1;
+      }
+      a0 = __fadd_rn(a0, v0);
+      a1 = __fadd_rn(a1, v1);
+    }
+    T* out = y + ((size_t)bg * S_cmp + c) * D + 2 * p;
+    PrT<T>::st(out, __fdiv_rn(a0, (float)l));
+    PrT<T>::st(out + 1, __fdiv_rn(a1, (float)l));
+  }
+}
+
+// dx[bg, s, :] = rot(s)^T ( (1/l) sum_{c : c*d <= s < c*d + l} dy[bg, c, :] ).  One thread per input pair.
+template <typename T>
+__global__ void __launch_bounds__(256)
+phi_avgpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int BG, int S, int S_cmp, int D, int l, int d, int rope,
+                       int t0, float base, float scale) {
+  const long long n = (long long)BG * S * (D / 2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % (D / 2));
+    const long long r = i / (D / 2);
+    const int s = (int)(r % S), bg = (int)(r / S);
+    int c_lo = s - l + 1 > 0 ? (s - l + 1 + d - 1) / d : 0;
+    int c_hi = s / d;
+    if (c_hi > S_cmp - 1) c_hi = S_cmp - 1;
+    float a0 = 0.f, a1 = 0.f;
+    for (int c = c_lo; c <= c_hi; ++c) {
+      const T* row = dy + ((size_t)bg * S_cmp + c) * D + 2 * p;
+      a0 += PrT<T>::ld(row);
+      a1 += PrT<T>::ld(row + 1);
+    }
+    a0 = PrT<T>::rnd(a0 / (float)l);
+    a1 = PrT<T>::rnd(a1 / (float)l);
+    float g0 = a0, g1 = a1;
+    if (rope) {
+      float sn, cs;
+      rope_sincos<T>(t0 + s, p, D, base, scale, sn, cs);
+      rope_rotate<T>(a0, a1, sn, cs, true, g0, g1);
+    }
+    T* out = dx + ((size_t)bg * S + s) * D + 2 * p;
+    PrT<T>::st(out, g0);
+    PrT<T>::st(out + 1, g1);
+  }
+}
+
+static int pr_blocks(long long n) {
+  long long b = (n + 255) / 256;
+  if (b > 148LL * 16) b = 148LL * 16;
+  return b < 1 ? 1 : (int)b;
+}
+
+int launch_rope_shape(const void* x, void* y, int B, int S, int V, int D, int src_layout, int dst_layout, int rot_dim, int t0,
+                      float base, float scale, int inverse, int dtype, cudaStream_t stream) {
+  NSA_REQUIRE(x && y, "rope_shape: NULL pointer");
+  NSA_REQUIRE(B >= 0 && S >= 0 && V >= 1 && D >= 2 && D % 2 == 0, "rope_shape: B=%d S=%d V=%d D=%d", B, S, V, D);
+  NSA_REQUIRE(rot_dim == 0 || rot_dim == D || rot_dim == V * D, "rope_shape: rot_dim=%d is neither 0, D nor V*D", rot_dim);
+  NSA_REQUIRE((src_layout | dst_layout | 1) == 1, "rope_shape: layouts are 0 ([B,S,V,D]) or 1 ([B,V,S,D])");
+  const long long n = (long long)B * S * V * (D / 2);
+  if (n == 0) return NSA_OK;
+  if (!(scale > 0.f)) scale = 1.0f;
+  const int blocks = pr_blocks(n);
+  if (dtype == NSA_F32)
+    rope_shape_kernel<float><<<blocks, 256, 0, stream>>>((const float*)x, (float*)y, B, S, V, D, src_layout, dst_layout, rot_dim, t0, base, scale, inverse);
+  else if (dtype == NSA_BF16)
+    rope_shape_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, S, V, D, src_layout, dst_layout, rot_dim, t0, base, scale, inverse);
+  else
+    rope_shape_kernel<__half><<<blocks, 256, 0, stream>>>((const __half*)x, (__half*)y, B, S, V, D, src_layout, dst_layout, rot_dim, t0, base, scale, inverse);
+  return check_launch("rope_shape_kernel");
+}
+
+int launch_phi_avgpool(const void* x, void* y, int BG, int S, int D, int l, int d, int rope, int t0, float base, float scale,
+                       int backward, int dtype, cudaStream_t stream) {
+  NSA_REQUIRE(x && y, "phi_avgpool: NULL pointer");
+  NSA_REQUIRE(BG >= 0 && S >= l && l >= 1 && d >= 1 && D >= 2 && D % 2 == 0, "phi_avgpool: BG=%d S=%d D=%d l=%d d=%d", BG, S, D, l, d);
+  const int S_cmp = (S - l) / d + 1;
+  const long long n = (long long)BG * (backward ? S : S_cmp) * (D / 2);
+  if (n == 0) return NSA_OK;
+  if (!(scale > 0.f)) scale = 1.0f;
+  const int blocks = pr_blocks(n);
+#define NSA_PHI(T)                                                                                                              \
+  do {                                                                                                                          \
+    if (backward) phi_avgpool_bwd_kernel<T><<<blocks, 256, 0, stream>>>((const T*)x, (T*)y, BG, S, S_cmp, D, l, d, rope, t0, base, scale); \
+    else phi_avgpool_fwd_kernel<T><<<blocks, 256, 0, stream>>>((const T*)x, (T*)y, BG, S, S_cmp, D, l, d, rope, t0, base, scale); \
+  } while (0)
+  if (dtype == NSA_F32) NSA_PHI(float);
+  else if (dtype == NSA_BF16) NSA_PHI(__nv_bfloat16);
+  else NSA_PHI(__half);
+#undef NSA_PHI
+  return check_launch("phi_avgpool_kernel");
+}
+
+}  // namespace nsa

@@ -247,17 +247,18 @@ __device__ inline void select_row_warp_1024(const float* __restrict__ src, float
                                             int nf, int K, int t, int32_t* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const float NEG = -INFINITY;
+  int nvalid = (t + 1) / l_sel;
+  if (nvalid > S_sel) nvalid = S_sel;
+  // only complete blocks (j < nvalid) can be candidates: buckets past them are neither loaded nor scanned (warp-uniform)
   float raw[32];
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
     const int j = lane + 32 * k;
-    raw[k] = j < S_sel ? __ldg(src + j) : 0.f;
+    raw[k] = (32 * (k & ~7) < nvalid && j < S_sel) ? __ldg(src + j) : 0.f;
   }
   uint32_t bm[kSelMaxWords];
 #pragma unroll
   for (int i = 0; i < kSelMaxWords; ++i) bm[i] = 0u;
-  int nvalid = (t + 1) / l_sel;
-  if (nvalid > S_sel) nvalid = S_sel;
   const int cb = t / l_sel;
   const int cb1 = cb > 0 ? cb - 1 : 0;
   if (mode == 0 && n_sel >= S_sel) {
@@ -293,6 +294,7 @@ __device__ inline void select_row_warp_1024(const float* __restrict__ src, float
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         v1[g] = NEG; v2[g] = NEG; j1[g] = 0x7fffffff; j2[g] = 0x7fffffff;
+        if (256 * g >= nvalid) continue;  // no candidate in this bucket for any lane; its sc[] entries are never read
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const int j = lane + 32 * (8 * g + kk);

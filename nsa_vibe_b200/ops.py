@@ -360,6 +360,77 @@ def prefill_core(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, gate, cfg: NSAConf
 
 
 # ----------------------------------------------------------------------------------------------------
+# producers of the hot path's inputs: RoPE + re-layout, phi average pool
+# ----------------------------------------------------------------------------------------------------
+class _RopeShape(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, V, D, rot_dim, dst_layout, t0, base, scale):
+        xc = _c(x)
+        B, S = xc.shape[0], xc.shape[1]
+        y = torch.empty((B, S, V, D) if dst_layout == 0 else (B, V, S, D), dtype=xc.dtype, device=xc.device)
+        if y.numel():
+            _call("nsa_rope_shape", _ptr(xc), _ptr(y), B, S, V, D, 0, dst_layout, rot_dim, int(t0), float(base), float(scale), 0,
+                  _DTYPES[xc.dtype], _stream())
+        ctx.meta = (B, S, V, D, rot_dim, dst_layout, int(t0), float(base), float(scale), x.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, S, V, D, rot_dim, dst_layout, t0, base, scale, xshape = ctx.meta
+        dyc = _c(dy)
+        dx = torch.empty((B, S, V, D), dtype=dyc.dtype, device=dyc.device)
+        if dx.numel():
+            _call("nsa_rope_shape", _ptr(dyc), _ptr(dx), B, S, V, D, dst_layout, 0, rot_dim, t0, base, scale, 1,
+                  _DTYPES[dyc.dtype], _stream())
+        return dx.view(xshape), None, None, None, None, None, None, None
+
+
+def rope_shape(x: torch.Tensor, V: int, D: int, *, rope: str = "none", to_cache_layout: bool = False, t0: int = 0,
+               base: float = 10000.0, scale: float = 1.0) -> torch.Tensor:
+    """x [B,S,V*D] (a projection output) -> [B,S,V,D] or, with to_cache_layout, [B,V,S,D] in ONE pass, with RoPE
+    (nsa/core/rope.py:16-51) applied per D-vector (rope="vector"), across the V*D values of a token as one vector
+    (rope="token": what the reference does to Q, nsa_attention.py:1002-1009) or not at all (rope="none": V tensors)."""
+    _require_cuda(x)
+    rot = {"none": 0, "vector": D, "token": V * D}[rope]
+    if not (scale > 0):
+        scale = 1.0
+    return _RopeShape.apply(x, V, D, rot, 1 if to_cache_layout else 0, t0, base, scale)
+
+
+class _PhiAvgPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, l, d, rope, t0):
+        xc = _c(x)
+        B, G, S, D = xc.shape
+        S_cmp = (S - l) // d + 1
+        y = torch.empty((B, G, S_cmp, D), dtype=xc.dtype, device=xc.device)
+        if y.numel():
+            _call("nsa_phi_avgpool", _ptr(xc), _ptr(y), B * G, S, D, l, d, int(rope), int(t0), 10000.0, 1.0, 0, _DTYPES[xc.dtype],
+                  _stream())
+        ctx.meta = (B, G, S, D, l, d, int(rope), int(t0))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, G, S, D, l, d, rope, t0 = ctx.meta
+        dyc = _c(dy)
+        dx = torch.empty((B, G, S, D), dtype=dyc.dtype, device=dyc.device)
+        if dx.numel():
+            _call("nsa_phi_avgpool", _ptr(dyc), _ptr(dx), B * G, S, D, l, d, rope, t0, 10000.0, 1.0, 1, _DTYPES[dyc.dtype], _stream())
+        return dx, None, None, None, None
+
+
+def phi_avgpool(K_raw: torch.Tensor, V_raw: torch.Tensor, l: int, d: int, *, t0: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """avg_pool_phi_rope_kv (nsa/core/compress_pool.py:9-38) for rows at positions t0, t0+1, ...: K_cmp = avgpool_{l,d}(RoPE(K_raw)),
+    V_cmp = avgpool_{l,d}(V_raw); [B,G,S,D] -> [B,G,(S-l)//d+1,D].  S < l gives empty outputs."""
+    _require_cuda(K_raw, V_raw)
+    B, G, S, Dk = K_raw.shape
+    if S < l:
+        return K_raw.new_zeros((B, G, 0, Dk)), V_raw.new_zeros((B, G, 0, V_raw.shape[-1]))
+    return _PhiAvgPool.apply(K_raw, l, d, 1, t0), _PhiAvgPool.apply(V_raw, l, d, 0, t0)
+
+
+# ----------------------------------------------------------------------------------------------------
 # fused hot path: decode
 # ----------------------------------------------------------------------------------------------------
 def decode_core(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, gate, cfg: NSAConfig, *, t: int, S_sel_kv: int,
