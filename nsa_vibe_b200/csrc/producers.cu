@@ -45,28 +45,37 @@ __device__ __forceinline__ void rope_rotate(float x0, float x1, float sn, float 
   y1 = PrT<T>::rnd(__fadd_rn(PrT<T>::rnd(__fmul_rn(x0, sn)), PrT<T>::rnd(__fmul_rn(x1, cs))));
 }
 
-// One thread per pair.  Element (b, s, v, e): layout 0 = [B,S,V,D], layout 1 = [B,V,S,D].
+// Element (b, s, v, e): layout 0 = [B,S,V,D], layout 1 = [B,V,S,D].  A thread owns one rotation pair of the token (column
+// c = v*D/2 + p) and walks kRopeRows rows, so the pair's frequency (a powf) is computed once per thread and a row costs one
+// sincosf; consecutive threads touch consecutive pairs, i.e. contiguous 128-byte segments in either layout.
+constexpr int kRopeRows = 16;
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 rope_shape_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int S, int V, int D, int src_layout, int dst_layout,
                   int rot_dim, int t0, float base, float scale, int inverse) {
-  const long long n_pairs = (long long)B * S * V * (D / 2);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pairs; i += (long long)gridDim.x * blockDim.x) {
-    // iterate in DESTINATION order so the stores coalesce; the loads coalesce too (D stays the fastest axis)
-    const int p = (int)(i % (D / 2));
-    long long r = i / (D / 2);
-    int b, s, v;
-    if (dst_layout == 0) { v = (int)(r % V); r /= V; s = (int)(r % S); b = (int)(r / S); }
-    else { s = (int)(r % S); r /= S; v = (int)(r % V); b = (int)(r / V); }
+  const int C = V * (D / 2);
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int v = c / (D / 2), p = c - v * (D / 2);
+  const int b = blockIdx.z;
+  const int s0 = blockIdx.y * kRopeRows;
+  const int s1 = s0 + kRopeRows < S ? s0 + kRopeRows : S;
+  // ATen divides a tensor by a scalar as a multiplication by its fp32 reciprocal (BinaryDivTrueKernel.cu): mirrored here so
+  // that fp32 results agree with the reference's `base ** (-2 * idx / dim)` and `pos / scale` to the last bit
+  const int pair = rot_dim == D ? p : c;  // Q is rotated as ONE vector of width V*D (nsa_attention.py:1002-1009)
+  const float inv_freq = rot_dim > 0 ? powf(base, __fmul_rn(__fmul_rn(-2.0f, (float)pair), __fdiv_rn(1.0f, (float)rot_dim))) : 0.f;
+  const float inv_scale = __fdiv_rn(1.0f, scale);
+  for (int s = s0; s < s1; ++s) {
     const size_t so = (src_layout == 0 ? (((size_t)b * S + s) * V + v) : (((size_t)b * V + v) * S + s)) * D + 2 * p;
     const size_t dof = (dst_layout == 0 ? (((size_t)b * S + s) * V + v) : (((size_t)b * V + v) * S + s)) * D + 2 * p;
     const float x0 = PrT<T>::ld(x + so), x1 = PrT<T>::ld(x + so + 1);
     float y0 = x0, y1 = x1;
     if (rot_dim > 0) {
-      const int pair = rot_dim == D ? p : v * (D / 2) + p;  // Q is rotated as ONE vector of width V*D (nsa_attention.py:1002-1009)
+      const float ang = __fmul_rn(__fmul_rn((float)(t0 + s), inv_scale), inv_freq);
       float sn, cs;
-      rope_sincos<T>(t0 + s, pair, rot_dim, base, scale, sn, cs);
-      rope_rotate<T>(x0, x1, sn, cs, inverse != 0, y0, y1);
+      sincosf(ang, &sn, &cs);
+      rope_rotate<T>(x0, x1, PrT<T>::rnd(sn), PrT<T>::rnd(cs), inverse != 0, y0, y1);
     }
     PrT<T>::st(y + dof, y0);
     PrT<T>::st(y + dof + 1, y1);
@@ -152,13 +161,16 @@ int launch_rope_shape(const void* x, void* y, int B, int S, int V, int D, int sr
   const long long n = (long long)B * S * V * (D / 2);
   if (n == 0) return NSA_OK;
   if (!(scale > 0.f)) scale = 1.0f;
-  const int blocks = pr_blocks(n);
+  const int C = V * (D / 2);
+  const int bdx = C >= 256 ? 256 : ((C + 31) / 32) * 32;
+  const dim3 grid((C + bdx - 1) / bdx, (S + kRopeRows - 1) / kRopeRows, B);
+  NSA_REQUIRE(grid.y <= 65535 && B <= 65535, "rope_shape: S=%d B=%d too large for one launch", S, B);
   if (dtype == NSA_F32)
-    rope_shape_kernel<float><<<blocks, 256, 0, stream>>>((const float*)x, (float*)y, B, S, V, D, src_layout, dst_layout, rot_dim, t0, base, scale, inverse);
+    rope_shape_kernel<float><<<grid, bdx, 0, stream>>>((const float*)x, (float*)y, B, S, V, D, src_layout, dst_layout, rot_dim, t0, base, scale, inverse);
   else if (dtype == NSA_BF16)
-    rope_shape_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, S, V, D, src_layout, dst_layout, rot_dim, t0, base, scale, inverse);
+    rope_shape_kernel<__nv_bfloat16><<<grid, bdx, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, S, V, D, src_layout, dst_layout, rot_dim, t0, base, scale, inverse);
   else
-    rope_shape_kernel<__half><<<blocks, 256, 0, stream>>>((const __half*)x, (__half*)y, B, S, V, D, src_layout, dst_layout, rot_dim, t0, base, scale, inverse);
+    rope_shape_kernel<__half><<<grid, bdx, 0, stream>>>((const __half*)x, (__half*)y, B, S, V, D, src_layout, dst_layout, rot_dim, t0, base, scale, inverse);
   return check_launch("rope_shape_kernel");
 }
 
