@@ -2,6 +2,9 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 __device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// packed 16-bit variants: two exponentials per instruction in PTX (SASS: one MUFU.EX2.BF16 / .F16 per half)
+__device__ __forceinline__ float ex2_bf16x2(float x) { unsigned u = __float_as_uint(x), y; asm volatile("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(u)); return __uint_as_float(y); }
+__device__ __forceinline__ float ex2_f16x2(float x) { unsigned u = __float_as_uint(x), y; asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(u)); return __uint_as_float(y); }
 template <int MODE>
 __global__ void k(float* out, int iters, float seed) {
   float a[16];
@@ -14,6 +17,8 @@ __global__ void k(float* out, int iters, float seed) {
       if (MODE == 1) a[i] = fmaf(a[i], 0.999f, 1e-3f);        // FFMA only
       if (MODE == 2) a[i] = ex2(fmaf(a[i], 0.999f, -1e-3f));  // FFMA + MUFU
       if (MODE == 3) { a[i] = ex2(fmaf(a[i], 0.999f, -1e-3f)); a[(i + 1) & 15] += a[i]; }  // + FADD
+      if (MODE == 4) a[i] = ex2_bf16x2(a[i]);                 // 2 bf16 exponentials per op
+      if (MODE == 5) a[i] = ex2_f16x2(a[i]);                  // 2 f16 exponentials per op
     }
   }
   float s = 0;
@@ -37,6 +42,6 @@ void run(const char* name, int threads) {
   cudaFree(out);
 }
 int main() {
-  for (int t : {128, 256, 512, 1024}) { run<0>("ex2", t); run<1>("ffma", t); run<2>("ffma+ex2", t); run<3>("ffma+ex2+fadd", t); }
+  for (int t : {128, 256, 512, 1024}) { run<0>("ex2", t); run<1>("ffma", t); run<2>("ffma+ex2", t); run<3>("ffma+ex2+fadd", t); run<4>("ex2.bf16x2 (x2)", t); run<5>("ex2.f16x2 (x2)", t); }
   return 0;
 }
