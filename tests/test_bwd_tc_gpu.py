@@ -165,3 +165,24 @@ def test_bwd_tc_linearity_large():
     for a, b, c, z in zip(g1, g2, g12, g0):
         assert torch.all(z == 0)
         assert _rel(a + b, c) <= 3e-2, _rel(a + b, c)
+
+
+def test_bwd_tc_long_sequence_vs_simt_same_saved_tensors(monkeypatch):
+    """S = 16384 (256 selection blocks, 1023 compressed keys, chunked M-tile walks): the tensor-core backward against the SIMT
+    backward fed the SAME saved O / lse / ranges (NSA_B200_IMPL=1 switches the kernel family at call time), so only the
+    backward kernels differ.  Tolerance: rel-err 2e-2 per gradient (16-bit P and dS in the tensor-core path)."""
+    ops = _ops()
+    B, S, G, h, l, d, ls, n, w = 1, 16384, 2, 6, 32, 16, 64, 16, 512
+    dtype = torch.bfloat16
+    ts = _case(B, S, G, h, l, d, seed=44, dtype=dtype)
+    cfg = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w, gate_mode=ops.GATE_UNIFORM)
+    dev = [t.cuda().to(dtype).requires_grad_(True) for t in ts]
+    Oc, _, _ = ops.prefill_core(*dev, None, cfg, sel_mode=0)
+    dO = torch.randn(Oc.shape, generator=torch.Generator().manual_seed(6)).to(dtype).cuda()
+    g_tc = torch.autograd.grad(Oc, dev, dO, retain_graph=True)
+    monkeypatch.setenv("NSA_B200_IMPL", "1")
+    g_si = torch.autograd.grad(Oc, dev, dO, retain_graph=True)
+    monkeypatch.delenv("NSA_B200_IMPL")
+    for nme, a, b in zip(["Q", "K_sel", "V_sel", "K_win", "V_win", "K_cmp", "V_cmp"], g_tc, g_si):
+        assert torch.isfinite(a.float()).all(), nme
+        assert _rel(a.float(), b.float()) <= TOL_SIMT, (nme, _rel(a.float(), b.float()))
