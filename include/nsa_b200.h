@@ -160,6 +160,25 @@ int nsa_rope_shape(const void* x, void* y, int B, int S, int V, int D, int src_l
 int nsa_phi_avgpool(const void* x, void* y, int BG, int S, int D, int l, int d, int rope, int t0, float base, float scale,
                     int backward, int dtype, void* stream);
 
+/* Producer of one decode step: the token's fused projection output y [B, H*Dk + G*(3*Dk + 3*Dv)] =
+ * (Q | K_sel | V_sel | K_win | V_win | K_raw | V_raw) is rotated (Q as one H*Dk-wide vector, K_sel / K_win per Dk-vector;
+ * position t) and scattered: Q into q_out [B, H*Dk], the six rows into row `row[i]` of their cache slabs [B,G,cap[i],D] --
+ * the seven rope / view / torch.cat chains of the reference's decode step (nsa_attention.py:545-586, kv_cache.py:28-49) in one
+ * launch.  counters (optional, [5][counters_cap] int64): the step's read counters (kv_cache.py:51-65) written at counters_idx. */
+typedef struct nsa_decode_produce {
+  const void* y;
+  void* q_out;
+  void* slab[6];
+  int32_t cap[6], row[6];
+  int64_t* counters;
+  int32_t counters_cap, counters_idx;
+  int64_t counter_val[5];
+  int32_t B, H, G, Dk, Dv, t;
+  float base, scale;
+  int32_t dtype;
+} nsa_decode_produce_t;
+int nsa_decode_produce(const nsa_decode_produce_t* a, void* stream);
+
 enum { NSA_WS_SCORE_SELECT = 0, NSA_WS_DECODE = 1, NSA_WS_PREFILL = 2, NSA_WS_SEL_BLOCKMAJOR = 3, NSA_WS_BWD = 4 };
 int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which);
 

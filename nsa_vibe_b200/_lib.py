@@ -34,6 +34,15 @@ class GateParams(C.Structure):
     _fields_ = [("fc1_w", C.c_void_p), ("fc1_b", C.c_void_p), ("fc2_w", C.c_void_p), ("fc2_b", C.c_void_p)]
 
 
+class DecodeProduce(C.Structure):
+    """struct nsa_decode_produce (include/nsa_b200.h)."""
+
+    _fields_ = [("y", C.c_void_p), ("q_out", C.c_void_p), ("slab", C.c_void_p * 6), ("cap", C.c_int32 * 6), ("row", C.c_int32 * 6),
+                ("counters", C.c_void_p), ("counters_cap", C.c_int32), ("counters_idx", C.c_int32), ("counter_val", C.c_int64 * 5),
+                ("B", C.c_int32), ("H", C.c_int32), ("G", C.c_int32), ("Dk", C.c_int32), ("Dv", C.c_int32), ("t", C.c_int32),
+                ("base", C.c_float), ("scale", C.c_float), ("dtype", C.c_int32)]
+
+
 _P, _I, _I64 = C.c_void_p, C.c_int, C.c_int64
 _DP, _GP = C.POINTER(Dims), C.POINTER(GateParams)
 
@@ -57,6 +66,7 @@ SIGNATURES = {
     "nsa_decode_fwd": (_I, [_DP] + [_P] * 7 + [_GP] + [_P] * 4),
     "nsa_rope_shape": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, C.c_float, C.c_float, _I, _I, _P]),
     "nsa_phi_avgpool": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, C.c_float, C.c_float, _I, _I, _P]),
+    "nsa_decode_produce": (_I, [C.c_void_p, _P]),
     "nsa_workspace_bytes": (_I64, [_DP, _I]),
 }
 

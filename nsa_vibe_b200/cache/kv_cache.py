@@ -132,6 +132,56 @@ class NSA_KV:
         self._append("K_cmp_raw_seq", K_raw_tok)
         self._append("V_cmp_raw_seq", V_raw_tok)
 
+    # ---- in-place decode append (one kernel writes the six token rows, ops.decode_produce) --------------
+    _TOKEN_FIELDS = ("K_sel", "V_sel", "K_win", "V_win", "K_cmp_raw_seq", "V_cmp_raw_seq")
+    _COUNTER_FIELDS = ("reads_pred", "reads_act_total", "reads_act_sel", "reads_act_cmp", "reads_act_win")
+
+    def token_append_slots(self, like: torch.Tensor):
+        """Slabs and row indices where the next token's (K_sel, V_sel, K_win, V_win, K_raw, V_raw) rows go; the caller writes
+        them on the device and then calls commit_token_append()."""
+        slabs, rows = [], []
+        for name in self._TOKEN_FIELDS:
+            cur: torch.Tensor = getattr(self, name)
+            if cur.dtype != like.dtype or cur.device != like.device:
+                if cur.shape[2] != 0:
+                    raise RuntimeError(f"NSA_KV.{name}: dtype/device of the cache does not match the new tokens")
+                setattr(self, name, like.new_zeros((cur.shape[0], cur.shape[1], 0, cur.shape[3])))
+                self._slabs.pop(name, None)
+            self._ensure(name, 1)
+            slabs.append(self._slabs[name])
+            rows.append(self._lens[name])
+        return slabs, rows
+
+    def commit_token_append(self, w: int) -> None:
+        for name in self._TOKEN_FIELDS:
+            if name in ("K_win", "V_win"):
+                self._lens["__w_" + name] = int(w)
+            self._lens[name] += 1
+            self._set_view(name)
+
+    def counter_slot(self):
+        """([5,cap] int64 slab, column) where the next step's read counters go (rows ordered as _COUNTER_FIELDS); the five
+        public tensors become views of it.  commit_counters() publishes the column."""
+        sync = "__ctr" in self._slabs and all(self._views.get(f) is getattr(self, f) for f in self._COUNTER_FIELDS)
+        n = self._lens["__ctr"] if sync else int(self.reads_pred.numel())
+        if not sync or self._slabs["__ctr"].shape[1] <= n:
+            new = torch.zeros((5, max(2 * n, 1024)), dtype=torch.int64, device=self.reads_pred.device)
+            for i, f in enumerate(self._COUNTER_FIELDS):
+                cur = getattr(self, f)
+                m = min(n, int(cur.numel()))
+                if m:
+                    new[i, :m] = cur[:m]
+            self._slabs["__ctr"], self._lens["__ctr"] = new, n
+        return self._slabs["__ctr"], n
+
+    def commit_counters(self) -> None:
+        n = self._lens["__ctr"] + 1
+        self._lens["__ctr"] = n
+        for i, f in enumerate(self._COUNTER_FIELDS):
+            v = self._slabs["__ctr"][i, :n]
+            self._views[f] = v
+            setattr(self, f, v)
+
     # ---- read counters (kv_cache.py:51-65) --------------------------------------------------------
     @staticmethod
     def _cat(t: torch.Tensor, val: int) -> torch.Tensor:

@@ -257,16 +257,50 @@ class NSAAttention(nn.Module):
         out = self.out(O.reshape(B, S, self.n_heads * self.d_v))
         return out, kv
 
+    def _decode_weights(self) -> torch.Tensor:
+        """The seven projection weights stacked as one [H*Dk + G*(3Dk+3Dv), dim] matrix (rebuilt when any of them changes), so
+        that a decode token needs ONE GEMM instead of seven M=B GEMVs."""
+        ws = (self.W_Q.weight, self.W_K_sel.weight, self.W_V_sel.weight, self.W_K_win.weight, self.W_V_win.weight,
+              self.W_K_cmp.weight, self.W_V_cmp.weight)
+        key = tuple((w.data_ptr(), w._version, w.dtype) for w in ws)
+        cached = getattr(self, "_wcat", None)
+        if cached is None or cached[0] != key:
+            with torch.no_grad():
+                cached = (key, torch.cat([w.detach() for w in ws], dim=0).contiguous())
+            self._wcat = cached
+        return cached[1]
+
+    def _decode_gate(self, cfg: ops.NSAConfig, dev):
+        if cfg.gate_mode != ops.GATE_MLP:
+            return None
+        ps = self.gate.params()
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        cached = getattr(self, "_gate_struct", None)
+        if cached is None or cached[0] != key:
+            cached = (key, ops._gate_struct(ps, dev))
+            self._gate_struct = cached
+        return cached[1]
+
     def _forward_decode(self, x: torch.Tensor, kv: NSA_KV) -> tuple[torch.Tensor, NSA_KV]:
-        """One decode step (nsa_attention.py:545-976)."""
+        """One decode step (nsa_attention.py:545-976): one GEMM for the seven projections, one kernel that rotates Q/K and writes
+        the token's six cache rows in place (ops.decode_produce), phi on emission steps, the fused decode kernel, the out GEMM."""
         B = x.shape[0]
+        G, Dk, Dv = self.n_kv_groups, self.d_k, self.d_v
         t = int(kv.K_sel.shape[2])  # position of the new token
         with torch.no_grad():
-            Q, K_sel, V_sel, K_win, V_win, K_raw, V_raw = self._project(x, t)
-            kv.update_selection_raw(K_sel, V_sel)
-            kv.update_window(K_win, V_win, self.w)
-            kv.append_cmp_raw(K_raw, V_raw)
-            S_raw = int(kv.K_cmp_raw_seq.shape[2])
+            y = F.linear(x.reshape(B, self.dim), self._decode_weights())
+            Q = torch.empty((B, 1, G, self.h_per_group, Dk), dtype=y.dtype, device=y.device)
+            slabs, rows = kv.token_append_slots(y)
+            S_raw = rows[4] + 1
+            num_cmp = 0 if S_raw < self.l else (S_raw - self.l) // self.d + 1
+            aux = not self._env_cache["disable_aux_stats"]
+            ctr, ctr_idx = kv.counter_slot() if aux else (None, 0)
+            reads = num_cmp + self.n_sel * self.l_sel + min(self.w, S_raw)  # :634-638
+            ops.decode_produce(y, Q, slabs, rows, H=self.n_heads, G=G, Dk=Dk, Dv=Dv, t=t, scale=self.rope_scale, counters=ctr,
+                               counters_idx=ctr_idx, counter_vals=(reads, reads, self.n_sel * self.l_sel, num_cmp, min(self.w, S_raw)))
+            kv.commit_token_append(self.w)
+            if aux:
+                kv.commit_counters()
             if S_raw >= self.l and (S_raw - self.l) % self.d == 0:  # emission schedule (:587-604)
                 K_new, V_new = ops.phi_avgpool(kv.K_cmp_raw_seq[:, :, S_raw - self.l:S_raw],
                                                kv.V_cmp_raw_seq[:, :, S_raw - self.l:S_raw], self.l, self.d, t0=S_raw - self.l)
@@ -274,18 +308,13 @@ class NSAAttention(nn.Module):
             need = max(t + 1, self.l_sel)
             if getattr(kv, "meta", None) is None or kv.meta.sel_starts.numel() * self.l_sel < t + 1 or kv.meta.sel_starts.numel() == 0:
                 kv.meta = build_block_meta(seq_len=need, l=self.l, d=self.d, l_sel=self.l_sel, n_sel=self.n_sel, w=self.w)
-            if not self._env_cache["disable_aux_stats"]:
-                num_cmp = 0 if S_raw < self.l else (S_raw - self.l) // self.d + 1
-                reads = num_cmp + self.n_sel * self.l_sel + min(self.w, S_raw)  # :634-638
-                kv.append_reads_pred(reads)
-                kv.append_reads_actual(reads, self.n_sel * self.l_sel, num_cmp, min(self.w, S_raw))
             cfg = self._cfg()
-            gate = self.gate.params() if cfg.gate_mode == ops.GATE_MLP else None
-            ranges = torch.empty((B, self.n_kv_groups, self.n_sel, 2), dtype=torch.int32, device=x.device)
+            ranges = torch.empty((B, G, self.n_sel, 2), dtype=torch.int32, device=x.device)
             n_win = kv.length("K_win")
             O = ops.decode_core(Q, kv.slab("K_sel"), kv.slab("V_sel"), kv.slab("K_win"), kv.slab("V_win"),
-                                kv.slab("K_cmp"), kv.slab("V_cmp"), gate, cfg, t=t, S_sel_kv=t + 1, S_win_kv=n_win,
-                                win_off=(t + 1) - n_win, S_cmp=int(kv.K_cmp.shape[2]), ranges_out=ranges)
+                                kv.slab("K_cmp"), kv.slab("V_cmp"), None, cfg, t=t, S_sel_kv=t + 1, S_win_kv=n_win,
+                                win_off=(t + 1) - n_win, S_cmp=int(kv.K_cmp.shape[2]), ranges_out=ranges,
+                                gate_cache=self._decode_gate(cfg, x.device) or ops._gate_struct(None, x.device))
             if self._env_cache["strict_asserts"]:
                 assert int(ranges[..., 1].max()) <= t + 1, "Selection must not access future tokens."
             self._last_ranges = ranges

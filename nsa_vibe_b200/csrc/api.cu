@@ -303,6 +303,12 @@ int nsa_phi_avgpool(const void* x, void* y, int BG, int S, int D, int l, int d, 
   return launch_phi_avgpool(x, y, BG, S, D, l, d, rope, t0, base, scale, backward, dtype, (cudaStream_t)stream);
 }
 
+int nsa_decode_produce(const nsa_decode_produce_t* a, void* stream) {
+  NSA_REQUIRE(a, "decode_produce: NULL argument block");
+  NSA_REQUIRE(a->dtype == NSA_F32 || a->dtype == NSA_BF16 || a->dtype == NSA_F16, "decode_produce: dtype %d", a->dtype);
+  return launch_decode_produce(*a, (cudaStream_t)stream);
+}
+
 int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which) {
   if (!dm) return 0;
   switch (which) {

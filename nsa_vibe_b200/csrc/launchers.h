@@ -46,6 +46,7 @@ int launch_rope_shape(const void* x, void* y, int B, int S, int V, int D, int sr
                       float base, float scale, int inverse, int dtype, cudaStream_t stream);
 int launch_phi_avgpool(const void* x, void* y, int BG, int S, int D, int l, int d, int rope, int t0, float base, float scale,
                        int backward, int dtype, cudaStream_t stream);
+int launch_decode_produce(const nsa_decode_produce_t& a, cudaStream_t stream);
 // tc_*.cu (tcgen05 / TMA kernels)
 bool tc_branch_supported(const nsa_dims_t& dm, int branch);
 bool tc_score_supported(const nsa_dims_t& dm);

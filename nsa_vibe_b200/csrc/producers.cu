@@ -195,4 +195,77 @@ int launch_phi_avgpool(const void* x, void* y, int BG, int S, int D, int l, int 
   return check_launch("phi_avgpool_kernel");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Decode-step producer: one kernel takes the token's fused projection output
+//   y [B, H*Dk + G*(3*Dk + 3*Dv)] = (Q | K_sel | V_sel | K_win | V_win | K_raw | V_raw)
+// rotates Q (as one H*Dk-wide vector) and the two K rows (per Dk-vector), and writes Q into its buffer and the six rows straight
+// into row `row` of their cache slabs [B,G,cap,D] -- the reference's seven rope / view / cat chains of a decode step
+// (nsa_attention.py:545-586, kv_cache.py:28-49).  It also records the step's read counters (kv_cache.py:51-65).
+// ---------------------------------------------------------------------------------------------------------------------
+using DecodeProduceArgs = nsa_decode_produce_t;  // include/nsa_b200.h
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+decode_produce_kernel(DecodeProduceArgs a) {
+  const int QW = a.H * a.Dk;
+  const int N = QW + a.G * (3 * a.Dk + 3 * a.Dv);
+  const int pairs = N / 2;
+  if (a.counters && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 5)
+    a.counters[(size_t)threadIdx.x * a.counters_cap + a.counters_idx] = a.counter_val[threadIdx.x];
+  const int pc = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (pc >= pairs) return;
+  const int c = 2 * pc;  // column of y
+  const T* src = reinterpret_cast<const T*>(a.y) + (size_t)b * N + c;
+  const float x0 = PrT<T>::ld(src), x1 = PrT<T>::ld(src + 1);
+  const float inv_scale = __fdiv_rn(1.0f, a.scale);
+  float y0 = x0, y1 = x1;
+  T* dst;
+  if (c < QW) {
+    const float inv_freq = powf(a.base, __fmul_rn(__fmul_rn(-2.0f, (float)pc), __fdiv_rn(1.0f, (float)QW)));
+    float sn, cs;
+    sincosf(__fmul_rn(__fmul_rn((float)a.t, inv_scale), inv_freq), &sn, &cs);
+    rope_rotate<T>(x0, x1, PrT<T>::rnd(sn), PrT<T>::rnd(cs), false, y0, y1);
+    dst = reinterpret_cast<T*>(a.q_out) + (size_t)b * QW + c;
+  } else {
+    // segments after Q: (K_sel, V_sel, K_win, V_win, K_raw, V_raw), widths G*Dk / G*Dv alternating
+    int off = c - QW, seg = 0;
+    for (; seg < 6; ++seg) {
+      const int wdt = a.G * ((seg & 1) ? a.Dv : a.Dk);
+      if (off < wdt) break;
+      off -= wdt;
+    }
+    const int D = (seg & 1) ? a.Dv : a.Dk;
+    const int g = off / D, e = off - g * D;
+    if (seg == 0 || seg == 2) {  // RoPE'd keys of the selection and window caches
+      const float inv_freq = powf(a.base, __fmul_rn(__fmul_rn(-2.0f, (float)(e / 2)), __fdiv_rn(1.0f, (float)D)));
+      float sn, cs;
+      sincosf(__fmul_rn(__fmul_rn((float)a.t, inv_scale), inv_freq), &sn, &cs);
+      rope_rotate<T>(x0, x1, PrT<T>::rnd(sn), PrT<T>::rnd(cs), false, y0, y1);
+    }
+    dst = reinterpret_cast<T*>(a.slab[seg]) + (((size_t)b * a.G + g) * a.cap[seg] + a.row[seg]) * D + e;
+  }
+  PrT<T>::st(dst, y0);
+  PrT<T>::st(dst + 1, y1);
+}
+
+int launch_decode_produce(const nsa_decode_produce_t& a, cudaStream_t stream) {
+  const int dtype = a.dtype;
+  NSA_REQUIRE(a.y && a.q_out, "decode_produce: NULL pointer");
+  for (int i = 0; i < 6; ++i) NSA_REQUIRE(a.slab[i] && a.row[i] >= 0 && a.row[i] < a.cap[i], "decode_produce: slab %d row %d cap %d", i, a.row[i], a.cap[i]);
+  NSA_REQUIRE(a.B >= 0 && a.H >= 1 && a.G >= 1 && a.Dk >= 2 && a.Dv >= 2 && a.Dk % 2 == 0 && a.Dv % 2 == 0, "decode_produce: bad geometry");
+  NSA_REQUIRE(!a.counters || (a.counters_idx >= 0 && a.counters_idx < a.counters_cap), "decode_produce: counter index");
+  if (a.B == 0) return NSA_OK;
+  DecodeProduceArgs b = a;
+  if (!(b.scale > 0.f)) b.scale = 1.0f;
+  const int pairs = (a.H * a.Dk + a.G * (3 * a.Dk + 3 * a.Dv)) / 2;
+  const dim3 grid((pairs + 255) / 256, a.B);
+  NSA_REQUIRE(a.B <= 65535, "decode_produce: B=%d", a.B);
+  if (dtype == NSA_F32) decode_produce_kernel<float><<<grid, 256, 0, stream>>>(b);
+  else if (dtype == NSA_BF16) decode_produce_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(b);
+  else decode_produce_kernel<__half><<<grid, 256, 0, stream>>>(b);
+  return check_launch("decode_produce_kernel");
+}
+
 }  // namespace nsa

@@ -430,6 +430,33 @@ def phi_avgpool(K_raw: torch.Tensor, V_raw: torch.Tensor, l: int, d: int, *, t0:
     return _PhiAvgPool.apply(K_raw, l, d, 1, t0), _PhiAvgPool.apply(V_raw, l, d, 0, t0)
 
 
+def decode_produce(y: torch.Tensor, q_out: torch.Tensor, slabs, rows, *, H: int, G: int, Dk: int, Dv: int, t: int,
+                   base: float = 10000.0, scale: float = 1.0, counters: Optional[torch.Tensor] = None, counters_idx: int = 0,
+                   counter_vals=(0, 0, 0, 0, 0)) -> None:
+    """One decode token's fused projection output y [B, H*Dk + G*(3*Dk+3*Dv)] = (Q | K_sel | V_sel | K_win | V_win | K_raw |
+    V_raw) -> RoPE'd Q into q_out [B, H*Dk] and the six rows into row rows[i] of slabs[i] ([B,G,cap,D], contiguous), in ONE
+    launch: the reference's seven rope/view/cat chains of a decode step (nsa_attention.py:545-586, kv_cache.py:28-49).
+    counters ([5,cap] int64, optional) receives the step's read counters (kv_cache.py:51-65) at column counters_idx."""
+    _require_cuda(y, q_out, *slabs)
+    B = y.shape[0]
+    if not y.is_contiguous() or y.shape[-1] != H * Dk + G * (3 * Dk + 3 * Dv) or not q_out.is_contiguous():
+        raise RuntimeError("decode_produce: y must be contiguous [B, H*Dk + G*(3*Dk+3*Dv)]")
+    a = _lib.DecodeProduce()
+    a.y, a.q_out = y.data_ptr(), q_out.data_ptr()
+    for i, (sl, r) in enumerate(zip(slabs, rows)):
+        D = Dv if (i & 1) else Dk
+        if not sl.is_contiguous() or sl.dtype != y.dtype or sl.shape[0] != B or sl.shape[1] != G or sl.shape[3] != D:
+            raise RuntimeError(f"decode_produce: slab {i} must be contiguous [B,G,cap,{D}] of dtype {y.dtype}")
+        a.slab[i], a.cap[i], a.row[i] = sl.data_ptr(), int(sl.shape[2]), int(r)
+    if counters is not None:
+        a.counters, a.counters_cap, a.counters_idx = counters.data_ptr(), int(counters.shape[1]), int(counters_idx)
+        for i, v in enumerate(counter_vals):
+            a.counter_val[i] = int(v)
+    a.B, a.H, a.G, a.Dk, a.Dv, a.t = B, H, G, Dk, Dv, int(t)
+    a.base, a.scale, a.dtype = float(base), float(scale if scale > 0 else 1.0), _DTYPES[y.dtype]
+    _call("nsa_decode_produce", C.byref(a), _stream())
+
+
 # ----------------------------------------------------------------------------------------------------
 # fused hot path: decode
 # ----------------------------------------------------------------------------------------------------

@@ -66,3 +66,53 @@ def test_phi_avgpool_matches_torch_chain(dtype, B, G, S, D, l, d, t0):
     (Vw.float() * dv.float()).sum().backward()
     assert torch.allclose(ka.grad.float(), kb.grad.float(), **_tol(dtype)), (ka.grad.float() - kb.grad.float()).abs().max()
     assert torch.allclose(va.grad.float(), vb.grad.float(), **_tol(dtype))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,G,Dk,Dv,t,scale", [(3, 12, 2, 64, 64, 0, 1.0), (2, 4, 2, 16, 32, 777, 1.0), (5, 12, 2, 64, 64, 4095, 2.0)])
+def test_decode_produce_matches_the_seven_chains(dtype, B, H, G, Dk, Dv, t, scale):
+    """One launch = rope(Q as one vector), rope(K_sel), rope(K_win) per Dk-vector, six rows scattered into their slabs
+    (nsa_attention.py:545-586), and the step's read counters (kv_cache.py:51-65)."""
+    ops, _, _ = _mods()
+    g = torch.Generator(device="cuda").manual_seed(B + t)
+    widths = [H * Dk] + [G * Dk, G * Dv] * 3
+    y = torch.randn(B, sum(widths), generator=g, device="cuda").to(dtype)
+    parts = torch.split(y, widths, dim=-1)
+    caps = [9, 11, 7, 8, 13, 10]
+    rows = [4, 10, 0, 3, 12, 5]
+    slabs = [torch.full((B, G, caps[i], Dv if i & 1 else Dk), 7.0, device="cuda", dtype=dtype) for i in range(6)]
+    q = torch.empty(B, H * Dk, device="cuda", dtype=dtype)
+    ctr = torch.zeros(5, 16, dtype=torch.int64, device="cuda")
+    ops.decode_produce(y, q, slabs, rows, H=H, G=G, Dk=Dk, Dv=Dv, t=t, scale=scale, counters=ctr, counters_idx=3,
+                       counter_vals=(11, 12, 13, 14, 15))
+    want_q = ops.rope_shape(parts[0].contiguous().view(B, 1, -1), H, Dk, rope="token", t0=t, scale=scale).reshape(B, H * Dk)
+    assert torch.equal(q, want_q)
+    for i in range(6):
+        D = Dv if i & 1 else Dk
+        rope = "vector" if i in (0, 2) else "none"
+        want = ops.rope_shape(parts[1 + i].contiguous().view(B, 1, -1), G, D, rope=rope, to_cache_layout=True, t0=t, scale=scale)
+        assert torch.equal(slabs[i][:, :, rows[i]], want[:, :, 0]), i
+        mask = torch.ones(caps[i], dtype=torch.bool, device="cuda")
+        mask[rows[i]] = False
+        assert bool((slabs[i][:, :, mask] == 7.0).all()), f"slab {i}: rows other than {rows[i]} were touched"
+    assert ctr[:, 3].tolist() == [11, 12, 13, 14, 15] and int(ctr.sum()) == 65
+
+
+def test_kv_inplace_append_keeps_reference_views():
+    """NSA_KV.token_append_slots / commit_token_append / counter_slot keep the reference's public tensors (kv_cache.py:8-65)."""
+    from nsa_vibe_b200.cache.kv_cache import create_empty_kv
+    from nsa_vibe_b200.core.block_index import build_block_meta
+    kv = create_empty_kv(2, 2, 16, 16, build_block_meta(64, 8, 4, 16, 2, 4), device=torch.device("cuda"), dtype=torch.float32)
+    like = torch.empty(1, device="cuda", dtype=torch.bfloat16)
+    for step in range(70):
+        slabs, rows = kv.token_append_slots(like)
+        assert rows == [step] * 6
+        for s in slabs:
+            s[:, :, step] = step
+        c, idx = kv.counter_slot()
+        c[:, idx] = step
+        kv.commit_token_append(4)
+        kv.commit_counters()
+    assert kv.K_sel.shape == (2, 2, 70, 16) and kv.K_sel.dtype == torch.bfloat16 and kv.K_win.shape == (2, 2, 4, 16)
+    assert kv.K_win[0, 0, :, 0].tolist() == [66, 67, 68, 69] and kv.K_sel[1, 1, :, 3].tolist() == list(range(70))
+    assert kv.reads_pred.tolist() == list(range(70)) and kv.reads_act_win.shape == (70,)
