@@ -179,6 +179,19 @@ typedef struct nsa_decode_produce {
 } nsa_decode_produce_t;
 int nsa_decode_produce(const nsa_decode_produce_t* a, void* stream);
 
+/* ---- caller-side row kernels of the block around the hot path ---------------------------------------
+ * RMSNorm (nsa/model/llama_block_nsa.py:13-22: y = x * rsqrt(mean(x^2) + eps) * w) fused with the residual add feeding it
+ * (llama_block_nsa.py:102-106: x = x + attn_out; mlp(norm2(x))) and with the cast of its consumers: x, s_out, dx, ds are
+ * [rows, dim] in x_dtype, r in r_dtype, y / dy in y_dtype, w / dw [dim] in w_dtype; fp32 arithmetic, one rounding on the way out.
+ *   fwd: s = x (+ r, then s is written to s_out); rstd[row] saved (fp32, may be NULL); y = (s * rstd) * w.
+ *   bwd: dx = rstd * (dy*w - xh * mean(dy*w*xh)) (+ ds), xh = s * rstd; dw = sum_rows dy * xh (dw may be NULL; otherwise
+ *        dw_partial is a caller-owned [nsa_rmsnorm_partials(rows), dim] fp32 workspace).  dim % 4 == 0. */
+int nsa_rmsnorm_fwd(const void* x, const void* r, const void* w, void* s_out, void* y, float* rstd, int rows, int dim, float eps,
+                    int x_dtype, int r_dtype, int w_dtype, int y_dtype, void* stream);
+int nsa_rmsnorm_bwd(const void* dy, const void* s, const void* w, const float* rstd, const void* ds, void* dx, void* dw,
+                    float* dw_partial, int rows, int dim, int x_dtype, int w_dtype, int y_dtype, void* stream);
+int nsa_rmsnorm_partials(int rows);
+
 enum { NSA_WS_SCORE_SELECT = 0, NSA_WS_DECODE = 1, NSA_WS_PREFILL = 2, NSA_WS_SEL_BLOCKMAJOR = 3, NSA_WS_BWD = 4 };
 int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which);
 

@@ -67,6 +67,9 @@ SIGNATURES = {
     "nsa_rope_shape": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, C.c_float, C.c_float, _I, _I, _P]),
     "nsa_phi_avgpool": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, C.c_float, C.c_float, _I, _I, _P]),
     "nsa_decode_produce": (_I, [C.c_void_p, _P]),
+    "nsa_rmsnorm_fwd": (_I, [_P] * 6 + [_I, _I, C.c_float, _I, _I, _I, _I, _P]),
+    "nsa_rmsnorm_bwd": (_I, [_P] * 8 + [_I, _I, _I, _I, _I, _P]),
+    "nsa_rmsnorm_partials": (_I, [_I]),
     "nsa_workspace_bytes": (_I64, [_DP, _I]),
 }
 

@@ -70,7 +70,7 @@ class NSA_KV:
         n = self._lens[name]
         window = self._lens.get("__w_" + name)
         lo = max(0, n - window) if window is not None else 0
-        v = self._slabs[name][:, :, lo:n]
+        v = self._slabs[name].narrow(2, lo, n - lo)
         self._views[name] = v
         setattr(self, name, v)
 

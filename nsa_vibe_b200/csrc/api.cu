@@ -309,6 +309,18 @@ int nsa_decode_produce(const nsa_decode_produce_t* a, void* stream) {
   return launch_decode_produce(*a, (cudaStream_t)stream);
 }
 
+int nsa_rmsnorm_fwd(const void* x, const void* r, const void* w, void* s_out, void* y, float* rstd, int rows, int dim, float eps,
+                    int x_dtype, int r_dtype, int w_dtype, int y_dtype, void* stream) {
+  return launch_rmsnorm_fwd(x, r, w, s_out, y, rstd, rows, dim, eps, x_dtype, r_dtype, w_dtype, y_dtype, (cudaStream_t)stream);
+}
+
+int nsa_rmsnorm_bwd(const void* dy, const void* s, const void* w, const float* rstd, const void* ds, void* dx, void* dw,
+                    float* dw_partial, int rows, int dim, int x_dtype, int w_dtype, int y_dtype, void* stream) {
+  return launch_rmsnorm_bwd(dy, s, w, rstd, ds, dx, dw, dw_partial, rows, dim, x_dtype, w_dtype, y_dtype, (cudaStream_t)stream);
+}
+
+int nsa_rmsnorm_partials(int rows) { return rmsnorm_partials(rows); }
+
 int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which) {
   if (!dm) return 0;
   switch (which) {

@@ -47,6 +47,12 @@ int launch_rope_shape(const void* x, void* y, int B, int S, int V, int D, int sr
 int launch_phi_avgpool(const void* x, void* y, int BG, int S, int D, int l, int d, int rope, int t0, float base, float scale,
                        int backward, int dtype, cudaStream_t stream);
 int launch_decode_produce(const nsa_decode_produce_t& a, cudaStream_t stream);
+// block_ops.cu
+int launch_rmsnorm_fwd(const void* x, const void* r, const void* w, void* s_out, void* y, float* rstd, int rows, int dim, float eps,
+                       int x_dtype, int r_dtype, int w_dtype, int y_dtype, cudaStream_t stream);
+int launch_rmsnorm_bwd(const void* dy, const void* s, const void* w, const float* rstd, const void* ds, void* dx, void* dw,
+                       float* dw_partial, int rows, int dim, int x_dtype, int w_dtype, int y_dtype, cudaStream_t stream);
+int rmsnorm_partials(int rows);
 // tc_*.cu (tcgen05 / TMA kernels)
 bool tc_branch_supported(const nsa_dims_t& dm, int branch);
 bool tc_score_supported(const nsa_dims_t& dm);

@@ -1,25 +1,40 @@
 """LlamaBlockNSA (nsa/model/llama_block_nsa.py:33-106): RMSNorm -> NSAAttention -> residual -> RMSNorm -> SiLU MLP.
-The caller of the hot path; plain torch around the B200 NSAAttention."""
+The caller of the hot path: nn.Linear GEMMs around the B200 NSAAttention, RMSNorm (+ residual add) as one kernel per direction."""
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import ops
 from ..cache.kv_cache import create_empty_kv
 from ..core.block_index import build_block_meta
 from ..core.nsa_attention import NSAAttention
 
 
+def rmsnorm_torch(x: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
+    """The reference's formula (llama_block_nsa.py:19-22), kept as the comparator of the kernel in tests."""
+    rms = x.pow(2).mean(dim=-1, keepdim=True).add(eps).rsqrt()
+    return (x * rms) * weight
+
+
+def _norm_out_dtype(x: torch.Tensor) -> torch.dtype:
+    # under autocast every consumer of a norm output is an nn.Linear that would cast it: emit that dtype directly
+    if torch.is_autocast_enabled("cuda") and x.dtype == torch.float32:
+        return torch.get_autocast_dtype("cuda")
+    return x.dtype
+
+
 class RMSNorm(nn.Module):
+    """llama_block_nsa.py:13-22; one kernel per direction (ops.rmsnorm).  forward(x, residual=r) returns (x + r, norm(x + r))."""
+
     def __init__(self, dim: int, eps: float = 1e-6) -> None:
         super().__init__()
         self.weight = nn.Parameter(torch.ones(dim))
         self.eps = eps
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        rms = x.pow(2).mean(dim=-1, keepdim=True).add(self.eps).rsqrt()
-        return (x * rms) * self.weight
+    def forward(self, x: torch.Tensor, residual: torch.Tensor = None):
+        return ops.rmsnorm(x, self.weight, self.eps, residual=residual, out_dtype=_norm_out_dtype(x))
 
 
 class MLP(nn.Module):
@@ -49,5 +64,5 @@ class LlamaBlockNSA(nn.Module):
         meta = build_block_meta(S, a.l, a.d, a.l_sel, a.n_sel, a.w)
         kv = create_empty_kv(B, a.n_kv_groups, a.d_k, a.d_v, meta, device=x.device, dtype=xn.dtype)
         out, _ = a(xn, kv, prefill=True)
-        x = x + out
-        return x + self.mlp(self.norm2(x))
+        x, xn2 = self.norm2(x, residual=out)  # x = x + out and norm2(x) in one pass
+        return x + self.mlp(xn2)

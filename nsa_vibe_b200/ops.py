@@ -43,7 +43,8 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # raw handle of torch's current stream on the current device (torch.cuda.current_stream() costs ~10 us of Python per call)
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
 
 
 def _require_cuda(*ts):
@@ -488,3 +489,67 @@ def decode_core(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, gate, cfg: NSAConfi
     _call("nsa_decode_fwd", C.byref(dm), _ptr(Q), _ptr(K_sel), _ptr(V_sel), _ptr(K_win), _ptr(V_win), _ptr(K_cmp),
           _ptr(V_cmp), C.byref(gp), _ptr(O), _ptr(ranges_out), _ptr(ws), _stream())
     return O
+
+
+# ----------------------------------------------------------------------------------------------------
+# caller-side row kernels of the block around the hot path
+# ----------------------------------------------------------------------------------------------------
+class _RMSNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, weight, eps, out_dtype):
+        xc = _c(x)
+        rc = None if residual is None else _c(residual)
+        dim = xc.shape[-1]
+        rows = xc.numel() // dim if dim else 0
+        y = torch.empty(xc.shape, dtype=out_dtype, device=xc.device)
+        s = torch.empty_like(xc) if rc is not None else xc
+        rstd = torch.empty(rows, dtype=torch.float32, device=xc.device)
+        wc = _c(weight)
+        if rows:
+            _call("nsa_rmsnorm_fwd", _ptr(xc), _ptr(rc), _ptr(wc), _ptr(s) if rc is not None else None, _ptr(y), _ptr(rstd), rows, dim,
+                  float(eps), _DTYPES[xc.dtype], _DTYPES[rc.dtype] if rc is not None else 0, _DTYPES[wc.dtype], _DTYPES[out_dtype], _stream())
+        ctx.save_for_backward(s, wc, rstd)
+        ctx.has_res = rc is not None
+        ctx.res_dtype = None if rc is None else rc.dtype
+        if rc is not None:
+            return s, y
+        return y
+
+    @staticmethod
+    def backward(ctx, *grads):
+        s, w, rstd = ctx.saved_tensors
+        ds, dy = (grads if ctx.has_res else (None, grads[0]))
+        dim = s.shape[-1]
+        rows = s.numel() // dim if dim else 0
+        if dy is None:  # only the running sum was used downstream
+            return (ds, None if ds is None else ds.to(ctx.res_dtype), None, None, None) if ctx.has_res else (None,) * 5
+        dyc = _c(dy)
+        dsc = None if ds is None else _c(ds.to(s.dtype))
+        dx = torch.empty_like(s)
+        need_dw = ctx.needs_input_grad[2]
+        dw = torch.empty_like(w) if need_dw else None
+        part = None
+        if need_dw:
+            part = torch.empty((int(_lib.load().nsa_rmsnorm_partials(rows)), dim), dtype=torch.float32, device=s.device)
+        _call("nsa_rmsnorm_bwd", _ptr(dyc), _ptr(s), _ptr(w), _ptr(rstd), _ptr(dsc), _ptr(dx), _ptr(dw), _ptr(part), rows, dim,
+              _DTYPES[s.dtype], _DTYPES[w.dtype], _DTYPES[dyc.dtype], _stream())
+        return dx, (dx.to(ctx.res_dtype) if ctx.has_res else None), dw, None, None
+
+
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-6, *, residual: Optional[torch.Tensor] = None,
+            out_dtype: Optional[torch.dtype] = None):
+    """RMSNorm (nsa/model/llama_block_nsa.py:13-22) in one pass, optionally fused with the residual add that feeds it
+    (llama_block_nsa.py:102-106) and emitting the dtype its consumers want (under autocast the projections cast the fp32 norm output
+    to bf16 once each; rounding the same fp32 value here is bit-equal and is done once).
+    residual=None -> y;  residual=r -> (s, y) with s = x + r (dtype of x) and y = norm(s)."""
+    _require_cuda(x, weight, residual)
+    if x.dtype not in _DTYPES or weight.dtype not in _DTYPES:
+        raise RuntimeError(f"rmsnorm: unsupported dtype {x.dtype} / {weight.dtype}")
+    if x.shape[-1] % 4 != 0 or x.shape[-1] != weight.shape[-1]:
+        raise RuntimeError(f"rmsnorm: dim {x.shape[-1]} must be a multiple of 4 and match the weight ({tuple(weight.shape)})")
+    if residual is not None and (residual.shape != x.shape or residual.dtype not in _DTYPES):
+        raise RuntimeError("rmsnorm: residual must have the shape of x and a supported dtype")
+    od = out_dtype if out_dtype is not None else x.dtype
+    if od not in _DTYPES:
+        raise RuntimeError(f"rmsnorm: unsupported output dtype {od}")
+    return _RMSNorm.apply(x, residual, weight, eps, od)

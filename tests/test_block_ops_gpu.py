@@ -1,0 +1,90 @@
+"""RMSNorm (+ residual add, + output cast) kernel, forward and backward, against the reference's formula
+(nsa/model/llama_block_nsa.py:13-22, restated as model.llama_block_nsa.rmsnorm_torch) evaluated in fp32 with autograd.
+Tolerances: fp32 in/out max-abs 2e-5 (the only difference is the summation order of mean(x^2) and of the dw column sums);
+16-bit outputs one rounding step (2^-8 relative) around the fp32 result."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+_EPS = 1e-6
+
+
+def _ref(x, w, r=None):
+    from nsa_vibe_b200.model.llama_block_nsa import rmsnorm_torch
+    s = x if r is None else x + r
+    return s, rmsnorm_torch(s, w, _EPS)
+
+
+def _close(a, b, dt):
+    a, b = a.float(), b.float()
+    tol = 2e-5 if dt == torch.float32 else 1.6e-2
+    assert torch.allclose(a, b, atol=tol, rtol=tol), (dt, (a - b).abs().max())
+
+
+@pytest.mark.parametrize("shape", [(2, 37, 768), (1, 1, 64), (5, 132), (3000, 256)])
+@pytest.mark.parametrize("xdt,wdt,odt", [(torch.float32, torch.float32, torch.float32), (torch.float32, torch.float32, torch.bfloat16),
+                                         (torch.bfloat16, torch.bfloat16, torch.bfloat16), (torch.float16, torch.float32, torch.float16)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_rmsnorm_forward_backward(shape, xdt, wdt, odt, with_res):
+    from nsa_vibe_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(shape[0] + shape[-1])
+    x32 = torch.randn(*shape, generator=g, device="cuda") * 1.7
+    w32 = torch.rand(shape[-1], generator=g, device="cuda") + 0.5
+    r32 = torch.randn(*shape, generator=g, device="cuda") if with_res else None
+    rdt = torch.bfloat16 if (with_res and xdt == torch.float32 and odt == torch.bfloat16) else xdt  # residual of another dtype
+    x = x32.to(xdt).requires_grad_(True)
+    w = w32.to(wdt).requires_grad_(True)
+    r = None if r32 is None else r32.to(rdt).requires_grad_(True)
+    xr = x.detach().float().requires_grad_(True)
+    wr = w.detach().float().requires_grad_(True)
+    rr = None if r is None else r.detach().float().requires_grad_(True)
+    got = ops.rmsnorm(x, w, _EPS, residual=r, out_dtype=odt)
+    s_ref, y_ref = _ref(xr, wr, rr)
+    if with_res:
+        s, y = got
+        assert s.dtype == xdt and y.dtype == odt
+        _close(s, s_ref, xdt)
+    else:
+        y = got
+        assert y.dtype == odt
+    # a 16-bit running sum is rounded before the norm sees it (as in torch): compare against the norm of the rounded sum
+    if with_res and xdt != torch.float32:
+        _, y_ref2 = _ref(s.detach().float(), wr.detach())
+        _close(y, y_ref2, odt)
+    else:
+        _close(y, y_ref, odt)
+    dy = torch.randn(*shape, generator=g, device="cuda")
+    dsum = torch.randn(*shape, generator=g, device="cuda") if with_res else None
+    loss = (y.float() * dy).sum() + ((s.float() * dsum).sum() if with_res else 0.0)
+    loss_ref = (y_ref * dy).sum() + ((s_ref * dsum).sum() if with_res else 0.0)
+    loss.backward()
+    loss_ref.backward()
+    gt = 2e-4 if (xdt == torch.float32 and odt == torch.float32) else 6e-2
+    scale = max(1.0, float(xr.grad.abs().max()))
+    assert (x.grad.float() - xr.grad).abs().max() <= gt * scale, (x.grad.float() - xr.grad).abs().max()
+    wscale = max(1.0, float(wr.grad.abs().max()))
+    assert (w.grad.float() - wr.grad).abs().max() <= gt * wscale, ((w.grad.float() - wr.grad).abs().max(), wscale)
+    if with_res:
+        assert (r.grad.float() - rr.grad).abs().max() <= gt * scale
+
+
+def test_rmsnorm_module_autocast_emits_bf16_equal_to_cast_of_fp32():
+    """Under autocast the norm emits bf16 directly: bit-equal to casting the fp32 output (what the consuming nn.Linear would do)."""
+    from nsa_vibe_b200.model.llama_block_nsa import RMSNorm
+    torch.manual_seed(3)
+    n = RMSNorm(768).cuda()
+    x = torch.randn(4, 50, 768, device="cuda")
+    y32 = n(x)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y16 = n(x)
+    assert y32.dtype == torch.float32 and y16.dtype == torch.bfloat16
+    assert torch.equal(y16, y32.to(torch.bfloat16))
+
+
+def test_rmsnorm_rejects_cpu_and_bad_dims():
+    from nsa_vibe_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.rmsnorm(torch.randn(2, 8), torch.ones(8))
+    with pytest.raises(RuntimeError):
+        ops.rmsnorm(torch.randn(2, 6, device="cuda"), torch.ones(6, device="cuda"))
