@@ -160,11 +160,14 @@ int nsa_rope_shape(const void* x, void* y, int B, int S, int V, int D, int src_l
 int nsa_phi_avgpool(const void* x, void* y, int BG, int S, int D, int l, int d, int rope, int t0, float base, float scale,
                     int backward, int dtype, void* stream);
 
-/* Producer of one decode step: the token's fused projection output y [B, H*Dk + G*(3*Dk + 3*Dv)] =
- * (Q | K_sel | V_sel | K_win | V_win | K_raw | V_raw) is rotated (Q as one H*Dk-wide vector, K_sel / K_win per Dk-vector;
- * position t) and scattered: Q into q_out [B, H*Dk], the six rows into row `row[i]` of their cache slabs [B,G,cap[i],D] --
- * the seven rope / view / torch.cat chains of the reference's decode step (nsa_attention.py:545-586, kv_cache.py:28-49) in one
- * launch.  counters (optional, [5][counters_cap] int64): the step's read counters (kv_cache.py:51-65) written at counters_idx. */
+/* Projection-split producer: the fused projection output y [B, S, H*Dk + G*(3*Dk + 3*Dv)] =
+ * (Q | K_sel | V_sel | K_win | V_win | K_raw | V_raw) of S tokens per sequence is rotated (Q as one H*Dk-wide vector, K_sel /
+ * K_win per Dk-vector; row s at position t + s) and scattered: Q into q_out [B,S,H*Dk], the six streams into rows
+ * row[i] .. row[i]+S-1 of slab[i] ([B,G,cap[i],D]) -- the seven rope / view / permute / torch.cat chains of the reference
+ * (nsa_attention.py:545-586 decode, :998-1016 prefill, kv_cache.py:28-49) in one launch.  S = 1 with the cache slabs as
+ * destinations is a decode step.  inverse = 1 is the backward pass: the seven gradients are read from q_out / slab and dy is
+ * written to y.  counters (optional, [5][counters_cap] int64): the step's read counters (kv_cache.py:51-65) written at
+ * counters_idx. */
 typedef struct nsa_decode_produce {
   const void* y;
   void* q_out;
@@ -176,6 +179,7 @@ typedef struct nsa_decode_produce {
   int32_t B, H, G, Dk, Dv, t;
   float base, scale;
   int32_t dtype;
+  int32_t S, inverse;
 } nsa_decode_produce_t;
 int nsa_decode_produce(const nsa_decode_produce_t* a, void* stream);
 

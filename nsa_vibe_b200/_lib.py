@@ -40,7 +40,7 @@ class DecodeProduce(C.Structure):
     _fields_ = [("y", C.c_void_p), ("q_out", C.c_void_p), ("slab", C.c_void_p * 6), ("cap", C.c_int32 * 6), ("row", C.c_int32 * 6),
                 ("counters", C.c_void_p), ("counters_cap", C.c_int32), ("counters_idx", C.c_int32), ("counter_val", C.c_int64 * 5),
                 ("B", C.c_int32), ("H", C.c_int32), ("G", C.c_int32), ("Dk", C.c_int32), ("Dv", C.c_int32), ("t", C.c_int32),
-                ("base", C.c_float), ("scale", C.c_float), ("dtype", C.c_int32)]
+                ("base", C.c_float), ("scale", C.c_float), ("dtype", C.c_int32), ("S", C.c_int32), ("inverse", C.c_int32)]
 
 
 _P, _I, _I64 = C.c_void_p, C.c_int, C.c_int64

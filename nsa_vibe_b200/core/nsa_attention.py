@@ -193,21 +193,16 @@ class NSAAttention(nn.Module):
                         f"This ensures proper causal ordering in decode steps.")
         return self._forward_decode(x, kv)
 
+    def _proj_weights(self):
+        return (self.W_Q.weight, self.W_K_sel.weight, self.W_V_sel.weight, self.W_K_win.weight, self.W_V_win.weight,
+                self.W_K_cmp.weight, self.W_V_cmp.weight)
+
     def _project(self, x: torch.Tensor, t0: int):
-        """Projections (cuBLAS through nn.Linear) followed by ONE kernel per tensor that applies RoPE and writes the cache
-        layout (ops.rope_shape) -- the reference's rope + view + permute + contiguous chain (nsa_attention.py:998-1016)."""
-        rs = self.rope_scale
-        G, Dk, Dv = self.n_kv_groups, self.d_k, self.d_v
-        # the reference rotates Q as ONE vector of width n_heads*d_k (nsa_attention.py:1002-1009, :551-556)
-        Q = ops.rope_shape(self.W_Q(x), self.n_heads, Dk, rope="token", t0=t0, scale=rs)
-        Q = Q.view(x.shape[0], x.shape[1], G, self.h_per_group, Dk)
-        K_sel = ops.rope_shape(self.W_K_sel(x), G, Dk, rope="vector", to_cache_layout=True, t0=t0, scale=rs)
-        V_sel = ops.rope_shape(self.W_V_sel(x), G, Dv, to_cache_layout=True)
-        K_win = ops.rope_shape(self.W_K_win(x), G, Dk, rope="vector", to_cache_layout=True, t0=t0, scale=rs)
-        V_win = ops.rope_shape(self.W_V_win(x), G, Dv, to_cache_layout=True)
-        K_raw = ops.rope_shape(self.W_K_cmp(x), G, Dk, to_cache_layout=True)
-        V_raw = ops.rope_shape(self.W_V_cmp(x), G, Dv, to_cache_layout=True)
-        return Q, K_sel, V_sel, K_win, V_win, K_raw, V_raw
+        """The seven projections as ONE GEMM over the stacked weights (cuBLAS through F.linear; the state dict keeps the seven
+        nn.Linear parameters), followed by ONE kernel that applies RoPE and writes Q and the six cache-layout tensors
+        (ops.project_split) -- the reference's per-tensor rope + view + permute + contiguous chains (nsa_attention.py:998-1016)."""
+        y = F.linear(x, torch.cat(self._proj_weights(), dim=0))
+        return ops.project_split(y, H=self.n_heads, G=self.n_kv_groups, Dk=self.d_k, Dv=self.d_v, t0=t0, scale=self.rope_scale)
 
     def _nvtx(self, name: Optional[str]):
         if self._env_cache["nvtx"]:
@@ -260,8 +255,7 @@ class NSAAttention(nn.Module):
     def _decode_weights(self) -> torch.Tensor:
         """The seven projection weights stacked as one [H*Dk + G*(3Dk+3Dv), dim] matrix (rebuilt when any of them changes), so
         that a decode token needs ONE GEMM instead of seven M=B GEMVs."""
-        ws = (self.W_Q.weight, self.W_K_sel.weight, self.W_V_sel.weight, self.W_K_win.weight, self.W_V_win.weight,
-              self.W_K_cmp.weight, self.W_V_cmp.weight)
+        ws = self._proj_weights()
         key = tuple((w.data_ptr(), w._version, w.dtype) for w in ws)
         cached = getattr(self, "_wcat", None)
         if cached is None or cached[0] != key:

@@ -11,16 +11,36 @@ namespace nsa {
 
 template <typename T> struct PrT;
 template <> struct PrT<float> {
+  static __device__ __forceinline__ void ld2(const float* p, float& a, float& b) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    a = t.x;
+    b = t.y;
+  }
+  static __device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
   static __device__ __forceinline__ float ld(const float* p) { return *p; }
   static __device__ __forceinline__ float rnd(float v) { return v; }
   static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
 };
 template <> struct PrT<__nv_bfloat16> {
+  static __device__ __forceinline__ void ld2(const __nv_bfloat16* p, float& a, float& b) {
+    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+    a = t.x;
+    b = t.y;
+  }
+  static __device__ __forceinline__ void st2(__nv_bfloat16* p, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+  }
   static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
   static __device__ __forceinline__ float rnd(float v) { return __bfloat162float(__float2bfloat16(v)); }
   static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
 };
 template <> struct PrT<__half> {
+  static __device__ __forceinline__ void ld2(const __half* p, float& a, float& b) {
+    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(p));
+    a = t.x;
+    b = t.y;
+  }
+  static __device__ __forceinline__ void st2(__half* p, float a, float b) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(a, b); }
   static __device__ __forceinline__ float ld(const __half* p) { return __half2float(*p); }
   static __device__ __forceinline__ float rnd(float v) { return __half2float(__float2half(v)); }
   static __device__ __forceinline__ void st(__half* p, float v) { *p = __float2half(v); }
@@ -197,41 +217,43 @@ int launch_phi_avgpool(const void* x, void* y, int BG, int S, int D, int l, int 
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Decode-step producer: one kernel takes the token's fused projection output
-//   y [B, H*Dk + G*(3*Dk + 3*Dv)] = (Q | K_sel | V_sel | K_win | V_win | K_raw | V_raw)
-// rotates Q (as one H*Dk-wide vector) and the two K rows (per Dk-vector), and writes Q into its buffer and the six rows straight
-// into row `row` of their cache slabs [B,G,cap,D] -- the reference's seven rope / view / cat chains of a decode step
-// (nsa_attention.py:545-586, kv_cache.py:28-49).  It also records the step's read counters (kv_cache.py:51-65).
+// Projection-split producer: one kernel takes the fused projection output of S tokens per sequence
+//   y [B, S, H*Dk + G*(3*Dk + 3*Dv)] = (Q | K_sel | V_sel | K_win | V_win | K_raw | V_raw)
+// rotates Q (as one H*Dk-wide vector) and the two K streams (per Dk-vector; row s sits at position t + s), and writes Q into
+// q_out [B,S,H*Dk] and the six streams straight into rows row[i] + s of their [B,G,cap,D] tensors -- the reference's seven
+// rope / view / permute().contiguous() / torch.cat chains (nsa_attention.py:545-586 decode, :998-1016 prefill, kv_cache.py:28-49).
+// S = 1 with the cache slabs as destinations is a decode step (it also records the step's read counters, kv_cache.py:51-65);
+// inverse = 1 is the backward pass: it reads the seven gradients from the same places and writes dy (transposed rotation).
+// A thread owns one rotation pair of the fused row (its frequency, a powf, is computed once) and walks `rows` consecutive tokens.
 // ---------------------------------------------------------------------------------------------------------------------
 using DecodeProduceArgs = nsa_decode_produce_t;  // include/nsa_b200.h
+constexpr int kProduceBatch = 8;
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-decode_produce_kernel(DecodeProduceArgs a) {
+decode_produce_kernel(DecodeProduceArgs a, int rows) {
   const int QW = a.H * a.Dk;
   const int N = QW + a.G * (3 * a.Dk + 3 * a.Dv);
   const int pairs = N / 2;
-  if (a.counters && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 5)
+  if (a.counters && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x < 5)
     a.counters[(size_t)threadIdx.x * a.counters_cap + a.counters_idx] = a.counter_val[threadIdx.x];
   const int pc = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.y;
+  const int b = blockIdx.z;
   if (pc >= pairs) return;
   const int c = 2 * pc;  // column of y
-  const T* src = reinterpret_cast<const T*>(a.y) + (size_t)b * N + c;
-  const float x0 = PrT<T>::ld(src), x1 = PrT<T>::ld(src + 1);
-  const float inv_scale = __fdiv_rn(1.0f, a.scale);
-  float y0 = x0, y1 = x1;
-  T* dst;
+  // where this pair lives on the split side, and how it is rotated
+  T* other;            // element (b, s = 0) of the pair on the split side
+  size_t other_pitch;  // elements between consecutive tokens there
+  int rot_pair = -1, rot_dim = 0;
   if (c < QW) {
-    const float inv_freq = powf(a.base, __fmul_rn(__fmul_rn(-2.0f, (float)pc), __fdiv_rn(1.0f, (float)QW)));
-    float sn, cs;
-    sincosf(__fmul_rn(__fmul_rn((float)a.t, inv_scale), inv_freq), &sn, &cs);
-    rope_rotate<T>(x0, x1, PrT<T>::rnd(sn), PrT<T>::rnd(cs), false, y0, y1);
-    dst = reinterpret_cast<T*>(a.q_out) + (size_t)b * QW + c;
+    other = reinterpret_cast<T*>(a.q_out) + (size_t)b * a.S * QW + c;
+    other_pitch = QW;
+    rot_pair = pc;
+    rot_dim = QW;
   } else {
     // segments after Q: (K_sel, V_sel, K_win, V_win, K_raw, V_raw), widths G*Dk / G*Dv alternating
     int off = c - QW, seg = 0;
-    for (; seg < 6; ++seg) {
+    for (; seg < 5; ++seg) {
       const int wdt = a.G * ((seg & 1) ? a.Dv : a.Dk);
       if (off < wdt) break;
       off -= wdt;
@@ -239,32 +261,64 @@ decode_produce_kernel(DecodeProduceArgs a) {
     const int D = (seg & 1) ? a.Dv : a.Dk;
     const int g = off / D, e = off - g * D;
     if (seg == 0 || seg == 2) {  // RoPE'd keys of the selection and window caches
-      const float inv_freq = powf(a.base, __fmul_rn(__fmul_rn(-2.0f, (float)(e / 2)), __fdiv_rn(1.0f, (float)D)));
-      float sn, cs;
-      sincosf(__fmul_rn(__fmul_rn((float)a.t, inv_scale), inv_freq), &sn, &cs);
-      rope_rotate<T>(x0, x1, PrT<T>::rnd(sn), PrT<T>::rnd(cs), false, y0, y1);
+      rot_pair = e / 2;
+      rot_dim = D;
     }
-    dst = reinterpret_cast<T*>(a.slab[seg]) + (((size_t)b * a.G + g) * a.cap[seg] + a.row[seg]) * D + e;
+    other = reinterpret_cast<T*>(a.slab[seg]) + (((size_t)b * a.G + g) * a.cap[seg] + a.row[seg]) * D + e;
+    other_pitch = D;
   }
-  PrT<T>::st(dst, y0);
-  PrT<T>::st(dst + 1, y1);
+  // ATen divides a tensor by a scalar as a multiplication by its fp32 reciprocal: mirrored (see rope_shape_kernel)
+  const float inv_freq = rot_dim > 0 ? powf(a.base, __fmul_rn(__fmul_rn(-2.0f, (float)rot_pair), __fdiv_rn(1.0f, (float)rot_dim))) : 0.f;
+  const float inv_scale = __fdiv_rn(1.0f, a.scale);
+  T* yp = reinterpret_cast<T*>(const_cast<void*>(a.y)) + (size_t)b * a.S * N + c;
+  const int s0 = blockIdx.y * rows;
+  const int s1 = s0 + rows < a.S ? s0 + rows : a.S;
+  // eight tokens per trip: their loads are issued before any of the (long) sincosf chains, so a thread keeps eight requests in flight
+  for (int sb = s0; sb < s1; sb += kProduceBatch) {
+    float x0[kProduceBatch], x1[kProduceBatch];
+#pragma unroll
+    for (int u = 0; u < kProduceBatch; ++u)
+      if (sb + u < s1) {
+        const T* src = a.inverse ? other + (size_t)(sb + u) * other_pitch : yp + (size_t)(sb + u) * N;
+        PrT<T>::ld2(src, x0[u], x1[u]);
+      }
+#pragma unroll
+    for (int u = 0; u < kProduceBatch; ++u)
+      if (sb + u < s1) {
+        const int s = sb + u;
+        float y0 = x0[u], y1 = x1[u];
+        if (rot_dim > 0) {
+          float sn, cs;
+          sincosf(__fmul_rn(__fmul_rn((float)(a.t + s), inv_scale), inv_freq), &sn, &cs);
+          rope_rotate<T>(x0[u], x1[u], PrT<T>::rnd(sn), PrT<T>::rnd(cs), a.inverse != 0, y0, y1);
+        }
+        T* dst = a.inverse ? yp + (size_t)s * N : other + (size_t)s * other_pitch;
+        PrT<T>::st2(dst, y0, y1);
+      }
+  }
 }
 
 int launch_decode_produce(const nsa_decode_produce_t& a, cudaStream_t stream) {
   const int dtype = a.dtype;
-  NSA_REQUIRE(a.y && a.q_out, "decode_produce: NULL pointer");
-  for (int i = 0; i < 6; ++i) NSA_REQUIRE(a.slab[i] && a.row[i] >= 0 && a.row[i] < a.cap[i], "decode_produce: slab %d row %d cap %d", i, a.row[i], a.cap[i]);
-  NSA_REQUIRE(a.B >= 0 && a.H >= 1 && a.G >= 1 && a.Dk >= 2 && a.Dv >= 2 && a.Dk % 2 == 0 && a.Dv % 2 == 0, "decode_produce: bad geometry");
-  NSA_REQUIRE(!a.counters || (a.counters_idx >= 0 && a.counters_idx < a.counters_cap), "decode_produce: counter index");
+  NSA_REQUIRE(a.y && a.q_out, "produce: NULL pointer");
+  NSA_REQUIRE(a.S >= 1, "produce: S=%d", a.S);
+  for (int i = 0; i < 6; ++i)
+    NSA_REQUIRE(a.slab[i] && a.row[i] >= 0 && a.row[i] + a.S <= a.cap[i], "produce: slab %d rows [%d, %d) cap %d", i, a.row[i],
+                a.row[i] + a.S, a.cap[i]);
+  NSA_REQUIRE(a.B >= 0 && a.H >= 1 && a.G >= 1 && a.Dk >= 2 && a.Dv >= 2 && a.Dk % 2 == 0 && a.Dv % 2 == 0, "produce: bad geometry");
+  NSA_REQUIRE(!a.counters || (a.counters_idx >= 0 && a.counters_idx < a.counters_cap), "produce: counter index");
   if (a.B == 0) return NSA_OK;
   DecodeProduceArgs b = a;
   if (!(b.scale > 0.f)) b.scale = 1.0f;
   const int pairs = (a.H * a.Dk + a.G * (3 * a.Dk + 3 * a.Dv)) / 2;
-  const dim3 grid((pairs + 255) / 256, a.B);
-  NSA_REQUIRE(a.B <= 65535, "decode_produce: B=%d", a.B);
-  if (dtype == NSA_F32) decode_produce_kernel<float><<<grid, 256, 0, stream>>>(b);
-  else if (dtype == NSA_BF16) decode_produce_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(b);
-  else decode_produce_kernel<__half><<<grid, 256, 0, stream>>>(b);
+  // rows per thread: amortise the powf over up to 16 tokens, but keep at least ~4 CTAs per SM in flight
+  int rows = 16;
+  while (rows > 1 && (long long)((pairs + 255) / 256) * ((a.S + rows - 1) / rows) * a.B < 4 * 148) rows /= 2;
+  const dim3 grid((pairs + 255) / 256, (a.S + rows - 1) / rows, a.B);
+  NSA_REQUIRE(a.B <= 65535 && grid.y <= 65535, "produce: B=%d S=%d", a.B, a.S);
+  if (dtype == NSA_F32) decode_produce_kernel<float><<<grid, 256, 0, stream>>>(b, rows);
+  else if (dtype == NSA_BF16) decode_produce_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(b, rows);
+  else decode_produce_kernel<__half><<<grid, 256, 0, stream>>>(b, rows);
   return check_launch("decode_produce_kernel");
 }
 

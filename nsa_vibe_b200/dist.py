@@ -49,3 +49,34 @@ def register_bf16_compress(ddp_model) -> None:
     cast back.  78.3 M parameters -> 156.6 MB per step over NCCL / NVLink."""
     from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
     ddp_model.register_comm_hook(state=None, hook=default_hooks.bf16_compress_hook)
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
+    """What DDP's constructor does: every rank starts from rank `src`'s parameters and buffers."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t, src)
+
+
+def allreduce_grads_bf16(params, *, compress_dtype: torch.dtype = torch.bfloat16) -> int:
+    """The reference's DDP gradient exchange with `bf16_compress_hook` (scripts/train_showcase.py:654-665) as ONE flat collective
+    that a CUDA graph can capture (DDP's reducer cannot be captured): gradients are divided by the world size, cast to bf16,
+    summed over the ranks in one all_reduce, cast back and written into `p.grad` -- the hook's arithmetic (divide, compress,
+    allreduce, decompress) on one bucket holding every gradient.  Returns the bytes each rank contributes (2 per element)."""
+    ps = [p for p in params if p.grad is not None]
+    if not ps:
+        return 0
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    grads = [p.grad for p in ps]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    if world > 1:
+        flat = flat.div_(world).to(compress_dtype)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        off = 0
+        for g in grads:
+            n = g.numel()
+            g.copy_(flat[off:off + n].view_as(g))
+            off += n
+    return int(flat.numel()) * 2

@@ -57,12 +57,19 @@ class LlamaBlockNSA(nn.Module):
         self.norm2 = RMSNorm(dim)
         self.mlp = MLP(dim)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, delta: torch.Tensor = None, defer_residual: bool = False):
+        """x -> x + attn(norm1(x)) -> (+ mlp(norm2(.))).  `delta`: a pending residual of the previous block (x stands for
+        x + delta; the add happens inside norm1's kernel).  defer_residual=True returns (x, mlp_out) and leaves the last add to
+        the next norm -- a stack of blocks then never runs a stand-alone residual add (llama_block_nsa.py:102-106)."""
         B, S, _ = x.shape
-        xn = self.norm1(x)
+        if delta is not None:
+            x, xn = self.norm1(x, residual=delta)
+        else:
+            xn = self.norm1(x)
         a = self.attn
         meta = build_block_meta(S, a.l, a.d, a.l_sel, a.n_sel, a.w)
         kv = create_empty_kv(B, a.n_kv_groups, a.d_k, a.d_v, meta, device=x.device, dtype=xn.dtype)
         out, _ = a(xn, kv, prefill=True)
         x, xn2 = self.norm2(x, residual=out)  # x = x + out and norm2(x) in one pass
-        return x + self.mlp(xn2)
+        m = self.mlp(xn2)
+        return (x, m) if defer_residual else x + m

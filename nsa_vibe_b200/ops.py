@@ -433,15 +433,19 @@ def phi_avgpool(K_raw: torch.Tensor, V_raw: torch.Tensor, l: int, d: int, *, t0:
 
 def decode_produce(y: torch.Tensor, q_out: torch.Tensor, slabs, rows, *, H: int, G: int, Dk: int, Dv: int, t: int,
                    base: float = 10000.0, scale: float = 1.0, counters: Optional[torch.Tensor] = None, counters_idx: int = 0,
-                   counter_vals=(0, 0, 0, 0, 0)) -> None:
-    """One decode token's fused projection output y [B, H*Dk + G*(3*Dk+3*Dv)] = (Q | K_sel | V_sel | K_win | V_win | K_raw |
-    V_raw) -> RoPE'd Q into q_out [B, H*Dk] and the six rows into row rows[i] of slabs[i] ([B,G,cap,D], contiguous), in ONE
-    launch: the reference's seven rope/view/cat chains of a decode step (nsa_attention.py:545-586, kv_cache.py:28-49).
-    counters ([5,cap] int64, optional) receives the step's read counters (kv_cache.py:51-65) at column counters_idx."""
+                   counter_vals=(0, 0, 0, 0, 0), inverse: bool = False) -> None:
+    """Fused projection output y [B,(S,) H*Dk + G*(3*Dk+3*Dv)] = (Q | K_sel | V_sel | K_win | V_win | K_raw | V_raw) -> RoPE'd Q
+    into q_out [B,(S,) H*Dk] and the six streams into rows rows[i].. of slabs[i] ([B,G,cap,D], contiguous), in ONE launch: the
+    reference's seven rope/view/permute/cat chains (nsa_attention.py:545-586, :998-1016, kv_cache.py:28-49).  inverse=True is the
+    backward direction (reads q_out / slabs, writes y).  counters ([5,cap] int64, optional) receives the step's read counters
+    (kv_cache.py:51-65) at column counters_idx."""
     _require_cuda(y, q_out, *slabs)
     B = y.shape[0]
-    if not y.is_contiguous() or y.shape[-1] != H * Dk + G * (3 * Dk + 3 * Dv) or not q_out.is_contiguous():
-        raise RuntimeError("decode_produce: y must be contiguous [B, H*Dk + G*(3*Dk+3*Dv)]")
+    S = y.shape[1] if y.dim() == 3 else 1
+    if not y.is_contiguous() or y.shape[-1] != H * Dk + G * (3 * Dk + 3 * Dv) or not q_out.is_contiguous() or q_out.dtype != y.dtype:
+        raise RuntimeError("decode_produce: y must be contiguous [B,(S,) H*Dk + G*(3*Dk+3*Dv)] and q_out of the same dtype")
+    if q_out.numel() != B * S * H * Dk:
+        raise RuntimeError("decode_produce: q_out must hold B*S*H*Dk elements")
     a = _lib.DecodeProduce()
     a.y, a.q_out = y.data_ptr(), q_out.data_ptr()
     for i, (sl, r) in enumerate(zip(slabs, rows)):
@@ -455,7 +459,38 @@ def decode_produce(y: torch.Tensor, q_out: torch.Tensor, slabs, rows, *, H: int,
             a.counter_val[i] = int(v)
     a.B, a.H, a.G, a.Dk, a.Dv, a.t = B, H, G, Dk, Dv, int(t)
     a.base, a.scale, a.dtype = float(base), float(scale if scale > 0 else 1.0), _DTYPES[y.dtype]
-    _call("nsa_decode_produce", C.byref(a), _stream())
+    a.S, a.inverse = int(S), int(bool(inverse))
+    if B * S:
+        _call("nsa_decode_produce", C.byref(a), _stream())
+
+
+class _ProjectSplit(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, H, G, Dk, Dv, t0, base, scale):
+        yc = _c(y)
+        B, S, _ = yc.shape
+        q = torch.empty((B, S, G, H // G, Dk), dtype=yc.dtype, device=yc.device)
+        outs = [torch.empty((B, G, S, Dv if (i & 1) else Dk), dtype=yc.dtype, device=yc.device) for i in range(6)]
+        decode_produce(yc, q, outs, [0] * 6, H=H, G=G, Dk=Dk, Dv=Dv, t=t0, base=base, scale=scale)
+        ctx.meta = (H, G, Dk, Dv, int(t0), float(base), float(scale), tuple(yc.shape))
+        return (q, *outs)
+
+    @staticmethod
+    def backward(ctx, dq, *douts):
+        H, G, Dk, Dv, t0, base, scale, yshape = ctx.meta
+        dy = torch.empty(yshape, dtype=dq.dtype, device=dq.device)
+        decode_produce(dy, _c(dq), [_c(g) for g in douts], [0] * 6, H=H, G=G, Dk=Dk, Dv=Dv, t=t0, base=base, scale=scale, inverse=True)
+        return dy, None, None, None, None, None, None, None
+
+
+def project_split(y: torch.Tensor, *, H: int, G: int, Dk: int, Dv: int, t0: int = 0, base: float = 10000.0, scale: float = 1.0):
+    """y [B,S,H*Dk + G*(3Dk+3Dv)] (ONE GEMM over the seven stacked projection weights) -> (Q [B,S,G,h,Dk] RoPE'd as the reference
+    does (one H*Dk-wide vector per token, nsa_attention.py:1002-1009), K_sel, V_sel, K_win, V_win, K_raw, V_raw [B,G,S,D] with
+    K_sel / K_win RoPE'd per Dk-vector) in one launch; the backward is one launch too."""
+    _require_cuda(y)
+    if y.dim() != 3 or y.shape[-1] != H * Dk + G * (3 * Dk + 3 * Dv) or y.dtype not in _DTYPES:
+        raise RuntimeError("project_split: y must be [B,S,H*Dk + G*(3*Dk+3*Dv)] in fp32/bf16/fp16")
+    return _ProjectSplit.apply(y, H, G, Dk, Dv, t0, base, scale if scale > 0 else 1.0)
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -88,3 +88,49 @@ def test_rmsnorm_rejects_cpu_and_bad_dims():
         ops.rmsnorm(torch.randn(2, 8), torch.ones(8))
     with pytest.raises(RuntimeError):
         ops.rmsnorm(torch.randn(2, 6, device="cuda"), torch.ones(6, device="cuda"))
+
+
+def test_block_stack_with_deferred_residual_matches_plain_stack_and_torch_norm():
+    """Two LlamaBlockNSA blocks (llama_block_nsa.py:33-106): (a) the stack with every residual add folded into the next norm's
+    kernel, (b) the plain stack, (c) the plain stack with the reference's ATen RMSNorm formula -- same outputs and gradients
+    (fp32: 2e-4 max-abs on values, 2e-3 relative to the largest gradient)."""
+    import os
+    from nsa_vibe_b200.model import llama_block_nsa as M
+    os.environ["NSA_PREFILL_BATCHED"] = "1"
+    try:
+        torch.manual_seed(11)
+        blocks = [M.LlamaBlockNSA(64, 4, 2, 16, 16, l=16, d=8, l_sel=32, n_sel=4, w=40).cuda() for _ in range(2)]
+    finally:
+        os.environ.pop("NSA_PREFILL_BATCHED", None)
+    x0 = torch.randn(2, 96, 64, device="cuda")
+
+    def run(mode):
+        for b in blocks:
+            b.zero_grad(set_to_none=True)
+        x = x0.clone().requires_grad_(True)
+        if mode == "deferred":
+            h, delta = x, None
+            for b in blocks:
+                h, delta = b(h, delta, defer_residual=True)
+            y = h + delta
+        else:
+            y = x
+            for b in blocks:
+                y = b(y)
+        y.square().sum().backward()
+        return y.detach(), x.grad.detach(), [p.grad.detach().clone() for b in blocks for p in b.parameters()]
+
+    ya, ga, pa = run("deferred")
+    yb, gb, pb = run("plain")
+    orig = M.RMSNorm.forward
+    M.RMSNorm.forward = lambda self, x, residual=None: (
+        M.rmsnorm_torch(x, self.weight, self.eps) if residual is None else (x + residual, M.rmsnorm_torch(x + residual, self.weight, self.eps)))
+    try:
+        yc, gc, pc = run("plain")
+    finally:
+        M.RMSNorm.forward = orig
+    for y, g_, p_ in ((yb, gb, pb), (yc, gc, pc)):
+        assert (ya - y).abs().max() <= 2e-4, (ya - y).abs().max()
+        assert (ga - g_).abs().max() <= 2e-3 * max(1.0, float(g_.abs().max()))
+        for u, v in zip(pa, p_):
+            assert (u - v).abs().max() <= 2e-3 * max(1.0, float(v.abs().max())), (u.shape, (u - v).abs().max())

@@ -51,7 +51,15 @@ def _worker(rank, world, port, out):
             model.weight.fill_(0.5)
         ddp = torch.nn.parallel.DistributedDataParallel(model)
         ddp(x[first:first + n]).sum().backward()
-        out[rank] = dict(ms=ms, total=total, rows=[g.tolist() for g in gathered], n=n, grad=model.weight.grad.clone())
+        # the graph-capturable flat exchange (nd.allreduce_grads_bf16) against DDP's averaged gradient
+        m2 = torch.nn.Linear(3, 2, bias=False)
+        with torch.no_grad():
+            m2.weight.fill_(0.5 + rank)  # differs per rank until broadcast
+        nd.broadcast_parameters(m2, 0)
+        m2(x[first:first + n]).sum().backward()
+        nbytes = nd.allreduce_grads_bf16(m2.parameters(), compress_dtype=torch.float32)  # gloo: no bf16 sum everywhere
+        out[rank] = dict(ms=ms, total=total, rows=[g.tolist() for g in gathered], n=n, grad=model.weight.grad.clone(),
+                         grad2=m2.weight.grad.clone(), w2=m2.weight.detach().clone(), nbytes=nbytes)
     finally:
         dist.destroy_process_group()
 
@@ -73,3 +81,6 @@ def test_world2_gloo_sharding_and_max_timing():
     g1 = x[3:].sum(0).expand(2, 3)
     assert torch.allclose(out[0]["grad"], (g0 + g1) / 2)
     assert torch.allclose(out[1]["grad"], out[0]["grad"])
+    for r in (0, 1):
+        assert torch.allclose(out[r]["grad2"], out[0]["grad"]) and out[r]["nbytes"] == 12
+        assert torch.equal(out[r]["w2"], torch.full((2, 3), 0.5))

@@ -116,3 +116,32 @@ def test_kv_inplace_append_keeps_reference_views():
     assert kv.K_sel.shape == (2, 2, 70, 16) and kv.K_sel.dtype == torch.bfloat16 and kv.K_win.shape == (2, 2, 4, 16)
     assert kv.K_win[0, 0, :, 0].tolist() == [66, 67, 68, 69] and kv.K_sel[1, 1, :, 3].tolist() == list(range(70))
     assert kv.reads_pred.tolist() == list(range(70)) and kv.reads_act_win.shape == (70,)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,S,H,G,Dk,Dv,t0,scale", [(2, 37, 12, 2, 64, 64, 0, 1.0), (1, 300, 4, 2, 16, 32, 50, 2.0), (3, 1, 12, 2, 64, 64, 9, 1.0)])
+def test_project_split_matches_the_seven_chains_forward_and_backward(dtype, B, S, H, G, Dk, Dv, t0, scale):
+    """ops.project_split (one launch per direction) == rope_shape per tensor on column slices of the fused projection output,
+    values and gradients bit for bit (same arithmetic, nsa_attention.py:998-1016)."""
+    ops, _, _ = _mods()
+    g = torch.Generator(device="cuda").manual_seed(S + H)
+    widths = [H * Dk] + [G * Dk, G * Dv] * 3
+    y = torch.randn(B, S, sum(widths), generator=g, device="cuda").to(dtype)
+    ya = y.clone().requires_grad_(True)
+    yb = y.clone().requires_grad_(True)
+    got = ops.project_split(ya, H=H, G=G, Dk=Dk, Dv=Dv, t0=t0, scale=scale)
+    parts = torch.split(yb, widths, dim=-1)
+    want = [ops.rope_shape(parts[0].contiguous(), H, Dk, rope="token", t0=t0, scale=scale).view(B, S, G, H // G, Dk)]
+    for i in range(6):
+        D = Dv if i & 1 else Dk
+        want.append(ops.rope_shape(parts[1 + i].contiguous(), G, D, rope="vector" if i in (0, 2) else "none", to_cache_layout=True,
+                                   t0=t0, scale=scale))
+    loss_a = loss_b = 0.0
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and torch.equal(a, b)
+        dy = torch.randn(a.shape, generator=g, device="cuda").to(dtype)
+        loss_a = loss_a + (a.float() * dy.float()).sum()
+        loss_b = loss_b + (b.float() * dy.float()).sum()
+    loss_a.backward()
+    loss_b.backward()
+    assert torch.equal(ya.grad, yb.grad)

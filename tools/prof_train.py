@@ -33,4 +33,4 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=110))

@@ -29,10 +29,11 @@ class TinyLM(nn.Module):  # scripts/train_showcase.py:30-117 (embedding -> block
         self.lm_head = nn.Linear(dim, vocab, bias=False)
 
     def forward(self, ids):
-        x = self.embed(ids)
-        for b in self.blocks:
-            x = b(x)
-        return self.lm_head(self.norm_f(x))
+        x, delta = self.embed(ids), None
+        for b in self.blocks:  # each block's last residual add runs inside the next norm's kernel
+            x, delta = b(x, delta, defer_residual=True)
+        _, xn = self.norm_f(x, residual=delta)
+        return self.lm_head(xn)
 
 
 def main():
@@ -54,10 +55,17 @@ def main():
     os.environ.setdefault("NSA_PREFILL_BATCHED", "1")
     model = TinyLM(256, 768, a.layers, 12, 2, 64, 64, 32, 16, 64, 16, 512).to(dev)
     n_params = sum(p.numel() for p in model.parameters())
-    if world > 1:
+    flat_exchange = a.graph and world > 1
+    if flat_exchange:
+        # DDP's reducer cannot be captured in a CUDA graph; the same exchange (divide, bf16, allreduce, cast back) as one flat NCCL
+        # all_reduce after the backward can (nd.allreduce_grads_bf16).  156.6 MB over NVLink: ~0.5 ms of a ~27 ms step.
+        nd.broadcast_parameters(model, 0)
+    elif world > 1:
         model = nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
         nd.register_bf16_compress(model)
-    opt = torch.optim.AdamW(model.parameters(), lr=2e-4, capturable=a.graph)
+    # NSA_OPT_FUSED=1: the reference's opt-in fused AdamW (scripts/train_showcase.py:747-758)
+    fused = os.getenv("NSA_OPT_FUSED", "0").lower() in ("1", "true", "yes")
+    opt = torch.optim.AdamW(model.parameters(), lr=2e-4, capturable=a.graph, fused=fused)
     ids = torch.randint(0, 256, (a.B, a.S + 1), device=dev)
     lib = _lib.load()
 
@@ -67,16 +75,12 @@ def main():
             logits = model(ids[:, :-1])
         loss = F.cross_entropy(logits.float().reshape(-1, 256), ids[:, 1:].reshape(-1))
         loss.backward()
+        if flat_exchange:
+            nd.allreduce_grads_bf16(model.parameters())
         opt.step()
         return loss
 
     mode = "eager"
-    if a.graph and world > 1:
-        # measured on 2 B200s: capturing a DDP step fails with cudaErrorStreamCaptureImplicit (the reducer touches the legacy
-        # stream during capture); the multi-GPU step therefore runs eagerly
-        if rank == 0:
-            print("--graph ignored under DDP (capture of the DDP reducer is not supported here)", file=sys.stderr)
-        a.graph = False
     if a.graph:
         # whole-step capture: the step is host-bound in eager mode (~170 NSA launches + ~2000 torch ops per step); the C ABI
         # allocates nothing and never synchronises, so its launches are captured like any other kernel
@@ -95,6 +99,8 @@ def main():
                 logits = model(ids[:, :-1])
             holder["loss"] = F.cross_entropy(logits.float().reshape(-1, 256), ids[:, 1:].reshape(-1))
             holder["loss"].backward()
+            if flat_exchange:
+                nd.allreduce_grads_bf16(model.parameters())
             opt.step()
 
         def step():  # noqa: F811
@@ -126,10 +132,18 @@ def main():
     ms = nd.max_over_ranks(s.elapsed_time(e) / a.steps, device=dev)
     if rank == 0:
         print(json.dumps({"config": "C5 m7c TinyLM DDP training step", "layers": a.layers, "params": n_params, "S": a.S,
-                          "batch_per_gpu": a.B, "n_gpus": world, "mode": mode, "ms_per_step": ms, "tokens_per_s": world * a.B * a.S / (ms * 1e-3),
+                          "batch_per_gpu": a.B, "n_gpus": world, "mode": mode, "adamw": "fused" if fused else "foreach", "ms_per_step": ms, "tokens_per_s": world * a.B * a.S / (ms * 1e-3),
                           "loss": float(loss.detach()), "nsa_kernel_launches_per_step": (lib.nsa_kernel_launches() - n0) / a.steps,
-                          "grad_allreduce": "DDP bf16_compress_hook over NCCL" if world > 1 else "none (single GPU)",
+                          "grad_allreduce": ("one flat bf16 NCCL all_reduce captured in the graph" if flat_exchange else "DDP bf16_compress_hook over NCCL") if world > 1 else "none (single GPU)",
                           "allreduce_bytes_per_step": 2 * n_params if world > 1 else 0}))
+    if flat_exchange:
+        # a process group whose collective sits in a live CUDA graph does not tear down cleanly here (destroy_process_group hung
+        # on 2 B200s until the launcher's timeout): flush and leave without the NCCL destructor
+        sys.stdout.flush()
+        sys.stderr.flush()
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)
     if world > 1:
         dist.destroy_process_group()
 
