@@ -701,7 +701,7 @@ gate_bwd_kernel(nsa_dims_t dm, const void* __restrict__ Q, nsa_gate_params_t gp,
 constexpr int kGbWarps = 8;
 
 template <typename T>
-__global__ void __launch_bounds__(kGbWarps * 32)
+__global__ void __launch_bounds__(kGbWarps * 32, 2)
 gate_bwd_fast_kernel(nsa_dims_t dm, const T* __restrict__ Q, nsa_gate_params_t gp, const float* __restrict__ dgates,
                      float* __restrict__ dQ, float* d_fc1_w, float* d_fc1_b, float* d_fc2_w, float* d_fc2_b) {
   constexpr int DK = 64;
@@ -819,13 +819,14 @@ gate_bwd_fast_kernel(nsa_dims_t dm, const T* __restrict__ Q, nsa_gate_params_t g
       }
       dq0 *= inv_h;
       dq1 *= inv_h;
-      for (int hh = 0; hh < h; ++hh) {  // row owned by this warp
-        float2* dst = reinterpret_cast<float2*>(dQ + ((size_t)row * h + hh) * DK) + lane;
-        float2 v = *dst;
-        v.x += dq0;
-        v.y += dq1;
-        *dst = v;
-      }
+      // row owned by this warp; all heads are read before any is written (one global round trip, not h dependent ones)
+      float2 cur[HM];
+#pragma unroll
+      for (int hh = 0; hh < HM; ++hh)
+        if (hh < h) cur[hh] = *(reinterpret_cast<const float2*>(dQ + ((size_t)row * h + hh) * DK) + lane);
+#pragma unroll
+      for (int hh = 0; hh < HM; ++hh)
+        if (hh < h) *(reinterpret_cast<float2*>(dQ + ((size_t)row * h + hh) * DK) + lane) = make_float2(cur[hh].x + dq0, cur[hh].y + dq1);
     }
   }
   if (unit) {
