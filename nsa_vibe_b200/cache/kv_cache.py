@@ -152,6 +152,21 @@ class NSA_KV:
             rows.append(self._lens[name])
         return slabs, rows
 
+    def fast_token_rows(self, slabs) -> Optional[list]:
+        """Row indices for the next token if the six token caches are still backed by exactly `slabs` (a tuple handed out by
+        token_append_slots earlier), in sync with the public views and with a free row each; else None (no tensor op is run)."""
+        sl, vw, ln = self._slabs, self._views, self._lens
+        rows = []
+        for i, name in enumerate(self._TOKEN_FIELDS):
+            s = sl.get(name)
+            if s is not slabs[i] or vw.get(name) is not getattr(self, name):
+                return None
+            n = ln[name]
+            if n >= s.shape[2]:
+                return None
+            rows.append(n)
+        return rows
+
     def commit_token_append(self, w: int) -> None:
         for name in self._TOKEN_FIELDS:
             if name in ("K_win", "V_win"):

@@ -275,23 +275,53 @@ class NSAAttention(nn.Module):
             self._gate_struct = cached
         return cached[1]
 
+    def _decode_plan(self, y: torch.Tensor, kv: NSA_KV, aux: bool):
+        """(plan, rows): the prebuilt argument blocks of this module's decode step on `kv` (ops.DecodeStepPlan), rebuilt whenever a
+        cache slab was reallocated or replaced, the batch / dtype changed, or gate / rope settings moved."""
+        cfg_key = (float(self.gate_temp), self.gate.mode(), float(self.rope_scale), aux, y.dtype, y.shape[0],
+                   tuple((p.data_ptr(), p._version) for p in self.gate.params()))
+        plan = getattr(kv, "_decode_plan", None)
+        if plan is not None and plan[0] is self and plan[1] == cfg_key:
+            rows = kv.fast_token_rows(plan[2].slabs)
+            if rows is not None and kv._slabs.get("K_cmp") is plan[2].cmp_slabs[0] and kv._slabs.get("V_cmp") is plan[2].cmp_slabs[1] \
+                    and kv._views.get("K_cmp") is kv.K_cmp and kv._views.get("V_cmp") is kv.V_cmp \
+                    and (not aux or (kv._slabs.get("__ctr") is plan[2].counters and kv._lens["__ctr"] < plan[2].counters.shape[1]
+                                     and kv._views.get("reads_pred") is kv.reads_pred)):
+                return plan[2], rows
+        slabs, rows = kv.token_append_slots(y)
+        # room for the compressed token a step may emit, so that the slab the plan points at survives the emission
+        for name, D in (("K_cmp", self.d_k), ("V_cmp", self.d_v)):
+            cur = getattr(kv, name)
+            if cur.dtype != y.dtype or cur.device != y.device:
+                if cur.shape[2] != 0:
+                    raise RuntimeError(f"NSA_KV.{name}: dtype/device of the cache does not match the new tokens")
+                setattr(kv, name, y.new_zeros((cur.shape[0], cur.shape[1], 0, D)))
+                kv._slabs.pop(name, None)
+            kv._ensure(name, 1)
+        ctr = kv.counter_slot()[0] if aux else None
+        cfg = self._cfg()
+        gate = self.gate.params() if cfg.gate_mode == ops.GATE_MLP else None
+        p = ops.DecodeStepPlan(y, slabs, (kv._slabs["K_cmp"], kv._slabs["V_cmp"]), ctr, H=self.n_heads, G=self.n_kv_groups,
+                               Dk=self.d_k, Dv=self.d_v, cfg=cfg, gate=gate, rope_scale=self.rope_scale)
+        kv._decode_plan = (self, cfg_key, p)
+        return p, rows
+
     def _forward_decode(self, x: torch.Tensor, kv: NSA_KV) -> tuple[torch.Tensor, NSA_KV]:
         """One decode step (nsa_attention.py:545-976): one GEMM for the seven projections, one kernel that rotates Q/K and writes
-        the token's six cache rows in place (ops.decode_produce), phi on emission steps, the fused decode kernel, the out GEMM."""
+        the token's six cache rows in place (nsa_decode_produce), phi on emission steps, the fused decode kernel, the out GEMM.
+        The two C-ABI calls go through a per-cache DecodeStepPlan (argument blocks built once, scalars updated per step)."""
         B = x.shape[0]
-        G, Dk, Dv = self.n_kv_groups, self.d_k, self.d_v
-        t = int(kv.K_sel.shape[2])  # position of the new token
+        G = self.n_kv_groups
         with torch.no_grad():
             y = F.linear(x.reshape(B, self.dim), self._decode_weights())
-            Q = torch.empty((B, 1, G, self.h_per_group, Dk), dtype=y.dtype, device=y.device)
-            slabs, rows = kv.token_append_slots(y)
+            aux = not self._env_cache["disable_aux_stats"]
+            plan, rows = self._decode_plan(y, kv, aux)
+            t = rows[0]            # position of the new token = tokens already in K_sel
             S_raw = rows[4] + 1
             num_cmp = 0 if S_raw < self.l else (S_raw - self.l) // self.d + 1
-            aux = not self._env_cache["disable_aux_stats"]
-            ctr, ctr_idx = kv.counter_slot() if aux else (None, 0)
-            reads = num_cmp + self.n_sel * self.l_sel + min(self.w, S_raw)  # :634-638
-            ops.decode_produce(y, Q, slabs, rows, H=self.n_heads, G=G, Dk=Dk, Dv=Dv, t=t, scale=self.rope_scale, counters=ctr,
-                               counters_idx=ctr_idx, counter_vals=(reads, reads, self.n_sel * self.l_sel, num_cmp, min(self.w, S_raw)))
+            n_win_read = min(self.w, S_raw)
+            reads = num_cmp + self.n_sel * self.l_sel + n_win_read  # :634-638
+            plan.produce(y, t, rows, kv._lens["__ctr"] if aux else 0, (reads, reads, self.n_sel * self.l_sel, num_cmp, n_win_read))
             kv.commit_token_append(self.w)
             if aux:
                 kv.commit_counters()
@@ -299,18 +329,25 @@ class NSAAttention(nn.Module):
                 K_new, V_new = ops.phi_avgpool(kv.K_cmp_raw_seq[:, :, S_raw - self.l:S_raw],
                                                kv.V_cmp_raw_seq[:, :, S_raw - self.l:S_raw], self.l, self.d, t0=S_raw - self.l)
                 kv.append_compressed(K_new, V_new)
-            need = max(t + 1, self.l_sel)
+                if kv._slabs["K_cmp"] is not plan.cmp_slabs[0] or kv._slabs["V_cmp"] is not plan.cmp_slabs[1]:
+                    kv._decode_plan = None  # the emission outgrew the compressed slab: rebuild on the new one
+                    plan, _ = self._decode_plan_after_growth(y, kv, aux, plan)
             if getattr(kv, "meta", None) is None or kv.meta.sel_starts.numel() * self.l_sel < t + 1 or kv.meta.sel_starts.numel() == 0:
-                kv.meta = build_block_meta(seq_len=need, l=self.l, d=self.d, l_sel=self.l_sel, n_sel=self.n_sel, w=self.w)
-            cfg = self._cfg()
+                kv.meta = build_block_meta(seq_len=max(t + 1, self.l_sel), l=self.l, d=self.d, l_sel=self.l_sel, n_sel=self.n_sel, w=self.w)
             ranges = torch.empty((B, G, self.n_sel, 2), dtype=torch.int32, device=x.device)
-            n_win = kv.length("K_win")
-            O = ops.decode_core(Q, kv.slab("K_sel"), kv.slab("V_sel"), kv.slab("K_win"), kv.slab("V_win"),
-                                kv.slab("K_cmp"), kv.slab("V_cmp"), None, cfg, t=t, S_sel_kv=t + 1, S_win_kv=n_win,
-                                win_off=(t + 1) - n_win, S_cmp=int(kv.K_cmp.shape[2]), ranges_out=ranges,
-                                gate_cache=self._decode_gate(cfg, x.device) or ops._gate_struct(None, x.device))
+            O = plan.attend(t, kv._lens["K_win"], kv._lens["K_cmp"], ranges)
             if self._env_cache["strict_asserts"]:
                 assert int(ranges[..., 1].max()) <= t + 1, "Selection must not access future tokens."
             self._last_ranges = ranges
             out = self.out(O.reshape(B, 1, self.n_heads * self.d_v))
         return out, kv
+
+    def _decode_plan_after_growth(self, y: torch.Tensor, kv: NSA_KV, aux: bool, old):
+        """Plan on the reallocated compressed slabs; the step's Q (already produced into the old plan's buffer) is carried over."""
+        cfg = self._cfg()
+        gate = self.gate.params() if cfg.gate_mode == ops.GATE_MLP else None
+        slabs = tuple(kv._slabs[n] for n in kv._TOKEN_FIELDS)
+        p = ops.DecodeStepPlan(y, slabs, (kv._slabs["K_cmp"], kv._slabs["V_cmp"]), old.counters, H=self.n_heads, G=self.n_kv_groups,
+                               Dk=self.d_k, Dv=self.d_v, cfg=cfg, gate=gate, rope_scale=self.rope_scale)
+        p.Q.copy_(old.Q)
+        return p, None

@@ -58,3 +58,29 @@ with torch.no_grad():
             byts = reads * G * 2 * D * 2
             print(json.dumps({"config": "C3 decode step (fused kernel), bf16", "B": Bd, "S": Sd, "us_per_step": ms * 1e3, "us_per_token": ms * 1e3 / Bd,
                               "reads_per_token": reads, "algorithmic_GBps": Bd * byts / (ms * 1e-3) / 1e9, "frac_of_hbm_6549": Bd * byts / (ms * 1e-3) / 1e9 / 6549.1}), flush=True)
+
+# ---- the same two configs through the module API (NSAAttention.forward: projections, cache append, hot path, output projection) ----
+os.environ.setdefault("NSA_PREFILL_BATCHED", "1")
+from nsa_vibe_b200.cache.kv_cache import create_empty_kv  # noqa: E402
+from nsa_vibe_b200.core.block_index import build_block_meta  # noqa: E402
+from nsa_vibe_b200.core.nsa_attention import NSAAttention  # noqa: E402
+
+torch.manual_seed(0)
+attn = NSAAttention(dim=768, n_heads=12, n_kv_groups=G, d_k=D, d_v=D, l=l, d=d, l_sel=ls, n_sel=n, w=w).to(dev).bfloat16()
+mk = lambda B_, S_: create_empty_kv(B_, G, D, D, build_block_meta(S_ + 64, l, d, ls, n, w), device=torch.device(dev), dtype=torch.bfloat16)
+with torch.no_grad():
+    for B in (1, 32):  # C2: m7c prefill S=2048 (bench/bench_prefill.py:76-85)
+        x = torch.randn(B, 2048, 768, device=dev).bfloat16()
+        ms = timeit(lambda: attn(x, mk(B, 2048), prefill=True), n=10)
+        print(json.dumps({"config": "C2 NSAAttention.forward(prefill=True), m7c dims, bf16 (module API, one layer)", "B": B, "S": 2048, "ms": ms,
+                          "tok_per_s": B * 2048 / (ms * 1e-3)}), flush=True)
+    for Bd in (1, 64, 592):  # C3: bench/bench_decode.py:113-136 -- prefill a random context, then timed single-token steps
+        for Sd in (512, 1024, 2048, 4096):
+            kv = mk(Bd, Sd)
+            attn(torch.randn(Bd, Sd - 48, 768, device=dev).bfloat16(), kv, prefill=True)
+            kv.reserve(Sd + 64)
+            x1 = torch.randn(Bd, 1, 768, device=dev).bfloat16()
+            us = timeit(lambda: attn(x1, kv, prefill=False), n=32, warm=8) * 1e3
+            print(json.dumps({"config": "C3 NSAAttention.forward(prefill=False), m7c dims, bf16 (module API)", "B": Bd, "S": int(kv.K_sel.shape[2]),
+                              "us_per_step": us, "us_per_token": us / Bd}), flush=True)
+            del kv
