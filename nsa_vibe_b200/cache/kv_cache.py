@@ -12,7 +12,6 @@ Callers may still construct it with zero-length tensors exactly as the reference
 """
 from __future__ import annotations
 
-import os
 from dataclasses import dataclass, field
 from typing import Dict, Optional
 
@@ -166,6 +165,49 @@ class NSA_KV:
                 return None
             rows.append(n)
         return rows
+
+    def decode_state(self, token_slabs, cmp_slabs, counters) -> Optional[list]:
+        """Rows for the next token if this cache is still exactly what a prebuilt decode plan points at: the six token slabs
+        (`token_slabs`) with a free row each, the two compressed slabs (`cmp_slabs`) and, when given, the counter slab with a free
+        column, all in sync with the public tensors.  None = something was reallocated or replaced: rebuild the plan."""
+        rows = self.fast_token_rows(token_slabs)
+        if rows is None:
+            return None
+        if not self.same_compressed_slabs(cmp_slabs):
+            return None
+        sl, vw = self._slabs, self._views
+        if counters is not None and (sl.get("__ctr") is not counters or self._lens["__ctr"] >= counters.shape[1]
+                                     or vw.get("reads_pred") is not self.reads_pred):
+            return None
+        return rows
+
+    def same_compressed_slabs(self, cmp_slabs) -> bool:
+        """True if K_cmp / V_cmp are still backed by exactly these slabs (an emission that outgrows a slab reallocates it)."""
+        sl, vw = self._slabs, self._views
+        return (sl.get("K_cmp") is cmp_slabs[0] and sl.get("V_cmp") is cmp_slabs[1] and vw.get("K_cmp") is self.K_cmp
+                and vw.get("V_cmp") is self.V_cmp)
+
+    def prepare_decode(self, like: torch.Tensor, with_counters: bool):
+        """Make every cache a decode step touches slab-backed with room for one more row (token caches, one compressed token an
+        emission may add, one counter column): returns (token_slabs, rows, (K_cmp slab, V_cmp slab), counter slab or None)."""
+        slabs, rows = self.token_append_slots(like)
+        for name in ("K_cmp", "V_cmp"):
+            cur: torch.Tensor = getattr(self, name)
+            if cur.dtype != like.dtype or cur.device != like.device:
+                if cur.shape[2] != 0:
+                    raise RuntimeError(f"NSA_KV.{name}: dtype/device of the cache does not match the new tokens")
+                setattr(self, name, like.new_zeros((cur.shape[0], cur.shape[1], 0, cur.shape[3])))
+                self._slabs.pop(name, None)
+            self._ensure(name, 1)
+        ctr = self.counter_slot()[0] if with_counters else None
+        return tuple(slabs), rows, (self._slabs["K_cmp"], self._slabs["V_cmp"]), ctr
+
+    def rows_present(self, name: str) -> int:
+        """Rows held in the slab of `name` when it is known to be slab-backed and in sync (no tensor op)."""
+        return self._lens[name]
+
+    def counter_column(self) -> int:
+        return self._lens["__ctr"]
 
     def commit_token_append(self, w: int) -> None:
         for name in self._TOKEN_FIELDS:

@@ -26,8 +26,6 @@ import torch.nn.functional as F
 from .. import ops
 from ..cache.kv_cache import NSA_KV
 from .block_index import build_block_meta
-from .compress_pool import avg_pool_phi_rope_kv
-from .rope import apply_rope
 
 
 def _env_true(name: str, default: str = "0") -> bool:
@@ -264,17 +262,6 @@ class NSAAttention(nn.Module):
             self._wcat = cached
         return cached[1]
 
-    def _decode_gate(self, cfg: ops.NSAConfig, dev):
-        if cfg.gate_mode != ops.GATE_MLP:
-            return None
-        ps = self.gate.params()
-        key = tuple((p.data_ptr(), p._version) for p in ps)
-        cached = getattr(self, "_gate_struct", None)
-        if cached is None or cached[0] != key:
-            cached = (key, ops._gate_struct(ps, dev))
-            self._gate_struct = cached
-        return cached[1]
-
     def _decode_plan(self, y: torch.Tensor, kv: NSA_KV, aux: bool):
         """(plan, rows): the prebuilt argument blocks of this module's decode step on `kv` (ops.DecodeStepPlan), rebuilt whenever a
         cache slab was reallocated or replaced, the batch / dtype changed, or gate / rope settings moved."""
@@ -282,29 +269,19 @@ class NSAAttention(nn.Module):
                    tuple((p.data_ptr(), p._version) for p in self.gate.params()))
         plan = getattr(kv, "_decode_plan", None)
         if plan is not None and plan[0] is self and plan[1] == cfg_key:
-            rows = kv.fast_token_rows(plan[2].slabs)
-            if rows is not None and kv._slabs.get("K_cmp") is plan[2].cmp_slabs[0] and kv._slabs.get("V_cmp") is plan[2].cmp_slabs[1] \
-                    and kv._views.get("K_cmp") is kv.K_cmp and kv._views.get("V_cmp") is kv.V_cmp \
-                    and (not aux or (kv._slabs.get("__ctr") is plan[2].counters and kv._lens["__ctr"] < plan[2].counters.shape[1]
-                                     and kv._views.get("reads_pred") is kv.reads_pred)):
+            rows = kv.decode_state(plan[2].slabs, plan[2].cmp_slabs, plan[2].counters if aux else None)
+            if rows is not None:
                 return plan[2], rows
-        slabs, rows = kv.token_append_slots(y)
-        # room for the compressed token a step may emit, so that the slab the plan points at survives the emission
-        for name, D in (("K_cmp", self.d_k), ("V_cmp", self.d_v)):
-            cur = getattr(kv, name)
-            if cur.dtype != y.dtype or cur.device != y.device:
-                if cur.shape[2] != 0:
-                    raise RuntimeError(f"NSA_KV.{name}: dtype/device of the cache does not match the new tokens")
-                setattr(kv, name, y.new_zeros((cur.shape[0], cur.shape[1], 0, D)))
-                kv._slabs.pop(name, None)
-            kv._ensure(name, 1)
-        ctr = kv.counter_slot()[0] if aux else None
-        cfg = self._cfg()
-        gate = self.gate.params() if cfg.gate_mode == ops.GATE_MLP else None
-        p = ops.DecodeStepPlan(y, slabs, (kv._slabs["K_cmp"], kv._slabs["V_cmp"]), ctr, H=self.n_heads, G=self.n_kv_groups,
-                               Dk=self.d_k, Dv=self.d_v, cfg=cfg, gate=gate, rope_scale=self.rope_scale)
+        slabs, rows, cmp_slabs, ctr = kv.prepare_decode(y, aux)
+        p = self._new_plan(y, slabs, cmp_slabs, ctr)
         kv._decode_plan = (self, cfg_key, p)
         return p, rows
+
+    def _new_plan(self, y, slabs, cmp_slabs, ctr) -> "ops.DecodeStepPlan":
+        cfg = self._cfg()
+        gate = self.gate.params() if cfg.gate_mode == ops.GATE_MLP else None
+        return ops.DecodeStepPlan(y, slabs, cmp_slabs, ctr, H=self.n_heads, G=self.n_kv_groups, Dk=self.d_k, Dv=self.d_v, cfg=cfg,
+                                  gate=gate, rope_scale=self.rope_scale)
 
     def _forward_decode(self, x: torch.Tensor, kv: NSA_KV) -> tuple[torch.Tensor, NSA_KV]:
         """One decode step (nsa_attention.py:545-976): one GEMM for the seven projections, one kernel that rotates Q/K and writes
@@ -321,7 +298,7 @@ class NSAAttention(nn.Module):
             num_cmp = 0 if S_raw < self.l else (S_raw - self.l) // self.d + 1
             n_win_read = min(self.w, S_raw)
             reads = num_cmp + self.n_sel * self.l_sel + n_win_read  # :634-638
-            plan.produce(y, t, rows, kv._lens["__ctr"] if aux else 0, (reads, reads, self.n_sel * self.l_sel, num_cmp, n_win_read))
+            plan.produce(y, t, rows, kv.counter_column() if aux else 0, (reads, reads, self.n_sel * self.l_sel, num_cmp, n_win_read))
             kv.commit_token_append(self.w)
             if aux:
                 kv.commit_counters()
@@ -329,25 +306,19 @@ class NSAAttention(nn.Module):
                 K_new, V_new = ops.phi_avgpool(kv.K_cmp_raw_seq[:, :, S_raw - self.l:S_raw],
                                                kv.V_cmp_raw_seq[:, :, S_raw - self.l:S_raw], self.l, self.d, t0=S_raw - self.l)
                 kv.append_compressed(K_new, V_new)
-                if kv._slabs["K_cmp"] is not plan.cmp_slabs[0] or kv._slabs["V_cmp"] is not plan.cmp_slabs[1]:
-                    kv._decode_plan = None  # the emission outgrew the compressed slab: rebuild on the new one
-                    plan, _ = self._decode_plan_after_growth(y, kv, aux, plan)
+                if not kv.same_compressed_slabs(plan.cmp_slabs):
+                    # the emission outgrew the compressed slab: finish this step on the new slabs (the step's Q, already produced
+                    # into the old plan's buffer, is carried over) and let the next step build its plan afresh
+                    slabs, _, cmp_slabs, _ = kv.prepare_decode(y, False)
+                    grown = self._new_plan(y, slabs, cmp_slabs, None)
+                    grown.Q.copy_(plan.Q)
+                    plan, kv._decode_plan = grown, None
             if getattr(kv, "meta", None) is None or kv.meta.sel_starts.numel() * self.l_sel < t + 1 or kv.meta.sel_starts.numel() == 0:
                 kv.meta = build_block_meta(seq_len=max(t + 1, self.l_sel), l=self.l, d=self.d, l_sel=self.l_sel, n_sel=self.n_sel, w=self.w)
             ranges = torch.empty((B, G, self.n_sel, 2), dtype=torch.int32, device=x.device)
-            O = plan.attend(t, kv._lens["K_win"], kv._lens["K_cmp"], ranges)
+            O = plan.attend(t, kv.rows_present("K_win"), kv.rows_present("K_cmp"), ranges)
             if self._env_cache["strict_asserts"]:
                 assert int(ranges[..., 1].max()) <= t + 1, "Selection must not access future tokens."
             self._last_ranges = ranges
             out = self.out(O.reshape(B, 1, self.n_heads * self.d_v))
         return out, kv
-
-    def _decode_plan_after_growth(self, y: torch.Tensor, kv: NSA_KV, aux: bool, old):
-        """Plan on the reallocated compressed slabs; the step's Q (already produced into the old plan's buffer) is carried over."""
-        cfg = self._cfg()
-        gate = self.gate.params() if cfg.gate_mode == ops.GATE_MLP else None
-        slabs = tuple(kv._slabs[n] for n in kv._TOKEN_FIELDS)
-        p = ops.DecodeStepPlan(y, slabs, (kv._slabs["K_cmp"], kv._slabs["V_cmp"]), old.counters, H=self.n_heads, G=self.n_kv_groups,
-                               Dk=self.d_k, Dv=self.d_v, cfg=cfg, gate=gate, rope_scale=self.rope_scale)
-        p.Q.copy_(old.Q)
-        return p, None

@@ -7,7 +7,7 @@ max(kernels, H2D, D2H) per batch instead of their sum.  PyTorch is plumbing here
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable, List, Optional, Sequence
+from typing import Dict, List, Optional, Sequence
 
 import torch
 

@@ -2,9 +2,7 @@
 golden vectors.  Tolerances (SURVEY 8c, the reference's own vocabulary in its GPU tests): fp32 max-abs <= 5e-5;
 bf16 inputs vs the fp32 oracle max-abs <= 2e-2 and MAE <= 1e-3 per branch and for the gated output; gradients
 relative error <= 5e-3 (fp32) / 3e-2 (bf16)."""
-import math
 
-import numpy as np
 import pytest
 import torch
 

@@ -3,7 +3,6 @@
 attention_bgh(causal=False)) on the same weights and inputs."""
 import os
 
-import numpy as np
 import pytest
 import torch
 
@@ -176,3 +175,34 @@ def test_module_m7c_bf16_tensor_core_path_prefill_and_decode():
     assert err.mean() <= 3e-3 and err.max() <= 0.15, (err.mean(), err.max())
     err_dec = err[:, S0:]
     assert err_dec.mean() <= 3e-3 and err_dec.max() <= 0.15, (err_dec.mean(), err_dec.max())
+
+
+def test_long_stepwise_decode_crosses_every_slab_reallocation():
+    """150 decode steps from an empty cache with l=4, d=2 (74 emitted compressed tokens): the token slabs (capacity 64 -> 130 ->
+    ...), the compressed slabs (64 -> 130) and hence the prebuilt decode plan are rebuilt mid-stream, also in the middle of an
+    emission step.  Reference: the same tokens as ONE prefill under NSA_PREFILL_TILE (== S decode steps, nsa_attention.py:1507-1519).
+    fp32, tolerance 5e-5 max-abs; read counters against the closed form (nsa_attention.py:634-638)."""
+    from nsa_vibe_b200 import NSAAttention, build_block_meta, create_empty_kv
+    dim, H, G, dk, dv, l, d, ls, n, w = 32, 4, 2, 8, 8, 4, 2, 8, 4, 16
+    os.environ["NSA_PREFILL_TILE"] = "8"
+    try:
+        torch.manual_seed(21)
+        m = NSAAttention(dim, H, G, dk, dv, l=l, d=d, l_sel=ls, n_sel=n, w=w).cuda()
+    finally:
+        os.environ.pop("NSA_PREFILL_TILE", None)
+    S = 150
+    x = torch.randn(2, S, dim, device="cuda")
+    mk = lambda: create_empty_kv(2, G, dk, dv, build_block_meta(ls, l, d, ls, n, w), device="cuda", dtype=torch.float32)
+    with torch.no_grad():
+        ref, kv_ref = m(x, mk(), prefill=True)
+        kv = mk()
+        outs = []
+        for i in range(S):
+            o, kv = m(x[:, i:i + 1], kv, prefill=False)
+            outs.append(o)
+    out = torch.cat(outs, dim=1)
+    assert torch.allclose(out, ref, atol=5e-5), (out - ref).abs().max()
+    assert kv.K_cmp.shape[2] == (S - l) // d + 1 == 74 and torch.allclose(kv.K_cmp, kv_ref.K_cmp, atol=1e-5)
+    assert torch.allclose(kv.K_sel, kv_ref.K_sel, atol=1e-5) and kv.K_win.shape[2] == w  # (GEMMs of different M: not bitwise)
+    want_reads = [(0 if t + 1 < l else (t + 1 - l) // d + 1) + n * ls + min(w, t + 1) for t in range(S)]
+    assert kv.reads_act_total.tolist() == want_reads and kv.reads_act_cmp.tolist() == [(0 if t + 1 < l else (t + 1 - l) // d + 1) for t in range(S)]

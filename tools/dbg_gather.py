@@ -1,4 +1,4 @@
-import sys, os
+import sys
 sys.path.insert(0, '/root/repo')
 import torch
 from nsa_vibe_b200 import ops
