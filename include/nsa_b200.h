@@ -196,6 +196,23 @@ int nsa_rmsnorm_bwd(const void* dy, const void* s, const void* w, const float* r
                     float* dw_partial, int rows, int dim, int x_dtype, int w_dtype, int y_dtype, void* stream);
 int nsa_rmsnorm_partials(int rows);
 
+/* ---- observability reductions ---------------------------------------------------------------------
+ * One device record holding what _compute_gate_stats (nsa_attention.py:127-165) and _update_sel_stats_from_ranges (:455-507)
+ * report: the host reads it with ONE copy and divides by the row counts.  gates [n_gate_rows,3] fp32 (may be NULL), ranges
+ * [n_range_rows,K,2] int32 (may be NULL), row_len: workspace of n_range_rows int32.
+ *   gate_sum = { sum entropy, sum max_gate, #collapsed (entropy < 0.1 and max_gate > 0.95), sum g_cmp, sum g_sel, sum g_win };
+ *   entropy_min_ord / max_gate_max_ord: fp32 bits mapped to a total order (i >= 0 ? i : i ^ 0x7fffffff), the map is its own inverse;
+ *   k_sum = sum_rows L, k_max = max_rows L, rows_at_max = #rows with L == k_max, L = sum_k max(end - start, 0). */
+typedef struct nsa_stats {
+  double gate_sum[6];
+  int32_t entropy_min_ord, max_gate_max_ord;
+  int64_t k_sum;
+  int32_t k_max, pad_;
+  int64_t rows_at_max;
+} nsa_stats_t;
+int nsa_stats(const float* gates, int64_t n_gate_rows, const int32_t* ranges, int64_t n_range_rows, int K, int32_t* row_len,
+              nsa_stats_t* out, void* stream);
+
 enum { NSA_WS_SCORE_SELECT = 0, NSA_WS_DECODE = 1, NSA_WS_PREFILL = 2, NSA_WS_SEL_BLOCKMAJOR = 3, NSA_WS_BWD = 4 };
 int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which);
 

@@ -43,6 +43,13 @@ class DecodeProduce(C.Structure):
                 ("base", C.c_float), ("scale", C.c_float), ("dtype", C.c_int32), ("S", C.c_int32), ("inverse", C.c_int32)]
 
 
+class Stats(C.Structure):
+    """struct nsa_stats (include/nsa_b200.h)."""
+
+    _fields_ = [("gate_sum", C.c_double * 6), ("entropy_min_ord", C.c_int32), ("max_gate_max_ord", C.c_int32), ("k_sum", C.c_int64),
+                ("k_max", C.c_int32), ("pad_", C.c_int32), ("rows_at_max", C.c_int64)]
+
+
 _P, _I, _I64 = C.c_void_p, C.c_int, C.c_int64
 _DP, _GP = C.POINTER(Dims), C.POINTER(GateParams)
 
@@ -70,6 +77,7 @@ SIGNATURES = {
     "nsa_rmsnorm_fwd": (_I, [_P] * 6 + [_I, _I, C.c_float, _I, _I, _I, _I, _P]),
     "nsa_rmsnorm_bwd": (_I, [_P] * 8 + [_I, _I, _I, _I, _I, _P]),
     "nsa_rmsnorm_partials": (_I, [_I]),
+    "nsa_stats": (_I, [_P, _I64, _P, _I64, _I, _P, _P, _P]),
     "nsa_workspace_bytes": (_I64, [_DP, _I]),
 }
 

@@ -73,15 +73,10 @@ class GateMLP(nn.Module):
 
 
 def _compute_gate_stats(gates: torch.Tensor) -> dict:
-    """Gate health statistics (nsa_attention.py:127-165), one device->host transfer."""
-    with torch.no_grad():
-        g = gates.reshape(-1, 3).float()
-        ent = -(g * (g + 1e-8).log()).sum(dim=-1)
-        mx = g.max(dim=-1)[0]
-        collapsed = ((ent < 0.1) & (mx > 0.95)).float().mean()
-        packed = torch.cat([torch.stack([ent.mean(), ent.min(), mx.mean(), mx.max(), collapsed]), g.mean(dim=0)]).tolist()
-    return {"entropy_mean": packed[0], "entropy_min": packed[1], "max_gate_mean": packed[2], "max_gate_max": packed[3],
-            "branch_shares": packed[5:8], "collapse_fraction": packed[4], "total_gates": int(g.shape[0])}
+    """Gate health statistics (nsa_attention.py:127-165): one reduction kernel, one device->host transfer (ops.stats)."""
+    st = ops.stats(gates=gates)
+    return {k: st[k] for k in ("entropy_mean", "entropy_min", "max_gate_mean", "max_gate_max", "branch_shares", "collapse_fraction",
+                               "total_gates")}
 
 
 class NSAAttention(nn.Module):
@@ -165,18 +160,15 @@ class NSAAttention(nn.Module):
         return prev
 
     def get_selection_stats(self) -> Optional[dict]:
+        """nsa_attention.py:455-507, reduced on the device (ops.stats)."""
         r = self._last_ranges
         if r is None:
             return None
         base = {"l_sel": int(self.l_sel), "n_sel": int(self.n_sel)}
         if r.numel() == 0:
             return {"k_mean": 0.0, "k_max": 0, "rows": 0, "pct_at_max": 0.0, **base}
-        L = (r[..., 1] - r[..., 0]).clamp_min(0).sum(dim=-1).to(torch.int64).reshape(-1)
-        k_max = L.max()
-        packed = torch.stack([L.float().mean(), k_max.float(), (L == k_max).float().mean()]).tolist()
-        k_max_i = int(packed[1])
-        return {"k_mean": packed[0], "k_max": k_max_i, "rows": int(L.numel()), "pct_at_max": packed[2] if k_max_i > 0 else 0.0,
-                **base}
+        st = ops.stats(ranges=r)
+        return {"k_mean": st["k_mean"], "k_max": st["k_max"], "rows": st["rows"], "pct_at_max": st["pct_at_max"], **base}
 
     # ---- forward ---------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor, kv: NSA_KV, *, prefill: bool) -> tuple[torch.Tensor, NSA_KV]:

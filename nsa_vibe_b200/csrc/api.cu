@@ -321,6 +321,11 @@ int nsa_rmsnorm_bwd(const void* dy, const void* s, const void* w, const float* r
 
 int nsa_rmsnorm_partials(int rows) { return rmsnorm_partials(rows); }
 
+int nsa_stats(const float* gates, int64_t n_gate_rows, const int32_t* ranges, int64_t n_range_rows, int K, int32_t* row_len,
+              nsa_stats_t* out, void* stream) {
+  return launch_stats(gates, (long long)n_gate_rows, ranges, (long long)n_range_rows, K, row_len, out, (cudaStream_t)stream);
+}
+
 int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which) {
   if (!dm) return 0;
   switch (which) {

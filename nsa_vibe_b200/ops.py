@@ -656,3 +656,49 @@ def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-6, *, residua
     if od not in _DTYPES:
         raise RuntimeError(f"rmsnorm: unsupported output dtype {od}")
     return _RMSNorm.apply(x, residual, weight, eps, od)
+
+
+# ----------------------------------------------------------------------------------------------------
+# observability reductions
+# ----------------------------------------------------------------------------------------------------
+def _ord_to_float(i: int) -> float:
+    import struct
+    i = i if i >= 0 else i ^ 0x7FFFFFFF
+    return struct.unpack("<f", struct.pack("<i", i))[0]
+
+
+def stats(gates: Optional[torch.Tensor] = None, ranges: Optional[torch.Tensor] = None) -> dict:
+    """Gate-health statistics (nsa_attention.py:127-165) of gates [...,3] and / or selection statistics (:455-507) of ranges
+    [...,K,2], reduced on the device and read back with ONE device->host copy of an 80-byte record.  Returns the reference's keys:
+    entropy_mean/min, max_gate_mean/max, branch_shares, collapse_fraction, total_gates; k_mean, k_max, rows, pct_at_max."""
+    _require_cuda(gates, ranges)
+    dev = (gates if gates is not None else ranges).device
+    g = None
+    if gates is not None:
+        g = _c(gates.detach().reshape(-1, 3).float())
+    r, K = None, 0
+    if ranges is not None:
+        K = int(ranges.shape[-2]) if ranges.dim() >= 2 else 0
+        r = _c(ranges.detach().reshape(-1, K, 2).to(torch.int32)) if ranges.numel() else None
+    n_g = 0 if g is None else int(g.shape[0])
+    n_r = 0 if r is None else int(r.shape[0])
+    rec = torch.empty(C.sizeof(_lib.Stats), dtype=torch.uint8, device=dev)
+    row_len = torch.empty(max(n_r, 1), dtype=torch.int32, device=dev)
+    _call("nsa_stats", _ptr(g) if n_g else None, n_g, _ptr(r) if n_r else None, n_r, K, _ptr(row_len), _ptr(rec), _stream())
+    st = _lib.Stats.from_buffer_copy(rec.cpu().numpy().tobytes())  # the one transfer (synchronises)
+    out = {}
+    if gates is not None:
+        if n_g:
+            out.update(entropy_mean=st.gate_sum[0] / n_g, entropy_min=_ord_to_float(st.entropy_min_ord),
+                       max_gate_mean=st.gate_sum[1] / n_g, max_gate_max=_ord_to_float(st.max_gate_max_ord),
+                       branch_shares=[st.gate_sum[3] / n_g, st.gate_sum[4] / n_g, st.gate_sum[5] / n_g],
+                       collapse_fraction=st.gate_sum[2] / n_g, total_gates=n_g)
+        else:
+            out.update(entropy_mean=float("nan"), entropy_min=float("nan"), max_gate_mean=float("nan"), max_gate_max=float("nan"),
+                       branch_shares=[float("nan")] * 3, collapse_fraction=float("nan"), total_gates=0)
+    if ranges is not None:
+        if n_r:
+            out.update(k_mean=st.k_sum / n_r, k_max=int(st.k_max), rows=n_r, pct_at_max=(st.rows_at_max / n_r) if st.k_max > 0 else 0.0)
+        else:
+            out.update(k_mean=0.0, k_max=0, rows=0, pct_at_max=0.0)
+    return out

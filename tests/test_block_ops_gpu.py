@@ -134,3 +134,31 @@ def test_block_stack_with_deferred_residual_matches_plain_stack_and_torch_norm()
         assert (ga - g_).abs().max() <= 2e-3 * max(1.0, float(g_.abs().max()))
         for u, v in zip(pa, p_):
             assert (u - v).abs().max() <= 2e-3 * max(1.0, float(v.abs().max())), (u.shape, (u - v).abs().max())
+
+
+@pytest.mark.parametrize("n_rows", [1, 37, 5000, 200003])
+def test_device_stats_match_the_reference_formulas(n_rows):
+    """ops.stats against the reference's ATen formulas (nsa_attention.py:127-165 gate health, :455-507 selection statistics):
+    integers and extrema exactly, means to 1e-6."""
+    from nsa_vibe_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(n_rows)
+    logits = torch.randn(n_rows, 3, generator=g, device="cuda") * 4.0
+    logits[::7] = torch.tensor([60.0, 0.0, -3.0], device="cuda")  # collapsed rows
+    gates = torch.softmax(logits, dim=-1)
+    K = 5
+    starts = torch.randint(0, 500, (n_rows, K), generator=g, device="cuda", dtype=torch.int32)
+    lens = torch.randint(-3, 64, (n_rows, K), generator=g, device="cuda", dtype=torch.int32)  # negative: empty / padded ranges
+    ranges = torch.stack([starts, starts + lens], dim=-1)
+    got = ops.stats(gates=gates.view(-1, 1, 3) if n_rows > 1 else gates, ranges=ranges.view(n_rows, 1, K, 2))
+    ent = -(gates * (gates + 1e-8).log()).sum(dim=-1)
+    mx = gates.max(dim=-1)[0]
+    assert got["total_gates"] == n_rows and got["rows"] == n_rows
+    assert abs(got["entropy_mean"] - ent.double().mean().item()) <= 1e-6 and abs(got["max_gate_mean"] - mx.double().mean().item()) <= 1e-6
+    assert abs(got["entropy_min"] - ent.min().item()) <= 1e-7 and got["max_gate_max"] == mx.max().item()
+    assert abs(got["collapse_fraction"] - ((ent < 0.1) & (mx > 0.95)).double().mean().item()) <= 1e-12
+    for a, b in zip(got["branch_shares"], gates.double().mean(dim=0).tolist()):
+        assert abs(a - b) <= 1e-6
+    L = (ranges[..., 1] - ranges[..., 0]).clamp_min(0).sum(dim=-1).to(torch.int64)
+    assert got["k_max"] == int(L.max()) and abs(got["k_mean"] - L.double().mean().item()) <= 1e-9
+    assert abs(got["pct_at_max"] - (L == L.max()).double().mean().item()) <= 1e-12
+    assert ops.stats(ranges=torch.zeros(0, 2, 4, 2, dtype=torch.int32, device="cuda")) == {"k_mean": 0.0, "k_max": 0, "rows": 0, "pct_at_max": 0.0}
