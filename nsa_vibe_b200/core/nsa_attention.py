@@ -124,6 +124,8 @@ class NSAAttention(nn.Module):
             "nvtx": _env_true("NSA_NVTX"),
             "disable_aux_stats": _env_true("NSA_DISABLE_AUX_STATS"),
             "pcmp_norm": os.getenv("NSA_PCMP_NORM", "full_row").strip().lower(),  # B200 addition
+            # selection_scorer.py:46-56: score fp32 activations with bf16 operands (here: the tcgen05 scorer, fp32 accumulation)
+            "pcmp_mixed": os.getenv("NSA_P_CMP_MIXED", "0").lower() in ("1", "true", "yes", "on"),
         }
         try:
             rs = float(os.getenv("NSA_ROPE_SCALE", "1.0"))
@@ -226,14 +228,19 @@ class NSAAttention(nn.Module):
         cfg = self._cfg(causal_norm=via_decode)
         gate = self.gate.params() if cfg.gate_mode == ops.GATE_MLP else None
         self._nvtx("branch_attn+gate")
+        pre_ranges = None
+        if self._env_cache["pcmp_mixed"] and Q.dtype == torch.float32:
+            # NSA_P_CMP_MIXED (selection_scorer.py:46-56): the scores that drive the selection come from bf16 operands; the three
+            # branches still attend in fp32 over the ranges chosen that way
+            pre_ranges = ops.score_select(Q.detach().bfloat16(), K_cmp.detach().bfloat16(), cfg, mode=sel_mode, t0=t0)
         if t0 == 0:
             O, ranges, gates = ops.prefill_core(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, gate, cfg, sel_mode=sel_mode,
-                                                t0=0, stopgrad_gates=self._env_cache["stopgrad_gates"])
+                                                t0=0, stopgrad_gates=self._env_cache["stopgrad_gates"], ranges=pre_ranges)
         else:  # chunked prefill continues on the cache slabs (inference only)
             n = t0 + S
             O, ranges, gates = ops.prefill_core(
                 Q, kv.slab("K_sel"), kv.slab("V_sel"), kv.slab("K_win"), kv.slab("V_win"), K_cmp, V_cmp, gate, cfg,
-                sel_mode=sel_mode, t0=t0, S_sel_kv=n, S_win_kv=kv.length("K_win"), win_off=n - kv.length("K_win"))
+                sel_mode=sel_mode, t0=t0, S_sel_kv=n, S_win_kv=kv.length("K_win"), win_off=n - kv.length("K_win"), ranges=pre_ranges)
         self._nvtx(None)
         if self._env_cache["strict_asserts"] and ranges.numel() > 0:
             tpos = torch.arange(t0, t0 + S, device=x.device).view(1, S, 1, 1)

@@ -206,3 +206,33 @@ def test_long_stepwise_decode_crosses_every_slab_reallocation():
     assert torch.allclose(kv.K_sel, kv_ref.K_sel, atol=1e-5) and kv.K_win.shape[2] == w  # (GEMMs of different M: not bitwise)
     want_reads = [(0 if t + 1 < l else (t + 1 - l) // d + 1) + n * ls + min(w, t + 1) for t in range(S)]
     assert kv.reads_act_total.tolist() == want_reads and kv.reads_act_cmp.tolist() == [(0 if t + 1 < l else (t + 1 - l) // d + 1) for t in range(S)]
+
+
+def test_pcmp_mixed_flag_scores_with_bf16_operands():
+    """NSA_P_CMP_MIXED=1 (selection_scorer.py:46-56): an fp32 module scores with bf16 operands (tcgen05 scorer, m7c head dims) and
+    attends in fp32.  Measured agreement with the all-fp32 selection: >= 90 % of the (b,t,g) rows pick identical ranges, and the
+    module output stays within mean-abs 2e-3 (a flipped near-tie swaps one of 16 blocks of one row)."""
+    from nsa_vibe_b200 import NSAAttention, build_block_meta, create_empty_kv
+    dim, H, G, dk, dv, l, d, ls, n, w = 768, 12, 2, 64, 64, 32, 16, 64, 16, 512
+    mods = {}
+    for flag in ("0", "1"):
+        os.environ["NSA_PREFILL_BATCHED"] = "1"
+        os.environ["NSA_P_CMP_MIXED"] = flag
+        try:
+            torch.manual_seed(9)
+            mods[flag] = NSAAttention(dim, H, G, dk, dv, l=l, d=d, l_sel=ls, n_sel=n, w=w).cuda()
+        finally:
+            os.environ.pop("NSA_PREFILL_BATCHED", None)
+            os.environ.pop("NSA_P_CMP_MIXED", None)
+    mods["1"].load_state_dict(mods["0"].state_dict())
+    x = torch.randn(1, 2048, dim, device="cuda")
+    outs, rngs = {}, {}
+    with torch.no_grad():
+        for flag, m in mods.items():
+            kv = create_empty_kv(1, G, dk, dv, build_block_meta(64, l, d, ls, n, w), device="cuda", dtype=torch.float32)
+            outs[flag], _ = m(x, kv, prefill=True)
+            rngs[flag] = m._last_ranges
+    same = (rngs["0"] == rngs["1"]).flatten(3).all(dim=-1).float().mean().item()
+    err = (outs["0"] - outs["1"]).abs()
+    assert same >= 0.90, same
+    assert err.mean() <= 2e-3 and torch.isfinite(outs["1"]).all(), (same, err.mean(), err.max())
