@@ -121,19 +121,28 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def wait_first(self, timeout=1.5):
+        t_end = time.time() + timeout
+        while self.proc is not None and not self.lines and time.time() < t_end:
+            time.sleep(0.01)
+
+    def stop(self, t0=None, t1=None):
+        """Median SM clock and throttle reasons over the samples that arrived inside [t0, t1] (the timed region; the sampler is
+        started before the warm-up so that nvidia-smi is already streaming when it begins)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        inside = [ln for ts, ln in self.lines if (t0 is None or ts >= t0) and (t1 is None or ts <= t1 + 0.06)]
+        if not inside:  # a region shorter than one sampling period: take the samples after its start
+            inside = [ln for ts, ln in self.lines if t0 is None or ts >= t0] or [ln for _, ln in self.lines[-1:]]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -275,12 +284,15 @@ def main():
         torch.cuda.synchronize()
 
     with torch.no_grad():
-        for _ in range(args.warmup):
-            step(inp)
-        barrier()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
+        for _ in range(args.warmup):
+            step(inp)
+        if rank == 0:
+            sampler.wait_first()
+        barrier()
+        t_wall0 = time.time()
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
         n0 = lib.nsa_kernel_launches()
         e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -295,7 +307,7 @@ def main():
         e_end.record()
         barrier()
         launches = lib.nsa_kernel_launches() - n0
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
         ms_total = e_start.elapsed_time(e_end)
         ms_score = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
         ms_attn = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
@@ -408,6 +420,24 @@ def main():
                                 "unit": "TFLOP/s" if b_ == "tensor" else "GB/s",
                                 "frac": (w_ / (m_ * 1e-3) / (1e12 if b_ == "tensor" else 1e9)) / (pk["tf_sustained"] if b_ == "tensor" else pk["hbm"])}
                                for n_, m_, b_, w_, _ in cand]}
+    # the same 64k step under the semantics the reference itself can run at this length (per-token decode steps, i.e.
+    # NSA_PREFILL_TILE: decode selection rule, p_cmp normalised over the visible compressed keys only) -- reported beside the headline,
+    # which keeps the batched-prefill rule with the full-row normaliser (more exponentials)
+    alt = None
+    try:
+        cfg_c = ops.NSAConfig(l=c["l"], d=c["d"], l_sel=c["l_sel"], n_sel=c["n_sel"], w=c["w"], norm_mode=ops.NORM_CAUSAL)
+
+        def step_causal():
+            rg2 = ops.score_select(inp["Q"], inp["K_cmp"], cfg_c, mode=1)
+            ops.prefill_core(inp["Q"], inp["K_sel"], inp["V_sel"], inp["K_win"], inp["V_win"], inp["K_cmp"], inp["V_cmp"], gate, cfg_c,
+                             sel_mode=1, ranges=rg2)
+        with torch.no_grad():
+            ms_alt = t_of(step_causal, n=5)
+        alt = {"selection": "decode rule (select_topn_ranges), causal p_cmp normaliser: what NSA_PREFILL_TILE / stepwise decode computes",
+               "ms_per_step": ms_alt, "tok_per_s_per_gpu": B * S / (ms_alt * 1e-3)}
+    except Exception as ex:
+        alt = {"error": f"{type(ex).__name__}: {ex}"}
+    roofline["alt_semantics"] = alt
     cpu = None
     if not args.no_cpu:
         v, cores, sample = cpu_prefill_sample(S, args.cpu_rows)
@@ -516,11 +546,22 @@ def bench_decode(args, ops, cfg, dev, rank, world, barrier):
     e1.record()
     torch.cuda.synchronize()
     b1_us = s1.elapsed_time(e1) / n * 1e3
-    module = None
+    # module-level line: timed locally (no collective inside the try, so a rank that fails cannot leave the others waiting);
+    # the max over ranks is taken outside
+    module, mod_ms = None, float("nan")
     try:
-        module = bench_decode_module(S, Bd, dev, rank, world, barrier)
+        module = bench_decode_module(S, Bd, dev, rank)
+        mod_ms = module["us_per_step"] * 1e-3
     except Exception as ex:  # the module-level line is additional evidence; never lose the kernel line over it
         module = {"error": f"{type(ex).__name__}: {ex}"}
+    if world > 1:
+        mt = torch.tensor([mod_ms if mod_ms == mod_ms else 1e30], device=dev)
+        dist.all_reduce(mt, op=dist.ReduceOp.MAX)
+        if "error" not in module and float(mt.item()) < 1e29:
+            module["us_per_step"] = float(mt.item()) * 1e3
+            module["us_per_token"] = module["us_per_step"] / (Bd * world)
+        elif "error" not in module:
+            module["note"] += "; another rank failed, figures are this rank's"
     byts, reads = decode_bytes_per_token(S)
     pk = measured_peaks()
     ach = Bd * byts / (ms * 1e-3) / 1e9
@@ -532,12 +573,11 @@ def bench_decode(args, ops, cfg, dev, rank, world, barrier):
             "module": module}
 
 
-def bench_decode_module(S, Bd, dev, rank, world, barrier, n=24):
+def bench_decode_module(S, Bd, dev, rank, n=24):
     """The same step through the reference-facing module API: NSAAttention.forward(x [B,1,dim], kv, prefill=False) at context S
     (bench/bench_decode.py:113-136) -- one GEMM for the seven projections, the produce kernel (RoPE + in-place cache rows +
     read counters), phi on emission steps, the fused decode kernel, the output projection.  Caches are built directly from random
     tensors of length S - n (no prefill needed for timing), bf16, m7c dims."""
-    import torch.distributed as dist
     from nsa_vibe_b200.cache.kv_cache import create_empty_kv
     from nsa_vibe_b200.core.block_index import build_block_meta
     from nsa_vibe_b200.core.nsa_attention import NSAAttention
@@ -558,22 +598,20 @@ def bench_decode_module(S, Bd, dev, rank, world, barrier, n=24):
     with torch.no_grad():
         for _ in range(8):
             attn(x1, kv, prefill=False)
-        barrier()
+        torch.cuda.synchronize()
         k0 = ops_launches()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for _ in range(n):
             attn(x1, kv, prefill=False)
         e.record()
-        barrier()
+        torch.cuda.synchronize()
         k1 = ops_launches()
-    tt = torch.tensor([s.elapsed_time(e) / n], device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms = float(tt.item())
+    ms = s.elapsed_time(e) / n
     return {"what": "NSAAttention.forward(prefill=False): projections + cache append + fused decode step + output projection",
-            "us_per_step": ms * 1e3, "us_per_token": ms * 1e3 / (Bd * world), "batch_per_gpu": Bd, "context": int(kv.K_sel.shape[2]),
-            "nsa_launches_per_step": (k1 - k0) / n, "note": "eager Python step over prebuilt argument blocks (ops.DecodeStepPlan); about 145 us of host time per step"}
+            "us_per_step": ms * 1e3, "us_per_token": ms * 1e3 / Bd, "batch_per_gpu": Bd, "context": int(kv.K_sel.shape[2]),
+            "nsa_launches_per_step": (k1 - k0) / n,
+            "note": "eager Python step over prebuilt argument blocks (ops.DecodeStepPlan); about 120-145 us of host time per step"}
 
 
 def ops_launches():
