@@ -498,7 +498,7 @@ combine_kernel(nsa_dims_t dm, const void* __restrict__ Q, nsa_gate_params_t gp, 
 constexpr int kCfWarps = 8;
 
 template <typename T>
-__global__ void __launch_bounds__(kCfWarps * 32)
+__global__ void __launch_bounds__(kCfWarps * 32, 4)
 combine_fast_kernel(nsa_dims_t dm, const T* __restrict__ Q, nsa_gate_params_t gp, const T* __restrict__ O_br, T* __restrict__ O,
                     float* __restrict__ gates) {
   extern __shared__ float smem[];
@@ -524,6 +524,20 @@ combine_fast_kernel(nsa_dims_t dm, const T* __restrict__ Q, nsa_gate_params_t gp
   const size_t per_branch = (size_t)n_rows * row_elems;
   const float inv_tau = 1.0f / fmaxf(dm.gate_tau, 1e-6f);
   for (int row = blockIdx.x * kCfWarps + warp; row < n_rows; row += gridDim.x * kCfWarps) {
+    // the branch outputs do not depend on the gate: their loads (up to two 16-byte chunks per lane and branch) are issued before the
+    // MLP, whose dependent FMA chain then hides their latency
+    const size_t base = (size_t)row * row_elems;
+    constexpr int kPre = 2;
+    uint4 pa[kPre], pb[kPre], pc[kPre];
+#pragma unroll
+    for (int j = 0; j < kPre; ++j) {
+      const int cidx = lane + 32 * j;
+      if (cidx < chunks) {
+        pa[j] = *reinterpret_cast<const uint4*>(O_br + base + cidx * 8);
+        pb[j] = *reinterpret_cast<const uint4*>(O_br + per_branch + base + cidx * 8);
+        pc[j] = *reinterpret_cast<const uint4*>(O_br + 2 * per_branch + base + cidx * 8);
+      }
+    }
     float g0 = 1.0f / 3.0f, g1 = 1.0f / 3.0f, g2 = 1.0f / 3.0f;
     if (dm.gate_mode == NSA_GATE_CMP) { g0 = 1.f; g1 = 0.f; g2 = 0.f; }
     else if (dm.gate_mode == NSA_GATE_SEL) { g0 = 0.f; g1 = 1.f; g2 = 0.f; }
@@ -533,10 +547,15 @@ combine_fast_kernel(nsa_dims_t dm, const T* __restrict__ Q, nsa_gate_params_t gp
       const T* qrow = Q + (size_t)row * h * Dk;
       for (int k = 2 * lane; k < Dk; k += 64) {
         float m0 = 0.f, m1 = 0.f;
-        for (int hh = 0; hh < h; ++hh) {
-          const uint32_t v = *reinterpret_cast<const uint32_t*>(qrow + hh * Dk + k);
-          m0 += (float)reinterpret_cast<const T*>(&v)[0];
-          m1 += (float)reinterpret_cast<const T*>(&v)[1];
+        for (int h0 = 0; h0 < h; h0 += 8) {  // eight heads' loads in flight at a time
+          uint32_t v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = h0 + u < h ? *reinterpret_cast<const uint32_t*>(qrow + (h0 + u) * Dk + k) : 0u;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {  // zero bits are +0.0 in both 16-bit formats
+            m0 += (float)reinterpret_cast<const T*>(&v[u])[0];
+            m1 += (float)reinterpret_cast<const T*>(&v[u])[1];
+          }
         }
         qgp[k] = m0 / (float)h;
         qgp[k + 1] = m1 / (float)h;
@@ -571,19 +590,24 @@ combine_fast_kernel(nsa_dims_t dm, const T* __restrict__ Q, nsa_gate_params_t gp
       gates[(size_t)row * 3 + 1] = g1;
       gates[(size_t)row * 3 + 2] = g2;
     }
-    const size_t base = (size_t)row * row_elems;
-    for (int cidx = lane; cidx < chunks; cidx += 32) {
-      const uint4 a = *reinterpret_cast<const uint4*>(O_br + base + cidx * 8);
-      const uint4 b = *reinterpret_cast<const uint4*>(O_br + per_branch + base + cidx * 8);
-      const uint4 c = *reinterpret_cast<const uint4*>(O_br + 2 * per_branch + base + cidx * 8);
-      const T* pa = reinterpret_cast<const T*>(&a);
-      const T* pb = reinterpret_cast<const T*>(&b);
-      const T* pc = reinterpret_cast<const T*>(&c);
+    auto blend = [&](const uint4& a, const uint4& b, const uint4& c, int cidx) {
+      const T* ea = reinterpret_cast<const T*>(&a);
+      const T* eb = reinterpret_cast<const T*>(&b);
+      const T* ec = reinterpret_cast<const T*>(&c);
       uint4 o;
       T* po = reinterpret_cast<T*>(&o);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) po[e] = T(g0 * (float)pa[e] + g1 * (float)pb[e] + g2 * (float)pc[e]);
+      for (int e = 0; e < 8; ++e) po[e] = T(g0 * (float)ea[e] + g1 * (float)eb[e] + g2 * (float)ec[e]);
       *reinterpret_cast<uint4*>(O + base + cidx * 8) = o;
+    };
+#pragma unroll
+    for (int j = 0; j < kPre; ++j)
+      if (lane + 32 * j < chunks) blend(pa[j], pb[j], pc[j], lane + 32 * j);
+    for (int cidx = lane + 32 * kPre; cidx < chunks; cidx += 32) {  // rows wider than 2 x 32 chunks (h * Dv > 512)
+      const uint4 a = *reinterpret_cast<const uint4*>(O_br + base + cidx * 8);
+      const uint4 b = *reinterpret_cast<const uint4*>(O_br + per_branch + base + cidx * 8);
+      const uint4 c = *reinterpret_cast<const uint4*>(O_br + 2 * per_branch + base + cidx * 8);
+      blend(a, b, c, cidx);
     }
   }
 }

@@ -526,43 +526,56 @@ bwd_delta_kernel(nsa_dims_t dm, const void* __restrict__ dO, const void* __restr
   }
 }
 
-// 16-bit, Dv = 64: one 4-byte load per lane covers a head row; all loads of a head are issued before any is used.
+// 16-bit, Dv = 64: eight lanes per (b,s,g) row, 16-byte loads (a 64-element head row = 8 lanes x 8 elements), a 3-step shuffle
+// per head and branch; a warp works on four rows at once.  (One warp per head row with 4-byte loads and a 5-step warp sum per
+// head and branch was instruction-bound: 59 % issue-active at 2.6 TB/s.)
 template <typename T>
 __global__ void __launch_bounds__(kBwDeltaWarps * 32)
 bwd_delta16_kernel(nsa_dims_t dm, const T* __restrict__ dO, const T* __restrict__ O_br, int branch_mask, float* __restrict__ delta,
                    float* __restrict__ dgates) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane & 7, grp = lane >> 3;
   const int n_rows = dm.B * dm.S * dm.G, h = dm.h;
   const size_t rows_h = (size_t)n_rows * h;
-  auto unpack = [](uint32_t u, float& lo, float& hi) {
-    T a, b;
-    memcpy(&a, &u, 2);
-    memcpy(&b, reinterpret_cast<const char*>(&u) + 2, 2);
-    lo = (float)a;
-    hi = (float)b;
+  auto dot8 = [](const uint4& a, const uint4& b) {
+    const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w};
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      T a0, a1, b0, b1;
+      memcpy(&a0, &ua[k], 2);
+      memcpy(&a1, reinterpret_cast<const char*>(&ua[k]) + 2, 2);
+      memcpy(&b0, &ub[k], 2);
+      memcpy(&b1, reinterpret_cast<const char*>(&ub[k]) + 2, 2);
+      acc = fmaf((float)a0, (float)b0, acc);
+      acc = fmaf((float)a1, (float)b1, acc);
+    }
+    return acc;
   };
-  for (int row = blockIdx.x * kBwDeltaWarps + warp; row < n_rows; row += gridDim.x * kBwDeltaWarps) {
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  for (int base = (blockIdx.x * kBwDeltaWarps + warp) * 4; base < n_rows; base += gridDim.x * kBwDeltaWarps * 4) {  // warp-uniform
+    const int row = base + grp;
+    const bool valid = row < n_rows;
     float dg[3] = {0.f, 0.f, 0.f};
     for (int hh = 0; hh < h; ++hh) {
-      const size_t e0 = ((size_t)row * h + hh) * 64;
-      const uint32_t ud = reinterpret_cast<const uint32_t*>(dO + e0)[lane];
-      uint32_t uo[3];
+      const size_t e0 = ((size_t)(valid ? row : 0) * h + hh) * 64 + sub * 8;
+      const uint4 ud = valid ? *reinterpret_cast<const uint4*>(dO + e0) : zero;
+      uint4 uo[3];
 #pragma unroll
       for (int br = 0; br < 3; ++br)
-        uo[br] = (branch_mask & (1 << br)) ? reinterpret_cast<const uint32_t*>(O_br + br * rows_h * 64 + e0)[lane] : 0u;
-      float d0, d1;
-      unpack(ud, d0, d1);
+        uo[br] = (valid && (branch_mask & (1 << br))) ? *reinterpret_cast<const uint4*>(O_br + br * rows_h * 64 + e0) : zero;
 #pragma unroll
       for (int br = 0; br < 3; ++br) {
-        if (!(branch_mask & (1 << br))) continue;
-        float o0, o1;
-        unpack(uo[br], o0, o1);
-        const float part = warp_sum(fmaf(d0, o0, d1 * o1));
+        if (!(branch_mask & (1 << br))) continue;  // kernel-uniform
+        float part = dot8(ud, uo[br]);
+        part += __shfl_xor_sync(0xffffffffu, part, 4);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
         dg[br] += part;
-        if (lane == 0) delta[br * rows_h + (size_t)row * h + hh] = part;
+        if (valid && sub == 0) delta[br * rows_h + (size_t)row * h + hh] = part;
       }
     }
-    if (dgates && lane < 3 && (branch_mask & (1 << lane))) dgates[(size_t)row * 3 + lane] = lane == 0 ? dg[0] : (lane == 1 ? dg[1] : dg[2]);
+    if (dgates && valid && sub < 3 && (branch_mask & (1 << sub))) dgates[(size_t)row * 3 + sub] = sub == 0 ? dg[0] : (sub == 1 ? dg[1] : dg[2]);
   }
 }
 
@@ -671,7 +684,7 @@ static int launch_bwd_tc_t(const nsa_dims_t& dm, const BwdArgs& a, int tc_mask, 
   char* ws = reinterpret_cast<char*>(workspace);
   float* delta = reinterpret_cast<float*>(ws);
   const int n_rows = dm.B * dm.S * dm.G;
-  int blocks = ceil_div(n_rows, kBwDeltaWarps);
+  int blocks = ceil_div(n_rows, kBwDeltaWarps * (dm.Dv == 64 ? 4 : 1));
   if (blocks > 148 * 32) blocks = 148 * 32;
   if (dm.Dv == 64)
     bwd_delta16_kernel<T><<<blocks, kBwDeltaWarps * 32, 0, stream>>>(dm, (const T*)a.dO, (const T*)a.O_br, a.branch_mask, delta, a.dgates);
