@@ -319,3 +319,38 @@ def test_score_select_causal_pass2_is_bit_exact(S, h, B):
         t0, Sc = S // 2 + 5, S // 4
         part = ops.score_select(Q[:, t0:t0 + Sc].contiguous(), Kc, cfg, mode=0, t0=t0)
         assert torch.equal(part, fused0[:, t0:t0 + Sc])
+
+
+def test_needle_at_64k_full_size_is_selected_and_retrieved():
+    """BASELINE config 4 at full size (S=65536, m7c head dims, bf16): the needle check of bench/needle_64k_smoke.py:39-66 run through
+    the whole path instead of with a hand-made range -- a needle (32 identical key rows = one compressed window, with a distinctive
+    value) is planted at S/2, every later query matches it; scoring + selection must pick its selection block for every later row
+    and the selected-branch output must be the needle value (cosine > 0.999).  Rows before
+    the needle must never reach it (causality).  Size-independent property, no oracle call."""
+    ops = _ops()
+    B, S, G, h, D, l, d, ls, n, w = 1, 65536, 2, 6, 64, 32, 16, 64, 16, 512
+    pos = S // 2
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    r = lambda *s: torch.randn(*s, generator=gen, device="cuda")
+    K, V, Q = r(B, G, S, D), r(B, G, S, D), r(B, S, G, h, D)
+    k_star, v_star = r(B, G, D), r(B, G, D)
+    K[:, :, pos:pos + l] = k_star[:, :, None]          # one whole compressed window [pos, pos+l) (pos is a multiple of d)
+    V[:, :, pos:pos + l] = v_star[:, :, None]
+    Q[:, pos + l:] = 4.0 * k_star[:, None, :, None, :]   # every later query is aligned with the needle
+    # phi without RoPE for this synthetic check: K_cmp[i] = mean of rows [i*d, i*d + l)
+    K_cmp = K.unfold(2, l, d).mean(dim=-1).contiguous()
+    assert K_cmp.shape[2] == (S - l) // d + 1
+    Qb, Kb, Vb, Kcb = Q.bfloat16(), K.bfloat16(), V.bfloat16(), K_cmp.bfloat16()
+    cfg = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w)
+    ranges = ops.score_select(Qb, Kcb, cfg, mode=0)                  # [1,S,G,K,2]
+    s_, e_ = ranges[..., 0].long(), ranges[..., 1].long()
+    t = torch.arange(S, device="cuda").view(1, S, 1, 1)
+    covers = ((s_ <= pos) & (e_ >= pos + l) & (e_ > s_)).any(dim=-1)  # some range holds the whole needle window
+    later = slice(pos + ls, S)                                        # rows whose block pos//ls is complete
+    assert bool(covers[:, later].all()), f"{int((~covers[:, later]).sum())} later rows missed the needle block"
+    assert not bool(((e_ > pos) & (t < pos)).any()), "a row before the needle reached it"
+    rows = torch.tensor([pos + ls, pos + 4096, 50000, S - 1], device="cuda")
+    out = ops.sel_attention_blockmajor(Qb, Kb, Vb, cfg, ranges)      # the kernel nsa_prefill_fwd uses at this length
+    got = out[0, rows].float()                                       # [4,G,h,D]
+    cos = torch.nn.functional.cosine_similarity(got, v_star[0][None, :, None, :].expand_as(got), dim=-1)
+    assert float(cos.min()) > 0.999, float(cos.min())
