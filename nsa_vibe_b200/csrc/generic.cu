@@ -564,7 +564,15 @@ combine_fast_kernel(nsa_dims_t dm, const T* __restrict__ Q, nsa_gate_params_t gp
       float l0 = 0.f, l1 = 0.f, l2 = 0.f;
       for (int u = lane; u < H; u += 32) {
         float a = b1[u];
-        for (int k = 0; k < Dk; ++k) a = fmaf(w1t[k * H + u], qgp[k], a);
+        int k = 0;
+        for (; k + 4 <= Dk; k += 4) {  // one 16-byte broadcast read serves four products (same summation order as the scalar loop)
+          const float4 qv = *reinterpret_cast<const float4*>(qgp + k);
+          a = fmaf(w1t[k * H + u], qv.x, a);
+          a = fmaf(w1t[(k + 1) * H + u], qv.y, a);
+          a = fmaf(w1t[(k + 2) * H + u], qv.z, a);
+          a = fmaf(w1t[(k + 3) * H + u], qv.w, a);
+        }
+        for (; k < Dk; ++k) a = fmaf(w1t[k * H + u], qgp[k], a);
         const float x = a / (1.0f + expf(-a));  // silu
         l0 = fmaf(w2[u], x, l0);
         l1 = fmaf(w2[H + u], x, l1);
@@ -629,7 +637,7 @@ int launch_combine(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t&
   const int n_rows = dm.B * dm.S * dm.G;
   if (n_rows == 0) return NSA_OK;
   const int H = dm.gate_mode == NSA_GATE_MLP ? dm.gate_hidden : 0;
-  if (dm.dtype != NSA_F32 && (dm.h * dm.Dv) % 8 == 0 && dm.Dk % 2 == 0 &&
+  if (dm.dtype != NSA_F32 && (dm.h * dm.Dv) % 8 == 0 && dm.Dk % 4 == 0 &&
       ((size_t)dm.Dk * H + 4 * H + 4 + (size_t)kCfWarps * dm.Dk) * sizeof(float) <= 48 * 1024 &&
       ((uintptr_t)O_br & 15) == 0 && ((uintptr_t)O & 15) == 0 && ((uintptr_t)Q & 3) == 0) {
     if (dm.dtype == NSA_BF16) return launch_combine_fast<__nv_bfloat16>(dm, Q, gp, O_br, O, gates, stream);
