@@ -72,11 +72,13 @@ def allreduce_grads_bf16(params, *, compress_dtype: torch.dtype = torch.bfloat16
     grads = [p.grad for p in ps]
     flat = torch.cat([g.reshape(-1) for g in grads])
     if world > 1:
-        flat = flat.div_(world).to(compress_dtype)
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        off = 0
+        packed = torch.empty(flat.shape, dtype=compress_dtype, device=flat.device)
+        torch.div(flat, world, out=packed)  # divide, then compress: the hook's order (one pass)
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+        views, off = [], 0
         for g in grads:
             n = g.numel()
-            g.copy_(flat[off:off + n].view_as(g))
+            views.append(packed[off:off + n].view_as(g))
             off += n
+        torch._foreach_copy_(grads, views)  # decompress into p.grad: one multi-tensor kernel instead of one copy per parameter
     return int(flat.numel()) * 2
