@@ -1,5 +1,6 @@
-"""phi = avg-pool(kernel l, stride d) over RoPE(K) and raw V (nsa/core/compress_pool.py:9-38).
-Producer of K_cmp/V_cmp; kept in torch (SURVEY 8f-1 lists fusing it as 'next')."""
+"""Torch restatement of phi = avg-pool(kernel l, stride d) over RoPE(K) and raw V (nsa/core/compress_pool.py:9-38).  The product path
+pools inside `ops.phi_avgpool` (one CUDA pass per tensor, forward and backward); this function is the comparator that kernel is tested
+against and keeps the reference's public name."""
 from __future__ import annotations
 
 from typing import Optional, Tuple

@@ -1,26 +1,31 @@
-"""Rotary embedding as the reference applies it (nsa/core/rope.py:16-51): interleaved pairs, fp32 angles,
-sin/cos cast to the input dtype.  Producer of the hot path's inputs, kept in torch."""
+"""Torch restatement of the rotary embedding the reference applies (nsa/core/rope.py:16-51: interleaved pairs, angles in fp32,
+sin / cos rounded to the input dtype, every product rounded to that dtype).  The product path rotates inside the CUDA producers
+(`ops.project_split`, `ops.rope_shape`, `ops.phi_avgpool`); this module is the comparator those kernels are tested against and
+keeps the reference's two public names."""
 from __future__ import annotations
 
 import torch
 
 
 def build_inv_freq(dim: int, base: float = 10000.0, device=None) -> torch.Tensor:
-    assert dim % 2 == 0, "RoPE requires even dimension"
-    idx = torch.arange(dim // 2, device=device, dtype=torch.float32)
-    return base ** (-2 * idx / dim)
+    """base^(-2i/dim) for the dim/2 rotation pairs, fp32."""
+    if dim % 2:
+        raise AssertionError("RoPE requires even dimension")
+    pair = torch.arange(dim // 2, dtype=torch.float32, device=device)
+    return base ** (-2 * pair / dim)
 
 
 def apply_rope(x: torch.Tensor, pos: torch.Tensor, base: float = 10000.0, *, scale: float = 1.0) -> torch.Tensor:
-    D = x.shape[-1]
-    assert D % 2 == 0, "RoPE requires even dimension"
-    inv_freq = build_inv_freq(D, base=base, device=x.device)
-    while pos.dim() < x.dim() - 1:
-        pos = pos.unsqueeze(0)
-    if scale <= 0:
-        scale = 1.0
-    ang = (pos.to(torch.float32) / float(scale)).unsqueeze(-1) * inv_freq
-    sin, cos = torch.sin(ang).to(x.dtype), torch.cos(ang).to(x.dtype)
-    x2 = x.reshape(*x.shape[:-1], D // 2, 2)
-    x0, x1 = x2[..., 0], x2[..., 1]
-    return torch.stack((x0 * cos - x1 * sin, x0 * sin + x1 * cos), dim=-1).reshape(x.shape)
+    """x [..., S, D] (D even), pos [S] or [..., S] -> x rotated pair-wise: (x_2i, x_2i+1) by the angle (pos / scale) * base^(-2i/D)."""
+    width = x.shape[-1]
+    freq = build_inv_freq(width, base=base, device=x.device)
+    div = float(scale) if scale > 0 else 1.0
+    p = pos.to(torch.float32)
+    p = p.reshape((1,) * (x.dim() - 1 - p.dim()) + tuple(p.shape)) if p.dim() < x.dim() - 1 else p
+    theta = (p / div)[..., None] * freq                      # fp32 [..., S, D/2]
+    s, c = theta.sin().to(x.dtype), theta.cos().to(x.dtype)
+    even, odd = x[..., 0::2], x[..., 1::2]
+    out = torch.empty_like(x)
+    out[..., 0::2] = even * c - odd * s
+    out[..., 1::2] = even * s + odd * c
+    return out
