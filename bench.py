@@ -270,6 +270,7 @@ def main():
     c = M7C
     cfg = ops.NSAConfig(l=c["l"], d=c["d"], l_sel=c["l_sel"], n_sel=c["n_sel"], w=c["w"])
     S, B = args.S, args.B
+    args.warmup = max(int(args.warmup), 3)  # timing rule: at least three untimed steps; the JSON reports the count actually run
     inp, gate = make_inputs(B, S, dev, seed=1234 + rank)
 
     def step(t):
