@@ -276,7 +276,7 @@ def main():
     def step(t):
         ranges = ops.score_select(t["Q"], t["K_cmp"], cfg, mode=0)
         O, _, _ = ops.prefill_core(t["Q"], t["K_sel"], t["V_sel"], t["K_win"], t["V_win"], t["K_cmp"], t["V_cmp"], gate, cfg,
-                                   sel_mode=0, ranges=ranges)
+                                   sel_mode=0, ranges=ranges, ranges_trusted=True)
         return O
 
     def barrier():
@@ -303,7 +303,7 @@ def main():
             ranges = ops.score_select(inp["Q"], inp["K_cmp"], cfg, mode=0)
             ev[i][1].record()
             ops.prefill_core(inp["Q"], inp["K_sel"], inp["V_sel"], inp["K_win"], inp["V_win"], inp["K_cmp"], inp["V_cmp"], gate,
-                             cfg, sel_mode=0, ranges=ranges)
+                             cfg, sel_mode=0, ranges=ranges, ranges_trusted=True)
             ev[i][2].record()
         e_end.record()
         barrier()
@@ -431,7 +431,7 @@ def main():
         def step_causal():
             rg2 = ops.score_select(inp["Q"], inp["K_cmp"], cfg_c, mode=1)
             ops.prefill_core(inp["Q"], inp["K_sel"], inp["V_sel"], inp["K_win"], inp["V_win"], inp["K_cmp"], inp["V_cmp"], gate, cfg_c,
-                             sel_mode=1, ranges=rg2)
+                             sel_mode=1, ranges=rg2, ranges_trusted=True)
         with torch.no_grad():
             ms_alt = t_of(step_causal, n=5)
         alt = {"selection": "decode rule (select_topn_ranges), causal p_cmp normaliser: what NSA_PREFILL_TILE / stepwise decode computes",

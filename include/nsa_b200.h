@@ -87,8 +87,9 @@ int nsa_select_ranges_decode(const float* p_grp, int B, int G, int S_sel, int l_
 /* ---- (1) scoring: Q, K_cmp -> p_grp  (compute_pcmp_all + map_pcmp_to_pslc_batched + sum over h;
  * selection_scorer.py:42-61, :89-116, nsa_attention.py:1091).  p_grp [B,S,G,S_sel] fp32. */
 int nsa_score(const nsa_dims_t* dm, const void* Q, const void* K_cmp, int S_sel, float* p_grp, void* stream);
-/* Fused scoring + selection: nothing but the ranges leaves the SM.  mode 0 = prefill rule, 1 = decode rule.
- * workspace: nsa_workspace_bytes(dm, NSA_WS_SCORE_SELECT). */
+/* Fused scoring + selection.  mode 0 = prefill rule, 1 = decode rule.  The SIMT scorer selects inside the scoring kernel
+ * (nothing but the ranges leaves the SM); the tcgen05 scorer stages p_grp [B,S,G,S_sel] fp32 in the workspace for the
+ * selection kernel that follows it.  workspace: nsa_workspace_bytes(dm, NSA_WS_SCORE_SELECT). */
 int nsa_score_select(const nsa_dims_t* dm, const void* Q, const void* K_cmp, int S_sel, int S_total, int mode,
                      int32_t* ranges, void* workspace, void* stream);
 
@@ -99,6 +100,14 @@ int nsa_score_select(const nsa_dims_t* dm, const void* Q, const void* K_cmp, int
  * every allowed key.  O_b [B,S,G,h,Dv] in dm->dtype, lse_b [B,S,G,h] fp32 (either may be NULL). */
 int nsa_branch_attn_fwd(const nsa_dims_t* dm, int branch, const void* Q, const void* K, const void* V,
                         const int32_t* ranges, void* O_b, float* lse_b, void* stream);
+/* INVARIANT of the tcgen05 selected-branch kernels (16-bit, Dk = Dv = 64; forward, block-major forward and backward):
+ * a row's ranges, each clamped to [0, S_sel_kv) and cut into 64-key blocks, give at most NSA_MAX_SEL_BLOCKS blocks.
+ * Ranges produced by nsa_select_ranges_* / nsa_score_select always do (n_sel * l_sel <= 1024 keys in whole l_sel blocks).
+ * For ranges from anywhere else (many short or unaligned ranges, > 1024 keys per row) call nsa_ranges_max_blocks first and
+ * pass dims.impl = NSA_IMPL_SIMT when it reports more: the SIMT kernels take any ranges, like the reference's
+ * grouped_selection_attention (attention_kernels.py:181-226).  max_blocks: ONE int32 in device memory. */
+#define NSA_MAX_SEL_BLOCKS 16
+int nsa_ranges_max_blocks(const int32_t* ranges, int64_t n_rows, int K, int S_kv, int32_t* max_blocks, void* stream);
 /* Selected branch, KV-block-major: every 64-key block is read once per run of the queries that selected it and the
  * per-(query, block) partials are merged (same result as nsa_branch_attn_fwd(branch = 1); the form that scales to long
  * prefill, where the query-major gather is bound by L2 bandwidth).  workspace: nsa_workspace_bytes(dm, NSA_WS_SEL_BLOCKMAJOR).

@@ -16,6 +16,7 @@ NORM_FULL_ROW, NORM_CAUSAL = 0, 1
 GATE_MLP, GATE_UNIFORM, GATE_CMP, GATE_SEL, GATE_WIN = 0, 1, 2, 3, 4
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
 WS_SCORE_SELECT, WS_DECODE, WS_PREFILL, WS_SEL_BLOCKMAJOR, WS_BWD = 0, 1, 2, 3, 4
+MAX_SEL_BLOCKS = 16  # NSA_MAX_SEL_BLOCKS
 
 
 class Dims(C.Structure):
@@ -78,6 +79,7 @@ SIGNATURES = {
     "nsa_rmsnorm_bwd": (_I, [_P] * 8 + [_I, _I, _I, _I, _I, _P]),
     "nsa_rmsnorm_partials": (_I, [_I]),
     "nsa_stats": (_I, [_P, _I64, _P, _I64, _I, _P, _P, _P]),
+    "nsa_ranges_max_blocks": (_I, [_P, _I64, _I, _I, _P, _P]),
     "nsa_workspace_bytes": (_I64, [_DP, _I]),
 }
 

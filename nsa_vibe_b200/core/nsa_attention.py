@@ -193,7 +193,12 @@ class NSAAttention(nn.Module):
         """The seven projections as ONE GEMM over the stacked weights (cuBLAS through F.linear; the state dict keeps the seven
         nn.Linear parameters), followed by ONE kernel that applies RoPE and writes Q and the six cache-layout tensors
         (ops.project_split) -- the reference's per-tensor rope + view + permute + contiguous chains (nsa_attention.py:998-1016)."""
-        y = F.linear(x, torch.cat(self._proj_weights(), dim=0))
+        ws = self._proj_weights()
+        if torch.is_grad_enabled() and any(w.requires_grad for w in ws):
+            w_all = torch.cat(ws, dim=0)          # autograd splits the gradient back onto the seven parameters
+        else:
+            w_all = self._decode_weights()        # inference: the stacked matrix is cached (rebuilt when a weight changes)
+        y = F.linear(x, w_all)
         return ops.project_split(y, H=self.n_heads, G=self.n_kv_groups, Dk=self.d_k, Dv=self.d_v, t0=t0, scale=self.rope_scale)
 
     def _nvtx(self, name: Optional[str]):
@@ -227,20 +232,32 @@ class NSAAttention(nn.Module):
         sel_mode = 0 if (self._env_cache["prefill_batched"] and not via_decode) else 1
         cfg = self._cfg(causal_norm=via_decode)
         gate = self.gate.params() if cfg.gate_mode == ops.GATE_MLP else None
-        self._nvtx("branch_attn+gate")
-        pre_ranges = None
+        # the reference's three ranges (nsa_attention.py:1070, :1077, :1103) cover ONE fused launch pair here (scoring with the
+        # Eq.9 / Eq.10 folds, then top-n + range merging), so they are pushed nested around it
+        for name in ("pcmp_all", "map_pcmp_to_pslc", "topk+ranges"):
+            self._nvtx(name)
         if self._env_cache["pcmp_mixed"] and Q.dtype == torch.float32:
             # NSA_P_CMP_MIXED (selection_scorer.py:46-56): the scores that drive the selection come from bf16 operands; the three
             # branches still attend in fp32 over the ranges chosen that way
             pre_ranges = ops.score_select(Q.detach().bfloat16(), K_cmp.detach().bfloat16(), cfg, mode=sel_mode, t0=t0)
+        else:
+            pre_ranges = ops.score_select(Q.detach(), K_cmp.detach(), cfg, mode=sel_mode, t0=t0)
+        for _ in range(3):
+            self._nvtx(None)
+        self._nvtx("branch_attn+gate")
         if t0 == 0:
             O, ranges, gates = ops.prefill_core(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, gate, cfg, sel_mode=sel_mode,
-                                                t0=0, stopgrad_gates=self._env_cache["stopgrad_gates"], ranges=pre_ranges)
+                                                t0=0, stopgrad_gates=self._env_cache["stopgrad_gates"], ranges=pre_ranges,
+                                                ranges_trusted=True)
         else:  # chunked prefill continues on the cache slabs (inference only)
+            if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+                raise RuntimeError("chunked prefill (kv already holds tokens) attends over the detached cache slabs: gradients "
+                                   "would reach Q and the gate only.  Run it under torch.no_grad(), or prefill in one call.")
             n = t0 + S
             O, ranges, gates = ops.prefill_core(
                 Q, kv.slab("K_sel"), kv.slab("V_sel"), kv.slab("K_win"), kv.slab("V_win"), K_cmp, V_cmp, gate, cfg,
-                sel_mode=sel_mode, t0=t0, S_sel_kv=n, S_win_kv=kv.length("K_win"), win_off=n - kv.length("K_win"), ranges=pre_ranges)
+                sel_mode=sel_mode, t0=t0, S_sel_kv=n, S_win_kv=kv.length("K_win"), win_off=n - kv.length("K_win"), ranges=pre_ranges,
+                stopgrad_gates=self._env_cache["stopgrad_gates"], ranges_trusted=True)
         self._nvtx(None)
         if self._env_cache["strict_asserts"] and ranges.numel() > 0:
             tpos = torch.arange(t0, t0 + S, device=x.device).view(1, S, 1, 1)

@@ -326,6 +326,10 @@ int nsa_stats(const float* gates, int64_t n_gate_rows, const int32_t* ranges, in
   return launch_stats(gates, (long long)n_gate_rows, ranges, (long long)n_range_rows, K, row_len, out, (cudaStream_t)stream);
 }
 
+int nsa_ranges_max_blocks(const int32_t* ranges, int64_t n_rows, int K, int S_kv, int32_t* max_blocks, void* stream) {
+  return launch_ranges_max_blocks(ranges, (long long)n_rows, K, S_kv, max_blocks, (cudaStream_t)stream);
+}
+
 int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which) {
   if (!dm) return 0;
   switch (which) {

@@ -422,7 +422,10 @@ int launch_rmsnorm_bwd(const void* dy, const void* s, const void* w, const float
   NSA_REQUIRE(smem <= 200 * 1024, "rmsnorm_bwd: dim=%d too wide for the column-sum staging", dim);
   const int grid = norm_grid(rows, sm_count());
   if (rows > 0) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(rmsnorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(rmsnorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { set_error("rmsnorm_bwd: smem attr: %s", cudaGetErrorString(e)); return NSA_ERR_CUDA; }
+    }
     float* part = dw ? dw_partial : nullptr;
     const int nv = ceil_div(dim / 4, 32);
     const size_t smem_reg = smem + (size_t)dim * sizeof(float);

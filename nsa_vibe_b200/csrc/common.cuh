@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
+#include <atomic>
 
 #include "../../include/nsa_b200.h"
 
@@ -26,6 +27,25 @@ int check_launch(const char* what);
   } while (0)
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// cudaFuncSetAttribute is per device (context): `done` remembers, one bit per device ordinal, where the opt-in has been
+// made, so a process that drives several GPUs (or several host threads) gets it on each.  max_carveout also asks for the
+// largest shared-memory carve-out, which a kernel needs when TWO of its CTAs are meant to share an SM: the driver otherwise
+// sizes the carve-out for one (ncu: launch__shared_mem_config_size 135 KB, launch__occupancy_limit_shared_mem 1).
+template <typename Kern>
+inline int ensure_smem_attr(Kern kern, int bytes, std::atomic<unsigned long long>& done, const char* who, bool max_carveout = false) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { set_error("%s: cudaGetDevice: %s", who, cudaGetErrorString(e)); return NSA_ERR_CUDA; }
+  const unsigned long long bit = dev >= 0 && dev < 64 ? 1ull << dev : 0ull;
+  if (bit && (done.load(std::memory_order_acquire) & bit)) return NSA_OK;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && max_carveout)
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) { set_error("%s: shared-memory attribute: %s", who, cudaGetErrorString(e)); return NSA_ERR_CUDA; }
+  if (bit) done.fetch_or(bit, std::memory_order_release);
+  return NSA_OK;
+}
 
 // num_cmp(t): compressed tokens visible at absolute position t (nsa/core/packing.py:15-23)
 __host__ __device__ inline int num_cmp_at(int t, int l, int d, int S_cmp) {

@@ -50,6 +50,7 @@ int launch_decode_produce(const nsa_decode_produce_t& a, cudaStream_t stream);
 // stats.cu
 int launch_stats(const float* gates, long long n_gate_rows, const int32_t* ranges, long long n_range_rows, int K, int32_t* row_len,
                  nsa_stats_t* out, cudaStream_t stream);
+int launch_ranges_max_blocks(const int32_t* ranges, long long n_rows, int K, int S_kv, int32_t* out, cudaStream_t stream);
 // block_ops.cu
 int launch_rmsnorm_fwd(const void* x, const void* r, const void* w, void* s_out, void* y, float* rstd, int rows, int dim, float eps,
                        int x_dtype, int r_dtype, int w_dtype, int y_dtype, cudaStream_t stream);

@@ -111,6 +111,30 @@ sel_stats_count_kernel(const int32_t* __restrict__ L, long long n_rows, nsa_stat
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(reinterpret_cast<unsigned long long*>(&out->rows_at_max), (unsigned long long)c);
 }
 
+// blocks[0] = max over rows of the number of 64-key blocks the tcgen05 selected-branch kernels cut the row's ranges into
+// (each range clamped to [0, S_kv) and cut separately, as tc_gather.cu / tc_sel2.cu do)
+__global__ void __launch_bounds__(256)
+ranges_max_blocks_kernel(const int32_t* __restrict__ ranges, long long n_rows, int K, int S_kv, int32_t* __restrict__ out) {
+  int mx = 0;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x) {
+    const int2* rr = reinterpret_cast<const int2*>(ranges + r * K * 2);
+    int n = 0;
+    for (int k = 0; k < K; ++k) {
+      int2 v = rr[k];
+      if (v.x < 0) v.x = 0;
+      if (v.y > S_kv) v.y = S_kv;
+      if (v.y > v.x) n += (v.y - v.x + 63) >> 6;
+    }
+    mx = n > mx ? n : mx;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int m2 = __shfl_xor_sync(0xffffffffu, mx, o);
+    mx = m2 > mx ? m2 : mx;
+  }
+  if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(out, mx);
+}
+
 int grid_for(long long n) {
   long long g = (n + 255) / 256;
   return (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
@@ -136,6 +160,15 @@ int launch_stats(const float* gates, long long n_gate_rows, const int32_t* range
     if (int rc = check_launch("sel_stats_count_kernel")) return rc;
   }
   return NSA_OK;
+}
+
+int launch_ranges_max_blocks(const int32_t* ranges, long long n_rows, int K, int S_kv, int32_t* out, cudaStream_t stream) {
+  NSA_REQUIRE(out && (ranges || n_rows == 0) && n_rows >= 0 && K >= 0, "ranges_max_blocks: bad arguments");
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(int32_t), stream);
+  if (e != cudaSuccess) { set_error("ranges_max_blocks: cudaMemsetAsync: %s", cudaGetErrorString(e)); return NSA_ERR_CUDA; }
+  if (n_rows == 0 || K == 0) return NSA_OK;
+  ranges_max_blocks_kernel<<<grid_for(n_rows), 256, 0, stream>>>(ranges, n_rows, K, S_kv, out);
+  return check_launch("ranges_max_blocks_kernel");
 }
 
 }  // namespace nsa

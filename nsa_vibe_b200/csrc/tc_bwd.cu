@@ -650,12 +650,8 @@ static int launch_bwd_branch(const nsa_dims_t& dm, const BwdArgs& a, const float
     NSA_REQUIRE(n_kt <= 65535 && slabs <= 65535, "bwd(tc): grid too large (key tiles %d, slabs %d)", n_kt, slabs);
   }
   auto kern = bwd_tc_kernel<T, BR>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwSmem::total);
-    if (e != cudaSuccess) { set_error("bwd tc: smem attr: %s", cudaGetErrorString(e)); return NSA_ERR_CUDA; }
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int rc = ensure_smem_attr(kern, BwSmem::total, attr_done, "bwd tc")) return rc;
 #ifdef NSA_BWD_DBG
   static long long* dbg_buf = nullptr;
   if (!dbg_buf) cudaMalloc(&dbg_buf, 8008 * sizeof(long long));

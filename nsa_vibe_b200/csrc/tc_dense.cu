@@ -416,12 +416,8 @@ static int launch_dense_t(const nsa_dims_t& dm, int branch, const void* Q, const
   if (int rc = make_tmap_rows(&tmK, K, dm.dtype, 64, rows, 64, cap * 64, dm.B * dm.G, NK)) return rc;
   if (int rc = make_tmap_rows(&tmV, V, dm.dtype, 64, rows, 64, cap * 64, dm.B * dm.G, NK)) return rc;
   auto kern = dense_attn_tc_kernel<T, MT, NK>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::total);
-    if (e != cudaSuccess) { set_error("dense tc: smem attr: %s", cudaGetErrorString(e)); return NSA_ERR_CUDA; }
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int rc = ensure_smem_attr(kern, SM::total, attr_done, "dense tc")) return rc;
   const int grid = dm.B * dm.G * ceil_div(dm.S, MT * TOK);
   static const bool dbg_on = getenv("NSA_B200_DENSE_DBG") != nullptr;
   static long long* dbg_buf = nullptr;

@@ -82,6 +82,7 @@ struct GatherArgs {
   long long* dbg;       // debug timeline of CTA 0 (NSA_B200_GATHER_DBG=1), else NULL
 };
 
+#ifdef NSA_GATHER_DBG  // compile-time (NSA_B200_NVCC_FLAGS=-DNSA_GATHER_DBG): timeline of CTA 0 for tools/dbg_gather.py
 #define GDBG(tag, it)                                                                 \
   do {                                                                                \
     if (a.dbg && blockIdx.x == 0) {                                                   \
@@ -89,6 +90,9 @@ struct GatherArgs {
       if (i_ < 4000) { a.dbg[1 + 2 * i_] = ((long long)(tag) << 32) | (unsigned)(it); a.dbg[2 + 2 * i_] = clock64(); } \
     }                                                                                 \
   } while (0)
+#else
+#define GDBG(tag, it) do { } while (0)
+#endif
 
 __device__ __forceinline__ float g_ex2(float x) {
   float y;
@@ -644,12 +648,9 @@ static int launch_gather_t(const nsa_dims_t& dm, const GatherPtrs& kv, GatherArg
   long long grid_ll = tokens >= 16LL * 296 ? (tokens + 15) / 16 : (tokens < 296 ? tokens : 296);
   const int grid = (int)grid_ll;
   auto kern = gather_attn_tc_kernel<T>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GSmem::total);
-    if (e != cudaSuccess) { set_error("gather tc: smem attr: %s", cudaGetErrorString(e)); return NSA_ERR_CUDA; }
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int rc = ensure_smem_attr(kern, GSmem::total, attr_done, "gather tc", /*two CTAs per SM*/ true)) return rc;
+#ifdef NSA_GATHER_DBG
   static const bool dbg_on = getenv("NSA_B200_GATHER_DBG") != nullptr;
   static long long* dbg_buf = nullptr;
   if (dbg_on) {
@@ -657,7 +658,9 @@ static int launch_gather_t(const nsa_dims_t& dm, const GatherPtrs& kv, GatherArg
     cudaMemsetAsync(dbg_buf, 0, 8008 * sizeof(long long), stream);
     a.dbg = dbg_buf;
   }
+#endif
   kern<<<grid, 192, GSmem::total, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], dm, a);
+#ifdef NSA_GATHER_DBG
   if (dbg_on) {  // debug only: dump the timeline of CTA 0 (tag, item, clock)
     static int dumps = 0;
     cudaStreamSynchronize(stream);
@@ -669,6 +672,7 @@ static int launch_gather_t(const nsa_dims_t& dm, const GatherPtrs& kv, GatherArg
         fprintf(stderr, "GDBG %lld %lld %lld\n", host[1 + 2 * i] >> 32, host[1 + 2 * i] & 0xffffffff, host[2 + 2 * i]);
     }
   }
+#endif
   return check_launch("gather_attn_tc_kernel");
 }
 

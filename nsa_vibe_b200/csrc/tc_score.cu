@@ -319,12 +319,8 @@ static int launch_score_t(const nsa_dims_t& dm, const void* Q, const void* Kc, i
   if (int rc = make_tmap_q_heads(&tmQ, Q, dm.dtype, 64, dm.h, dm.G, (long long)dm.B * dm.S, TOK)) return rc;
   if (int rc = make_tmap_rows(&tmK, Kc, dm.dtype, 64, dm.S_cmp, 64, (long long)dm.cap_cmp * 64, dm.B * dm.G, 128)) return rc;
   auto kern = score_tc_kernel<T, MT, 4>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ScSmem<MT>::total);
-    if (e != cudaSuccess) { set_error("score tc: smem attr: %s", cudaGetErrorString(e)); return NSA_ERR_CUDA; }
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int rc = ensure_smem_attr(kern, ScSmem<MT>::total, attr_done, "score tc")) return rc;
   const int grid = dm.B * dm.G * ceil_div(dm.S, MT * TOK);
   kern<<<grid, 32 * (4 * MT + 2), ScSmem<MT>::total, stream>>>(tmQ, tmK, dm, S_sel, p_grp, TOK, sel_only ? 1 : 0);
   return check_launch("score_tc_kernel");

@@ -636,16 +636,14 @@ static int s2_build(const nsa_dims_t& dm, const int32_t* ranges, char* ws, const
   int* pair_of = with_pair_of ? reinterpret_cast<int*>(ws + w.pair_of) : nullptr;
   const int n_rows = dm.B * dm.S * dm.G;
   const int nlists = dm.B * dm.G * gm.NB;
-  cudaMemsetAsync(counts, 0, (size_t)nlists * 4, stream);
-  cudaMemsetAsync(tok, 0xff, (size_t)w.max_pairs * 4, stream);  // -1 = padding pair
+  cudaError_t me = cudaMemsetAsync(counts, 0, (size_t)nlists * 4, stream);
+  if (me == cudaSuccess) me = cudaMemsetAsync(tok, 0xff, (size_t)w.max_pairs * 4, stream);  // -1 = padding pair
+  if (me != cudaSuccess) { set_error("sel2 index: cudaMemsetAsync: %s", cudaGetErrorString(me)); return NSA_ERR_CUDA; }
   const int idx_blocks = ceil_div(n_rows, kS2IdxThreads);
   const size_t hist_bytes = (size_t)2 * gm.G * gm.NB * 4;
-  static bool idx_attr = false;
-  if (!idx_attr) {
-    cudaFuncSetAttribute(sel2_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(sel2_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    idx_attr = true;
-  }
+  static std::atomic<unsigned long long> cnt_done{0}, fill_done{0};
+  if (int rc = ensure_smem_attr(sel2_count_kernel, 200 * 1024, cnt_done, "sel2 count")) return rc;
+  if (int rc = ensure_smem_attr(sel2_fill_kernel, 200 * 1024, fill_done, "sel2 fill")) return rc;
   sel2_count_kernel<<<idx_blocks, kS2IdxThreads, hist_bytes, stream>>>(gm, ranges, counts);
   if (int rc = check_launch("sel2_count_kernel")) return rc;
   sel2_scan_kernel<<<1, 1024, 0, stream>>>(gm, counts, offs, cursors, runs, n_runs);
@@ -690,12 +688,9 @@ static int launch_sel2_t(const nsa_dims_t& dm, const void* Q, const void* K, con
   if (int rc = make_tmap_rows(&tmK, K, dm.dtype, 64, dm.S_sel_kv, 64, (long long)dm.cap_sel * 64, slabs, 64)) return rc;
   if (int rc = make_tmap_rows(&tmV, V, dm.dtype, 64, dm.S_sel_kv, 64, (long long)dm.cap_sel * 64, slabs, 64)) return rc;
   auto kern = sel2_attn_kernel<T>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S2Smem::total);
-    if (e != cudaSuccess) { set_error("sel2: smem attr: %s", cudaGetErrorString(e)); return NSA_ERR_CUDA; }
-    attr_set = true;
-  }
+  // two CTAs per SM (S2Smem::total): needs the largest carve-out -- with the driver's default this kernel ran one CTA per SM
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int rc = ensure_smem_attr(kern, S2Smem::total, attr_done, "sel2", true)) return rc;
   long long* dbg_buf = nullptr;
 #ifdef NSA_SEL2_DBG
   static long long* dbg_static = nullptr;

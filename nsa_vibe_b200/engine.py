@@ -38,7 +38,7 @@ class PrefillEngine:
         """Scoring + selection + three-branch attention + gated combine for one resident batch."""
         ranges = ops.score_select(d["Q"], d["K_cmp"], self.cfg, mode=0)
         O, _, _ = ops.prefill_core(d["Q"], d["K_sel"], d["V_sel"], d["K_win"], d["V_win"], d["K_cmp"], d["V_cmp"], self.gate,
-                                   self.cfg, sel_mode=0, ranges=ranges)
+                                   self.cfg, sel_mode=0, ranges=ranges, ranges_trusted=True)
         return O
 
     @torch.no_grad()

@@ -86,7 +86,7 @@ def make_dims(Q: torch.Tensor, cfg: NSAConfig, *, t0: int = 0, K_sel=None, K_win
     dm.n_ranges = int(n_ranges)
     dm.dtype = _DTYPES[Q.dtype]
     dm.gate_mode, dm.gate_hidden, dm.norm_mode = int(cfg.gate_mode), int(gate_hidden), int(cfg.norm_mode)
-    dm.impl = int(os.environ.get("NSA_B200_IMPL", cfg.impl))
+    dm.impl = int(cfg.impl) if int(cfg.impl) == IMPL_SIMT else int(os.environ.get("NSA_B200_IMPL", cfg.impl))
     dm.gate_tau = float(cfg.gate_tau)
     dm.scale = 1.0 / math.sqrt(Dk)
     return dm
@@ -184,6 +184,33 @@ def score_select(Q: torch.Tensor, K_cmp: torch.Tensor, cfg: NSAConfig, *, mode: 
 BR_CMP, BR_SEL, BR_WIN = 0, 1, 2
 
 
+def ranges_max_blocks(ranges: torch.Tensor, S_kv: int) -> int:
+    """Largest number of 64-key blocks any row of `ranges` [...,K,2] is cut into (nsa_ranges_max_blocks).  Synchronises:
+    one int32 comes back to the host."""
+    _require_cuda(ranges)
+    K = int(ranges.shape[-2])
+    r = _c(ranges.detach().to(torch.int32))
+    n_rows = r.numel() // max(2 * K, 1)
+    out = torch.empty(1, dtype=torch.int32, device=r.device)
+    _call("nsa_ranges_max_blocks", _ptr(r), n_rows, K, int(S_kv), _ptr(out), _stream())
+    return int(out.item())
+
+
+def _cfg_for_ranges(cfg: "NSAConfig", ranges: Optional[torch.Tensor], S_kv: int, trusted: bool) -> "NSAConfig":
+    """Caller-supplied ranges may break the invariant the tcgen05 selected-branch kernels rely on (<= 16 blocks of 64 keys per
+    row, include/nsa_b200.h): such calls run on the SIMT kernels, which take any ranges like the reference's
+    grouped_selection_attention (attention_kernels.py:181-226).  Ranges the library selected itself are `trusted`."""
+    if ranges is None or trusted or cfg.impl == IMPL_SIMT or ranges.numel() == 0:
+        return cfg
+    if ranges_max_blocks(ranges, S_kv) <= _lib.MAX_SEL_BLOCKS:
+        return cfg
+    if cfg.impl == IMPL_TC or int(os.environ.get("NSA_B200_IMPL", 0)) == IMPL_TC:
+        raise RuntimeError("ranges cut into more than 16 blocks of 64 keys per row: the tcgen05 selected-branch kernels cannot "
+                           "serve them (impl=TC was forced)")
+    from dataclasses import replace
+    return replace(cfg, impl=IMPL_SIMT)
+
+
 def _branch_dims(branch, Q, K, V, cfg, ranges, t0, win_off):
     kw = dict(t0=t0, V=V, n_ranges=0 if ranges is None else ranges.shape[3])
     if branch == BR_CMP:
@@ -227,17 +254,24 @@ class _BranchAttn(torch.autograd.Function):
 
 
 def branch_attention(branch: int, Q, K, V, cfg: NSAConfig, ranges=None, *, t0: int = 0, win_off: int = 0,
-                     return_lse: bool = False):
-    """True-softmax attention of one NSA branch (0 cmp, 1 sel, 2 win) with analytical backward."""
+                     return_lse: bool = False, ranges_trusted: bool = False):
+    """True-softmax attention of one NSA branch (0 cmp, 1 sel, 2 win) with analytical backward.  ranges_trusted: the ranges
+    come from this library's selection (<= 16 blocks of 64 keys per row); otherwise they are checked first (one host sync)."""
     _require_cuda(Q, K, V, ranges)
+    if branch == BR_SEL:
+        cfg = _cfg_for_ranges(cfg, ranges, K.shape[2], ranges_trusted)
     O, lse = _BranchAttn.apply(Q, K, V, ranges, branch, cfg, t0, win_off)
     return (O, lse) if return_lse else O
 
 
-def sel_attention_blockmajor(Q, K, V, cfg: NSAConfig, ranges, *, t0: int = 0, return_lse: bool = False):
+def sel_attention_blockmajor(Q, K, V, cfg: NSAConfig, ranges, *, t0: int = 0, return_lse: bool = False,
+                             ranges_trusted: bool = False):
     """Selected-branch attention, KV-block-major (forward only; nsa_sel_attn_fwd_blockmajor).  Same result as
     branch_attention(BR_SEL, ...)."""
     _require_cuda(Q, K, V, ranges)
+    if not ranges_trusted and ranges.numel() and ranges_max_blocks(ranges, K.shape[2]) > _lib.MAX_SEL_BLOCKS:
+        raise RuntimeError("sel_attention_blockmajor: a row's ranges cut into more than 16 blocks of 64 keys; use "
+                           "branch_attention(BR_SEL, ...), which serves such ranges on the SIMT kernel")
     Qc, Kc, Vc = _c(Q.detach()), _c(K.detach()), _c(V.detach())
     rg = _c(ranges.to(torch.int32))
     dm = _branch_dims(BR_SEL, Qc, Kc, Vc, cfg, rg, t0, 0)
@@ -345,10 +379,13 @@ class _PrefillCore(torch.autograd.Function):
 
 def prefill_core(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, gate, cfg: NSAConfig, *, sel_mode: int = 0, t0: int = 0,
                  stopgrad_gates: bool = False, ranges: Optional[torch.Tensor] = None, S_sel_kv: Optional[int] = None,
-                 S_win_kv: Optional[int] = None, S_cmp: Optional[int] = None, win_off: int = 0):
+                 S_win_kv: Optional[int] = None, S_cmp: Optional[int] = None, win_off: int = 0, ranges_trusted: bool = False):
     """NSA hot path for S query rows.  gate = (fc1_w, fc1_b, fc2_w, fc2_b) or None for forced/uniform gates.
-    Returns (O [B,S,G,h,Dv], ranges [B,S,G,K,2] int32, gates [B,S,G,3] fp32)."""
+    Returns (O [B,S,G,h,Dv], ranges [B,S,G,K,2] int32, gates [B,S,G,3] fp32).  ranges: use these instead of scoring and
+    selecting; unless ranges_trusted (they came from score_select / select_ranges_*), they are checked against the 16-block
+    invariant of the tcgen05 kernels first (one host sync) and served by the SIMT kernels when they break it."""
     _require_cuda(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp)
+    cfg = _cfg_for_ranges(cfg, ranges, S_sel_kv if S_sel_kv is not None else K_sel.shape[2], ranges_trusted)
     g = gate if gate is not None else (None, None, None, None)
     if gate is not None:
         # the kernels read fp32 gate weights; keep autograd attached to the caller's parameters

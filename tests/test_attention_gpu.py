@@ -227,3 +227,36 @@ def test_decode_core_vs_oracle():
                               win_off=0, S_cmp=S_cmp, ranges_out=rg)
         assert torch.equal(rg.cpu(), want["ranges"]), f"t={t}"
         assert torch.allclose(got[:, 0].cpu(), want["O"], atol=FP32_ATOL), (t, (got[:, 0].cpu() - want["O"]).abs().max())
+
+
+def test_many_short_ranges_beyond_16_blocks_are_served_not_truncated():
+    """the tcgen05 selected-branch kernels hold <= 16 blocks of 64 keys per row.  Caller-supplied ranges that break
+    that (here 20 disjoint 1-token ranges) must not be silently truncated: ops checks them (nsa_ranges_max_blocks) and runs
+    the SIMT kernel, forward and backward."""
+    ops = _ops()
+    B, S, G, h, D, S_kv, K = 1, 8, 2, 6, 64, 256, 20
+    gen = torch.Generator().manual_seed(5)
+    r16 = lambda *s: torch.randn(*s, generator=gen).bfloat16().float()
+    Q, Kk, V = r16(B, S, G, h, D), r16(B, G, S_kv, D), r16(B, G, S_kv, D)
+    ranges = torch.zeros(B, S, G, K, 2, dtype=torch.int32)
+    for s in range(S):
+        for g in range(G):
+            starts = torch.arange(K) * 11 + s + g          # disjoint, unaligned 1-token ranges
+            ranges[0, s, g, :, 0] = starts
+            ranges[0, s, g, :, 1] = starts + 1
+    cfg = ops.NSAConfig()
+    assert ops.ranges_max_blocks(ranges.cuda(), S_kv) == K
+    want = O.sel_attention(Q, Kk, V, ranges)
+    dev = [t.cuda().bfloat16().requires_grad_(True) for t in (Q, Kk, V)]
+    got = ops.branch_attention(ops.BR_SEL, *dev, cfg, ranges.cuda())
+    assert (got.float().cpu() - want).abs().max() <= BF16_MAXABS
+    dO = r16(*got.shape)
+    (got.float() * dO.cuda()).sum().backward()
+    cpu = [t.clone().requires_grad_(True) for t in (Q, Kk, V)]
+    (O.sel_attention(*cpu, ranges) * dO).sum().backward()
+    for a, b in zip(dev, cpu):
+        assert _rel(a.grad.float().cpu(), b.grad) <= 3e-2
+    # ranges within the invariant stay on the tensor-core path and agree too
+    assert ops.ranges_max_blocks(ranges[..., :16, :].contiguous().cuda(), S_kv) == 16
+    with pytest.raises(RuntimeError, match="more than 16 blocks"):
+        ops.sel_attention_blockmajor(dev[0].detach(), dev[1].detach(), dev[2].detach(), cfg, ranges.cuda())
