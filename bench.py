@@ -159,11 +159,88 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle port on a bounded sample of the same workload
+# CPU baselines.  (1) the UNMODIFIED reference package (oracle/_ref, copied by oracle/make_ref.py), timed the way BASELINE.md
+# section 3-C4 prescribes for S=64k; (2) the oracle port on a bounded sample of the batched-prefill workload, whose OUTPUT is
+# also the parity check of the GPU step at full size (parity_64k).
 # ------------------------------------------------------------------------------------------------------
-def cpu_prefill_sample(S, rows, seed=0, budget_s=25.0):
-    """Time the oracle's hot path for `rows` consecutive query rows in the middle of an S-token sequence (B=1) against
-    the full caches.  Returns (tok_per_s, cores, sample description)."""
+def reference_path():
+    p = os.path.join(ROOT, "oracle", "_ref")
+    return p if os.path.isdir(os.path.join(p, "nsa")) else None
+
+
+class ReferenceDecode:
+    """The reference's own NSAAttention (m7c dims, fp32, default environment = its stock CPU route) stepping single tokens on an
+    NSA_KV that already holds S_ctx tokens of random K/V -- what the reference's NSA_PREFILL_TILE route does per token
+    (nsa_attention.py:1507-1519), and the only way the reference can run a 64k context (its batched route needs O(S^2) masks
+    and a 12.9 GB p_cmp tensor).  Contexts are spread evenly over the sequence, so tokens / time estimates whole-sequence
+    prefill throughput."""
+
+    def __init__(self, S_max, seed=0):
+        ref = reference_path()
+        if ref not in sys.path:
+            sys.path.insert(0, ref)
+        from nsa.cache.kv_cache import NSA_KV
+        from nsa.core.block_index import build_block_meta
+        from nsa.core.nsa_attention import NSAAttention
+        c = M7C
+        self.NSA_KV, self.c, self.S_max = NSA_KV, c, S_max
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        torch.manual_seed(seed)
+        self.attn = NSAAttention(dim=768, n_heads=c["H"], n_kv_groups=c["G"], d_k=c["Dk"], d_v=c["Dv"], l=c["l"], d=c["d"],
+                                 l_sel=c["l_sel"], n_sel=c["n_sel"], w=c["w"])
+        self.meta = build_block_meta(S_max + c["l_sel"], c["l"], c["d"], c["l_sel"], n_sel=c["n_sel"], w=c["w"])
+        g = torch.Generator().manual_seed(seed)
+        r = lambda n, D: torch.randn(1, c["G"], n, D, generator=g)
+        self.K, self.V = r(S_max, c["Dk"]), r(S_max, c["Dv"])
+        self.Kc, self.Vc = r((S_max - c["l"]) // c["d"] + 1, c["Dk"]), r((S_max - c["l"]) // c["d"] + 1, c["Dv"])
+        self.g = g
+
+    def kv(self, S):
+        c = self.c
+        nc = 0 if S < c["l"] else (S - c["l"]) // c["d"] + 1
+        z = lambda: torch.zeros((0,), dtype=torch.int64)
+        cut = lambda t, n: t[:, :, :n].contiguous()
+        lo = max(0, S - c["w"])
+        return self.NSA_KV(K_sel=cut(self.K, S), V_sel=cut(self.V, S), K_win=self.K[:, :, lo:S].contiguous(),
+                           V_win=self.V[:, :, lo:S].contiguous(), K_cmp_raw_seq=cut(self.K, S), V_cmp_raw_seq=cut(self.V, S),
+                           K_cmp=cut(self.Kc, nc), V_cmp=cut(self.Vc, nc), win_ptr=torch.zeros((1, c["G"]), dtype=torch.int32),
+                           cmp_emit_next=torch.zeros((1, c["G"]), dtype=torch.int32), reads_pred=z(), reads_act_total=z(),
+                           reads_act_sel=z(), reads_act_cmp=z(), reads_act_win=z(), meta=self.meta)
+
+    def steps(self, S_ctx, reps):
+        """`reps` decode steps starting from a context of S_ctx tokens; returns seconds (cache construction not timed)."""
+        kv = self.kv(S_ctx)
+        xs = torch.randn(reps, 1, 1, 768, generator=self.g)
+        with torch.no_grad():
+            t = time.perf_counter()
+            for i in range(reps):
+                _, kv = self.attn(xs[i], kv, prefill=False)
+            return time.perf_counter() - t
+
+
+def reference_decode_sample(S, strata, reps, seed=0, rd=None):
+    """(tok/s, cores, sample text, ms per token at the last stratum): reps decode steps at each of `strata` contexts spread evenly
+    over an S-token sequence (the last one is S - reps: the 65,535-token cache of BASELINE.md section 3-C4)."""
+    rd = rd or ReferenceDecode(S, seed)
+    rd.steps(min(S - 4, 4096), 2)  # warm-up (first call pays one-off costs: 83 ms vs 35 ms measured)
+    tot_t, tot_n, last = 0.0, 0, 0.0
+    for i in range(strata):
+        ctx = min(S - reps, max(M7C["l"], int((i + 1) / strata * S) - reps))
+        dt = rd.steps(ctx, reps)
+        tot_t += dt
+        tot_n += reps
+        last = dt / reps
+    return (tot_n / tot_t, rd.cores,
+            f"UNMODIFIED reference (oracle/_ref), NSAAttention.forward(prefill=False), fp32, default env: {reps} single-token steps "
+            f"at each of {strata} contexts spread evenly up to {S - reps} cached tokens of one S={S} sequence (B=1, m7c dims; "
+            f"BASELINE.md section 3-C4)", last * 1e3)
+
+
+def cpu_prefill_sample(S, rows, seed=0, budget_s=25.0, tensors=None, gate=None):
+    """Time the oracle's hot path (batched-prefill semantics) for `rows` consecutive query rows in the middle of an S-token
+    sequence (B=1) against the full caches.  tensors: the GPU step's own inputs as fp32 CPU tensors (then the output is
+    returned for the parity check).  Returns (tok_per_s, cores, sample description, oracle output dict, t0)."""
     from oracle import nsa_oracle as O
     c = M7C
     cores = os.cpu_count() or 1
@@ -172,42 +249,170 @@ def cpu_prefill_sample(S, rows, seed=0, budget_s=25.0):
     S_cmp = O.num_cmp_blocks(S, c["l"], c["d"])
     bf = lambda *s: torch.randn(*s, generator=g).bfloat16().float()
     t0 = S // 2
-    Q = bf(1, rows, c["G"], c["h"], c["Dk"])
-    K_sel, V_sel, K_win, V_win = bf(1, c["G"], S, c["Dk"]), bf(1, c["G"], S, c["Dv"]), bf(1, c["G"], S, c["Dk"]), bf(1, c["G"], S, c["Dv"])
-    K_cmp, V_cmp = bf(1, c["G"], S_cmp, c["Dk"]), bf(1, c["G"], S_cmp, c["Dv"])
-    hid = c["Dk"] // 2
-    gate = (torch.randn(hid, c["Dk"], generator=g) * 0.1, torch.zeros(hid), torch.randn(3, hid, generator=g) * 0.1, torch.zeros(3))
+    if tensors is None:
+        Q = bf(1, rows, c["G"], c["h"], c["Dk"])
+        K_sel, V_sel, K_win, V_win = bf(1, c["G"], S, c["Dk"]), bf(1, c["G"], S, c["Dv"]), bf(1, c["G"], S, c["Dk"]), bf(1, c["G"], S, c["Dv"])
+        K_cmp, V_cmp = bf(1, c["G"], S_cmp, c["Dk"]), bf(1, c["G"], S_cmp, c["Dv"])
+        hid = c["Dk"] // 2
+        gate = (torch.randn(hid, c["Dk"], generator=g) * 0.1, torch.zeros(hid), torch.randn(3, hid, generator=g) * 0.1, torch.zeros(3))
+    else:
+        Q = tensors["Q"][:1, t0:t0 + rows]
+        K_sel, V_sel, K_win, V_win, K_cmp, V_cmp = (tensors[k][:1] for k in ("K_sel", "V_sel", "K_win", "V_win", "K_cmp", "V_cmp"))
     kw = dict(l=c["l"], d=c["d"], l_sel=c["l_sel"], n_sel=c["n_sel"], w=c["w"], t0=t0, S_total=S)
     with torch.no_grad():
         O.prefill_core(Q[:, :4], K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, gate, **kw)  # warm-up
-        n, el = 0, 0.0
+        n, el, out = 0, 0.0, None
         while True:
             t = time.perf_counter()
-            O.prefill_core(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, gate, **kw)
+            out = O.prefill_core(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, gate, **kw)
             el += time.perf_counter() - t
             n += 1
             if el > budget_s or n >= 3:
                 break
-    return rows * n / el, cores, f"{rows} query rows at t0={t0} of one S={S} sequence (B=1), full K/V caches, {n} repeats, fp32 oracle"
+    return (rows * n / el, cores, f"{rows} query rows at t0={t0} of one S={S} sequence (B=1), full K/V caches, {n} repeats, fp32 oracle port, "
+            "batched-prefill semantics", out, t0)
+
+
+def parity_64k(ora, t0, rows, gpu):
+    """GPU step vs the oracle on the same inputs at full size.  gpu: dict of the step's device outputs (O, ranges, O_cmp, O_sel,
+    O_win).  Outputs are compared on the rows where both selected the same ranges (a different selection is a different
+    function); those rows are counted, and for each the fp32 gap between the last kept and the first dropped candidate score is
+    reported: a selection that differs from the fp32 oracle's may only do so at a near-tie."""
+    from oracle import nsa_oracle as O
+    sl = slice(t0, t0 + rows)
+    rg = gpu["ranges"][:1, sl].cpu()
+    same = torch.tensor([[O.nonempty_ranges(rg[0, s, g].tolist()) == O.nonempty_ranges(ora["ranges"][0, s, g].tolist())
+                          for g in range(rg.shape[2])] for s in range(rows)])
+    out = {"rows": rows * rg.shape[2], "t0": t0, "rows_with_different_ranges": int((~same).sum())}
+    gaps = []
+    if ora.get("p_grp") is not None:
+        c = M7C
+        for s, g in (~same).nonzero().tolist():
+            t = t0 + s
+            p = ora["p_grp"][0, s, g].clone()
+            nvalid = (t + 1) // c["l_sel"]
+            cb = t // c["l_sel"]
+            comp = p.float() - torch.arange(p.numel(), dtype=torch.float32) * torch.tensor(1e-8, dtype=torch.float32)
+            comp[nvalid:] = float("-inf")
+            for j in {0, cb, max(cb - 1, 0)}:
+                if j < comp.numel():
+                    comp[j] = float("-inf")
+            v = torch.sort(comp, descending=True).values
+            k = c["n_sel"] - 3
+            gaps.append(float(v[k - 1] - v[k]) if v.numel() > k else float("nan"))
+        out["max_score_gap_at_cut_of_differing_rows"] = max(gaps) if gaps else 0.0
+    m = same[:, :, None, None].expand(-1, -1, M7C["h"], M7C["Dv"])
+    for k in ("O", "O_sel", "O_cmp", "O_win"):
+        if gpu.get(k) is None:
+            continue
+        d = (gpu[k][:1, sl].float().cpu()[0] - ora[k][0]).abs()
+        if k in ("O", "O_sel"):
+            d = d[m]
+        out[k] = {"max_abs": float(d.max()) if d.numel() else 0.0, "mae": float(d.mean()) if d.numel() else 0.0}
+    out["tolerance"] = "bf16 kernels vs the fp32 oracle: max_abs <= 2e-2, mae <= 1e-3 per branch and for the gated O"
+    out["ok"] = all(out[k]["max_abs"] <= 2e-2 and out[k]["mae"] <= 1e-3 for k in ("O", "O_sel", "O_cmp", "O_win") if k in out)
+    return out
+
+
+def reference_gpu_block(dev):
+    """The reference's best library route on THIS GPU (scripts/run_m7c_1xa100_production.sh:22-31: batched prefill, masked SDPA
+    selection): NSAAttention.forward(prefill=True), m7c dims, B=1.  It cannot run at 64k (O(S^2) masks); S=2048 / 4096 are
+    what fits.  Apples-to-apples with `module_prefill` of our own arm."""
+    out = {"route": "NSA_PREFILL_BATCHED=1 NSA_USE_SEL_MASK=1 NSA_FORCE_SEL_MASK=1 NSA_USE_FA2=0 (run_m7c_1xa100_production.sh)"}
+    try:
+        ref = reference_path()
+        if ref not in sys.path:
+            sys.path.insert(0, ref)
+        for k, v in dict(NSA_PREFILL_BATCHED="1", NSA_USE_SEL_MASK="1", NSA_FORCE_SEL_MASK="1", NSA_USE_FA2="0", NSA_USE_SEL_VARLEN="0",
+                         NSA_USE_TRITON_SEL="0", NSA_USE_SEL_PACK="0").items():
+            os.environ[k] = v
+        from nsa.cache.kv_cache import NSA_KV
+        from nsa.core.block_index import build_block_meta
+        from nsa.core.nsa_attention import NSAAttention
+        c = M7C
+        torch.manual_seed(0)
+        for dtype in (torch.bfloat16, torch.float32):
+            try:
+                attn = NSAAttention(dim=768, n_heads=c["H"], n_kv_groups=c["G"], d_k=c["Dk"], d_v=c["Dv"], l=c["l"], d=c["d"],
+                                    l_sel=c["l_sel"], n_sel=c["n_sel"], w=c["w"]).to(dev).to(dtype)
+                res = {}
+                for S in (2048, 4096):
+                    meta = build_block_meta(S, c["l"], c["d"], c["l_sel"], n_sel=c["n_sel"], w=c["w"])
+                    x = torch.randn(1, S, 768, device=dev, dtype=dtype)
+
+                    def kv0():
+                        z = lambda D: torch.zeros((1, c["G"], 0, D), device=dev, dtype=dtype)
+                        zi = lambda: torch.zeros((0,), dtype=torch.int64, device=dev)
+                        return NSA_KV(K_sel=z(c["Dk"]), V_sel=z(c["Dv"]), K_win=z(c["Dk"]), V_win=z(c["Dv"]), K_cmp_raw_seq=z(c["Dk"]),
+                                      V_cmp_raw_seq=z(c["Dv"]), K_cmp=z(c["Dk"]), V_cmp=z(c["Dv"]),
+                                      win_ptr=torch.zeros((1, c["G"]), dtype=torch.int32, device=dev),
+                                      cmp_emit_next=torch.zeros((1, c["G"]), dtype=torch.int32, device=dev), reads_pred=zi(),
+                                      reads_act_total=zi(), reads_act_sel=zi(), reads_act_cmp=zi(), reads_act_win=zi(), meta=meta)
+                    with torch.no_grad():
+                        for _ in range(2):
+                            attn(x, kv0(), prefill=True)
+                        torch.cuda.synchronize()
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        n = 5
+                        a.record()
+                        for _ in range(n):
+                            attn(x, kv0(), prefill=True)
+                        b.record()
+                        torch.cuda.synchronize()
+                    ms = a.elapsed_time(b) / n
+                    res[f"S={S}"] = {"ms_per_call": ms, "tok_per_s": S / (ms * 1e-3)}
+                out.update(dtype=str(dtype).replace("torch.", ""), results=res)
+                break
+            except Exception as ex:  # e.g. a dtype the reference's route does not take: try the next one
+                out[f"error_{str(dtype).replace('torch.', '')}"] = f"{type(ex).__name__}: {str(ex)[:200]}"
+        out["note_64k"] = "not runnable: the batched route materialises O(S^2) masks and a 12.9 GB p_cmp tensor at S=65536"
+    except Exception as ex:
+        out["error"] = f"{type(ex).__name__}: {str(ex)[:300]}"
+    return out
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference cannot travel to the GPU box)
-    on the host cores, same metric and config.  Rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, same metric and config.  With
+    oracle/_ref present (copied by oracle/make_ref.py; it travels with the snapshot) that is the UNMODIFIED reference package
+    (kind "reference"); otherwise the oracle port (kind "port").  Rank 0 only."""
     if rank != 0:
         return
-    per_step = []
-    rows = max(32, args.cpu_rows // 2)  # ~1.5 s per step on 16 cores: a 40-step run ends within a minute
-    for i in range(args.warmup + args.steps):
-        v, cores, sample = cpu_prefill_sample(args.S, rows, seed=i, budget_s=0.0)
-        if i >= args.warmup:
-            per_step.append(v)
-    val = sum(per_step) / len(per_step)
+    extra = {}
+    if reference_path() is not None:
+        rd = ReferenceDecode(args.S)
+        rd.steps(min(args.S - 4, 4096), 2)
+        reps, n_steps = 4, args.warmup + args.steps
+        tot_t, tot_n, per = 0.0, 0, []
+        for i in range(n_steps):  # step i = `reps` single-token steps at a context from the i-th of K evenly spread positions
+            k = max(i - args.warmup, 0)
+            ctx = min(args.S - reps, max(M7C["l"], int((k + 1) / max(args.steps, 1) * args.S) - reps))
+            dt = rd.steps(ctx, reps)
+            if i >= args.warmup:
+                tot_t += dt
+                tot_n += reps
+                per.append(dt)
+        val, cores, kind = tot_n / tot_t, rd.cores, "reference"
+        ms_step = 1e3 * tot_t / len(per)
+        sample = (f"UNMODIFIED reference (oracle/_ref) NSAAttention.forward(prefill=False), fp32, default env: each step = {reps} "
+                  f"single-token steps on an NSA_KV holding random K/V, step k at context ~ (k+1)/{args.steps} * {args.S} "
+                  f"(the last one on {args.S - reps} cached tokens, BASELINE.md 3-C4); tok/s = tokens / time over the {args.steps} steps")
+        extra["ms_per_token_at_64k_context"] = 1e3 * per[-1] / reps
+        if torch.cuda.is_available():
+            extra["reference_gpu"] = reference_gpu_block(torch.device("cuda", 0))
+    else:
+        per_step = []
+        rows = max(32, args.cpu_rows // 2)  # ~1.5 s per step on 16 cores: a 40-step run ends within a minute
+        for i in range(args.warmup + args.steps):
+            v, cores, sample, _, _ = cpu_prefill_sample(args.S, rows, seed=i, budget_s=0.0)
+            if i >= args.warmup:
+                per_step.append(v)
+        val, kind = sum(per_step) / len(per_step), "port"
+        ms_step = 1e3 * rows / val
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "tok/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * rows / val, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
-            "cpu_baseline": {"value": val, "unit": "tok/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "cpu_baseline": {"value": val, "unit": "tok/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0, **extra}
     print(json.dumps(line))
 
 
@@ -264,6 +469,8 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from nsa_vibe_b200.engine import ModulePrefillEngine, PrefillEngine, bind_to_gpu_numa_node
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None  # pinned e2e buffers are first-touched after this
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
@@ -320,27 +527,82 @@ def main():
         value = world * B * S / (ms_step * 1e-3)
 
         # ---- e2e: host buffers in, host result out, copies inside the timed region ------------------------
-        # Public API: PrefillEngine.run -- every step copies its inputs from pinned host memory and its result back; the
-        # copies of neighbouring steps overlap the kernels on separate streams (nothing is cached between steps).
-        from nsa_vibe_b200.engine import PrefillEngine
-        host = {k: v.cpu().pin_memory() for k, v in inp.items()}
+        # Public API = the reference-facing module call: x [B,S,768] (pinned host) -> NSAAttention.forward(x, kv, prefill=True)
+        # -> out [B,S,768] (pinned host), projections and output projection included (bench/bench_prefill.py:76-85).  Every step
+        # copies its input in and its result back; the copies of neighbouring steps overlap the kernels on separate streams
+        # (nothing is cached between steps).  `hot_path_only` is the same pipeline around the hot path alone (post-projection
+        # Q / K / V tensors in, O out: 270 MB of host traffic per step).
+        from nsa_vibe_b200.core.nsa_attention import NSAAttention
         n_e2e = max(4, args.steps)  # the same K steps as the device-resident figure (pipeline fill and drain included)
-        o_host = [torch.empty((B, S, c["G"], c["h"], c["Dv"]), dtype=torch.bfloat16).pin_memory() for _ in range(2)]
-        h2d = sum(v.numel() * v.element_size() for v in host.values())
-        d2h = o_host[0].numel() * o_host[0].element_size()
-        eng = PrefillEngine(cfg, gate, dev)
-        eng.run([host] * 3, [o_host[i % 2] for i in range(3)])  # warm-up
+        os.environ["NSA_PREFILL_BATCHED"] = "1"  # the batched-prefill selection rule of the headline (flags are read at construction)
+        torch.manual_seed(11 + rank)
+        attn = NSAAttention(dim=768, n_heads=c["H"], n_kv_groups=c["G"], d_k=c["Dk"], d_v=c["Dv"], l=c["l"], d=c["d"], l_sel=c["l_sel"],
+                            n_sel=c["n_sel"], w=c["w"]).to(dev).bfloat16()
+        x_host = [torch.randn(B, S, 768).bfloat16().pin_memory() for _ in range(2)]
+        y_host = [torch.empty((B, S, 768), dtype=torch.bfloat16).pin_memory() for _ in range(2)]
+        h2d = x_host[0].numel() * 2
+        d2h = y_host[0].numel() * 2
+        meng = ModulePrefillEngine(attn, dev)
+        meng.run([{"x": x_host[i % 2]} for i in range(3)], [y_host[i % 2] for i in range(3)])  # warm-up
         barrier()
         s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s2.record()
-        eng.run([host] * n_e2e, [o_host[i % 2] for i in range(n_e2e)])
+        meng.run([{"x": x_host[i % 2]} for i in range(n_e2e)], [y_host[i % 2] for i in range(n_e2e)])
         e2.record()
         barrier()
         t2 = torch.tensor([s2.elapsed_time(e2)], device=dev)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         e2e_val = world * B * S / (float(t2.item()) / n_e2e * 1e-3)
-        e2e_ok = bool(torch.equal(o_host[(n_e2e - 1) % 2].to(dev), step(inp)))  # the pipelined result is the plain result
+        xd = x_host[(n_e2e - 1) % 2].to(dev)
+        e2e_ok = bool(torch.equal(y_host[(n_e2e - 1) % 2].to(dev), meng.step_module({"x": xd})))  # the pipelined result is the plain result
+        # device-resident module call (no copies): what the copies cost on top
+        ms_mod = None
+        try:
+            for _ in range(2):
+                meng.step_module({"x": xd})
+            barrier()
+            s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s3.record()
+            for _ in range(5):
+                meng.step_module({"x": xd})
+            e3.record()
+            barrier()
+            ms_mod = s3.elapsed_time(e3) / 5
+        except Exception:
+            pass
+        # the reference's GPU library route runs at S=2048 / 4096 only: the same module call at those sizes for the apples-to-apples line
+        module_small = {}
+        for S_small in (2048, 4096):
+            xs = torch.randn(1, S_small, 768, device=dev).bfloat16()
+            for _ in range(3):
+                meng.step_module({"x": xs})
+            torch.cuda.synchronize()
+            s4, e4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s4.record()
+            for _ in range(10):
+                meng.step_module({"x": xs})
+            e4.record()
+            torch.cuda.synchronize()
+            module_small[f"S={S_small}"] = {"ms_per_call": s4.elapsed_time(e4) / 10, "tok_per_s": S_small / (s4.elapsed_time(e4) / 10 * 1e-3)}
+        del x_host, y_host, meng, attn, xd
+        # hot path alone through the same pipeline (round-1 definition of e2e)
+        host = {k: v.cpu().pin_memory() for k, v in inp.items()}
+        o_host = [torch.empty((B, S, c["G"], c["h"], c["Dv"]), dtype=torch.bfloat16).pin_memory() for _ in range(2)]
+        hp_h2d = sum(v.numel() * v.element_size() for v in host.values())
+        eng = PrefillEngine(cfg, gate, dev)
+        eng.run([host] * 3, [o_host[i % 2] for i in range(3)])  # warm-up
+        barrier()
+        s5, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s5.record()
+        eng.run([host] * n_e2e, [o_host[i % 2] for i in range(n_e2e)])
+        e5.record()
+        barrier()
+        t5 = torch.tensor([s5.elapsed_time(e5)], device=dev)
+        if world > 1:
+            dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        hp_val = world * B * S / (float(t5.item()) / n_e2e * 1e-3)
+        hp_ok = bool(torch.equal(o_host[(n_e2e - 1) % 2].to(dev), step(inp)))
         del host, o_host, eng
 
         # ---- per-kernel device times (outside the timed region; same inputs) -------------------------------
@@ -369,12 +631,27 @@ def main():
         kms = {"score": max(0.0, t_ss - t_sel),
                "select": t_sel,
                "cmp": t_of(lambda: ops.branch_attention(ops.BR_CMP, inp["Q"], inp["K_cmp"], inp["V_cmp"], cfg)),
-               "sel": t_of((lambda: ops.sel_attention_blockmajor(inp["Q"], inp["K_sel"], inp["V_sel"], cfg, rg_)) if sel_blockmajor else
-                           (lambda: ops.branch_attention(ops.BR_SEL, inp["Q"], inp["K_sel"], inp["V_sel"], cfg, rg_))),
+               "sel": t_of((lambda: ops.sel_attention_blockmajor(inp["Q"], inp["K_sel"], inp["V_sel"], cfg, rg_, ranges_trusted=True)) if sel_blockmajor else
+                           (lambda: ops.branch_attention(ops.BR_SEL, inp["Q"], inp["K_sel"], inp["V_sel"], cfg, rg_, ranges_trusted=True))),
                "win": t_of(lambda: ops.branch_attention(ops.BR_WIN, inp["Q"], inp["K_win"], inp["V_win"], cfg))}
         kms["gate_combine_and_rest"] = max(0.0, ms_step - sum(kms.values()))
         kms["score_full_pgrp"] = t_full  # not part of the step
         del pg, rg_
+        # ---- the step's outputs for the rows the CPU leg recomputes (parity at full size) ------------------------
+        gpu_rows = None
+        if rank == 0 and not args.no_cpu:
+            t0p = S // 2
+            rg_step = ops.score_select(inp["Q"], inp["K_cmp"], cfg, mode=0)
+            O_step, _, _ = ops.prefill_core(inp["Q"], inp["K_sel"], inp["V_sel"], inp["K_win"], inp["V_win"], inp["K_cmp"], inp["V_cmp"],
+                                            gate, cfg, sel_mode=0, ranges=rg_step, ranges_trusted=True)
+            sl = slice(0, t0p + args.cpu_rows)
+            gpu_rows = {"ranges": rg_step[:1, sl].clone(), "O": O_step[:1, sl].clone(),
+                        "O_cmp": ops.branch_attention(ops.BR_CMP, inp["Q"], inp["K_cmp"], inp["V_cmp"], cfg)[:1, sl].clone(),
+                        "O_win": ops.branch_attention(ops.BR_WIN, inp["Q"], inp["K_win"], inp["V_win"], cfg)[:1, sl].clone(),
+                        "O_sel": (ops.sel_attention_blockmajor(inp["Q"], inp["K_sel"], inp["V_sel"], cfg, rg_step, ranges_trusted=True)
+                                  if sel_blockmajor else
+                                  ops.branch_attention(ops.BR_SEL, inp["Q"], inp["K_sel"], inp["V_sel"], cfg, rg_step, ranges_trusted=True))[:1, sl].clone()}
+            del rg_step, O_step
 
         # ---- decode @S=4096 -------------------------------------------------------------------------------
         decode = None
@@ -439,17 +716,41 @@ def main():
     except Exception as ex:
         alt = {"error": f"{type(ex).__name__}: {ex}"}
     roofline["alt_semantics"] = alt
-    cpu = None
+    cpu, cpu_port, parity = None, None, None
     if not args.no_cpu:
-        v, cores, sample = cpu_prefill_sample(S, args.cpu_rows)
-        cpu = {"value": v, "unit": "tok/s", "cores": cores, "kind": "port", "sample": sample}
+        # (1) oracle port on the GPU step's own inputs: a bounded sample of the batched-prefill workload AND the parity check
+        host_in = {k: v[:1].float().cpu() for k, v in inp.items()}
+        v, cores, sample, ora, t0p = cpu_prefill_sample(S, args.cpu_rows, tensors=host_in, gate=tuple(t.float().cpu() for t in gate))
+        cpu_port = {"value": v, "unit": "tok/s", "cores": cores, "kind": "port", "sample": sample}
+        try:
+            parity = parity_64k(ora, t0p, args.cpu_rows, gpu_rows)
+        except Exception as ex:
+            parity = {"error": f"{type(ex).__name__}: {ex}"}
+        del host_in, ora
+        cpu = cpu_port
+        # (2) the UNMODIFIED reference on the same host cores (>= 128 decode steps up to a 65,535-token cache)
+        if reference_path() is not None:
+            try:
+                v, cores, sample, ms_last = reference_decode_sample(S, strata=16, reps=8)
+                cpu = {"value": v, "unit": "tok/s", "cores": cores, "kind": "reference", "sample": sample,
+                       "ms_per_token_at_64k_context": ms_last}
+            except Exception as ex:
+                cpu_port["reference_error"] = f"{type(ex).__name__}: {str(ex)[:200]}"
     line = {"metric": METRIC, "value": value, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "tok/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "how": "PrefillEngine.run: pinned host tensors in/out every step, H2D / kernels / D2H of neighbouring steps on 3 streams",
-                    "matches_device_path": e2e_ok},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "decode": decode, "train_core": train}
+                    "how": "ModulePrefillEngine.run: x [B,S,768] bf16 from pinned host memory -> NSAAttention.forward(x, kv, prefill=True) "
+                           "(projections, RoPE, cache build, hot path, output projection) -> out [B,S,768] to pinned host memory, every "
+                           "step; H2D / kernels / D2H of neighbouring steps on 3 streams",
+                    "matches_device_path": e2e_ok, "module_ms_device_resident": ms_mod, "numa_node_bound": numa_node,
+                    "hot_path_only": {"value": hp_val, "unit": "tok/s", "h2d_bytes_per_step": hp_h2d, "d2h_bytes_per_step": B * S * c["H"] * c["Dv"] * 2,
+                                      "how": "PrefillEngine.run: post-projection Q + six K/V tensors in, O out (round-1 e2e definition)",
+                                      "matches_device_path": hp_ok}},
+            "module_prefill": {"what": "NSAAttention.forward(prefill=True), B=1, bf16, device-resident x: the sizes the reference's GPU route can run "
+                                       "(see reference_gpu in the --impl reference line)", **module_small},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "cpu_port": cpu_port, "parity_64k": parity,
+            "decode": decode, "train_core": train}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

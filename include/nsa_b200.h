@@ -76,13 +76,28 @@ int64_t nsa_kernel_launches(void);
  * (nsa/core/selection_scorer.py:255-362, :434-605).  S_total is the S argument of the reference
  * (decides the forced-column count); rows are t = t0 .. t0+S-1.  K must be
  * nsa_prefill_range_cols(S_total, l_sel, n_sel). */
-int nsa_prefill_range_cols(int S_total, int l_sel, int n_sel);
+int nsa_prefill_range_cols(int S_total, int l_sel, int n_sel);   /* force_init = 1, force_local = 2: the module's call */
+int nsa_prefill_range_cols_ex(int S_total, int l_sel, int n_sel, int force_init, int force_local);
+/* force_init / force_local: the reference's arguments of the same name (block 0 forced; the last force_local blocks forced);
+ * force_init + force_local <= 3.  The module calls with (1, 2); the reference's tie-break tests with (0, 0). */
 int nsa_select_ranges_prefill(const float* p_grp, int B, int S, int G, int S_sel, int l_sel, int n_sel,
-                              int S_total, int t0, int K, int32_t* ranges, void* stream);
+                              int S_total, int t0, int K, int force_init, int force_local, int32_t* ranges, void* stream);
 /* Replaces select_topn_ranges (selection_scorer.py:124-249): p_grp [B,G,S_sel], one position t,
  * ranges [B,G,n_sel,2].  Rows the reference leaves as end<=start garbage are written as [0,0]. */
 int nsa_select_ranges_decode(const float* p_grp, int B, int G, int S_sel, int l_sel, int n_sel, int t,
-                             int32_t* ranges, void* stream);
+                             int force_init, int force_local, int32_t* ranges, void* stream);
+/* The stages of the scorer / selector as stand-alone functions, for callers of the reference's free functions (the fused hot
+ * path never materialises these tensors):
+ *   nsa_pcmp_all           compute_pcmp_all (selection_scorer.py:42-61): p_cmp [B,S,G,h,S_cmp] fp32 = softmax over ALL S_cmp keys;
+ *   nsa_map_pcmp_to_pslc   map_pcmp_to_pslc(_batched) (:64-116): p_cmp [n_rows,S_cmp] -> p_slc [n_rows,S_sel], Eq.9, any d|l, d|l_sel;
+ *   nsa_indices_to_ranges  convert_indices_to_ranges_batched(_v2) (:380-605): block ids [B,S,G,K] int32 (ascending per row,
+ *                          negative = padding) -> ranges [B,S,G,K,2]: duplicates dropped, adjacent blocks merged, ends clamped to
+ *                          t0 + s + 1, [0,0] padded. */
+int nsa_pcmp_all(const nsa_dims_t* dm, const void* Q, const void* K_cmp, float* p_cmp, void* stream);
+int nsa_map_pcmp_to_pslc(const float* p_cmp, int64_t n_rows, int S_cmp, int S_sel, int l, int d, int l_sel, float* p_slc,
+                         void* stream);
+int nsa_indices_to_ranges(const int32_t* indices, int B, int S, int G, int K, int S_sel, int l_sel, int t0, int32_t* ranges,
+                          void* stream);
 
 /* ---- (1) scoring: Q, K_cmp -> p_grp  (compute_pcmp_all + map_pcmp_to_pslc_batched + sum over h;
  * selection_scorer.py:42-61, :89-116, nsa_attention.py:1091).  p_grp [B,S,G,S_sel] fp32. */

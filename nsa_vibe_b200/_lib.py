@@ -60,8 +60,12 @@ SIGNATURES = {
     "nsa_last_error": (C.c_char_p, []),
     "nsa_kernel_launches": (_I64, []),
     "nsa_prefill_range_cols": (_I, [_I, _I, _I]),
-    "nsa_select_ranges_prefill": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
-    "nsa_select_ranges_decode": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "nsa_prefill_range_cols_ex": (_I, [_I, _I, _I, _I, _I]),
+    "nsa_select_ranges_prefill": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "nsa_select_ranges_decode": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "nsa_pcmp_all": (_I, [_DP, _P, _P, _P, _P]),
+    "nsa_map_pcmp_to_pslc": (_I, [_P, _I64, _I, _I, _I, _I, _I, _P, _P]),
+    "nsa_indices_to_ranges": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "nsa_score": (_I, [_DP, _P, _P, _I, _P, _P]),
     "nsa_score_select": (_I, [_DP, _P, _P, _I, _I, _I, _P, _P, _P]),
     "nsa_branch_attn_fwd": (_I, [_DP, _I, _P, _P, _P, _P, _P, _P, _P]),

@@ -68,22 +68,48 @@ const char* nsa_last_error(void) { return g_err; }
 int64_t nsa_kernel_launches(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int nsa_prefill_range_cols(int S_total, int l_sel, int n_sel) { return prefill_range_cols(S_total, l_sel, n_sel); }
-
-int nsa_select_ranges_prefill(const float* p_grp, int B, int S, int G, int S_sel, int l_sel, int n_sel, int S_total,
-                              int t0, int K, int32_t* ranges, void* stream) {
-  NSA_REQUIRE(p_grp && ranges, "select_prefill: NULL pointer");
-  NSA_REQUIRE(l_sel >= 1 && n_sel >= 0 && S_total >= 1, "select_prefill: bad l_sel/n_sel/S_total");
-  NSA_REQUIRE(K == prefill_range_cols(S_total, l_sel, n_sel), "select_prefill: K=%d but the reference emits %d columns",
-              K, prefill_range_cols(S_total, l_sel, n_sel));
-  return launch_select(p_grp, B * S * G, S, G, S_sel, l_sel, n_sel, 0, prefill_forced_cols(S_total, l_sel), K, t0, ranges,
-                       (cudaStream_t)stream);
+int nsa_prefill_range_cols_ex(int S_total, int l_sel, int n_sel, int force_init, int force_local) {
+  return prefill_range_cols_ex(S_total, l_sel, n_sel, force_init, force_local);
 }
 
-int nsa_select_ranges_decode(const float* p_grp, int B, int G, int S_sel, int l_sel, int n_sel, int t, int32_t* ranges,
-                             void* stream) {
+int nsa_select_ranges_prefill(const float* p_grp, int B, int S, int G, int S_sel, int l_sel, int n_sel, int S_total,
+                              int t0, int K, int force_init, int force_local, int32_t* ranges, void* stream) {
+  NSA_REQUIRE(p_grp && ranges, "select_prefill: NULL pointer");
+  NSA_REQUIRE(l_sel >= 1 && n_sel >= 0 && S_total >= 1, "select_prefill: bad l_sel/n_sel/S_total");
+  NSA_REQUIRE(force_local >= 0 && (force_init ? 1 : 0) + force_local <= 3, "select_prefill: force_init + force_local must be <= 3");
+  const int Kw = prefill_range_cols_ex(S_total, l_sel, n_sel, force_init, force_local);
+  NSA_REQUIRE(K == Kw, "select_prefill: K=%d but the reference emits %d columns", K, Kw);
+  return launch_select(p_grp, B * S * G, S, G, S_sel, l_sel, n_sel, 0, forced_code(0, S_total, l_sel, force_init, force_local), K, t0,
+                       ranges, (cudaStream_t)stream);
+}
+
+int nsa_select_ranges_decode(const float* p_grp, int B, int G, int S_sel, int l_sel, int n_sel, int t, int force_init,
+                             int force_local, int32_t* ranges, void* stream) {
   NSA_REQUIRE(p_grp && ranges, "select_decode: NULL pointer");
   NSA_REQUIRE(l_sel >= 1 && n_sel >= 0 && t >= 0, "select_decode: bad l_sel/n_sel/t");
-  return launch_select(p_grp, B * G, 1, G, S_sel, l_sel, n_sel, 1, 3, n_sel, t, ranges, (cudaStream_t)stream);
+  NSA_REQUIRE(force_local >= 0 && (force_init ? 1 : 0) + force_local <= 3, "select_decode: force_init + force_local must be <= 3");
+  return launch_select(p_grp, B * G, 1, G, S_sel, l_sel, n_sel, 1, forced_code(1, t + 1, l_sel, force_init, force_local), n_sel, t,
+                       ranges, (cudaStream_t)stream);
+}
+
+int nsa_pcmp_all(const nsa_dims_t* dm, const void* Q, const void* K_cmp, float* p_cmp, void* stream) {
+  if (int rc = validate_dims(dm, "pcmp_all")) return rc;
+  NSA_REQUIRE(Q && p_cmp && (K_cmp || dm->S_cmp == 0), "pcmp_all: NULL pointer");
+  return launch_pcmp_all(*dm, Q, K_cmp, p_cmp, (cudaStream_t)stream);
+}
+
+int nsa_map_pcmp_to_pslc(const float* p_cmp, int64_t n_rows, int S_cmp, int S_sel, int l, int d, int l_sel, float* p_slc,
+                         void* stream) {
+  NSA_REQUIRE((p_cmp || n_rows * S_cmp == 0) && (p_slc || n_rows * S_sel == 0), "map_pcmp_to_pslc: NULL pointer");
+  NSA_REQUIRE(n_rows >= 0 && S_cmp >= 0 && S_sel >= 0 && l >= 1 && d >= 1 && l_sel >= 1, "map_pcmp_to_pslc: bad sizes");
+  return launch_map_pslc(p_cmp, (long long)n_rows, S_cmp, S_sel, l, d, l_sel, p_slc, (cudaStream_t)stream);
+}
+
+int nsa_indices_to_ranges(const int32_t* indices, int B, int S, int G, int K, int S_sel, int l_sel, int t0, int32_t* ranges,
+                          void* stream) {
+  NSA_REQUIRE((indices && ranges) || (long long)B * S * G * K == 0, "indices_to_ranges: NULL pointer");
+  NSA_REQUIRE(B >= 0 && S >= 0 && G >= 0 && K >= 0 && l_sel >= 1, "indices_to_ranges: bad sizes");
+  return launch_indices_to_ranges(indices, B, S, G, K, S_sel, l_sel, t0, ranges, (cudaStream_t)stream);
 }
 
 int nsa_score(const nsa_dims_t* dm, const void* Q, const void* K_cmp, int S_sel, float* p_grp, void* stream) {

@@ -98,10 +98,136 @@ int launch_score_generic(const nsa_dims_t& dm, const void* Q, const void* Kc, in
   }
   int blocks = ceil_div(n_rows, kScoreWarps);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  const int nf = prefill_forced_cols(S_total, dm.l_sel);
+  const int nf = forced_code_default(sel_mode, S_total, dm.l_sel);
   score_generic_kernel<<<blocks, kScoreWarps * 32, smem, stream>>>(dm, Q, Kc, S_sel, S_total, sel_mode, nf, Kr, p_grp,
                                                                   ranges);
   return check_launch("score_generic_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// The scorer's stages as stand-alone functions (the reference's free functions compute_pcmp_all, map_pcmp_to_pslc(_batched),
+// convert_indices_to_ranges_batched(_v2): selection_scorer.py:42-61, :64-116, :380-605).  The hot path never materialises
+// these tensors (p_cmp alone is 12.9 GB per 64k sequence); callers and tests that want them get them from here.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kScoreWarps * 32)
+pcmp_all_kernel(nsa_dims_t dm, const void* __restrict__ Q, const void* __restrict__ Kc, float* __restrict__ p) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* lg = smem + (size_t)warp * (dm.S_cmp + dm.Dk);
+  float* qh = lg + dm.S_cmp;
+  const long long n = (long long)dm.B * dm.S * dm.G * dm.h;
+  const int dt = dm.dtype;
+  for (long long rh = (long long)blockIdx.x * kScoreWarps + warp; rh < n; rh += (long long)gridDim.x * kScoreWarps) {
+    const long long row = rh / dm.h;
+    const int g = (int)(row % dm.G), b = (int)(row / ((long long)dm.G * dm.S));
+    for (int i = lane; i < dm.Dk; i += 32) qh[i] = ld_elt(Q, (size_t)rh * dm.Dk + i, dt);
+    __syncwarp();
+    const size_t kbase = (size_t)(b * dm.G + g) * dm.cap_cmp * dm.Dk;
+    float m = -INFINITY;
+    for (int i = lane; i < dm.S_cmp; i += 32) {
+      float a = 0.f;
+      for (int k = 0; k < dm.Dk; ++k) a = fmaf(qh[k], ld_elt(Kc, kbase + (size_t)i * dm.Dk + k, dt), a);
+      a *= dm.scale;
+      lg[i] = a;
+      m = fmaxf(m, a);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int i = lane; i < dm.S_cmp; i += 32) {
+      const float e = expf(lg[i] - m);
+      lg[i] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int i = lane; i < dm.S_cmp; i += 32) p[(size_t)rh * dm.S_cmp + i] = lg[i] * inv;
+    __syncwarp();
+  }
+}
+
+int launch_pcmp_all(const nsa_dims_t& dm, const void* Q, const void* Kc, float* p_cmp, cudaStream_t stream) {
+  const long long n = (long long)dm.B * dm.S * dm.G * dm.h;
+  if (n == 0 || dm.S_cmp == 0) return NSA_OK;
+  const size_t smem = (size_t)kScoreWarps * (dm.S_cmp + dm.Dk) * sizeof(float);
+  NSA_REQUIRE(smem <= 200 * 1024, "pcmp_all: S_cmp=%d needs %zu B of shared memory (this stand-alone stage serves S_cmp <= ~12k; the "
+              "hot path scores any length without materialising p_cmp)", dm.S_cmp, smem);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(pcmp_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("pcmp_all: smem attr: %s", cudaGetErrorString(e)); return NSA_ERR_CUDA; }
+  }
+  long long blocks = (n + kScoreWarps - 1) / kScoreWarps;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pcmp_all_kernel<<<(int)blocks, kScoreWarps * 32, smem, stream>>>(dm, Q, Kc, p_cmp);
+  return check_launch("pcmp_all_kernel");
+}
+
+// Eq.9 for any d | l, d | l_sel: p_slc[row][j] = sum_i p_cmp[row][i] * overlap(i, j) / l, ascending i (the COO order of the
+// reference's CPU scatter_add, block_index.py:81-85, selection_scorer.py:102-115).  One thread per (row, j).
+__global__ void __launch_bounds__(256)
+map_pslc_kernel(const float* __restrict__ p, long long n_rows, int S_cmp, int S_sel, int l, int d, int l_sel, float* __restrict__ out) {
+  const long long total = n_rows * S_sel;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / S_sel;
+    const int j = (int)(idx - row * S_sel);
+    const int b0 = j * l_sel, b1 = b0 + l_sel;
+    int i_lo = b0 - l + 1 <= 0 ? 0 : (b0 - l + 1 + d - 1) / d;
+    int i_hi = (b1 - 1) / d;
+    if (i_hi > S_cmp - 1) i_hi = S_cmp - 1;
+    float acc = 0.f;
+    for (int i = i_lo; i <= i_hi; ++i) {
+      const int a0 = i * d, a1 = a0 + l;
+      const int ov = min(a1, b1) - max(a0, b0);
+      if (ov > 0) acc += p[row * S_cmp + i] * ((float)ov / (float)l);
+    }
+    out[idx] = acc;
+  }
+}
+
+int launch_map_pslc(const float* p_cmp, long long n_rows, int S_cmp, int S_sel, int l, int d, int l_sel, float* p_slc, cudaStream_t stream) {
+  const long long total = n_rows * S_sel;
+  if (total == 0) return NSA_OK;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  map_pslc_kernel<<<(int)blocks, 256, 0, stream>>>(p_cmp, n_rows, S_cmp, S_sel, l, d, l_sel, p_slc);
+  return check_launch("map_pslc_kernel");
+}
+
+// Block ids (ascending per row, negative = padding) -> merged [start, end) token ranges, clamped to t + 1, [0,0] padded: the
+// loop of convert_indices_to_ranges_batched (selection_scorer.py:380-431), which ranges v2 (:434-605) reproduces.  One thread
+// per (b, t, g) row; the hot path never calls this (its selection kernel emits ranges straight from the pick bitmap).
+__global__ void __launch_bounds__(128)
+indices_to_ranges_kernel(const int32_t* __restrict__ idx, long long n_rows, int S, int G, int K, int S_sel, int l_sel, int t0,
+                         int32_t* __restrict__ out) {
+  for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < n_rows; row += (long long)gridDim.x * blockDim.x) {
+    const int t = t0 + (int)((row / G) % S);
+    const int32_t* r = idx + row * K;
+    int32_t* o = out + row * K * 2;
+    int n = 0, prev = -1, last_s = -1, last_e = -1;
+    for (int k = 0; k < K; ++k) {
+      const int bid = r[k];
+      if (bid < 0 || bid >= S_sel || bid == prev) continue;
+      prev = bid;
+      const int s0 = bid * l_sel;
+      int e0 = s0 + l_sel;
+      if (e0 > t + 1) e0 = t + 1;
+      if (e0 <= s0) continue;
+      if (last_s < 0) { last_s = s0; last_e = e0; }
+      else if (s0 == last_e) last_e = e0;
+      else { o[2 * n] = last_s; o[2 * n + 1] = last_e; ++n; last_s = s0; last_e = e0; }
+    }
+    if (last_s >= 0) { o[2 * n] = last_s; o[2 * n + 1] = last_e; ++n; }
+    for (; n < K; ++n) { o[2 * n] = 0; o[2 * n + 1] = 0; }
+  }
+}
+
+int launch_indices_to_ranges(const int32_t* indices, int B, int S, int G, int K, int S_sel, int l_sel, int t0, int32_t* ranges,
+                             cudaStream_t stream) {
+  const long long n_rows = (long long)B * S * G;
+  if (n_rows == 0 || K == 0) return NSA_OK;
+  long long blocks = (n_rows + 127) / 128;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  indices_to_ranges_kernel<<<(int)blocks, 128, 0, stream>>>(indices, n_rows, S, G, K, S_sel, l_sel, t0, ranges);
+  return check_launch("indices_to_ranges_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------

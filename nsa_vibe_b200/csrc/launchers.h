@@ -36,6 +36,10 @@ int launch_score_generic(const nsa_dims_t& dm, const void* Q, const void* Kc, in
                          float* p_grp, int32_t* ranges, cudaStream_t stream);
 int launch_fwd_generic(const nsa_dims_t& dm, const FwdArgs& a, cudaStream_t stream);
 int launch_bwd_generic(const nsa_dims_t& dm, const BwdArgs& a, cudaStream_t stream);
+int launch_pcmp_all(const nsa_dims_t& dm, const void* Q, const void* Kc, float* p_cmp, cudaStream_t stream);
+int launch_map_pslc(const float* p_cmp, long long n_rows, int S_cmp, int S_sel, int l, int d, int l_sel, float* p_slc, cudaStream_t stream);
+int launch_indices_to_ranges(const int32_t* indices, int B, int S, int G, int K, int S_sel, int l_sel, int t0, int32_t* ranges,
+                             cudaStream_t stream);
 int launch_gate_fwd(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t& gp, float* gates, cudaStream_t stream);
 int launch_gate_bwd(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t& gp, const float* dgates, float* dQ,
                     float* d_fc1_w, float* d_fc1_b, float* d_fc2_w, float* d_fc2_b, cudaStream_t stream);

@@ -27,6 +27,52 @@ __host__ __device__ inline int prefill_range_cols(int S_total, int l_sel, int n_
   return nf < n_sel ? nf : n_sel;
 }
 
+// Forced blocks of a row as a code: bits [0,2) = count n <= 3, slot i at bits [2+4i, 6+4i): 15 = block 0 (force_init), k = the
+// local block max(cb - k, 0) with cb = t / l_sel (force_local).  Slots are in ascending block order.
+//   decode rule (select_topn_ranges, selection_scorer.py:159-170): [0 if force_init] + [cb - k for k < force_local], no dedup;
+//   prefill rule (select_topn_ranges_batched, :283-300): the same columns sorted per row, then COLUMNS that are identical for
+//   every row of the S_total-row tensor collapse (unique_consecutive(dim=-1)): a column is all-zero iff max_cb <= k.
+__host__ __device__ inline int forced_code(int mode, int S_total, int l_sel, int force_init, int force_local) {
+  int codes[3] = {0, 0, 0};
+  int n = 0;
+  if (mode == 1) {
+    if (force_init) codes[n++] = 15;
+    for (int k = 0; k < force_local && n < 3; ++k) codes[n++] = k;
+  } else {
+    const int max_cb = S_total > 0 ? (S_total - 1) / l_sel : 0;
+    int nz = 0;
+    for (int k = 0; k < force_local; ++k) nz += max_cb > k ? 1 : 0;
+    if ((force_init ? 1 : 0) + (force_local - nz) > 0) codes[n++] = 15;
+    for (int k = force_local - 1; k >= 0; --k)
+      if (max_cb > k && n < 3) codes[n++] = k;
+  }
+  int c = n;
+  for (int i = 0; i < n; ++i) c |= codes[i] << (2 + 4 * i);
+  return c;
+}
+__host__ __device__ inline int forced_code_default(int mode, int S_total, int l_sel) { return forced_code(mode, S_total, l_sel, 1, 2); }
+
+__host__ __device__ inline int prefill_range_cols_ex(int S_total, int l_sel, int n_sel, int force_init, int force_local) {
+  int S_sel = S_total <= 0 ? 0 : (S_total + l_sel - 1) / l_sel;
+  if (n_sel >= S_sel) return S_sel;
+  int nf = forced_code(0, S_total, l_sel, force_init, force_local) & 3;
+  int k_rest = n_sel - nf > 0 ? n_sel - nf : 0;
+  if (k_rest > 0) return nf + (k_rest < S_sel ? k_rest : S_sel);
+  return nf < n_sel ? nf : n_sel;
+}
+
+__device__ __forceinline__ int forced_decode(int fcode, int cb, int (&forced)[3]) {
+  const int n = fcode & 3;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int code = (fcode >> (2 + 4 * i)) & 15;
+    int v = code == 15 ? 0 : cb - code;
+    if (v < 0) v = 0;
+    forced[i] = i < n ? v : -1;
+  }
+  return n;
+}
+
 __device__ __forceinline__ void bitmap_set(uint32_t (&bm)[kSelMaxWords], int lane, int j) {
   int word = j >> 5;
   if ((word & 31) == lane) bm[word >> 5] |= 1u << (j & 31);
@@ -87,7 +133,8 @@ __device__ inline void sel_bitmap_to_ranges(const uint32_t (&bm)[kSelMaxWords], 
 }
 
 // `sc`: this warp's copy of the row (S_sel floats in shared memory, clobbered).
-// mode 0 = prefill rule, 1 = decode rule.  Writes out[K][2] (int32 token ranges, [0,0] padded).
+// mode 0 = prefill rule, 1 = decode rule; nf = forced_code(mode, S_total, l_sel, force_init, force_local).
+// Writes out[K][2] (int32 token ranges, [0,0] padded).
 __device__ inline void select_row_warp(float* sc, int S_sel, int l_sel, int n_sel, int mode, int nf, int K, int t,
                                        int32_t* __restrict__ out) {
   const int lane = threadIdx.x & 31;
@@ -99,7 +146,6 @@ __device__ inline void select_row_warp(float* sc, int S_sel, int l_sel, int n_se
   int nvalid = (t + 1) / l_sel;
   if (nvalid > S_sel) nvalid = S_sel;
   const int cb = t / l_sel;
-  const int cb1 = cb > 0 ? cb - 1 : 0;
 
   if (mode == 0 && n_sel >= S_sel) {
     // selection_scorer.py:348-354: n_top >= S_sel -> exactly all complete blocks [0, nvalid).
@@ -111,16 +157,7 @@ __device__ inline void select_row_warp(float* sc, int S_sel, int l_sel, int n_se
   } else {
     // forced ids (sorted ascending): prefill keeps nf distinct columns, decode always three
     int forced[3];
-    int nfc;
-    if (mode == 0) {
-      nfc = nf;
-      if (nf == 1) { forced[0] = 0; forced[1] = 0; forced[2] = 0; }
-      else if (nf == 2) { forced[0] = 0; forced[1] = cb; forced[2] = cb; }
-      else { forced[0] = 0; forced[1] = cb1; forced[2] = cb; }
-    } else {
-      nfc = 3;
-      forced[0] = 0; forced[1] = cb1; forced[2] = cb;
-    }
+    const int nfc = forced_decode(nf, cb, forced);  // nf = forced_code(...)
     const int k_rest = n_sel - nfc > 0 ? n_sel - nfc : 0;
     // forced members of the selection
     int take = nfc;
@@ -260,7 +297,6 @@ __device__ inline void select_row_warp_1024(const float* __restrict__ src, float
 #pragma unroll
   for (int i = 0; i < kSelMaxWords; ++i) bm[i] = 0u;
   const int cb = t / l_sel;
-  const int cb1 = cb > 0 ? cb - 1 : 0;
   if (mode == 0 && n_sel >= S_sel) {
     for (int w = lane; w * 32 < nvalid; w += 32) {
       int rem = nvalid - w * 32;
@@ -268,16 +304,7 @@ __device__ inline void select_row_warp_1024(const float* __restrict__ src, float
     }
   } else {
     int forced[3];
-    int nfc;
-    if (mode == 0) {
-      nfc = nf;
-      if (nf == 1) { forced[0] = 0; forced[1] = 0; forced[2] = 0; }
-      else if (nf == 2) { forced[0] = 0; forced[1] = cb; forced[2] = cb; }
-      else { forced[0] = 0; forced[1] = cb1; forced[2] = cb; }
-    } else {
-      nfc = 3;
-      forced[0] = 0; forced[1] = cb1; forced[2] = cb;
-    }
+    const int nfc = forced_decode(nf, cb, forced);  // nf = forced_code(...)
     const int k_rest = n_sel - nfc > 0 ? n_sel - nfc : 0;
     int take = nfc;
     if (mode == 0 && k_rest == 0) take = nfc < n_sel ? nfc : n_sel;

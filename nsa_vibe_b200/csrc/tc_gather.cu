@@ -541,7 +541,7 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
         if (warp == 1 && tp >= kGGateSlots) gate_of_token(row, tp, fz->qgp, fz->xs);  // tokens the prologue did not cover
         g_named_bar(1, 128);
         if (warp == 0) {
-          select_row_warp(fz->pg, a.S_sel, dm.l_sel, dm.n_sel, 1, 3, dm.n_sel, t, fz->ranges[tp & 1]);
+          select_row_warp(fz->pg, a.S_sel, dm.l_sel, dm.n_sel, 1, forced_code_default(1, 0, dm.l_sel), dm.n_sel, t, fz->ranges[tp & 1]);
           __syncwarp();
           if (a.ranges_out && lane < dm.n_sel)
             *reinterpret_cast<int2*>(a.ranges_out + (row * dm.n_sel + lane) * 2) =

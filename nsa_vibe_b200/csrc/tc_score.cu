@@ -351,7 +351,7 @@ int launch_score_tc(const nsa_dims_t& dm, const void* Q, const void* Kc, int S_s
     rc = big ? launch_score_t<__half, 4>(dm, Q, Kc, S_sel, pg, so, stream) : launch_score_t<__half, 2>(dm, Q, Kc, S_sel, pg, so, stream);
   if (rc) return rc;
   if (!ranges) return NSA_OK;
-  const int nf = sel_mode == 0 ? prefill_forced_cols(S_total, dm.l_sel) : 3;
+  const int nf = forced_code_default(sel_mode, S_total, dm.l_sel);
   return launch_select(pg, dm.B * dm.S * dm.G, dm.S, dm.G, S_sel, dm.l_sel, dm.n_sel, sel_mode, nf, Kr, dm.t0, ranges, stream);
 }
 

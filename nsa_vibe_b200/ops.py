@@ -106,8 +106,8 @@ def _workspace(dm, which: int, dev) -> Optional[torch.Tensor]:
     return torch.empty(n, dtype=torch.uint8, device=dev) if n else None
 
 
-def prefill_range_cols(S_total: int, l_sel: int, n_sel: int) -> int:
-    return int(_lib.load().nsa_prefill_range_cols(S_total, l_sel, n_sel))
+def prefill_range_cols(S_total: int, l_sel: int, n_sel: int, force_init: bool = True, force_local: int = 2) -> int:
+    return int(_lib.load().nsa_prefill_range_cols_ex(S_total, l_sel, n_sel, int(bool(force_init)), int(force_local)))
 
 
 def num_sel_blocks(seq_len: int, l_sel: int) -> int:
@@ -117,28 +117,70 @@ def num_sel_blocks(seq_len: int, l_sel: int) -> int:
 # ----------------------------------------------------------------------------------------------------
 # (2) selection
 # ----------------------------------------------------------------------------------------------------
-def select_ranges_prefill(p_grp: torch.Tensor, l_sel: int, n_sel: int, S_total: Optional[int] = None, t0: int = 0) -> torch.Tensor:
+def select_ranges_prefill(p_grp: torch.Tensor, l_sel: int, n_sel: int, S_total: Optional[int] = None, t0: int = 0, *,
+                          force_init: bool = True, force_local: int = 2) -> torch.Tensor:
     """p_grp [B,S,G,S_sel] fp32 -> ranges [B,S,G,K,2] int32; bit-exact vs select_topn_ranges_batched
     (nsa/core/selection_scorer.py:255-362)."""
     _require_cuda(p_grp)
     B, S, G, S_sel = p_grp.shape
     S_total = S if S_total is None else S_total
     p = _c(p_grp.detach().float())
-    K = prefill_range_cols(S_total, l_sel, n_sel)
+    K = prefill_range_cols(S_total, l_sel, n_sel, force_init, force_local)
     out = torch.empty((B, S, G, K, 2), dtype=torch.int32, device=p.device)
     if out.numel():
-        _call("nsa_select_ranges_prefill", _ptr(p), B, S, G, S_sel, l_sel, n_sel, S_total, t0, K, _ptr(out), _stream())
+        _call("nsa_select_ranges_prefill", _ptr(p), B, S, G, S_sel, l_sel, n_sel, S_total, t0, K, int(bool(force_init)), int(force_local),
+              _ptr(out), _stream())
     return out
 
 
-def select_ranges_decode(p_grp: torch.Tensor, l_sel: int, n_sel: int, t: int) -> torch.Tensor:
+def select_ranges_decode(p_grp: torch.Tensor, l_sel: int, n_sel: int, t: int, *, force_init: bool = True,
+                         force_local: int = 2) -> torch.Tensor:
     """p_grp [B,G,S_sel] fp32 -> ranges [B,G,n_sel,2] int32 (select_topn_ranges, selection_scorer.py:124-249)."""
     _require_cuda(p_grp)
     B, G, S_sel = p_grp.shape
     p = _c(p_grp.detach().float())
     out = torch.empty((B, G, n_sel, 2), dtype=torch.int32, device=p.device)
     if out.numel():
-        _call("nsa_select_ranges_decode", _ptr(p), B, G, S_sel, l_sel, n_sel, int(t), _ptr(out), _stream())
+        _call("nsa_select_ranges_decode", _ptr(p), B, G, S_sel, l_sel, n_sel, int(t), int(bool(force_init)), int(force_local),
+              _ptr(out), _stream())
+    return out
+
+
+def pcmp_all(Q: torch.Tensor, K_cmp: torch.Tensor) -> torch.Tensor:
+    """compute_pcmp_all (selection_scorer.py:42-61) as a stand-alone stage: softmax over ALL S_cmp keys of Q.K_cmp^T/sqrt(Dk);
+    Q [B,S,G,h,Dk], K_cmp [B,G,S_cmp,Dk] -> p_cmp [B,S,G,h,S_cmp] fp32.  For callers of the reference's free functions: the hot
+    path never materialises this tensor, and this stage serves S_cmp up to ~12k."""
+    _require_cuda(Q, K_cmp)
+    Q, K_cmp = _c(Q.detach()), _c(K_cmp.detach())
+    B, S, G, h, _ = Q.shape
+    dm = make_dims(Q, NSAConfig(), K_cmp=K_cmp)
+    out = torch.empty((B, S, G, h, K_cmp.shape[2]), dtype=torch.float32, device=Q.device)
+    if out.numel():
+        _call("nsa_pcmp_all", C.byref(dm), _ptr(Q), _ptr(K_cmp), _ptr(out), _stream())
+    return out
+
+
+def map_pcmp_to_pslc(p_cmp: torch.Tensor, S_sel: int, l: int, d: int, l_sel: int) -> torch.Tensor:
+    """Eq.9 as a stand-alone stage (map_pcmp_to_pslc(_batched), selection_scorer.py:64-116): p_cmp [..., S_cmp] -> [..., S_sel] fp32."""
+    _require_cuda(p_cmp)
+    p = _c(p_cmp.detach().float())
+    S_cmp = int(p.shape[-1])
+    n_rows = p.numel() // S_cmp if S_cmp else 0
+    out = torch.zeros((*p.shape[:-1], int(S_sel)), dtype=torch.float32, device=p.device)
+    if out.numel() and S_cmp:
+        _call("nsa_map_pcmp_to_pslc", _ptr(p), n_rows, S_cmp, int(S_sel), int(l), int(d), int(l_sel), _ptr(out), _stream())
+    return out
+
+
+def indices_to_ranges(indices: torch.Tensor, S_sel: int, l_sel: int, t0: int = 0) -> torch.Tensor:
+    """convert_indices_to_ranges_batched(_v2) (selection_scorer.py:380-605): block ids [B,S,G,K] (ascending per row, negative =
+    padding) -> [B,S,G,K,2] int32 token ranges, duplicates dropped, adjacent blocks merged, ends clamped to t + 1, [0,0] padded."""
+    _require_cuda(indices)
+    B, S, G, K = indices.shape
+    idx = _c(indices.detach().to(torch.int32))
+    out = torch.zeros((B, S, G, K, 2), dtype=torch.int32, device=idx.device)
+    if out.numel():
+        _call("nsa_indices_to_ranges", _ptr(idx), B, S, G, K, int(S_sel), int(l_sel), int(t0), _ptr(out), _stream())
     return out
 
 

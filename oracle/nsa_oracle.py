@@ -189,7 +189,8 @@ def _composite(masked: np.ndarray) -> np.ndarray:
     return (masked.astype(np.float32) - bias).astype(np.float32)
 
 
-def select_ranges_decode(p_grp: torch.Tensor, l_sel: int, n_sel: int, t: int) -> torch.Tensor:
+def select_ranges_decode(p_grp: torch.Tensor, l_sel: int, n_sel: int, t: int, force_init: bool = True,
+                         force_local: int = 2) -> torch.Tensor:
     """select_topn_ranges (selection_scorer.py:124-249): p_grp [B,G,S_sel] -> [B,G,n_sel,2] int32.
     Forced {0, cb, max(cb-1,0)} always included; other picks from valid blocks
     ((j+1)*l_sel <= t+1) by composite; sort, dedup, merge adjacent, clamp end to t+1, pad [0,0].
@@ -199,8 +200,8 @@ def select_ranges_decode(p_grp: torch.Tensor, l_sel: int, n_sel: int, t: int) ->
     B, G, S_sel = p.shape
     out = np.zeros((B, G, n_sel, 2), dtype=np.int32)
     cb = max(t // l_sel, 0)
-    forced = [0, cb, max(cb - 1, 0)]
-    k_rest = max(n_sel - 3, 0)
+    forced = ([0] if force_init else []) + [max(cb - i, 0) for i in range(force_local)]  # selection_scorer.py:159-170
+    k_rest = max(n_sel - len(forced), 0)
     for b in range(B):
         for g in range(G):
             masked = p[b, g].copy()
@@ -240,36 +241,47 @@ def prefill_forced_cols(S: int, l_sel: int) -> int:
     return 3
 
 
-def prefill_range_cols(S: int, l_sel: int, n_sel: int) -> int:
+def prefill_forced_table(S: int, l_sel: int, force_init: bool = True, force_local: int = 2) -> np.ndarray:
+    """Forced block ids of every row t < S as the reference builds them (selection_scorer.py:283-300): [0 if force_init] +
+    [max(cb - k, 0) for k < force_local], sorted per row, then COLUMNS equal to their left neighbour on every row are dropped
+    (unique_consecutive(dim=-1) acts on whole columns).  Returns [S, nf] int."""
+    rows = []
+    for t in range(S):
+        cb = t // l_sel
+        rows.append(sorted(([0] if force_init else []) + [max(cb - k, 0) for k in range(force_local)]))
+    arr = np.array(rows, dtype=np.int64).reshape(S, -1)
+    keep = [c for c in range(arr.shape[1]) if c == 0 or not np.array_equal(arr[:, c], arr[:, c - 1])]
+    return arr[:, keep]
+
+
+def prefill_range_cols(S: int, l_sel: int, n_sel: int, force_init: bool = True, force_local: int = 2) -> int:
     """Width K of the batched ranges tensor [B,S,G,K,2]."""
     S_sel = num_sel_blocks(S, l_sel)
     if n_sel >= S_sel:
         return S_sel
-    nf = prefill_forced_cols(S, l_sel)
+    nf = prefill_forced_table(S, l_sel, force_init, force_local).shape[1]
     k_rest = max(0, n_sel - nf)
     return nf + min(k_rest, S_sel) if k_rest > 0 else min(nf, n_sel)
 
 
-def select_ranges_prefill(p_grp: torch.Tensor, l_sel: int, n_sel: int, S: int, t0: int = 0) -> torch.Tensor:
+def select_ranges_prefill(p_grp: torch.Tensor, l_sel: int, n_sel: int, S: int, t0: int = 0, force_init: bool = True,
+                          force_local: int = 2) -> torch.Tensor:
     """select_topn_ranges_batched + convert_indices_to_ranges_batched_v2
     (selection_scorer.py:255-362, :434-605): p_grp [B,S,G,S_sel] -> [B,S,G,K,2] int32.
     Every entry (forced included) must be a *complete* block at row t; if n_sel >= S_sel the
     row is all valid blocks; runs of equal/+1 ids merge; end clamped to t+1; left aligned."""
     p = p_grp.detach().float().numpy()
     B, S_q, G, S_sel = p.shape
-    nf = prefill_forced_cols(S, l_sel)
-    K = prefill_range_cols(S, l_sel, n_sel)
+    table = prefill_forced_table(S, l_sel, force_init, force_local)
+    nf = table.shape[1]
+    K = prefill_range_cols(S, l_sel, n_sel, force_init, force_local)
     k_rest = max(0, n_sel - nf)
     out = np.zeros((B, S_q, G, K, 2), dtype=np.int32)
     for b in range(B):
         for tq in range(S_q):
             t = t0 + tq  # absolute position of this row
             nvalid = min((t + 1) // l_sel, S_sel)
-            cb = t // l_sel
-            forced3 = sorted([0, cb, max(cb - 1, 0)])
-            forced = {1: [forced3[0]], 2: forced3[1:], 3: forced3}[nf]
-            # column-wise unique keeps, for nf=1: col of zeros; nf=2: (0, cb) == sorted[1:] since
-            # sorted = (0,0,cb) when cb<=1.  Values are what matters: the id multiset.
+            forced = [int(v) for v in table[t]] if t < S else []
             for g in range(G):
                 if n_sel >= S_sel:
                     ids = list(range(nvalid))
@@ -277,7 +289,8 @@ def select_ranges_prefill(p_grp: torch.Tensor, l_sel: int, n_sel: int, S: int, t
                     masked = p[b, tq, g].copy()
                     masked[nvalid:] = NEG_INF
                     for j in forced:
-                        masked[j] = NEG_INF
+                        if j < S_sel:
+                            masked[j] = NEG_INF
                     picks: List[int] = []
                     if k_rest > 0:
                         comp = _composite(masked)
@@ -298,6 +311,34 @@ def select_ranges_prefill(p_grp: torch.Tensor, l_sel: int, n_sel: int, S: int, t
     return torch.from_numpy(out)
 
 
+def indices_to_ranges(indices: torch.Tensor, S_sel: int, l_sel: int, t0: int = 0) -> torch.Tensor:
+    """convert_indices_to_ranges_batched (selection_scorer.py:380-431; v2 :434-605 gives the same runs, padded to K columns):
+    ids [B,S,G,K] ascending, negative = padding -> [B,S,G,K,2] int32."""
+    idx = indices.numpy()
+    B, S, G, K = idx.shape
+    out = np.zeros((B, S, G, K, 2), dtype=np.int32)
+    for b in range(B):
+        for s in range(S):
+            for g in range(G):
+                spans: List[List[int]] = []
+                prev = None
+                for bid in idx[b, s, g].tolist():
+                    if bid < 0 or bid >= S_sel or bid == prev:
+                        continue
+                    prev = bid
+                    s0 = bid * l_sel
+                    e0 = min(s0 + l_sel, t0 + s + 1)
+                    if e0 <= s0:
+                        continue
+                    if spans and spans[-1][1] == s0:
+                        spans[-1][1] = e0
+                    else:
+                        spans.append([s0, e0])
+                for i, (s0, e0) in enumerate(spans):
+                    out[b, s, g, i] = (s0, e0)
+    return torch.from_numpy(out)
+
+
 def nonempty_ranges(row: Sequence[Sequence[int]]) -> List[Tuple[int, int]]:
     """The reference's own equivalence criterion: ordered list of ranges with end > start
     (nsa/tests/test_selection_v2_equiv.py:80-111)."""
@@ -312,6 +353,42 @@ def ranges_equivalent(a: torch.Tensor, b: torch.Tensor) -> Tuple[bool, int]:
     assert len(A) == len(Bm)
     bad = sum(1 for ra, rb in zip(A, Bm) if nonempty_ranges(ra) != nonempty_ranges(rb))
     return bad == 0, bad
+
+
+def blocks_of_ranges(row: Sequence[Sequence[int]], l_sel: int) -> set:
+    """Selection-block ids covered by a row of [start, end) ranges (the last block of a range may be clamped)."""
+    out = set()
+    for s0, e0 in nonempty_ranges(row):
+        out.update(range(s0 // l_sel, (e0 + l_sel - 1) // l_sel))
+    return out
+
+
+def selection_difference_is_near_tie(p_row: torch.Tensor, row_a, row_b, l_sel: int, n_sel: int, t: int, delta: float,
+                                     mode: int = 0) -> bool:
+    """True when two selections of one row differ only by candidates whose fp32 composite lies within 2*delta of the cut (the
+    n-th best candidate of `p_row`): a scorer whose p_grp is within `delta` of p_row can order such candidates either way,
+    and no others.  mode 0 = prefill rule, 1 = decode rule (forced blocks {0, cb-1, cb} are never candidates)."""
+    a, b = blocks_of_ranges(row_a, l_sel), blocks_of_ranges(row_b, l_sel)
+    diff = a ^ b
+    if not diff:
+        return True
+    p = p_row.detach().float().numpy()
+    S_sel = p.shape[0]
+    nvalid = min((t + 1) // l_sel, S_sel)
+    cb = t // l_sel
+    forced = {0, cb, max(cb - 1, 0)}
+    masked = p.copy()
+    masked[nvalid:] = NEG_INF
+    for j in forced:
+        if j < S_sel:
+            masked[j] = NEG_INF
+    comp = _composite(masked)
+    k = min(max(n_sel - 3, 0), S_sel)
+    order = np.sort(comp)[::-1]
+    if k == 0 or k > order.shape[0] or not np.isfinite(order[k - 1]):
+        return False
+    cut = float(order[k - 1])
+    return all(j < S_sel and np.isfinite(comp[j]) and abs(float(comp[j]) - cut) <= 2.0 * delta + 1e-12 for j in diff)
 
 
 # ----------------------------------------------------------------------------------------

@@ -296,7 +296,79 @@ def gen_module():
     save("module", **arrs)
 
 
+def gen_free_functions():
+    """The reference's stage-by-stage free functions: selection with other force_init / force_local settings, p_cmp,
+    Eq.9 for several geometries, ids -> ranges, the one-query attention primitive."""
+    from nsa.core.block_index import build_block_meta
+    from nsa.core.selection_scorer import (compute_pcmp_all, convert_indices_to_ranges_batched, convert_indices_to_ranges_batched_v2,
+                                           map_pcmp_to_pslc, map_pcmp_to_pslc_batched, select_topn_ranges, select_topn_ranges_batched)
+    from nsa.kernels.flash_wrappers import attention_bgh
+
+    g = torch.Generator().manual_seed(23)
+    arrs = {}
+    flags = [(0, 0), (1, 0), (0, 1), (0, 2), (1, 1), (0, 3), (1, 2)]
+    i = 0
+    for (S_ctx, ls, n) in [(700, 64, 16), (300, 32, 8), (130, 64, 5), (64, 64, 16), (260, 32, 2)]:
+        meta = build_block_meta(S_ctx, ls // 2, ls // 4, ls, n, 512)
+        S_sel = meta.sel_starts.numel()
+        for (fi, fl) in flags:
+            for t in sorted({0, ls - 1, ls, 2 * ls, S_ctx // 2, S_ctx - 1}):
+                if t >= S_ctx:
+                    continue
+                p = torch.rand((1, 2, S_sel), generator=g)
+                arrs[f"dec_p{i}"], arrs[f"dec_r{i}"] = p, select_topn_ranges(p, meta, n, t, bool(fi), fl)
+                arrs[f"dec_c{i}"] = np.array([ls, n, t, fi, fl])
+                i += 1
+    arrs["dec_n"] = np.array(i)
+    i = 0
+    for (S, ls, n) in [(200, 64, 16), (40, 64, 16), (100, 64, 16), (128, 32, 8), (300, 32, 3), (192, 64, 2), (96, 32, 1), (640, 64, 10)]:
+        meta = build_block_meta(S, ls // 2, ls // 4, ls, n, 512)
+        S_sel = meta.sel_starts.numel()
+        for (fi, fl) in flags:
+            p = torch.rand((1, S, 2, S_sel), generator=g)
+            arrs[f"pre_p{i}"], arrs[f"pre_r{i}"] = p, select_topn_ranges_batched(p, meta, n, S, bool(fi), fl)
+            arrs[f"pre_c{i}"] = np.array([ls, n, S, fi, fl])
+            i += 1
+    arrs["pre_n"] = np.array(i)
+    # compute_pcmp_all (selection_scorer.py:42-61)
+    Q = torch.randn(2, 20, 2, 3, 16, generator=g)
+    Kc = torch.randn(2, 2, 9, 16, generator=g)
+    arrs["pcmp_Q"], arrs["pcmp_K"], arrs["pcmp_p"] = Q, Kc, compute_pcmp_all(Q, Kc, 1.0 / 4.0)
+    # Eq.9, several geometries (selection_scorer.py:64-116)
+    for k, (S, l, d, ls) in enumerate([(512, 32, 16, 64), (256, 16, 8, 32), (64, 4, 2, 4), (96, 8, 8, 16), (200, 32, 16, 64), (300, 64, 16, 64)]):
+        meta = build_block_meta(S, l, d, ls, 8, 64)
+        S_cmp = meta.cmp_starts.numel()
+        pc = torch.rand(1, 7, 2, 3, S_cmp, generator=g)
+        arrs[f"map_c{k}"] = np.array([S, l, d, ls])
+        arrs[f"map_p{k}"], arrs[f"map_o{k}"] = pc, map_pcmp_to_pslc_batched(pc, meta)
+        short = torch.rand(2, 2, 3, max(S_cmp - 3, 1), generator=g)  # fewer compressed rows than the map covers (early decode)
+        arrs[f"map_ps{k}"], arrs[f"map_os{k}"] = short, map_pcmp_to_pslc(short, meta)
+    arrs["map_n"] = np.array(6)
+    # ids -> ranges (selection_scorer.py:380-605)
+    for k, (B, S, G, K, ls, hi) in enumerate([(2, 8, 2, 12, 4, 16), (1, 40, 2, 16, 64, 12), (1, 1, 1, 5, 32, 4), (2, 16, 1, 32, 64, 40)]):
+        meta = build_block_meta(max(hi * ls, S), ls // 2, ls // 4, ls, 8, 64)
+        idx = torch.randint(-1, hi, (B, S, G, K), generator=g)
+        idx = torch.sort(torch.where(idx < 0, torch.full_like(idx, 10 ** 6), idx), dim=-1).values
+        idx = torch.where(idx == 10 ** 6, torch.full_like(idx, -1), idx)
+        arrs[f"i2r_c{k}"] = np.array([ls, meta.sel_starts.numel()])
+        arrs[f"i2r_i{k}"] = idx
+        arrs[f"i2r_v1_{k}"] = convert_indices_to_ranges_batched(idx, meta, S)
+        arrs[f"i2r_v2_{k}"] = convert_indices_to_ranges_batched_v2(idx, meta, S)
+    arrs["i2r_n"] = np.array(4)
+    # attention_bgh, all keys (flash_wrappers.py:191-282; causal=True with one query row is the degenerate first-key route, SURVEY F1)
+    q = torch.randn(2, 2, 3, 16, generator=g)
+    K = torch.randn(2, 2, 37, 16, generator=g)
+    V = torch.randn(2, 2, 37, 16, generator=g)
+    arrs["bgh_q"], arrs["bgh_K"], arrs["bgh_V"], arrs["bgh_O"] = q, K, V, attention_bgh(q, K, V, causal=False)
+    save("free_functions", **arrs)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:  # python tests/golden/make_golden.py free_functions [...]: regenerate only the named fixtures
+        for name in sys.argv[1:]:
+            globals()["gen_" + name]()
+        sys.exit(0)
+    gen_free_functions()
     gen_meta()
     gen_rope_phi()
     gen_scores()

@@ -246,14 +246,14 @@ def test_many_short_ranges_beyond_16_blocks_are_served_not_truncated():
             ranges[0, s, g, :, 1] = starts + 1
     cfg = ops.NSAConfig()
     assert ops.ranges_max_blocks(ranges.cuda(), S_kv) == K
-    want = O.sel_attention(Q, Kk, V, ranges)
+    want = O.sel_attention(Q, Kk, V, ranges)[0]
     dev = [t.cuda().bfloat16().requires_grad_(True) for t in (Q, Kk, V)]
     got = ops.branch_attention(ops.BR_SEL, *dev, cfg, ranges.cuda())
     assert (got.float().cpu() - want).abs().max() <= BF16_MAXABS
     dO = r16(*got.shape)
     (got.float() * dO.cuda()).sum().backward()
     cpu = [t.clone().requires_grad_(True) for t in (Q, Kk, V)]
-    (O.sel_attention(*cpu, ranges) * dO).sum().backward()
+    (O.sel_attention(*cpu, ranges)[0] * dO).sum().backward()
     for a, b in zip(dev, cpu):
         assert _rel(a.grad.float().cpu(), b.grad) <= 3e-2
     # ranges within the invariant stay on the tensor-core path and agree too

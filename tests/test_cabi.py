@@ -33,7 +33,7 @@ def test_invalid_arguments_return_codes_not_crashes():
     assert lib.nsa_prefill_range_cols(200, 64, 16) == 4      # 3 forced + min(13, 4) -> n >= S_sel -> S_sel
     assert lib.nsa_prefill_range_cols(2048, 64, 16) == 16
     assert lib.nsa_prefill_range_cols(40, 64, 16) == 1
-    rc = lib.nsa_select_ranges_prefill(None, 1, 1, 1, 4, 64, 16, 200, 0, 4, None, None)
+    rc = lib.nsa_select_ranges_prefill(None, 1, 1, 1, 4, 64, 16, 200, 0, 4, 1, 2, None, None)
     assert rc == -1 and b"NULL" in lib.nsa_last_error()
     dm = _lib.Dims()
     dm.B, dm.S, dm.G, dm.h, dm.Dk, dm.Dv = 1, 1, 1, 1, 16, 16

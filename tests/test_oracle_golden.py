@@ -199,3 +199,58 @@ def test_oracle_autograd_matches_reference_grads():
     for k, v in sd.items():
         ref = T(g["grad__" + k])
         assert torch.allclose(v.grad, ref, atol=2e-4, rtol=1e-3), (k, (v.grad - ref).abs().max())
+
+
+def decode_case_is_well_defined(S_sel, l_sel, n_sel, t, fi, fl):
+    """select_topn_ranges keeps picks that landed on -inf (future / incomplete) blocks; which -inf entry torch.topk returns is
+    unspecified, and without a forced local block such a pick can merge into a visible [cb*l_sel, t+1) range.  The rule is
+    defined when the current block is forced anyway (force_local >= 1) or enough finite candidates exist."""
+    if fl >= 1:
+        return True
+    nvalid = min((t + 1) // l_sel, S_sel)
+    forced_valid = 1 if (fi and nvalid > 0) else 0
+    return nvalid - forced_valid >= min(max(n_sel - fi - fl, 0), S_sel)
+
+
+def test_free_function_goldens_select_with_force_flags():
+    """select_topn_ranges(_batched) with every (force_init, force_local) the reference's callers and tests use."""
+    g = load_golden("free_functions")
+    checked = 0
+    for i in range(int(g["dec_n"])):
+        ls, ns, t, fi, fl = [int(v) for v in g[f"dec_c{i}"]]
+        if not decode_case_is_well_defined(g[f"dec_p{i}"].shape[-1], ls, ns, t, fi, fl):
+            continue
+        mine = O.select_ranges_decode(T(g[f"dec_p{i}"]), ls, ns, t, bool(fi), fl)
+        ok, bad = O.ranges_equivalent(mine, T(g[f"dec_r{i}"]))
+        assert ok, f"decode case {i} (l_sel={ls}, n={ns}, t={t}, force=({fi},{fl})): {bad} rows differ"
+        checked += 1
+    assert checked > 100
+    for i in range(int(g["pre_n"])):
+        ls, ns, S, fi, fl = [int(v) for v in g[f"pre_c{i}"]]
+        mine = O.select_ranges_prefill(T(g[f"pre_p{i}"]), ls, ns, S, 0, bool(fi), fl)
+        ref = T(g[f"pre_r{i}"])
+        assert mine.shape == ref.shape, f"prefill case {i} force=({fi},{fl}): K {mine.shape} vs {ref.shape}"
+        assert torch.equal(mine, ref), f"prefill case {i} (l_sel={ls}, n={ns}, S={S}, force=({fi},{fl}))"
+
+
+def test_free_function_goldens_pcmp_map_and_ranges():
+    g = load_golden("free_functions")
+    p = O.pcmp_all(T(g["pcmp_Q"]), T(g["pcmp_K"]), 0.25)
+    assert torch.allclose(p, T(g["pcmp_p"]), atol=1e-6)
+    for k in range(int(g["map_n"])):
+        S, l, d, ls = [int(v) for v in g[f"map_c{k}"]]
+        meta = O.build_meta(S, l, d, ls, 8, 64)
+        assert torch.allclose(O.pslc_from_pcmp(T(g[f"map_p{k}"]), meta), T(g[f"map_o{k}"]), atol=1e-6)
+        short = T(g[f"map_ps{k}"])
+        assert torch.allclose(O.pslc_from_pcmp(short[:, None], meta)[:, 0], T(g[f"map_os{k}"]), atol=1e-6)
+    for k in range(int(g["i2r_n"])):
+        ls, S_sel = [int(v) for v in g[f"i2r_c{k}"]]
+        mine = O.indices_to_ranges(T(g[f"i2r_i{k}"]), S_sel, ls)
+        # v2 leaves clamped-away runs as rows with end <= start; the criterion of the reference's own equivalence test
+        # (test_selection_v2_equiv.py:80-111) compares the non-empty ranges in order
+        for ref in (T(g[f"i2r_v2_{k}"]), T(g[f"i2r_v1_{k}"])):
+            ok, bad = O.ranges_equivalent(mine, ref)
+            assert ok, bad
+    q, K, V = T(g["bgh_q"]), T(g["bgh_K"]), T(g["bgh_V"])
+    o, _ = O._masked_attention(q[:, None], K, V, torch.ones(q.shape[0], 1, q.shape[1], K.shape[2], dtype=torch.bool))
+    assert torch.allclose(o[:, 0], T(g["bgh_O"]), atol=2e-6)

@@ -85,8 +85,28 @@ def test_score_tc_vs_oracle(dtype, norm, S, h, t0):
     # fused scoring + selection == standalone selection on the same scores; near-ties only vs the oracle's scores
     r = ops.score_select(Q.cuda().to(dtype), Kc.cuda().to(dtype), cfg_tc, mode=0).cpu()
     assert torch.equal(r, ops.select_ranges_prefill(got.cuda(), ls, n, S).cpu())
-    ok, bad = O.ranges_equivalent(r, O.select_ranges_prefill(want, ls, n, S))
-    assert bad <= max(2, B * S * G // 200), f"{bad} of {B * S * G} rows differ"
+    _assert_only_near_ties(r, O.select_ranges_prefill(want, ls, n, S), want, got, ls, n)
+
+
+def _assert_only_near_ties(r_gpu, r_oracle, p_oracle, p_gpu, l_sel, n_sel, t0=0, max_frac=0.005):
+    """The fused scoring + selection may differ from the selection on the oracle's fp32 scores ONLY where the scores tie within
+    the scorer's own error: every differing row is checked (O.selection_difference_is_near_tie with delta = that row's
+    max |p_grp_gpu - p_grp_oracle| over the columns the row can select), and such rows stay below max_frac of all rows."""
+    B, S, G = r_gpu.shape[:3]
+    bad = 0
+    for b in range(B):
+        for s in range(S):
+            for g in range(G):
+                if O.nonempty_ranges(r_gpu[b, s, g].tolist()) == O.nonempty_ranges(r_oracle[b, s, g].tolist()):
+                    continue
+                bad += 1
+                t = t0 + s
+                nv = min((t + 1) // l_sel, p_oracle.shape[-1])
+                delta = float((p_gpu[b, s, g, :nv] - p_oracle[b, s, g, :nv]).abs().max()) if nv else 0.0
+                assert O.selection_difference_is_near_tie(p_oracle[b, s, g], r_gpu[b, s, g].tolist(), r_oracle[b, s, g].tolist(), l_sel,
+                                                          n_sel, t, delta), (
+                    f"row (b={b}, t={t}, g={g}) selects different blocks and the scores do not tie within 2*{delta:.2e}")
+    assert bad <= max(2, int(B * S * G * max_frac)), f"{bad} of {B * S * G} rows differ"
 
 
 def test_score_tc_chunked_t0():
@@ -164,8 +184,8 @@ def test_prefill_core_all_tc_bf16_m7c():
     err = (Oc.float().cpu() - want["O"]).abs()
     assert err.max() <= 2e-2 and err.mean() <= 1e-3, (err.max(), err.mean())
     pg = O.prefill_scores(ts[0], ts[5], l, d, ls, n, w)
-    _, bad = O.ranges_equivalent(ranges.cpu(), O.select_ranges_prefill(pg, ls, n, S))
-    assert bad <= B * S * G // 200, bad
+    pg_gpu = ops.score_pgrp(ts[0].cuda().bfloat16(), ts[5].cuda().bfloat16(), cfg).cpu()
+    _assert_only_near_ties(ranges.cpu(), O.select_ranges_prefill(pg, ls, n, S), pg, pg_gpu, ls, n)
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
@@ -225,8 +245,7 @@ def test_score_tc_four_mtile_path(norm):
     assert torch.isfinite(got).all()
     assert (got - want).abs().max() <= 2e-5 * h, (got - want).abs().max()
     r = ops.score_select(Q.cuda().bfloat16(), Kc.cuda().bfloat16(), cfg, mode=0).cpu()
-    _, bad = O.ranges_equivalent(r, O.select_ranges_prefill(want, ls, n, S))
-    assert bad <= B * S * G // 200, bad
+    _assert_only_near_ties(r, O.select_ranges_prefill(want, ls, n, S), want, got, ls, n)
 
 
 def test_dense_tc_reference_jump():

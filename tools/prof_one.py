@@ -29,8 +29,8 @@ with torch.no_grad():
         elif what == "win":
             ops.branch_attention(ops.BR_WIN, Q, Kw, Vw, cfg)
         elif what == "sel2":
-            ops.sel_attention_blockmajor(Q, Ks, Vs, cfg, ranges)
+            ops.sel_attention_blockmajor(Q, Ks, Vs, cfg, ranges, ranges_trusted=True)
         else:
-            ops.branch_attention(ops.BR_SEL, Q, Ks, Vs, cfg, ranges)
+            ops.branch_attention(ops.BR_SEL, Q, Ks, Vs, cfg, ranges, ranges_trusted=True)
 torch.cuda.synchronize()
 print("ok")
