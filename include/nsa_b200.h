@@ -171,6 +171,29 @@ int nsa_decode_fwd(const nsa_dims_t* dm, const void* Q,
                    const void* K_cmp, const void* V_cmp, const nsa_gate_params_t* gp,
                    void* O, int32_t* ranges_out, void* workspace, void* stream);
 
+/* Device-resident record of a decode loop.  With it the three decode entry points (nsa_decode_produce, nsa_decode_emit,
+ * nsa_decode_fwd_stepped) read the position / row counts of the step from DEVICE memory and nsa_decode_advance moves them on, so
+ * a caller can capture one decode step in a CUDA graph and replay it with no host-side patching of arguments (the reference's
+ * decode loop is bench/bench_decode.py:123-136).  All caches must be slabs with spare capacity ([B,G,cap,D]). */
+typedef struct nsa_decode_state {
+  int32_t t;        /* position of the next token = rows present in K_sel / V_sel */
+  int32_t row_win;  /* rows present in the K_win / V_win slabs (their whole history; the window is the last w of them) */
+  int32_t row_raw;  /* rows present in the raw (pre-phi) K / V streams */
+  int32_t S_cmp;    /* compressed tokens present in K_cmp / V_cmp */
+  int32_t ctr_idx;  /* next column of the read-counter slab */
+  int32_t pad_[3];
+} nsa_decode_state_t;
+
+/* nsa_decode_fwd with t0, S_sel_kv, S_win_kv, win_off and S_cmp taken from the device record (after this step's produce + emit:
+ * t0 = state->t, S_sel_kv = t0 + 1, S_win_kv = row_win + 1, win_off = t0 + 1 - S_win_kv, S_cmp = state->S_cmp + emitted); the
+ * dims only carry the static geometry and the slab capacities.  Served by the fused tcgen05 decode kernel only: returns
+ * NSA_ERR_UNSUPPORTED when the shape / capacity has none (cap_sel <= 20480 tokens, compressed capacity <= 1024). */
+int nsa_decode_stepped_supported(const nsa_dims_t* dm);  /* 1 when nsa_decode_fwd_stepped serves these dims / capacities */
+int nsa_decode_fwd_stepped(const nsa_dims_t* dm, const void* Q,
+                           const void* K_sel, const void* V_sel, const void* K_win, const void* V_win,
+                           const void* K_cmp, const void* V_cmp, const nsa_gate_params_t* gp,
+                           void* O, int32_t* ranges_out, const nsa_decode_state_t* state, void* stream);
+
 /* ---- producers of the hot path's inputs ----------------------------------------------------------
  * RoPE (nsa/core/rope.py:16-51: interleaved pairs, angle = (pos / scale) * base^(-2i/dim) in fp32, sin/cos rounded to the
  * tensor's dtype) fused with the re-layout between the projection output [B,S,V,D] (layout 0) and the cache layout [B,V,S,D]
@@ -204,8 +227,27 @@ typedef struct nsa_decode_produce {
   float base, scale;
   int32_t dtype;
   int32_t S, inverse;
+  /* optional (S = 1): take t, row[] (= t, t, row_win, row_win, row_raw, row_raw), counters_idx and the counter values from this
+   * device record instead of the fields above; l, d, l_sel, n_sel, w then give the counter formula (nsa_attention.py:634-638) */
+  const nsa_decode_state_t* state;
+  int32_t l, d, l_sel, n_sel, w;
 } nsa_decode_produce_t;
 int nsa_decode_produce(const nsa_decode_produce_t* a, void* stream);
+
+/* Emission of a decode step (nsa_attention.py:587-604): with S_raw = state->row_raw + 1 raw tokens present, if S_raw >= l and
+ * (S_raw - l) % d == 0 the compressed token phi(raw rows [S_raw - l, S_raw)) (K with RoPE, compress_pool.py:9-38) is written to
+ * row state->S_cmp of the K_cmp / V_cmp slabs; otherwise nothing happens.  Runs after nsa_decode_produce of the same step. */
+typedef struct nsa_decode_emit {
+  const nsa_decode_state_t* state;
+  const void *K_raw, *V_raw;   /* [B,G,cap_raw,Dk|Dv] */
+  void *K_cmp, *V_cmp;         /* [B,G,cap_cmp,Dk|Dv] */
+  int32_t BG, cap_raw, cap_cmp, Dk, Dv, l, d;
+  float base, scale;
+  int32_t dtype;
+} nsa_decode_emit_t;
+int nsa_decode_emit(const nsa_decode_emit_t* a, void* stream);
+/* state += one step: t, row_win, row_raw, ctr_idx advance by one, S_cmp by one when this step emitted. */
+int nsa_decode_advance(nsa_decode_state_t* state, int l, int d, void* stream);
 
 /* ---- caller-side row kernels of the block around the hot path ---------------------------------------
  * RMSNorm (nsa/model/llama_block_nsa.py:13-22: y = x * rsqrt(mean(x^2) + eps) * w) fused with the residual add feeding it

@@ -41,7 +41,23 @@ class DecodeProduce(C.Structure):
     _fields_ = [("y", C.c_void_p), ("q_out", C.c_void_p), ("slab", C.c_void_p * 6), ("cap", C.c_int32 * 6), ("row", C.c_int32 * 6),
                 ("counters", C.c_void_p), ("counters_cap", C.c_int32), ("counters_idx", C.c_int32), ("counter_val", C.c_int64 * 5),
                 ("B", C.c_int32), ("H", C.c_int32), ("G", C.c_int32), ("Dk", C.c_int32), ("Dv", C.c_int32), ("t", C.c_int32),
-                ("base", C.c_float), ("scale", C.c_float), ("dtype", C.c_int32), ("S", C.c_int32), ("inverse", C.c_int32)]
+                ("base", C.c_float), ("scale", C.c_float), ("dtype", C.c_int32), ("S", C.c_int32), ("inverse", C.c_int32),
+                ("state", C.c_void_p), ("l", C.c_int32), ("d", C.c_int32), ("l_sel", C.c_int32), ("n_sel", C.c_int32), ("w", C.c_int32)]
+
+
+class DecodeState(C.Structure):
+    """struct nsa_decode_state (include/nsa_b200.h); lives in device memory, this mirror is for sizes and host-side initialisation."""
+
+    _fields_ = [("t", C.c_int32), ("row_win", C.c_int32), ("row_raw", C.c_int32), ("S_cmp", C.c_int32), ("ctr_idx", C.c_int32),
+                ("pad_", C.c_int32 * 3)]
+
+
+class DecodeEmit(C.Structure):
+    """struct nsa_decode_emit (include/nsa_b200.h)."""
+
+    _fields_ = [("state", C.c_void_p), ("K_raw", C.c_void_p), ("V_raw", C.c_void_p), ("K_cmp", C.c_void_p), ("V_cmp", C.c_void_p),
+                ("BG", C.c_int32), ("cap_raw", C.c_int32), ("cap_cmp", C.c_int32), ("Dk", C.c_int32), ("Dv", C.c_int32),
+                ("l", C.c_int32), ("d", C.c_int32), ("base", C.c_float), ("scale", C.c_float), ("dtype", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -79,6 +95,10 @@ SIGNATURES = {
     "nsa_rope_shape": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, C.c_float, C.c_float, _I, _I, _P]),
     "nsa_phi_avgpool": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, C.c_float, C.c_float, _I, _I, _P]),
     "nsa_decode_produce": (_I, [C.c_void_p, _P]),
+    "nsa_decode_emit": (_I, [C.c_void_p, _P]),
+    "nsa_decode_advance": (_I, [_P, _I, _I, _P]),
+    "nsa_decode_stepped_supported": (_I, [_DP]),
+    "nsa_decode_fwd_stepped": (_I, [_DP] + [_P] * 7 + [_GP] + [_P] * 4),
     "nsa_rmsnorm_fwd": (_I, [_P] * 6 + [_I, _I, C.c_float, _I, _I, _I, _I, _P]),
     "nsa_rmsnorm_bwd": (_I, [_P] * 8 + [_I, _I, _I, _I, _I, _P]),
     "nsa_rmsnorm_partials": (_I, [_I]),

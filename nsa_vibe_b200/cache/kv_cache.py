@@ -216,6 +216,12 @@ class NSA_KV:
             self._lens[name] += 1
             self._set_view(name)
 
+    def commit_compressed_append(self) -> None:
+        """One compressed token was written on the device into the next free row of the K_cmp / V_cmp slabs (nsa_decode_emit)."""
+        for name in ("K_cmp", "V_cmp"):
+            self._lens[name] += 1
+            self._set_view(name)
+
     def counter_slot(self):
         """([5,cap] int64 slab, column) where the next step's read counters go (rows ordered as _COUNTER_FIELDS); the five
         public tensors become views of it.  commit_counters() publishes the column."""

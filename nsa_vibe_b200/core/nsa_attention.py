@@ -126,6 +126,9 @@ class NSAAttention(nn.Module):
             "pcmp_norm": os.getenv("NSA_PCMP_NORM", "full_row").strip().lower(),  # B200 addition
             # selection_scorer.py:46-56: score fp32 activations with bf16 operands (here: the tcgen05 scorer, fp32 accumulation)
             "pcmp_mixed": os.getenv("NSA_P_CMP_MIXED", "0").lower() in ("1", "true", "yes", "on"),
+            # B200 addition: replay the decode step as a CUDA graph (ops.DecodeGraphStep) when the fused tcgen05 decode kernel serves
+            # the shape; NSA_DECODE_GRAPH=0 keeps the eager step
+            "decode_graph": _env_true("NSA_DECODE_GRAPH", "1"),
         }
         try:
             rs = float(os.getenv("NSA_ROPE_SCALE", "1.0"))
@@ -299,12 +302,86 @@ class NSAAttention(nn.Module):
         return ops.DecodeStepPlan(y, slabs, cmp_slabs, ctr, H=self.n_heads, G=self.n_kv_groups, Dk=self.d_k, Dv=self.d_v, cfg=cfg,
                                   gate=gate, rope_scale=self.rope_scale)
 
+    # ---- decode as a replayed CUDA graph ----------------------------------------------------------------------------
+    def _graph_step(self, x: torch.Tensor, kv: NSA_KV, aux: bool):
+        """The captured decode step of this module on `kv` (ops.DecodeGraphStep), or None when the shape has no fused tcgen05 decode
+        kernel (fp32, other head dims, capacities beyond the fused scorer): those run the eager step.  Rebuilt (re-captured) when a
+        cache slab was reallocated or replaced, the batch / dtype changed, or a weight / gate / rope setting moved."""
+        ws = self._proj_weights()
+        cfg_key = (float(self.gate_temp), self.gate.mode(), float(self.rope_scale), aux, x.dtype, x.shape[0],
+                   tuple((p.data_ptr(), p._version) for p in (*self.gate.params(), *ws, self.out.weight)))
+        ent = getattr(kv, "_decode_graph", None)
+        if ent is not None and ent[0] is self and ent[1] == cfg_key:
+            gs = ent[2]
+            if gs is None:
+                return None
+            if kv.decode_state(gs.slabs, gs.cmp_slabs, gs.counters if aux else None) is not None:
+                # an emission needs a free row in the compressed slabs
+                if kv.rows_present("K_cmp") < gs.cmp_slabs[0].shape[2]:
+                    return gs
+        like = torch.empty((x.shape[0], 1), dtype=x.dtype, device=x.device)
+        slabs, _, cmp_slabs, ctr = kv.prepare_decode(like, aux)
+        # room to run: re-capturing every few steps would cost more than the graph saves
+        need = max(int(kv.rows_present("K_sel")) + 256, 2 * self.l_sel)
+        if any(s.shape[2] < kv.rows_present(n) + 64 for s, n in zip(slabs, kv._TOKEN_FIELDS)) or cmp_slabs[0].shape[2] < kv.rows_present("K_cmp") + 8:
+            kv.reserve(need)
+            slabs, _, cmp_slabs, ctr = kv.prepare_decode(like, aux)
+        cfg = self._cfg()
+        gate = self.gate.params() if cfg.gate_mode == ops.GATE_MLP else None
+        hid = int(self.gate.fc1.weight.shape[0]) if gate is not None else 0
+        gs = None
+        if ops.DecodeGraphStep.supported(x, slabs, cmp_slabs, cfg, H=self.n_heads, G=self.n_kv_groups, Dk=self.d_k, Dv=self.d_v,
+                                         gate_hidden=hid):
+            gs = ops.DecodeGraphStep(x.reshape(x.shape[0], self.dim), self._decode_weights(), self.out.weight.detach(), slabs, cmp_slabs,
+                                     ctr, H=self.n_heads, G=self.n_kv_groups, Dk=self.d_k, Dv=self.d_v, cfg=cfg, gate=gate,
+                                     rope_scale=self.rope_scale)
+            st = (kv.rows_present("K_sel"), kv.rows_present("K_win"), kv.rows_present("K_cmp_raw_seq"), kv.rows_present("K_cmp"),
+                  kv.counter_column() if aux else 0)
+            gs.set_state(*st)
+            gs.capture()
+            gs.set_state(*st)
+        kv._decode_graph = (self, cfg_key, gs)
+        return gs
+
+    def _forward_decode_graph(self, x: torch.Tensor, kv: NSA_KV, gs, aux: bool) -> tuple[torch.Tensor, NSA_KV]:
+        B = x.shape[0]
+        t, row_win, row_raw = kv.rows_present("K_sel"), kv.rows_present("K_win"), kv.rows_present("K_cmp_raw_seq")
+        st = (t, row_win, row_raw, kv.rows_present("K_cmp"), kv.counter_column() if aux else 0)
+        if gs.expected != st:  # the cache moved without us (a prefill in between, another module): re-seed the device record
+            gs.set_state(*st)
+        gs.x.copy_(x.reshape(B, self.dim))
+        gs.replay()
+        # mirror the step in the host bookkeeping while the GPU runs
+        S_raw = row_raw + 1
+        emitted = S_raw >= self.l and (S_raw - self.l) % self.d == 0
+        kv.commit_token_append(self.w)
+        if aux:
+            kv.commit_counters()
+        if emitted:
+            kv.commit_compressed_append()
+        gs.expected = (t + 1, row_win + 1, row_raw + 1, st[3] + (1 if emitted else 0), st[4] + (1 if aux else 0))
+        if not aux:
+            gs.expected = gs.expected[:4] + (0,)
+            gs.state_host[4] = 0
+        if getattr(kv, "meta", None) is None or kv.meta.sel_starts.numel() * self.l_sel < t + 1 or kv.meta.sel_starts.numel() == 0:
+            kv.meta = build_block_meta(seq_len=max(t + 1, self.l_sel), l=self.l, d=self.d, l_sel=self.l_sel, n_sel=self.n_sel, w=self.w)
+        self._last_ranges = gs.ranges
+        return gs.out.clone(), kv
+
     def _forward_decode(self, x: torch.Tensor, kv: NSA_KV) -> tuple[torch.Tensor, NSA_KV]:
         """One decode step (nsa_attention.py:545-976): one GEMM for the seven projections, one kernel that rotates Q/K and writes
         the token's six cache rows in place (nsa_decode_produce), phi on emission steps, the fused decode kernel, the out GEMM.
-        The two C-ABI calls go through a per-cache DecodeStepPlan (argument blocks built once, scalars updated per step)."""
+        Where the fused tcgen05 decode kernel serves the shape the whole step is ONE replayed CUDA graph driven by a device-side
+        step record (ops.DecodeGraphStep); otherwise the two C-ABI calls go through a per-cache DecodeStepPlan (argument blocks
+        built once, scalars updated per step)."""
         B = x.shape[0]
         G = self.n_kv_groups
+        if self._env_cache["decode_graph"] and not self._env_cache["strict_asserts"] and x.dtype in (torch.bfloat16, torch.float16):
+            with torch.no_grad():
+                aux = not self._env_cache["disable_aux_stats"]
+                gs = self._graph_step(x, kv, aux)
+                if gs is not None:
+                    return self._forward_decode_graph(x, kv, gs, aux)
         with torch.no_grad():
             y = F.linear(x.reshape(B, self.dim), self._decode_weights())
             aux = not self._env_cache["disable_aux_stats"]

@@ -317,6 +317,39 @@ int nsa_decode_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, const
   return launch_fwd_generic(*dm, a, (cudaStream_t)stream);
 }
 
+int nsa_decode_fwd_stepped(const nsa_dims_t* dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
+                           const void* V_win, const void* K_cmp, const void* V_cmp, const nsa_gate_params_t* gp, void* O,
+                           int32_t* ranges_out, const nsa_decode_state_t* state, void* stream) {
+  NSA_REQUIRE(dm && state, "decode_fwd_stepped: NULL dims / state");
+  nsa_dims_t d2 = *dm;  // rows present are read from the device record: validate the static geometry against the capacities
+  d2.S_sel_kv = d2.cap_sel; d2.S_win_kv = d2.cap_win; d2.S_cmp = d2.cap_cmp; d2.t0 = 0; d2.win_off = 0;
+  if (int rc = validate_dims(&d2, "decode_fwd_stepped")) return rc;
+  NSA_REQUIRE(dm->S == 1, "decode_fwd_stepped: decode requires S == 1, got S=%d", dm->S);
+  NSA_REQUIRE(Q && O && gp && K_sel && V_sel && K_win && V_win && K_cmp && V_cmp, "decode_fwd_stepped: NULL pointer");
+  NSA_REQUIRE(dm->n_ranges == dm->n_sel, "decode_fwd_stepped: dims.n_ranges must equal n_sel");
+  if (!tc_decode_stepped_supported(d2)) {
+    set_error("decode_fwd_stepped: no fused tcgen05 decode kernel for this shape / capacity");
+    return NSA_ERR_UNSUPPORTED;
+  }
+  return launch_decode_tc_stepped(d2, Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, *gp, O, ranges_out, state, (cudaStream_t)stream);
+}
+
+int nsa_decode_stepped_supported(const nsa_dims_t* dm) {
+  if (!dm || dm->S != 1 || dm->n_ranges != dm->n_sel) return 0;
+  nsa_dims_t d2 = *dm;
+  d2.S_sel_kv = d2.cap_sel; d2.S_win_kv = d2.cap_win; d2.S_cmp = d2.cap_cmp; d2.t0 = 0; d2.win_off = 0;
+  return tc_eligible(d2) && tc_decode_stepped_supported(d2) ? 1 : 0;
+}
+
+int nsa_decode_emit(const nsa_decode_emit_t* a, void* stream) {
+  NSA_REQUIRE(a, "decode_emit: NULL argument block");
+  return launch_decode_emit(*a, (cudaStream_t)stream);
+}
+
+int nsa_decode_advance(nsa_decode_state_t* state, int l, int d, void* stream) {
+  return launch_decode_advance(state, l, d, (cudaStream_t)stream);
+}
+
 int nsa_rope_shape(const void* x, void* y, int B, int S, int V, int D, int src_layout, int dst_layout, int rot_dim, int t0,
                    float base, float scale, int inverse, int dtype, void* stream) {
   NSA_REQUIRE(dtype == NSA_F32 || dtype == NSA_BF16 || dtype == NSA_F16, "rope_shape: dtype %d", dtype);

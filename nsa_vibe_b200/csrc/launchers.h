@@ -51,6 +51,8 @@ int launch_rope_shape(const void* x, void* y, int B, int S, int V, int D, int sr
 int launch_phi_avgpool(const void* x, void* y, int BG, int S, int D, int l, int d, int rope, int t0, float base, float scale,
                        int backward, int dtype, cudaStream_t stream);
 int launch_decode_produce(const nsa_decode_produce_t& a, cudaStream_t stream);
+int launch_decode_emit(const nsa_decode_emit_t& a, cudaStream_t stream);
+int launch_decode_advance(nsa_decode_state_t* state, int l, int d, cudaStream_t stream);
 // stats.cu
 int launch_stats(const float* gates, long long n_gate_rows, const int32_t* ranges, long long n_range_rows, int K, int32_t* row_len,
                  nsa_stats_t* out, cudaStream_t stream);
@@ -83,5 +85,9 @@ int launch_branch_tc(const nsa_dims_t& dm, int branch, const void* Q, const void
 int launch_decode_tc(const nsa_dims_t& dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
                      const void* V_win, const void* K_cmp, const void* V_cmp, const nsa_gate_params_t& gp, void* O,
                      int32_t* ranges_out, void* workspace, cudaStream_t stream);
+bool tc_decode_stepped_supported(const nsa_dims_t& dm);
+int launch_decode_tc_stepped(const nsa_dims_t& dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
+                             const void* V_win, const void* K_cmp, const void* V_cmp, const nsa_gate_params_t& gp, void* O,
+                             int32_t* ranges_out, const nsa_decode_state_t* state, cudaStream_t stream);
 
 }  // namespace nsa

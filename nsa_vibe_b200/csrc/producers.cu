@@ -235,8 +235,23 @@ decode_produce_kernel(DecodeProduceArgs a, int rows) {
   const int QW = a.H * a.Dk;
   const int N = QW + a.G * (3 * a.Dk + 3 * a.Dv);
   const int pairs = N / 2;
-  if (a.counters && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x < 5)
-    a.counters[(size_t)threadIdx.x * a.counters_cap + a.counters_idx] = a.counter_val[threadIdx.x];
+  // device-stepped decode (CUDA-graph replay): position, rows and counters come from the device record
+  int t_pos = a.t, ctr_idx = a.counters_idx, r_sel = 0, r_win = 0, r_raw = 0;
+  const bool stepped = a.state != nullptr;
+  if (stepped) {
+    t_pos = a.state->t; r_sel = t_pos; r_win = a.state->row_win; r_raw = a.state->row_raw; ctr_idx = a.state->ctr_idx;
+  }
+  if (a.counters && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x < 5 && ctr_idx < a.counters_cap) {
+    long long v = a.counter_val[threadIdx.x];
+    if (stepped) {  // nsa_attention.py:634-638 / kv_cache.py:51-65: (pred, total, sel, cmp, win)
+      const int S_raw = r_raw + 1;
+      const long long nc = S_raw < a.l ? 0 : (S_raw - a.l) / a.d + 1;
+      const long long nw = S_raw < a.w ? S_raw : a.w;
+      const long long ns = (long long)a.n_sel * a.l_sel;
+      v = threadIdx.x <= 1 ? nc + ns + nw : (threadIdx.x == 2 ? ns : (threadIdx.x == 3 ? nc : nw));
+    }
+    a.counters[(size_t)threadIdx.x * a.counters_cap + ctr_idx] = v;
+  }
   const int pc = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.z;
   if (pc >= pairs) return;
@@ -264,7 +279,9 @@ decode_produce_kernel(DecodeProduceArgs a, int rows) {
       rot_pair = e / 2;
       rot_dim = D;
     }
-    other = reinterpret_cast<T*>(a.slab[seg]) + (((size_t)b * a.G + g) * a.cap[seg] + a.row[seg]) * D + e;
+    const int row_seg = stepped ? (seg < 2 ? r_sel : (seg < 4 ? r_win : r_raw)) : a.row[seg];
+    if (row_seg + a.S > a.cap[seg]) return;  // a stepped loop that outran its slabs writes nothing (the host re-plans before that)
+    other = reinterpret_cast<T*>(a.slab[seg]) + (((size_t)b * a.G + g) * a.cap[seg] + row_seg) * D + e;
     other_pitch = D;
   }
   // ATen divides a tensor by a scalar as a multiplication by its fp32 reciprocal: mirrored (see rope_shape_kernel)
@@ -289,7 +306,7 @@ decode_produce_kernel(DecodeProduceArgs a, int rows) {
         float y0 = x0[u], y1 = x1[u];
         if (rot_dim > 0) {
           float sn, cs;
-          sincosf(__fmul_rn(__fmul_rn((float)(a.t + s), inv_scale), inv_freq), &sn, &cs);
+          sincosf(__fmul_rn(__fmul_rn((float)(t_pos + s), inv_scale), inv_freq), &sn, &cs);
           rope_rotate<T>(x0[u], x1[u], PrT<T>::rnd(sn), PrT<T>::rnd(cs), a.inverse != 0, y0, y1);
         }
         T* dst = a.inverse ? yp + (size_t)s * N : other + (size_t)s * other_pitch;
@@ -302,11 +319,12 @@ int launch_decode_produce(const nsa_decode_produce_t& a, cudaStream_t stream) {
   const int dtype = a.dtype;
   NSA_REQUIRE(a.y && a.q_out, "produce: NULL pointer");
   NSA_REQUIRE(a.S >= 1, "produce: S=%d", a.S);
+  NSA_REQUIRE(!a.state || (a.S == 1 && !a.inverse && a.l >= 1 && a.d >= 1), "produce: a device step record needs S = 1, forward, l, d");
   for (int i = 0; i < 6; ++i)
-    NSA_REQUIRE(a.slab[i] && a.row[i] >= 0 && a.row[i] + a.S <= a.cap[i], "produce: slab %d rows [%d, %d) cap %d", i, a.row[i],
-                a.row[i] + a.S, a.cap[i]);
+    NSA_REQUIRE(a.slab[i] && (a.state || (a.row[i] >= 0 && a.row[i] + a.S <= a.cap[i])), "produce: slab %d rows [%d, %d) cap %d", i,
+                a.row[i], a.row[i] + a.S, a.cap[i]);
   NSA_REQUIRE(a.B >= 0 && a.H >= 1 && a.G >= 1 && a.Dk >= 2 && a.Dv >= 2 && a.Dk % 2 == 0 && a.Dv % 2 == 0, "produce: bad geometry");
-  NSA_REQUIRE(!a.counters || (a.counters_idx >= 0 && a.counters_idx < a.counters_cap), "produce: counter index");
+  NSA_REQUIRE(!a.counters || a.state || (a.counters_idx >= 0 && a.counters_idx < a.counters_cap), "produce: counter index");
   if (a.B == 0) return NSA_OK;
   DecodeProduceArgs b = a;
   if (!(b.scale > 0.f)) b.scale = 1.0f;
@@ -320,6 +338,73 @@ int launch_decode_produce(const nsa_decode_produce_t& a, cudaStream_t stream) {
   else if (dtype == NSA_BF16) decode_produce_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(b, rows);
   else decode_produce_kernel<__half><<<grid, 256, 0, stream>>>(b, rows);
   return check_launch("decode_produce_kernel");
+}
+
+// ---- device-stepped decode: emission and state advance ---------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+decode_emit_kernel(nsa_decode_emit_t a) {
+  const int S_raw = a.state->row_raw + 1;
+  if (S_raw < a.l || (S_raw - a.l) % a.d != 0) return;  // not an emission step (nsa_attention.py:587-588)
+  const int c_row = a.state->S_cmp;
+  if (c_row >= a.cap_cmp || S_raw > a.cap_raw) return;
+  const int s0 = S_raw - a.l;
+  const int hk = a.Dk / 2, hv = a.Dv / 2;
+  const long long n = (long long)a.BG * (hk + hv);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int bg = (int)(i / (hk + hv));
+    int p = (int)(i - (long long)bg * (hk + hv));
+    const bool is_k = p < hk;
+    if (!is_k) p -= hk;
+    const int D = is_k ? a.Dk : a.Dv;
+    const T* x = reinterpret_cast<const T*>(is_k ? a.K_raw : a.V_raw) + ((size_t)bg * a.cap_raw + s0) * D + 2 * p;
+    float a0 = 0.f, a1 = 0.f;
+    for (int k = 0; k < a.l; ++k) {  // same arithmetic as phi_avgpool_fwd_kernel: the window at absolute positions s0 .. s0 + l - 1
+      float v0 = PrT<T>::ld(x + (size_t)k * D), v1 = PrT<T>::ld(x + (size_t)k * D + 1);
+      if (is_k) {
+        float sn, cs, w0, w1;
+        rope_sincos<T>(s0 + k, p, D, a.base, a.scale, sn, cs);
+        rope_rotate<T>(v0, v1, sn, cs, false, w0, w1);
+        v0 = w0;
+        v1 = w1;
+      }
+      a0 = __fadd_rn(a0, v0);
+      a1 = __fadd_rn(a1, v1);
+    }
+    T* out = reinterpret_cast<T*>(is_k ? a.K_cmp : a.V_cmp) + ((size_t)bg * a.cap_cmp + c_row) * D + 2 * p;
+    PrT<T>::st(out, __fdiv_rn(a0, (float)a.l));
+    PrT<T>::st(out + 1, __fdiv_rn(a1, (float)a.l));
+  }
+}
+
+int launch_decode_emit(const nsa_decode_emit_t& a0, cudaStream_t stream) {
+  nsa_decode_emit_t a = a0;
+  NSA_REQUIRE(a.state && a.K_raw && a.V_raw && a.K_cmp && a.V_cmp, "decode_emit: NULL pointer");
+  NSA_REQUIRE(a.BG >= 0 && a.l >= 1 && a.d >= 1 && a.Dk >= 2 && a.Dv >= 2 && a.Dk % 2 == 0 && a.Dv % 2 == 0, "decode_emit: bad geometry");
+  NSA_REQUIRE(a.dtype == NSA_F32 || a.dtype == NSA_BF16 || a.dtype == NSA_F16, "decode_emit: dtype %d", a.dtype);
+  if (a.BG == 0) return NSA_OK;
+  if (!(a.scale > 0.f)) a.scale = 1.0f;
+  const int blocks = pr_blocks((long long)a.BG * (a.Dk / 2 + a.Dv / 2));
+  if (a.dtype == NSA_F32) decode_emit_kernel<float><<<blocks, 256, 0, stream>>>(a);
+  else if (a.dtype == NSA_BF16) decode_emit_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(a);
+  else decode_emit_kernel<__half><<<blocks, 256, 0, stream>>>(a);
+  return check_launch("decode_emit_kernel");
+}
+
+__global__ void decode_advance_kernel(nsa_decode_state_t* st, int l, int d) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int S_raw = st->row_raw + 1;
+  if (S_raw >= l && (S_raw - l) % d == 0) st->S_cmp += 1;
+  st->t += 1;
+  st->row_win += 1;
+  st->row_raw += 1;
+  st->ctr_idx += 1;
+}
+
+int launch_decode_advance(nsa_decode_state_t* state, int l, int d, cudaStream_t stream) {
+  NSA_REQUIRE(state && l >= 1 && d >= 1, "decode_advance: bad arguments");
+  decode_advance_kernel<<<1, 32, 0, stream>>>(state, l, d);
+  return check_launch("decode_advance_kernel");
 }
 
 }  // namespace nsa

@@ -84,7 +84,8 @@ bool tc_dense_supported(const nsa_dims_t& dm, int branch);
 bool tc_gather_supported(const nsa_dims_t& dm, int branch_mask);
 int launch_gather_tc(const nsa_dims_t& dm, int branch_mask, const void* Q, const void* const* K, const void* const* V,
                      const int32_t* ranges, void* const* O_br, float* const* lse, const float* gates, void* O,
-                     const nsa_gate_params_t* gp_fuse, int S_sel, int32_t* ranges_out, cudaStream_t stream);
+                     const nsa_gate_params_t* gp_fuse, int S_sel, int32_t* ranges_out, cudaStream_t stream,
+                     const nsa_decode_state_t* state = nullptr);
 bool tc_gather_fuse_supported(const nsa_dims_t& dm, int S_sel);
 int launch_dense_tc(const nsa_dims_t& dm, int branch, const void* Q, const void* K, const void* V, void* O, float* lse,
                     cudaStream_t stream);
@@ -119,6 +120,24 @@ int launch_decode_tc(const nsa_dims_t& dm, const void* Q, const void* K_sel, con
   if (int rc = launch_score_generic(d2, Q, K_cmp, S_sel, t + 1, 1, dm.n_sel, nullptr, ranges, stream)) return rc;
   if (int rc = launch_gate_fwd(dm, Q, gp, gates, stream)) return rc;
   return launch_gather_tc(dm, 7, Q, Ks, Vs, ranges, nullptr, nullptr, gates, O, nullptr, 0, nullptr, stream);
+}
+
+// Device-stepped decode (CUDA-graph replay): the kernel reads position and row counts from the device record, so everything is
+// validated against the slab CAPACITIES here: the fused scorer ranks <= kGMaxSel selection blocks and <= 1024 compressed keys.
+bool tc_decode_stepped_supported(const nsa_dims_t& dm) {
+  if (dm.S != 1 || dm.cap_sel < 1 || dm.cap_win < 1 || dm.cap_cmp < 1) return false;
+  nsa_dims_t d2 = dm;
+  d2.S_sel_kv = dm.cap_sel; d2.S_win_kv = dm.cap_win; d2.S_cmp = dm.cap_cmp; d2.t0 = dm.cap_sel - 1;
+  const int S_sel_max = ceil_div(dm.cap_sel > dm.l_sel ? dm.cap_sel : dm.l_sel, dm.l_sel);
+  return tc_gather_fuse_supported(d2, S_sel_max);
+}
+
+int launch_decode_tc_stepped(const nsa_dims_t& dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
+                             const void* V_win, const void* K_cmp, const void* V_cmp, const nsa_gate_params_t& gp, void* O,
+                             int32_t* ranges_out, const nsa_decode_state_t* state, cudaStream_t stream) {
+  const void* Ks[3] = {K_cmp, K_sel, K_win};
+  const void* Vs[3] = {V_cmp, V_sel, V_win};
+  return launch_gather_tc(dm, 7, Q, Ks, Vs, nullptr, nullptr, nullptr, nullptr, O, &gp, 1, ranges_out, stream, state);
 }
 
 int launch_branch_tc(const nsa_dims_t& dm, int branch, const void* Q, const void* K, const void* V, const int32_t* ranges,

@@ -79,6 +79,7 @@ struct GatherArgs {
   int S_sel;
   nsa_gate_params_t gp;
   int32_t* ranges_out;  // [rows][n_sel][2] (may be NULL)
+  const nsa_decode_state_t* state;  // device-stepped decode: t0 / rows present come from here (CUDA-graph replay), else NULL
   long long* dbg;       // debug timeline of CTA 0 (NSA_B200_GATHER_DBG=1), else NULL
 };
 
@@ -116,6 +117,16 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   GMisc* ms = reinterpret_cast<GMisc*>(smem + GSmem::misc);
   uint8_t* ring = smem + GSmem::ring;
+  if (a.state) {  // device-stepped decode: the step's position and row counts (after this step's produce + emit) live on the device
+    const int t = a.state->t, S_raw = a.state->row_raw + 1;
+    dm.t0 = t;
+    dm.S_sel_kv = t + 1;
+    dm.S_win_kv = a.state->row_win + 1;
+    dm.win_off = t + 1 - dm.S_win_kv;
+    dm.S_cmp = a.state->S_cmp + ((S_raw >= dm.l && (S_raw - dm.l) % dm.d == 0) ? 1 : 0);
+    const int cover = t + 1 > dm.l_sel ? t + 1 : dm.l_sel;  // meta covers max(t+1, l_sel) tokens (nsa_attention.py:609-632)
+    a.S_sel = ceil_div(cover, dm.l_sel);
+  }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = dm.h;
 
@@ -634,7 +645,9 @@ static int launch_gather_t(const nsa_dims_t& dm, const GatherPtrs& kv, GatherArg
   CUtensorMap tm[6];
   memset(tm, 0, sizeof(tm));
   const int slabs = dm.B * dm.G;
-  const int rows[3] = {dm.S_cmp, dm.S_sel_kv, dm.S_win_kv};
+  // stepped decode: the maps are baked into a CUDA graph, so they bound the slab capacity; rows past the ones present are
+  // masked by their counts inside the kernel (slabs are zero-initialised / hold finite stale rows)
+  const int rows[3] = {a.state ? dm.cap_cmp : dm.S_cmp, a.state ? dm.cap_sel : dm.S_sel_kv, a.state ? dm.cap_win : dm.S_win_kv};
   const long long caps[3] = {dm.cap_cmp, dm.cap_sel, dm.cap_win};
   for (int br = 0; br < 3; ++br) {
     if (!(a.branch_mask & (1 << br))) continue;
@@ -685,7 +698,8 @@ bool tc_gather_fuse_supported(const nsa_dims_t& dm, int S_sel) {
 // gp_fuse != NULL: fused decode step (scoring + selection + gate inside the kernel; `ranges`/`gates` are ignored).
 int launch_gather_tc(const nsa_dims_t& dm, int branch_mask, const void* Q, const void* const* K, const void* const* V,
                      const int32_t* ranges, void* const* O_br, float* const* lse, const float* gates, void* O,
-                     const nsa_gate_params_t* gp_fuse, int S_sel, int32_t* ranges_out, cudaStream_t stream) {
+                     const nsa_gate_params_t* gp_fuse, int S_sel, int32_t* ranges_out, cudaStream_t stream,
+                     const nsa_decode_state_t* state) {
   static_assert(sizeof(GMisc) <= 1280, "GMisc must fit its slot");
   if (dm.B * dm.S * dm.G == 0 || branch_mask == 0) return NSA_OK;
   NSA_REQUIRE((long long)dm.B * dm.S * dm.G < (1LL << 31), "gather(tc): B*S*G must be below 2^31");
@@ -698,7 +712,8 @@ int launch_gather_tc(const nsa_dims_t& dm, int branch_mask, const void* Q, const
   a.O = O;
   a.branch_mask = branch_mask;
   if (gp_fuse) {
-    NSA_REQUIRE(branch_mask == 7 && tc_gather_fuse_supported(dm, S_sel) && O, "gather(tc): fused decode step not available for this shape");
+    NSA_REQUIRE(branch_mask == 7 && (state || tc_gather_fuse_supported(dm, S_sel)) && O, "gather(tc): fused decode step not available for this shape");
+    a.state = state;
     a.fuse = 1;
     a.S_sel = S_sel;
     a.gp = *gp_fuse;

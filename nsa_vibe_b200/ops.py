@@ -673,6 +673,104 @@ class DecodeStepPlan:
         return self.O
 
 
+class DecodeGraphStep:
+    """One module-level decode step -- projection GEMM, nsa_decode_produce, nsa_decode_emit, nsa_decode_fwd_stepped, output GEMM,
+    nsa_decode_advance -- captured ONCE in a CUDA graph and replayed per token with no host-side argument patching: position and
+    row counts live in a device record (nsa_decode_state_t) that the last kernel of the step advances.  The reference's loop is
+    bench/bench_decode.py:123-136 (an eager Python step: ~150 us of host time against ~125 us of GPU time at S=4096, B=592).
+    The host only copies the token in, replays, and mirrors the bookkeeping (cache lengths) in Python while the GPU runs."""
+
+    KERNELS_PER_REPLAY = 4  # produce, emit, fused decode, advance (+ two cuBLAS GEMMs)
+
+    def __init__(self, x_like: torch.Tensor, W_cat: torch.Tensor, W_out: torch.Tensor, slabs, cmp_slabs, counters, *, H: int, G: int,
+                 Dk: int, Dv: int, cfg: NSAConfig, gate, rope_scale: float):
+        _require_cuda(x_like, W_cat, W_out, *slabs, *cmp_slabs)
+        B, dim = x_like.shape[0], x_like.shape[-1]
+        dev, dt = x_like.device, x_like.dtype
+        h = H // G
+        self.B, self.dim, self.H, self.G, self.h, self.Dk, self.Dv, self.cfg = B, dim, H, G, h, Dk, Dv, cfg
+        self.N = H * Dk + G * (3 * Dk + 3 * Dv)
+        self.W_cat, self.W_out = W_cat, W_out
+        self.slabs, self.cmp_slabs, self.counters = tuple(slabs), tuple(cmp_slabs), counters
+        self.x = torch.zeros((B, dim), dtype=dt, device=dev)
+        self.Q = torch.empty((B, 1, G, h, Dk), dtype=dt, device=dev)
+        self.O = torch.empty((B, 1, G, h, Dv), dtype=dt, device=dev)
+        self.ranges = torch.zeros((B, G, cfg.n_sel, 2), dtype=torch.int32, device=dev)
+        self.state = torch.zeros(8, dtype=torch.int32, device=dev)          # nsa_decode_state_t
+        self.state_host = torch.zeros(8, dtype=torch.int32).pin_memory()
+        self.expected = None                                                 # host mirror of the device record (tuple of 5 ints)
+        self.out = None                                                      # [B,1,dim], allocated inside the captured region
+        self.gate_keep = _gate_struct(gate, dev)
+        gp, _, hid = self.gate_keep
+        a = _lib.DecodeProduce()
+        a.q_out = self.Q.data_ptr()
+        for i, sl in enumerate(self.slabs):
+            a.slab[i], a.cap[i] = sl.data_ptr(), int(sl.shape[2])
+        if counters is not None:
+            a.counters, a.counters_cap = counters.data_ptr(), int(counters.shape[1])
+        a.B, a.H, a.G, a.Dk, a.Dv, a.S, a.inverse = B, H, G, Dk, Dv, 1, 0
+        a.base, a.scale, a.dtype = 10000.0, float(rope_scale if rope_scale > 0 else 1.0), _DTYPES[dt]
+        a.state = self.state.data_ptr()
+        a.l, a.d, a.l_sel, a.n_sel, a.w = cfg.l, cfg.d, cfg.l_sel, cfg.n_sel, cfg.w
+        self.a = a
+        e = _lib.DecodeEmit()
+        e.state = self.state.data_ptr()
+        e.K_raw, e.V_raw = self.slabs[4].data_ptr(), self.slabs[5].data_ptr()
+        e.K_cmp, e.V_cmp = cmp_slabs[0].data_ptr(), cmp_slabs[1].data_ptr()
+        e.BG, e.cap_raw, e.cap_cmp, e.Dk, e.Dv, e.l, e.d = B * G, int(self.slabs[4].shape[2]), int(cmp_slabs[0].shape[2]), Dk, Dv, cfg.l, cfg.d
+        e.base, e.scale, e.dtype = 10000.0, 1.0, _DTYPES[dt]  # phi pools RoPE'd keys at scale 1 (ops.phi_avgpool)
+        self.e = e
+        self.dm = make_dims(self.Q, cfg, K_sel=self.slabs[0], K_win=self.slabs[2], K_cmp=cmp_slabs[0], Dv=Dv, n_ranges=cfg.n_sel,
+                            gate_hidden=hid)
+        self.gp = gp
+        self.graph = None
+
+    @staticmethod
+    def supported(x_like, slabs, cmp_slabs, cfg: NSAConfig, *, H: int, G: int, Dk: int, Dv: int, gate_hidden: int) -> bool:
+        if x_like.dtype not in (torch.bfloat16, torch.float16):
+            return False
+        q = torch.empty((x_like.shape[0], 1, G, H // G, Dk), dtype=x_like.dtype, device="meta")
+        dm = make_dims(q, cfg, K_sel=slabs[0], K_win=slabs[2], K_cmp=cmp_slabs[0], Dv=Dv, n_ranges=cfg.n_sel, gate_hidden=gate_hidden)
+        return bool(_lib.load().nsa_decode_stepped_supported(C.byref(dm)))
+
+    def set_state(self, t: int, row_win: int, row_raw: int, S_cmp: int, ctr_idx: int) -> None:
+        h = self.state_host
+        h[0], h[1], h[2], h[3], h[4] = t, row_win, row_raw, S_cmp, ctr_idx
+        self.state.copy_(h, non_blocking=True)
+        self.expected = (t, row_win, row_raw, S_cmp, ctr_idx)
+
+    def _body(self) -> None:
+        import torch.nn.functional as F
+        y = F.linear(self.x, self.W_cat)
+        self.a.y = y.data_ptr()
+        P = lambda t_: C.c_void_p(t_.data_ptr())
+        _call("nsa_decode_produce", C.byref(self.a), _stream())
+        _call("nsa_decode_emit", C.byref(self.e), _stream())
+        _call("nsa_decode_fwd_stepped", C.byref(self.dm), P(self.Q), P(self.slabs[0]), P(self.slabs[1]), P(self.slabs[2]), P(self.slabs[3]),
+              P(self.cmp_slabs[0]), P(self.cmp_slabs[1]), C.byref(self.gp), P(self.O), P(self.ranges), P(self.state), _stream())
+        self.out = F.linear(self.O.view(self.B, 1, self.H * self.Dv), self.W_out)
+        _call("nsa_decode_advance", P(self.state), self.cfg.l, self.cfg.d, _stream())
+        self._keep = y
+
+    def capture(self) -> None:
+        """Warm up once eagerly (library handles, function attributes), then capture.  The caller sets the state before and after:
+        the warm-up advances the record and writes this step's rows, which the first replay rewrites identically."""
+        cur = torch.cuda.current_stream(self.x.device)
+        side = torch.cuda.Stream(device=self.x.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self._body()
+        cur.wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+
+    def replay(self) -> None:
+        global launch_count
+        self.graph.replay()
+        launch_count += self.KERNELS_PER_REPLAY
+
+
 # ----------------------------------------------------------------------------------------------------
 # caller-side row kernels of the block around the hot path (SURVEY 8f-2)
 # ----------------------------------------------------------------------------------------------------
