@@ -28,6 +28,16 @@ def _kv(B, dtype):
     return create_empty_kv(B, 2, 64, 64, build_block_meta(64, 32, 16, 64, 16, 128), device="cuda", dtype=dtype)
 
 
+def _same_step(og, oe, kv_eager, i):
+    """Bit-equal whenever both paths run the fused tcgen05 decode kernel.  Before the first compressed token exists the eager step
+    runs the SIMT kernels (nsa_decode_fwd needs S_cmp >= 1 for the fused kernel; the stepped entry point always uses it): same
+    function, different summation order."""
+    if kv_eager.K_cmp.shape[2] >= 1:
+        assert torch.equal(og, oe), f"step {i}: max diff {(og.float() - oe.float()).abs().max()}"
+    else:
+        assert (og.float() - oe.float()).abs().max() <= 2e-2, i
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("S0,steps", [(0, 70), (200, 90), (37, 40)])
 def test_graph_decode_equals_eager_decode(dtype, S0, steps):
@@ -49,7 +59,7 @@ def test_graph_decode_equals_eager_decode(dtype, S0, steps):
             og, kvg = mg(xs[:, i:i + 1], kvg, prefill=False)
             oe, kve = me(xs[:, i:i + 1], kve, prefill=False)
             assert og.shape == (B, 1, 256)
-            assert torch.equal(og, oe), f"step {i}: max diff {(og.float() - oe.float()).abs().max()}"
+            _same_step(og, oe, kve, i)
             assert torch.equal(mg._last_ranges, me._last_ranges), f"step {i}: selected ranges differ"
     assert getattr(kvg, "_decode_graph")[2] is not None, "the graph path was not taken"
     assert getattr(kve, "_decode_graph", None) is None
@@ -79,7 +89,7 @@ def test_graph_decode_survives_cache_growth_and_weight_updates():
                     m.W_Q.weight.data.mul_(1.01)
             og, kvg = mg(xs[:, i:i + 1], kvg, prefill=False)
             oe, kve = me(xs[:, i:i + 1], kve, prefill=False)
-            assert torch.equal(og, oe), i
+            _same_step(og, oe, kve, i)
     assert torch.equal(kvg.K_cmp, kve.K_cmp) and torch.equal(kvg.K_sel, kve.K_sel) and kvg.K_sel.shape[2] == 700
 
 
