@@ -854,6 +854,7 @@ def bench_decode(args, ops, cfg, dev, rank, world, barrier):
     try:
         module = bench_decode_module(S, Bd, dev, rank)
         mod_ms = module["us_per_step"] * 1e-3
+        module["b1_us_per_step"] = bench_decode_module(S, 1, dev, rank)["us_per_step"]
     except Exception as ex:  # the module-level line is additional evidence; never lose the kernel line over it
         module = {"error": f"{type(ex).__name__}: {ex}"}
     if world > 1:
@@ -912,8 +913,10 @@ def bench_decode_module(S, Bd, dev, rank, n=24):
     ms = s.elapsed_time(e) / n
     return {"what": "NSAAttention.forward(prefill=False): projections + cache append + fused decode step + output projection",
             "us_per_step": ms * 1e3, "us_per_token": ms * 1e3 / Bd, "batch_per_gpu": Bd, "context": int(kv.K_sel.shape[2]),
-            "nsa_launches_per_step": (k1 - k0) / n,
-            "note": "eager Python step over prebuilt argument blocks (ops.DecodeStepPlan); about 120-145 us of host time per step"}
+            "nsa_launches_per_step": (k1 - k0) / n, "graph": getattr(kv, "_decode_graph", (None, None, None))[2] is not None,
+            "hbm_frac": (Bd * decode_bytes_per_token(S)[0] / (ms * 1e-3) / 1e9) / measured_peaks()["hbm"],
+            "note": "one replayed CUDA graph per step (ops.DecodeGraphStep: GEMM, produce, emit, fused decode, GEMM, advance; position and "
+                    "row counts in a device record), token copied in and result cloned out on the host side"}
 
 
 def ops_launches():

@@ -43,9 +43,38 @@ class NSA_KV:
     _views: Dict[str, torch.Tensor] = field(default_factory=dict, repr=False, compare=False)
     _lens: Dict[str, int] = field(default_factory=dict, repr=False, compare=False)
 
+    # ---- lazily rebuilt views ------------------------------------------------------------------
+    # A decode step only bumps the row counts (commit_*): the public tensors of the fields it touched are dropped from the
+    # instance and rebuilt from the slab on the next read (__getattr__ runs only when the attribute is missing), so a step costs
+    # a few dictionary operations instead of thirteen narrow() calls.
+    _CACHE_FIELDS = ("K_sel", "V_sel", "K_win", "V_win", "K_cmp_raw_seq", "V_cmp_raw_seq", "K_cmp", "V_cmp")
+
+    def __getattr__(self, name: str):
+        d = self.__dict__
+        slabs = d.get("_slabs")
+        if slabs is not None:
+            if name in NSA_KV._CACHE_FIELDS and name in slabs:
+                self._set_view(name)
+                return d[name]
+            if name in NSA_KV._COUNTER_FIELDS and "__ctr" in slabs:
+                v = slabs["__ctr"][NSA_KV._COUNTER_FIELDS.index(name), :d["_lens"]["__ctr"]]
+                d["_views"][name] = v
+                d[name] = v
+                return v
+        raise AttributeError(name)
+
+    def _invalidate(self, name: str) -> None:
+        self.__dict__.pop(name, None)
+        self._views.pop(name, None)
+
+    def _is_synced(self, name: str) -> bool:
+        """The public tensor of `name` is (or, when dropped, will be rebuilt as) the view of its slab."""
+        d = self.__dict__
+        return name not in d or self._views.get(name) is d[name]
+
     # ---- slab management -----------------------------------------------------------------------
     def _in_sync(self, name: str) -> bool:
-        return name in self._slabs and self._views.get(name) is getattr(self, name)
+        return name in self._slabs and self._is_synced(name)
 
     def _ensure(self, name: str, extra: int) -> None:
         """Make `name` slab-backed with room for `extra` more rows, preserving its current content.  A field the
@@ -158,7 +187,7 @@ class NSA_KV:
         rows = []
         for i, name in enumerate(self._TOKEN_FIELDS):
             s = sl.get(name)
-            if s is not slabs[i] or vw.get(name) is not getattr(self, name):
+            if s is not slabs[i] or not self._is_synced(name):
                 return None
             n = ln[name]
             if n >= s.shape[2]:
@@ -177,15 +206,15 @@ class NSA_KV:
             return None
         sl, vw = self._slabs, self._views
         if counters is not None and (sl.get("__ctr") is not counters or self._lens["__ctr"] >= counters.shape[1]
-                                     or vw.get("reads_pred") is not self.reads_pred):
+                                     or not all(self._is_synced(f) for f in self._COUNTER_FIELDS)):
             return None
         return rows
 
     def same_compressed_slabs(self, cmp_slabs) -> bool:
         """True if K_cmp / V_cmp are still backed by exactly these slabs (an emission that outgrows a slab reallocates it)."""
-        sl, vw = self._slabs, self._views
-        return (sl.get("K_cmp") is cmp_slabs[0] and sl.get("V_cmp") is cmp_slabs[1] and vw.get("K_cmp") is self.K_cmp
-                and vw.get("V_cmp") is self.V_cmp)
+        sl = self._slabs
+        return (sl.get("K_cmp") is cmp_slabs[0] and sl.get("V_cmp") is cmp_slabs[1] and self._is_synced("K_cmp")
+                and self._is_synced("V_cmp"))
 
     def prepare_decode(self, like: torch.Tensor, with_counters: bool):
         """Make every cache a decode step touches slab-backed with room for one more row (token caches, one compressed token an
@@ -210,22 +239,22 @@ class NSA_KV:
         return self._lens["__ctr"]
 
     def commit_token_append(self, w: int) -> None:
+        lens = self._lens
+        lens["__w_K_win"] = lens["__w_V_win"] = int(w)
         for name in self._TOKEN_FIELDS:
-            if name in ("K_win", "V_win"):
-                self._lens["__w_" + name] = int(w)
-            self._lens[name] += 1
-            self._set_view(name)
+            lens[name] += 1
+            self._invalidate(name)
 
     def commit_compressed_append(self) -> None:
         """One compressed token was written on the device into the next free row of the K_cmp / V_cmp slabs (nsa_decode_emit)."""
         for name in ("K_cmp", "V_cmp"):
             self._lens[name] += 1
-            self._set_view(name)
+            self._invalidate(name)
 
     def counter_slot(self):
         """([5,cap] int64 slab, column) where the next step's read counters go (rows ordered as _COUNTER_FIELDS); the five
         public tensors become views of it.  commit_counters() publishes the column."""
-        sync = "__ctr" in self._slabs and all(self._views.get(f) is getattr(self, f) for f in self._COUNTER_FIELDS)
+        sync = "__ctr" in self._slabs and all(self._is_synced(f) for f in self._COUNTER_FIELDS)
         n = self._lens["__ctr"] if sync else int(self.reads_pred.numel())
         if not sync or self._slabs["__ctr"].shape[1] <= n:
             new = torch.zeros((5, max(2 * n, 1024)), dtype=torch.int64, device=self.reads_pred.device)
@@ -238,12 +267,9 @@ class NSA_KV:
         return self._slabs["__ctr"], n
 
     def commit_counters(self) -> None:
-        n = self._lens["__ctr"] + 1
-        self._lens["__ctr"] = n
-        for i, f in enumerate(self._COUNTER_FIELDS):
-            v = self._slabs["__ctr"][i, :n]
-            self._views[f] = v
-            setattr(self, f, v)
+        self._lens["__ctr"] += 1
+        for f in self._COUNTER_FIELDS:
+            self._invalidate(f)
 
     # ---- read counters (kv_cache.py:51-65) --------------------------------------------------------
     @staticmethod
