@@ -79,6 +79,24 @@ int make_tmap_q_heads(CUtensorMap* out, const void* base, int dtype, int D, int 
   return NSA_OK;
 }
 
+// 3-D map over a [tiles][rows_per_tile][D] row-major tensor (2-byte elements, 128-byte rows) with 128-B swizzle: box =
+// (D, box_rows, 1).  Used for STORES of whole warps' row groups: rows of a box beyond rows_per_tile are clipped by the TMA unit.
+int make_tmap_tiles(CUtensorMap* out, const void* base, int dtype, int D, int rows_per_tile, long long n_tiles, int box_rows) {
+  auto enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return NSA_ERR_CUDA; }
+  NSA_REQUIRE(((uintptr_t)base & 15) == 0, "TMA needs 16-byte aligned tensors");
+  NSA_REQUIRE(D * 2 == 128, "TMA tiles here are 128-byte rows (D=64, 2-byte elements), got D=%d", D);
+  if (n_tiles < 1) n_tiles = 1;
+  cuuint64_t gdim[3] = {(cuuint64_t)D, (cuuint64_t)rows_per_tile, (cuuint64_t)n_tiles};
+  cuuint64_t gstr[2] = {(cuuint64_t)D * 2, (cuuint64_t)rows_per_tile * D * 2};
+  cuuint32_t box[3] = {(cuuint32_t)D, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, tm_dtype(dtype), 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(tiles) failed with CUresult %d", (int)r); return NSA_ERR_CUDA; }
+  return NSA_OK;
+}
+
 // ---- capability checks ---------------------------------------------------------------------------------------
 bool tc_dense_supported(const nsa_dims_t& dm, int branch);
 bool tc_gather_supported(const nsa_dims_t& dm, int branch_mask);

@@ -174,24 +174,37 @@ sel2_fill_kernel(S2Geom gm, const int32_t* __restrict__ ranges, const int* __res
 
 // ---------------------------------------------------------------------------------------------------------------------
 // 2. block-major attention on tcgen05
+//
+// One CTA loads the K/V tile of its block once and walks its M-tiles as a three-stage pipeline over specialised warps:
+//   warps 0-3  softmax : S(i) from TMEM -> exact softmax of the 64 keys -> P(i) (16-bit, swizzled) + the row's (l, m)
+//   warps 4-7  epilogue: O(i) from TMEM -> / l -> 16-bit rows staged in the tile's own Q buffer -> one TMA tensor store per warp
+//   warp 8 producer (one TMA box per query into a ring of four Q buffers), warp 9 MMA issuer (QK(i) ahead of PV(i-1)).
+// S, O and P are double buffered, so softmax(i+1) runs while PV(i) and the epilogue of tile i are in flight.  The first version
+// gave each M-tile to ONE group of four warps that did softmax and epilogue back to back: its timeline (-DNSA_SEL2_DBG,
+// profiles/r2_sel2_timeline.log) showed ~6100 cycles per tile and slot, of which ~1900 in an epilogue whose un-swizzled staging
+// stores were 8-way bank conflicted, with the tensor pipe and MUFU idle 3/4 of the time.  The Q buffer of a tile is free once
+// QK(i) has completed, which the epilogue knows from O(i) being there, so staging needs no extra shared memory; the producer
+// refills a Q buffer only after the epilogue's store has read it (q_free).
 // ---------------------------------------------------------------------------------------------------------------------
+constexpr int kS2QRing = 3;  // Q buffers in flight: tile i loads into i % 3 while tiles i-1, i-2 are in softmax / epilogue
+
 struct S2Smem {
   static constexpr int kv = 0;                              // K tile 8 KB, V tile 8 KB (64 keys)
-  static constexpr int q = kv + 2 * 8192;                   // [2 slots][2 stages] x 16 KB
-  static constexpr int p = q + 4 * kS2Tile;                 // [2 slots] x 16 KB  (128 rows x 64 keys, 16-bit, 128B-swizzled)
+  static constexpr int q = kv + 2 * 8192;                   // ring of kS2QRing x 16 KB (Q rows of a tile; later its O staging)
+  static constexpr int p = q + kS2QRing * kS2Tile;          // [2] x 16 KB  (128 rows x 64 keys, 16-bit, 128B-swizzled)
   static constexpr int misc = p + 2 * kS2Tile;
   // Two CTAs must fit one SM (2 x (total + 1 KB reserved) <= 228 KB), so there is no alignment slack: the kernel requires the
   // dynamic shared-memory window to start 1024-byte aligned (it does on sm_100: it follows the 1 KB reserved region) and
   // traps otherwise.
-  static constexpr int total = misc + 256;
+  static constexpr int stat = misc + 256;                   // [kS2QRing][128] float2 (l, m) of a tile's rows: softmax -> epilogue
+  static constexpr int total = stat + kS2QRing * 128 * 8;
 };
 
 struct S2Misc {
   uint64_t kv_full;
-  uint64_t q_full[2][2], q_empty[2][2];
+  uint64_t q_full[kS2QRing], q_free[kS2QRing], st_full[kS2QRing];
   uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2], o_full[2], o_empty[2];
   uint32_t tmem_base;
-  int tile0, ntiles, bg, blk;
 };
 
 __device__ __forceinline__ float s2_ex2(float x) {
@@ -218,48 +231,48 @@ __device__ __forceinline__ void s2_ld_wait32(uint32_t (&r)[32]) {
 #define S2DBG(tag, it) do { } while (0)
 #endif
 
-// grid: an upper bound on the number of runs; CTAs beyond *n_runs exit.  Each CTA loads the K/V tile of its block once and
-// walks its M-tiles, alternating between two slots (softmax warpgroups) that ping-pong on the tensor core.
-// O_p [pairs][h][64] (dtype T, normalised by the tile's own l), lse_p [pairs][h] fp32 (natural log).
+// grid: an upper bound on the number of runs; CTAs beyond *n_runs exit.
+// O_p [tiles][TOK*h][64] (dtype T, normalised by the tile's own l; written through tmO), lse_p [pairs][h] fp32 (natural log).
 template <typename T>
 __global__ void __launch_bounds__(320, 2)
 sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                 const __grid_constant__ CUtensorMap tmV, nsa_dims_t dm, S2Geom gm, const S2Run* __restrict__ runs,
-                 const int* __restrict__ n_runs, const int* __restrict__ tok, const int* __restrict__ hi,
-                 T* __restrict__ O_p, float* __restrict__ lse_p, long long* dbg) {
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, nsa_dims_t dm, S2Geom gm,
+                 const S2Run* __restrict__ runs, const int* __restrict__ n_runs, const int* __restrict__ tok,
+                 const int* __restrict__ hi, float* __restrict__ lse_p, long long* dbg) {
   if ((int)blockIdx.x >= *n_runs) return;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  if (smem_u32(smem_raw) & 1023u) __trap();  // see S2Smem::total
+  if (smem_u32(smem_raw) & 1023u) __trap();  // see S2Smem
   uint8_t* smem = smem_raw;
   S2Misc* ms = reinterpret_cast<S2Misc*>(smem + S2Smem::misc);
+  float2* stat = reinterpret_cast<float2*>(smem + S2Smem::stat);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = dm.h, TOK = gm.tokp;
   const S2Run run = runs[blockIdx.x];
   const int bg = run.list / gm.NB, blk = run.list % gm.NB;
   const int g = bg % gm.G;
-  const int n = run.ntiles;                 // M-tiles of this CTA; tile i goes to slot i & 1
-  const int n0 = (n + 1) >> 1, n1 = n >> 1;  // tiles per slot
+  const int n = run.ntiles;  // M-tiles of this CTA; tile i uses Q buffer i % kS2QRing and S / O / P buffer i & 1
 
   // ---- setup ---------------------------------------------------------------------------------------------
   {  // rows the TMA never writes (padding rows >= TOK*h, padded queries) must hold finite data
     uint4 z = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < 4 * kS2Tile / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem + S2Smem::q)[i] = z;
+    for (int i = tid; i < kS2QRing * kS2Tile / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem + S2Smem::q)[i] = z;
   }
   if (tid == 0) {
     mbar_init(&ms->kv_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      for (int i = 0; i < 2; ++i) { mbar_init(&ms->q_full[s][i], 1); mbar_init(&ms->q_empty[s][i], 1); }
-      mbar_init(&ms->s_full[s], 1);
-      mbar_init(&ms->s_empty[s], 4);
-      mbar_init(&ms->p_full[s], 4);
-      mbar_init(&ms->p_empty[s], 1);
-      mbar_init(&ms->o_full[s], 1);
-      mbar_init(&ms->o_empty[s], 4);
+    for (int i = 0; i < kS2QRing; ++i) { mbar_init(&ms->q_full[i], 1); mbar_init(&ms->q_free[i], 4); mbar_init(&ms->st_full[i], 4); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ms->s_full[i], 1);
+      mbar_init(&ms->s_empty[i], 4);
+      mbar_init(&ms->p_full[i], 4);
+      mbar_init(&ms->p_empty[i], 1);
+      mbar_init(&ms->o_full[i], 1);
+      mbar_init(&ms->o_empty[i], 4);
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
   }
   if (warp == 0) tmem_alloc(&ms->tmem_base, 256);
   fence_proxy_async();
@@ -267,7 +280,7 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = ms->tmem_base;
-  // TMEM columns: S[slot] at slot*64 ; O[slot] at 128 + slot*64
+  // TMEM columns: S[b] at b*64 ; O[b] at 128 + b*64
 
   if (warp == 8) {
     // ===== TMA producer: K/V tile once, then one box per query of every M-tile =================================
@@ -277,19 +290,19 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tma_load_3d(smem + S2Smem::kv + 8192, &tmV, &ms->kv_full, 0, blk * 64, bg);
     }
     for (int i = 0; i < n; ++i) {
-      const int s = i & 1, k = i >> 1, st = k & 1;
+      const int qb = i % kS2QRing;
       const int p0 = (run.tile0 + i) * TOK;
       const int tk = lane < TOK ? tok[p0 + lane] : -1;                // query (b*S + s) of pair p0 + lane, -1 = padding
       const unsigned have = __ballot_sync(0xffffffffu, tk >= 0);
       if (lane == 0) {
         S2DBG(1, i);
-        mbar_wait(&ms->q_empty[s][st], ((k >> 1) & 1) ^ 1);
+        mbar_wait(&ms->q_free[qb], ((i / kS2QRing) & 1) ^ 1);         // the epilogue's store of tile i - kS2QRing has read this buffer
         S2DBG(2, i);
-        mbar_expect_tx(&ms->q_full[s][st], __popc(have) * h * 128);
+        mbar_expect_tx(&ms->q_full[qb], __popc(have) * h * 128);
       }
       __syncwarp();
       if (tk >= 0)  // one box (64 x h x 1 x 1) = the h head rows of one query, swizzled by the TMA unit
-        tma_load_4d(smem + S2Smem::q + (s * 2 + st) * kS2Tile + lane * h * 128, &tmQ, &ms->q_full[s][st], 0, 0, g, tk);
+        tma_load_4d(smem + S2Smem::q + qb * kS2Tile + lane * h * 128, &tmQ, &ms->q_full[qb], 0, 0, g, tk);
       __syncwarp();
     }
   } else if (warp == 9) {
@@ -300,87 +313,71 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     constexpr uint32_t kLoK = (16u >> 4) << 16, kLoMN = (8192u >> 4) << 16;
     const uint32_t smem0 = smem_u32(smem) >> 4;
     const uint32_t k_lo = (smem0 + (S2Smem::kv >> 4)) | kLoK, v_lo = (smem0 + ((S2Smem::kv + 8192) >> 4)) | kLoMN;
-    auto issue_qk = [&](int s, int k) {  // k-th tile of slot s
-      const int st = k & 1;
-      if (lane == 0) S2DBG(10, 2 * k + s);
-      mbar_wait(&ms->q_full[s][st], (k >> 1) & 1);
-      if (lane == 0) S2DBG(11, 2 * k + s);
-      mbar_wait(&ms->s_empty[s], (k & 1) ^ 1);
-      if (lane == 0) S2DBG(12, 2 * k + s);
-      tc_fence_after();
-      const uint32_t q_lo = (smem0 + ((S2Smem::q + (s * 2 + st) * kS2Tile) >> 4)) | kLoK;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) umma_f16_elect(tmem + s * 64, q_lo + kk * 2, kHi, k_lo + kk * 2, kHi, idesc_qk, kk > 0);
-      umma_commit_elect(&ms->s_full[s]);
-      umma_commit_elect(&ms->q_empty[s][st]);
-    };
-    auto issue_pv = [&](int s, int k) {
-      if (lane == 0) S2DBG(13, 2 * k + s);
-      mbar_wait(&ms->p_full[s], k & 1);
-      if (lane == 0) S2DBG(14, 2 * k + s);
-      mbar_wait(&ms->o_empty[s], (k & 1) ^ 1);
-      if (lane == 0) S2DBG(15, 2 * k + s);
-      tc_fence_after();
-      const uint32_t p_lo = (smem0 + ((S2Smem::p + s * kS2Tile) >> 4)) | kLoK;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        umma_f16_elect(tmem + 128 + s * 64, p_lo + kk * 2, kHi, v_lo + kk * (2048 >> 4), kHi, idesc_pv, kk > 0);
-      umma_commit_elect(&ms->o_full[s]);
-      umma_commit_elect(&ms->p_empty[s]);
-    };
     mbar_wait(&ms->kv_full, 0);
-    if (n0 > 0) issue_qk(0, 0);
-    if (n1 > 0) issue_qk(1, 0);
-    for (int k = 0; k < n0; ++k) {
-      issue_pv(0, k);
-      if (k + 1 < n0) issue_qk(0, k + 1);
-      if (k < n1) {
-        issue_pv(1, k);
-        if (k + 1 < n1) issue_qk(1, k + 1);
+    for (int i = 0; i <= n; ++i) {
+      if (i < n) {  // S(i) = Q(i) . K^T
+        const int b = i & 1, qb = i % kS2QRing;
+        if (lane == 0) S2DBG(10, i);
+        mbar_wait(&ms->q_full[qb], (i / kS2QRing) & 1);
+        mbar_wait(&ms->s_empty[b], ((i >> 1) & 1) ^ 1);
+        if (lane == 0) S2DBG(12, i);
+        tc_fence_after();
+        const uint32_t q_lo = (smem0 + ((S2Smem::q + qb * kS2Tile) >> 4)) | kLoK;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_f16_elect(tmem + b * 64, q_lo + kk * 2, kHi, k_lo + kk * 2, kHi, idesc_qk, kk > 0);
+        umma_commit_elect(&ms->s_full[b]);
+      }
+      if (i > 0) {  // O(i-1) = P(i-1) . V
+        const int j = i - 1, b = j & 1;
+        if (lane == 0) S2DBG(13, j);
+        mbar_wait(&ms->p_full[b], (j >> 1) & 1);
+        mbar_wait(&ms->o_empty[b], ((j >> 1) & 1) ^ 1);
+        if (lane == 0) S2DBG(15, j);
+        tc_fence_after();
+        const uint32_t p_lo = (smem0 + ((S2Smem::p + b * kS2Tile) >> 4)) | kLoK;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_f16_elect(tmem + 128 + b * 64, p_lo + kk * 2, kHi, v_lo + kk * (2048 >> 4), kHi, idesc_pv, kk > 0);
+        umma_commit_elect(&ms->o_full[b]);
+        umma_commit_elect(&ms->p_empty[b]);
       }
     }
-  } else {
-    // ===== softmax warps: slot = warp / 4, thread = TMEM lane = row (query, head) ============================
-    const int s = warp >> 2;
-    const int r = tid & 127;
-    const int tok_l = r / h, head = r - tok_l * h;
-    const int ns = s == 0 ? n0 : n1;
+  } else if (warp < 4) {
+    // ===== softmax warps: thread = TMEM lane = row (query, head) ==============================================
+    const int r = tid;  // 0..127
+    const int tok_l = r / h;
     const float c = dm.scale * kLog2e;
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tm_S = tmem + lane_off + s * 64;
-    const uint32_t tm_O = tmem + lane_off + 128 + s * 64;
-    uint8_t* prow = smem + S2Smem::p + s * kS2Tile + r * 128;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const int sw = r & 7;
-    // the pair's (query, valid keys) of the NEXT tile are fetched while the current one is processed: no global latency
-    // at the head of a tile
+    // the pair's valid-key count of the NEXT tile is fetched while the current one is processed
     int tok_n = -1, hi_n = 64;
-    if (ns > 0 && tok_l < TOK) {
-      const int p0 = (run.tile0 + s) * TOK + tok_l;
+    if (n > 0 && tok_l < TOK) {
+      const int p0 = run.tile0 * TOK + tok_l;
       tok_n = tok[p0];
       hi_n = hi[p0];
     }
-    for (int k = 0; k < ns; ++k) {
-      const int i = 2 * k + s;
+    for (int i = 0; i < n; ++i) {
+      const int b = i & 1;
       const int p = (run.tile0 + i) * TOK + tok_l;
       const bool row_ok = tok_l < TOK && tok_n >= 0;
       // rows that are not stored see the whole tile, so they never push their warp onto the masked path
       const int nk = row_ok ? hi_n : 64;
-      if (k + 1 < ns && tok_l < TOK) {
-        tok_n = tok[p + 2 * TOK];
-        hi_n = hi[p + 2 * TOK];
+      if (i + 1 < n && tok_l < TOK) {
+        tok_n = tok[p + TOK];
+        hi_n = hi[p + TOK];
       }
-      if ((tid & 127) == 0) S2DBG(20, i);
-      mbar_wait(&ms->s_full[s], k & 1);
-      if ((tid & 127) == 0) S2DBG(21, i);
+      if (tid == 0) S2DBG(20, i);
+      mbar_wait(&ms->s_full[b], (i >> 1) & 1);
+      if (tid == 0) S2DBG(21, i);
       tc_fence_after();
       uint32_t va[32], vb2[32];
-      tmem_ld32(tm_S, va);
-      tmem_ld32(tm_S + 32, vb2);
+      tmem_ld32(tmem + lane_off + b * 64, va);
+      tmem_ld32(tmem + lane_off + b * 64 + 32, vb2);
       s2_ld_wait32(va);
       s2_ld_wait32(vb2);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ms->s_empty[s]);
+      if (lane == 0) mbar_arrive(&ms->s_empty[b]);
       // exact softmax of the tile (64 keys): max, exponentials, sum
       const bool full = __all_sync(0xffffffffu, nk >= 64);
       float m = -INFINITY;
@@ -418,12 +415,10 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         l3 += __uint_as_float(vb2[e + 1]);
       }
       const float l = (l0 + l1) + (l2 + l3);
-      if ((tid & 127) == 0) S2DBG(22, i);
-      // the warp's 32 rows of the P buffer double as the staging area of its partial-O store: the bulk store of the previous
-      // tile must have read them (issued by this warp's lane 0) and P.V of the previous tile must have read P
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncwarp();
-      mbar_wait(&ms->p_empty[s], (k & 1) ^ 1);
+      stat[(i % kS2QRing) * 128 + r] = make_float2(l, m);  // tile i + kS2QRing cannot start before the epilogue of tile i (q_free)
+      if (tid == 0) S2DBG(22, i);
+      mbar_wait(&ms->p_empty[b], ((i >> 1) & 1) ^ 1);  // P.V of tile i - 2 has read this P buffer
+      uint8_t* prow = smem + S2Smem::p + b * kS2Tile + r * 128;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {  // keys 0..31: chunks 0..3 ; keys 32..63: chunks 4..7 (16 B = 8 keys each)
         uint4 u, w;
@@ -440,59 +435,76 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ms->p_full[s]);
-      if ((tid & 127) == 0) S2DBG(23, i);
-      // ---- partial output of this (query, block) pair ----
-      mbar_wait(&ms->o_full[s], k & 1);
-      if ((tid & 127) == 0) S2DBG(24, i);
+      if (lane == 0) {
+        mbar_arrive(&ms->p_full[b]);
+        mbar_arrive(&ms->st_full[i % kS2QRing]);
+      }
+      if (tid == 0) S2DBG(23, i);
+    }
+  } else {
+    // ===== epilogue warps: thread = TMEM lane = row; partial O of every (query, block) pair -> global ========================
+    const int ew = warp - 4;                 // TMEM lane quarter
+    const int r = ew * 32 + lane;
+    const int tok_l = r / h, head = r - tok_l * h;
+    const uint32_t lane_off = (uint32_t)(ew * 32) << 16;
+    const int sw = r & 7;
+    const int row0 = ew * 32;
+    const bool warp_has_rows = row0 < TOK * h;
+    int tok_n = -1;
+    if (n > 0 && tok_l < TOK) tok_n = tok[run.tile0 * TOK + tok_l];
+    for (int i = 0; i < n; ++i) {
+      const int b = i & 1, qb = i % kS2QRing;
+      const int p = (run.tile0 + i) * TOK + tok_l;
+      const bool row_ok = tok_l < TOK && tok_n >= 0;
+      if (i + 1 < n && tok_l < TOK) tok_n = tok[p + TOK];
+      if (i > 0 && lane == 0) {  // the store of tile i - 1 has read its staging rows: that Q buffer may be refilled
+        bulk_wait_read0();
+        mbar_arrive(&ms->q_free[(i - 1) % kS2QRing]);
+      }
+      if (tid == 128) S2DBG(30, i);
+      mbar_wait(&ms->o_full[b], (i >> 1) & 1);
+      if (tid == 128) S2DBG(31, i);
       tc_fence_after();
-      tmem_ld32(tm_O, va);
-      tmem_ld32(tm_O + 32, vb2);
+      uint32_t va[32], vb2[32];
+      tmem_ld32(tmem + lane_off + 128 + b * 64, va);
+      tmem_ld32(tmem + lane_off + 128 + b * 64 + 32, vb2);
       s2_ld_wait32(va);
       s2_ld_wait32(vb2);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ms->o_empty[s]);
-      // Partial O of the tile: every warp stages its 32 rows (16-bit, normalised by the tile's own l) in its rows of the
-      // slot's P buffer -- P.V has completed, so the buffer is free -- and sends them as one bulk store (the rows of a tile
-      // are contiguous in O_p).  Per-thread 16-byte
-      // stores of 128-byte rows touch 32 sectors per instruction: the store queue then stalled each warp for ~3000 cycles
-      // per tile (timeline, -DNSA_SEL2_DBG).  Rows of padding pairs carry stale bytes: the merge never reads them.
-      {
-        const float inv = l > 0.f ? 1.0f / l : 0.f;
-        uint4* dst = reinterpret_cast<uint4*>(smem + S2Smem::p + s * kS2Tile + r * 128);
-        if (row_ok) {
+      if (lane == 0) mbar_arrive(&ms->o_empty[b]);
+      mbar_wait(&ms->st_full[qb], (i / kS2QRing) & 1);
+      const float2 lm = stat[qb * 128 + r];
+      const float inv = lm.x > 0.f ? 1.0f / lm.x : 0.f;
+      // staging = this tile's Q buffer (QK(i) has completed: O(i) is here), rows in the 128B-swizzle pattern the tensor store undoes
+      uint8_t* orow = smem + S2Smem::q + qb * kS2Tile + r * 128;
+      if (row_ok) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 u, w;
-            u.x = pack2(T(), __uint_as_float(va[q * 8 + 0]) * inv, __uint_as_float(va[q * 8 + 1]) * inv);
-            u.y = pack2(T(), __uint_as_float(va[q * 8 + 2]) * inv, __uint_as_float(va[q * 8 + 3]) * inv);
-            u.z = pack2(T(), __uint_as_float(va[q * 8 + 4]) * inv, __uint_as_float(va[q * 8 + 5]) * inv);
-            u.w = pack2(T(), __uint_as_float(va[q * 8 + 6]) * inv, __uint_as_float(va[q * 8 + 7]) * inv);
-            w.x = pack2(T(), __uint_as_float(vb2[q * 8 + 0]) * inv, __uint_as_float(vb2[q * 8 + 1]) * inv);
-            w.y = pack2(T(), __uint_as_float(vb2[q * 8 + 2]) * inv, __uint_as_float(vb2[q * 8 + 3]) * inv);
-            w.z = pack2(T(), __uint_as_float(vb2[q * 8 + 4]) * inv, __uint_as_float(vb2[q * 8 + 5]) * inv);
-            w.w = pack2(T(), __uint_as_float(vb2[q * 8 + 6]) * inv, __uint_as_float(vb2[q * 8 + 7]) * inv);
-            dst[q] = u;
-            dst[4 + q] = w;
-          }
-          lse_p[(size_t)p * h + head] = l > 0.f ? m * dm.scale + logf(l) : -INFINITY;
+        for (int q = 0; q < 4; ++q) {
+          uint4 u, w;
+          u.x = pack2(T(), __uint_as_float(va[q * 8 + 0]) * inv, __uint_as_float(va[q * 8 + 1]) * inv);
+          u.y = pack2(T(), __uint_as_float(va[q * 8 + 2]) * inv, __uint_as_float(va[q * 8 + 3]) * inv);
+          u.z = pack2(T(), __uint_as_float(va[q * 8 + 4]) * inv, __uint_as_float(va[q * 8 + 5]) * inv);
+          u.w = pack2(T(), __uint_as_float(va[q * 8 + 6]) * inv, __uint_as_float(va[q * 8 + 7]) * inv);
+          w.x = pack2(T(), __uint_as_float(vb2[q * 8 + 0]) * inv, __uint_as_float(vb2[q * 8 + 1]) * inv);
+          w.y = pack2(T(), __uint_as_float(vb2[q * 8 + 2]) * inv, __uint_as_float(vb2[q * 8 + 3]) * inv);
+          w.z = pack2(T(), __uint_as_float(vb2[q * 8 + 4]) * inv, __uint_as_float(vb2[q * 8 + 5]) * inv);
+          w.w = pack2(T(), __uint_as_float(vb2[q * 8 + 6]) * inv, __uint_as_float(vb2[q * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + ((q ^ sw) << 4)) = u;
+          *reinterpret_cast<uint4*>(orow + (((4 + q) ^ sw) << 4)) = w;
         }
-        fence_proxy_async();
-        __syncwarp();
-        const int row0 = (warp & 3) * 32;
-        const int nrows = TOK * h - row0 < 32 ? TOK * h - row0 : 32;  // rows beyond TOK*h are padding
-        if (lane == 0 && nrows > 0) {
-          T* gdst = O_p + ((size_t)(run.tile0 + i) * TOK * h + row0) * 64;
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-                       "r"(smem_u32(smem + S2Smem::p + s * kS2Tile + row0 * 128)), "r"(nrows * 128)
-                       : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
+        lse_p[(size_t)p * h + head] = lm.x > 0.f ? lm.y * dm.scale + logf(lm.x) : -INFINITY;
       }
-      if ((tid & 127) == 0) S2DBG(25, i);
+      fence_proxy_async();
+      __syncwarp();
+      // rows of padding pairs carry stale bytes (the merge never reads them); rows >= TOK*h of the box are clipped by the TMA unit
+      if (lane == 0) {
+        if (warp_has_rows) tma_store_3d(&tmO, smem + S2Smem::q + qb * kS2Tile + row0 * 128, 0, row0, run.tile0 + i);
+        bulk_commit();
+      }
+      if (tid == 128) S2DBG(32, i);
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (lane == 0) bulk_wait0();
   }
 
   tc_fence_before();
@@ -682,11 +694,12 @@ static int launch_sel2_t(const nsa_dims_t& dm, const void* Q, const void* K, con
   const int n_rows = dm.B * dm.S * dm.G;
   if (int rc = s2_build(dm, ranges, ws, w, true, stream)) return rc;
 
-  CUtensorMap tmQ, tmK, tmV;
+  CUtensorMap tmQ, tmK, tmV, tmO;
   const int slabs = dm.B * dm.G;
   if (int rc = make_tmap_q_heads(&tmQ, Q, dm.dtype, 64, dm.h, dm.G, (long long)dm.B * dm.S, 1)) return rc;
   if (int rc = make_tmap_rows(&tmK, K, dm.dtype, 64, dm.S_sel_kv, 64, (long long)dm.cap_sel * 64, slabs, 64)) return rc;
   if (int rc = make_tmap_rows(&tmV, V, dm.dtype, 64, dm.S_sel_kv, 64, (long long)dm.cap_sel * 64, slabs, 64)) return rc;
+  if (int rc = make_tmap_tiles(&tmO, O_p, dm.dtype, 64, gm.tokp * dm.h, w.max_pairs / gm.tokp, 32)) return rc;
   auto kern = sel2_attn_kernel<T>;
   // two CTAs per SM (S2Smem::total): needs the largest carve-out -- with the driver's default this kernel ran one CTA per SM
   static std::atomic<unsigned long long> attr_done{0};
@@ -698,7 +711,7 @@ static int launch_sel2_t(const nsa_dims_t& dm, const void* Q, const void* K, con
   cudaMemsetAsync(dbg_static, 0, 4000 * sizeof(long long), stream);
   dbg_buf = dbg_static;
 #endif
-  kern<<<w.max_runs, 320, S2Smem::total, stream>>>(tmQ, tmK, tmV, dm, gm, runs, n_runs, tok, hi, O_p, lse_p, dbg_buf);
+  kern<<<w.max_runs, 320, S2Smem::total, stream>>>(tmQ, tmK, tmV, tmO, dm, gm, runs, n_runs, tok, hi, lse_p, dbg_buf);
   if (int rc = check_launch("sel2_attn_kernel")) return rc;
 #ifdef NSA_SEL2_DBG
   {
@@ -722,6 +735,7 @@ static int launch_sel2_t(const nsa_dims_t& dm, const void* Q, const void* K, con
 int launch_sel2_tc(const nsa_dims_t& dm, const void* Q, const void* K, const void* V, const int32_t* ranges, void* O, float* lse,
                    void* workspace, cudaStream_t stream) {
   static_assert(sizeof(S2Misc) <= 256, "S2Misc must fit its slot");
+  static_assert(2 * (S2Smem::total + 1024) <= 228 * 1024, "two sel2 CTAs must fit one SM");
   if (dm.B * dm.S * dm.G == 0) return NSA_OK;
   NSA_REQUIRE(workspace, "sel2: needs a workspace of nsa_workspace_bytes(NSA_WS_SEL) bytes");
   if (dm.dtype == NSA_BF16) return launch_sel2_t<__nv_bfloat16>(dm, Q, K, V, ranges, O, lse, workspace, stream);

@@ -11,7 +11,8 @@ NAMES = {1: "prod wait", 2: "prod go", 10: "mma sdp: wait qdo", 11: "mma sdp: wa
 if len(sys.argv) > 4 and sys.argv[4] == "sel2":  # -DNSA_SEL2_DBG build: the block-major forward (tc_sel2.cu)
     NAMES = {1: "prod wait q_empty", 2: "prod go", 10: "mma qk: wait q_full", 11: "mma qk: wait s_empty", 12: "mma qk: issue",
              13: "mma pv: wait p_full", 14: "mma pv: wait o_empty", 15: "mma pv: issue", 20: "soft: wait s_full", 21: "soft: start",
-             22: "soft: P ready, wait p_empty", 23: "soft: P published", 24: "soft: O arrived", 25: "soft: partial stored"}
+             22: "soft: P ready, wait p_empty", 23: "soft: P published", 24: "soft: O arrived", 25: "soft: partial stored",
+             30: "epi: wait o_full", 31: "epi: O arrived", 32: "epi: store issued"}
 ev = []
 for line in open(sys.argv[1]):
     if line.startswith("BDBG "):
