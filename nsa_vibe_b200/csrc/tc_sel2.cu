@@ -289,10 +289,12 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tma_load_3d(smem + S2Smem::kv, &tmK, &ms->kv_full, 0, blk * 64, bg);
       tma_load_3d(smem + S2Smem::kv + 8192, &tmV, &ms->kv_full, 0, blk * 64, bg);
     }
+    int tk_next = (n > 0 && lane < TOK) ? tok[run.tile0 * TOK + lane] : -1;
     for (int i = 0; i < n; ++i) {
       const int qb = i % kS2QRing;
-      const int p0 = (run.tile0 + i) * TOK;
-      const int tk = lane < TOK ? tok[p0 + lane] : -1;                // query (b*S + s) of pair p0 + lane, -1 = padding
+      const int tk = tk_next;                                         // query (b*S + s) of pair p0 + lane, -1 = padding
+      // the next tile's queries are fetched while this tile's boxes are issued: no global-load latency at the head of a tile
+      tk_next = (i + 1 < n && lane < TOK) ? tok[(run.tile0 + i + 1) * TOK + lane] : -1;
       const unsigned have = __ballot_sync(0xffffffffu, tk >= 0);
       if (lane == 0) {
         S2DBG(1, i);
@@ -314,32 +316,39 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t smem0 = smem_u32(smem) >> 4;
     const uint32_t k_lo = (smem0 + (S2Smem::kv >> 4)) | kLoK, v_lo = (smem0 + ((S2Smem::kv + 8192) >> 4)) | kLoMN;
     mbar_wait(&ms->kv_full, 0);
-    for (int i = 0; i <= n; ++i) {
-      if (i < n) {  // S(i) = Q(i) . K^T
-        const int b = i & 1, qb = i % kS2QRing;
-        if (lane == 0) S2DBG(10, i);
-        mbar_wait(&ms->q_full[qb], (i / kS2QRing) & 1);
-        mbar_wait(&ms->s_empty[b], ((i >> 1) & 1) ^ 1);
-        if (lane == 0) S2DBG(12, i);
-        tc_fence_after();
-        const uint32_t q_lo = (smem0 + ((S2Smem::q + qb * kS2Tile) >> 4)) | kLoK;
+    // QK(i) and PV(j) are issued in whichever order their inputs arrive (lane 0 polls, the warp follows): with a fixed order a
+    // late Q tile held back the P.V of the tile before it, which held back that tile's epilogue, which held back the producer
+    int qi = 0, pj = 0;  // next S = Q.K^T / next O = P.V to issue
+    while (pj < n) {
+      if (pj < qi) {
+        const int b = pj & 1;
+        bool ok = false;
+        if (lane == 0) ok = mbar_test_wait(&ms->p_full[b], (pj >> 1) & 1) && mbar_test_wait(&ms->o_empty[b], ((pj >> 1) & 1) ^ 1);
+        if (__shfl_sync(0xffffffffu, ok ? 1 : 0, 0)) {
+          if (lane == 0) S2DBG(15, pj);
+          tc_fence_after();
+          const uint32_t p_lo = (smem0 + ((S2Smem::p + b * kS2Tile) >> 4)) | kLoK;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) umma_f16_elect(tmem + b * 64, q_lo + kk * 2, kHi, k_lo + kk * 2, kHi, idesc_qk, kk > 0);
-        umma_commit_elect(&ms->s_full[b]);
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16_elect(tmem + 128 + b * 64, p_lo + kk * 2, kHi, v_lo + kk * (2048 >> 4), kHi, idesc_pv, kk > 0);
+          umma_commit_elect(&ms->o_full[b]);
+          umma_commit_elect(&ms->p_empty[b]);
+          ++pj;
+        }
       }
-      if (i > 0) {  // O(i-1) = P(i-1) . V
-        const int j = i - 1, b = j & 1;
-        if (lane == 0) S2DBG(13, j);
-        mbar_wait(&ms->p_full[b], (j >> 1) & 1);
-        mbar_wait(&ms->o_empty[b], ((j >> 1) & 1) ^ 1);
-        if (lane == 0) S2DBG(15, j);
-        tc_fence_after();
-        const uint32_t p_lo = (smem0 + ((S2Smem::p + b * kS2Tile) >> 4)) | kLoK;
+      if (qi < n) {
+        const int b = qi & 1, qb = qi % kS2QRing;
+        bool ok = false;
+        if (lane == 0) ok = mbar_test_wait(&ms->q_full[qb], (qi / kS2QRing) & 1) && mbar_test_wait(&ms->s_empty[b], ((qi >> 1) & 1) ^ 1);
+        if (__shfl_sync(0xffffffffu, ok ? 1 : 0, 0)) {
+          if (lane == 0) S2DBG(12, qi);
+          tc_fence_after();
+          const uint32_t q_lo = (smem0 + ((S2Smem::q + qb * kS2Tile) >> 4)) | kLoK;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_f16_elect(tmem + 128 + b * 64, p_lo + kk * 2, kHi, v_lo + kk * (2048 >> 4), kHi, idesc_pv, kk > 0);
-        umma_commit_elect(&ms->o_full[b]);
-        umma_commit_elect(&ms->p_empty[b]);
+          for (int kk = 0; kk < 4; ++kk) umma_f16_elect(tmem + b * 64, q_lo + kk * 2, kHi, k_lo + kk * 2, kHi, idesc_qk, kk > 0);
+          umma_commit_elect(&ms->s_full[b]);
+          ++qi;
+        }
       }
     }
   } else if (warp < 4) {

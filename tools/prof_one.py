@@ -17,9 +17,13 @@ r = lambda *s: torch.randn(*s, generator=g, device=dev).bfloat16()
 S_cmp = (S - l) // d + 1
 Q, Ks, Vs, Kw, Vw, Kc, Vc = r(B, S, G, h, D), r(B, G, S, D), r(B, G, S, D), r(B, G, S, D), r(B, G, S, D), r(B, G, S_cmp, D), r(B, G, S_cmp, D)
 cfg = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w)
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 with torch.no_grad():
     ranges = ops.score_select(Q, Kc, cfg, mode=0)
-    for _ in range(3):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
         if what == "score":
             ops.score_pgrp(Q, Kc, cfg)
         elif what == "score_select":  # the scorer as the hot path runs it: pass 2 stops at the causal limit
@@ -32,5 +36,6 @@ with torch.no_grad():
             ops.sel_attention_blockmajor(Q, Ks, Vs, cfg, ranges, ranges_trusted=True)
         else:
             ops.branch_attention(ops.BR_SEL, Q, Ks, Vs, cfg, ranges, ranges_trusted=True)
+    e1.record()
 torch.cuda.synchronize()
-print("ok")
+print(f"ok {what} S={S}: {e0.elapsed_time(e1) / reps:.3f} ms per call (first call included)")

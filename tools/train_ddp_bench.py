@@ -17,23 +17,7 @@ import torch.nn.functional as F
 
 from nsa_vibe_b200 import _lib
 from nsa_vibe_b200 import dist as nd
-from nsa_vibe_b200.model.llama_block_nsa import LlamaBlockNSA, RMSNorm
-
-
-class TinyLM(nn.Module):  # scripts/train_showcase.py:30-117 (embedding -> blocks -> norm -> lm_head)
-    def __init__(self, vocab, dim, n_layers, heads, groups, dk, dv, l, d, l_sel, n_sel, w):
-        super().__init__()
-        self.embed = nn.Embedding(vocab, dim)
-        self.blocks = nn.ModuleList([LlamaBlockNSA(dim, heads, groups, dk, dv, l, d, l_sel, n_sel, w) for _ in range(n_layers)])
-        self.norm_f = RMSNorm(dim)
-        self.lm_head = nn.Linear(dim, vocab, bias=False)
-
-    def forward(self, ids):
-        x, delta = self.embed(ids), None
-        for b in self.blocks:  # each block's last residual add runs inside the next norm's kernel
-            x, delta = b(x, delta, defer_residual=True)
-        _, xn = self.norm_f(x, residual=delta)
-        return self.lm_head(xn)
+from nsa_vibe_b200.model.tiny_lm import TinyLM
 
 
 def main():
@@ -44,6 +28,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--graph", action="store_true", help="capture forward + backward + optimizer step in one CUDA graph and replay it")
+    ap.add_argument("--flat", action="store_true", help="with --graph: one flat all_reduce after backward instead of per-layer buckets overlapped with it")
     ap.add_argument("--profile", action="store_true", help="cProfile of the host side of the timed steps (rank 0)")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -60,6 +45,7 @@ def main():
         # DDP's reducer cannot be captured in a CUDA graph; the same exchange (divide, bf16, allreduce, cast back) as one flat NCCL
         # all_reduce after the backward can (nd.allreduce_grads_bf16).  156.6 MB over NVLink: ~0.5 ms of a ~27 ms step.
         nd.broadcast_parameters(model, 0)
+        exch = None if a.flat else nd.OverlappedGradExchange(model.grad_buckets())
     elif world > 1:
         model = nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
         nd.register_bf16_compress(model)
@@ -76,7 +62,7 @@ def main():
         loss = F.cross_entropy(logits.float().reshape(-1, 256), ids[:, 1:].reshape(-1))
         loss.backward()
         if flat_exchange:
-            nd.allreduce_grads_bf16(model.parameters())
+            exch.finish() if exch is not None else nd.allreduce_grads_bf16(model.parameters())
         opt.step()
         return loss
 
@@ -100,7 +86,7 @@ def main():
             holder["loss"] = F.cross_entropy(logits.float().reshape(-1, 256), ids[:, 1:].reshape(-1))
             holder["loss"].backward()
             if flat_exchange:
-                nd.allreduce_grads_bf16(model.parameters())
+                exch.finish() if exch is not None else nd.allreduce_grads_bf16(model.parameters())
             opt.step()
 
         def step():  # noqa: F811
@@ -134,7 +120,7 @@ def main():
         print(json.dumps({"config": "C5 m7c TinyLM DDP training step", "layers": a.layers, "params": n_params, "S": a.S,
                           "batch_per_gpu": a.B, "n_gpus": world, "mode": mode, "adamw": "fused" if fused else "foreach", "ms_per_step": ms, "tokens_per_s": world * a.B * a.S / (ms * 1e-3),
                           "loss": float(loss.detach()), "nsa_kernel_launches_per_step": (lib.nsa_kernel_launches() - n0) / a.steps,
-                          "grad_allreduce": ("one flat bf16 NCCL all_reduce captured in the graph" if flat_exchange else "DDP bf16_compress_hook over NCCL") if world > 1 else "none (single GPU)",
+                          "grad_allreduce": (("one flat bf16 NCCL all_reduce captured in the graph" if a.flat else "per-layer bf16 buckets, async NCCL all_reduce overlapped with backward, captured in the graph") if flat_exchange else "DDP bf16_compress_hook over NCCL") if world > 1 else "none (single GPU)",
                           "allreduce_bytes_per_step": 2 * n_params if world > 1 else 0}))
     if flat_exchange:
         # a process group whose collective sits in a live CUDA graph does not tear down cleanly here (destroy_process_group hung
