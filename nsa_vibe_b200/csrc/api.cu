@@ -245,8 +245,13 @@ int nsa_prefill_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, cons
   NSA_REQUIRE(obr, "prefill_fwd: this shape needs O_branches or a workspace of nsa_workspace_bytes(NSA_WS_PREFILL)");
   const void* Ks[3] = {K_cmp, K_sel, K_win};
   const void* Vs[3] = {V_cmp, V_sel, V_win};
+  // No-grad long prefill (nothing saved for backward, all three branches on tensor cores, block-major selected branch): the
+  // selected branch's partials are merged, gated and combined with the other two branches in ONE pass -- O_sel and the gates never
+  // reach HBM and there is no separate combine kernel.  NSA_B200_FUSE_COMBINE=0 keeps the separate kernels (A/B runs).
+  static const bool fuse_env = !(getenv("NSA_B200_FUSE_COMBINE") && atoi(getenv("NSA_B200_FUSE_COMBINE")) == 0);
+  const bool fuse = fuse_env && tc_mask == 7 && !O_branches && !lse && workspace && use_sel2(*dm) && sel2_fuse_supported(*dm);
   for (int br = 0; br < 3; ++br) {
-    if (!(tc_mask & (1 << br))) continue;
+    if (!(tc_mask & (1 << br)) || (fuse && br == 1)) continue;
     void* ob = (char*)obr + br * per_branch;
     float* lb = lse ? lse + br * rows_h : nullptr;
     if (br == 1 && workspace && use_sel2(*dm)) {  // long prefill: KV-block-major selected branch
@@ -254,6 +259,15 @@ int nsa_prefill_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, cons
       continue;
     }
     if (int rc = launch_branch_tc(*dm, br, Q, Ks[br], Vs[br], ranges, ob, lb, st)) return rc;
+  }
+  if (fuse) {
+    Sel2Fuse f;
+    f.gp = gp;
+    f.O_cmp = obr;
+    f.O_win = (char*)obr + 2 * per_branch;
+    f.O = O;
+    f.gates = gates;
+    return launch_sel2_tc(*dm, Q, K_sel, V_sel, ranges, nullptr, nullptr, (char*)workspace + staging, st, &f);
   }
   if (tc_mask != 7) {
     a.O_br = obr;

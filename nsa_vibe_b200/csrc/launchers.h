@@ -69,8 +69,17 @@ bool tc_score_supported(const nsa_dims_t& dm);
 bool tc_decode_supported(const nsa_dims_t& dm);
 bool tc_sel2_supported(const nsa_dims_t& dm);
 int64_t tc_sel2_workspace(const nsa_dims_t& dm);
+// fuse != NULL: instead of writing the selected branch's O / lse, merge the partials, evaluate the gate and write the gated
+// combination with the given compressed / sliding outputs (no-grad prefill: O_sel and the gates stay on chip)
+struct Sel2Fuse {
+  const nsa_gate_params_t* gp;
+  const void *O_cmp, *O_win;
+  void* O;
+  float* gates;  // [rows,3] (may be NULL)
+};
+bool sel2_fuse_supported(const nsa_dims_t& dm);
 int launch_sel2_tc(const nsa_dims_t& dm, const void* Q, const void* K, const void* V, const int32_t* ranges, void* O, float* lse,
-                   void* workspace, cudaStream_t stream);
+                   void* workspace, cudaStream_t stream, const Sel2Fuse* fuse = nullptr);
 // tensor-core backward (tc_bwd.cu); falls back to launch_bwd_generic per branch when a shape has no tcgen05 kernel or
 // workspace is NULL
 bool tc_bwd_supported(const nsa_dims_t& dm, int branch);

@@ -51,6 +51,8 @@ __host__ __device__ inline int forced_code(int mode, int S_total, int l_sel, int
   return c;
 }
 __host__ __device__ inline int forced_code_default(int mode, int S_total, int l_sel) { return forced_code(mode, S_total, l_sel, 1, 2); }
+// forced_code(1, *, *, 1, 2) = {block 0, cb, cb - 1}: the decode rule's default, as a constant for kernels that select in place
+constexpr int kForcedDecodeDefault = 3 | (15 << 2) | (0 << 6) | (1 << 10);
 
 __host__ __device__ inline int prefill_range_cols_ex(int S_total, int l_sel, int n_sel, int force_init, int force_local) {
   int S_sel = S_total <= 0 ? 0 : (S_total + l_sel - 1) / l_sel;

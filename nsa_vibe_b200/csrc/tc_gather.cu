@@ -117,15 +117,18 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   GMisc* ms = reinterpret_cast<GMisc*>(smem + GSmem::misc);
   uint8_t* ring = smem + GSmem::ring;
-  if (a.state) {  // device-stepped decode: the step's position and row counts (after this step's produce + emit) live on the device
+  // position / rows present: kernel parameters, or (device-stepped decode, CUDA-graph replay) the device record after this step's
+  // produce + emit.  Kept in scalars: writing into the by-value `dm` would move the whole struct to local memory.
+  int k_t0 = dm.t0, k_S_sel_kv = dm.S_sel_kv, k_S_win_kv = dm.S_win_kv, k_win_off = dm.win_off, k_S_cmp = dm.S_cmp, k_S_sel = a.S_sel;
+  if (a.state) {
     const int t = a.state->t, S_raw = a.state->row_raw + 1;
-    dm.t0 = t;
-    dm.S_sel_kv = t + 1;
-    dm.S_win_kv = a.state->row_win + 1;
-    dm.win_off = t + 1 - dm.S_win_kv;
-    dm.S_cmp = a.state->S_cmp + ((S_raw >= dm.l && (S_raw - dm.l) % dm.d == 0) ? 1 : 0);
+    k_t0 = t;
+    k_S_sel_kv = t + 1;
+    k_S_win_kv = a.state->row_win + 1;
+    k_win_off = t + 1 - k_S_win_kv;
+    k_S_cmp = a.state->S_cmp + ((S_raw >= dm.l && (S_raw - dm.l) % dm.d == 0) ? 1 : 0);
     const int cover = t + 1 > dm.l_sel ? t + 1 : dm.l_sel;  // meta covers max(t+1, l_sel) tokens (nsa_attention.py:609-632)
-    a.S_sel = ceil_div(cover, dm.l_sel);
+    k_S_sel = ceil_div(cover, dm.l_sel);
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = dm.h;
@@ -165,7 +168,7 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
     const int s = tok - bg * dm.S;
     const int g = bg % dm.G, b = bg / dm.G;
     row = ((size_t)b * dm.S + s) * dm.G + g;
-    t = dm.t0 + s;
+    t = k_t0 + s;
     tp = tk;
   };
 
@@ -234,18 +237,18 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
         if (lane < dm.n_ranges && !a.fuse) {
           const int2 rr = *reinterpret_cast<const int2*>(a.ranges + (row * dm.n_ranges + lane) * 2);
           pr.a0 = rr.x < 0 ? 0 : rr.x;
-          pr.a1 = rr.y > dm.S_sel_kv ? dm.S_sel_kv : rr.y;
+          pr.a1 = rr.y > k_S_sel_kv ? k_S_sel_kv : rr.y;
         }
       } else if (lane == 0) {
         if (br == 0) {
-          pr.a1 = num_cmp_at(t, dm.l, dm.d, dm.S_cmp);
+          pr.a1 = num_cmp_at(t, dm.l, dm.d, k_S_cmp);
         } else {
           int lo = t - dm.w + 1;
-          if (lo < dm.win_off) lo = dm.win_off;
+          if (lo < k_win_off) lo = k_win_off;
           if (lo < 0) lo = 0;
-          pr.a0 = lo - dm.win_off;
-          pr.a1 = t + 1 - dm.win_off;
-          if (pr.a1 > dm.S_win_kv) pr.a1 = dm.S_win_kv;
+          pr.a0 = lo - k_win_off;
+          pr.a1 = t + 1 - k_win_off;
+          if (pr.a1 > k_S_win_kv) pr.a1 = k_S_win_kv;
           if (dm.w <= 0) pr.a1 = pr.a0;
         }
       }
@@ -272,7 +275,7 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
         mbar_wait(&ms->sel_ready[tp & 1], ((tok_sel_count[tp & 1]++) & 1));
         if (lane < dm.n_ranges) {
           a0 = fz->ranges[tp & 1][2 * lane] < 0 ? 0 : fz->ranges[tp & 1][2 * lane];
-          a1 = fz->ranges[tp & 1][2 * lane + 1] > dm.S_sel_kv ? dm.S_sel_kv : fz->ranges[tp & 1][2 * lane + 1];
+          a1 = fz->ranges[tp & 1][2 * lane + 1] > k_S_sel_kv ? k_S_sel_kv : fz->ranges[tp & 1][2 * lane + 1];
         }
       }
       const int nb = a1 > a0 ? (a1 - a0 + 63) >> 6 : 0;
@@ -540,7 +543,7 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
       if (a.fuse && br == 0) {
         g_named_bar(1, 128);
         const int nkeys = nblk > 0 ? (nblk - 1) * 64 + ms->blk_valid[ls][nblk - 1] : 0;
-        for (int blk = tid; blk < a.S_sel; blk += 128) {  // Eq.9 with l = 2d, l_sel = 4d, ascending compressed index
+        for (int blk = tid; blk < k_S_sel; blk += 128) {  // Eq.9 with l = 2d, l_sel = 4d, ascending compressed index
           const int i0 = 4 * blk;
           float acc = (i0 - 1 >= 0 && i0 - 1 < nkeys) ? 0.5f * fz->pkey[i0 - 1] : 0.f;
 #pragma unroll
@@ -552,7 +555,7 @@ gather_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
         if (warp == 1 && tp >= kGGateSlots) gate_of_token(row, tp, fz->qgp, fz->xs);  // tokens the prologue did not cover
         g_named_bar(1, 128);
         if (warp == 0) {
-          select_row_warp(fz->pg, a.S_sel, dm.l_sel, dm.n_sel, 1, forced_code_default(1, 0, dm.l_sel), dm.n_sel, t, fz->ranges[tp & 1]);
+          select_row_warp(fz->pg, k_S_sel, dm.l_sel, dm.n_sel, 1, kForcedDecodeDefault, dm.n_sel, t, fz->ranges[tp & 1]);
           __syncwarp();
           if (a.ranges_out && lane < dm.n_sel)
             *reinterpret_cast<int2*>(a.ranges_out + (row * dm.n_sel + lane) * 2) =
@@ -701,6 +704,7 @@ int launch_gather_tc(const nsa_dims_t& dm, int branch_mask, const void* Q, const
                      const nsa_gate_params_t* gp_fuse, int S_sel, int32_t* ranges_out, cudaStream_t stream,
                      const nsa_decode_state_t* state) {
   static_assert(sizeof(GMisc) <= 1280, "GMisc must fit its slot");
+  NSA_REQUIRE(forced_code_default(1, 0, dm.l_sel) == kForcedDecodeDefault, "gather(tc): forced-block code changed");
   if (dm.B * dm.S * dm.G == 0 || branch_mask == 0) return NSA_OK;
   NSA_REQUIRE((long long)dm.B * dm.S * dm.G < (1LL << 31), "gather(tc): B*S*G must be below 2^31");
   GatherArgs a;

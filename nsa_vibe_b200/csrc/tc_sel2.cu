@@ -581,6 +581,152 @@ sel2_merge_kernel(int n_rows, int h, const int* __restrict__ pair_of, const T* _
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// 3b. merge + gate + combine in one pass (no-grad prefill): O[row] = g_cmp O_cmp + g_sel merge_k(O_k, lse_k) + g_win O_win with the
+//     gates of GateMLP(mean_h Q[row]) (nsa_attention.py:32-82, :1356-1398) -- the selected branch's output and the gates never
+//     reach HBM, and the separate combine pass (405 MB read + 88 MB written at 64k) disappears.  64 threads per row (one per
+//     16-byte chunk, as in the merge kernel); the first warp of a row evaluates the gate from weights staged in shared memory
+//     while the row's partial loads are in flight.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kS2MergeRows * 64)
+sel2_merge_combine_kernel(nsa_dims_t dm, const T* __restrict__ Q, nsa_gate_params_t gp, const int* __restrict__ pair_of,
+                          const T* __restrict__ O_p, const float* __restrict__ lse_p, const T* __restrict__ O_cmp,
+                          const T* __restrict__ O_win, T* __restrict__ O, float* __restrict__ gates) {
+  extern __shared__ float smf[];
+  const int Dk = dm.Dk, H = dm.gate_hidden, h = dm.h;
+  float* w1t = smf;                 // [Dk][H]
+  float* b1 = w1t + Dk * H;         // [H]
+  float* w2 = b1 + H;               // [3][H]
+  float* b2 = w2 + 3 * H;           // [4]
+  float* qg = b2 + 4;               // [rows][Dk]
+  float* g3 = qg + kS2MergeRows * Dk;  // [rows][4]
+  const bool mlp = dm.gate_mode == NSA_GATE_MLP;
+  if (mlp) {
+    for (int i = threadIdx.x; i < Dk * H; i += blockDim.x) w1t[(i % Dk) * H + i / Dk] = gp.fc1_w[i];
+    for (int i = threadIdx.x; i < H; i += blockDim.x) b1[i] = gp.fc1_b ? gp.fc1_b[i] : 0.f;
+    for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) w2[i] = gp.fc2_w[i];
+    if (threadIdx.x < 3) b2[threadIdx.x] = gp.fc2_b ? gp.fc2_b[threadIdx.x] : 0.f;
+  }
+  __syncthreads();
+  const int n_rows = dm.B * dm.S * dm.G;
+  const int chunks = h * 8;                   // 16-byte chunks per row (Dv = 64), <= 64 threads per row
+  const int rl = threadIdx.x / 64, cidx = threadIdx.x % 64, lane = threadIdx.x & 31;
+  const float inv_tau = 1.0f / fmaxf(dm.gate_tau, 1e-6f);
+  const int n_iter = ceil_div(n_rows, gridDim.x * kS2MergeRows);
+  for (int it = 0; it < n_iter; ++it) {
+    const int row = (it * gridDim.x + blockIdx.x) * kS2MergeRows + rl;
+    const bool row_ok = row < n_rows;          // the 64 threads of a row agree: their named barrier stays matched
+    const bool act = row_ok && cidx < chunks;
+    const int head = cidx >> 3;
+    // ---- requests that depend on nothing: slot table, the other two branches' chunks, the row's query ----
+    int pk[kS2MaxSlots];
+    uint4 oc = make_uint4(0, 0, 0, 0), ow = make_uint4(0, 0, 0, 0);
+    if (act) {
+      const int4* pp = reinterpret_cast<const int4*>(pair_of + (size_t)row * kS2MaxSlots);
+#pragma unroll
+      for (int q = 0; q < kS2MaxSlots / 4; ++q) {
+        const int4 t = pp[q];
+        pk[4 * q] = t.x; pk[4 * q + 1] = t.y; pk[4 * q + 2] = t.z; pk[4 * q + 3] = t.w;
+      }
+      oc = *reinterpret_cast<const uint4*>(O_cmp + (size_t)row * h * 64 + cidx * 8);
+      ow = *reinterpret_cast<const uint4*>(O_win + (size_t)row * h * 64 + cidx * 8);
+    }
+    float g0 = 1.0f / 3.0f, g1 = 1.0f / 3.0f, g2 = 1.0f / 3.0f;
+    if (dm.gate_mode == NSA_GATE_CMP) { g0 = 1.f; g1 = 0.f; g2 = 0.f; }
+    else if (dm.gate_mode == NSA_GATE_SEL) { g0 = 0.f; g1 = 1.f; g2 = 0.f; }
+    else if (dm.gate_mode == NSA_GATE_WIN) { g0 = 0.f; g1 = 0.f; g2 = 1.f; }
+    else if (mlp) {
+      // q_gp = mean over heads (nsa_attention.py:1357): thread k of the row owns dimension k
+      if (row_ok && cidx < Dk) {
+        const T* qrow = Q + (size_t)row * h * Dk + cidx;
+        float m = 0.f;
+        for (int hh = 0; hh < h; ++hh) m += (float)qrow[hh * Dk];
+        qg[rl * Dk + cidx] = m / (float)h;
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + rl) : "memory");
+      if (cidx < 32) {  // first warp of the row: fc1 -> silu -> fc2 -> softmax / one-hot, same order of operations as combine_fast_kernel
+        const float* qgp = qg + rl * Dk;
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f;
+        for (int u = lane; u < H; u += 32) {
+          float a = b1[u];
+          int k = 0;
+          for (; k + 4 <= Dk; k += 4) {
+            const float4 qv = *reinterpret_cast<const float4*>(qgp + k);
+            a = fmaf(w1t[k * H + u], qv.x, a);
+            a = fmaf(w1t[(k + 1) * H + u], qv.y, a);
+            a = fmaf(w1t[(k + 2) * H + u], qv.z, a);
+            a = fmaf(w1t[(k + 3) * H + u], qv.w, a);
+          }
+          for (; k < Dk; ++k) a = fmaf(w1t[k * H + u], qgp[k], a);
+          const float x = a / (1.0f + expf(-a));  // silu
+          l0 = fmaf(w2[u], x, l0);
+          l1 = fmaf(w2[H + u], x, l1);
+          l2 = fmaf(w2[2 * H + u], x, l2);
+        }
+        l0 = (warp_sum(l0) + b2[0]) * inv_tau;
+        l1 = (warp_sum(l1) + b2[1]) * inv_tau;
+        l2 = (warp_sum(l2) + b2[2]) * inv_tau;
+        const float mx = fmaxf(l0, fmaxf(l1, l2));
+        const int am = l0 >= l1 ? (l0 >= l2 ? 0 : 2) : (l1 >= l2 ? 1 : 2);  // first maximum
+        const float second = am == 0 ? fmaxf(l1, l2) : (am == 1 ? fmaxf(l0, l2) : fmaxf(l0, l1));
+        float a0, a1, a2;
+        if (mx - second > 50.0f) {  // hard one-hot (nsa_attention.py:74-81)
+          a0 = am == 0 ? 1.f : 0.f; a1 = am == 1 ? 1.f : 0.f; a2 = am == 2 ? 1.f : 0.f;
+        } else {
+          const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), e2 = expf(l2 - mx);
+          const float inv = 1.0f / (e0 + e1 + e2);
+          a0 = e0 * inv; a1 = e1 * inv; a2 = e2 * inv;
+        }
+        if (lane == 0) { g3[rl * 4] = a0; g3[rl * 4 + 1] = a1; g3[rl * 4 + 2] = a2; }
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + rl) : "memory");
+      g0 = g3[rl * 4]; g1 = g3[rl * 4 + 1]; g2 = g3[rl * 4 + 2];
+    }
+    if (!act) continue;
+    if (gates && cidx == 0) {
+      gates[(size_t)row * 3] = g0;
+      gates[(size_t)row * 3 + 1] = g1;
+      gates[(size_t)row * 3 + 2] = g2;
+    }
+    // ---- merge the row's partials (slot order: deterministic), eight slots' chunks in flight at a time ----
+    float ls[kS2MaxSlots];
+#pragma unroll
+    for (int k = 0; k < kS2MaxSlots; ++k) ls[k] = pk[k] >= 0 ? lse_p[(size_t)pk[k] * h + head] : -INFINITY;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kS2MaxSlots; ++k) mx = fmaxf(mx, ls[k]);
+    float acc[8], den = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int k0 = 0; k0 < kS2MaxSlots; k0 += 8) {
+      uint4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        v[k] = pk[k0 + k] >= 0 ? *reinterpret_cast<const uint4*>(O_p + (size_t)pk[k0 + k] * h * 64 + cidx * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (ls[k0 + k] > -INFINITY) {
+          const float w = __expf(ls[k0 + k] - mx);
+          den += w;
+          const T* pv = reinterpret_cast<const T*>(&v[k]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, (float)pv[e], acc[e]);
+        }
+      }
+    }
+    const float sc = den > 0.f ? g1 / den : 0.f;  // empty row -> the selected branch contributes zeros (attention_kernels.py:769-771)
+    const T* ec = reinterpret_cast<const T*>(&oc);
+    const T* ew = reinterpret_cast<const T*>(&ow);
+    uint4 o;
+    T* po = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) po[e] = T(g0 * (float)ec[e] + sc * acc[e] + g2 * (float)ew[e]);
+    *reinterpret_cast<uint4*>(O + (size_t)row * h * 64 + cidx * 8) = o;
+  }
+}
+
 // ---- host ------------------------------------------------------------------------------------------------------
 int make_tmap_q_heads(CUtensorMap* out, const void* base, int dtype, int D, int h, int G, long long n_tokens, int box_tokens);
 
@@ -689,7 +835,7 @@ int sel2_build_index(const nsa_dims_t& dm, const int32_t* ranges, void* workspac
 
 template <typename T>
 static int launch_sel2_t(const nsa_dims_t& dm, const void* Q, const void* K, const void* V, const int32_t* ranges, void* O,
-                         float* lse, void* workspace, cudaStream_t stream) {
+                         float* lse, void* workspace, cudaStream_t stream, const Sel2Fuse* fuse) {
   const S2Geom gm = s2_geom(dm);
   const S2Ws w = s2_ws(dm);
   char* ws = reinterpret_cast<char*>(workspace);
@@ -737,18 +883,33 @@ static int launch_sel2_t(const nsa_dims_t& dm, const void* Q, const void* K, con
 #endif
   int mblocks = ceil_div(n_rows, kS2MergeRows);
   if (mblocks > 148 * 64) mblocks = 148 * 64;
+  if (fuse) {  // no-grad prefill: merge + gate + combine in one pass, the selected branch's output never reaches HBM
+    const int Hh = dm.gate_mode == NSA_GATE_MLP ? dm.gate_hidden : 0;
+    const size_t smem = ((size_t)dm.Dk * Hh + Hh + 3 * Hh + 4 + (size_t)kS2MergeRows * (dm.Dk + 4)) * sizeof(float);
+    sel2_merge_combine_kernel<T><<<mblocks, kS2MergeRows * 64, smem, stream>>>(dm, (const T*)Q, *fuse->gp, pair_of, O_p, lse_p,
+                                                                             (const T*)fuse->O_cmp, (const T*)fuse->O_win, (T*)fuse->O,
+                                                                             fuse->gates);
+    return check_launch("sel2_merge_combine_kernel");
+  }
   sel2_merge_kernel<T><<<mblocks, kS2MergeRows * 64, 0, stream>>>(n_rows, dm.h, pair_of, O_p, lse_p, (T*)O, lse);
   return check_launch("sel2_merge_kernel");
 }
 
+bool sel2_fuse_supported(const nsa_dims_t& dm) {
+  const int Hh = dm.gate_mode == NSA_GATE_MLP ? dm.gate_hidden : 0;
+  return tc_sel2_supported(dm) && dm.Dk == 64 && dm.Dk % 4 == 0 &&
+         ((size_t)dm.Dk * Hh + 4 * Hh + 4 + (size_t)kS2MergeRows * (dm.Dk + 4)) * sizeof(float) <= 48 * 1024;
+}
+
 int launch_sel2_tc(const nsa_dims_t& dm, const void* Q, const void* K, const void* V, const int32_t* ranges, void* O, float* lse,
-                   void* workspace, cudaStream_t stream) {
+                   void* workspace, cudaStream_t stream, const Sel2Fuse* fuse) {
   static_assert(sizeof(S2Misc) <= 256, "S2Misc must fit its slot");
   static_assert(2 * (S2Smem::total + 1024) <= 228 * 1024, "two sel2 CTAs must fit one SM");
   if (dm.B * dm.S * dm.G == 0) return NSA_OK;
   NSA_REQUIRE(workspace, "sel2: needs a workspace of nsa_workspace_bytes(NSA_WS_SEL) bytes");
-  if (dm.dtype == NSA_BF16) return launch_sel2_t<__nv_bfloat16>(dm, Q, K, V, ranges, O, lse, workspace, stream);
-  return launch_sel2_t<__half>(dm, Q, K, V, ranges, O, lse, workspace, stream);
+  NSA_REQUIRE(!fuse || sel2_fuse_supported(dm), "sel2: fused merge + combine does not serve this shape");
+  if (dm.dtype == NSA_BF16) return launch_sel2_t<__nv_bfloat16>(dm, Q, K, V, ranges, O, lse, workspace, stream, fuse);
+  return launch_sel2_t<__half>(dm, Q, K, V, ranges, O, lse, workspace, stream, fuse);
 }
 
 }  // namespace nsa
