@@ -599,8 +599,7 @@ sel2_merge_combine_kernel(nsa_dims_t dm, const T* __restrict__ Q, nsa_gate_param
   float* b1 = w1t + Dk * H;         // [H]
   float* w2 = b1 + H;               // [3][H]
   float* b2 = w2 + 3 * H;           // [4]
-  float* qg = b2 + 4;               // [rows][Dk]
-  float* g3 = qg + kS2MergeRows * Dk;  // [rows][4]
+  float* qg = b2 + 4;               // [warps][Dk]
   const bool mlp = dm.gate_mode == NSA_GATE_MLP;
   if (mlp) {
     for (int i = threadIdx.x; i < Dk * H; i += blockDim.x) w1t[(i % Dk) * H + i / Dk] = gp.fc1_w[i];
@@ -611,15 +610,13 @@ sel2_merge_combine_kernel(nsa_dims_t dm, const T* __restrict__ Q, nsa_gate_param
   __syncthreads();
   const int n_rows = dm.B * dm.S * dm.G;
   const int chunks = h * 8;                   // 16-byte chunks per row (Dv = 64), <= 64 threads per row
-  const int rl = threadIdx.x / 64, cidx = threadIdx.x % 64, lane = threadIdx.x & 31;
+  const int rl = threadIdx.x / 64, cidx = threadIdx.x % 64, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* qgp = qg + warp * Dk;
   const float inv_tau = 1.0f / fmaxf(dm.gate_tau, 1e-6f);
-  const int n_iter = ceil_div(n_rows, gridDim.x * kS2MergeRows);
-  for (int it = 0; it < n_iter; ++it) {
-    const int row = (it * gridDim.x + blockIdx.x) * kS2MergeRows + rl;
-    const bool row_ok = row < n_rows;          // the 64 threads of a row agree: their named barrier stays matched
-    const bool act = row_ok && cidx < chunks;
+  for (int row = blockIdx.x * kS2MergeRows + rl; row < n_rows; row += gridDim.x * kS2MergeRows) {  // warp-uniform trip count
+    const bool act = cidx < chunks;
     const int head = cidx >> 3;
-    // ---- requests that depend on nothing: slot table, the other two branches' chunks, the row's query ----
+    // ---- requests that depend on nothing: slot table, the other two branches' chunks ----
     int pk[kS2MaxSlots];
     uint4 oc = make_uint4(0, 0, 0, 0), ow = make_uint4(0, 0, 0, 0);
     if (act) {
@@ -631,68 +628,83 @@ sel2_merge_combine_kernel(nsa_dims_t dm, const T* __restrict__ Q, nsa_gate_param
       }
       oc = *reinterpret_cast<const uint4*>(O_cmp + (size_t)row * h * 64 + cidx * 8);
       ow = *reinterpret_cast<const uint4*>(O_win + (size_t)row * h * 64 + cidx * 8);
+    } else {
+#pragma unroll
+      for (int k = 0; k < kS2MaxSlots; ++k) pk[k] = -1;
     }
+    // ---- q_gp = mean over heads (nsa_attention.py:1357): each warp of the row builds its own copy (lane owns dims 2*lane, +1) ----
+    if (mlp) {
+      const T* qrow = Q + (size_t)row * h * Dk;
+      for (int k = 2 * lane; k < Dk; k += 64) {
+        float m0 = 0.f, m1 = 0.f;
+        for (int h0 = 0; h0 < h; h0 += 8) {
+          uint32_t v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = h0 + u < h ? *reinterpret_cast<const uint32_t*>(qrow + (h0 + u) * Dk + k) : 0u;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            m0 += (float)reinterpret_cast<const T*>(&v[u])[0];
+            m1 += (float)reinterpret_cast<const T*>(&v[u])[1];
+          }
+        }
+        qgp[k] = m0 / (float)h;
+        qgp[k + 1] = m1 / (float)h;
+      }
+      __syncwarp();
+    }
+    // ---- second round trip: the row's lse values and the first eight partial chunks (the slot table has arrived by now) ----
+    float ls[kS2MaxSlots];
+#pragma unroll
+    for (int k = 0; k < kS2MaxSlots; ++k) ls[k] = pk[k] >= 0 ? lse_p[(size_t)pk[k] * h + head] : -INFINITY;
+    uint4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      v[k] = pk[k] >= 0 ? *reinterpret_cast<const uint4*>(O_p + (size_t)pk[k] * h * 64 + cidx * 8) : make_uint4(0, 0, 0, 0);
+    // ---- gate MLP while those loads fly (both warps of a row evaluate it: no barrier between them) ----
     float g0 = 1.0f / 3.0f, g1 = 1.0f / 3.0f, g2 = 1.0f / 3.0f;
     if (dm.gate_mode == NSA_GATE_CMP) { g0 = 1.f; g1 = 0.f; g2 = 0.f; }
     else if (dm.gate_mode == NSA_GATE_SEL) { g0 = 0.f; g1 = 1.f; g2 = 0.f; }
     else if (dm.gate_mode == NSA_GATE_WIN) { g0 = 0.f; g1 = 0.f; g2 = 1.f; }
     else if (mlp) {
-      // q_gp = mean over heads (nsa_attention.py:1357): thread k of the row owns dimension k
-      if (row_ok && cidx < Dk) {
-        const T* qrow = Q + (size_t)row * h * Dk + cidx;
-        float m = 0.f;
-        for (int hh = 0; hh < h; ++hh) m += (float)qrow[hh * Dk];
-        qg[rl * Dk + cidx] = m / (float)h;
-      }
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + rl) : "memory");
-      if (cidx < 32) {  // first warp of the row: fc1 -> silu -> fc2 -> softmax / one-hot, same order of operations as combine_fast_kernel
-        const float* qgp = qg + rl * Dk;
-        float l0 = 0.f, l1 = 0.f, l2 = 0.f;
-        for (int u = lane; u < H; u += 32) {
-          float a = b1[u];
-          int k = 0;
-          for (; k + 4 <= Dk; k += 4) {
-            const float4 qv = *reinterpret_cast<const float4*>(qgp + k);
-            a = fmaf(w1t[k * H + u], qv.x, a);
-            a = fmaf(w1t[(k + 1) * H + u], qv.y, a);
-            a = fmaf(w1t[(k + 2) * H + u], qv.z, a);
-            a = fmaf(w1t[(k + 3) * H + u], qv.w, a);
-          }
-          for (; k < Dk; ++k) a = fmaf(w1t[k * H + u], qgp[k], a);
-          const float x = a / (1.0f + expf(-a));  // silu
-          l0 = fmaf(w2[u], x, l0);
-          l1 = fmaf(w2[H + u], x, l1);
-          l2 = fmaf(w2[2 * H + u], x, l2);
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f;
+      for (int u = lane; u < H; u += 32) {
+        float a = b1[u];
+        int k = 0;
+        for (; k + 4 <= Dk; k += 4) {
+          const float4 qv = *reinterpret_cast<const float4*>(qgp + k);
+          a = fmaf(w1t[k * H + u], qv.x, a);
+          a = fmaf(w1t[(k + 1) * H + u], qv.y, a);
+          a = fmaf(w1t[(k + 2) * H + u], qv.z, a);
+          a = fmaf(w1t[(k + 3) * H + u], qv.w, a);
         }
-        l0 = (warp_sum(l0) + b2[0]) * inv_tau;
-        l1 = (warp_sum(l1) + b2[1]) * inv_tau;
-        l2 = (warp_sum(l2) + b2[2]) * inv_tau;
-        const float mx = fmaxf(l0, fmaxf(l1, l2));
-        const int am = l0 >= l1 ? (l0 >= l2 ? 0 : 2) : (l1 >= l2 ? 1 : 2);  // first maximum
-        const float second = am == 0 ? fmaxf(l1, l2) : (am == 1 ? fmaxf(l0, l2) : fmaxf(l0, l1));
-        float a0, a1, a2;
-        if (mx - second > 50.0f) {  // hard one-hot (nsa_attention.py:74-81)
-          a0 = am == 0 ? 1.f : 0.f; a1 = am == 1 ? 1.f : 0.f; a2 = am == 2 ? 1.f : 0.f;
-        } else {
-          const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), e2 = expf(l2 - mx);
-          const float inv = 1.0f / (e0 + e1 + e2);
-          a0 = e0 * inv; a1 = e1 * inv; a2 = e2 * inv;
-        }
-        if (lane == 0) { g3[rl * 4] = a0; g3[rl * 4 + 1] = a1; g3[rl * 4 + 2] = a2; }
+        for (; k < Dk; ++k) a = fmaf(w1t[k * H + u], qgp[k], a);
+        const float x = a / (1.0f + expf(-a));  // silu
+        l0 = fmaf(w2[u], x, l0);
+        l1 = fmaf(w2[H + u], x, l1);
+        l2 = fmaf(w2[2 * H + u], x, l2);
       }
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + rl) : "memory");
-      g0 = g3[rl * 4]; g1 = g3[rl * 4 + 1]; g2 = g3[rl * 4 + 2];
+      l0 = (warp_sum(l0) + b2[0]) * inv_tau;
+      l1 = (warp_sum(l1) + b2[1]) * inv_tau;
+      l2 = (warp_sum(l2) + b2[2]) * inv_tau;
+      const float mxg = fmaxf(l0, fmaxf(l1, l2));
+      const int am = l0 >= l1 ? (l0 >= l2 ? 0 : 2) : (l1 >= l2 ? 1 : 2);  // first maximum
+      const float second = am == 0 ? fmaxf(l1, l2) : (am == 1 ? fmaxf(l0, l2) : fmaxf(l0, l1));
+      if (mxg - second > 50.0f) {  // hard one-hot (nsa_attention.py:74-81)
+        g0 = am == 0 ? 1.f : 0.f; g1 = am == 1 ? 1.f : 0.f; g2 = am == 2 ? 1.f : 0.f;
+      } else {
+        const float e0 = expf(l0 - mxg), e1 = expf(l1 - mxg), e2 = expf(l2 - mxg);
+        const float inv = 1.0f / (e0 + e1 + e2);
+        g0 = e0 * inv; g1 = e1 * inv; g2 = e2 * inv;
+      }
+      __syncwarp();  // qgp is rewritten for the next row
     }
-    if (!act) continue;
     if (gates && cidx == 0) {
       gates[(size_t)row * 3] = g0;
       gates[(size_t)row * 3 + 1] = g1;
       gates[(size_t)row * 3 + 2] = g2;
     }
-    // ---- merge the row's partials (slot order: deterministic), eight slots' chunks in flight at a time ----
-    float ls[kS2MaxSlots];
-#pragma unroll
-    for (int k = 0; k < kS2MaxSlots; ++k) ls[k] = pk[k] >= 0 ? lse_p[(size_t)pk[k] * h + head] : -INFINITY;
+    if (!act) continue;
+    // ---- merge the row's partials in slot order (deterministic) ----
     float mx = -INFINITY;
 #pragma unroll
     for (int k = 0; k < kS2MaxSlots; ++k) mx = fmaxf(mx, ls[k]);
@@ -701,10 +713,11 @@ sel2_merge_combine_kernel(nsa_dims_t dm, const T* __restrict__ Q, nsa_gate_param
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
 #pragma unroll
     for (int k0 = 0; k0 < kS2MaxSlots; k0 += 8) {
-      uint4 v[8];
+      if (k0 > 0) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        v[k] = pk[k0 + k] >= 0 ? *reinterpret_cast<const uint4*>(O_p + (size_t)pk[k0 + k] * h * 64 + cidx * 8) : make_uint4(0, 0, 0, 0);
+        for (int k = 0; k < 8; ++k)
+          v[k] = pk[k0 + k] >= 0 ? *reinterpret_cast<const uint4*>(O_p + (size_t)pk[k0 + k] * h * 64 + cidx * 8) : make_uint4(0, 0, 0, 0);
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         if (ls[k0 + k] > -INFINITY) {
@@ -885,7 +898,7 @@ static int launch_sel2_t(const nsa_dims_t& dm, const void* Q, const void* K, con
   if (mblocks > 148 * 64) mblocks = 148 * 64;
   if (fuse) {  // no-grad prefill: merge + gate + combine in one pass, the selected branch's output never reaches HBM
     const int Hh = dm.gate_mode == NSA_GATE_MLP ? dm.gate_hidden : 0;
-    const size_t smem = ((size_t)dm.Dk * Hh + Hh + 3 * Hh + 4 + (size_t)kS2MergeRows * (dm.Dk + 4)) * sizeof(float);
+    const size_t smem = ((size_t)dm.Dk * Hh + Hh + 3 * Hh + 4 + (size_t)kS2MergeRows * 2 * dm.Dk) * sizeof(float);
     sel2_merge_combine_kernel<T><<<mblocks, kS2MergeRows * 64, smem, stream>>>(dm, (const T*)Q, *fuse->gp, pair_of, O_p, lse_p,
                                                                              (const T*)fuse->O_cmp, (const T*)fuse->O_win, (T*)fuse->O,
                                                                              fuse->gates);
@@ -898,7 +911,7 @@ static int launch_sel2_t(const nsa_dims_t& dm, const void* Q, const void* K, con
 bool sel2_fuse_supported(const nsa_dims_t& dm) {
   const int Hh = dm.gate_mode == NSA_GATE_MLP ? dm.gate_hidden : 0;
   return tc_sel2_supported(dm) && dm.Dk == 64 && dm.Dk % 4 == 0 &&
-         ((size_t)dm.Dk * Hh + 4 * Hh + 4 + (size_t)kS2MergeRows * (dm.Dk + 4)) * sizeof(float) <= 48 * 1024;
+         ((size_t)dm.Dk * Hh + 4 * Hh + 4 + (size_t)kS2MergeRows * 2 * dm.Dk) * sizeof(float) <= 48 * 1024 && ((uintptr_t)0 == 0);
 }
 
 int launch_sel2_tc(const nsa_dims_t& dm, const void* Q, const void* K, const void* V, const int32_t* ranges, void* O, float* lse,
