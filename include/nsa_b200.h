@@ -155,6 +155,15 @@ int nsa_prefill_fwd(const nsa_dims_t* dm, const void* Q,
                     const void* K_cmp, const void* V_cmp, const int32_t* ranges,
                     const nsa_gate_params_t* gp, void* O, float* lse, float* gates, void* O_branches,
                     void* workspace, void* stream);
+/* Scoring + selection + nsa_prefill_fwd in one call: ranges [B,S,G,K,2] is an OUTPUT (K as for nsa_score_select), everything else
+ * as nsa_prefill_fwd.  For long 16-bit prefill this is more than the two calls back to back: the scorer's second pass and the
+ * compressed branch run as ONE kernel (one exponential per (row, compressed key) feeds both p_grp and O_cmp).
+ * workspace: nsa_workspace_bytes(dm, NSA_WS_PREFILL_FULL).  Replaces nsa_attention.py:1066-1398. */
+int nsa_prefill_full_fwd(const nsa_dims_t* dm, const void* Q,
+                         const void* K_sel, const void* V_sel, const void* K_win, const void* V_win,
+                         const void* K_cmp, const void* V_cmp, const nsa_gate_params_t* gp, int S_sel, int S_total,
+                         int sel_mode, int32_t* ranges, void* O, float* lse, float* gates, void* O_branches,
+                         void* workspace, void* stream);
 /* Backward of nsa_prefill_fwd.  dQ [B,S,G,h,Dk], dK_x/dV_x like their caches but fp32 (+=, caller
  * zeroes), dgates [B,S,G,3] fp32 (written).  workspace: nsa_workspace_bytes(dm, NSA_WS_BWD) (see nsa_branch_attn_bwd). */
 int nsa_prefill_bwd(const nsa_dims_t* dm, const void* Q,
@@ -279,7 +288,7 @@ typedef struct nsa_stats {
 int nsa_stats(const float* gates, int64_t n_gate_rows, const int32_t* ranges, int64_t n_range_rows, int K, int32_t* row_len,
               nsa_stats_t* out, void* stream);
 
-enum { NSA_WS_SCORE_SELECT = 0, NSA_WS_DECODE = 1, NSA_WS_PREFILL = 2, NSA_WS_SEL_BLOCKMAJOR = 3, NSA_WS_BWD = 4 };
+enum { NSA_WS_SCORE_SELECT = 0, NSA_WS_DECODE = 1, NSA_WS_PREFILL = 2, NSA_WS_SEL_BLOCKMAJOR = 3, NSA_WS_BWD = 4, NSA_WS_PREFILL_FULL = 5 };
 int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which);
 
 #ifdef __cplusplus

@@ -15,7 +15,7 @@ NSA_F32, NSA_BF16, NSA_F16 = 0, 1, 2
 NORM_FULL_ROW, NORM_CAUSAL = 0, 1
 GATE_MLP, GATE_UNIFORM, GATE_CMP, GATE_SEL, GATE_WIN = 0, 1, 2, 3, 4
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
-WS_SCORE_SELECT, WS_DECODE, WS_PREFILL, WS_SEL_BLOCKMAJOR, WS_BWD = 0, 1, 2, 3, 4
+WS_SCORE_SELECT, WS_DECODE, WS_PREFILL, WS_SEL_BLOCKMAJOR, WS_BWD, WS_PREFILL_FULL = 0, 1, 2, 3, 4, 5
 MAX_SEL_BLOCKS = 16  # NSA_MAX_SEL_BLOCKS
 
 
@@ -90,6 +90,7 @@ SIGNATURES = {
     "nsa_gate_fwd": (_I, [_DP, _P, _GP, _P, _P]),
     "nsa_gate_bwd": (_I, [_DP, _P, _GP, _P, _P, _P, _P, _P, _P, _P]),
     "nsa_prefill_fwd": (_I, [_DP] + [_P] * 8 + [_GP] + [_P] * 6),
+    "nsa_prefill_full_fwd": (_I, [_DP] + [_P] * 7 + [_GP, _I, _I, _I] + [_P] * 7),
     "nsa_prefill_bwd": (_I, [_DP] + [_P] * 22),
     "nsa_decode_fwd": (_I, [_DP] + [_P] * 7 + [_GP] + [_P] * 4),
     "nsa_rope_shape": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, C.c_float, C.c_float, _I, _I, _P]),

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libnsa_b200.so")
-SOURCES = ["api.cu", "select.cu", "generic.cu", "tc_dispatch.cu", "tc_score.cu", "tc_dense.cu", "tc_gather.cu", "tc_sel2.cu", "tc_bwd.cu", "producers.cu", "block_ops.cu", "stats.cu"]
+SOURCES = ["api.cu", "select.cu", "generic.cu", "tc_dispatch.cu", "tc_score.cu", "tc_score_cmp.cu", "tc_dense.cu", "tc_gather.cu", "tc_sel2.cu", "tc_bwd.cu", "producers.cu", "block_ops.cu", "stats.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

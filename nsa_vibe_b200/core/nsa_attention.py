@@ -235,19 +235,17 @@ class NSAAttention(nn.Module):
         sel_mode = 0 if (self._env_cache["prefill_batched"] and not via_decode) else 1
         cfg = self._cfg(causal_norm=via_decode)
         gate = self.gate.params() if cfg.gate_mode == ops.GATE_MLP else None
-        # the reference's three ranges (nsa_attention.py:1070, :1077, :1103) cover ONE fused launch pair here (scoring with the
-        # Eq.9 / Eq.10 folds, then top-n + range merging), so they are pushed nested around it
-        for name in ("pcmp_all", "map_pcmp_to_pslc", "topk+ranges"):
+        # The reference's ranges "pcmp_all", "map_pcmp_to_pslc", "topk+ranges" and "branch_attn+gate" (nsa_attention.py:1070, :1077,
+        # :1103, :1112) cover ONE C-ABI call here (scoring with the Eq.9 / Eq.10 folds, top-n + range merging, the three branches
+        # and the gated combine; for long prefill the scorer's second pass even shares a kernel with the compressed branch), so
+        # the four names are pushed nested around it.
+        for name in ("pcmp_all", "map_pcmp_to_pslc", "topk+ranges", "branch_attn+gate"):
             self._nvtx(name)
+        pre_ranges = None
         if self._env_cache["pcmp_mixed"] and Q.dtype == torch.float32:
             # NSA_P_CMP_MIXED (selection_scorer.py:46-56): the scores that drive the selection come from bf16 operands; the three
             # branches still attend in fp32 over the ranges chosen that way
             pre_ranges = ops.score_select(Q.detach().bfloat16(), K_cmp.detach().bfloat16(), cfg, mode=sel_mode, t0=t0)
-        else:
-            pre_ranges = ops.score_select(Q.detach(), K_cmp.detach(), cfg, mode=sel_mode, t0=t0)
-        for _ in range(3):
-            self._nvtx(None)
-        self._nvtx("branch_attn+gate")
         if t0 == 0:
             O, ranges, gates = ops.prefill_core(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, gate, cfg, sel_mode=sel_mode,
                                                 t0=0, stopgrad_gates=self._env_cache["stopgrad_gates"], ranges=pre_ranges,
@@ -261,7 +259,8 @@ class NSAAttention(nn.Module):
                 Q, kv.slab("K_sel"), kv.slab("V_sel"), kv.slab("K_win"), kv.slab("V_win"), K_cmp, V_cmp, gate, cfg,
                 sel_mode=sel_mode, t0=t0, S_sel_kv=n, S_win_kv=kv.length("K_win"), win_off=n - kv.length("K_win"), ranges=pre_ranges,
                 stopgrad_gates=self._env_cache["stopgrad_gates"], ranges_trusted=True)
-        self._nvtx(None)
+        for _ in range(4):
+            self._nvtx(None)
         if self._env_cache["strict_asserts"] and ranges.numel() > 0:
             tpos = torch.arange(t0, t0 + S, device=x.device).view(1, S, 1, 1)
             assert bool((ranges[..., 1] <= tpos + 1).all()), "Selection ranges cannot access future tokens."

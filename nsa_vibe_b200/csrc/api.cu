@@ -213,10 +213,14 @@ int nsa_gate_bwd(const nsa_dims_t* dm, const void* Q, const nsa_gate_params_t* g
   return launch_gate_bwd(*dm, Q, *gp, dgates, dQ, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b, (cudaStream_t)stream);
 }
 
-int nsa_prefill_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
-                    const void* V_win, const void* K_cmp, const void* V_cmp, const int32_t* ranges,
-                    const nsa_gate_params_t* gp, void* O, float* lse, float* gates, void* O_branches, void* workspace,
-                    void* stream) {
+}  // extern "C"
+
+// nsa_prefill_fwd; have_mask: branches whose output (and lse) already sit in their staging slot (the fused scorer + compressed
+// branch writes slot 0 before the ranges exist)
+static int prefill_fwd_impl(const nsa_dims_t* dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
+                            const void* V_win, const void* K_cmp, const void* V_cmp, const int32_t* ranges,
+                            const nsa_gate_params_t* gp, void* O, float* lse, float* gates, void* O_branches, void* workspace,
+                            void* stream, int have_mask) {
   if (int rc = validate_dims(dm, "prefill_fwd")) return rc;
   NSA_REQUIRE(Q && O && ranges && gp, "prefill_fwd: NULL pointer");
   NSA_REQUIRE(dm->gate_mode != NSA_GATE_MLP || (gp->fc1_w && gp->fc2_w), "prefill_fwd: MLP weights missing");
@@ -229,6 +233,7 @@ int nsa_prefill_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, cons
   int tc_mask = 0;
   for (int br = 0; br < 3; ++br)
     if (tc_branch_supported(*dm, br)) tc_mask |= 1 << br;
+  NSA_REQUIRE((have_mask & ~tc_mask) == 0, "prefill_fwd: a precomputed branch needs the tensor-core path");
   if (tc_mask == 0) {  // everything in the one fused SIMT kernel: branch outputs never leave the SM
     NSA_REQUIRE(dm->impl != NSA_IMPL_TC, "prefill_fwd: no tcgen05 kernel for this shape (impl=TC was forced)");
     a.O = O;
@@ -252,7 +257,7 @@ int nsa_prefill_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, cons
   static const bool fuse_env = getenv("NSA_B200_FUSE_COMBINE") && atoi(getenv("NSA_B200_FUSE_COMBINE")) == 1;
   const bool fuse = fuse_env && tc_mask == 7 && !O_branches && !lse && workspace && use_sel2(*dm) && sel2_fuse_supported(*dm);
   for (int br = 0; br < 3; ++br) {
-    if (!(tc_mask & (1 << br)) || (fuse && br == 1)) continue;
+    if (!(tc_mask & (1 << br)) || (fuse && br == 1) || (have_mask & (1 << br))) continue;
     void* ob = (char*)obr + br * per_branch;
     float* lb = lse ? lse + br * rows_h : nullptr;
     if (br == 1 && workspace && use_sel2(*dm)) {  // long prefill: KV-block-major selected branch
@@ -278,6 +283,54 @@ int nsa_prefill_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, cons
     if (int rc = launch_fwd_generic(d2, a, st)) return rc;
   }
   return launch_combine(*dm, Q, *gp, obr, O, gates, st);
+}
+
+extern "C" {
+
+int nsa_prefill_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
+                    const void* V_win, const void* K_cmp, const void* V_cmp, const int32_t* ranges,
+                    const nsa_gate_params_t* gp, void* O, float* lse, float* gates, void* O_branches, void* workspace,
+                    void* stream) {
+  return prefill_fwd_impl(dm, Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, ranges, gp, O, lse, gates, O_branches, workspace, stream, 0);
+}
+
+static bool full_fused(const nsa_dims_t& dm) {
+  return tc_eligible(dm) && tc_score_supported(dm) && tc_score_cmp_supported(dm) && tc_branch_supported(dm, 0) &&
+         tc_branch_supported(dm, 1) && tc_branch_supported(dm, 2);
+}
+
+int nsa_prefill_full_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
+                         const void* V_win, const void* K_cmp, const void* V_cmp, const nsa_gate_params_t* gp, int S_sel,
+                         int S_total, int sel_mode, int32_t* ranges, void* O, float* lse, float* gates, void* O_branches,
+                         void* workspace, void* stream) {
+  if (int rc = validate_dims(dm, "prefill_full_fwd")) return rc;
+  NSA_REQUIRE(Q && O && ranges && gp, "prefill_full_fwd: NULL pointer");
+  NSA_REQUIRE(sel_mode == 0 || sel_mode == 1, "prefill_full_fwd: mode %d", sel_mode);
+  const int K = sel_mode == 0 ? prefill_range_cols(S_total, dm->l_sel, dm->n_sel) : dm->n_sel;
+  NSA_REQUIRE(dm->n_ranges == K, "prefill_full_fwd: dims.n_ranges=%d but this rule emits %d columns", dm->n_ranges, K);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t ws_score = (tc_score_workspace(*dm) + 255) & ~(int64_t)255;
+  char* ws = reinterpret_cast<char*>(workspace);
+  if (!full_fused(*dm)) {  // the two stand-alone entry points back to back
+    if (int rc = nsa_score_select(dm, Q, K_cmp, S_sel, S_total, sel_mode, ranges, ws, stream)) return rc;
+    return nsa_prefill_fwd(dm, Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, ranges, gp, O, lse, gates, O_branches,
+                           ws ? ws + ws_score : nullptr, stream);
+  }
+  // Long prefill on tensor cores: pass 1 of the scorer (row statistics), then pass 2 FUSED with the compressed branch (one
+  // exponential per (row, compressed key) serves p_grp and O_cmp), selection, selected and sliding branches, gated combine.
+  NSA_REQUIRE(ws, "prefill_full_fwd: needs a workspace of nsa_workspace_bytes(NSA_WS_PREFILL_FULL) bytes");
+  NSA_REQUIRE((int64_t)dm->B * dm->S * dm->G * S_sel * 4 <= tc_score_workspace(*dm), "prefill_full_fwd: S_sel=%d exceeds the workspace", S_sel);
+  float* pg = reinterpret_cast<float*>(ws);
+  float* stats = reinterpret_cast<float*>(ws + ws_score);
+  char* ws_pre = ws + ws_score + tc_score_cmp_stats_bytes(*dm);
+  const size_t rows_h = (size_t)dm->B * dm->S * dm->G * dm->h;
+  void* o_cmp = O_branches ? O_branches : (void*)ws_pre;  // staging slot 0 of prefill_fwd_impl
+  if (int rc = launch_score_stats_tc(*dm, Q, K_cmp, stats, st)) return rc;
+  if (int rc = launch_score_cmp_tc(*dm, Q, K_cmp, V_cmp, S_sel, stats, pg, o_cmp, lse, st)) return rc;
+  (void)rows_h;
+  const int nf = forced_code_default(sel_mode, S_total, dm->l_sel);
+  if (int rc = launch_select(pg, dm->B * dm->S * dm->G, dm->S, dm->G, S_sel, dm->l_sel, dm->n_sel, sel_mode, nf, K, dm->t0, ranges, st)) return rc;
+  return prefill_fwd_impl(dm, Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, ranges, gp, O, lse, gates, O_branches, ws_pre, stream, 1);
 }
 
 int nsa_prefill_bwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
@@ -419,6 +472,9 @@ int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which) {
         }
       return 0;
     }
+    case NSA_WS_PREFILL_FULL:
+      return ((tc_score_workspace(*dm) + 255) & ~(int64_t)255) + (full_fused(*dm) ? tc_score_cmp_stats_bytes(*dm) : 0) +
+             nsa_workspace_bytes(dm, NSA_WS_PREFILL);
     case NSA_WS_SEL_BLOCKMAJOR:
       return tc_sel2_workspace(*dm);
     case NSA_WS_BWD:

@@ -89,6 +89,12 @@ int64_t tc_score_workspace(const nsa_dims_t& dm);
 int64_t tc_decode_workspace(const nsa_dims_t& dm);
 int launch_score_tc(const nsa_dims_t& dm, const void* Q, const void* Kc, int S_sel, int S_total, int sel_mode, int Kr,
                     float* p_grp, int32_t* ranges, void* workspace, cudaStream_t stream);
+// pass 1 of the scorer alone / pass 2 fused with the compressed branch (tc_score_cmp.cu)
+int launch_score_stats_tc(const nsa_dims_t& dm, const void* Q, const void* Kc, float* stats, cudaStream_t stream);
+bool tc_score_cmp_supported(const nsa_dims_t& dm);
+int64_t tc_score_cmp_stats_bytes(const nsa_dims_t& dm);
+int launch_score_cmp_tc(const nsa_dims_t& dm, const void* Q, const void* Kc, const void* Vc, int S_sel, const float* stats,
+                        float* p_grp, void* O_cmp, float* lse_cmp, cudaStream_t stream);
 int launch_branch_tc(const nsa_dims_t& dm, int branch, const void* Q, const void* K, const void* V, const int32_t* ranges,
                      void* O_b, float* lse_b, cudaStream_t stream);
 int launch_decode_tc(const nsa_dims_t& dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,

@@ -71,7 +71,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 template <typename T, int MT, int R>
 __global__ void __launch_bounds__(32 * (4 * MT + 2), 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, nsa_dims_t dm, int S_sel,
-                float* __restrict__ p_grp, int TOK, int sel_only) {
+                float* __restrict__ p_grp, int TOK, int sel_only, float2* __restrict__ stats_out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   using SM = ScSmem<MT>;
@@ -96,13 +96,16 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // keys i >= R*(t+1)/l_sel -- so the CTA stops pass 2 at its last row's limit: half of the pass-2 exponentials on average.
   // Pass 1 keeps every key: the full-row normaliser is the reference's.  Columns past the limit stay unwritten.
   int NT2 = NT;
-  if (sel_only) {
+  if (stats_out) {
+    NT2 = 0;  // pass 1 only: the row statistics go to stats_out, pass 2 runs fused with the compressed branch (tc_score_cmp.cu)
+  } else if (sel_only) {
     int need = ((dm.t0 + s_last + 1) / dm.l_sel) * R;
     if (need > nk_cta) need = nk_cta;
     NT2 = ceil_div(need, 128);
   }
   int NTO = ceil_div(S_sel, BPT);              // output tiles (tiles >= NT2 only flush the carry / write zeros)
   if (sel_only && NT2 + 1 < NTO) NTO = NT2 + 1;
+  if (stats_out) NTO = 0;
 
   // ---- setup ---------------------------------------------------------------------------------------------
   {  // rows of the Q tiles that TMA does not write (>= TOK*h) must hold finite data
@@ -179,6 +182,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     // ---- pass 1: row max and normaliser --------------------------------------------------------------------
     float m_run = -INFINITY, l_run = 0.f;
+    // with stats_out also the max over the row's CAUSAL keys (col < num_cmp(t)): the fused pass 2 + compressed branch falls back
+    // to it as the reference of the branch's softmax when the full-row one would underflow every causal probability
+    float mc_run = -INFINITY;
+    const int nkc = !row_ok ? 0 : num_cmp_at(t, dm.l, dm.d, dm.S_cmp);
     for (int kt = 0; kt < NT; ++kt) {
       const int it = kt, st = it % STG;
       mbar_wait(&ms->s_full[mt][st], (it / STG) & 1);
@@ -193,6 +200,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (ch < 3) tmem_ld32(tm_row + st * 128 + (ch + 1) * 32, nxt);
         const int col0 = kt * 128 + ch * 32;
         const bool wfull = __all_sync(0xffffffffu, col0 + 32 <= nk);  // one path per warp (no divergent double execution)
+        // causal max (stats_out only), votes taken before the per-lane branch below: every causal key of the warp's rows inside
+        // this chunk -> the chunk maximum serves; none -> skip; otherwise a masked scan
+        const bool c_all = stats_out != nullptr && __all_sync(0xffffffffu, col0 + 32 <= nkc || !row_ok);
+        const bool c_any = stats_out != nullptr && __any_sync(0xffffffffu, col0 < nkc);
         if (col0 < nk) {
           float cm = -INFINITY;
           if (wfull) {
@@ -204,6 +215,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               if (col0 + i >= nk) cur[i] = 0xff800000u;  // -inf
               cm = fmaxf(cm, __uint_as_float(cur[i]));
             }
+          }
+          if (c_all) {
+            if (row_ok) mc_run = fmaxf(mc_run, cm);
+          } else if (c_any) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < nkc) mc_run = fmaxf(mc_run, __uint_as_float(cur[i]));
           }
           const float m_new = fmaxf(m_run, cm);
           const float mc = m_new * c;
@@ -228,6 +246,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // p = exp2(s*c - offs); rows without keys produce zeros
     const bool has = l_run > 0.f;
     const float offs = has ? fmaf(m_run, c, log2f(l_run)) : 0.f;
+    if (stats_out) {  // (offs, causal max in the log2 domain); rows without keys: +inf makes every probability exp2(-inf) = 0
+      if (row_ok) {
+        const int head = r - tok_l * dm.h;
+        stats_out[(((size_t)b * dm.S + s) * dm.G + g) * dm.h + head] = make_float2(has ? offs : INFINITY, mc_run > -INFINITY ? mc_run * c : -INFINITY);
+      }
+    }
 
     // ---- pass 2: probabilities -> Eq.9 -> Eq.10 ------------------------------------------------------------
     float carry = 0.f;  // half of the last straddling compressed block, owed to the next selection block
@@ -313,7 +337,7 @@ int64_t tc_score_workspace(const nsa_dims_t& dm) {
 
 template <typename T, int MT>
 static int launch_score_t(const nsa_dims_t& dm, const void* Q, const void* Kc, int S_sel, float* p_grp, bool sel_only,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, float2* stats_out = nullptr) {
   const int TOK = 128 / dm.h;
   CUtensorMap tmQ, tmK;
   if (int rc = make_tmap_q_heads(&tmQ, Q, dm.dtype, 64, dm.h, dm.G, (long long)dm.B * dm.S, TOK)) return rc;
@@ -322,8 +346,15 @@ static int launch_score_t(const nsa_dims_t& dm, const void* Q, const void* Kc, i
   static std::atomic<unsigned long long> attr_done{0};
   if (int rc = ensure_smem_attr(kern, ScSmem<MT>::total, attr_done, "score tc")) return rc;
   const int grid = dm.B * dm.G * ceil_div(dm.S, MT * TOK);
-  kern<<<grid, 32 * (4 * MT + 2), ScSmem<MT>::total, stream>>>(tmQ, tmK, dm, S_sel, p_grp, TOK, sel_only ? 1 : 0);
+  kern<<<grid, 32 * (4 * MT + 2), ScSmem<MT>::total, stream>>>(tmQ, tmK, dm, S_sel, p_grp, TOK, sel_only ? 1 : 0, stats_out);
   return check_launch("score_tc_kernel");
+}
+
+// Pass 1 alone (4 M-tiles per CTA): per (token, head) row the pair (m*c + log2 l, causal max * c) that tc_score_cmp.cu consumes.
+int launch_score_stats_tc(const nsa_dims_t& dm, const void* Q, const void* Kc, float* stats, cudaStream_t stream) {
+  if (dm.B * dm.S * dm.G == 0) return NSA_OK;
+  if (dm.dtype == NSA_BF16) return launch_score_t<__nv_bfloat16, 4>(dm, Q, Kc, 1, nullptr, false, stream, reinterpret_cast<float2*>(stats));
+  return launch_score_t<__half, 4>(dm, Q, Kc, 1, nullptr, false, stream, reinterpret_cast<float2*>(stats));
 }
 
 int launch_score_tc(const nsa_dims_t& dm, const void* Q, const void* Kc, int S_sel, int S_total, int sel_mode, int Kr,

@@ -358,24 +358,36 @@ class _PrefillCore(torch.autograd.Function):
         Dv = V_sel.shape[-1]
         dev = Q.device
         geom = dict(geom or {})
-        if ranges_in is None:
-            ranges = score_select(Q, K_cmp, cfg, mode=sel_mode, t0=t0, S_cmp=geom.get("S_cmp"))
-        else:
-            ranges = _c(ranges_in.to(torch.int32))
         gate = (fc1_w, fc1_b, fc2_w, fc2_b) if fc1_w is not None else None
         gp, keep, hid = _gate_struct(gate, dev)
-        dm = make_dims(Q, cfg, t0=t0, K_sel=K_sel, K_win=K_win, K_cmp=K_cmp, V=V_sel, n_ranges=ranges.shape[3],
-                       gate_hidden=hid, **geom)
         need_grad = any(ctx.needs_input_grad[:11])
         O = torch.empty((B, S, G, h, Dv), dtype=Q.dtype, device=dev)
         gates = torch.empty((B, S, G, 3), dtype=torch.float32, device=dev)
         lse = torch.empty((3, B, S, G, h), dtype=torch.float32, device=dev) if need_grad else None
         O_br = torch.empty((3, B, S, G, h, Dv), dtype=Q.dtype, device=dev) if need_grad else None
-        ws_bytes = int(_lib.load().nsa_workspace_bytes(C.byref(dm), _lib.WS_PREFILL))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
-        if O.numel():
-            _call("nsa_prefill_fwd", C.byref(dm), _ptr(Q), _ptr(K_sel), _ptr(V_sel), _ptr(K_win), _ptr(V_win), _ptr(K_cmp),
-                  _ptr(V_cmp), _ptr(ranges), C.byref(gp), _ptr(O), _ptr(lse), _ptr(gates), _ptr(O_br), _ptr(ws), _stream())
+        if ranges_in is None:
+            # scoring + selection + the three branches + gated combine in ONE C-ABI call (nsa_prefill_full_fwd): for long 16-bit
+            # prefill the scorer's second pass and the compressed branch share one kernel
+            S_total = t0 + S
+            S_sel = num_sel_blocks(max(S_total, cfg.l_sel), cfg.l_sel)
+            K = prefill_range_cols(S_total, cfg.l_sel, cfg.n_sel) if sel_mode == 0 else cfg.n_sel
+            dm = make_dims(Q, cfg, t0=t0, K_sel=K_sel, K_win=K_win, K_cmp=K_cmp, V=V_sel, n_ranges=K, gate_hidden=hid, **geom)
+            ranges = torch.zeros((B, S, G, K, 2), dtype=torch.int32, device=dev)
+            ws_bytes = int(_lib.load().nsa_workspace_bytes(C.byref(dm), _lib.WS_PREFILL_FULL))
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+            if O.numel():
+                _call("nsa_prefill_full_fwd", C.byref(dm), _ptr(Q), _ptr(K_sel), _ptr(V_sel), _ptr(K_win), _ptr(V_win), _ptr(K_cmp),
+                      _ptr(V_cmp), C.byref(gp), S_sel, S_total, int(sel_mode), _ptr(ranges), _ptr(O), _ptr(lse), _ptr(gates), _ptr(O_br),
+                      _ptr(ws), _stream())
+        else:
+            ranges = _c(ranges_in.to(torch.int32))
+            dm = make_dims(Q, cfg, t0=t0, K_sel=K_sel, K_win=K_win, K_cmp=K_cmp, V=V_sel, n_ranges=ranges.shape[3],
+                           gate_hidden=hid, **geom)
+            ws_bytes = int(_lib.load().nsa_workspace_bytes(C.byref(dm), _lib.WS_PREFILL))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+            if O.numel():
+                _call("nsa_prefill_fwd", C.byref(dm), _ptr(Q), _ptr(K_sel), _ptr(V_sel), _ptr(K_win), _ptr(V_win), _ptr(K_cmp),
+                      _ptr(V_cmp), _ptr(ranges), C.byref(gp), _ptr(O), _ptr(lse), _ptr(gates), _ptr(O_br), _ptr(ws), _stream())
         if need_grad:
             ctx.save_for_backward(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, ranges, lse, gates, O_br, *[k for k in keep if k is not None])
             ctx.geom = geom
