@@ -53,17 +53,18 @@ def prefill_flops(S, c=M7C):
 
 
 def scorer_exps(S, c=M7C):
-    """Exponentials the scorer evaluates for one sequence when p_grp only feeds the selection: pass 1 (row max + normaliser)
-    over every compressed key, pass 2 (probabilities) up to each CTA's causal limit -- a CTA is 4 M-tiles of 128 // h tokens,
-    its limit the last row's 4 * ((t + 1) // l_sel) keys rounded up to whole 128-key tiles (tc_score.cu)."""
+    """Exponentials the split scorer evaluates for one sequence: pass 1 (row max + normaliser) over every compressed key; pass 2
+    (probabilities, shared with the compressed branch) per CTA of 4 M-tiles x 4 * (32 // h) tokens up to the larger of the last
+    row's selection limit 4 * ((t + 1) // l_sel) and its causal key count num_cmp(t), in whole 64-key tiles (tc_score_cmp.cu)."""
     H, l, d, ls = c["H"], c["l"], c["d"], c["l_sel"]
     S_cmp = 0 if S < l else (S - l) // d + 1
-    tok = 4 * (128 // c["h"])
+    tok = 4 * 4 * (32 // c["h"])
     p2 = 0
     for s0 in range(0, S, tok):
         s_last = min(S, s0 + tok) - 1
         need = min(S_cmp, (ls // d) * ((s_last + 1) // ls))
-        p2 += (min(S, s0 + tok) - s0) * min(S_cmp, -(-need // 128) * 128)
+        hi = num_cmp_at(s_last, l, d, S_cmp)
+        p2 += (min(S, s0 + tok) - s0) * min(S_cmp + 63, -(-max(need, hi) // 64) * 64)
     return float(H) * (S * S_cmp + p2)
 
 
@@ -482,9 +483,8 @@ def main():
     inp, gate = make_inputs(B, S, dev, seed=1234 + rank)
 
     def step(t):
-        ranges = ops.score_select(t["Q"], t["K_cmp"], cfg, mode=0)
-        O, _, _ = ops.prefill_core(t["Q"], t["K_sel"], t["V_sel"], t["K_win"], t["V_win"], t["K_cmp"], t["V_cmp"], gate, cfg,
-                                   sel_mode=0, ranges=ranges, ranges_trusted=True)
+        # ONE C-ABI call (nsa_prefill_full_fwd): scoring, selection, three branches, gated combine
+        O, _, _ = ops.prefill_core(t["Q"], t["K_sel"], t["V_sel"], t["K_win"], t["V_win"], t["K_cmp"], t["V_cmp"], gate, cfg, sel_mode=0)
         return O
 
     def barrier():
@@ -502,24 +502,16 @@ def main():
             sampler.wait_first()
         barrier()
         t_wall0 = time.time()
-        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
         n0 = lib.nsa_kernel_launches()
         e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e_start.record()
         for i in range(args.steps):
-            ev[i][0].record()
-            ranges = ops.score_select(inp["Q"], inp["K_cmp"], cfg, mode=0)
-            ev[i][1].record()
-            ops.prefill_core(inp["Q"], inp["K_sel"], inp["V_sel"], inp["K_win"], inp["V_win"], inp["K_cmp"], inp["V_cmp"], gate,
-                             cfg, sel_mode=0, ranges=ranges, ranges_trusted=True)
-            ev[i][2].record()
+            step(inp)
         e_end.record()
         barrier()
         launches = lib.nsa_kernel_launches() - n0
         clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
         ms_total = e_start.elapsed_time(e_end)
-        ms_score = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
-        ms_attn = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
         tt = torch.tensor([ms_total], device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -624,35 +616,50 @@ def main():
         dm_ = ops.make_dims(inp["Q"], cfg, K_sel=inp["K_sel"], K_win=inp["K_win"], K_cmp=inp["K_cmp"], V=inp["V_sel"], n_ranges=rg_.shape[3], gate_hidden=c["Dk"] // 2)
         staging_ = (3 * inp["Q"].numel() * 2 + 255) // 256 * 256
         sel_blockmajor = int(lib.nsa_workspace_bytes(_C.byref(dm_), _lib.WS_PREFILL)) > staging_
-        # the step's scorer stops its second pass at the causal limit (p_grp only feeds the selection); time it in place:
-        # score_select minus the stand-alone selection kernel.  "score_full_pgrp" is the same kernel asked for all of p_grp.
+        # The step (nsa_prefill_full_fwd) runs: scorer pass 1 (row statistics) -> pass 2 fused with the compressed branch -> selection
+        # -> selected branch (block-major: index, attention, merge) -> sliding branch -> gate + combine.  Each is timed in place
+        # through its stand-alone entry point on the same inputs.  "score_select_unfused" / "cmp_unfused" are the kernels the fusion
+        # replaced (stand-alone scorer with both passes; dense compressed branch), "score_full_pgrp" the scorer asked for all of p_grp.
+        fused_scorer = True
+        try:
+            st_ = ops.score_stats(inp["Q"], inp["K_cmp"], cfg)
+            t_p1 = t_of(lambda: ops.score_stats(inp["Q"], inp["K_cmp"], cfg))
+            t_p2 = t_of(lambda: ops.score_cmp(inp["Q"], inp["K_cmp"], inp["V_cmp"], cfg, st_))
+            del st_
+        except RuntimeError:
+            fused_scorer = False
         t_ss = t_of(lambda: ops.score_select(inp["Q"], inp["K_cmp"], cfg, mode=0))
         t_sel = t_of(lambda: ops.select_ranges_prefill(pg, c["l_sel"], c["n_sel"], S))
         t_full = t_of(lambda: ops.score_pgrp(inp["Q"], inp["K_cmp"], cfg))
-        kms = {"score": max(0.0, t_ss - t_sel),
-               "select": t_sel,
-               "cmp": t_of(lambda: ops.branch_attention(ops.BR_CMP, inp["Q"], inp["K_cmp"], inp["V_cmp"], cfg)),
-               "sel": t_of((lambda: ops.sel_attention_blockmajor(inp["Q"], inp["K_sel"], inp["V_sel"], cfg, rg_, ranges_trusted=True)) if sel_blockmajor else
-                           (lambda: ops.branch_attention(ops.BR_SEL, inp["Q"], inp["K_sel"], inp["V_sel"], cfg, rg_, ranges_trusted=True))),
-               "win": t_of(lambda: ops.branch_attention(ops.BR_WIN, inp["Q"], inp["K_win"], inp["V_win"], cfg))}
+        t_cmp = t_of(lambda: ops.branch_attention(ops.BR_CMP, inp["Q"], inp["K_cmp"], inp["V_cmp"], cfg))
+        kms = ({"score_pass1": t_p1, "score_pass2+cmp": t_p2} if fused_scorer else {"score": max(0.0, t_ss - t_sel), "cmp": t_cmp})
+        kms.update({"select": t_sel,
+                    "sel": t_of((lambda: ops.sel_attention_blockmajor(inp["Q"], inp["K_sel"], inp["V_sel"], cfg, rg_, ranges_trusted=True)) if sel_blockmajor else
+                                (lambda: ops.branch_attention(ops.BR_SEL, inp["Q"], inp["K_sel"], inp["V_sel"], cfg, rg_, ranges_trusted=True))),
+                    "win": t_of(lambda: ops.branch_attention(ops.BR_WIN, inp["Q"], inp["K_win"], inp["V_win"], cfg))})
         kms["gate_combine_and_rest"] = max(0.0, ms_step - sum(kms.values()))
         kms["score_full_pgrp"] = t_full  # not part of the step
+        kms["score_select_unfused"] = t_ss  # not part of the step
+        kms["cmp_unfused"] = t_cmp  # not part of the step
         del pg, rg_
         # ---- the step's outputs for the rows the CPU leg recomputes (parity at full size) ------------------------
         gpu_rows = None
         if rank == 0 and not args.no_cpu:
             t0p = S // 2
-            rg_step = ops.score_select(inp["Q"], inp["K_cmp"], cfg, mode=0)
-            O_step, _, _ = ops.prefill_core(inp["Q"], inp["K_sel"], inp["V_sel"], inp["K_win"], inp["V_win"], inp["K_cmp"], inp["V_cmp"],
-                                            gate, cfg, sel_mode=0, ranges=rg_step, ranges_trusted=True)
+            O_step, rg_step, _ = ops.prefill_core(inp["Q"], inp["K_sel"], inp["V_sel"], inp["K_win"], inp["V_win"], inp["K_cmp"], inp["V_cmp"],
+                                                  gate, cfg, sel_mode=0)
             sl = slice(0, t0p + args.cpu_rows)
+            if fused_scorer:  # O_cmp as the step computes it (the fused kernel), not the stand-alone dense kernel
+                o_cmp_step = ops.score_cmp(inp["Q"], inp["K_cmp"], inp["V_cmp"], cfg, ops.score_stats(inp["Q"], inp["K_cmp"], cfg))[1]
+            else:
+                o_cmp_step = ops.branch_attention(ops.BR_CMP, inp["Q"], inp["K_cmp"], inp["V_cmp"], cfg)
             gpu_rows = {"ranges": rg_step[:1, sl].clone(), "O": O_step[:1, sl].clone(),
-                        "O_cmp": ops.branch_attention(ops.BR_CMP, inp["Q"], inp["K_cmp"], inp["V_cmp"], cfg)[:1, sl].clone(),
+                        "O_cmp": o_cmp_step[:1, sl].clone(),
                         "O_win": ops.branch_attention(ops.BR_WIN, inp["Q"], inp["K_win"], inp["V_win"], cfg)[:1, sl].clone(),
                         "O_sel": (ops.sel_attention_blockmajor(inp["Q"], inp["K_sel"], inp["V_sel"], cfg, rg_step, ranges_trusted=True)
                                   if sel_blockmajor else
                                   ops.branch_attention(ops.BR_SEL, inp["Q"], inp["K_sel"], inp["V_sel"], cfg, rg_step, ranges_trusted=True))[:1, sl].clone()}
-            del rg_step, O_step
+            del rg_step, O_step, o_cmp_step
 
         # ---- decode @S=4096 -------------------------------------------------------------------------------
         decode = None
@@ -676,15 +683,27 @@ def main():
     fl = prefill_flops(S)
     traffic = load_traffic()
     # (name, ms, bound, algorithmic work per launch [FLOP or bytes], how the work is counted)
-    cand = [
-        ("score_tc_kernel", kms["score"], "tensor", B * fl["score"], "2*S*S_cmp*H*Dk (full-row scoring QK^T)"),
+    if "score_pass1" in kms:
+        # pass 1 carries the QK^T of every (row, key); pass 2 recomputes it up to the causal limit and adds the branch's P.V
+        cand = [
+            ("score_tc_kernel[pass 1: row statistics]", kms["score_pass1"], "tensor", B * fl["score"],
+             "2*S*S_cmp*H*Dk (full-row scoring QK^T; pass 2's recomputation is not counted as work)"),
+            ("score_cmp_tc_kernel[pass 2 + compressed branch]", kms["score_pass2+cmp"], "tensor", B * fl["cmp_pv"],
+             "2*H*Dv*sum_t num_cmp(t) (the branch's P.V; the QK^T it shares with scoring is counted under pass 1)"),
+        ]
+    else:
+        cand = [
+            ("score_tc_kernel", kms["score"], "tensor", B * fl["score"], "2*S*S_cmp*H*Dk (full-row scoring QK^T)"),
+            ("dense_attn_tc_kernel[cmp]", kms["cmp"], "tensor", B * fl["cmp_pv"], "2*H*Dv*sum_t num_cmp(t) (P.V; its QK^T is counted under scoring)"),
+        ]
+    cand += [
         ("select_kernel", kms["select"], "hbm", B * S * c["G"] * (4.0 * num_sel_blocks(S, c["l_sel"]) + 8.0 * c["n_sel"]),
          "4*S_sel B read + 8*n_sel B written per (b,t,g) row"),
-        ("dense_attn_tc_kernel[cmp]", kms["cmp"], "tensor", B * fl["cmp_pv"], "2*H*Dv*sum_t num_cmp(t) (P.V; its QK^T is counted under scoring)"),
-        ("sel2_attn_kernel+index+merge[sel, KV-block-major]" if sel_blockmajor else "gather_attn_tc_kernel[sel]", kms["sel"], "hbm",
-         B * fl["sel_gather_bytes"], "2 B*G*(Dk+Dv)*sum_t min(t+1, n_sel*l_sel) K/V bytes a query-major gather moves (the reference's own GB/s definition, triton_sel_kernel/__init__.py:483-509); the block-major kernels read each block once per run of queries, so >1 of HBM peak is expected"),
+        ("sel2_attn_kernel+index+merge[sel, KV-block-major]" if sel_blockmajor else "gather_attn_tc_kernel[sel]", kms["sel"], "tensor",
+         B * fl["sel"], "2*H*(Dk+Dv)*sum_t min(t+1, n_sel*l_sel) (QK^T + PV of the selected keys)"),
         ("dense_attn_tc_kernel[win]", kms["win"], "tensor", B * fl["win"], "2*H*(Dk+Dv)*sum_t min(t+1, w)"),
     ]
+    ms_scorer = kms["score_pass1"] + kms["score_pass2+cmp"] if "score_pass1" in kms else kms["score"]
     kname, k_ms, bound, work, how = max(cand, key=lambda x: x[1])
     if bound == "tensor":
         achieved, peak, unit, src = work / (k_ms * 1e-3) / 1e12, pk["tf_sustained"], "TFLOP/s", pk["src"] + " (bf16 sustained)"
@@ -693,12 +712,12 @@ def main():
     roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
                 "traffic": traffic.get(kname), "kernel": kname, "kernel_ms": k_ms, "algorithmic_work": how, "peak_source": src,
                 "exp_bound": {"what": "MUFU ex2 throughput also bounds the scorer: S*S_cmp*H exponentials in pass 1 plus pass 2 up to each CTA's causal limit",
-                              "ex2_per_launch": B * scorer_exps(S), "ex2_per_s": B * scorer_exps(S) / (kms["score"] * 1e-3),
+                              "ex2_per_launch": B * scorer_exps(S), "ex2_per_s": B * scorer_exps(S) / (ms_scorer * 1e-3),
                               "peak_ex2_per_s": 16 * 148 * 1.965e9, "peak_source": "tools/ubench/mufu.cu on this pool: 15.9 ex2/clk/SM",
-                              "frac": B * scorer_exps(S) / (kms["score"] * 1e-3) / (16 * 148 * 1.965e9)},
+                              "frac": B * scorer_exps(S) / (ms_scorer * 1e-3) / (16 * 148 * 1.965e9)},
                 "step_tflops": B * fl["total"] / (ms_step * 1e-3) / 1e12,
                 "step_frac_of_tensor_peak": B * fl["total"] / (ms_step * 1e-3) / 1e12 / pk["tf_sustained"],
-                "kernel_ms_breakdown": kms, "ms_score_select": ms_score, "ms_prefill_fwd": ms_attn,
+                "kernel_ms_breakdown": kms,
                 "algorithmic_gflop_per_seq": {k: v / 1e9 for k, v in fl.items() if k != "sel_gather_bytes"},
                 "per_kernel": [{"kernel": n_, "ms": m_, "bound": b_, "achieved": (w_ / (m_ * 1e-3) / (1e12 if b_ == "tensor" else 1e9)),
                                 "unit": "TFLOP/s" if b_ == "tensor" else "GB/s",

@@ -164,6 +164,15 @@ int nsa_prefill_full_fwd(const nsa_dims_t* dm, const void* Q,
                          const void* K_cmp, const void* V_cmp, const nsa_gate_params_t* gp, int S_sel, int S_total,
                          int sel_mode, int32_t* ranges, void* O, float* lse, float* gates, void* O_branches,
                          void* workspace, void* stream);
+/* The two kernels nsa_prefill_full_fwd runs for the scorer on long 16-bit prefill, on their own (profiling, tests):
+ *   nsa_score_stats: pass 1 -- stats [B,S,G,h,2] fp32 = (m*c + log2 l of the p_cmp softmax, c * max over the row's causal keys),
+ *                    c = scale * log2 e, normaliser per dims.norm_mode;
+ *   nsa_score_cmp:   pass 2 fused with the compressed branch -- p_grp [B,S,G,S_sel] fp32 (written up to each CTA's selection limit,
+ *                    as the staging of nsa_score_select is), O_cmp [B,S,G,h,Dv], lse_cmp [B,S,G,h] (may be NULL).
+ * Both return NSA_ERR_UNSUPPORTED for shapes the fused path does not serve. */
+int nsa_score_stats(const nsa_dims_t* dm, const void* Q, const void* K_cmp, float* stats, void* stream);
+int nsa_score_cmp(const nsa_dims_t* dm, const void* Q, const void* K_cmp, const void* V_cmp, int S_sel, const float* stats,
+                  float* p_grp, void* O_cmp, float* lse_cmp, void* stream);
 /* Backward of nsa_prefill_fwd.  dQ [B,S,G,h,Dk], dK_x/dV_x like their caches but fp32 (+=, caller
  * zeroes), dgates [B,S,G,3] fp32 (written).  workspace: nsa_workspace_bytes(dm, NSA_WS_BWD) (see nsa_branch_attn_bwd). */
 int nsa_prefill_bwd(const nsa_dims_t* dm, const void* Q,

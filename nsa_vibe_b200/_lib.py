@@ -91,6 +91,8 @@ SIGNATURES = {
     "nsa_gate_bwd": (_I, [_DP, _P, _GP, _P, _P, _P, _P, _P, _P, _P]),
     "nsa_prefill_fwd": (_I, [_DP] + [_P] * 8 + [_GP] + [_P] * 6),
     "nsa_prefill_full_fwd": (_I, [_DP] + [_P] * 7 + [_GP, _I, _I, _I] + [_P] * 7),
+    "nsa_score_stats": (_I, [_DP, _P, _P, _P, _P]),
+    "nsa_score_cmp": (_I, [_DP, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "nsa_prefill_bwd": (_I, [_DP] + [_P] * 22),
     "nsa_decode_fwd": (_I, [_DP] + [_P] * 7 + [_GP] + [_P] * 4),
     "nsa_rope_shape": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, C.c_float, C.c_float, _I, _I, _P]),

@@ -294,6 +294,27 @@ int nsa_prefill_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, cons
   return prefill_fwd_impl(dm, Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, ranges, gp, O, lse, gates, O_branches, workspace, stream, 0);
 }
 
+int nsa_score_stats(const nsa_dims_t* dm, const void* Q, const void* K_cmp, float* stats, void* stream) {
+  if (int rc = validate_dims(dm, "score_stats")) return rc;
+  NSA_REQUIRE(Q && K_cmp && stats, "score_stats: NULL pointer");
+  if (!(tc_eligible(*dm) && tc_score_supported(*dm) && tc_score_cmp_supported(*dm))) {
+    set_error("score_stats: the split scorer serves long 16-bit prefill only (Dk = Dv = 64, l = 2d, l_sel = 4d, h <= 32)");
+    return NSA_ERR_UNSUPPORTED;
+  }
+  return launch_score_stats_tc(*dm, Q, K_cmp, stats, (cudaStream_t)stream);
+}
+
+int nsa_score_cmp(const nsa_dims_t* dm, const void* Q, const void* K_cmp, const void* V_cmp, int S_sel, const float* stats,
+                  float* p_grp, void* O_cmp, float* lse_cmp, void* stream) {
+  if (int rc = validate_dims(dm, "score_cmp")) return rc;
+  NSA_REQUIRE(Q && K_cmp && V_cmp && stats && p_grp && O_cmp, "score_cmp: NULL pointer");
+  if (!(tc_eligible(*dm) && tc_score_supported(*dm) && tc_score_cmp_supported(*dm))) {
+    set_error("score_cmp: the fused scorer + compressed branch serves long 16-bit prefill only");
+    return NSA_ERR_UNSUPPORTED;
+  }
+  return launch_score_cmp_tc(*dm, Q, K_cmp, V_cmp, S_sel, stats, p_grp, O_cmp, lse_cmp, (cudaStream_t)stream);
+}
+
 static bool full_fused(const nsa_dims_t& dm) {
   return tc_eligible(dm) && tc_score_supported(dm) && tc_score_cmp_supported(dm) && tc_branch_supported(dm, 0) &&
          tc_branch_supported(dm, 1) && tc_branch_supported(dm, 2);

@@ -15,6 +15,10 @@
 //                the full-row reference (future keys dominate it: possible only with the full-row normaliser) takes mcc as the
 //                reference of its branch softmax instead -- a second exponential for that warp's tile, never seen on sane data.
 //
+// Row layout: a row is one (token, head); the h rows of a token sit on consecutive TMEM lanes of ONE warp (TOKW = 32 / h tokens per
+// warp, 4 * TOKW per M-tile; lanes >= TOKW * h of a warp are padding: 2 of 32 at h = 6), so the Eq.10 head sum never crosses a
+// warp: it goes through a per-warp shared-memory buffer between two __syncwarp()s.  With the tokens packed densely (21 per M-tile
+// at h = 6) three tokens straddled warps and every key tile cost two 128-thread named barriers per M-tile: 1.10 ms at 64k.
 // Warp roles: warps [0, 16) softmax (thread = TMEM lane = row), warp 16 TMA producer, warp 17 MMA issuer.
 #include <stdlib.h>
 
@@ -38,7 +42,7 @@ struct FcSmem {
   static constexpr int k = q + kFcMT * kFcTile;
   static constexpr int v = k + kFcKS * kFcKV;
   static constexpr int p = v + kFcVS * kFcKV;
-  static constexpr int red = p + kFcMT * kFcTile;                       // [MT][128][17] fp32
+  static constexpr int red = p + kFcMT * kFcTile;                       // [16 warps][32 rows][17] fp32
   static constexpr int misc = red + kFcMT * 128 * kFcRedLd * 4;
   static constexpr int total = misc + 512 + 1024;
 };
@@ -72,7 +76,6 @@ __device__ __forceinline__ void fc_ld_wait32(uint32_t (&r)[32]) {
                :
                : "memory");
 }
-__device__ __forceinline__ void fc_named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 template <typename T>
 __global__ void __launch_bounds__(32 * (4 * kFcMT + 2), 1)
@@ -132,9 +135,11 @@ score_cmp_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == kSoftWarps) {
     // ===== TMA producer ====================================================================================
     if (lane == 0 && n > 0) {
+      const int TOKW = TOK / 4;
       mbar_expect_tx(&ms->q_full, MT * TOK * dm.h * 128);
       for (int m = 0; m < MT; ++m)
-        tma_load_4d(smem + SM::q + m * kFcTile, &tmQ, &ms->q_full, 0, 0, g, b * dm.S + s_base + m * TOK);
+        for (int q = 0; q < 4; ++q)  // one box per warp quarter: TOKW tokens x h heads land on that warp's first TOKW * h rows
+          tma_load_4d(smem + SM::q + m * kFcTile + q * 32 * 128, &tmQ, &ms->q_full, 0, 0, g, b * dm.S + s_base + m * TOK + q * TOKW);
       for (int i = 0; i < n; ++i) {
         const int ks = i % kFcKS, vs = i % kFcVS;
         mbar_wait(&ms->k_empty[ks], ((i / kFcKS) & 1) ^ 1);
@@ -192,11 +197,12 @@ score_cmp_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
   } else {
     // ===== softmax / Eq.9 / Eq.10 / P warps ================================================================
-    const int mt = warp >> 2;
+    const int mt = warp >> 2, w4 = warp & 3;
     const int r = tid & 127;
-    const int tok_l = r / dm.h, head = r - tok_l * dm.h;
-    const int s = s_base + mt * TOK + tok_l;
-    const bool row_ok = tok_l < TOK && s < dm.S;
+    const int TOKW = TOK / 4;
+    const int tok_w = lane / dm.h, head = lane - tok_w * dm.h;
+    const int s = s_base + mt * TOK + w4 * TOKW + tok_w;
+    const bool row_ok = tok_w < TOKW && s < dm.S;
     const int t = dm.t0 + s;
     // rows that are not stored (padding rows of the M-tile, tokens beyond S) behave like the CTA's last row, so they never push
     // their warp onto a masked path
@@ -217,8 +223,8 @@ score_cmp_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t tm_O = tmem + lane_off + MT * NK + mt * 64;
     uint8_t* prow = smem + SM::p + mt * kFcTile + r * 128;
     const int sw = r & 7;
-    float* red = reinterpret_cast<float*>(smem + SM::red) + (size_t)mt * 128 * kFcRedLd;
-    float* rb = red + (size_t)r * kFcRedLd;
+    float* red = reinterpret_cast<float*>(smem + SM::red) + (size_t)warp * 32 * kFcRedLd;  // this warp's 32 rows
+    float* rb = red + (size_t)lane * kFcRedLd;
 
     float carry = 0.f;   // half of the last straddling compressed block, owed to the next selection block
     float rowsum = 0.f;  // sum of the branch's (masked) numerators, relative to `ref`
@@ -296,11 +302,11 @@ score_cmp_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int jj = 0; jj < kFcBPT; ++jj) rb[jj] = jj == 0 ? carry : 0.f;
         carry = 0.f;
       }
-      fc_named_bar(1 + mt, 128);
-      // Eq.10: sum the h head rows of each token; consecutive threads write consecutive blocks of one token
-      for (int idx = r; idx < TOK * kFcBPT; idx += 128) {
+      __syncwarp();
+      // Eq.10: sum the h head rows of each of the warp's tokens; consecutive lanes write consecutive blocks of one token
+      for (int idx = lane; idx < TOKW * kFcBPT; idx += 32) {
         const int tk = idx / kFcBPT, cc = idx % kFcBPT;
-        const int ss = s_base + mt * TOK + tk;
+        const int ss = s_base + mt * TOK + w4 * TOKW + tk;
         const int j = i * kFcBPT + cc;
         if (ss < dm.S && j < S_sel) {
           float a = 0.f;
@@ -308,7 +314,7 @@ score_cmp_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           p_grp[(((size_t)b * dm.S + ss) * dm.G + g) * S_sel + j] = a;
         }
       }
-      fc_named_bar(1 + mt, 128);  // single buffer: the next tile's partial sums overwrite it
+      __syncwarp();  // single buffer: the next tile's partial sums overwrite it
     }
 
     // ---- epilogue: O (TMEM, all key tiles accumulated) / rowsum -> global ------------------------------------
@@ -357,7 +363,7 @@ bool tc_score_cmp_supported(const nsa_dims_t& dm) {
   static const bool off = getenv("NSA_B200_FUSE_CMP") && atoi(getenv("NSA_B200_FUSE_CMP")) == 0;  // A/B switch (benchmarks / tests)
   if (off || dm.impl == NSA_IMPL_SIMT) return false;
   if (!((dm.dtype == NSA_BF16 || dm.dtype == NSA_F16) && dm.Dk == 64 && dm.Dv == 64 && dm.l == 2 * dm.d && dm.l_sel == 4 * dm.d)) return false;
-  if (dm.h < 1 || dm.h > 64 || dm.S_cmp < 1 || dm.S < 1) return false;
+  if (dm.h < 1 || dm.h > 32 || dm.S_cmp < 1 || dm.S < 1) return false;  // a token's heads must fit one warp
   return (long long)dm.B * dm.G * dm.S >= 4LL * (128 / dm.h) * 148;
 }
 
@@ -368,9 +374,9 @@ int64_t tc_score_cmp_stats_bytes(const nsa_dims_t& dm) {
 template <typename T>
 static int launch_score_cmp_t(const nsa_dims_t& dm, const void* Q, const void* Kc, const void* Vc, int S_sel, const float* stats,
                               float* p_grp, void* O_cmp, float* lse_cmp, cudaStream_t stream) {
-  const int TOK = 128 / dm.h;
+  const int TOK = 4 * (32 / dm.h);  // TOKW = 32 / h tokens per warp quarter
   CUtensorMap tmQ, tmK, tmV;
-  if (int rc = make_tmap_q_heads(&tmQ, Q, dm.dtype, 64, dm.h, dm.G, (long long)dm.B * dm.S, TOK)) return rc;
+  if (int rc = make_tmap_q_heads(&tmQ, Q, dm.dtype, 64, dm.h, dm.G, (long long)dm.B * dm.S, TOK / 4)) return rc;
   if (int rc = make_tmap_rows(&tmK, Kc, dm.dtype, 64, dm.S_cmp, 64, (long long)dm.cap_cmp * 64, dm.B * dm.G, kFcNK)) return rc;
   if (int rc = make_tmap_rows(&tmV, Vc, dm.dtype, 64, dm.S_cmp, 64, (long long)dm.cap_cmp * 64, dm.B * dm.G, kFcNK)) return rc;
   auto kern = score_cmp_tc_kernel<T>;

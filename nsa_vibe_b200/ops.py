@@ -220,6 +220,33 @@ def score_select(Q: torch.Tensor, K_cmp: torch.Tensor, cfg: NSAConfig, *, mode: 
     return out
 
 
+def score_stats(Q: torch.Tensor, K_cmp: torch.Tensor, cfg: NSAConfig, *, t0: int = 0) -> torch.Tensor:
+    """Pass 1 of the split scorer (nsa_score_stats): [B,S,G,h,2] fp32 row statistics.  Long 16-bit prefill only."""
+    _require_cuda(Q, K_cmp)
+    Q, K_cmp = _c(Q.detach()), _c(K_cmp.detach())
+    B, S, G, h, _ = Q.shape
+    dm = make_dims(Q, cfg, t0=t0, K_cmp=K_cmp)
+    out = torch.empty((B, S, G, h, 2), dtype=torch.float32, device=Q.device)
+    _call("nsa_score_stats", C.byref(dm), _ptr(Q), _ptr(K_cmp), _ptr(out), _stream())
+    return out
+
+
+def score_cmp(Q: torch.Tensor, K_cmp: torch.Tensor, V_cmp: torch.Tensor, cfg: NSAConfig, stats: torch.Tensor, *, t0: int = 0,
+              S_sel: Optional[int] = None):
+    """Pass 2 of the scorer fused with the compressed branch (nsa_score_cmp) -> (p_grp staging [B,S,G,S_sel] fp32, O_cmp, lse_cmp)."""
+    _require_cuda(Q, K_cmp, V_cmp, stats)
+    Q, K_cmp, V_cmp = _c(Q.detach()), _c(K_cmp.detach()), _c(V_cmp.detach())
+    B, S, G, h, _ = Q.shape
+    if S_sel is None:
+        S_sel = num_sel_blocks(max(t0 + S, cfg.l_sel), cfg.l_sel)
+    dm = make_dims(Q, cfg, t0=t0, K_cmp=K_cmp, V=V_cmp)
+    pg = torch.empty((B, S, G, S_sel), dtype=torch.float32, device=Q.device)
+    O = torch.empty((B, S, G, h, V_cmp.shape[-1]), dtype=Q.dtype, device=Q.device)
+    lse = torch.empty((B, S, G, h), dtype=torch.float32, device=Q.device)
+    _call("nsa_score_cmp", C.byref(dm), _ptr(Q), _ptr(K_cmp), _ptr(V_cmp), int(S_sel), _ptr(_c(stats)), _ptr(pg), _ptr(O), _ptr(lse), _stream())
+    return pg, O, lse
+
+
 # ----------------------------------------------------------------------------------------------------
 # (3)(4) single-branch attention with autograd
 # ----------------------------------------------------------------------------------------------------

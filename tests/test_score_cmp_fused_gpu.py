@@ -41,7 +41,8 @@ def test_fused_pass2_cmp_equals_separate_kernels(dtype, norm, B, S, h, sel_mode)
         assert torch.equal(r_f, r_s)
         O_s, _, g_s = ops.prefill_core(*dev, gd, cfg, sel_mode=sel_mode, ranges=r_s, ranges_trusted=True)
     assert torch.equal(g_f, g_s)
-    assert (O_f.float() - O_s.float()).abs().max() <= 2e-2
+    dd = (O_f.float() - O_s.float()).abs()  # two 16-bit results: one rounding step of an O(1) value apart at most, equal on average
+    assert dd.max() <= 4e-2 and dd.mean() <= 5e-4, (float(dd.max()), float(dd.mean()))
     # the compressed branch alone (forced gate): fused vs stand-alone dense kernel vs oracle
     cfg_c = ops.NSAConfig(l=L, d=D, l_sel=LS, n_sel=N, w=W, norm_mode=nm, gate_mode=ops.GATE_CMP)
     with torch.no_grad():
@@ -76,7 +77,7 @@ def test_fused_pass2_cmp_saves_what_backward_needs():
     O_f, r_f, g_f = run(False)   # nsa_prefill_full_fwd: lse / O_cmp saved by the fused kernel
     O_s, r_s, g_s = run(True)    # nsa_prefill_fwd: the dense compressed kernel
     assert torch.equal(r_f, r_s)
-    assert (O_f.float() - O_s.float()).abs().max() <= 2e-2
+    assert (O_f.float() - O_s.float()).abs().max() <= 4e-2
     for a, b in zip(g_f, g_s):
         assert torch.isfinite(a.float()).all()
         assert float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)) <= 3e-2
