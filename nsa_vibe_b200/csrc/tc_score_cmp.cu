@@ -34,7 +34,7 @@ constexpr int kFcKS = 3, kFcVS = 3;   // K / V ring stages
 constexpr int kFcTile = 128 * 128;    // bytes: 128 rows x 64 x 2 B
 constexpr int kFcKV = kFcNK * 128;    // bytes of one K or V tile
 constexpr int kFcBPT = kFcNK / 4;     // selection blocks completed per key tile (R = l_sel / d = 4)
-constexpr int kFcRedLd = kFcBPT + 1;  // padded row of the head-reduction buffer
+constexpr int kFcRedLd = kFcBPT + 4;  // row of the head-reduction buffer: 20 floats = 80 B keeps 16-byte accesses aligned and conflict-free
 constexpr float kRefGap = 100.f;      // log2 units
 
 struct FcSmem {
@@ -42,7 +42,7 @@ struct FcSmem {
   static constexpr int k = q + kFcMT * kFcTile;
   static constexpr int v = k + kFcKS * kFcKV;
   static constexpr int p = v + kFcVS * kFcKV;
-  static constexpr int red = p + kFcMT * kFcTile;                       // [16 warps][32 rows][17] fp32
+  static constexpr int red = p + kFcMT * kFcTile;                       // [16 warps][32 rows][20] fp32
   static constexpr int misc = red + kFcMT * 128 * kFcRedLd * 4;
   static constexpr int total = misc + 512 + 1024;
 };
@@ -262,26 +262,32 @@ score_cmp_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               cur[e] = __float_as_uint(pv);
             }
           }
-          // Eq.9 (l = 2d, l_sel = 4d): block j = 1/2 p[4j-1] + p[4j] + p[4j+1] + p[4j+2] + 1/2 p[4j+3], ascending compressed index
+          // Eq.9 (l = 2d, l_sel = 4d): block j = 1/2 p[4j-1] + p[4j] + p[4j+1] + p[4j+2] + 1/2 p[4j+3], ascending compressed index.
+          // `carry` holds the UNSCALED p[4j-1]; the halves enter through FMAs: 0.5 * x is exact, so fma(0.5, x, y) rounds like
+          // y + 0.5 * x -- the same four roundings per block as the stand-alone scorer.
+          float blk[4];
+          const float chunk_in = carry;
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
-            float a = carry;
-            a += __uint_as_float(cur[jj * 4]);
+            float a = fmaf(0.5f, carry, __uint_as_float(cur[jj * 4]));
             a += __uint_as_float(cur[jj * 4 + 1]);
             a += __uint_as_float(cur[jj * 4 + 2]);
-            const float half = 0.5f * __uint_as_float(cur[jj * 4 + 3]);
-            a += half;
-            carry = half;
-            rb[ch * 4 + jj] = a;
+            carry = __uint_as_float(cur[jj * 4 + 3]);
+            blk[jj] = fmaf(0.5f, carry, a);
           }
-          float r0 = 0.f, r1 = 0.f;
+          *reinterpret_cast<float4*>(rb + ch * 4) = make_float4(blk[0], blk[1], blk[2], blk[3]);
           uint32_t pk[8];
+          if (plain) {  // the branch's numerators are the scorer's: their sum over the chunk follows from the four block sums
+            rowsum += ((blk[0] + blk[1]) + (blk[2] + blk[3])) + 0.5f * (carry - chunk_in);
+          } else {
+            float r0 = 0.f, r1 = 0.f;
 #pragma unroll
-          for (int e = 0; e < 16; e += 4) {
-            r0 += pp[e] + pp[e + 1];
-            r1 += pp[e + 2] + pp[e + 3];
+            for (int e = 0; e < 16; e += 4) {
+              r0 += pp[e] + pp[e + 1];
+              r1 += pp[e + 2] + pp[e + 3];
+            }
+            rowsum += r0 + r1;
           }
-          rowsum += r0 + r1;
 #pragma unroll
           for (int e = 0; e < 16; e += 2) pk[e >> 1] = pack2(T(), pp[e], pp[e + 1]);
 #pragma unroll
@@ -299,19 +305,32 @@ score_cmp_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       } else {
 #pragma unroll
-        for (int jj = 0; jj < kFcBPT; ++jj) rb[jj] = jj == 0 ? carry : 0.f;
+        for (int jj = 0; jj < kFcBPT; ++jj) rb[jj] = jj == 0 ? 0.5f * carry : 0.f;
         carry = 0.f;
       }
       __syncwarp();
-      // Eq.10: sum the h head rows of each of the warp's tokens; consecutive lanes write consecutive blocks of one token
-      for (int idx = lane; idx < TOKW * kFcBPT; idx += 32) {
-        const int tk = idx / kFcBPT, cc = idx % kFcBPT;
+      // Eq.10: sum the h head rows of each of the warp's tokens, heads in ascending order like the stand-alone scorer; a lane
+      // owns four consecutive blocks of one token (one 16-byte load per head, one 16-byte store)
+      if (lane < TOKW * (kFcBPT / 4)) {
+        const int tk = lane / (kFcBPT / 4), qd = lane % (kFcBPT / 4);
         const int ss = s_base + mt * TOK + w4 * TOKW + tk;
-        const int j = i * kFcBPT + cc;
+        const int j = i * kFcBPT + qd * 4;
         if (ss < dm.S && j < S_sel) {
-          float a = 0.f;
-          for (int hh = 0; hh < dm.h; ++hh) a += red[(size_t)(tk * dm.h + hh) * kFcRedLd + cc];
-          p_grp[(((size_t)b * dm.S + ss) * dm.G + g) * S_sel + j] = a;
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float* src = red + (size_t)(tk * dm.h) * kFcRedLd + qd * 4;
+          for (int hh = 0; hh < dm.h; ++hh) {
+            const float4 v = *reinterpret_cast<const float4*>(src + (size_t)hh * kFcRedLd);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+          }
+          float* dst = p_grp + (((size_t)b * dm.S + ss) * dm.G + g) * S_sel + j;
+          if (j + 4 <= S_sel && (S_sel & 3) == 0) {
+            *reinterpret_cast<float4*>(dst) = a;
+          } else {
+            dst[0] = a.x;
+            if (j + 1 < S_sel) dst[1] = a.y;
+            if (j + 2 < S_sel) dst[2] = a.z;
+            if (j + 3 < S_sel) dst[3] = a.w;
+          }
         }
       }
       __syncwarp();  // single buffer: the next tile's partial sums overwrite it
