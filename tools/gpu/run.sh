@@ -13,9 +13,9 @@ for step in "$@"; do
     bench:*) python bench.py ${step#bench:} > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err ;;
     ref) python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_ref.json 2> gpurun_out/${tag}_ref.err ;;
     launches) ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
-                python bench.py --steps 2 --warmup 3 --no-cpu --no-decode --no-train > gpurun_out/${tag}_launches.log 2>&1 ;;
+                python bench.py --steps 2 --warmup 3 --no-cpu --no-decode --no-train --no-train-ddp > gpurun_out/${tag}_launches.log 2>&1 ;;
     ncu:*) IFS=: read -r _ kre skip cnt script <<< "$step"
-           script=${script:-"bench.py --steps 2 --warmup 3 --no-cpu --no-decode --no-train"}
+           script=${script:-"bench.py --steps 2 --warmup 3 --no-cpu --no-decode --no-train --no-train-ddp"}
            name=$(echo "$kre" | tr -c 'A-Za-z0-9_' '_')
            ncu --set full --clock-control none --import-source on -k regex:$kre -s ${skip:-0} -c ${cnt:-1} -o gpurun_out/${tag}_ncu_$name \
              python $script > gpurun_out/${tag}_ncu_$name.log 2>&1
