@@ -225,6 +225,13 @@ int nsa_rope_shape(const void* x, void* y, int B, int S, int V, int D, int src_l
 int nsa_phi_avgpool(const void* x, void* y, int BG, int S, int D, int l, int d, int rope, int t0, float base, float scale,
                     int backward, int dtype, void* stream);
 
+/* Learnable phi (phi = "mlp", nsa_attention.py:275-291, :1741-1777): a depthwise Conv1d over time, kernel l, stride d, no bias,
+ * taps w [D][l] fp32 (nn.Conv1d.weight [D,1,l]), applied to RoPE(K_raw) (rope = 1) or V_raw (rope = 0); initialised to 1/l it is
+ * the average pool.  mode 0: y [BG,S_cmp,D] = conv(x [BG,S,D]);  mode 1: x = dy [BG,S_cmp,D] -> y = dx [BG,S,D];
+ * mode 2: x = the raw stream [BG,S,D], dy [BG,S_cmp,D] -> y = dw [D][l] fp32 (written). */
+int nsa_phi_conv(const void* x, const float* w, void* y, const void* dy, int BG, int S, int D, int l, int d, int rope, int t0,
+                 float base, float scale, int mode, int dtype, void* stream);
+
 /* Projection-split producer: the fused projection output y [B, S, H*Dk + G*(3*Dk + 3*Dv)] =
  * (Q | K_sel | V_sel | K_win | V_win | K_raw | V_raw) of S tokens per sequence is rotated (Q as one H*Dk-wide vector, K_sel /
  * K_win per Dk-vector; row s at position t + s) and scattered: Q into q_out [B,S,H*Dk], the six streams into rows
@@ -262,6 +269,7 @@ typedef struct nsa_decode_emit {
   int32_t BG, cap_raw, cap_cmp, Dk, Dv, l, d;
   float base, scale;
   int32_t dtype;
+  const float *w_k, *w_v;      /* learnable phi taps [Dk][l] / [Dv][l] fp32, or NULL = average pool */
 } nsa_decode_emit_t;
 int nsa_decode_emit(const nsa_decode_emit_t* a, void* stream);
 /* state += one step: t, row_win, row_raw, ctr_idx advance by one, S_cmp by one when this step emitted. */

@@ -57,7 +57,8 @@ class DecodeEmit(C.Structure):
 
     _fields_ = [("state", C.c_void_p), ("K_raw", C.c_void_p), ("V_raw", C.c_void_p), ("K_cmp", C.c_void_p), ("V_cmp", C.c_void_p),
                 ("BG", C.c_int32), ("cap_raw", C.c_int32), ("cap_cmp", C.c_int32), ("Dk", C.c_int32), ("Dv", C.c_int32),
-                ("l", C.c_int32), ("d", C.c_int32), ("base", C.c_float), ("scale", C.c_float), ("dtype", C.c_int32)]
+                ("l", C.c_int32), ("d", C.c_int32), ("base", C.c_float), ("scale", C.c_float), ("dtype", C.c_int32),
+                ("w_k", C.c_void_p), ("w_v", C.c_void_p)]
 
 
 class Stats(C.Structure):
@@ -97,6 +98,7 @@ SIGNATURES = {
     "nsa_decode_fwd": (_I, [_DP] + [_P] * 7 + [_GP] + [_P] * 4),
     "nsa_rope_shape": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, C.c_float, C.c_float, _I, _I, _P]),
     "nsa_phi_avgpool": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, C.c_float, C.c_float, _I, _I, _P]),
+    "nsa_phi_conv": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, C.c_float, C.c_float, _I, _I, _P]),
     "nsa_decode_produce": (_I, [C.c_void_p, _P]),
     "nsa_decode_emit": (_I, [C.c_void_p, _P]),
     "nsa_decode_advance": (_I, [_P, _I, _I, _P]),

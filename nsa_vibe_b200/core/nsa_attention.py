@@ -94,9 +94,8 @@ class NSAAttention(nn.Module):
         self.l, self.d, self.l_sel, self.n_sel, self.w = l, d, l_sel, n_sel, w
         self.gate_temp = gate_temp
         self.phi_type = (phi or "avg").lower()
-        if self.phi_type != "avg":
-            # the reference's phi="mlp" is broken (phi_v_conv is always None, nsa_attention.py:289-291)
-            raise NotImplementedError("only phi='avg' is supported on the B200 path")
+        if self.phi_type not in ("avg", "mlp"):
+            raise ValueError(f"phi must be 'avg' or 'mlp', got {phi!r}")
         self._last_gates: Optional[torch.Tensor] = None
         self._last_ranges: Optional[torch.Tensor] = None
         self._fallback_counters = {k: 0 for k in (
@@ -111,6 +110,17 @@ class NSAAttention(nn.Module):
         self.W_V_cmp = nn.Linear(dim, n_kv_groups * d_v, bias=False)
         self.out = nn.Linear(n_heads * d_v, dim, bias=False)
         self.gate = GateMLP(d_k, gate_hidden)
+        # Learnable phi (nsa_attention.py:275-291): depthwise Conv1d over time, kernel l, stride d, initialised to the average pool.
+        # (In the reference the line that clears phi_v_conv is dedented one level too far, :289-291, so phi_v_conv is always None
+        # and phi="mlp" asserts on first use; this is the constructor as its comment describes it.)
+        self.phi_k_conv: Optional[nn.Conv1d] = None
+        self.phi_v_conv: Optional[nn.Conv1d] = None
+        if self.phi_type == "mlp":
+            self.phi_k_conv = nn.Conv1d(d_k, d_k, kernel_size=l, stride=d, groups=d_k, bias=False)
+            self.phi_v_conv = nn.Conv1d(d_v, d_v, kernel_size=l, stride=d, groups=d_v, bias=False)
+            with torch.no_grad():
+                self.phi_k_conv.weight.fill_(1.0 / float(l))
+                self.phi_v_conv.weight.fill_(1.0 / float(l))
         self.use_flash_default = use_flash      # accepted for API compatibility; no flash-attn route exists
         self.use_triton_sel = use_triton_sel    # accepted for API compatibility; no Triton route exists
         self._cache_env_vars()
@@ -188,6 +198,9 @@ class NSAAttention(nn.Module):
                         f"This ensures proper causal ordering in decode steps.")
         return self._forward_decode(x, kv)
 
+    def _phi_weights(self):
+        return (self.phi_k_conv.weight, self.phi_v_conv.weight) if self.phi_type == "mlp" else ()
+
     def _proj_weights(self):
         return (self.W_Q.weight, self.W_K_sel.weight, self.W_V_sel.weight, self.W_K_win.weight, self.W_V_win.weight,
                 self.W_K_cmp.weight, self.W_V_cmp.weight)
@@ -203,6 +216,13 @@ class NSAAttention(nn.Module):
             w_all = self._decode_weights()        # inference: the stacked matrix is cached (rebuilt when a weight changes)
         y = F.linear(x, w_all)
         return ops.project_split(y, H=self.n_heads, G=self.n_kv_groups, Dk=self.d_k, Dv=self.d_v, t0=t0, scale=self.rope_scale)
+
+    def _phi(self, K_raw: torch.Tensor, V_raw: torch.Tensor, t0: int = 0):
+        """phi over rows at positions t0.. (compress_pool.py:9-38 / nsa_attention.py:1741-1758): one kernel per stream."""
+        if self.phi_type == "mlp":
+            return ops.phi_conv(K_raw, V_raw, self.phi_k_conv.weight, self.phi_v_conv.weight, self.l, self.d, t0=t0,
+                                rope_scale=self.rope_scale)
+        return ops.phi_avgpool(K_raw, V_raw, self.l, self.d, t0=t0)
 
     def _nvtx(self, name: Optional[str]):
         if self._env_cache["nvtx"]:
@@ -226,9 +246,9 @@ class NSAAttention(nn.Module):
         # emission count at zero) the raw stream is recorded, keeping "emit every d after warm-up l" absolute.
         kv.append_cmp_raw(K_raw.detach(), V_raw.detach())
         if t0 == 0:
-            K_cmp, V_cmp = ops.phi_avgpool(K_raw, V_raw, self.l, self.d)
+            K_cmp, V_cmp = self._phi(K_raw, V_raw)
         else:
-            K_cmp, V_cmp = ops.phi_avgpool(kv.K_cmp_raw_seq, kv.V_cmp_raw_seq, self.l, self.d)
+            K_cmp, V_cmp = self._phi(kv.K_cmp_raw_seq, kv.V_cmp_raw_seq)
         kv.update_compressed(K_cmp.detach(), V_cmp.detach(), self.l, self.d)
 
         via_decode = self.prefill_tile > 0
@@ -308,7 +328,7 @@ class NSAAttention(nn.Module):
         cache slab was reallocated or replaced, the batch / dtype changed, or a weight / gate / rope setting moved."""
         ws = self._proj_weights()
         cfg_key = (float(self.gate_temp), self.gate.mode(), float(self.rope_scale), aux, x.dtype, x.shape[0],
-                   tuple((p.data_ptr(), p._version) for p in (*self.gate.params(), *ws, self.out.weight)))
+                   tuple((p.data_ptr(), p._version) for p in (*self.gate.params(), *ws, self.out.weight, *self._phi_weights())))
         ent = getattr(kv, "_decode_graph", None)
         if ent is not None and ent[0] is self and ent[1] == cfg_key:
             gs = ent[2]
@@ -333,7 +353,7 @@ class NSAAttention(nn.Module):
                                          gate_hidden=hid):
             gs = ops.DecodeGraphStep(x.reshape(x.shape[0], self.dim), self._decode_weights(), self.out.weight.detach(), slabs, cmp_slabs,
                                      ctr, H=self.n_heads, G=self.n_kv_groups, Dk=self.d_k, Dv=self.d_v, cfg=cfg, gate=gate,
-                                     rope_scale=self.rope_scale)
+                                     rope_scale=self.rope_scale, phi_w=self._phi_weights() or None)
             st = (kv.rows_present("K_sel"), kv.rows_present("K_win"), kv.rows_present("K_cmp_raw_seq"), kv.rows_present("K_cmp"),
                   kv.counter_column() if aux else 0)
             gs.set_state(*st)
@@ -395,8 +415,8 @@ class NSAAttention(nn.Module):
             if aux:
                 kv.commit_counters()
             if S_raw >= self.l and (S_raw - self.l) % self.d == 0:  # emission schedule (:587-604)
-                K_new, V_new = ops.phi_avgpool(kv.K_cmp_raw_seq[:, :, S_raw - self.l:S_raw],
-                                               kv.V_cmp_raw_seq[:, :, S_raw - self.l:S_raw], self.l, self.d, t0=S_raw - self.l)
+                K_new, V_new = self._phi(kv.K_cmp_raw_seq[:, :, S_raw - self.l:S_raw], kv.V_cmp_raw_seq[:, :, S_raw - self.l:S_raw],
+                                         t0=S_raw - self.l)
                 kv.append_compressed(K_new, V_new)
                 if not kv.same_compressed_slabs(plan.cmp_slabs):
                     # the emission outgrew the compressed slab: finish this step on the new slabs (the step's Q, already produced

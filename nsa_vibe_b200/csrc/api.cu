@@ -451,6 +451,13 @@ int nsa_phi_avgpool(const void* x, void* y, int BG, int S, int D, int l, int d, 
   return launch_phi_avgpool(x, y, BG, S, D, l, d, rope, t0, base, scale, backward, dtype, (cudaStream_t)stream);
 }
 
+int nsa_phi_conv(const void* x, const float* w, void* y, const void* dy, int BG, int S, int D, int l, int d, int rope, int t0,
+                 float base, float scale, int mode, int dtype, void* stream) {
+  NSA_REQUIRE(dtype == NSA_F32 || dtype == NSA_BF16 || dtype == NSA_F16, "phi_conv: dtype %d", dtype);
+  NSA_REQUIRE(mode >= 0 && mode <= 2 && (w || mode == 2), "phi_conv: mode %d / NULL weights", mode);
+  return launch_phi_avgpool(x, y, BG, S, D, l, d, rope, t0, base, scale, mode, dtype, (cudaStream_t)stream, w, dy);
+}
+
 int nsa_decode_produce(const nsa_decode_produce_t* a, void* stream) {
   NSA_REQUIRE(a, "decode_produce: NULL argument block");
   NSA_REQUIRE(a->dtype == NSA_F32 || a->dtype == NSA_BF16 || a->dtype == NSA_F16, "decode_produce: dtype %d", a->dtype);

@@ -106,7 +106,7 @@ rope_shape_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int S, int 
 template <typename T>
 __global__ void __launch_bounds__(256)
 phi_avgpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int BG, int S, int S_cmp, int D, int l, int d, int rope, int t0,
-                       float base, float scale) {
+                       float base, float scale, const float* __restrict__ w) {  // w [D][l]: learnable phi (depthwise conv), else mean
   const long long n = (long long)BG * S_cmp * (D / 2);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int p = (int)(i % (D / 2));
@@ -124,12 +124,17 @@ phi_avgpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int BG, int S
         v0 = w0;
         v1 = w1;
       }
-      a0 = __fadd_rn(a0, v0);
-      a1 = __fadd_rn(a1, v1);
+      if (w) {
+        a0 = fmaf(w[(size_t)(2 * p) * l + k], v0, a0);
+        a1 = fmaf(w[(size_t)(2 * p + 1) * l + k], v1, a1);
+      } else {
+        a0 = __fadd_rn(a0, v0);
+        a1 = __fadd_rn(a1, v1);
+      }
     }
     T* out = y + ((size_t)bg * S_cmp + c) * D + 2 * p;
-    PrT<T>::st(out, __fdiv_rn(a0, (float)l));
-    PrT<T>::st(out + 1, __fdiv_rn(a1, (float)l));
+    PrT<T>::st(out, w ? a0 : __fdiv_rn(a0, (float)l));
+    PrT<T>::st(out + 1, w ? a1 : __fdiv_rn(a1, (float)l));
   }
 }
 
@@ -137,7 +142,7 @@ phi_avgpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int BG, int S
 template <typename T>
 __global__ void __launch_bounds__(256)
 phi_avgpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int BG, int S, int S_cmp, int D, int l, int d, int rope,
-                       int t0, float base, float scale) {
+                       int t0, float base, float scale, const float* __restrict__ w) {
   const long long n = (long long)BG * S * (D / 2);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int p = (int)(i % (D / 2));
@@ -149,11 +154,16 @@ phi_avgpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int BG, int
     float a0 = 0.f, a1 = 0.f;
     for (int c = c_lo; c <= c_hi; ++c) {
       const T* row = dy + ((size_t)bg * S_cmp + c) * D + 2 * p;
-      a0 += PrT<T>::ld(row);
-      a1 += PrT<T>::ld(row + 1);
+      if (w) {  // tap r = s - c*d of the window that starts at c*d
+        a0 = fmaf(w[(size_t)(2 * p) * l + (s - c * d)], PrT<T>::ld(row), a0);
+        a1 = fmaf(w[(size_t)(2 * p + 1) * l + (s - c * d)], PrT<T>::ld(row + 1), a1);
+      } else {
+        a0 += PrT<T>::ld(row);
+        a1 += PrT<T>::ld(row + 1);
+      }
     }
-    a0 = PrT<T>::rnd(a0 / (float)l);
-    a1 = PrT<T>::rnd(a1 / (float)l);
+    a0 = PrT<T>::rnd(w ? a0 : a0 / (float)l);
+    a1 = PrT<T>::rnd(w ? a1 : a1 / (float)l);
     float g0 = a0, g1 = a1;
     if (rope) {
       float sn, cs;
@@ -163,6 +173,45 @@ phi_avgpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int BG, int
     T* out = dx + ((size_t)bg * S + s) * D + 2 * p;
     PrT<T>::st(out, g0);
     PrT<T>::st(out + 1, g1);
+  }
+}
+
+// dw[e][r] = sum over (bg, c) of dy[bg, c, e] * rot(x[bg, c*d + r, :])[e]: one CTA per (rotation pair, tap), fixed-order
+// reduction (per-thread partial sums over a strided walk, then a shared-memory tree), so the result is reproducible.
+template <typename T>
+__global__ void __launch_bounds__(256)
+phi_conv_dw_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, int BG, int S, int S_cmp, int D, int l,
+                   int d, int rope, int t0, float base, float scale) {
+  __shared__ float red0[256], red1[256];
+  const int p = blockIdx.x, r = blockIdx.y;
+  float a0 = 0.f, a1 = 0.f;
+  const long long n = (long long)BG * S_cmp;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = (int)(i % S_cmp), bg = (int)(i / S_cmp);
+    const int s = c * d + r;
+    const T* row = x + ((size_t)bg * S + s) * D + 2 * p;
+    float v0 = PrT<T>::ld(row), v1 = PrT<T>::ld(row + 1);
+    if (rope) {
+      float sn, cs, w0, w1;
+      rope_sincos<T>(t0 + s, p, D, base, scale, sn, cs);
+      rope_rotate<T>(v0, v1, sn, cs, false, w0, w1);
+      v0 = w0;
+      v1 = w1;
+    }
+    const T* g = dy + ((size_t)bg * S_cmp + c) * D + 2 * p;
+    a0 = fmaf(PrT<T>::ld(g), v0, a0);
+    a1 = fmaf(PrT<T>::ld(g + 1), v1, a1);
+  }
+  red0[threadIdx.x] = a0;
+  red1[threadIdx.x] = a1;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { red0[threadIdx.x] += red0[threadIdx.x + o]; red1[threadIdx.x] += red1[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    dw[(size_t)(2 * p) * l + r] = red0[0];
+    dw[(size_t)(2 * p + 1) * l + r] = red1[0];
   }
 }
 
@@ -195,8 +244,18 @@ int launch_rope_shape(const void* x, void* y, int B, int S, int V, int D, int sr
 }
 
 int launch_phi_avgpool(const void* x, void* y, int BG, int S, int D, int l, int d, int rope, int t0, float base, float scale,
-                       int backward, int dtype, cudaStream_t stream) {
+                       int backward, int dtype, cudaStream_t stream, const float* w, const void* dy_for_dw) {
   NSA_REQUIRE(x && y, "phi_avgpool: NULL pointer");
+  if (backward == 2) {  // dw of the learnable phi: x = the raw stream, dy_for_dw = dy, y = dw [D][l] fp32
+    NSA_REQUIRE(dy_for_dw && BG >= 0 && S >= l && l >= 1 && d >= 1 && D >= 2 && D % 2 == 0, "phi_conv dw: bad arguments");
+    const int S_c = (S - l) / d + 1;
+    if (!(scale > 0.f)) scale = 1.0f;
+    const dim3 grid(D / 2, l);
+    if (dtype == NSA_F32) phi_conv_dw_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, (const float*)dy_for_dw, (float*)y, BG, S, S_c, D, l, d, rope, t0, base, scale);
+    else if (dtype == NSA_BF16) phi_conv_dw_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy_for_dw, (float*)y, BG, S, S_c, D, l, d, rope, t0, base, scale);
+    else phi_conv_dw_kernel<__half><<<grid, 256, 0, stream>>>((const __half*)x, (const __half*)dy_for_dw, (float*)y, BG, S, S_c, D, l, d, rope, t0, base, scale);
+    return check_launch("phi_conv_dw_kernel");
+  }
   NSA_REQUIRE(BG >= 0 && S >= l && l >= 1 && d >= 1 && D >= 2 && D % 2 == 0, "phi_avgpool: BG=%d S=%d D=%d l=%d d=%d", BG, S, D, l, d);
   const int S_cmp = (S - l) / d + 1;
   const long long n = (long long)BG * (backward ? S : S_cmp) * (D / 2);
@@ -205,8 +264,8 @@ int launch_phi_avgpool(const void* x, void* y, int BG, int S, int D, int l, int 
   const int blocks = pr_blocks(n);
 #define NSA_PHI(T)                                                                                                              \
   do {                                                                                                                          \
-    if (backward) phi_avgpool_bwd_kernel<T><<<blocks, 256, 0, stream>>>((const T*)x, (T*)y, BG, S, S_cmp, D, l, d, rope, t0, base, scale); \
-    else phi_avgpool_fwd_kernel<T><<<blocks, 256, 0, stream>>>((const T*)x, (T*)y, BG, S, S_cmp, D, l, d, rope, t0, base, scale); \
+    if (backward) phi_avgpool_bwd_kernel<T><<<blocks, 256, 0, stream>>>((const T*)x, (T*)y, BG, S, S_cmp, D, l, d, rope, t0, base, scale, w); \
+    else phi_avgpool_fwd_kernel<T><<<blocks, 256, 0, stream>>>((const T*)x, (T*)y, BG, S, S_cmp, D, l, d, rope, t0, base, scale, w); \
   } while (0)
   if (dtype == NSA_F32) NSA_PHI(float);
   else if (dtype == NSA_BF16) NSA_PHI(__nv_bfloat16);
@@ -358,6 +417,7 @@ decode_emit_kernel(nsa_decode_emit_t a) {
     if (!is_k) p -= hk;
     const int D = is_k ? a.Dk : a.Dv;
     const T* x = reinterpret_cast<const T*>(is_k ? a.K_raw : a.V_raw) + ((size_t)bg * a.cap_raw + s0) * D + 2 * p;
+    const float* wt = is_k ? a.w_k : a.w_v;  // learnable phi (depthwise conv taps [D][l]) or NULL = mean
     float a0 = 0.f, a1 = 0.f;
     for (int k = 0; k < a.l; ++k) {  // same arithmetic as phi_avgpool_fwd_kernel: the window at absolute positions s0 .. s0 + l - 1
       float v0 = PrT<T>::ld(x + (size_t)k * D), v1 = PrT<T>::ld(x + (size_t)k * D + 1);
@@ -368,12 +428,17 @@ decode_emit_kernel(nsa_decode_emit_t a) {
         v0 = w0;
         v1 = w1;
       }
-      a0 = __fadd_rn(a0, v0);
-      a1 = __fadd_rn(a1, v1);
+      if (wt) {
+        a0 = fmaf(wt[(size_t)(2 * p) * a.l + k], v0, a0);
+        a1 = fmaf(wt[(size_t)(2 * p + 1) * a.l + k], v1, a1);
+      } else {
+        a0 = __fadd_rn(a0, v0);
+        a1 = __fadd_rn(a1, v1);
+      }
     }
     T* out = reinterpret_cast<T*>(is_k ? a.K_cmp : a.V_cmp) + ((size_t)bg * a.cap_cmp + c_row) * D + 2 * p;
-    PrT<T>::st(out, __fdiv_rn(a0, (float)a.l));
-    PrT<T>::st(out + 1, __fdiv_rn(a1, (float)a.l));
+    PrT<T>::st(out, wt ? a0 : __fdiv_rn(a0, (float)a.l));
+    PrT<T>::st(out + 1, wt ? a1 : __fdiv_rn(a1, (float)a.l));
   }
 }
 

@@ -549,6 +549,50 @@ def phi_avgpool(K_raw: torch.Tensor, V_raw: torch.Tensor, l: int, d: int, *, t0:
     return _PhiAvgPool.apply(K_raw, l, d, 1, t0), _PhiAvgPool.apply(V_raw, l, d, 0, t0)
 
 
+class _PhiConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, l, d, rope, t0, scale):
+        xc, wc = _c(x), _c(w.detach().float())
+        B, G, S, D = xc.shape
+        S_cmp = (S - l) // d + 1
+        y = torch.empty((B, G, S_cmp, D), dtype=xc.dtype, device=xc.device)
+        if y.numel():
+            _call("nsa_phi_conv", _ptr(xc), _ptr(wc), _ptr(y), None, B * G, S, D, l, d, int(rope), int(t0), 10000.0, float(scale), 0,
+                  _DTYPES[xc.dtype], _stream())
+        ctx.save_for_backward(xc, wc)
+        ctx.meta = (B, G, S, D, l, d, int(rope), int(t0), float(scale), w.dtype, tuple(w.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, wc = ctx.saved_tensors
+        B, G, S, D, l, d, rope, t0, scale, wdt, wshape = ctx.meta
+        dyc = _c(dy.to(xc.dtype))
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(xc)
+            _call("nsa_phi_conv", _ptr(dyc), _ptr(wc), _ptr(dx), None, B * G, S, D, l, d, rope, t0, 10000.0, scale, 1, _DTYPES[xc.dtype], _stream())
+        if ctx.needs_input_grad[1]:
+            dwf = torch.empty((D, l), dtype=torch.float32, device=xc.device)
+            _call("nsa_phi_conv", _ptr(xc), None, _ptr(dwf), _ptr(dyc), B * G, S, D, l, d, rope, t0, 10000.0, scale, 2, _DTYPES[xc.dtype], _stream())
+            dw = dwf.to(wdt).view(wshape)
+        return dx, dw, None, None, None, None, None
+
+
+def phi_conv(K_raw: torch.Tensor, V_raw: torch.Tensor, w_k: torch.Tensor, w_v: torch.Tensor, l: int, d: int, *, t0: int = 0,
+             rope_scale: float = 1.0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Learnable phi (phi = "mlp": depthwise Conv1d over time, kernel l, stride d, no bias; nsa_attention.py:275-291, :1741-1777) for
+    rows at positions t0, t0+1, ...: K_cmp = conv_k(RoPE(K_raw)), V_cmp = conv_v(V_raw); w_* are the Conv1d weights ([D,1,l] or [D,l]).
+    [B,G,S,D] -> [B,G,(S-l)//d+1,D]; gradients flow to the inputs and to the taps.  S < l gives empty outputs."""
+    _require_cuda(K_raw, V_raw, w_k, w_v)
+    B, G, S, Dk = K_raw.shape
+    if S < l:
+        return K_raw.new_zeros((B, G, 0, Dk)), V_raw.new_zeros((B, G, 0, V_raw.shape[-1]))
+    sc = rope_scale if rope_scale > 0 else 1.0
+    return (_PhiConv.apply(K_raw, w_k.reshape(Dk, l), l, d, 1, t0, sc),
+            _PhiConv.apply(V_raw, w_v.reshape(V_raw.shape[-1], l), l, d, 0, t0, 1.0))
+
+
 def decode_produce(y: torch.Tensor, q_out: torch.Tensor, slabs, rows, *, H: int, G: int, Dk: int, Dv: int, t: int,
                    base: float = 10000.0, scale: float = 1.0, counters: Optional[torch.Tensor] = None, counters_idx: int = 0,
                    counter_vals=(0, 0, 0, 0, 0), inverse: bool = False) -> None:
@@ -722,7 +766,7 @@ class DecodeGraphStep:
     KERNELS_PER_REPLAY = 4  # produce, emit, fused decode, advance (+ two cuBLAS GEMMs)
 
     def __init__(self, x_like: torch.Tensor, W_cat: torch.Tensor, W_out: torch.Tensor, slabs, cmp_slabs, counters, *, H: int, G: int,
-                 Dk: int, Dv: int, cfg: NSAConfig, gate, rope_scale: float):
+                 Dk: int, Dv: int, cfg: NSAConfig, gate, rope_scale: float, phi_w=None):
         _require_cuda(x_like, W_cat, W_out, *slabs, *cmp_slabs)
         B, dim = x_like.shape[0], x_like.shape[-1]
         dev, dt = x_like.device, x_like.dtype
@@ -758,6 +802,10 @@ class DecodeGraphStep:
         e.K_cmp, e.V_cmp = cmp_slabs[0].data_ptr(), cmp_slabs[1].data_ptr()
         e.BG, e.cap_raw, e.cap_cmp, e.Dk, e.Dv, e.l, e.d = B * G, int(self.slabs[4].shape[2]), int(cmp_slabs[0].shape[2]), Dk, Dv, cfg.l, cfg.d
         e.base, e.scale, e.dtype = 10000.0, 1.0, _DTYPES[dt]  # phi pools RoPE'd keys at scale 1 (ops.phi_avgpool)
+        if phi_w is not None:  # learnable phi: fp32 copies of the Conv1d taps [D, l] (the graph is re-captured when they change)
+            self.phi_w = tuple(_c(t.detach().float().reshape(t.shape[0], -1)) for t in phi_w)
+            e.w_k, e.w_v = self.phi_w[0].data_ptr(), self.phi_w[1].data_ptr()
+            e.scale = float(rope_scale if rope_scale > 0 else 1.0)
         self.e = e
         self.dm = make_dims(self.Q, cfg, K_sel=self.slabs[0], K_win=self.slabs[2], K_cmp=cmp_slabs[0], Dv=Dv, n_ranges=cfg.n_sel,
                             gate_hidden=hid)

@@ -131,6 +131,24 @@ def phi_avg_pool(K_raw: torch.Tensor, V_raw: torch.Tensor, l: int, d: int,
     return Kc, Vc
 
 
+def phi_conv(K_raw: torch.Tensor, V_raw: torch.Tensor, w_k: torch.Tensor, w_v: torch.Tensor, l: int, d: int,
+             pos: Optional[torch.Tensor] = None, rope_scale: float = 1.0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Learnable phi (phi="mlp"): depthwise Conv1d over time, kernel l, stride d, no bias, on RoPE(K_raw) and V_raw
+    (_phi_apply_seq, nsa_attention.py:1741-1758); w_* [D, l] (Conv1d.weight [D,1,l] squeezed):
+    K_cmp[i, e] = sum_r w_k[e, r] * RoPE(K_raw)[i*d + r, e]."""
+    B, G, S, Dk = K_raw.shape
+    if pos is None:
+        pos = torch.arange(S)
+    Kr = rope(K_raw, pos, scale=rope_scale)
+    n = num_cmp_blocks(S, l, d)
+    if n == 0:
+        return K_raw.new_zeros(B, G, 0, Dk), V_raw.new_zeros(B, G, 0, V_raw.shape[-1])
+    wk, wv = w_k.reshape(Dk, l), w_v.reshape(V_raw.shape[-1], l)
+    Kc = torch.stack([(Kr[:, :, i * d:i * d + l] * wk.t()).sum(dim=2) for i in range(n)], dim=2)
+    Vc = torch.stack([(V_raw[:, :, i * d:i * d + l] * wv.t()).sum(dim=2) for i in range(n)], dim=2)
+    return Kc, Vc
+
+
 def num_cmp_at(t: int, l: int, d: int, S_cmp: int) -> int:
     """packing.py:15-23 / attention_kernels.py:121  --  compressed tokens visible at row t."""
     return 0 if t + 1 < l else min((t + 1 - l) // d + 1, S_cmp)

@@ -363,12 +363,55 @@ def gen_free_functions():
     save("free_functions", **arrs)
 
 
+def gen_phi_mlp():
+    """phi="mlp" (learnable depthwise Conv1d, nsa_attention.py:275-291, :1741-1777).  The reference's constructor clears
+    phi_v_conv unconditionally (the `self.phi_v_conv = None` of the else-branch is dedented one level, :289-291), so the module as
+    shipped asserts on first use; the generating script repairs exactly that attribute and then calls the reference's own
+    _phi_apply_seq / _phi_apply_last and a whole prefill + decode loop."""
+    import torch.nn as nn
+    from nsa.cache.kv_cache import NSA_KV  # noqa: F401
+    from nsa.core.block_index import build_block_meta
+    from nsa.core.nsa_attention import NSAAttention
+
+    torch.manual_seed(41)
+    dim, H, G, dk, dv, l, d, ls, n, w = 64, 4, 2, 16, 16, 8, 4, 16, 4, 32
+    m = NSAAttention(dim=dim, n_heads=H, n_kv_groups=G, d_k=dk, d_v=dv, l=l, d=d, l_sel=ls, n_sel=n, w=w, phi="mlp")
+    assert m.phi_k_conv is not None and m.phi_v_conv is None  # the bug
+    m.phi_v_conv = nn.Conv1d(dv, dv, kernel_size=l, stride=d, groups=dv, bias=False)
+    with torch.no_grad():
+        m.phi_k_conv.weight.copy_(torch.randn_like(m.phi_k_conv.weight) * 0.3)
+        m.phi_v_conv.weight.copy_(torch.randn_like(m.phi_v_conv.weight) * 0.3)
+    arrs = {"cfg": np.array([dim, H, G, dk, dv, l, d, ls, n, w])}
+    for k, v in m.state_dict().items():
+        arrs["sd__" + k] = v
+    K_raw, V_raw = torch.randn(2, G, 37, dk), torch.randn(2, G, 37, dv)
+    with torch.no_grad():
+        Kc, Vc = m._phi_apply_seq(K_raw, V_raw, torch.arange(37))
+        Kl, Vl = m._phi_apply_last(K_raw[:, :, 20:28], V_raw[:, :, 20:28], torch.arange(20, 28))
+    arrs.update(K_raw=K_raw, V_raw=V_raw, K_cmp=Kc, V_cmp=Vc, K_last=Kl, V_last=Vl)
+    # whole module: prefill S0 tokens, then decode (emission through _phi_apply_last); only the compressed stream is compared
+    # (attention outputs on the reference's default routes are the degenerate first-key ones, SURVEY F1)
+    x = torch.randn(1, 30, dim)
+    kv = _empty_kv(1, G, dk, dv, build_block_meta(64, l, d, ls, n, w))
+    with torch.no_grad():
+        _, kv = m(x[:, :18], kv, prefill=True)
+        arrs["K_cmp_after_prefill"] = kv.K_cmp.clone()
+        # the reference's prefill does not record the raw stream (its decode would restart the emission count): seed it
+        kv.K_cmp_raw_seq = m._shape_kv(m.W_K_cmp(x[:, :18]), 1, 18)
+        kv.V_cmp_raw_seq = m._shape_kv(m.W_V_cmp(x[:, :18]), 1, 18)
+        for i in range(18, 30):
+            _, kv = m(x[:, i:i + 1], kv, prefill=False)
+    arrs.update(x=x, K_cmp_final=kv.K_cmp, V_cmp_final=kv.V_cmp)
+    save("phi_mlp", **arrs)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:  # python tests/golden/make_golden.py free_functions [...]: regenerate only the named fixtures
         for name in sys.argv[1:]:
             globals()["gen_" + name]()
         sys.exit(0)
     gen_free_functions()
+    gen_phi_mlp()
     gen_meta()
     gen_rope_phi()
     gen_scores()

@@ -73,8 +73,11 @@ def test_module_contract_on_cpu():
     from nsa_vibe_b200 import NSAAttention, build_block_meta, create_empty_kv
     with pytest.raises(ValueError):
         NSAAttention(64, 4, 2, 16, 16, l=32, d=12)
-    with pytest.raises(NotImplementedError):
-        NSAAttention(64, 4, 2, 16, 16, phi="mlp")
+    with pytest.raises(ValueError):
+        NSAAttention(64, 4, 2, 16, 16, phi="conv2d")
+    m = NSAAttention(64, 4, 2, 16, 16, l=8, d=4, l_sel=16, phi="mlp")  # learnable phi: depthwise Conv1d initialised to the mean
+    assert m.phi_k_conv.weight.shape == (16, 1, 8) and m.phi_v_conv is not None
+    assert torch.all(m.phi_k_conv.weight == 1.0 / 8)
     m = NSAAttention(64, 4, 2, 16, 16, l=16, d=8, l_sel=32, n_sel=4, w=40)
     assert sorted(m.state_dict()) == sorted([
         "W_Q.weight", "W_K_sel.weight", "W_V_sel.weight", "W_K_win.weight", "W_V_win.weight", "W_K_cmp.weight",

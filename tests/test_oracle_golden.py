@@ -254,3 +254,18 @@ def test_free_function_goldens_pcmp_map_and_ranges():
     q, K, V = T(g["bgh_q"]), T(g["bgh_K"]), T(g["bgh_V"])
     o, _ = O._masked_attention(q[:, None], K, V, torch.ones(q.shape[0], 1, q.shape[1], K.shape[2], dtype=torch.bool))
     assert torch.allclose(o[:, 0], T(g["bgh_O"]), atol=2e-6)
+
+
+def test_phi_mlp_depthwise_conv():
+    """phi="mlp" against the reference's own _phi_apply_seq / _phi_apply_last (its constructor bug repaired in make_golden.py)."""
+    g = load_golden("phi_mlp")
+    dim, H, G, dk, dv, l, d, ls, n, w = [int(v) for v in g["cfg"]]
+    wk, wv = T(g["sd__phi_k_conv.weight"]), T(g["sd__phi_v_conv.weight"])
+    Kc, Vc = O.phi_conv(T(g["K_raw"]), T(g["V_raw"]), wk, wv, l, d)
+    assert torch.allclose(Kc, T(g["K_cmp"]), atol=2e-6) and torch.allclose(Vc, T(g["V_cmp"]), atol=2e-6)
+    Kl, Vl = O.phi_conv(T(g["K_raw"])[:, :, 20:28], T(g["V_raw"])[:, :, 20:28], wk, wv, l, d, pos=torch.arange(20, 28))
+    assert torch.allclose(Kl, T(g["K_last"]), atol=2e-6) and torch.allclose(Vl, T(g["V_last"]), atol=2e-6)
+    # initialised to 1/l it is the average pool
+    Ka, Va = O.phi_avg_pool(T(g["K_raw"]), T(g["V_raw"]), l, d)
+    Kc1, Vc1 = O.phi_conv(T(g["K_raw"]), T(g["V_raw"]), torch.full_like(wk, 1.0 / l), torch.full_like(wv, 1.0 / l), l, d)
+    assert torch.allclose(Kc1, Ka, atol=1e-6) and torch.allclose(Vc1, Va, atol=1e-6)

@@ -145,3 +145,58 @@ def test_project_split_matches_the_seven_chains_forward_and_backward(dtype, B, S
     loss_a.backward()
     loss_b.backward()
     assert torch.equal(ya.grad, yb.grad)
+
+
+def test_phi_mlp_conv_matches_reference_and_autograd():
+    """Learnable phi (depthwise Conv1d, phi="mlp"): kernels vs the reference's own outputs (tests/golden/phi_mlp.npz), gradients
+    of inputs and taps vs autograd through the oracle, and the module (prefill, eager decode and CUDA-graph decode emission)."""
+    from conftest import T, load_golden
+    from nsa_vibe_b200 import ops
+    from oracle import nsa_oracle as O
+    g = load_golden("phi_mlp")
+    dim, H, G, dk, dv, l, d, ls, n, w = [int(v) for v in g["cfg"]]
+    wk, wv = T(g["sd__phi_k_conv.weight"]), T(g["sd__phi_v_conv.weight"])
+    K_raw, V_raw = T(g["K_raw"]), T(g["V_raw"])
+    Kc, Vc = ops.phi_conv(K_raw.cuda(), V_raw.cuda(), wk.cuda(), wv.cuda(), l, d)
+    assert torch.allclose(Kc.cpu(), T(g["K_cmp"]), atol=5e-6) and torch.allclose(Vc.cpu(), T(g["V_cmp"]), atol=5e-6)
+    Kl, Vl = ops.phi_conv(K_raw[:, :, 20:28].cuda().contiguous(), V_raw[:, :, 20:28].cuda().contiguous(), wk.cuda(), wv.cuda(), l, d, t0=20)
+    assert torch.allclose(Kl.cpu(), T(g["K_last"]), atol=5e-6) and torch.allclose(Vl.cpu(), T(g["V_last"]), atol=5e-6)
+    # gradients: dx (rotation transposed), dw (reduction over batch and positions)
+    dev = [t.clone().cuda().requires_grad_(True) for t in (K_raw, V_raw, wk, wv)]
+    cpu = [t.clone().requires_grad_(True) for t in (K_raw, V_raw, wk, wv)]
+    gk, gv = torch.randn_like(T(g["K_cmp"])), torch.randn_like(T(g["V_cmp"]))
+    a, b = ops.phi_conv(*dev, l, d)
+    ((a * gk.cuda()).sum() + (b * gv.cuda()).sum()).backward()
+    a2, b2 = O.phi_conv(*cpu, l, d)
+    ((a2 * gk).sum() + (b2 * gv).sum()).backward()
+    for x, y in zip(dev, cpu):
+        assert x.grad.shape == y.grad.shape
+        assert float((x.grad.cpu() - y.grad).norm() / y.grad.norm()) <= 1e-5
+    # module: state-dict compatible parameters, prefill + decode emission equals the reference's compressed stream
+    from nsa_vibe_b200.cache.kv_cache import create_empty_kv
+    from nsa_vibe_b200.core.block_index import build_block_meta
+    from nsa_vibe_b200.core.nsa_attention import NSAAttention
+    m = NSAAttention(dim=dim, n_heads=H, n_kv_groups=G, d_k=dk, d_v=dv, l=l, d=d, l_sel=ls, n_sel=n, w=w, phi="mlp").cuda()
+    m.load_state_dict({k[4:]: T(v).cuda() for k, v in g.items() if k.startswith("sd__")})
+    x = T(g["x"]).cuda()
+    kv = create_empty_kv(1, G, dk, dv, build_block_meta(64, l, d, ls, n, w), device="cuda")
+    with torch.no_grad():
+        _, kv = m(x[:, :18], kv, prefill=True)
+        assert torch.allclose(kv.K_cmp.cpu(), T(g["K_cmp_after_prefill"]), atol=5e-6)
+        for i in range(18, 30):
+            _, kv = m(x[:, i:i + 1], kv, prefill=False)
+    assert torch.allclose(kv.K_cmp.cpu(), T(g["K_cmp_final"]), atol=5e-6) and torch.allclose(kv.V_cmp.cpu(), T(g["V_cmp_final"]), atol=5e-6)
+    # bf16, m7c head dims: the CUDA-graph decode step emits through the same taps as the eager step
+    torch.manual_seed(0)
+    mg = NSAAttention(dim=256, n_heads=12, n_kv_groups=2, d_k=64, d_v=64, l=32, d=16, l_sel=64, n_sel=16, w=128, phi="mlp").cuda().bfloat16()
+    with torch.no_grad():
+        mg.phi_k_conv.weight.add_(torch.randn_like(mg.phi_k_conv.weight) * 0.02)
+        mg.phi_v_conv.weight.add_(torch.randn_like(mg.phi_v_conv.weight) * 0.02)
+    xs = torch.randn(2, 80, 256, device="cuda").bfloat16()
+    kv = create_empty_kv(2, 2, 64, 64, build_block_meta(64, 32, 16, 64, 16, 128), device="cuda", dtype=torch.bfloat16)
+    with torch.no_grad():
+        for i in range(80):
+            _, kv = mg(xs[:, i:i + 1], kv, prefill=False)
+        assert getattr(kv, "_decode_graph")[2] is not None
+        want_k, want_v = ops.phi_conv(kv.K_cmp_raw_seq, kv.V_cmp_raw_seq, mg.phi_k_conv.weight, mg.phi_v_conv.weight, 32, 16)
+    assert kv.K_cmp.shape[2] == 4 and torch.equal(kv.K_cmp, want_k) and torch.equal(kv.V_cmp, want_v)
