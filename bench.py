@@ -456,6 +456,7 @@ def main():
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the forward+backward block (training shape, config C5)")
     ap.add_argument("--no-train-ddp", action="store_true", help="skip the 12-layer DDP training step (config C5)")
+    ap.add_argument("--no-stack", action="store_true", help="skip the end-to-end run through a 12-layer block stack")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -597,6 +598,13 @@ def main():
         hp_val = world * B * S / (float(t5.item()) / n_e2e * 1e-3)
         hp_ok = bool(torch.equal(o_host[(n_e2e - 1) % 2].to(dev), step(inp)))
         del host, o_host, eng
+        # ---- e2e through a 12-layer LlamaBlockNSA stack: one H2D of x feeds twelve layers of compute ----------------------------
+        stack = None
+        if not args.no_stack:
+            try:
+                stack = bench_stack_e2e(args, dev, rank, world, barrier)
+            except Exception as ex:
+                stack = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
 
         # ---- per-kernel device times (outside the timed region; same inputs) -------------------------------
         def t_of(fn, n=3):
@@ -776,12 +784,48 @@ def main():
                     "hot_path_only": {"value": hp_val, "unit": "tok/s", "h2d_bytes_per_step": hp_h2d, "d2h_bytes_per_step": B * S * c["H"] * c["Dv"] * 2,
                                       "how": "PrefillEngine.run: post-projection Q + six K/V tensors in, O out (round-1 e2e definition)",
                                       "matches_device_path": hp_ok}},
+            "e2e_stack12": stack,
             "module_prefill": {"what": "NSAAttention.forward(prefill=True), B=1, bf16, device-resident x: the sizes the reference's GPU route can run "
                                        "(see reference_gpu in the --impl reference line)", **module_small},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "cpu_port": cpu_port, "parity_64k": parity,
             "decode": decode, "train_core": train, "train_ddp": train_ddp}
     print(json.dumps(line))
     _leave(world, train_ddp)
+
+
+def bench_stack_e2e(args, dev, rank, world, barrier, layers=12, steps=6):
+    """End to end through a stack: x [B,S,768] bf16 in pinned host memory -> 12 LlamaBlockNSA layers (m7c dims; RMSNorm kernels,
+    NSAAttention prefill with the batched selection rule, SiLU MLP) -> hidden states back to pinned host memory, every step, with
+    the copies of neighbouring steps overlapped (StackPrefillEngine).  Same bytes per step as the one-layer e2e, twelve times the
+    compute: what the host side of the box can feed."""
+    import torch.distributed as dist
+    from nsa_vibe_b200.engine import StackPrefillEngine
+    from nsa_vibe_b200.model.llama_block_nsa import LlamaBlockNSA
+    c = M7C
+    os.environ["NSA_PREFILL_BATCHED"] = "1"
+    torch.manual_seed(21 + rank)
+    blocks = [LlamaBlockNSA(768, c["H"], c["G"], c["Dk"], c["Dv"], c["l"], c["d"], c["l_sel"], c["n_sel"], c["w"]).to(dev).bfloat16()
+              for _ in range(layers)]
+    B, S = args.B, args.S
+    x_host = [(torch.randn(B, S, 768) * 0.5).bfloat16().pin_memory() for _ in range(2)]
+    y_host = [torch.empty((B, S, 768), dtype=torch.bfloat16).pin_memory() for _ in range(2)]
+    eng = StackPrefillEngine(blocks, dev)
+    with torch.no_grad():
+        eng.run([{"x": x_host[i % 2]} for i in range(2)], [y_host[i % 2] for i in range(2)])
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        eng.run([{"x": x_host[i % 2]} for i in range(steps)], [y_host[i % 2] for i in range(steps)])
+        e.record()
+        barrier()
+    tt = torch.tensor([s.elapsed_time(e) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    finite = bool(torch.isfinite(y_host[(steps - 1) % 2].float()).all())
+    return {"what": f"{layers} LlamaBlockNSA layers, x [B,S,768] bf16 from / hidden states to pinned host memory every step", "layers": layers,
+            "ms_per_step": ms, "value": world * B * S / (ms * 1e-3), "unit": "tok/s (through the whole stack)",
+            "h2d_bytes_per_step": B * S * 768 * 2, "d2h_bytes_per_step": B * S * 768 * 2, "finite": finite}
 
 
 def _leave(world, train_ddp):

@@ -131,3 +131,20 @@ class ModulePrefillEngine(Pipeline):
                       device=x.device, dtype=x.dtype)
         out, _ = a(x, kv, prefill=True)
         return out
+
+
+class StackPrefillEngine(Pipeline):
+    """x [B,S,dim] (pinned host) -> a stack of LlamaBlockNSA layers (RMSNorm, NSAAttention prefill, residual, RMSNorm, SiLU MLP,
+    residual; nsa/model/llama_block_nsa.py:33-106) -> hidden states [B,S,dim] (pinned host): ONE host->device copy feeds every
+    layer's compute, which is how a model uses the hot path (the per-layer module call moves 200 MB per 64k sequence for ~5 ms of
+    kernels and saturates the host side of a multi-GPU box; a 12-layer stack moves the same bytes per ~70 ms)."""
+
+    def __init__(self, blocks, device, depth: int = 2):
+        self.blocks = list(blocks)
+        super().__init__(self.step_stack, ("x",), device, depth)
+
+    def step_stack(self, d: Dict[str, torch.Tensor]) -> torch.Tensor:
+        x, delta = d["x"], None
+        for b in self.blocks:  # each block's last residual add runs inside the next norm's kernel
+            x, delta = b(x, delta, defer_residual=True)
+        return x + delta
