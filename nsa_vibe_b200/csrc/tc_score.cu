@@ -23,6 +23,7 @@ using namespace tc;
 constexpr int kScStages = 4;       // K ring depth (16 KB tiles)
 constexpr int kScTile = 128 * 128; // bytes of one 128-row x 64-element tile
 constexpr int kScRedLd = 33;       // padded row of the head-reduction buffer
+constexpr int kScPolyDefault = 6;  // NSA_B200_POLY_EX2 default: every 6th exponential of pass 1 on the FMA pipe (0 = none; 4, 5, 6, 8 built)
 
 // MT M-tiles per CTA share every K tile.  TMEM (512 columns) holds STG = 4 / MT accumulator stages of 128 columns per
 // M-tile: MT = 2 double-buffers S; MT = 4 single-buffers it and relies on 4 softmax warps per scheduler to hide the MMA.
@@ -51,6 +52,23 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// exp2 on the FMA pipe (no MUFU): x <= 0 clamped to >= -125, split as n + f with n = rint(x), |f| <= 1/2 (magic-number rounding),
+// 2^f by its degree-6 Taylor polynomial in f*ln2 (remainder < 1.3e-7 relative, the accuracy class of ex2.approx), 2^n by an integer
+// add into the exponent field.  11 issue slots against 1 (+ 8 cycles of the scheduler's 4-lane MUFU unit): pass 1 of the scorer
+// is bound by MUFU throughput with half of its issue slots idle, so every PE-th column goes this way (NSA_B200_POLY_EX2).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;            // 1.5 * 2^23: the low mantissa bits of t hold rint(x)
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 1.5403530e-4f, 1.3333558e-3f);
+  p = fmaf(p, f, 9.6181291e-3f);
+  p = fmaf(p, f, 5.5504109e-2f);
+  p = fmaf(p, f, 2.4022651e-1f);
+  p = fmaf(p, f, 6.9314718e-1f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 // tcgen05.wait::ld that also names the destination registers, so no use of them can be scheduled above the wait
 __device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
@@ -68,7 +86,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // R = l_sel / d compressed blocks start inside one selection block; l = 2 d, so the last of them straddles into the
 // next selection block with weight 1/2 each (block_index.py:43-71).
-template <typename T, int MT, int R>
+template <typename T, int MT, int R, int PE>
 __global__ void __launch_bounds__(32 * (4 * MT + 2), 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, nsa_dims_t dm, int S_sel,
                 float* __restrict__ p_grp, int TOK, int sel_only, float2* __restrict__ stats_out) {
@@ -229,7 +247,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           // the next instruction stalls the in-order issue for the MUFU latency
           float e[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) e[i] = ex2f(fmaf(__uint_as_float(cur[i]), c, -mc));
+          for (int i = 0; i < 32; ++i) {
+            const float xx = fmaf(__uint_as_float(cur[i]), c, -mc);
+            e[i] = (PE > 0 && (i % (PE > 0 ? PE : 1)) == (PE > 0 ? PE : 1) - 1) ? ex2_poly(xx) : ex2f(xx);
+          }
           const float corr = ex2f((m_run - m_new) * c);
           float s0 = e[0], s1 = e[1], s2 = e[2], s3 = e[3];
 #pragma unroll
@@ -342,11 +363,25 @@ static int launch_score_t(const nsa_dims_t& dm, const void* Q, const void* Kc, i
   CUtensorMap tmQ, tmK;
   if (int rc = make_tmap_q_heads(&tmQ, Q, dm.dtype, 64, dm.h, dm.G, (long long)dm.B * dm.S, TOK)) return rc;
   if (int rc = make_tmap_rows(&tmK, Kc, dm.dtype, 64, dm.S_cmp, 64, (long long)dm.cap_cmp * 64, dm.B * dm.G, 128)) return rc;
-  auto kern = score_tc_kernel<T, MT, 4>;
-  static std::atomic<unsigned long long> attr_done{0};
-  if (int rc = ensure_smem_attr(kern, ScSmem<MT>::total, attr_done, "score tc")) return rc;
+  // every PE-th exponential of pass 1 on the FMA pipe (4-M-tile kernel only; 0 = all on MUFU).  One process-wide setting, so the
+  // stand-alone scorer and the split scorer compute identical row statistics.
+  static const int pe_env = getenv("NSA_B200_POLY_EX2") ? atoi(getenv("NSA_B200_POLY_EX2")) : kScPolyDefault;
+  const int pe = MT == 4 ? pe_env : 0;
   const int grid = dm.B * dm.G * ceil_div(dm.S, MT * TOK);
-  kern<<<grid, 32 * (4 * MT + 2), ScSmem<MT>::total, stream>>>(tmQ, tmK, dm, S_sel, p_grp, TOK, sel_only ? 1 : 0, stats_out);
+  const int threads = 32 * (4 * MT + 2);
+#define NSA_SCORE_LAUNCH(PEV)                                                                                           \
+  do {                                                                                                                  \
+    auto kern = score_tc_kernel<T, MT, 4, PEV>;                                                                         \
+    static std::atomic<unsigned long long> attr_done{0};                                                               \
+    if (int rc = ensure_smem_attr(kern, ScSmem<MT>::total, attr_done, "score tc")) return rc;                         \
+    kern<<<grid, threads, ScSmem<MT>::total, stream>>>(tmQ, tmK, dm, S_sel, p_grp, TOK, sel_only ? 1 : 0, stats_out);  \
+  } while (0)
+  if (MT == 4 && pe == 8) NSA_SCORE_LAUNCH(8);
+  else if (MT == 4 && pe == 6) NSA_SCORE_LAUNCH(6);
+  else if (MT == 4 && pe == 5) NSA_SCORE_LAUNCH(5);
+  else if (MT == 4 && pe == 4) NSA_SCORE_LAUNCH(4);
+  else NSA_SCORE_LAUNCH(0);
+#undef NSA_SCORE_LAUNCH
   return check_launch("score_tc_kernel");
 }
 
