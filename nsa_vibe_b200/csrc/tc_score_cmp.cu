@@ -77,6 +77,61 @@ __device__ __forceinline__ void fc_ld_wait32(uint32_t (&r)[32]) {
                : "memory");
 }
 
+// One 16-column chunk of a row: probabilities, Eq.9 block sums (-> rb4[0..3]), the branch's numerators as 16-bit P (-> prow), row sum.
+template <typename T, bool PLAIN>
+__device__ __forceinline__ void fc_chunk(uint32_t (&cur)[16], int col0, int nk, int hi, bool own_ref, float c, float offs, float ref,
+                                         float& carry, float& rowsum, float* rb4, uint8_t* prow, int ch, int sw) {
+  float pp[16];  // numerators of the branch's softmax where they differ from the scorer's probabilities (!PLAIN only)
+  if (PLAIN) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) cur[e] = __float_as_uint(fc_ex2(fmaf(__uint_as_float(cur[e]), c, -offs)));
+  } else {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int col = col0 + e;
+      const float sv = __uint_as_float(cur[e]);
+      const float pv = col < nk ? fc_ex2(fmaf(sv, c, -offs)) : 0.f;
+      pp[e] = col < hi ? (own_ref ? fc_ex2(fmaf(sv, c, -ref)) : pv) : 0.f;
+      cur[e] = __float_as_uint(pv);
+    }
+  }
+  // Eq.9 (l = 2d, l_sel = 4d): block j = 1/2 p[4j-1] + p[4j] + p[4j+1] + p[4j+2] + 1/2 p[4j+3], ascending compressed index.
+  // `carry` holds the UNSCALED p[4j-1]; the halves enter through FMAs: 0.5 * x is exact, so fma(0.5, x, y) rounds like
+  // y + 0.5 * x -- the same four roundings per block as the stand-alone scorer.
+  float blk[4];
+  const float chunk_in = carry;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    float a = fmaf(0.5f, carry, __uint_as_float(cur[jj * 4]));
+    a += __uint_as_float(cur[jj * 4 + 1]);
+    a += __uint_as_float(cur[jj * 4 + 2]);
+    carry = __uint_as_float(cur[jj * 4 + 3]);
+    blk[jj] = fmaf(0.5f, carry, a);
+  }
+  *reinterpret_cast<float4*>(rb4) = make_float4(blk[0], blk[1], blk[2], blk[3]);
+  uint32_t pk[8];
+  if (PLAIN) {  // the row sum of the chunk follows from its four block sums
+    rowsum += ((blk[0] + blk[1]) + (blk[2] + blk[3])) + 0.5f * (carry - chunk_in);
+#pragma unroll
+    for (int e = 0; e < 16; e += 2) pk[e >> 1] = pack2(T(), __uint_as_float(cur[e]), __uint_as_float(cur[e + 1]));
+  } else {
+    float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; e += 4) {
+      r0 += pp[e] + pp[e + 1];
+      r1 += pp[e + 2] + pp[e + 3];
+    }
+    rowsum += r0 + r1;
+#pragma unroll
+    for (int e = 0; e < 16; e += 2) pk[e >> 1] = pack2(T(), pp[e], pp[e + 1]);
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {  // 16 keys = 2 chunks of 16 B: chunk kc = ch*2 + q of the 128-B row
+    const int kc = ch * 2 + q;
+    *reinterpret_cast<uint4*>(prow + ((kc ^ sw) << 4)) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(32 * (4 * kFcMT + 2), 1)
 score_cmp_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -176,6 +231,12 @@ score_cmp_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (i + 1 < n) mbar_wait(&ms->k_full[(i + 1) % kFcKS], ((i + 1) / kFcKS) & 1);
         const uint32_t v_lo = (smem0 + ((SM::v + vs * kFcKV) >> 4)) | kLoMN;
         for (int m = 0; m < MT; ++m) {
+          // the softmax warps wait for the NEXT tile's S; nothing waits for this tile's P.V before their next P write: S first
+          if (i + 1 < n) {
+            mbar_wait(&ms->s_empty[m], i & 1);
+            tc_fence_after();
+            issue_qk(m, i + 1);
+          }
           mbar_wait(&ms->p_full[m], i & 1);
           tc_fence_after();
           const uint32_t p_lo = (smem0 + ((SM::p + m * kFcTile) >> 4)) | kLoK;
@@ -185,11 +246,6 @@ score_cmp_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           for (int k = 0; k < NK / 16; ++k)  // P: 32 B per k-step inside the 128-B rows; V: 16 rows = 2048 B per k-step
             umma_f16_elect(od, p_lo + k * 2, kHi, v_lo + k * (2048 >> 4), kHi, idesc_pv, k > 0 ? 1u : acc0);
           umma_commit_elect(&ms->p_empty[m]);
-          if (i + 1 < n) {
-            mbar_wait(&ms->s_empty[m], i & 1);
-            tc_fence_after();
-            issue_qk(m, i + 1);
-          }
         }
         umma_commit_elect(&ms->v_empty[vs]);
         if (i + 1 < n) umma_commit_elect(&ms->k_empty[(i + 1) % kFcKS]);
@@ -246,55 +302,10 @@ score_cmp_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           uint32_t(&nxt)[16] = (ch & 1) ? ua : ub;
           fc_ld_wait16(cur);
           if (ch < NK / 16 - 1) tmem_ld16(tm_S + (ch + 1) * 16, nxt);
-          float pp[16];  // numerators of the branch's softmax (what goes into P)
-          if (plain) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) cur[e] = __float_as_uint(fc_ex2(fmaf(__uint_as_float(cur[e]), c, -offs)));
-#pragma unroll
-            for (int e = 0; e < 16; ++e) pp[e] = __uint_as_float(cur[e]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const int col = col_base + ch * 16 + e;
-              const float sv = __uint_as_float(cur[e]);
-              const float pv = col < nk ? fc_ex2(fmaf(sv, c, -offs)) : 0.f;
-              pp[e] = col < hi ? (own_ref ? fc_ex2(fmaf(sv, c, -ref)) : pv) : 0.f;
-              cur[e] = __float_as_uint(pv);
-            }
-          }
-          // Eq.9 (l = 2d, l_sel = 4d): block j = 1/2 p[4j-1] + p[4j] + p[4j+1] + p[4j+2] + 1/2 p[4j+3], ascending compressed index.
-          // `carry` holds the UNSCALED p[4j-1]; the halves enter through FMAs: 0.5 * x is exact, so fma(0.5, x, y) rounds like
-          // y + 0.5 * x -- the same four roundings per block as the stand-alone scorer.
-          float blk[4];
-          const float chunk_in = carry;
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            float a = fmaf(0.5f, carry, __uint_as_float(cur[jj * 4]));
-            a += __uint_as_float(cur[jj * 4 + 1]);
-            a += __uint_as_float(cur[jj * 4 + 2]);
-            carry = __uint_as_float(cur[jj * 4 + 3]);
-            blk[jj] = fmaf(0.5f, carry, a);
-          }
-          *reinterpret_cast<float4*>(rb + ch * 4) = make_float4(blk[0], blk[1], blk[2], blk[3]);
-          uint32_t pk[8];
-          if (plain) {  // the branch's numerators are the scorer's: their sum over the chunk follows from the four block sums
-            rowsum += ((blk[0] + blk[1]) + (blk[2] + blk[3])) + 0.5f * (carry - chunk_in);
-          } else {
-            float r0 = 0.f, r1 = 0.f;
-#pragma unroll
-            for (int e = 0; e < 16; e += 4) {
-              r0 += pp[e] + pp[e + 1];
-              r1 += pp[e + 2] + pp[e + 3];
-            }
-            rowsum += r0 + r1;
-          }
-#pragma unroll
-          for (int e = 0; e < 16; e += 2) pk[e >> 1] = pack2(T(), pp[e], pp[e + 1]);
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {  // 16 keys = 2 chunks of 16 B: chunk kc = ch*2 + q of the 128-B row
-            const int kc = ch * 2 + q;
-            *reinterpret_cast<uint4*>(prow + ((kc ^ sw) << 4)) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-          }
+          // two copies of the chunk body: in the plain one the branch's numerators ARE the scorer's probabilities (one register
+          // set; a shared body made the compiler copy every exponential into a second set: 56 M moves per 64k sequence)
+          if (plain) fc_chunk<T, true>(cur, col_base + ch * 16, nk, hi, own_ref, c, offs, ref, carry, rowsum, rb + ch * 4, prow, ch, sw);
+          else fc_chunk<T, false>(cur, col_base + ch * 16, nk, hi, own_ref, c, offs, ref, carry, rowsum, rb + ch * 4, prow, ch, sw);
         }
         tc_fence_before();
         fence_proxy_async();
