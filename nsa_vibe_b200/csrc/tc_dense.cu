@@ -193,6 +193,12 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (i + 1 < n) mbar_wait(&ms->k_full[(i + 1) % kDnKS], ((i + 1) / kDnKS) & 1);
         const uint32_t v_lo = (smem0 + ((SM::v + vs * SM::kvtile) >> 4)) | kLoMN;
         for (int m = 0; m < MT; ++m) {
+          // the softmax warps wait for the NEXT tile's S; nothing waits for this tile's P.V before their next P write: S first
+          if (i + 1 < n) {
+            mbar_wait(&ms->s_empty[m], i & 1);
+            tc_fence_after();
+            issue_qk(m, i + 1);
+          }
           if (lane == 0) DDBG(10 + m, i);
           mbar_wait(&ms->p_full[m], i & 1);
           if (lane == 0) DDBG(12 + m, i);
@@ -205,11 +211,6 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             umma_f16_elect(od, p_lo + (k >> 2) * (kDnTile >> 4) + (k & 3) * 2, kHi, v_lo + k * (2048 >> 4), kHi, idesc_pv,
                            k > 0 ? 1u : acc0);
           umma_commit_elect(&ms->p_empty[m]);
-          if (i + 1 < n) {
-            mbar_wait(&ms->s_empty[m], i & 1);
-            tc_fence_after();
-            issue_qk(m, i + 1);
-          }
         }
         umma_commit_elect(&ms->v_empty[vs]);
         if (i + 1 < n) umma_commit_elect(&ms->k_empty[(i + 1) % kDnKS]);
