@@ -275,6 +275,79 @@ __device__ inline void select_row_warp(float* sc, int S_sel, int l_sel, int n_se
   sel_bitmap_to_ranges(bm, S_sel, l_sel, K, t, out);
 }
 
+// Threshold form of the k_act picks among <= 1024 candidates held 32 per lane (raw[k] = p of block j = lane + 32 k; replaced by
+// the composites).  T = the k_act-th largest LANE maximum (k_act rounds of one warp reduction, no rescans) is a lower bound of the
+// k_act-th largest composite, so the picks are among the elements >= T -- about 17 of 1024 for k_act = 13, whatever the row
+// length.  Those are compacted into shared memory, every candidate is ranked against the others under the rounds' order
+// (larger composite first, lower block id on equal composites) and ranks < k_act are the picks: the same set as k_act rounds of
+// arg-max.  Returns false (nothing written to bm) when the row has to take the rounds: T = -inf or more than 32 candidates.
+// Needs 97 floats of `sc`.  The rounds cost ~2700 warp instructions per row and made the kernel issue-bound (82 % issue-active,
+// 0.38 ms for the 131072 rows of a 64k sequence).
+__device__ __forceinline__ bool select_threshold_1024(float (&raw)[32], float* sc, int nvalid, const int (&forced)[3], int k_act,
+                                                      uint32_t (&bm)[kSelMaxWords]) {
+  const int lane = threadIdx.x & 31;
+  const float NEG = -INFINITY;
+  // bit k of vm: block lane + 32 k is a candidate (complete and not forced)
+  const int nv_l = nvalid > lane ? (nvalid - lane + 31) >> 5 : 0;
+  uint32_t vm = nv_l >= 32 ? 0xffffffffu : ((1u << nv_l) - 1u);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    if (forced[i] >= 0 && forced[i] < 1024 && (forced[i] & 31) == lane) vm &= ~(1u << (forced[i] >> 5));
+  const float lanef = (float)lane;
+  float lm = NEG;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    // composite = fp32(p) - fp32(fp32(j) * 1e-8f): two separately rounded fp32 ops; fp32(j) = lane + 32 k exactly
+    const float v = __fsub_rn(raw[k], __fmul_rn(lanef + 32.f * k, 1e-8f));
+    raw[k] = ((vm >> k) & 1u) ? v : NEG;
+    lm = fmaxf(lm, raw[k]);
+  }
+  const uint32_t lb = __float_as_uint(lm);
+  uint32_t key = lb ^ ((lb >> 31) ? 0xffffffffu : 0x80000000u);  // order-preserving; -inf -> 0x007fffff
+  uint32_t tkey = 0u;
+  for (int it = 0; it < k_act; ++it) {  // equal lane maxima leave together: T only gets lower, never wrong
+    tkey = __reduce_max_sync(0xffffffffu, key);
+    if (key == tkey) key = 0u;
+  }
+  if (tkey <= 0x007fffffu) return false;  // fewer than k_act lanes with a candidate
+  const float T = __uint_as_float(tkey ^ ((tkey >> 31) ? 0x80000000u : 0xffffffffu));
+  float* cand_c = sc;
+  int* cand_j = reinterpret_cast<int*>(sc + 32);
+  uint32_t* sbm = reinterpret_cast<uint32_t*>(sc + 64);
+  int* cnt = reinterpret_cast<int*>(sc + 96);
+  sbm[lane] = bm[0];  // the forced members (ids < 1024: word = lane, slot 0)
+  if (lane == 0) *cnt = 0;
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    if (raw[k] >= T) {
+      const int pos = atomicAdd(cnt, 1);
+      if (pos < 32) {
+        cand_c[pos] = raw[k];
+        cand_j[pos] = lane + 32 * k;
+      }
+    }
+  }
+  __syncwarp();
+  const int n = *cnt;
+  if (n > 32) return false;
+  if (lane < n) {
+    const float c = cand_c[lane];
+    const int j = cand_j[lane];
+    int rank = 0;
+#pragma unroll 4
+    for (int q = 0; q < n; ++q) {
+      const float cq = cand_c[q];
+      const int jq = cand_j[q];
+      rank += (cq > c || (cq == c && jq < j)) ? 1 : 0;
+    }
+    if (rank < k_act) atomicOr(&sbm[j >> 5], 1u << (j & 31));
+  }
+  __syncwarp();
+  bm[0] = sbm[lane];
+  return true;
+}
+
 // Fast path of the standalone kernel for 128 < S_sel <= 1024 (long prefill): the row goes from global memory straight into
 // registers (lane owns blocks j = lane + 32k, all loads in flight at once), composites are formed there and written to shared
 // memory once (only the owner of a picked block ever re-reads them), and every (lane, group of 8 strides) bucket keeps its best
@@ -282,8 +355,8 @@ __device__ inline void select_row_warp(float* sc, int S_sel, int l_sel, int n_se
 // when one bucket is picked twice.  Same comparisons, same tie rule (lower block id first) as select_row_warp: the picked
 // set is identical.  The first version (row staged in shared memory, three passes over it, a rescan per pick) ran 3300
 // instructions per row and was issue-bound (79 % issue-active, 0.49 ms for 131072 rows at 64k).
-__device__ inline void select_row_warp_1024(const float* __restrict__ src, float* sc, int S_sel, int l_sel, int n_sel, int mode,
-                                            int nf, int K, int t, int32_t* __restrict__ out) {
+static __device__ __noinline__ void select_row_warp_1024_rounds(const float* __restrict__ src, float* sc, int S_sel, int l_sel, int n_sel,
+                                                        int mode, int nf, int K, int t, int32_t* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const float NEG = -INFINITY;
   int nvalid = (t + 1) / l_sel;
@@ -382,6 +455,39 @@ __device__ inline void select_row_warp_1024(const float* __restrict__ src, float
     }
   }
   sel_bitmap_to_ranges(bm, S_sel, l_sel, K, t, out);
+}
+
+// The row of the standalone kernel for 128 < S_sel <= 1024: the threshold form when it applies (it does for every row with at
+// least k_rest lanes holding a candidate), else the rounds (a call: the two never share registers).
+__device__ inline void select_row_warp_1024(const float* __restrict__ src, float* sc, int S_sel, int l_sel, int n_sel, int mode,
+                                            int nf, int K, int t, int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  int nvalid = (t + 1) / l_sel;
+  if (nvalid > S_sel) nvalid = S_sel;
+  int forced[3];
+  const int nfc = forced_decode(nf, t / l_sel, forced);
+  const int k_rest = n_sel - nfc;
+  if (k_rest > 0 && k_rest <= 32 && n_sel < S_sel && nvalid >= k_rest) {  // warp-uniform
+    float raw[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int j = lane + 32 * k;
+      raw[k] = (32 * (k & ~7) < nvalid && j < S_sel) ? __ldg(src + j) : 0.f;
+    }
+    uint32_t bm[kSelMaxWords];
+#pragma unroll
+    for (int i = 0; i < kSelMaxWords; ++i) bm[i] = 0u;
+    for (int i = 0; i < nfc; ++i) {
+      const int j = forced[i];
+      if (mode == 0 ? (j < nvalid) : (j < S_sel)) bitmap_set(bm, lane, j);  // prefill drops incomplete blocks
+    }
+    if (select_threshold_1024(raw, sc, nvalid, forced, k_rest, bm)) {
+      sel_bitmap_to_ranges(bm, S_sel, l_sel, K, t, out);
+      return;
+    }
+    __syncwarp();
+  }
+  select_row_warp_1024_rounds(src, sc, S_sel, l_sel, n_sel, mode, nf, K, t, out);
 }
 
 }  // namespace nsa

@@ -130,3 +130,34 @@ def test_decode_long_context():
         p = torch.rand(3, 2, S_sel, generator=torch.Generator().manual_seed(t))
         got = ops.select_ranges_decode(p.cuda(), ls, n, t).cpu()
         assert torch.equal(got, O.select_ranges_decode(p, ls, n, t))
+
+
+@pytest.mark.parametrize("pattern", ["quantised", "ones", "one_lane", "peaked", "zeros", "ramp"])
+def test_threshold_path_structured_rows(pattern):
+    """128 < S_sel <= 1024 takes the threshold form of the picks (select.cuh: select_threshold_1024) and falls back to the rounds
+    when more than 32 candidates reach the threshold: rows built to sit on both sides of that switch, and on exact ties."""
+    ops = _ops()
+    S, ls, n = 32768, 64, 16
+    S_sel = S // ls
+    gen = torch.Generator().manual_seed(11)
+    rows = sorted(set([ls * 16 - 1, ls * 16, ls * 17 + 5, 2047, 2048, 8191, 8200, 20000, S - 1] +
+                      [int(v) for v in torch.randint(ls * 13, S, (40,), generator=gen)]))
+    if pattern == "quantised":
+        p = torch.randint(0, 4, (1, S, 2, S_sel), generator=gen).float() / 4
+    elif pattern == "ones":
+        p = torch.ones(1, S, 2, S_sel)
+    elif pattern == "one_lane":  # every large value in the blocks j = 5 mod 32: few lanes hold the top of the row
+        p = torch.rand(1, S, 2, S_sel, generator=gen) * 0.5
+        p[..., 5::32] += 1.0
+    elif pattern == "peaked":
+        p = torch.zeros(1, S, 2, S_sel)
+        idx = torch.randint(0, S_sel, (1, S, 2, 6), generator=gen)
+        p.scatter_(-1, idx, torch.rand(1, S, 2, 6, generator=gen) + 0.5)
+    elif pattern == "zeros":
+        p = torch.zeros(1, S, 2, S_sel)
+    else:
+        p = torch.arange(S_sel).float().expand(1, S, 2, S_sel).contiguous() / S_sel
+    got = ops.select_ranges_prefill(p.cuda(), ls, n, S).cpu()
+    for tt in rows:
+        want = _row_oracle_big(p, tt, ls, n, S)
+        assert torch.equal(got[:, tt], want), f"{pattern}: t={tt}\n{got[0, tt, 0].tolist()}\n{want[0, 0].tolist()}"
