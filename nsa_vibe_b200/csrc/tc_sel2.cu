@@ -177,14 +177,16 @@ sel2_fill_kernel(S2Geom gm, const int32_t* __restrict__ ranges, const int* __res
 //
 // One CTA loads the K/V tile of its block once and walks its M-tiles as a three-stage pipeline over specialised warps:
 //   warps 0-3  softmax : S(i) from TMEM -> exact softmax of the 64 keys -> P(i) (16-bit, swizzled) + the row's (l, m)
-//   warps 4-7  epilogue: O(i) from TMEM -> / l -> 16-bit rows staged in the tile's own Q buffer -> one TMA tensor store per warp
-//   warp 8 producer (one TMA box per query into a ring of four Q buffers), warp 9 MMA issuer (QK(i) ahead of PV(i-1)).
+//   warps 4-7  epilogue: O(i) from TMEM -> / l -> 16-bit rows staged in the tile's own P buffer -> one TMA tensor store per warp
+//   warp 8 producer (one TMA box per query into a ring of three Q buffers), warp 9 MMA issuer (QK(i) and PV(j) as they arrive).
 // S, O and P are double buffered, so softmax(i+1) runs while PV(i) and the epilogue of tile i are in flight.  The first version
 // gave each M-tile to ONE group of four warps that did softmax and epilogue back to back: its timeline (-DNSA_SEL2_DBG,
 // profiles/r2_sel2_timeline.log) showed ~6100 cycles per tile and slot, of which ~1900 in an epilogue whose un-swizzled staging
-// stores were 8-way bank conflicted, with the tensor pipe and MUFU idle 3/4 of the time.  The Q buffer of a tile is free once
-// QK(i) has completed, which the epilogue knows from O(i) being there, so staging needs no extra shared memory; the producer
-// refills a Q buffer only after the epilogue's store has read it (q_free).
+// stores were 8-way bank conflicted, with the tensor pipe and MUFU idle 3/4 of the time.  The second staged O(i) in the tile's Q
+// buffer: a Q buffer then lived from the issue of its loads to the store of its O (~7000 cycles: 3500 of load latency, QK,
+// softmax, PV, epilogue; profiles/r2_sel2_timeline_v2.log), and three of them bounded the CTA at ~2850 cycles per tile with every
+// unit under 50 %.  The P buffer of a tile is free exactly when O(i) is there (P.V(i) complete), so it is the staging area now:
+// a Q buffer is released by the commit of QK(i) (q_free), and softmax(i+2) waits for the store of O(i) to leave P (ps_free).
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kS2QRing = 3;  // Q buffers in flight: tile i loads into i % 3 while tiles i-1, i-2 are in softmax / epilogue
 
@@ -203,7 +205,7 @@ struct S2Smem {
 struct S2Misc {
   uint64_t kv_full;
   uint64_t q_full[kS2QRing], q_free[kS2QRing], st_full[kS2QRing];
-  uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2], o_full[2], o_empty[2];
+  uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2], o_full[2], o_empty[2], ps_free[2];
   uint32_t tmem_base;
 };
 
@@ -259,7 +261,7 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
   if (tid == 0) {
     mbar_init(&ms->kv_full, 1);
-    for (int i = 0; i < kS2QRing; ++i) { mbar_init(&ms->q_full[i], 1); mbar_init(&ms->q_free[i], 4); mbar_init(&ms->st_full[i], 4); }
+    for (int i = 0; i < kS2QRing; ++i) { mbar_init(&ms->q_full[i], 1); mbar_init(&ms->q_free[i], 1); mbar_init(&ms->st_full[i], 4); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ms->s_full[i], 1);
       mbar_init(&ms->s_empty[i], 4);
@@ -267,6 +269,7 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(&ms->p_empty[i], 1);
       mbar_init(&ms->o_full[i], 1);
       mbar_init(&ms->o_empty[i], 4);
+      mbar_init(&ms->ps_free[i], 4);
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmQ);
@@ -284,6 +287,11 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   if (warp == 8) {
     // ===== TMA producer: K/V tile once, then one box per query of every M-tile =================================
+    // Issuing a box costs this warp ~110 cycles whichever lane does it (profiles/r2_sel2_timeline_v3.log: ~2300 cycles for the 21
+    // boxes of a tile), which is the period of the whole CTA now that the Q buffers turn over fast enough.  Tried and measured
+    // slower at 64k: 16-byte cp.async copies from this warp instead of boxes (~20 instructions per chunk on one warp, 1.19 ms
+    // for the branch against 1.11), both engines side by side (the warp issues them one after the other: 1.22), a second
+    // producer warp (352 threads leave 80 registers: spills in the softmax warps, 1.20), one lane issuing all boxes (1.41).
     if (lane == 0) {
       mbar_expect_tx(&ms->kv_full, 2 * 8192);
       tma_load_3d(smem + S2Smem::kv, &tmK, &ms->kv_full, 0, blk * 64, bg);
@@ -298,7 +306,7 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const unsigned have = __ballot_sync(0xffffffffu, tk >= 0);
       if (lane == 0) {
         S2DBG(1, i);
-        mbar_wait(&ms->q_free[qb], ((i / kS2QRing) & 1) ^ 1);         // the epilogue's store of tile i - kS2QRing has read this buffer
+        mbar_wait(&ms->q_free[qb], ((i / kS2QRing) & 1) ^ 1);         // QK of tile i - kS2QRing has read this buffer
         S2DBG(2, i);
         mbar_expect_tx(&ms->q_full[qb], __popc(have) * h * 128);
       }
@@ -347,6 +355,7 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) umma_f16_elect(tmem + b * 64, q_lo + kk * 2, kHi, k_lo + kk * 2, kHi, idesc_qk, kk > 0);
           umma_commit_elect(&ms->s_full[b]);
+          umma_commit_elect(&ms->q_free[qb]);  // S(qi) complete = the Q buffer has been read: the producer may refill it
           ++qi;
         }
       }
@@ -424,9 +433,10 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         l3 += __uint_as_float(vb2[e + 1]);
       }
       const float l = (l0 + l1) + (l2 + l3);
-      stat[(i % kS2QRing) * 128 + r] = make_float2(l, m);  // tile i + kS2QRing cannot start before the epilogue of tile i (q_free)
+      stat[(i % kS2QRing) * 128 + r] = make_float2(l, m);  // softmax(i + 2) waits for the epilogue of tile i (ps_free): no overrun
       if (tid == 0) S2DBG(22, i);
-      mbar_wait(&ms->p_empty[b], ((i >> 1) & 1) ^ 1);  // P.V of tile i - 2 has read this P buffer
+      mbar_wait(&ms->p_empty[b], ((i >> 1) & 1) ^ 1);  // P.V of tile i - 2 has read this P buffer ...
+      mbar_wait(&ms->ps_free[b], ((i >> 1) & 1) ^ 1);  // ... and the store of O(i - 2), staged in it afterwards, has left it
       uint8_t* prow = smem + S2Smem::p + b * kS2Tile + r * 128;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {  // keys 0..31: chunks 0..3 ; keys 32..63: chunks 4..7 (16 B = 8 keys each)
@@ -466,9 +476,9 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int p = (run.tile0 + i) * TOK + tok_l;
       const bool row_ok = tok_l < TOK && tok_n >= 0;
       if (i + 1 < n && tok_l < TOK) tok_n = tok[p + TOK];
-      if (i > 0 && lane == 0) {  // the store of tile i - 1 has read its staging rows: that Q buffer may be refilled
+      if (i > 0 && lane == 0) {  // the store of tile i - 1 has read its staging rows: softmax may write that P buffer again
         bulk_wait_read0();
-        mbar_arrive(&ms->q_free[(i - 1) % kS2QRing]);
+        mbar_arrive(&ms->ps_free[(i - 1) & 1]);
       }
       if (tid == 128) S2DBG(30, i);
       mbar_wait(&ms->o_full[b], (i >> 1) & 1);
@@ -485,8 +495,8 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_wait(&ms->st_full[qb], (i / kS2QRing) & 1);
       const float2 lm = stat[qb * 128 + r];
       const float inv = lm.x > 0.f ? 1.0f / lm.x : 0.f;
-      // staging = this tile's Q buffer (QK(i) has completed: O(i) is here), rows in the 128B-swizzle pattern the tensor store undoes
-      uint8_t* orow = smem + S2Smem::q + qb * kS2Tile + r * 128;
+      // staging = this tile's P buffer (P.V(i) has completed: O(i) is here), rows in the 128B-swizzle pattern the tensor store undoes
+      uint8_t* orow = smem + S2Smem::p + b * kS2Tile + r * 128;
       if (row_ok) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -508,7 +518,7 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       __syncwarp();
       // rows of padding pairs carry stale bytes (the merge never reads them); rows >= TOK*h of the box are clipped by the TMA unit
       if (lane == 0) {
-        if (warp_has_rows) tma_store_3d(&tmO, smem + S2Smem::q + qb * kS2Tile + row0 * 128, 0, row0, run.tile0 + i);
+        if (warp_has_rows) tma_store_3d(&tmO, smem + S2Smem::p + b * kS2Tile + row0 * 128, 0, row0, run.tile0 + i);
         bulk_commit();
       }
       if (tid == 128) S2DBG(32, i);
