@@ -536,7 +536,7 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 //    zeros and lse = -inf (attention_kernels.py:769-771).  Slots are folded in slot order, so the result is deterministic.
 // ---------------------------------------------------------------------------------------------------------------------
 // One thread per 16-byte chunk of a row (h*8 chunks): its 16 lse values and 16 partial chunks are all requested before any
-// is used, so a row costs two memory round trips (pair_of, then everything else).
+// is used, and the slot table of the thread's next row is already on its way: a row costs one memory round trip.
 constexpr int kS2MergeRows = 4;  // rows per CTA
 
 template <typename T>
@@ -545,17 +545,27 @@ sel2_merge_kernel(int n_rows, int h, const int* __restrict__ pair_of, const T* _
                   T* __restrict__ O, float* __restrict__ lse) {
   const int chunks = h * 8;                   // 16-byte chunks per row (h heads x 64 x 2 B), <= 64 threads per row
   const int rl = threadIdx.x / 64, cidx = threadIdx.x % 64;
-  for (int row = blockIdx.x * kS2MergeRows + rl; row < n_rows; row += gridDim.x * kS2MergeRows) {
-    if (cidx >= chunks) continue;
-    const int head = cidx >> 3;
-    int pk[kS2MaxSlots];
-    {
-      const int4* pp = reinterpret_cast<const int4*>(pair_of + (size_t)row * kS2MaxSlots);
+  if (cidx >= chunks) return;
+  const int head = cidx >> 3;
+  const int stride = gridDim.x * kS2MergeRows;
+  // the NEXT row's slot table is requested before this row's partials are consumed: one memory round trip per row, not two
+  int4 nx[kS2MaxSlots / 4];
+  int row = blockIdx.x * kS2MergeRows + rl;
+  if (row < n_rows) {
+    const int4* pp = reinterpret_cast<const int4*>(pair_of + (size_t)row * kS2MaxSlots);
 #pragma unroll
-      for (int q = 0; q < kS2MaxSlots / 4; ++q) {
-        const int4 t = pp[q];
-        pk[4 * q] = t.x; pk[4 * q + 1] = t.y; pk[4 * q + 2] = t.z; pk[4 * q + 3] = t.w;
-      }
+    for (int q = 0; q < kS2MaxSlots / 4; ++q) nx[q] = pp[q];
+  }
+  for (; row < n_rows; row += stride) {
+    int pk[kS2MaxSlots];
+#pragma unroll
+    for (int q = 0; q < kS2MaxSlots / 4; ++q) {
+      pk[4 * q] = nx[q].x; pk[4 * q + 1] = nx[q].y; pk[4 * q + 2] = nx[q].z; pk[4 * q + 3] = nx[q].w;
+    }
+    if (row + stride < n_rows) {
+      const int4* pp = reinterpret_cast<const int4*>(pair_of + (size_t)(row + stride) * kS2MaxSlots);
+#pragma unroll
+      for (int q = 0; q < kS2MaxSlots / 4; ++q) nx[q] = pp[q];
     }
     float ls[kS2MaxSlots];
     uint4 v[kS2MaxSlots];
@@ -905,7 +915,7 @@ static int launch_sel2_t(const nsa_dims_t& dm, const void* Q, const void* K, con
   }
 #endif
   int mblocks = ceil_div(n_rows, kS2MergeRows);
-  if (mblocks > 148 * 64) mblocks = 148 * 64;
+  if (mblocks > 148 * 8) mblocks = 148 * 8;  // two resident CTAs per SM, several rows each: the slot-table prefetch needs a next row
   if (fuse) {  // no-grad prefill: merge + gate + combine in one pass, the selected branch's output never reaches HBM
     const int Hh = dm.gate_mode == NSA_GATE_MLP ? dm.gate_hidden : 0;
     const size_t smem = ((size_t)dm.Dk * Hh + Hh + 3 * Hh + 4 + (size_t)kS2MergeRows * 2 * dm.Dk) * sizeof(float);
