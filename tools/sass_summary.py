@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Per-kernel SASS evidence of libnsa_b200.so: counts of the Blackwell mnemonics (UTCHMMA = tcgen05.mma, LDTM / STTM =
-tcgen05.ld / st, UTMALDG = TMA tensor load, UBLKCP / UBLKRED = bulk copy / bulk reduce, MUFU.EX2) from `cuobjdump -sass`, and
+tcgen05.ld / st, UTMALDG / UTMASTG = TMA tensor load / store, UBLKCP / UBLKRED = bulk copy / bulk reduce, MUFU.EX2) from `cuobjdump -sass`, and
 registers / spills / shared memory from the `-Xptxas -v` logs the build keeps next to the objects.
 
     python tools/sass_summary.py > profiles/sass_summary.txt
@@ -15,7 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "nsa_vibe_b200", "lib")
-MNEMONICS = ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "UBLKCP", "UBLKRED", "MUFU.EX2", "SYNCS")
+MNEMONICS = ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UBLKRED", "MUFU.EX2", "SYNCS")
 
 
 def demangle(names):
@@ -62,7 +62,7 @@ def main():
     info = ptxas_info()
     names = demangle(list(counts))
     print("# libnsa_b200.so -- per-kernel SASS mnemonic counts (cuobjdump -sass) and ptxas resources (-Xptxas -v)")
-    print("# UTCHMMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG = cp.async.bulk.tensor (TMA), UBLKCP/UBLKRED = bulk copy/reduce")
+    print("# UTCHMMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG = cp.async.bulk.tensor load/store (TMA), UBLKCP/UBLKRED = bulk copy/reduce")
     hdr = f"{'kernel':<78} {'instr':>6} " + " ".join(f"{k:>8}" for k in MNEMONICS) + f" {'regs':>5} {'spill_st':>8} {'spill_ld':>8}"
     print(hdr)
     for fn in sorted(counts, key=lambda f: names[f]):
