@@ -17,8 +17,7 @@
 namespace nsa {
 using namespace tc;
 
-constexpr int kDnKS = 3;             // K ring stages
-constexpr int kDnVS = 3;             // V ring stages
+constexpr int kDnMaxStages = 3;      // K / V ring stages (DnSmem::KS of them in use)
 constexpr int kDnTile = 128 * 128;   // bytes: 128 rows x 64 x 2 B
 constexpr int kDnMaxMT = 4;
 
@@ -26,19 +25,22 @@ constexpr int kDnMaxMT = 4;
 // (4 x 64 S columns + 4 x 64 O columns) -- is the default; (2, 128) is kept for comparison (NSA_B200_DENSE_MT=2).
 template <int MT, int NK>
 struct DnSmem {
+  static constexpr int KS = (MT == 2 && NK == 64) ? 2 : 3;  // K and V ring stages; the (2, 64) shape leaves room for a second CTA
+  static constexpr int tmem_cols = MT * (NK + 64) <= 256 ? 256 : 512;
+  static constexpr int ctas_per_sm = (MT == 2 && NK == 64) ? 2 : 1;
   static constexpr int kvtile = NK * 128;                   // bytes of one K or V tile
   static constexpr int ptile = 128 * NK * 2;                // bytes of one P tile: [NK/64 key halves][128 rows][128 B]
   static constexpr int q = 0;                               // MT x 16 KB
   static constexpr int k = q + MT * kDnTile;
-  static constexpr int v = k + kDnKS * kvtile;
-  static constexpr int p = v + kDnVS * kvtile;
+  static constexpr int v = k + KS * kvtile;
+  static constexpr int p = v + KS * kvtile;
   static constexpr int misc = p + MT * ptile;
   static constexpr int total = misc + 512 + 1024;
 };
 
 struct DnMisc {
   uint64_t q_full;
-  uint64_t k_full[kDnKS], k_empty[kDnKS], v_full[kDnVS], v_empty[kDnVS];
+  uint64_t k_full[kDnMaxStages], k_empty[kDnMaxStages], v_full[kDnMaxStages], v_empty[kDnMaxStages];
   uint64_t s_full[kDnMaxMT], s_empty[kDnMaxMT], p_full[kDnMaxMT], p_empty[kDnMaxMT];
   uint32_t tmem_base;
 };
@@ -95,11 +97,12 @@ __device__ __forceinline__ void dn_row_range(const nsa_dims_t& dm, int branch, i
 #endif
 
 template <typename T, int MT, int NK>
-__global__ void __launch_bounds__(32 * (4 * MT + 2), 1)
+__global__ void __launch_bounds__(32 * (4 * MT + 2), DnSmem<MT, NK>::ctas_per_sm)
 dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, nsa_dims_t dm, int branch, T* __restrict__ O,
                      float* __restrict__ lse, int TOK, long long* dbg) {
   using SM = DnSmem<MT, NK>;
+  constexpr int kDnKS = SM::KS, kDnVS = SM::KS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   DnMisc* ms = reinterpret_cast<DnMisc*>(smem + SM::misc);
@@ -140,7 +143,7 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
   }
-  if (warp == 0) tmem_alloc(&ms->tmem_base, 512);
+  if (warp == 0) tmem_alloc(&ms->tmem_base, SM::tmem_cols);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -390,7 +393,7 @@ dense_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (warp == 0) tmem_dealloc(tmem, SM::tmem_cols);
 }
 
 // ---- host ------------------------------------------------------------------------------------------------------
@@ -418,7 +421,7 @@ static int launch_dense_t(const nsa_dims_t& dm, int branch, const void* Q, const
   if (int rc = make_tmap_rows(&tmV, V, dm.dtype, 64, rows, 64, cap * 64, dm.B * dm.G, NK)) return rc;
   auto kern = dense_attn_tc_kernel<T, MT, NK>;
   static std::atomic<unsigned long long> attr_done{0};
-  if (int rc = ensure_smem_attr(kern, SM::total, attr_done, "dense tc")) return rc;
+  if (int rc = ensure_smem_attr(kern, SM::total, attr_done, "dense tc", SM::ctas_per_sm > 1)) return rc;
   const int grid = dm.B * dm.G * ceil_div(dm.S, MT * TOK);
   static const bool dbg_on = getenv("NSA_B200_DENSE_DBG") != nullptr;
   static long long* dbg_buf = nullptr;
@@ -447,6 +450,10 @@ static int launch_dense_mt(const nsa_dims_t& dm, int branch, const void* Q, cons
   static const int mt_env = getenv("NSA_B200_DENSE_MT") ? atoi(getenv("NSA_B200_DENSE_MT")) : 0;
   // 4 M-tiles per CTA once there are enough rows to fill the machine with 84-token CTAs
   const bool big = mt_env == 4 || (mt_env != 2 && (long long)dm.B * dm.G * dm.S >= 4LL * (128 / dm.h) * 148);
+  // the sliding branch walks only ~10 key tiles per CTA: with one CTA per SM its fill and drain (Q load, first K tile, epilogue) are
+  // not hidden by anything; the (2, 64) shape fits two CTAs per SM (half the TMEM, two ring stages) that overlap them
+  static const int win_env = getenv("NSA_B200_WIN_MT") ? atoi(getenv("NSA_B200_WIN_MT")) : 2;
+  if (big && branch == 2 && win_env == 2) return launch_dense_t<T, 2, 64>(dm, branch, Q, K, V, O, lse, stream);
   if (big) return launch_dense_t<T, 4, 64>(dm, branch, Q, K, V, O, lse, stream);
   return launch_dense_t<T, 2, 128>(dm, branch, Q, K, V, O, lse, stream);
 }

@@ -248,6 +248,29 @@ def test_score_tc_four_mtile_path(norm):
     _assert_only_near_ties(r, O.select_ranges_prefill(want, ls, n, S), want, got, ls, n)
 
 
+@pytest.mark.parametrize("norm", ["full_row", "causal"])
+@pytest.mark.parametrize("S", [1500, 4096 + 77])
+def test_score_tc_logits_growing_along_the_sequence(norm, S):
+    """Compressed keys that grow 40x / 400x along the sequence: later logits sit hundreds of log2 units above the first tiles', the
+    online maximum of pass 1 moves many times and nearly all probability mass is on a few keys.  Both scorer shapes (2 and 4
+    M-tiles per CTA) stay finite and match the fp32 oracle; the tolerance is the fp32 spacing of logits of that size (s*c ~ 500:
+    one ulp of the exponent argument is 3e-5, i.e. ~2e-5 relative on probabilities up to 2)."""
+    ops = _ops()
+    B, G, h, l, d, ls, n, w = 2, 2, 6, 32, 16, 64, 16, 512
+    gen = torch.Generator().manual_seed(S)
+    Q = torch.randn(B, S, G, h, 64, generator=gen).bfloat16().float()
+    Kc = torch.randn(B, G, O.num_cmp_blocks(S, l, d), 64, generator=gen)
+    Kc[:, :, 40:] *= 40.0
+    Kc[:, :, 70:] *= 10.0
+    Kc = Kc.bfloat16().float()
+    nm = ops.NORM_CAUSAL if norm == "causal" else ops.NORM_FULL_ROW
+    cfg = ops.NSAConfig(l=l, d=d, l_sel=ls, n_sel=n, w=w, impl=ops.IMPL_TC, norm_mode=nm)
+    want = O.prefill_scores(Q, Kc, l, d, ls, n, w, norm)
+    got = ops.score_pgrp(Q.cuda().bfloat16(), Kc.cuda().bfloat16(), cfg).cpu()
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max() <= 1e-4 * h, (got - want).abs().max()
+
+
 def test_dense_tc_reference_jump():
     """Later key tiles hold logits far above the first tile's maximum: the lazy softmax reference must move (rows redo the
     tile and rescale the accumulated O in TMEM) and still match the oracle."""
