@@ -374,6 +374,100 @@ decode_produce_kernel(DecodeProduceArgs a, int rows) {
   }
 }
 
+// The same producer with 16-byte accesses: a thread owns VE = 16 / sizeof(T) consecutive columns of the fused row (VE / 2 rotation
+// pairs, or a plain copy for the V and raw streams), so the address arithmetic, the load and the store of a token are shared by
+// 8 elements instead of 2.  ncu on the pair-per-thread kernel at 64k: 129 M warp instructions, 82 per pair and token, issue-active
+// 72 %, 167 us for 360 MB (profiles/r1_produce_ncu_raw.csv): instruction-bound at a third of the HBM rate.  Same arithmetic per
+// element, so the outputs are bit-identical (tests/test_producers_gpu.py).  Needs Dk, Dv multiples of VE and 16-byte aligned bases.
+constexpr int kProduceVecBatch = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(512)
+decode_produce_vec_kernel(DecodeProduceArgs a, int rows) {
+  constexpr int VE = 16 / (int)sizeof(T), NP = VE / 2;
+  const int QW = a.H * a.Dk;
+  const int N = QW + a.G * (3 * a.Dk + 3 * a.Dv);
+  const int vecs = N / VE;
+  int t_pos = a.t, ctr_idx = a.counters_idx, r_sel = 0, r_win = 0, r_raw = 0;
+  const bool stepped = a.state != nullptr;
+  if (stepped) {
+    t_pos = a.state->t; r_sel = t_pos; r_win = a.state->row_win; r_raw = a.state->row_raw; ctr_idx = a.state->ctr_idx;
+  }
+  if (a.counters && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x < 5 && ctr_idx < a.counters_cap) {
+    long long v = a.counter_val[threadIdx.x];
+    if (stepped) {  // nsa_attention.py:634-638 / kv_cache.py:51-65: (pred, total, sel, cmp, win)
+      const int S_raw = r_raw + 1;
+      const long long nc = S_raw < a.l ? 0 : (S_raw - a.l) / a.d + 1;
+      const long long nw = S_raw < a.w ? S_raw : a.w;
+      const long long ns = (long long)a.n_sel * a.l_sel;
+      v = threadIdx.x <= 1 ? nc + ns + nw : (threadIdx.x == 2 ? ns : (threadIdx.x == 3 ? nc : nw));
+    }
+    a.counters[(size_t)threadIdx.x * a.counters_cap + ctr_idx] = v;
+  }
+  const int vc = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.z;
+  if (vc >= vecs) return;
+  const int c = VE * vc;  // first column of y
+  T* other;
+  size_t other_pitch;
+  int rot_pair = -1, rot_dim = 0;
+  if (c < QW) {
+    other = reinterpret_cast<T*>(a.q_out) + (size_t)b * a.S * QW + c;
+    other_pitch = QW;
+    rot_pair = c / 2;
+    rot_dim = QW;
+  } else {
+    int off = c - QW, seg = 0;
+    for (; seg < 5; ++seg) {
+      const int wdt = a.G * ((seg & 1) ? a.Dv : a.Dk);
+      if (off < wdt) break;
+      off -= wdt;
+    }
+    const int D = (seg & 1) ? a.Dv : a.Dk;
+    const int g = off / D, e = off - g * D;
+    if (seg == 0 || seg == 2) {
+      rot_pair = e / 2;
+      rot_dim = D;
+    }
+    const int row_seg = stepped ? (seg < 2 ? r_sel : (seg < 4 ? r_win : r_raw)) : a.row[seg];
+    if (row_seg + a.S > a.cap[seg]) return;  // a stepped loop that outran its slabs writes nothing (the host re-plans before that)
+    other = reinterpret_cast<T*>(a.slab[seg]) + (((size_t)b * a.G + g) * a.cap[seg] + row_seg) * D + e;
+    other_pitch = D;
+  }
+  float inv_freq[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j)  // ATen's reciprocal-multiply form, see rope_shape_kernel
+    inv_freq[j] = rot_dim > 0 ? powf(a.base, __fmul_rn(__fmul_rn(-2.0f, (float)(rot_pair + j)), __fdiv_rn(1.0f, (float)rot_dim))) : 0.f;
+  const float inv_scale = __fdiv_rn(1.0f, a.scale);
+  T* yp = reinterpret_cast<T*>(const_cast<void*>(a.y)) + (size_t)b * a.S * N + c;
+  const int s0 = blockIdx.y * rows;
+  const int s1 = s0 + rows < a.S ? s0 + rows : a.S;
+  for (int sb = s0; sb < s1; sb += kProduceVecBatch) {
+    uint4 v[kProduceVecBatch];
+#pragma unroll
+    for (int u = 0; u < kProduceVecBatch; ++u)
+      if (sb + u < s1) v[u] = *reinterpret_cast<const uint4*>(a.inverse ? other + (size_t)(sb + u) * other_pitch : yp + (size_t)(sb + u) * N);
+#pragma unroll
+    for (int u = 0; u < kProduceVecBatch; ++u)
+      if (sb + u < s1) {
+        const int s = sb + u;
+        if (rot_dim > 0) {
+          T* el = reinterpret_cast<T*>(&v[u]);
+          const float pos = __fmul_rn((float)(t_pos + s), inv_scale);
+#pragma unroll
+          for (int j = 0; j < NP; ++j) {
+            float sn, cs, y0, y1;
+            sincosf(__fmul_rn(pos, inv_freq[j]), &sn, &cs);
+            rope_rotate<T>(PrT<T>::ld(el + 2 * j), PrT<T>::ld(el + 2 * j + 1), PrT<T>::rnd(sn), PrT<T>::rnd(cs), a.inverse != 0, y0, y1);
+            PrT<T>::st(el + 2 * j, y0);
+            PrT<T>::st(el + 2 * j + 1, y1);
+          }
+        }
+        *reinterpret_cast<uint4*>(a.inverse ? yp + (size_t)s * N : other + (size_t)s * other_pitch) = v[u];
+      }
+  }
+}
+
 int launch_decode_produce(const nsa_decode_produce_t& a, cudaStream_t stream) {
   const int dtype = a.dtype;
   NSA_REQUIRE(a.y && a.q_out, "produce: NULL pointer");
@@ -391,8 +485,26 @@ int launch_decode_produce(const nsa_decode_produce_t& a, cudaStream_t stream) {
   // rows per thread: amortise the powf over up to 16 tokens, but keep at least ~4 CTAs per SM in flight
   int rows = 16;
   while (rows > 1 && (long long)((pairs + 255) / 256) * ((a.S + rows - 1) / rows) * a.B < 4 * 148) rows /= 2;
+  NSA_REQUIRE(a.B <= 65535 && (a.S + rows - 1) / rows <= 65535, "produce: B=%d S=%d", a.B, a.S);
+  {  // 16-byte form when the geometry allows it
+    const int ve = dtype == NSA_F32 ? 4 : 8;
+    bool vec_ok = a.Dk % ve == 0 && a.Dv % ve == 0 && ((uintptr_t)a.y & 15) == 0 && ((uintptr_t)a.q_out & 15) == 0;
+    for (int i = 0; i < 6; ++i) vec_ok = vec_ok && ((uintptr_t)a.slab[i] & 15) == 0;
+    static const bool vec_env = !(getenv("NSA_B200_PRODUCE_VEC") && atoi(getenv("NSA_B200_PRODUCE_VEC")) == 0);
+    if (vec_ok && vec_env) {
+      const int vecs = 2 * pairs / ve;
+      const int bdx = vecs <= 512 ? ((vecs + 31) / 32) * 32 : 256;  // one CTA row per token row when the fused row fits (288 vectors at m7c)
+      int vrows = 16;
+      while (vrows > 1 && (long long)((vecs + bdx - 1) / bdx) * ((a.S + vrows - 1) / vrows) * a.B < 4 * 148) vrows /= 2;
+      const dim3 vgrid((vecs + bdx - 1) / bdx, (a.S + vrows - 1) / vrows, a.B);
+      NSA_REQUIRE(vgrid.y <= 65535, "produce: S=%d too long for one launch", a.S);
+      if (dtype == NSA_F32) decode_produce_vec_kernel<float><<<vgrid, bdx, 0, stream>>>(b, vrows);
+      else if (dtype == NSA_BF16) decode_produce_vec_kernel<__nv_bfloat16><<<vgrid, bdx, 0, stream>>>(b, vrows);
+      else decode_produce_vec_kernel<__half><<<vgrid, bdx, 0, stream>>>(b, vrows);
+      return check_launch("decode_produce_vec_kernel");
+    }
+  }
   const dim3 grid((pairs + 255) / 256, (a.S + rows - 1) / rows, a.B);
-  NSA_REQUIRE(a.B <= 65535 && grid.y <= 65535, "produce: B=%d S=%d", a.B, a.S);
   if (dtype == NSA_F32) decode_produce_kernel<float><<<grid, 256, 0, stream>>>(b, rows);
   else if (dtype == NSA_BF16) decode_produce_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(b, rows);
   else decode_produce_kernel<__half><<<grid, 256, 0, stream>>>(b, rows);
