@@ -291,7 +291,9 @@ sel2_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // boxes of a tile), which is the period of the whole CTA now that the Q buffers turn over fast enough.  Tried and measured
     // slower at 64k: 16-byte cp.async copies from this warp instead of boxes (~20 instructions per chunk on one warp, 1.19 ms
     // for the branch against 1.11), both engines side by side (the warp issues them one after the other: 1.22), a second
-    // producer warp (352 threads leave 80 registers: spills in the softmax warps, 1.20), one lane issuing all boxes (1.41).
+    // producer warp (352 threads leave 80 registers: spills in the softmax warps, 1.20), one lane issuing all boxes (1.41), the
+    // four epilogue warps issuing a quarter of every tile's boxes each (1.06 against 1.02: the limit is the TMA unit's box rate
+    // for the SM, ~55 cycles per box with two CTAs resident, not the issuing warp).
     if (lane == 0) {
       mbar_expect_tx(&ms->kv_full, 2 * 8192);
       tma_load_3d(smem + S2Smem::kv, &tmK, &ms->kv_full, 0, blk * 64, bg);
