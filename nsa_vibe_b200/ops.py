@@ -431,9 +431,17 @@ class _PrefillCore(torch.autograd.Function):
         dm = make_dims(Q, cfg, t0=t0, K_sel=K_sel, K_win=K_win, K_cmp=K_cmp, V=V_sel, n_ranges=ranges.shape[3], gate_hidden=hid,
                        **ctx.geom)
         f32 = dict(dtype=torch.float32, device=dev)
-        dQ = torch.zeros(Q.shape, **f32)
-        grads = [torch.zeros(t.shape, **f32) for t in (K_sel, V_sel, K_win, V_win, K_cmp, V_cmp)]
-        dgates = torch.zeros(gates.shape, **f32)
+        # ONE zero-filled fp32 buffer for the eight accumulators (segments padded to 64 elements: the kernels reduce into them with
+        # 16-byte bulk operations) and, below, ONE cast back to the tensors' dtype: 2 launches instead of 15 per layer and step
+        srcs = (Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp)
+        sizes = [(t.numel() + 63) // 64 * 64 for t in srcs]
+        flat = torch.zeros(sum(sizes) + gates.numel(), **f32)
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + n)
+        views = [flat[o:o + t.numel()].view(t.shape) for o, t in zip(offs, srcs)]
+        dQ, grads = views[0], views[1:]
+        dgates = flat[offs[-1]:].view(gates.shape)
         dOc = _c(dO.to(Q.dtype))
         ws = _workspace(dm, _lib.WS_BWD, dev)
         if Q.numel():
@@ -454,7 +462,11 @@ class _PrefillCore(torch.autograd.Function):
                       _ptr(d2w), _ptr(d2b), _stream())
             dparams = [d1w, d1b if gmask[1] else None, d2w, d2b if gmask[3] else None]
             dparams = [None if g is None else g.to(dt) for g, dt in zip(dparams, gdt)]
-        outs = [dQ.to(Q.dtype)] + [g.to(t.dtype) for g, t in zip(grads, (K_sel, V_sel, K_win, V_win, K_cmp, V_cmp))]
+        if all(t.dtype == Q.dtype for t in srcs):
+            low = flat[:offs[-1]].to(Q.dtype)
+            outs = [low[o:o + t.numel()].view(t.shape) for o, t in zip(offs, srcs)]
+        else:
+            outs = [v.to(t.dtype) for v, t in zip(views, srcs)]
         return (*outs, *dparams, None, None, None, None, None, None)
 
 
