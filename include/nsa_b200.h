@@ -256,8 +256,17 @@ typedef struct nsa_decode_produce {
    * device record instead of the fields above; l, d, l_sel, n_sel, w then give the counter formula (nsa_attention.py:634-638) */
   const nsa_decode_state_t* state;
   int32_t l, d, l_sel, n_sel, w;
+  /* optional rotation tables made by nsa_rope_table for positions [rope_t0, rope_t0 + rope_rows): rope_q [rows][H*Dk/2][2] (Q is
+   * rotated as one H*Dk-wide vector) and rope_k [rows][Dk/2][2], in the tensors' dtype, (sin, cos) per position and pair, rounded
+   * the way the kernel rounds them.  When both are given and cover [t, t + S) (and state is NULL) the kernel loads them instead
+   * of evaluating sincosf: bit-identical outputs, the rotation's ~70 instructions per pair become one 16-byte load per 4 pairs. */
+  const void *rope_q, *rope_k;
+  int32_t rope_t0, rope_rows;
 } nsa_decode_produce_t;
 int nsa_decode_produce(const nsa_decode_produce_t* a, void* stream);
+/* out [rows][pairs][2] in dtype: (sin, cos) of angle (t0 + row) / scale * base^(-2 * pair / rot_dim), computed and rounded exactly as
+ * the rotation kernels do (rope.py:14-33 through ATen's reciprocal-multiply forms). */
+int nsa_rope_table(int rows, int pairs, int rot_dim, int t0, float base, float scale, int dtype, void* out, void* stream);
 
 /* Emission of a decode step (nsa_attention.py:587-604): with S_raw = state->row_raw + 1 raw tokens present, if S_raw >= l and
  * (S_raw - l) % d == 0 the compressed token phi(raw rows [S_raw - l, S_raw)) (K with RoPE, compress_pool.py:9-38) is written to

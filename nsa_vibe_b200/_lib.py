@@ -42,7 +42,8 @@ class DecodeProduce(C.Structure):
                 ("counters", C.c_void_p), ("counters_cap", C.c_int32), ("counters_idx", C.c_int32), ("counter_val", C.c_int64 * 5),
                 ("B", C.c_int32), ("H", C.c_int32), ("G", C.c_int32), ("Dk", C.c_int32), ("Dv", C.c_int32), ("t", C.c_int32),
                 ("base", C.c_float), ("scale", C.c_float), ("dtype", C.c_int32), ("S", C.c_int32), ("inverse", C.c_int32),
-                ("state", C.c_void_p), ("l", C.c_int32), ("d", C.c_int32), ("l_sel", C.c_int32), ("n_sel", C.c_int32), ("w", C.c_int32)]
+                ("state", C.c_void_p), ("l", C.c_int32), ("d", C.c_int32), ("l_sel", C.c_int32), ("n_sel", C.c_int32), ("w", C.c_int32),
+                ("rope_q", C.c_void_p), ("rope_k", C.c_void_p), ("rope_t0", C.c_int32), ("rope_rows", C.c_int32)]
 
 
 class DecodeState(C.Structure):
@@ -100,6 +101,7 @@ SIGNATURES = {
     "nsa_phi_avgpool": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, C.c_float, C.c_float, _I, _I, _P]),
     "nsa_phi_conv": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, C.c_float, C.c_float, _I, _I, _P]),
     "nsa_decode_produce": (_I, [C.c_void_p, _P]),
+    "nsa_rope_table": (_I, [_I, _I, _I, _I, C.c_float, C.c_float, _I, _P, _P]),
     "nsa_decode_emit": (_I, [C.c_void_p, _P]),
     "nsa_decode_advance": (_I, [_P, _I, _I, _P]),
     "nsa_decode_stepped_supported": (_I, [_DP]),

@@ -458,6 +458,11 @@ int nsa_phi_conv(const void* x, const float* w, void* y, const void* dy, int BG,
   return launch_phi_avgpool(x, y, BG, S, D, l, d, rope, t0, base, scale, mode, dtype, (cudaStream_t)stream, w, dy);
 }
 
+int nsa_rope_table(int rows, int pairs, int rot_dim, int t0, float base, float scale, int dtype, void* out, void* stream) {
+  NSA_REQUIRE(dtype == NSA_F32 || dtype == NSA_BF16 || dtype == NSA_F16, "rope_table: dtype %d", dtype);
+  return launch_rope_table(rows, pairs, rot_dim, t0, base, scale, dtype, out, (cudaStream_t)stream);
+}
+
 int nsa_decode_produce(const nsa_decode_produce_t* a, void* stream) {
   NSA_REQUIRE(a, "decode_produce: NULL argument block");
   NSA_REQUIRE(a->dtype == NSA_F32 || a->dtype == NSA_BF16 || a->dtype == NSA_F16, "decode_produce: dtype %d", a->dtype);

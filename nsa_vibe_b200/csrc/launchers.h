@@ -50,6 +50,7 @@ int launch_rope_shape(const void* x, void* y, int B, int S, int V, int D, int sr
                       float base, float scale, int inverse, int dtype, cudaStream_t stream);
 int launch_phi_avgpool(const void* x, void* y, int BG, int S, int D, int l, int d, int rope, int t0, float base, float scale,
                        int backward, int dtype, cudaStream_t stream, const float* w = nullptr, const void* dy_for_dw = nullptr);
+int launch_rope_table(int rows, int pairs, int rot_dim, int t0, float base, float scale, int dtype, void* out, cudaStream_t stream);
 int launch_decode_produce(const nsa_decode_produce_t& a, cudaStream_t stream);
 int launch_decode_emit(const nsa_decode_emit_t& a, cudaStream_t stream);
 int launch_decode_advance(nsa_decode_state_t* state, int l, int d, cudaStream_t stream);

@@ -374,6 +374,35 @@ decode_produce_kernel(DecodeProduceArgs a, int rows) {
   }
 }
 
+// (sin, cos) tables for the producers: out[row][pair] = (rnd(sin a), rnd(cos a)), a = (t0 + row) / scale * base^(-2 pair / rot_dim),
+// the same expression and roundings as rope_sincos / decode_produce_kernel.
+template <typename T>
+__global__ void __launch_bounds__(256)
+rope_table_kernel(T* __restrict__ out, int rows, int pairs, int rot_dim, int t0, float base, float scale) {
+  const long long n = (long long)rows * pairs;
+  const float inv_scale = __fdiv_rn(1.0f, scale);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int pair = (int)(i % pairs);
+    const int row = (int)(i / pairs);
+    const float inv_freq = powf(base, __fmul_rn(__fmul_rn(-2.0f, (float)pair), __fdiv_rn(1.0f, (float)rot_dim)));
+    float sn, cs;
+    sincosf(__fmul_rn(__fmul_rn((float)(t0 + row), inv_scale), inv_freq), &sn, &cs);
+    PrT<T>::st2(out + 2 * i, PrT<T>::rnd(sn), PrT<T>::rnd(cs));
+  }
+}
+
+int launch_rope_table(int rows, int pairs, int rot_dim, int t0, float base, float scale, int dtype, void* out, cudaStream_t stream) {
+  NSA_REQUIRE(out && rows >= 0 && pairs >= 1 && rot_dim >= 2, "rope_table: rows=%d pairs=%d rot_dim=%d", rows, pairs, rot_dim);
+  const long long n = (long long)rows * pairs;
+  if (n == 0) return NSA_OK;
+  if (!(scale > 0.f)) scale = 1.0f;
+  const int blocks = pr_blocks(n);
+  if (dtype == NSA_F32) rope_table_kernel<float><<<blocks, 256, 0, stream>>>((float*)out, rows, pairs, rot_dim, t0, base, scale);
+  else if (dtype == NSA_BF16) rope_table_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((__nv_bfloat16*)out, rows, pairs, rot_dim, t0, base, scale);
+  else rope_table_kernel<__half><<<blocks, 256, 0, stream>>>((__half*)out, rows, pairs, rot_dim, t0, base, scale);
+  return check_launch("rope_table_kernel");
+}
+
 // The same producer with 16-byte accesses: a thread owns VE = 16 / sizeof(T) consecutive columns of the fused row (VE / 2 rotation
 // pairs, or a plain copy for the V and raw streams), so the address arithmetic, the load and the store of a token are shared by
 // 8 elements instead of 2.  ncu on the pair-per-thread kernel at 64k: 129 M warp instructions, 82 per pair and token, issue-active
@@ -434,33 +463,55 @@ decode_produce_vec_kernel(DecodeProduceArgs a, int rows) {
     other = reinterpret_cast<T*>(a.slab[seg]) + (((size_t)b * a.G + g) * a.cap[seg] + row_seg) * D + e;
     other_pitch = D;
   }
+  // rotation tables (nsa_rope_table), validated on the host: row (t_pos + s - rope_t0), this thread's NP pairs = 16 bytes
+  const T* tab = nullptr;
+  size_t tab_pitch = 0;
+  if (rot_dim > 0 && a.rope_q && a.rope_k && !stepped) {
+    tab_pitch = (size_t)rot_dim;  // rot_dim / 2 pairs x (sin, cos)
+    tab = reinterpret_cast<const T*>(c < QW ? a.rope_q : a.rope_k) + (size_t)(t_pos - a.rope_t0) * tab_pitch + 2 * rot_pair;
+  }
   float inv_freq[NP];
 #pragma unroll
   for (int j = 0; j < NP; ++j)  // ATen's reciprocal-multiply form, see rope_shape_kernel
-    inv_freq[j] = rot_dim > 0 ? powf(a.base, __fmul_rn(__fmul_rn(-2.0f, (float)(rot_pair + j)), __fdiv_rn(1.0f, (float)rot_dim))) : 0.f;
+    inv_freq[j] = (rot_dim > 0 && !tab) ? powf(a.base, __fmul_rn(__fmul_rn(-2.0f, (float)(rot_pair + j)), __fdiv_rn(1.0f, (float)rot_dim))) : 0.f;
   const float inv_scale = __fdiv_rn(1.0f, a.scale);
   T* yp = reinterpret_cast<T*>(const_cast<void*>(a.y)) + (size_t)b * a.S * N + c;
   const int s0 = blockIdx.y * rows;
   const int s1 = s0 + rows < a.S ? s0 + rows : a.S;
   for (int sb = s0; sb < s1; sb += kProduceVecBatch) {
-    uint4 v[kProduceVecBatch];
+    uint4 v[kProduceVecBatch], tv[kProduceVecBatch];
 #pragma unroll
     for (int u = 0; u < kProduceVecBatch; ++u)
-      if (sb + u < s1) v[u] = *reinterpret_cast<const uint4*>(a.inverse ? other + (size_t)(sb + u) * other_pitch : yp + (size_t)(sb + u) * N);
+      if (sb + u < s1) {
+        v[u] = *reinterpret_cast<const uint4*>(a.inverse ? other + (size_t)(sb + u) * other_pitch : yp + (size_t)(sb + u) * N);
+        if (tab) tv[u] = *reinterpret_cast<const uint4*>(tab + (size_t)(sb + u) * tab_pitch);
+      }
 #pragma unroll
     for (int u = 0; u < kProduceVecBatch; ++u)
       if (sb + u < s1) {
         const int s = sb + u;
         if (rot_dim > 0) {
           T* el = reinterpret_cast<T*>(&v[u]);
-          const float pos = __fmul_rn((float)(t_pos + s), inv_scale);
+          if (tab) {  // (sin, cos) of this thread's NP pairs at this position: one 16-byte load
+            const T* sc = reinterpret_cast<const T*>(&tv[u]);
 #pragma unroll
-          for (int j = 0; j < NP; ++j) {
-            float sn, cs, y0, y1;
-            sincosf(__fmul_rn(pos, inv_freq[j]), &sn, &cs);
-            rope_rotate<T>(PrT<T>::ld(el + 2 * j), PrT<T>::ld(el + 2 * j + 1), PrT<T>::rnd(sn), PrT<T>::rnd(cs), a.inverse != 0, y0, y1);
-            PrT<T>::st(el + 2 * j, y0);
-            PrT<T>::st(el + 2 * j + 1, y1);
+            for (int j = 0; j < NP; ++j) {
+              float y0, y1;
+              rope_rotate<T>(PrT<T>::ld(el + 2 * j), PrT<T>::ld(el + 2 * j + 1), PrT<T>::ld(sc + 2 * j), PrT<T>::ld(sc + 2 * j + 1),
+                             a.inverse != 0, y0, y1);
+              PrT<T>::st(el + 2 * j, y0);
+              PrT<T>::st(el + 2 * j + 1, y1);
+            }
+          } else {
+            const float pos = __fmul_rn((float)(t_pos + s), inv_scale);
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+              float sn, cs, y0, y1;
+              sincosf(__fmul_rn(pos, inv_freq[j]), &sn, &cs);
+              rope_rotate<T>(PrT<T>::ld(el + 2 * j), PrT<T>::ld(el + 2 * j + 1), PrT<T>::rnd(sn), PrT<T>::rnd(cs), a.inverse != 0, y0, y1);
+              PrT<T>::st(el + 2 * j, y0);
+              PrT<T>::st(el + 2 * j + 1, y1);
+            }
           }
         }
         *reinterpret_cast<uint4*>(a.inverse ? yp + (size_t)s * N : other + (size_t)s * other_pitch) = v[u];
@@ -481,6 +532,12 @@ int launch_decode_produce(const nsa_decode_produce_t& a, cudaStream_t stream) {
   if (a.B == 0) return NSA_OK;
   DecodeProduceArgs b = a;
   if (!(b.scale > 0.f)) b.scale = 1.0f;
+  // rotation tables only when both are there, aligned and cover [t, t + S); else the kernels evaluate sincosf
+  if (!(b.rope_q && b.rope_k && !b.state && b.t >= b.rope_t0 && (long long)b.t + b.S <= (long long)b.rope_t0 + b.rope_rows &&
+        ((uintptr_t)b.rope_q & 15) == 0 && ((uintptr_t)b.rope_k & 15) == 0)) {
+    b.rope_q = nullptr;
+    b.rope_k = nullptr;
+  }
   const int pairs = (a.H * a.Dk + a.G * (3 * a.Dk + 3 * a.Dv)) / 2;
   // rows per thread: amortise the powf over up to 16 tokens, but keep at least ~4 CTAs per SM in flight
   int rows = 16;

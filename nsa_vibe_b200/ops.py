@@ -6,6 +6,7 @@ fallback (BASELINE.json north_star).
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import math
 import os
@@ -312,13 +313,19 @@ class _BranchAttn(torch.autograd.Function):
         rg = rg if has_r else None
         dm = _branch_dims(branch, Q, K, V, cfg, rg, t0, win_off)
         ws = _workspace(dm, _lib.WS_BWD, Q.device)
-        dQ = torch.zeros(Q.shape, dtype=torch.float32, device=Q.device)
-        dK = torch.zeros(K.shape, dtype=torch.float32, device=Q.device)
-        dV = torch.zeros(V.shape, dtype=torch.float32, device=Q.device)
+        # one zero-filled fp32 buffer (segments padded to 64 elements), one cast back: see _PrefillCore.backward
+        srcs = (Q, K, V)
+        sizes = [(t.numel() + 63) // 64 * 64 for t in srcs]
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=Q.device)
+        offs = [0, sizes[0], sizes[0] + sizes[1]]
+        dQ, dK, dV = (flat[o:o + t.numel()].view(t.shape) for o, t in zip(offs, srcs))
         dOc = _c(dO.to(Q.dtype))
         if O.numel():
             _call("nsa_branch_attn_bwd", C.byref(dm), branch, _ptr(Q), _ptr(K), _ptr(V), _ptr(rg), _ptr(O), _ptr(lse),
                   _ptr(dOc), _ptr(dQ), _ptr(dK), _ptr(dV), _ptr(ws), _stream())
+        if K.dtype == Q.dtype and V.dtype == Q.dtype:
+            low = flat.to(Q.dtype)
+            return (*(low[o:o + t.numel()].view(t.shape) for o, t in zip(offs, srcs)), None, None, None, None, None)
         return dQ.to(Q.dtype), dK.to(K.dtype), dV.to(V.dtype), None, None, None, None, None
 
 
@@ -605,6 +612,38 @@ def phi_conv(K_raw: torch.Tensor, V_raw: torch.Tensor, w_k: torch.Tensor, w_v: t
             _PhiConv.apply(V_raw, w_v.reshape(V_raw.shape[-1], l), l, d, 0, t0, 1.0))
 
 
+_ROPE_TABLE_MIN_ROWS = int(os.environ.get("NSA_B200_ROPE_TABLE_MIN_ROWS", "256"))  # 0 or a huge value turns the tables off / on for all
+_rope_table_cache: "collections.OrderedDict" = collections.OrderedDict()
+
+
+def rope_tables(device, dtype, q_dim: int, k_dim: int, t0: int, rows: int, base: float, scale: float):
+    """(sin, cos) tables of the producers' rotations for positions [t0, t0 + rows): Q is rotated as one q_dim-wide vector, the K
+    streams per k_dim-vector (nsa_attention.py:1002-1009) -> ([rows, q_dim/2, 2], [rows, k_dim/2, 2]) in `dtype`, built by
+    nsa_rope_table with the producers' own arithmetic.  Position-only data, so the few most recent geometries are kept (a 64k table
+    is 108 MB in bf16); every layer and every step of a model shares them."""
+    key = (str(device), dtype, q_dim, k_dim, t0, rows, float(base), float(scale))
+    hit = _rope_table_cache.get(key)
+    if hit is not None:
+        if hit[2] is not None and not torch.cuda.is_current_stream_capturing():  # (event calls are not allowed while capturing)
+            hit[2].synchronize()  # built a moment ago, possibly on another stream: wait once, then the entry is plain data
+            hit = _rope_table_cache[key] = (hit[0], hit[1], None)
+        return hit[0], hit[1]
+    tq = torch.empty((rows, q_dim // 2, 2), dtype=dtype, device=device)
+    tk = torch.empty((rows, k_dim // 2, 2), dtype=dtype, device=device)
+    for tab, dim in ((tq, q_dim), (tk, k_dim)):
+        _call("nsa_rope_table", rows, dim // 2, dim, int(t0), float(base), float(scale), _DTYPES[dtype], _ptr(tab), _stream())
+    if torch.cuda.is_current_stream_capturing():
+        return tq, tk  # built inside the capture (its memory belongs to the graph's pool): not shared
+    ev = torch.cuda.Event()
+    ev.record()
+    _rope_table_cache[key] = (tq, tk, ev)
+    # captured graphs hold raw pointers into these tables, so entries leave only under real memory pressure (2 GB of tables)
+    while sum(t[0].numel() * t[0].element_size() + t[1].numel() * t[1].element_size() for t in _rope_table_cache.values()) > (2 << 30) \
+            and len(_rope_table_cache) > 1:
+        _rope_table_cache.popitem(last=False)
+    return tq, tk
+
+
 def decode_produce(y: torch.Tensor, q_out: torch.Tensor, slabs, rows, *, H: int, G: int, Dk: int, Dv: int, t: int,
                    base: float = 10000.0, scale: float = 1.0, counters: Optional[torch.Tensor] = None, counters_idx: int = 0,
                    counter_vals=(0, 0, 0, 0, 0), inverse: bool = False) -> None:
@@ -634,6 +673,9 @@ def decode_produce(y: torch.Tensor, q_out: torch.Tensor, slabs, rows, *, H: int,
     a.B, a.H, a.G, a.Dk, a.Dv, a.t = B, H, G, Dk, Dv, int(t)
     a.base, a.scale, a.dtype = float(base), float(scale if scale > 0 else 1.0), _DTYPES[y.dtype]
     a.S, a.inverse = int(S), int(bool(inverse))
+    if S >= _ROPE_TABLE_MIN_ROWS:  # long rows: the rotation's sin / cos come from a cached table instead of sincosf per element
+        tq, tk = rope_tables(y.device, y.dtype, H * Dk, Dk, int(t), int(S), a.base, a.scale)
+        a.rope_q, a.rope_k, a.rope_t0, a.rope_rows = tq.data_ptr(), tk.data_ptr(), int(t), int(S)
     if B * S:
         _call("nsa_decode_produce", C.byref(a), _stream())
 

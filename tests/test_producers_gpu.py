@@ -147,6 +147,49 @@ def test_project_split_matches_the_seven_chains_forward_and_backward(dtype, B, S
     assert torch.equal(ya.grad, yb.grad)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("t0,scale", [(0, 1.0), (1000, 2.0)])
+def test_project_split_with_rotation_tables_is_bit_identical(dtype, t0, scale, monkeypatch):
+    """Rows of 256 tokens and more take sin / cos from a cached table (nsa_rope_table) instead of sincosf per element: the table is
+    the producers' own arithmetic, so values and gradients equal the per-tensor rope_shape chains bit for bit, and the table itself
+    equals the torch expression of rope.py:14-33 rounded to the dtype."""
+    ops, _, _ = _mods()
+    B, S, H, G, Dk, Dv = 2, 700, 12, 2, 64, 64
+    assert S >= ops._ROPE_TABLE_MIN_ROWS
+    ops._rope_table_cache.clear()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    widths = [H * Dk] + [G * Dk, G * Dv] * 3
+    y = torch.randn(B, S, sum(widths), generator=g, device="cuda").to(dtype)
+    ya = y.clone().requires_grad_(True)
+    yb = y.clone().requires_grad_(True)
+    got = ops.project_split(ya, H=H, G=G, Dk=Dk, Dv=Dv, t0=t0, scale=scale)
+    assert len(ops._rope_table_cache) == 1, "the table path was not taken"
+    parts = torch.split(yb, widths, dim=-1)
+    want = [ops.rope_shape(parts[0].contiguous(), H, Dk, rope="token", t0=t0, scale=scale).view(B, S, G, H // G, Dk)]
+    for i in range(6):
+        D = Dv if i & 1 else Dk
+        want.append(ops.rope_shape(parts[1 + i].contiguous(), G, D, rope="vector" if i in (0, 2) else "none", to_cache_layout=True,
+                                   t0=t0, scale=scale))
+    loss_a = loss_b = 0.0
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and torch.equal(a, b)
+        dy = torch.randn(a.shape, generator=g, device="cuda").to(dtype)
+        loss_a = loss_a + (a.float() * dy.float()).sum()
+        loss_b = loss_b + (b.float() * dy.float()).sum()
+    loss_a.backward()
+    loss_b.backward()
+    assert torch.equal(ya.grad, yb.grad)
+    # the table against the reference's expression (fp32 angles; the device sin / cos may differ from torch's in the last bit)
+    tq, tk = ops.rope_tables(y.device, dtype, H * Dk, Dk, t0, S, 10000.0, scale)
+    pos = torch.arange(t0, t0 + S, device="cuda", dtype=torch.float32) / scale
+    for tab, dim in ((tq, H * Dk), (tk, Dk)):
+        inv = 10000.0 ** (-2.0 * torch.arange(dim // 2, device="cuda", dtype=torch.float32) / dim)
+        ang = pos[:, None] * inv[None, :]
+        tol = 2e-6 if dtype == torch.float32 else (8e-3 if dtype == torch.bfloat16 else 1e-3)
+        assert (tab[..., 0].float() - ang.sin()).abs().max() <= tol + 2e-3 * (t0 > 0)
+        assert (tab[..., 1].float() - ang.cos()).abs().max() <= tol + 2e-3 * (t0 > 0)
+
+
 def test_phi_mlp_conv_matches_reference_and_autograd():
     """Learnable phi (depthwise Conv1d, phi="mlp"): kernels vs the reference's own outputs (tests/golden/phi_mlp.npz), gradients
     of inputs and taps vs autograd through the oracle, and the module (prefill, eager decode and CUDA-graph decode emission)."""
