@@ -102,7 +102,7 @@ class NSA_KV:
         self._views[name] = v
         setattr(self, name, v)
 
-    def _append(self, name: str, x: torch.Tensor, window: Optional[int] = None) -> None:
+    def _append(self, name: str, x: torch.Tensor, window: Optional[int] = None, adopt: bool = False) -> None:
         cur: torch.Tensor = getattr(self, name)
         if cur.dtype != x.dtype or cur.device != x.device:  # zero-length placeholder of another dtype/device
             if cur.shape[2] != 0:
@@ -112,6 +112,17 @@ class NSA_KV:
         if window is not None:
             self._lens["__w_" + name] = int(window)
         s = x.shape[2]
+        if adopt and s > 0 and x.is_contiguous():
+            # prefill into an empty cache without reserved room: the caller's fresh tensor BECOMES the slab (no zero-filled
+            # allocation, no copy: 100 MB of device copies per 64k prefill).  It has no spare capacity, so the next append moves to a
+            # larger slab first and the adopted tensor is never written through the cache.
+            sync = self._in_sync(name)
+            n0 = self._lens[name] if sync else getattr(self, name).shape[2]
+            if n0 == 0 and not (sync and self._slabs[name].shape[2] >= s):
+                self._slabs[name] = x
+                self._lens[name] = s
+                self._set_view(name)
+                return
         self._ensure(name, s)
         n = self._lens[name]
         self._slabs[name][:, :, n:n + s] = x
@@ -136,13 +147,14 @@ class NSA_KV:
         return self._lens[name]
 
     # ---- the reference's update API ----------------------------------------------------------------
-    def update_selection_raw(self, K: torch.Tensor, V: torch.Tensor) -> None:
-        self._append("K_sel", K)
-        self._append("V_sel", V)
+    def update_selection_raw(self, K: torch.Tensor, V: torch.Tensor, adopt: bool = False) -> None:
+        """adopt=True: K / V are fresh tensors the caller will not write again (see _append)."""
+        self._append("K_sel", K, adopt=adopt)
+        self._append("V_sel", V, adopt=adopt)
 
-    def update_window(self, K: torch.Tensor, V: torch.Tensor, w: int) -> None:
-        self._append("K_win", K, window=w)  # view keeps the last w tokens (kv_cache.py:32-38)
-        self._append("V_win", V, window=w)
+    def update_window(self, K: torch.Tensor, V: torch.Tensor, w: int, adopt: bool = False) -> None:
+        self._append("K_win", K, window=w, adopt=adopt)  # view keeps the last w tokens (kv_cache.py:32-38)
+        self._append("V_win", V, window=w, adopt=adopt)
 
     def update_compressed(self, K_raw_cmp: torch.Tensor, V_raw_cmp: torch.Tensor, l: int, d: int) -> None:
         # prefill: replace with the freshly pooled sequence (kv_cache.py:40-45)
@@ -156,9 +168,9 @@ class NSA_KV:
         self._append("K_cmp", K_new)
         self._append("V_cmp", V_new)
 
-    def append_cmp_raw(self, K_raw_tok: torch.Tensor, V_raw_tok: torch.Tensor) -> None:
-        self._append("K_cmp_raw_seq", K_raw_tok)
-        self._append("V_cmp_raw_seq", V_raw_tok)
+    def append_cmp_raw(self, K_raw_tok: torch.Tensor, V_raw_tok: torch.Tensor, adopt: bool = False) -> None:
+        self._append("K_cmp_raw_seq", K_raw_tok, adopt=adopt)
+        self._append("V_cmp_raw_seq", V_raw_tok, adopt=adopt)
 
     # ---- in-place decode append (one kernel writes the six token rows, ops.decode_produce) --------------
     _TOKEN_FIELDS = ("K_sel", "V_sel", "K_win", "V_win", "K_cmp_raw_seq", "V_cmp_raw_seq")

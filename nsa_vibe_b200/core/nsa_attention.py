@@ -239,12 +239,13 @@ class NSAAttention(nn.Module):
         self._nvtx("projections+rope")
         Q, K_sel, V_sel, K_win, V_win, K_raw, V_raw = self._project(x, t0)
         self._nvtx(None)
-        kv.update_selection_raw(K_sel.detach(), V_sel.detach())
+        # the six streams are fresh outputs of the producer kernel: an empty cache adopts them as its slabs instead of copying
+        kv.update_selection_raw(K_sel.detach(), V_sel.detach(), adopt=True)
         kv.meta = build_block_meta(seq_len=t0 + S, l=self.l, d=self.d, l_sel=self.l_sel, n_sel=self.n_sel, w=self.w)
-        kv.update_window(K_win.detach(), V_win.detach(), self.w)
+        kv.update_window(K_win.detach(), V_win.detach(), self.w, adopt=True)
         # NOTE: unlike the reference (whose prefill never fills K_cmp_raw_seq, so a following decode restarts the
         # emission count at zero) the raw stream is recorded, keeping "emit every d after warm-up l" absolute.
-        kv.append_cmp_raw(K_raw.detach(), V_raw.detach())
+        kv.append_cmp_raw(K_raw.detach(), V_raw.detach(), adopt=True)
         if t0 == 0:
             K_cmp, V_cmp = self._phi(K_raw, V_raw)
         else:
