@@ -7,6 +7,9 @@
 
 #include "common.cuh"
 #include "select.cuh"
+#include <map>
+#include <mutex>
+#include <utility>
 #include "launchers.h"
 
 namespace nsa {
@@ -220,7 +223,12 @@ int nsa_gate_bwd(const nsa_dims_t* dm, const void* Q, const nsa_gate_params_t* g
 static int prefill_fwd_impl(const nsa_dims_t* dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
                             const void* V_win, const void* K_cmp, const void* V_cmp, const int32_t* ranges,
                             const nsa_gate_params_t* gp, void* O, float* lse, float* gates, void* O_branches, void* workspace,
-                            void* stream, int have_mask) {
+                            void* stream, int have_mask, cudaEvent_t join = nullptr) {
+  struct JoinGuard {  // the side stream's work (a precomputed branch) joins the caller's stream before anything reads it
+    cudaEvent_t ev; cudaStream_t st; bool done;
+    void now() { if (ev && !done) { cudaStreamWaitEvent(st, ev, 0); done = true; } }
+    ~JoinGuard() { now(); }
+  } join_guard{join, (cudaStream_t)stream, false};
   if (int rc = validate_dims(dm, "prefill_fwd")) return rc;
   NSA_REQUIRE(Q && O && ranges && gp, "prefill_fwd: NULL pointer");
   NSA_REQUIRE(dm->gate_mode != NSA_GATE_MLP || (gp->fc1_w && gp->fc2_w), "prefill_fwd: MLP weights missing");
@@ -266,6 +274,7 @@ static int prefill_fwd_impl(const nsa_dims_t* dm, const void* Q, const void* K_s
     }
     if (int rc = launch_branch_tc(*dm, br, Q, Ks[br], Vs[br], ranges, ob, lb, st)) return rc;
   }
+  join_guard.now();
   if (fuse) {
     Sel2Fuse f;
     f.gp = gp;
@@ -315,6 +324,23 @@ int nsa_score_cmp(const nsa_dims_t* dm, const void* Q, const void* K_cmp, const 
   return launch_score_cmp_tc(*dm, Q, K_cmp, V_cmp, S_sel, stats, p_grp, O_cmp, lse_cmp, (cudaStream_t)stream);
 }
 
+// A side stream per (device, caller stream) for work that may overlap the caller's chain inside one call (fork / join with
+// events, which is also how a capturing stream pulls a second stream into its graph).
+static cudaStream_t side_stream_for(cudaStream_t main) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, cudaStream_t> pool;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  auto key = std::make_pair(dev, main);
+  auto it = pool.find(key);
+  if (it != pool.end()) return it->second;
+  cudaStream_t s = nullptr;
+  if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  pool[key] = s;
+  return s;
+}
+
 static bool full_fused(const nsa_dims_t& dm) {
   return tc_eligible(dm) && tc_score_supported(dm) && tc_score_cmp_supported(dm) && tc_branch_supported(dm, 0) &&
          tc_branch_supported(dm, 1) && tc_branch_supported(dm, 2);
@@ -346,12 +372,48 @@ int nsa_prefill_full_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel,
   char* ws_pre = ws + ws_score + tc_score_cmp_stats_bytes(*dm);
   const size_t rows_h = (size_t)dm->B * dm->S * dm->G * dm->h;
   void* o_cmp = O_branches ? O_branches : (void*)ws_pre;  // staging slot 0 of prefill_fwd_impl
+  // The sliding branch depends on nothing the scorer or the selection produce: it runs on a side stream, forked here and joined
+  // before the combine, so the tails of its kernel and of the chain's first kernels fill each other.  Measured at 64k: step
+  // 3.27 -> 3.21 ms, module-level prefill 3.68 -> 3.60 ms (forking after the selection instead: no gain).  NSA_B200_WIN_SIDE=0
+  // keeps everything on the caller's stream.
+  static const int win_side_env = getenv("NSA_B200_WIN_SIDE") ? atoi(getenv("NSA_B200_WIN_SIDE")) : 1;
+  int have = 1;
+  cudaEvent_t ev_join = nullptr;
+  struct Joiner {  // whatever path leaves this function, the caller's stream has joined the side stream and the event is gone
+    cudaEvent_t& ev; cudaStream_t st;
+    ~Joiner() { if (ev) { cudaStreamWaitEvent(st, ev, 0); cudaEventDestroy(ev); ev = nullptr; } }
+  } joiner{ev_join, st};
+  auto fork_win = [&]() -> int {
+    cudaStream_t side = side_stream_for(st);
+    cudaEvent_t ev_fork = nullptr;
+    if (side && cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) == cudaSuccess) {
+      const size_t per_branch = rows_h * dm->Dv * elt_size(dm->dtype);
+      void* obr = O_branches ? O_branches : (void*)ws_pre;
+      cudaEventRecord(ev_fork, st);
+      cudaStreamWaitEvent(side, ev_fork, 0);
+      int rc = launch_branch_tc(*dm, 2, Q, K_win, V_win, nullptr, (char*)obr + 2 * per_branch, lse ? lse + 2 * rows_h : nullptr, side);
+      cudaEventRecord(ev_join, side);
+      cudaEventDestroy(ev_fork);
+      if (rc) return rc;
+      have |= 4;
+    } else {
+      if (ev_fork) cudaEventDestroy(ev_fork);
+      if (ev_join) cudaEventDestroy(ev_join);
+      ev_join = nullptr;
+    }
+    return NSA_OK;
+  };
+  // long prefill only: at the training shape (8 x 2048 tokens, the step replayed as one CUDA graph) the fork measured +1 % on the step
+  if (win_side_env == 1 && dm->S >= 8192)
+    if (int rc = fork_win()) return rc;
   if (int rc = launch_score_stats_tc(*dm, Q, K_cmp, stats, st)) return rc;
   if (int rc = launch_score_cmp_tc(*dm, Q, K_cmp, V_cmp, S_sel, stats, pg, o_cmp, lse, st)) return rc;
   (void)rows_h;
   const int nf = forced_code_default(sel_mode, S_total, dm->l_sel);
   if (int rc = launch_select(pg, dm->B * dm->S * dm->G, dm->S, dm->G, S_sel, dm->l_sel, dm->n_sel, sel_mode, nf, K, dm->t0, ranges, st)) return rc;
-  return prefill_fwd_impl(dm, Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, ranges, gp, O, lse, gates, O_branches, ws_pre, stream, 1);
+  return prefill_fwd_impl(dm, Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, ranges, gp, O, lse, gates, O_branches, ws_pre, stream, have,
+                          ev_join);
 }
 
 int nsa_prefill_bwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
