@@ -223,7 +223,7 @@ int nsa_gate_bwd(const nsa_dims_t* dm, const void* Q, const nsa_gate_params_t* g
 static int prefill_fwd_impl(const nsa_dims_t* dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
                             const void* V_win, const void* K_cmp, const void* V_cmp, const int32_t* ranges,
                             const nsa_gate_params_t* gp, void* O, float* lse, float* gates, void* O_branches, void* workspace,
-                            void* stream, int have_mask, cudaEvent_t join = nullptr) {
+                            void* stream, int have_mask, cudaEvent_t join = nullptr, const float* fuse_gates = nullptr) {
   struct JoinGuard {  // the side stream's work (a precomputed branch) joins the caller's stream before anything reads it
     cudaEvent_t ev; cudaStream_t st; bool done;
     void now() { if (ev && !done) { cudaStreamWaitEvent(st, ev, 0); done = true; } }
@@ -263,7 +263,9 @@ static int prefill_fwd_impl(const nsa_dims_t* dm, const void* Q, const void* K_s
   // gates never reach HBM (NSA_B200_FUSE_COMBINE=1).  Measured at 64k it is SLOWER than the two kernels it replaces (0.70 ms
   // against 0.405 + 0.136 ms: two dependent gather round trips per row plus the gate MLP at 16 warps per SM), so it is opt-in.
   static const bool fuse_env = getenv("NSA_B200_FUSE_COMBINE") && atoi(getenv("NSA_B200_FUSE_COMBINE")) == 1;
-  const bool fuse = fuse_env && tc_mask == 7 && !O_branches && !lse && workspace && use_sel2(*dm) && sel2_fuse_supported(*dm);
+  // fuse_gates: the gates were evaluated on the side stream (nsa_prefill_full_fwd): the merge of the selected branch's partials
+  // blends the three branches itself -- no O_sel round trip, no combine pass
+  const bool fuse = (fuse_env || fuse_gates) && tc_mask == 7 && !O_branches && !lse && workspace && use_sel2(*dm) && sel2_fuse_supported(*dm);
   for (int br = 0; br < 3; ++br) {
     if (!(tc_mask & (1 << br)) || (fuse && br == 1) || (have_mask & (1 << br))) continue;
     void* ob = (char*)obr + br * per_branch;
@@ -282,6 +284,7 @@ static int prefill_fwd_impl(const nsa_dims_t* dm, const void* Q, const void* K_s
     f.O_win = (char*)obr + 2 * per_branch;
     f.O = O;
     f.gates = gates;
+    f.gates_in = fuse_gates;
     return launch_sel2_tc(*dm, Q, K_sel, V_sel, ranges, nullptr, nullptr, (char*)workspace + staging, st, &f);
   }
   if (tc_mask != 7) {
@@ -341,6 +344,9 @@ static cudaStream_t side_stream_for(cudaStream_t main) {
   return s;
 }
 
+// workspace slot for the gates of the fused prefill when the caller passes no gates tensor
+static int64_t full_gate_bytes(const nsa_dims_t& dm) { return (((int64_t)dm.B * dm.S * dm.G * 3 * 4) + 255) & ~(int64_t)255; }
+
 static bool full_fused(const nsa_dims_t& dm) {
   return tc_eligible(dm) && tc_score_supported(dm) && tc_score_cmp_supported(dm) && tc_branch_supported(dm, 0) &&
          tc_branch_supported(dm, 1) && tc_branch_supported(dm, 2);
@@ -369,7 +375,7 @@ int nsa_prefill_full_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel,
   NSA_REQUIRE((int64_t)dm->B * dm->S * dm->G * S_sel * 4 <= tc_score_workspace(*dm), "prefill_full_fwd: S_sel=%d exceeds the workspace", S_sel);
   float* pg = reinterpret_cast<float*>(ws);
   float* stats = reinterpret_cast<float*>(ws + ws_score);
-  char* ws_pre = ws + ws_score + tc_score_cmp_stats_bytes(*dm);
+  char* ws_pre = ws + ws_score + tc_score_cmp_stats_bytes(*dm) + full_gate_bytes(*dm);
   const size_t rows_h = (size_t)dm->B * dm->S * dm->G * dm->h;
   void* o_cmp = O_branches ? O_branches : (void*)ws_pre;  // staging slot 0 of prefill_fwd_impl
   // The sliding branch depends on nothing the scorer or the selection produce: it runs on a side stream, forked here and joined
@@ -377,6 +383,12 @@ int nsa_prefill_full_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel,
   // 3.27 -> 3.21 ms, module-level prefill 3.68 -> 3.60 ms (forking after the selection instead: no gain).  NSA_B200_WIN_SIDE=0
   // keeps everything on the caller's stream.
   static const int win_side_env = getenv("NSA_B200_WIN_SIDE") ? atoi(getenv("NSA_B200_WIN_SIDE")) : 1;
+  // no-grad long prefill (nothing saved for a backward): the GateMLP runs on the side stream too and the selected branch's merge
+  // blends the three branches (sel2_merge_blend_kernel); gates go to the caller's tensor or to a workspace slot
+  static const bool gate_side_env = !(getenv("NSA_B200_GATE_SIDE") && atoi(getenv("NSA_B200_GATE_SIDE")) == 0);
+  float* gates_buf = gates ? gates : reinterpret_cast<float*>(ws + ws_score + tc_score_cmp_stats_bytes(*dm));
+  const bool gate_side = gate_side_env && !O_branches && !lse && gate_fast_supported(*dm, gp, Q) && use_sel2(*dm) && sel2_fuse_supported(*dm);
+  const float* fuse_gates = nullptr;
   int have = 1;
   cudaEvent_t ev_join = nullptr;
   struct Joiner {  // whatever path leaves this function, the caller's stream has joined the side stream and the event is gone
@@ -393,6 +405,10 @@ int nsa_prefill_full_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel,
       cudaEventRecord(ev_fork, st);
       cudaStreamWaitEvent(side, ev_fork, 0);
       int rc = launch_branch_tc(*dm, 2, Q, K_win, V_win, nullptr, (char*)obr + 2 * per_branch, lse ? lse + 2 * rows_h : nullptr, side);
+      if (!rc && gate_side) {
+        rc = launch_gate_fast(*dm, Q, *gp, gates_buf, side);
+        if (!rc) fuse_gates = gates_buf;
+      }
       cudaEventRecord(ev_join, side);
       cudaEventDestroy(ev_fork);
       if (rc) return rc;
@@ -413,7 +429,7 @@ int nsa_prefill_full_fwd(const nsa_dims_t* dm, const void* Q, const void* K_sel,
   const int nf = forced_code_default(sel_mode, S_total, dm->l_sel);
   if (int rc = launch_select(pg, dm->B * dm->S * dm->G, dm->S, dm->G, S_sel, dm->l_sel, dm->n_sel, sel_mode, nf, K, dm->t0, ranges, st)) return rc;
   return prefill_fwd_impl(dm, Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, ranges, gp, O, lse, gates, O_branches, ws_pre, stream, have,
-                          ev_join);
+                          ev_join, fuse_gates);
 }
 
 int nsa_prefill_bwd(const nsa_dims_t* dm, const void* Q, const void* K_sel, const void* V_sel, const void* K_win,
@@ -568,7 +584,7 @@ int64_t nsa_workspace_bytes(const nsa_dims_t* dm, int which) {
       return 0;
     }
     case NSA_WS_PREFILL_FULL:
-      return ((tc_score_workspace(*dm) + 255) & ~(int64_t)255) + (full_fused(*dm) ? tc_score_cmp_stats_bytes(*dm) : 0) +
+      return ((tc_score_workspace(*dm) + 255) & ~(int64_t)255) + (full_fused(*dm) ? tc_score_cmp_stats_bytes(*dm) + full_gate_bytes(*dm) : 0) +
              nsa_workspace_bytes(dm, NSA_WS_PREFILL);
     case NSA_WS_SEL_BLOCKMAJOR:
       return tc_sel2_workspace(*dm);

@@ -746,6 +746,105 @@ combine_fast_kernel(nsa_dims_t dm, const T* __restrict__ Q, nsa_gate_params_t gp
   }
 }
 
+// The gate half of combine_fast_kernel on its own (same statements, so the gates are bit-identical): q_gp by 16-byte-friendly
+// loads, weights in shared memory, one warp per row.  Used by the long no-grad prefill, where it runs on a side stream next to the
+// scorer and the merge of the selected branch's partials then blends the three branches itself (sel2_merge_blend_kernel).
+template <typename T>
+__global__ void __launch_bounds__(kCfWarps * 32, 4)
+gate_fast_kernel(nsa_dims_t dm, const T* __restrict__ Q, nsa_gate_params_t gp, float* __restrict__ gates) {
+  extern __shared__ float smem[];
+  const int Dk = dm.Dk, H = dm.gate_hidden, h = dm.h;
+  float* w1t = smem;                 // [Dk][H]
+  float* b1 = w1t + Dk * H;          // [H]
+  float* w2 = b1 + H;                // [3][H]
+  float* b2 = w2 + 3 * H;            // [4]
+  float* qg = b2 + 4;                // [warps][Dk]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < Dk * H; i += blockDim.x) w1t[(i % Dk) * H + i / Dk] = gp.fc1_w[i];
+  for (int i = threadIdx.x; i < H; i += blockDim.x) b1[i] = gp.fc1_b ? gp.fc1_b[i] : 0.f;
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) w2[i] = gp.fc2_w[i];
+  if (threadIdx.x < 3) b2[threadIdx.x] = gp.fc2_b ? gp.fc2_b[threadIdx.x] : 0.f;
+  __syncthreads();
+  float* qgp = qg + warp * Dk;
+  const int n_rows = dm.B * dm.S * dm.G;
+  const float inv_tau = 1.0f / fmaxf(dm.gate_tau, 1e-6f);
+  for (int row = blockIdx.x * kCfWarps + warp; row < n_rows; row += gridDim.x * kCfWarps) {
+    float g0, g1, g2;
+    const T* qrow = Q + (size_t)row * h * Dk;
+    for (int k = 2 * lane; k < Dk; k += 64) {
+      float m0 = 0.f, m1 = 0.f;
+      for (int h0 = 0; h0 < h; h0 += 8) {  // eight heads' loads in flight at a time
+        uint32_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = h0 + u < h ? *reinterpret_cast<const uint32_t*>(qrow + (h0 + u) * Dk + k) : 0u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {  // zero bits are +0.0 in both 16-bit formats
+          m0 += (float)reinterpret_cast<const T*>(&v[u])[0];
+          m1 += (float)reinterpret_cast<const T*>(&v[u])[1];
+        }
+      }
+      qgp[k] = m0 / (float)h;
+      qgp[k + 1] = m1 / (float)h;
+    }
+    __syncwarp();
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f;
+    for (int u = lane; u < H; u += 32) {
+      float a = b1[u];
+      int k = 0;
+      for (; k + 4 <= Dk; k += 4) {
+        const float4 qv = *reinterpret_cast<const float4*>(qgp + k);
+        a = fmaf(w1t[k * H + u], qv.x, a);
+        a = fmaf(w1t[(k + 1) * H + u], qv.y, a);
+        a = fmaf(w1t[(k + 2) * H + u], qv.z, a);
+        a = fmaf(w1t[(k + 3) * H + u], qv.w, a);
+      }
+      for (; k < Dk; ++k) a = fmaf(w1t[k * H + u], qgp[k], a);
+      const float x = a / (1.0f + expf(-a));  // silu
+      l0 = fmaf(w2[u], x, l0);
+      l1 = fmaf(w2[H + u], x, l1);
+      l2 = fmaf(w2[2 * H + u], x, l2);
+    }
+    l0 = (warp_sum(l0) + b2[0]) * inv_tau;
+    l1 = (warp_sum(l1) + b2[1]) * inv_tau;
+    l2 = (warp_sum(l2) + b2[2]) * inv_tau;
+    const float mx = fmaxf(l0, fmaxf(l1, l2));
+    const int am = l0 >= l1 ? (l0 >= l2 ? 0 : 2) : (l1 >= l2 ? 1 : 2);  // first maximum
+    const float second = am == 0 ? fmaxf(l1, l2) : (am == 1 ? fmaxf(l0, l2) : fmaxf(l0, l1));
+    if (mx - second > 50.0f) {  // hard one-hot (nsa_attention.py:74-81)
+      g0 = am == 0 ? 1.f : 0.f; g1 = am == 1 ? 1.f : 0.f; g2 = am == 2 ? 1.f : 0.f;
+    } else {
+      const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), e2 = expf(l2 - mx);
+      const float inv = 1.0f / (e0 + e1 + e2);
+      g0 = e0 * inv; g1 = e1 * inv; g2 = e2 * inv;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      gates[(size_t)row * 3] = g0;
+      gates[(size_t)row * 3 + 1] = g1;
+      gates[(size_t)row * 3 + 2] = g2;
+    }
+  }
+}
+
+bool gate_fast_supported(const nsa_dims_t& dm, const nsa_gate_params_t* gp, const void* Q) {
+  return gp && dm.gate_mode == NSA_GATE_MLP && gp->fc1_w && gp->fc2_w && dm.dtype != NSA_F32 && dm.Dk % 4 == 0 &&
+         ((size_t)dm.Dk * dm.gate_hidden + 4 * dm.gate_hidden + 4 + (size_t)kCfWarps * dm.Dk) * sizeof(float) <= 48 * 1024 &&
+         ((uintptr_t)Q & 3) == 0;
+}
+
+int launch_gate_fast(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t& gp, float* gates, cudaStream_t stream) {
+  const int n_rows = dm.B * dm.S * dm.G;
+  if (n_rows == 0) return NSA_OK;
+  NSA_REQUIRE(gate_fast_supported(dm, &gp, Q) && gates, "gate_fast: 16-bit GateMLP only");
+  const int H = dm.gate_hidden;
+  const size_t smem = ((size_t)dm.Dk * H + H + 3 * H + 4 + (size_t)kCfWarps * dm.Dk) * sizeof(float);
+  int blocks = ceil_div(n_rows, kCfWarps);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (dm.dtype == NSA_BF16) gate_fast_kernel<__nv_bfloat16><<<blocks, kCfWarps * 32, smem, stream>>>(dm, (const __nv_bfloat16*)Q, gp, gates);
+  else gate_fast_kernel<__half><<<blocks, kCfWarps * 32, smem, stream>>>(dm, (const __half*)Q, gp, gates);
+  return check_launch("gate_fast_kernel");
+}
+
 template <typename T>
 static int launch_combine_fast(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t& gp, const void* O_br, void* O,
                                float* gates, cudaStream_t stream) {

@@ -77,8 +77,11 @@ struct Sel2Fuse {
   const void *O_cmp, *O_win;
   void* O;
   float* gates;  // [rows,3] (may be NULL)
+  const float* gates_in = nullptr;  // gates already evaluated (launch_gate_fast, on a side stream): merge + blend only
 };
 bool sel2_fuse_supported(const nsa_dims_t& dm);
+bool gate_fast_supported(const nsa_dims_t& dm, const nsa_gate_params_t* gp, const void* Q);
+int launch_gate_fast(const nsa_dims_t& dm, const void* Q, const nsa_gate_params_t& gp, float* gates, cudaStream_t stream);
 int launch_sel2_tc(const nsa_dims_t& dm, const void* Q, const void* K, const void* V, const int32_t* ranges, void* O, float* lse,
                    void* workspace, cudaStream_t stream, const Sel2Fuse* fuse = nullptr);
 // tensor-core backward (tc_bwd.cu); falls back to launch_bwd_generic per branch when a shape has no tcgen05 kernel or

@@ -604,6 +604,77 @@ sel2_merge_kernel(int n_rows, int h, const int* __restrict__ pair_of, const T* _
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// 3a. merge + blend (long no-grad prefill): the merge kernel above with the other two branches' chunks and the row's gates (already
+//     evaluated, launch_gate_fast on a side stream) folded in: O[row] = g_cmp O_cmp + (g_sel / den) sum_k w_k O_k + g_win O_win.  The
+//     selected branch's output never reaches HBM and the separate combine pass (405 MB read + 88 MB written at 64k) disappears.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kS2MergeRows * 64, 2)
+sel2_merge_blend_kernel(int n_rows, int h, const int* __restrict__ pair_of, const T* __restrict__ O_p, const float* __restrict__ lse_p,
+                        const T* __restrict__ O_cmp, const T* __restrict__ O_win, const float* __restrict__ gates, T* __restrict__ O) {
+  const int chunks = h * 8;
+  const int rl = threadIdx.x / 64, cidx = threadIdx.x % 64;
+  if (cidx >= chunks) return;
+  const int head = cidx >> 3;
+  const int stride = gridDim.x * kS2MergeRows;
+  int4 nx[kS2MaxSlots / 4];
+  int row = blockIdx.x * kS2MergeRows + rl;
+  if (row < n_rows) {
+    const int4* pp = reinterpret_cast<const int4*>(pair_of + (size_t)row * kS2MaxSlots);
+#pragma unroll
+    for (int q = 0; q < kS2MaxSlots / 4; ++q) nx[q] = pp[q];
+  }
+  for (; row < n_rows; row += stride) {
+    int pk[kS2MaxSlots];
+#pragma unroll
+    for (int q = 0; q < kS2MaxSlots / 4; ++q) {
+      pk[4 * q] = nx[q].x; pk[4 * q + 1] = nx[q].y; pk[4 * q + 2] = nx[q].z; pk[4 * q + 3] = nx[q].w;
+    }
+    if (row + stride < n_rows) {
+      const int4* pp = reinterpret_cast<const int4*>(pair_of + (size_t)(row + stride) * kS2MaxSlots);
+#pragma unroll
+      for (int q = 0; q < kS2MaxSlots / 4; ++q) nx[q] = pp[q];
+    }
+    const size_t ro = (size_t)row * h * 64 + cidx * 8;
+    const uint4 oc = *reinterpret_cast<const uint4*>(O_cmp + ro);
+    const uint4 ow = *reinterpret_cast<const uint4*>(O_win + ro);
+    const float g0 = gates[(size_t)row * 3], g1 = gates[(size_t)row * 3 + 1], g2 = gates[(size_t)row * 3 + 2];
+    float ls[kS2MaxSlots];
+    uint4 v[kS2MaxSlots];
+#pragma unroll
+    for (int k = 0; k < kS2MaxSlots; ++k) {
+      const int p = pk[k];
+      ls[k] = p >= 0 ? lse_p[(size_t)p * h + head] : -INFINITY;
+      v[k] = p >= 0 ? *reinterpret_cast<const uint4*>(O_p + (size_t)p * h * 64 + cidx * 8) : make_uint4(0, 0, 0, 0);
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kS2MaxSlots; ++k) mx = fmaxf(mx, ls[k]);
+    float acc[8], den = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int k = 0; k < kS2MaxSlots; ++k) {
+      if (ls[k] > -INFINITY) {
+        const float w = __expf(ls[k] - mx);
+        den += w;
+        const T* pv = reinterpret_cast<const T*>(&v[k]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, (float)pv[e], acc[e]);
+      }
+    }
+    const float sc = den > 0.f ? g1 / den : 0.f;  // empty row -> the selected branch contributes zeros (attention_kernels.py:769-771)
+    const T* ec = reinterpret_cast<const T*>(&oc);
+    const T* ew = reinterpret_cast<const T*>(&ow);
+    uint4 o;
+    T* po = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) po[e] = T(g0 * (float)ec[e] + sc * acc[e] + g2 * (float)ew[e]);
+    *reinterpret_cast<uint4*>(O + ro) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // 3b. merge + gate + combine in one pass (no-grad prefill): O[row] = g_cmp O_cmp + g_sel merge_k(O_k, lse_k) + g_win O_win with the
 //     gates of GateMLP(mean_h Q[row]) (nsa_attention.py:32-82, :1356-1398) -- the selected branch's output and the gates never
 //     reach HBM, and the separate combine pass (405 MB read + 88 MB written at 64k) disappears.  64 threads per row (one per
@@ -918,6 +989,11 @@ static int launch_sel2_t(const nsa_dims_t& dm, const void* Q, const void* K, con
 #endif
   int mblocks = ceil_div(n_rows, kS2MergeRows);
   if (mblocks > 148 * 8) mblocks = 148 * 8;  // two resident CTAs per SM, several rows each: the slot-table prefetch needs a next row
+  if (fuse && fuse->gates_in) {  // gates already evaluated: merge + blend
+    sel2_merge_blend_kernel<T><<<mblocks, kS2MergeRows * 64, 0, stream>>>(n_rows, dm.h, pair_of, O_p, lse_p, (const T*)fuse->O_cmp,
+                                                                        (const T*)fuse->O_win, fuse->gates_in, (T*)fuse->O);
+    return check_launch("sel2_merge_blend_kernel");
+  }
   if (fuse) {  // no-grad prefill: merge + gate + combine in one pass, the selected branch's output never reaches HBM
     const int Hh = dm.gate_mode == NSA_GATE_MLP ? dm.gate_hidden : 0;
     const size_t smem = ((size_t)dm.Dk * Hh + Hh + 3 * Hh + 4 + (size_t)kS2MergeRows * 2 * dm.Dk) * sizeof(float);
