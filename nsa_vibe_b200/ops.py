@@ -394,7 +394,10 @@ class _PrefillCore(torch.autograd.Function):
         geom = dict(geom or {})
         gate = (fc1_w, fc1_b, fc2_w, fc2_b) if fc1_w is not None else None
         gp, keep, hid = _gate_struct(gate, dev)
-        need_grad = any(ctx.needs_input_grad[:11])
+        # needs_input_grad ignores torch.no_grad(): geom carries the caller's grad mode, so that inference neither allocates the
+        # per-branch outputs / lse (309 MB per 64k sequence) nor gives up the fused merge + blend
+        grad_mode = bool(geom.pop("__grad", True))
+        need_grad = grad_mode and any(ctx.needs_input_grad[:11])
         O = torch.empty((B, S, G, h, Dv), dtype=Q.dtype, device=dev)
         gates = torch.empty((B, S, G, 3), dtype=torch.float32, device=dev)
         lse = torch.empty((3, B, S, G, h), dtype=torch.float32, device=dev) if need_grad else None
@@ -493,6 +496,7 @@ def prefill_core(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, gate, cfg: NSAConf
     geom = {k: v for k, v in dict(S_sel_kv=S_sel_kv, S_win_kv=S_win_kv, S_cmp=S_cmp).items() if v is not None}
     if win_off:
         geom["win_off"] = win_off
+    geom["__grad"] = torch.is_grad_enabled()
     return _PrefillCore.apply(Q, K_sel, V_sel, K_win, V_win, K_cmp, V_cmp, g[0], g[1], g[2], g[3], cfg, sel_mode, t0,
                               stopgrad_gates, ranges, geom)
 
