@@ -158,6 +158,9 @@ int nsa_prefill_fwd(const nsa_dims_t* dm, const void* Q,
 /* Scoring + selection + nsa_prefill_fwd in one call: ranges [B,S,G,K,2] is an OUTPUT (K as for nsa_score_select), everything else
  * as nsa_prefill_fwd.  For long 16-bit prefill this is more than the two calls back to back: the scorer's second pass and the
  * compressed branch run as ONE kernel (one exponential per (row, compressed key) feeds both p_grp and O_cmp).
+ * For S >= 8192 the sliding branch and (when neither lse nor O_branches is requested) the GateMLP run on an internal side stream,
+ * forked from and joined into `stream` inside the call (capture-safe; NSA_B200_WIN_SIDE=0 disables), and the selected branch's
+ * merge then writes the gated output itself: O_sel and the gates' inputs never take an extra pass over HBM.
  * workspace: nsa_workspace_bytes(dm, NSA_WS_PREFILL_FULL).  Replaces nsa_attention.py:1066-1398. */
 int nsa_prefill_full_fwd(const nsa_dims_t* dm, const void* Q,
                          const void* K_sel, const void* V_sel, const void* K_win, const void* V_win,
