@@ -25,6 +25,23 @@ CASES = [
     ("test_selection_varlen_semantic.py", None, 1),     # true-softmax selection attention == SDPA over the ranges
     ("test_decode_counters.py", None, 1),               # read-counter formula
     ("test_decode_step.py", "emission_parity", 1),      # :226-278 decode emission == prefill phi (cache layout, emission schedule)
+    # second batch (end of round 2): every reference test file on the hot path that does not pin the literal first-key behaviour
+    # of the default SDPA routes or need fp64 kernels passes unchanged as well
+    ("test_masks.py", None, 1),                         # attention_kernels.py mask helpers
+    ("test_group_consistency_sel.py", None, 1),         # one selection per KV group
+    ("test_force_branch_gates.py", None, 3),            # NSA_FORCE_BRANCH one-hot gates through the module
+    ("test_selection_masked_empty_rows.py", None, 1),   # empty rows -> zeros (attention_kernels.py:769-771)
+    ("test_rope_dtype.py", None, 1),                    # rope.py dtype contract
+    ("test_long_context_needle.py", None, 2),           # needle retrieval through scoring + selection
+    ("test_long_context_smoke.py", None, 1),
+    ("test_phi_mlp_equiv.py", None, 2),                 # phi="mlp" (depthwise Conv1d compression)
+    ("test_selection_backward_reference.py", None, 1),  # selection_attention_backward_reference vs autograd
+    ("test_selection_backward_edges.py", None, 3),
+    ("test_decode_reads_trend.py", None, 1),            # read counters over a decode run
+    ("test_config_validation.py", None, 1),
+    ("test_pcmp_mixed_parity.py", None, 2),             # NSA_P_CMP_MIXED
+    ("test_equiv_ablation.py", None, 2),
+    ("test_sliding_sdpa_mask_nan.py", None, 11),        # sliding window rows without keys stay finite
 ]
 
 
